@@ -1,0 +1,411 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED
+reference (imported from /root/reference) on small seeded problems.
+
+TEST INFRASTRUCTURE.  Run in the build container only (the reference tree does
+not travel to the GPU box):
+
+    python oracle/make_golden.py
+
+Each fixture is an .npz of float64/int32 arrays: inputs, every intermediate the
+sweep produces (statistics, posterior parameters, sampled parameters,
+log-probabilities, uniforms, labels, responsibilities, lower bounds) and the
+raw random variates in the order the reference consumed them from the global
+legacy numpy.random stream, so the phases can be replayed one at a time by the
+oracle (tests/test_oracle_golden.py) and by the CUDA path (tests/test_gpu_*.py).
+While generating, every recorded sampled parameter is re-derived from the
+recorded variates through the oracle and asserted equal -- i.e. the generator
+also pins the oracle's sampling restatement.
+"""
+import os
+import sys
+
+import numpy as np
+import numpy.random as npr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference')
+
+import mimo.distributions as D          # noqa: E402
+import mimo.mixtures as M               # noqa: E402
+from oracle import mimo_oracle as orc   # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def spd(rng, d):
+    a = rng.standard_normal((d, d + 2))
+    return (a @ a.T) / d + 0.1 * np.eye(d)
+
+
+def blobs(rng, N, d, K, spread=4.0, full=True):
+    centres = spread * rng.standard_normal((K, d))
+    z = rng.integers(0, K, size=N)
+    x = np.empty((N, d))
+    for k in range(K):
+        idx = np.where(z == k)[0]
+        if full:
+            L = np.linalg.cholesky(spd(rng, d))
+            x[idx] = centres[k] + rng.standard_normal((idx.size, d)) @ L.T
+        else:
+            x[idx] = centres[k] + rng.standard_normal((idx.size, d)) * (0.5 + rng.random(d))
+    return x
+
+
+def close(a, b, tol=1e-9):
+    np.testing.assert_allclose(np.asarray(a, float), np.asarray(b, float), rtol=tol,
+                               atol=tol * max(1.0, float(np.max(np.abs(b)))))
+
+
+def draw_nw_variates(nus, d):
+    """Reference order per component: normal(d(d-1)/2), d x chisquare(nu - i),
+    normal(d)   (wishart.py:72-80, gaussian.py:311-313)."""
+    K = len(nus)
+    nt = d * (d - 1) // 2
+    normals, chisq, z = np.zeros((K, nt)), np.zeros((K, d)), np.zeros((K, d))
+    for k in range(K):
+        normals[k] = npr.normal(size=nt)
+        chisq[k] = [npr.chisquare(nus[k] - i, size=1)[0] for i in range(d)]
+        z[k] = npr.normal(size=d)
+    return normals, chisq, z
+
+
+def draw_mnw_variates(nus, o, c):
+    K = len(nus)
+    nt = o * (o - 1) // 2
+    normals, chisq, z = np.zeros((K, nt)), np.zeros((K, o)), np.zeros((K, o * c))
+    for k in range(K):
+        normals[k] = npr.normal(size=nt)
+        chisq[k] = [npr.chisquare(nus[k] - i, size=1)[0] for i in range(o)]
+        z[k] = npr.normal(size=o * c)
+    return normals, chisq, z
+
+
+def gating_kind(g):
+    return 'dirichlet' if isinstance(g, D.CategoricalWithDirichlet) else 'stick'
+
+
+def gating_prior_arrays(g):
+    if gating_kind(g) == 'dirichlet':
+        return dict(gate_alphas0=g.prior.alphas)
+    return dict(gate_gammas0=g.prior.gammas, gate_deltas0=g.prior.deltas)
+
+
+def resample_gating_recorded(g, labels, rec, t):
+    state = npr.get_state()
+    g.resample(labels)
+    npr.set_state(state)
+    if gating_kind(g) == 'dirichlet':
+        gam = npr.standard_gamma(g.posterior.alphas)   # consumes the same stream as npr.dirichlet
+        close(orc.dirichlet_probs_from_gammas(gam), g.likelihood.probs)
+        rec[f'gate_gamma_{t}'] = gam
+        rec[f'gate_alphas_{t}'] = g.posterior.alphas
+    else:
+        v = npr.beta(g.posterior.gammas[:-1], g.posterior.deltas[:-1])
+        close(orc.stick_probs_from_betas(v), g.likelihood.probs)
+        rec[f'gate_beta_{t}'] = v
+        rec[f'gate_gammas_{t}'] = g.posterior.gammas
+        rec[f'gate_deltas_{t}'] = g.posterior.deltas
+    rec[f'probs_{t}'] = g.likelihood.probs
+
+
+def gmm_gibbs_case(name, x, components, gating, sweeps, seed, diag=False):
+    """mixtures/gmm.py:207-225 replayed phase by phase."""
+    model = M.BayesianMixtureOfGaussians(gating=gating, components=components)
+    K, d = model.size, model.dim
+    rec = dict(obs=x, K=K, d=d, seed=seed, sweeps=sweeps)
+    rec.update(gating_prior_arrays(gating))
+    names = ('mus0', 'kappas0', 'alphas0', 'betas0') if diag else ('mus0', 'kappas0', 'psis0', 'nus0')
+    for n, p in zip(names, components.prior.params):
+        rec[n] = p
+    npr.seed(seed)
+    labels = npr.choice(K, size=len(x))
+    rec['labels_init'] = labels.astype(np.int32)
+    for t in range(sweeps):
+        # components
+        state = npr.get_state()
+        model.resample_components(x, labels)
+        npr.set_state(state)
+        post = components.posterior.params
+        if diag:
+            # per-dist reference update (composite.py:332-337); the stacked
+            # alphas/betas setters are broken so posterior.params
+            # keeps the PRIOR alphas/betas: record both.
+            w = orc.one_hot(labels, K)
+            nat = orc.add_stats(orc.ng_std_to_nat(*components.prior.params), orc.gauss_diag_wstats(x, w))
+            fixed = orc.ng_nat_to_std(nat)
+            for n, p in zip(('mus', 'kappas', 'alphas', 'betas'), fixed):
+                rec[f'post_{n}_{t}'] = p
+            rec[f'bug_alphas_{t}'], rec[f'bug_betas_{t}'] = post[2], post[3]
+            close(post[0], fixed[0]); close(post[1], fixed[1])
+            g = npr.gamma(post[2], 1.0 / post[3])   # one call per component in the reference,
+            # but element order is identical only if drawn per component: redo faithfully
+            npr.set_state(state)
+            gam, z = np.zeros((K, d)), np.zeros((K, d))
+            for k in range(K):
+                gam[k] = npr.gamma(post[2][k], 1.0 / post[3][k])
+                z[k] = npr.normal(size=d)
+            mu_s, l_s = orc.ng_rvs_from_variates(post[0], post[1], post[2], post[3], gam, z)
+            close(mu_s, components.likelihood.mus); close(l_s, components.likelihood.lmbdas_diags)
+            rec[f'var_gamma_{t}'], rec[f'var_z_{t}'] = gam, z
+            rec[f'lik_mus_{t}'] = components.likelihood.mus
+            rec[f'lik_lmbdas_diags_{t}'] = components.likelihood.lmbdas_diags
+        else:
+            for n, p in zip(('mus', 'kappas', 'psis', 'nus'), post):
+                rec[f'post_{n}_{t}'] = p
+            normals, chisq, z = draw_nw_variates(post[3], d)
+            for k in range(K):
+                mu_s, l_s = orc.nw_rvs_from_variates(post[0][k], post[1][k], post[2][k], post[3][k],
+                                                     normals[k], chisq[k], z[k])
+                close(mu_s, components.likelihood.mus[k]); close(l_s, components.likelihood.lmbdas[k])
+            rec[f'var_normals_{t}'], rec[f'var_chisq_{t}'], rec[f'var_z_{t}'] = normals, chisq, z
+            rec[f'lik_mus_{t}'] = components.likelihood.mus
+            rec[f'lik_lmbdas_{t}'] = components.likelihood.lmbdas
+        # gating
+        resample_gating_recorded(gating, labels, rec, t)
+        # labels
+        state = npr.get_state()
+        log_prob, labels = model.resample_labels(x)
+        npr.set_state(state)
+        u = npr.random(size=(1, len(x)))
+        assert np.array_equal(orc.sample_discrete_from_log(log_prob, u), labels)
+        rec[f'log_prob_{t}'] = log_prob
+        rec[f'u_{t}'] = u[0]
+        rec[f'labels_{t}'] = labels.astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'ok')
+
+
+def gmm_vi_case(name, x, components, gating, iters, seed, diag=False):
+    """mixtures/gmm.py:261-287: VI trajectory with the randomised start."""
+    model = M.BayesianMixtureOfGaussians(gating=gating, components=components)
+    K, d = model.size, model.dim
+    rec = dict(obs=x, K=K, d=d, seed=seed, iters=iters)
+    rec.update(gating_prior_arrays(gating))
+    names = ('mus0', 'kappas0', 'alphas0', 'betas0') if diag else ('mus0', 'kappas0', 'psis0', 'nus0')
+    for n, p in zip(names, components.prior.params):
+        rec[n] = p
+    npr.seed(seed)
+    resp = npr.rand(K, len(x))
+    resp /= np.sum(resp, axis=0)
+    rec['resp_init'] = resp
+    vlbs = []
+    for t in range(iters):
+        model.meanfield_update_parameters(x, resp)
+        resp = model.expected_responsibilities(x)
+        vlbs.append(model.variational_lowerbound(x, resp))
+        if not diag:
+            for n, p in zip(('mus', 'kappas', 'psis', 'nus'), components.posterior.params):
+                rec[f'post_{n}_{t}'] = p
+        else:
+            for n, p in zip(('mus', 'kappas'), components.posterior.params[:2]):
+                rec[f'post_{n}_{t}'] = p
+        if gating_kind(gating) == 'dirichlet':
+            rec[f'gate_alphas_{t}'] = gating.posterior.alphas
+        else:
+            rec[f'gate_gammas_{t}'] = gating.posterior.gammas
+            rec[f'gate_deltas_{t}'] = gating.posterior.deltas
+        rec[f'ell_{t}'] = model.expected_log_complete_likelihood(x)
+        rec[f'resp_{t}'] = resp
+    rec['vlb'] = np.array(vlbs)
+    rec['vlb_components'] = np.sum(components.variational_lowerbound())
+    rec['vlb_gating'] = gating.variational_lowerbound()
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'ok', 'vlb monotone:', bool(np.all(np.diff(vlbs) >= -1e-8)))
+
+
+def gmm_em_case(name, x, K, seed):
+    """mixtures/gmm.py:77-103 (EM) on full-covariance components."""
+    d = x.shape[1]
+    rng = np.random.default_rng(seed)
+    comp = D.StackedGaussiansWithPrecision(K, d, mus=rng.standard_normal((K, d)),
+                                           lmbdas=np.stack(K * [np.eye(d)]))
+    model = M.MixtureOfGaussians(gating=D.Categorical(K), components=comp)
+    npr.seed(seed)
+    resp = npr.rand(K, len(x))
+    resp /= np.sum(resp, axis=0)
+    npr.seed(seed)
+    ll = model.max_likelihood(x, maxiter=6, progress_bar=False)
+    rec = dict(obs=x, K=K, d=d, resp_init=resp, ll=np.array(ll), mus=comp.mus, lmbdas=comp.lmbdas,
+               probs=model.gating.probs, resp_final=model.responsibilities(x))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'ok', 'll monotone:', bool(np.all(np.diff(ll) >= -1e-8)))
+
+
+def ilr_models(K, din, o, tied, rng):
+    c = din + 1
+    basis_prior = D.StackedNormalWisharts(K, din, mus=np.zeros((K, din)), kappas=1e-2 * np.ones(K),
+                                          psis=np.stack(K * [1e2 * np.eye(din)]),
+                                          nus=(din + 1) * np.ones(K) + 1e-16)
+    basis = D.StackedGaussiansWithNormalWisharts(K, din, prior=basis_prior)
+    pcls = D.TiedMatrixNormalWisharts if tied else D.StackedMatrixNormalWisharts
+    mcls = D.TiedLinearGaussiansWithMatrixNormalWisharts if tied else D.StackedLinearGaussiansWithMatrixNormalWisharts
+    models_prior = pcls(K, c, o, Ms=np.zeros((K, o, c)), Ks=np.stack(K * [1e-2 * np.eye(c)]),
+                        psis=np.stack(K * [1e1 * np.eye(o)]), nus=(o + 1) * np.ones(K) + 1e-16)
+    models = mcls(K, c, o, models_prior, affine=True)
+    gating = D.CategoricalWithStickBreaking(K, D.TruncatedStickBreaking(K, np.ones(K), 5.0 * np.ones(K)))
+    return basis, models, gating
+
+
+def ilr_case(name, x, y, K, tied, seed, sweeps=2, iters=3):
+    """mixtures/ilr.py:134-159 (Gibbs) then :196-228 (VI, randomize=False) --
+    the order examples/ilr/evaluate_sine.py:124-147 uses."""
+    din, o = x.shape[1], y.shape[1]
+    c = din + 1
+    rng = np.random.default_rng(seed)
+    npr.seed(seed)
+    basis, models, gating = ilr_models(K, din, o, tied, rng)
+    ilr = M.BayesianMixtureOfLinearGaussians(K, din, o, gating=gating, basis=basis, models=models)
+    rec = dict(x=x, y=y, K=K, din=din, o=o, tied=int(tied), seed=seed, sweeps=sweeps, iters=iters)
+    for n, p in zip(('b_mus0', 'b_kappas0', 'b_psis0', 'b_nus0'), basis.prior.params):
+        rec[n] = p
+    for n, p in zip(('m_Ms0', 'm_Ks0', 'm_psis0', 'm_nus0'), models.prior.params):
+        rec[n] = p
+    rec.update(gating_prior_arrays(gating))
+    labels = npr.choice(K, size=len(x))
+    rec['labels_init'] = labels.astype(np.int32)
+    for t in range(sweeps):
+        state = npr.get_state()
+        ilr.resample_basis(x, labels)
+        npr.set_state(state)
+        bp = basis.posterior.params
+        normals, chisq, z = draw_nw_variates(bp[3], din)
+        for n, p in zip(('mus', 'kappas', 'psis', 'nus'), bp):
+            rec[f'b_post_{n}_{t}'] = p
+        rec[f'b_var_normals_{t}'], rec[f'b_var_chisq_{t}'], rec[f'b_var_z_{t}'] = normals, chisq, z
+        rec[f'b_lik_mus_{t}'], rec[f'b_lik_lmbdas_{t}'] = basis.likelihood.mus, basis.likelihood.lmbdas
+        state = npr.get_state()
+        ilr.resample_models(x, y, labels)
+        npr.set_state(state)
+        mp = models.posterior.params
+        normals, chisq, z = draw_mnw_variates(mp[3], o, c)
+        for k in range(K):
+            A_s, l_s = orc.mnw_rvs_from_variates(mp[0][k], mp[1][k], mp[2][k], mp[3][k], normals[k], chisq[k], z[k])
+            close(A_s, models.likelihood.As[k], 1e-8); close(l_s, models.likelihood.lmbdas[k], 1e-8)
+        for n, p in zip(('Ms', 'Ks', 'psis', 'nus'), mp):
+            rec[f'm_post_{n}_{t}'] = p
+        rec[f'm_var_normals_{t}'], rec[f'm_var_chisq_{t}'], rec[f'm_var_z_{t}'] = normals, chisq, z
+        rec[f'm_lik_As_{t}'], rec[f'm_lik_lmbdas_{t}'] = models.likelihood.As, models.likelihood.lmbdas
+        resample_gating_recorded(gating, labels, rec, t)
+        state = npr.get_state()
+        log_prob, labels = ilr.resample_labels(x, y)
+        npr.set_state(state)
+        u = npr.random(size=(1, len(x)))
+        assert np.array_equal(orc.sample_discrete_from_log(log_prob, u), labels)
+        rec[f'log_prob_{t}'], rec[f'u_{t}'], rec[f'labels_{t}'] = log_prob, u[0], labels.astype(np.int32)
+    # mean-field continuation from the Gibbs state (randomize=False)
+    resp = ilr.expected_responsibilities(x, y)
+    rec['vi_resp_init'] = resp
+    vlbs = []
+    for t in range(iters):
+        ilr.meanfield_update_parameters(x, y, resp)
+        resp = ilr.expected_responsibilities(x, y)
+        vlbs.append(ilr.variational_lowerbound(x, y, resp))
+        for n, p in zip(('mus', 'kappas', 'psis', 'nus'), basis.posterior.params):
+            rec[f'vi_b_post_{n}_{t}'] = p
+        for n, p in zip(('Ms', 'Ks', 'psis', 'nus'), models.posterior.params):
+            rec[f'vi_m_post_{n}_{t}'] = p
+        rec[f'vi_gate_gammas_{t}'], rec[f'vi_gate_deltas_{t}'] = gating.posterior.gammas, gating.posterior.deltas
+        rec[f'vi_ell_{t}'] = ilr.expected_log_complete_likelihood(x, y)
+        rec[f'vi_resp_{t}'] = resp
+    rec['vlb'] = np.array(vlbs)
+    mu, var, std = ilr.meanfield_prediction(x[:32], prediction='average')
+    rec['pred_mu'], rec['pred_var'] = mu, var
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'ok', 'vlb monotone:', bool(np.all(np.diff(vlbs) >= -1e-8)))
+
+
+def pointwise_case(name, K, d, N, seed):
+    """Per-point kernels at a cfg5-like shape (d=128): Gibbs log-lik and VI
+    expected log-lik of the full-covariance family + weighted statistics."""
+    rng = np.random.default_rng(seed)
+    x = blobs(rng, N, d, K, spread=2.0)
+    mus = 2.0 * rng.standard_normal((K, d))
+    lmbdas = np.stack([spd(rng, d) for _ in range(K)])
+    kappas = rng.random(K) + 0.5
+    psis = np.stack([spd(rng, d) / (d + 4.0) for _ in range(K)])
+    nus = d + 2.0 + 5 * rng.random(K)
+    lik = D.StackedGaussiansWithPrecision(K, d, mus=mus, lmbdas=lmbdas)
+    prior = D.StackedNormalWisharts(K, d, mus, kappas, psis, nus)
+    wrap = D.StackedGaussiansWithNormalWisharts(K, d, prior=prior, likelihood=lik)
+    w = rng.random((K, N))
+    w /= w.sum(0)
+    st = lik.weighted_statistics(x, w)
+    rec = dict(obs=x, mus=mus, lmbdas=lmbdas, kappas=kappas, psis=psis, nus=nus, weights=w,
+               log_lik=lik.log_likelihood(x.copy()), exp_log_lik=wrap.expected_log_likelihood(x),
+               st_x=st[0], st_n=st[1], st_xx=st[2])
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'ok')
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.default_rng(1337)
+
+    # cfg1: toy Bayesian GMM as shipped (examples/gmm/toy/gibbs_toy.py:41-59, vi_toy.py:41-59)
+    K, d = 4, 2
+    toy = blobs(rng, 500, d, K, spread=4.0)
+
+    def toy_model(gate='dirichlet', alpha=1.0):
+        prior = D.StackedNormalWisharts(K, d, mus=np.zeros((K, d)), kappas=1e-2 * np.ones(K),
+                                        psis=np.stack(K * [np.eye(d)]), nus=3.0 * np.ones(K) + 1e-8)
+        npr.seed(1)
+        comp = D.StackedGaussiansWithNormalWisharts(K, d, prior=prior)
+        if gate == 'dirichlet':
+            g = D.CategoricalWithDirichlet(K, D.Dirichlet(K, alpha * np.ones(K)))
+        else:
+            g = D.CategoricalWithStickBreaking(K, D.TruncatedStickBreaking(K, np.ones(K), 5.0 * np.ones(K)))
+        return comp, g
+
+    gmm_gibbs_case('gmm_toy_gibbs', toy, *toy_model(), sweeps=3, seed=1337)
+    gmm_vi_case('gmm_toy_vi', toy, *toy_model(), iters=6, seed=1337)
+    gmm_vi_case('gmm_toy_vi_stick', toy, *toy_model('stick'), iters=4, seed=7)
+    gmm_em_case('gmm_toy_em', toy, K, seed=3)
+
+    # cfg4-shaped: full covariance d=16, stick-breaking DP-GMM
+    K4, d4 = 8, 16
+    x4 = blobs(rng, 600, d4, K4, spread=3.0)
+    prior = D.StackedNormalWisharts(K4, d4, mus=np.zeros((K4, d4)), kappas=1e-2 * np.ones(K4),
+                                    psis=np.stack(K4 * [np.eye(d4)]), nus=(d4 + 1) * np.ones(K4) + 1e-8)
+    npr.seed(2)
+    comp = D.StackedGaussiansWithNormalWisharts(K4, d4, prior=prior)
+    g = D.CategoricalWithStickBreaking(K4, D.TruncatedStickBreaking(K4, np.ones(K4), 5.0 * np.ones(K4)))
+    gmm_vi_case('gmm_d16_vi_stick', x4, comp, g, iters=4, seed=11)
+    npr.seed(2)
+    comp = D.StackedGaussiansWithNormalWisharts(K4, d4, prior=prior)
+    g = D.CategoricalWithStickBreaking(K4, D.TruncatedStickBreaking(K4, np.ones(K4), 5.0 * np.ones(K4)))
+    gmm_gibbs_case('gmm_d16_gibbs_stick', x4, comp, g, sweeps=2, seed=12)
+
+    # cfg3-shaped: diagonal mixture (examples/dgmm/gibbs_dgmm.py:42-58)
+    K3, d3 = 6, 8
+    x3 = blobs(rng, 500, d3, K3, spread=4.0, full=False)
+
+    def diag_model():
+        prior = D.StackedNormalGammas(K3, d3, mus=np.zeros((K3, d3)), kappas=1e-2 * np.ones((K3, d3)),
+                                      alphas=(3.0 + 1e-8) / 2 * np.ones((K3, d3)), betas=0.5 * np.ones((K3, d3)))
+        npr.seed(3)
+        comp = D.StackedGaussiansWithNormalGammas(K3, d3, prior=prior)
+        return comp, D.CategoricalWithDirichlet(K3, D.Dirichlet(K3, np.ones(K3)))
+
+    gmm_gibbs_case('dgmm_gibbs', x3, *diag_model(), sweeps=2, seed=21, diag=True)
+    gmm_vi_case('dgmm_vi_bugcompat', x3, *diag_model(), iters=3, seed=22, diag=True)
+
+    # cfg2-shaped: ILR, stick-breaking, tied and stacked MNW (examples/ilr/evaluate_sine.py:88-127)
+    N2, din, o = 400, 2, 1
+    xi = rng.standard_normal((N2, din)) * 2.0
+    yi = np.sin(xi @ np.array([[1.0], [0.5]])) + 0.3 * rng.standard_normal((N2, o))
+    xi = (xi - xi.mean(0)) / xi.std(0)
+    yi = (yi - yi.mean(0)) / yi.std(0)
+    ilr_case('ilr_tied', xi, yi, K=6, tied=True, seed=31)
+    ilr_case('ilr_stacked', xi, yi, K=5, tied=False, seed=32)
+    y2 = np.hstack((yi, np.cos(xi[:, :1]) + 0.2 * rng.standard_normal((N2, 1))))
+    ilr_case('ilr_stacked_o2', xi, y2, K=4, tied=False, seed=33, sweeps=1, iters=2)
+
+    # cfg5-shaped per-point kernels at d=128 (N small: the reference's VI E-step is 8*K*N*d^2 bytes)
+    pointwise_case('pointwise_d128', K=5, d=128, N=48, seed=41)
+    pointwise_case('pointwise_d16', K=9, d=16, N=200, seed=42)
+
+
+if __name__ == '__main__':
+    main()

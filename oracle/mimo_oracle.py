@@ -1,0 +1,593 @@
+"""CPU oracle for the mimo mixture-inference sweep  --  TEST INFRASTRUCTURE ONLY.
+
+This module is a plain NumPy/SciPy (float64) restatement of the reference's
+algorithm for the sweep named in BASELINE.json.  It is the *checker* for the
+CUDA path: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import it.  Nothing under
+``mimo_b200/`` imports or calls it; the product path has no CPU fallback.
+
+Parity status: PINNED.  Every function below is checked against the unmodified
+reference (imported from /root/reference in the build container) by
+``tests/test_oracle_vs_reference.py`` and against the committed fixtures under
+``tests/golden/`` (made by ``oracle/make_golden.py``) by
+``tests/test_oracle_golden.py``.  The reference has no tests or golden vectors
+of its own, so "pinned" means "pinned by executing the
+reference on identical inputs".
+
+Each function cites the reference file:line it follows (paths relative to
+/root/reference/mimo).  The arithmetic follows the reference's contractions;
+where the reference materialises K*N*d*d tensors (distributions/gaussian.py:
+481-485) the same numbers are produced through an equivalent contraction that
+never builds that tensor, and point-axis chunking is available because every
+per-point quantity is independent across points and every statistic is a sum
+over points (the reference's own list-of-arrays semantics,
+distributions/gaussian.py:503-505).
+"""
+
+import numpy as np
+from scipy.special import digamma, gammaln, betaln, multigammaln, logsumexp
+from scipy.linalg import cholesky as sp_cholesky
+
+LOG_2PI = np.log(2.0 * np.pi)
+
+
+# ---------------------------------------------------------------------------
+# L0 utilities
+# ---------------------------------------------------------------------------
+
+def one_hot(z, K):
+    """utils/data.py:160-169 -- labels (N,) -> dense (K, N) float64 indicator."""
+    z = np.atleast_1d(z).astype(int)
+    if not (np.all(z >= 0) and np.all(z < K)):
+        raise AssertionError("labels out of range")
+    out = np.zeros((K, z.size))
+    out[z, np.arange(z.size)] = 1.0
+    return out
+
+
+def sample_discrete_from_log(p_log, u):
+    """utils/stats.py:8-21 with the uniform draw made explicit.
+
+    ``u`` is what ``npr.random(size=(1, N))`` returns at stats.py:14.
+    cdf is a sequential float64 cumsum over the component axis; the label is
+    the number of cdf entries strictly below u * cdf[-1].
+    """
+    lognorm = logsumexp(p_log, axis=0)
+    cdf = np.exp(p_log - lognorm[None, :]).cumsum(axis=0)
+    thresh = np.reshape(u, (1, -1)) * cdf[-1:, :]
+    return np.sum(thresh > cdf, axis=0, dtype=np.int32)
+
+
+def label_boundary_distance(p_log, u):
+    """min_k |u*cdf_K - cdf_k| per point: draws closer than 1e-6 to a CDF
+    boundary are excluded from bit-exact label comparisons (north_star)."""
+    lognorm = logsumexp(p_log, axis=0)
+    cdf = np.exp(p_log - lognorm[None, :]).cumsum(axis=0)
+    thresh = np.reshape(u, (1, -1)) * cdf[-1:, :]
+    return np.min(np.abs(thresh - cdf), axis=0)
+
+
+def responsibilities(log_joint):
+    """mixtures/gmm.py:72-75, 256-259 -- softmax over the component axis."""
+    lse = logsumexp(log_joint, axis=0, keepdims=True)
+    return np.exp(log_joint - lse), lse[0]
+
+
+# ---------------------------------------------------------------------------
+# L1a likelihoods: per-point log-likelihoods
+# ---------------------------------------------------------------------------
+
+def gauss_full_loglik(x, mus, lmbdas):
+    """distributions/gaussian.py:510-523 (+ log_partition :352-354, log_base
+    :69-74).  x (N,d), mus (K,d), lmbdas (K,d,d) -> (K,N)."""
+    d = x.shape[1]
+    lin = np.einsum('kd,kdl,nl->kn', mus, lmbdas, x, optimize=True)
+    quad = np.einsum('nd,kdl,nl->kn', x, lmbdas, x, optimize=True)
+    out = lin - 0.5 * quad
+    logpart = np.empty(mus.shape[0])
+    for k in range(mus.shape[0]):
+        U = sp_cholesky(lmbdas[k], lower=False)            # gaussian.py:298
+        logpart[k] = 0.5 * mus[k] @ lmbdas[k] @ mus[k] - np.sum(np.log(np.diag(U)))
+    return out - logpart[:, None] - 0.5 * d * LOG_2PI
+
+
+def gauss_diag_loglik(x, mus, lmbdas_diags):
+    """distributions/gaussian.py:837-850 (the reference builds dense diagonal
+    matrices; the numbers are the same)."""
+    d = x.shape[1]
+    lin = (mus * lmbdas_diags) @ x.T
+    quad = lmbdas_diags @ (x * x).T
+    logpart = 0.5 * np.sum(mus * lmbdas_diags * mus, axis=1) \
+        - np.sum(np.log(np.sqrt(lmbdas_diags)), axis=1)      # gaussian.py:679-681
+    return lin - 0.5 * quad - logpart[:, None] - 0.5 * d * LOG_2PI
+
+
+def _augment(x, affine):
+    """lingauss.py:312-313 -- append the constant-1 column when affine."""
+    return np.hstack((x, np.ones((x.shape[0], 1)))) if affine else x
+
+
+def lingauss_predict(x, As, affine=True):
+    """distributions/lingauss.py:251-257 -> (K,N,o)."""
+    return np.einsum('kdl,nl->knd', As, _augment(x, affine), optimize=True)
+
+
+def lingauss_loglik(x, y, As, lmbdas, affine=True):
+    """distributions/lingauss.py:330-347 (+ log_partition :166-169, 327-328)."""
+    o = y.shape[1]
+    mu = lingauss_predict(x, As, affine)                       # (K,N,o)
+    lin = np.einsum('knd,kdl,nl->kn', mu, lmbdas, y, optimize=True)
+    quad = np.einsum('nd,kdl,nl->kn', y, lmbdas, y, optimize=True)
+    out = lin - 0.5 * quad
+    for k in range(As.shape[0]):
+        U = sp_cholesky(lmbdas[k], lower=False)
+        logpart = 0.5 * np.einsum('nd,dl,nl->n', mu[k], lmbdas[k], mu[k]) \
+            - np.sum(np.log(np.diag(U)))
+        out[k] -= logpart
+    return out - 0.5 * o * LOG_2PI
+
+
+# ---------------------------------------------------------------------------
+# L1a likelihoods: weighted sufficient statistics (the all-reduced tensors)
+# ---------------------------------------------------------------------------
+
+def gauss_full_wstats(x, w):
+    """distributions/gaussian.py:491-505 -> [sum r x (K,d), sum r (K,),
+    sum r x x^T (K,d,d), sum r (K,)]."""
+    xk = np.einsum('kn,nd->kd', w, x, optimize=True)
+    xxk = np.einsum('nd,kn,nl->kdl', x, w, x, optimize=True)
+    nk = np.sum(w, axis=1)
+    return [xk, nk, xxk, nk]
+
+
+def gauss_diag_wstats(x, w):
+    """distributions/gaussian.py:819-832 -> [sum r x, n bcast, n bcast,
+    sum r x^2], all (K,d)."""
+    xk = np.einsum('kn,nd->kd', w, x)
+    xxk = np.einsum('nd,kn,nd->kd', x, w, x)
+    ndk = np.broadcast_to(np.sum(w, axis=1, keepdims=True), xk.shape).copy()
+    return [xk, ndk, ndk.copy(), xxk]
+
+
+def lingauss_wstats(x, y, w, affine=True):
+    """distributions/lingauss.py:306-325 -> [sum r y xt^T (K,o,c),
+    sum r xt xt^T (K,c,c), sum r y y^T (K,o,o), sum r (K,)]."""
+    xt = _augment(x, affine)
+    yx = np.einsum('nd,kn,nl->kdl', y, w, xt, optimize=True)
+    xx = np.einsum('nd,kn,nl->kdl', xt, w, xt, optimize=True)
+    yy = np.einsum('nd,kn,nl->kdl', y, w, y, optimize=True)
+    return [yx, xx, yy, np.sum(w, axis=1)]
+
+
+def categorical_wstats(w):
+    """distributions/categorical.py:41-46."""
+    return np.sum(np.atleast_2d(w), axis=1)
+
+
+def categorical_stats(labels, K):
+    """distributions/categorical.py:35-39."""
+    return np.bincount(labels, minlength=K)
+
+
+def add_stats(a, b):
+    """utils/abstraction.py:12-14."""
+    return [ai + bi for ai, bi in zip(a, b)]
+
+
+# ---------------------------------------------------------------------------
+# L1b Normal-Wishart (stacked: leading axis K)
+# ---------------------------------------------------------------------------
+
+def nw_std_to_nat(mus, kappas, psis, nus):
+    """distributions/composite.py:50-65 per component (stack :174-178)."""
+    d = mus.shape[1]
+    a = kappas[:, None] * mus
+    c = np.linalg.inv(psis) + kappas[:, None, None] * np.einsum('kd,kl->kdl', mus, mus)
+    return [a, kappas.copy(), c, nus - d]
+
+
+def nw_nat_to_std(nat, tied=False):
+    """composite.py:67-72 (stacked :180-184); tied :275-283."""
+    a, b, c, e = nat
+    d = a.shape[1]
+    mus = a / b[:, None]
+    inner = c - b[:, None, None] * np.einsum('kd,kl->kdl', mus, mus)
+    if tied:
+        psi = np.linalg.inv(np.mean(inner, axis=0))
+        nu = np.mean(e + d)
+        K = a.shape[0]
+        return mus, b.copy(), np.array(K * [psi]), np.array(K * [nu])
+    return mus, b.copy(), np.linalg.inv(inner), e + d
+
+
+def wishart_expected_logdet(psis, nus):
+    """distributions/wishart.py:139-143 / composite.py:115-116."""
+    d = psis.shape[-1]
+    out = np.empty(psis.shape[0])
+    for k in range(psis.shape[0]):
+        C = np.linalg.cholesky(psis[k])                      # wishart.py:59-62
+        out[k] = np.sum(digamma((nus[k] - np.arange(d)) / 2.0)) \
+            + d * np.log(2.0) + 2.0 * np.sum(np.log(np.diag(C)))
+    return out
+
+
+def nw_expected_statistics(mus, kappas, psis, nus):
+    """composite.py:106-118 (stacked :248-250)."""
+    d = mus.shape[1]
+    E_lm = nus[:, None] * np.einsum('kdl,kl->kd', psis, mus)
+    E_mlm = -0.5 * (d / kappas + np.einsum('kd,kd->k', mus, E_lm))
+    E_l = -0.5 * nus[:, None, None] * psis
+    E_logdet = 0.5 * wishart_expected_logdet(psis, nus)
+    return E_lm, E_mlm, E_l, E_logdet
+
+
+def nw_expected_loglik(x, mus, kappas, psis, nus):
+    """distributions/bayesian.py:287-301.  Same four terms; the per-point
+    statistics of gaussian.py:466-485 (x, 1, x x^T, 1 replicated K times) are
+    contracted on the fly instead of being materialised."""
+    d = x.shape[1]
+    E_lm, E_mlm, E_l, E_logdet = nw_expected_statistics(mus, kappas, psis, nus)
+    out = E_lm @ x.T
+    out += E_mlm[:, None]
+    out += np.einsum('kdl,nd,nl->kn', E_l, x, x, optimize=True)
+    out += E_logdet[:, None]
+    return out - 0.5 * d * LOG_2PI
+
+
+def wishart_log_partition(psis, nus):
+    """distributions/wishart.py:129-132."""
+    d = psis.shape[-1]
+    out = np.empty(psis.shape[0])
+    for k in range(psis.shape[0]):
+        C = np.linalg.cholesky(psis[k])
+        out[k] = 0.5 * nus[k] * d * np.log(2.0) + multigammaln(nus[k] / 2.0, d) \
+            + nus[k] * np.sum(np.log(np.diag(C)))
+    return out
+
+
+def nw_log_partition(mus, kappas, psis, nus):
+    """composite.py:95-98."""
+    d = mus.shape[1]
+    return -0.5 * d * np.log(kappas) + wishart_log_partition(psis, nus)
+
+
+def _nw_dot(nat, stats):
+    return np.einsum('kd,kd->k', nat[0], stats[0]) + nat[1] * stats[1] \
+        + np.einsum('kdl,kdl->k', nat[2], stats[2]) + nat[3] * stats[3]
+
+
+def nw_vlb(prior, post):
+    """bayesian.py:240-243 with composite.py:120-134: entropy(q) - cross_entropy(q, p),
+    per component.  prior/post are (mus, kappas, psis, nus) tuples.  The
+    log-base terms (composite.py:88-93) cancel between the two."""
+    stats = nw_expected_statistics(*post)
+    ent = nw_log_partition(*post) - _nw_dot(nw_std_to_nat(*post), stats)
+    xent = nw_log_partition(*prior) - _nw_dot(nw_std_to_nat(*prior), stats)
+    return ent - xent
+
+
+def nw_mode(mus, kappas, psis, nus):
+    """composite.py:77-80."""
+    d = mus.shape[1]
+    return mus.copy(), (nus - d)[:, None, None] * psis
+
+
+def wishart_rvs_from_variates(psi, normals, chisq):
+    """distributions/wishart.py:72-92 with the variates made explicit:
+    normals = npr.normal(size=d(d-1)/2) in np.tril_indices(d, -1) order,
+    chisq[i] = npr.chisquare(nu - i) (wishart.py:78-79)."""
+    d = psi.shape[0]
+    A = np.zeros((d, d))
+    A[np.tril_indices(d, k=-1)] = normals
+    A[np.diag_indices(d)] = np.sqrt(chisq)
+    T = np.linalg.cholesky(psi) @ A
+    return T @ T.T
+
+
+def nw_rvs_from_variates(mu, kappa, psi, nu, normals, chisq, z):
+    """composite.py:82-86 + gaussian.py:295-313: lmbda ~ W(psi, nu);
+    mu ~ N(m, (kappa lmbda)^-1) via the upper Cholesky factor of kappa*lmbda."""
+    lmbda = wishart_rvs_from_variates(psi, normals, chisq)
+    U = sp_cholesky(kappa * lmbda, lower=False)
+    return mu + np.linalg.inv(U) @ z, lmbda
+
+
+# ---------------------------------------------------------------------------
+# L1b Normal-Gamma (diagonal path)
+# ---------------------------------------------------------------------------
+
+def ng_std_to_nat(mus, kappas, alphas, betas):
+    """composite.py:313-329 (all (K,d))."""
+    return [kappas * mus, kappas.copy(), 2.0 * alphas - 1.0, 2.0 * betas + kappas * mus ** 2]
+
+
+def ng_nat_to_std(nat, tied=False):
+    """composite.py:331-337; tied :539-547."""
+    a, b, c, e = nat
+    mus = a / b
+    alphas = 0.5 * (c + 1.0)
+    betas = 0.5 * (e - b * mus ** 2)
+    if tied:
+        K = a.shape[0]
+        alphas = np.array(K * [np.mean(alphas, axis=0)])
+        betas = np.array(K * [np.mean(betas, axis=0)])
+    return mus, b.copy(), alphas, betas
+
+
+def ng_expected_statistics(mus, kappas, alphas, betas):
+    """composite.py:371-382."""
+    E_lm = alphas / betas * mus
+    E_lmm = -0.5 * (1.0 / kappas + mus * E_lm)
+    E_logl = 0.5 * (digamma(alphas) - np.log(betas))
+    E_l = -0.5 * (alphas / betas)
+    return E_lm, E_lmm, E_logl, E_l
+
+
+def ng_expected_loglik(x, mus, kappas, alphas, betas):
+    """bayesian.py:446-460 with the per-point stats of gaussian.py:794-813
+    (x, 1, 1, x^2)."""
+    d = x.shape[1]
+    E_lm, E_lmm, E_logl, E_l = ng_expected_statistics(mus, kappas, alphas, betas)
+    out = E_lm @ x.T + E_l @ (x * x).T
+    out += np.sum(E_lmm, axis=1)[:, None] + np.sum(E_logl, axis=1)[:, None]
+    return out - 0.5 * d * LOG_2PI
+
+
+def ng_log_partition(mus, kappas, alphas, betas):
+    """composite.py:360-363 + gamma.py:92-93."""
+    return -0.5 * np.sum(np.log(kappas), axis=1) \
+        + np.sum(gammaln(alphas) - alphas * np.log(betas), axis=1)
+
+
+def ng_vlb(prior, post):
+    """bayesian.py:401-404 with composite.py:384-398."""
+    stats = ng_expected_statistics(*post)
+
+    def dot(nat):
+        return sum(np.sum(n * s, axis=1) for n, s in zip(nat, stats))
+    ent = ng_log_partition(*post) - dot(ng_std_to_nat(*post))
+    xent = ng_log_partition(*prior) - dot(ng_std_to_nat(*prior))
+    return ent - xent
+
+
+def ng_mode(mus, kappas, alphas, betas):
+    """composite.py:342-345."""
+    return mus.copy(), (alphas - 0.5) / betas
+
+
+def ng_rvs_from_variates(mu, kappas, alphas, betas, g, z):
+    """composite.py:347-351: lmbda_diag = gamma draw (g = npr.gamma(alphas,
+    1/betas), gamma.py:54-56); mu ~ N(m, 1/(kappa lmbda)) (gaussian.py:644-646)."""
+    return mu + z / np.sqrt(kappas * g), g
+
+
+# ---------------------------------------------------------------------------
+# L1b Matrix-Normal-Wishart (linear-Gaussian experts)
+# ---------------------------------------------------------------------------
+
+def mnw_std_to_nat(Ms, Ks, psis, nus):
+    """composite.py:577-592."""
+    o, c = Ms.shape[1], Ms.shape[2]
+    a = np.einsum('kdl,klm->kdm', Ms, Ks)
+    cc = np.linalg.inv(psis) + np.einsum('kdl,klm,khm->kdh', Ms, Ks, Ms)
+    return [a, Ks.copy(), cc, nus - o - 1.0 + c]
+
+
+def mnw_nat_to_std(nat, tied=False):
+    """composite.py:594-599; tied :800-808."""
+    a, b, cc, e = nat
+    o, c = a.shape[1], a.shape[2]
+    Ms = np.einsum('kdl,klh->kdh', a, np.linalg.inv(b))
+    inner = cc - np.einsum('kdl,klm,khm->kdh', Ms, b, Ms)
+    if tied:
+        K = a.shape[0]
+        psi = np.linalg.inv(np.mean(inner, axis=0))
+        nu = np.mean(e + o + 1 - c)
+        return Ms, b.copy(), np.array(K * [psi]), np.array(K * [nu])
+    return Ms, b.copy(), np.linalg.inv(inner), e + o + 1.0 - c
+
+
+def mnw_expected_statistics(Ms, Ks, psis, nus):
+    """composite.py:635-647."""
+    o = Ms.shape[1]
+    E_LA = nus[:, None, None] * np.einsum('kdl,klm->kdm', psis, Ms)
+    E_ALA = -0.5 * (o * np.linalg.inv(Ks) + np.einsum('kdl,kdm->klm', Ms, E_LA))
+    E_L = -0.5 * nus[:, None, None] * psis
+    E_logdet = 0.5 * wishart_expected_logdet(psis, nus)
+    return E_LA, E_ALA, E_L, E_logdet
+
+
+def mnw_expected_loglik(x, y, Ms, Ks, psis, nus, affine=True):
+    """bayesian.py:933-947 with the per-point stats of lingauss.py:275-300
+    (y xt^T, xt xt^T, y y^T, 1) contracted on the fly."""
+    o = y.shape[1]
+    xt = _augment(x, affine)
+    E_LA, E_ALA, E_L, E_logdet = mnw_expected_statistics(Ms, Ks, psis, nus)
+    out = np.einsum('kdl,nd,nl->kn', E_LA, y, xt, optimize=True)
+    out += np.einsum('kdl,nd,nl->kn', E_ALA, xt, xt, optimize=True)
+    out += np.einsum('kdl,nd,nl->kn', E_L, y, y, optimize=True)
+    out += E_logdet[:, None]
+    return out - 0.5 * o * LOG_2PI
+
+
+def mnw_log_partition(Ms, Ks, psis, nus):
+    """composite.py:622-625."""
+    o = Ms.shape[1]
+    return -0.5 * o * np.linalg.slogdet(Ks)[1] + wishart_log_partition(psis, nus)
+
+
+def mnw_vlb(prior, post):
+    """bayesian.py:854-857 with composite.py:649-663."""
+    stats = mnw_expected_statistics(*post)
+
+    def dot(nat):
+        return np.einsum('kdl,kdl->k', nat[0], stats[0]) + np.einsum('kdl,kdl->k', nat[1], stats[1]) \
+            + np.einsum('kdl,kdl->k', nat[2], stats[2]) + nat[3] * stats[3]
+    ent = mnw_log_partition(*post) - dot(mnw_std_to_nat(*post))
+    xent = mnw_log_partition(*prior) - dot(mnw_std_to_nat(*prior))
+    return ent - xent
+
+
+def mnw_mode(Ms, Ks, psis, nus):
+    """composite.py:604-607."""
+    o = Ms.shape[1]
+    return Ms.copy(), (nus - o)[:, None, None] * psis
+
+
+def mnw_rvs_from_variates(M, K, psi, nu, normals, chisq, z):
+    """composite.py:609-613 + matrix.py:98-125: lmbda ~ W(psi, nu); A = M +
+    unvec_F(U^-1 z) with U the upper Cholesky factor of kron(K, lmbda)."""
+    o, c = M.shape
+    lmbda = wishart_rvs_from_variates(psi, normals, chisq)
+    U = sp_cholesky(np.kron(K, lmbda), lower=False)
+    aux = z @ np.linalg.inv(U).T
+    return M + np.reshape(aux, (o, c), order='F'), lmbda
+
+
+# ---------------------------------------------------------------------------
+# L1b gating: Dirichlet and truncated stick-breaking
+# ---------------------------------------------------------------------------
+
+def dirichlet_posterior(alphas0, counts):
+    """bayesian.py:70-72, 78-81 with dirichlet.py:30-38 (nat = alpha - 1)."""
+    return alphas0 + counts
+
+
+def dirichlet_expected_log(alphas):
+    """dirichlet.py:85-87."""
+    return digamma(alphas) - digamma(np.sum(alphas))
+
+
+def dirichlet_log_partition(alphas):
+    """dirichlet.py:78-79."""
+    return np.sum(gammaln(alphas)) - gammaln(np.sum(alphas))
+
+
+def dirichlet_vlb(alphas0, alphas):
+    """bayesian.py:93-96 with dirichlet.py:89-97."""
+    s = dirichlet_expected_log(alphas)
+    ent = dirichlet_log_partition(alphas) - (alphas - 1.0) @ s
+    xent = dirichlet_log_partition(alphas0) - (alphas0 - 1.0) @ s
+    return ent - xent
+
+
+def dirichlet_mode(alphas):
+    """dirichlet.py:43-45."""
+    if not np.all(alphas > 1.0):
+        raise AssertionError("Make sure alphas > 1.")
+    return (alphas - 1.0) / (np.sum(alphas) - alphas.size)
+
+
+def dirichlet_probs_from_gammas(g):
+    """npr.dirichlet (dirichlet.py:47-48) = normalised Gamma(alpha_k, 1)
+    draws; the Gibbs step clips to >= spacing(1) (bayesian.py:75)."""
+    return np.clip(g / np.sum(g), np.spacing(1.0), np.inf)
+
+
+def stick_posterior(gammas0, deltas0, counts):
+    """bayesian.py:140-146, 151-157: Blei & Jordan tail counts."""
+    acc = np.hstack((np.cumsum(counts[::-1])[-2::-1], 0))
+    return gammas0 + counts, deltas0 + acc
+
+
+def stick_expected_log(gammas, deltas):
+    """dirichlet.py:201-204 and the prefix sum of gmm.py:250-252."""
+    E_stick = digamma(gammas) - digamma(gammas + deltas)
+    E_rest = digamma(deltas) - digamma(gammas + deltas)
+    return E_stick + np.hstack((0, np.cumsum(E_rest)[:-1])), E_stick, E_rest
+
+
+def stick_vlb(prior, post):
+    """bayesian.py:173-176 with dirichlet.py:195-214."""
+    g, dl = post
+    g0, d0 = prior
+    _, E_stick, E_rest = stick_expected_log(g, dl)
+    ent = np.sum(betaln(g, dl)) - ((g - 1.0) @ E_stick + (dl - 1.0) @ E_rest)
+    xent = np.sum(betaln(g0, d0)) - ((g0 - 1.0) @ E_stick + (d0 - 1.0) @ E_rest)
+    return ent - xent
+
+
+def stick_probs_from_betas(v):
+    """dirichlet.py:177-186: v = npr.beta(gammas[:-1], deltas[:-1])."""
+    v = np.hstack((v, 1.0))
+    probs = np.empty(v.size)
+    probs[0] = v[0]
+    probs[1:] = v[1:] * np.cumprod(1.0 - v[:-1])
+    return probs
+
+
+def stick_mean(gammas, deltas):
+    """dirichlet.py:141-150."""
+    return stick_probs_from_betas(gammas[:-1] / (gammas[:-1] + deltas[:-1]))
+
+
+# ---------------------------------------------------------------------------
+# EM M-steps
+# ---------------------------------------------------------------------------
+
+def gauss_full_mstep(stats):
+    """gaussian.py:525-542."""
+    xk, nk, xxk, _ = stats
+    K, d = xk.shape
+    mus = xk / nk[:, None]
+    lmbdas = np.empty((K, d, d))
+    for k in range(K):
+        sigma = xxk[k] / nk[k] - np.outer(mus[k], mus[k])
+        sigma = 0.5 * (sigma + sigma.T) + 1e-16 * np.eye(d)
+        if not np.all(np.linalg.eigvalsh(sigma) > 0.0):
+            raise AssertionError("covariance not positive definite")
+        lmbdas[k] = np.linalg.inv(sigma)
+    return mus, lmbdas
+
+
+def gauss_diag_mstep(stats):
+    """gaussian.py:852-862."""
+    xk, ndk, _, xxk = stats
+    mus = xk / ndk
+    return mus, 1.0 / (xxk / ndk - mus ** 2 + 1e-16)
+
+
+def lingauss_mstep(stats):
+    """lingauss.py:350-367."""
+    yx, xx, yy, nk = stats
+    K, o, c = yx.shape
+    As = np.empty((K, o, c))
+    lmbdas = np.empty((K, o, o))
+    for k in range(K):
+        As[k] = np.linalg.solve(xx[k], yx[k].T).T
+        sigma = (yy[k] - As[k] @ yx[k].T) / nk[k]
+        sigma = 0.5 * (sigma + sigma.T) + 1e-16 * np.eye(o)
+        if not np.all(np.linalg.eigvalsh(sigma) > 0.0):
+            raise AssertionError("covariance not positive definite")
+        lmbdas[k] = np.linalg.inv(sigma)
+    return As, lmbdas
+
+
+def categorical_mstep(counts):
+    """categorical.py:65-68."""
+    return counts / counts.sum()
+
+
+# ---------------------------------------------------------------------------
+# L3 sweep pieces (mixtures/gmm.py, mixtures/ilr.py)
+# ---------------------------------------------------------------------------
+
+def vlb_labels_dirichlet(resp, E_log_pi):
+    """gmm.py:341-344, 352-356."""
+    with np.errstate(invalid='ignore', divide='ignore'):
+        return np.sum(resp * E_log_pi[:, None]) - np.nansum(resp * np.log(resp))
+
+
+def vlb_labels_stick(resp, E_stick, E_rest):
+    """gmm.py:345-356."""
+    acc = np.vstack((np.cumsum(resp[::-1, :], axis=0)[-2::-1, :], np.zeros((1, resp.shape[1]))))
+    with np.errstate(invalid='ignore', divide='ignore'):
+        return np.sum(resp * E_stick[:, None] + acc * E_rest[:, None]) - np.nansum(resp * np.log(resp))
+
+
+def chunked(fn, n, chunk):
+    """Apply fn(slice) over point chunks and concatenate along the point axis
+    (axis 1 for (K,N) outputs).  Exact: every per-point quantity is
+    independent across points."""
+    outs = [fn(slice(s, min(s + chunk, n))) for s in range(0, n, chunk)]
+    return np.concatenate(outs, axis=1)

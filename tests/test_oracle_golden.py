@@ -1,0 +1,191 @@
+"""Oracle vs the committed golden fixtures (made from the unmodified reference
+by oracle/make_golden.py).  CPU only; runs everywhere."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mimo_oracle as orc
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLD, name + '.npz')))
+
+
+def close(a, b, tol=1e-9):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert a.shape == b.shape
+    np.testing.assert_allclose(a, b, rtol=tol, atol=tol * max(1.0, float(np.max(np.abs(b)))))
+
+
+def gate_logw_vi(g, t, prefix=''):
+    if f'{prefix}gate_alphas_{t}' in g:
+        return orc.dirichlet_expected_log(g[f'{prefix}gate_alphas_{t}'])
+    return orc.stick_expected_log(g[f'{prefix}gate_gammas_{t}'], g[f'{prefix}gate_deltas_{t}'])[0]
+
+
+@pytest.mark.parametrize('name', ['gmm_toy_gibbs', 'gmm_d16_gibbs_stick'])
+def test_gmm_gibbs_phases(name):
+    g = load(name)
+    x, K = g['obs'], int(g['K'])
+    prior = (g['mus0'], g['kappas0'], g['psis0'], g['nus0'])
+    labels = g['labels_init']
+    for t in range(int(g['sweeps'])):
+        w = orc.one_hot(labels, K)
+        post = orc.nw_nat_to_std(orc.add_stats(orc.nw_std_to_nat(*prior), orc.gauss_full_wstats(x, w)))
+        for a, n in zip(post, ('mus', 'kappas', 'psis', 'nus')):
+            close(a, g[f'post_{n}_{t}'])
+        counts = orc.categorical_stats(labels, K)
+        if 'gate_alphas0' in g:
+            close(orc.dirichlet_posterior(g['gate_alphas0'], counts), g[f'gate_alphas_{t}'])
+            close(orc.dirichlet_probs_from_gammas(g[f'gate_gamma_{t}']), g[f'probs_{t}'])
+        else:
+            gp, dp = orc.stick_posterior(g['gate_gammas0'], g['gate_deltas0'], counts)
+            close(gp, g[f'gate_gammas_{t}'])
+            close(dp, g[f'gate_deltas_{t}'])
+            close(orc.stick_probs_from_betas(g[f'gate_beta_{t}']), g[f'probs_{t}'])
+        lp = orc.gauss_full_loglik(x, g[f'lik_mus_{t}'], g[f'lik_lmbdas_{t}']) + np.log(g[f'probs_{t}'])[:, None]
+        close(lp, g[f'log_prob_{t}'])
+        labels = orc.sample_discrete_from_log(g[f'log_prob_{t}'], g[f'u_{t}'])
+        assert np.array_equal(labels, g[f'labels_{t}'])
+
+
+@pytest.mark.parametrize('name', ['gmm_toy_vi', 'gmm_toy_vi_stick', 'gmm_d16_vi_stick'])
+def test_gmm_vi_trajectory(name):
+    g = load(name)
+    x, K = g['obs'], int(g['K'])
+    prior = (g['mus0'], g['kappas0'], g['psis0'], g['nus0'])
+    resp = g['resp_init']
+    for t in range(int(g['iters'])):
+        post = orc.nw_nat_to_std(orc.add_stats(orc.nw_std_to_nat(*prior), orc.gauss_full_wstats(x, resp)))
+        for a, n in zip(post, ('mus', 'kappas', 'psis', 'nus')):
+            close(a, g[f'post_{n}_{t}'])
+        counts = orc.categorical_wstats(resp)
+        if 'gate_alphas0' in g:
+            ga = orc.dirichlet_posterior(g['gate_alphas0'], counts)
+            close(ga, g[f'gate_alphas_{t}'])
+            logw = orc.dirichlet_expected_log(ga)
+            vg = orc.dirichlet_vlb(g['gate_alphas0'], ga)
+        else:
+            gp, dp = orc.stick_posterior(g['gate_gammas0'], g['gate_deltas0'], counts)
+            close(gp, g[f'gate_gammas_{t}'])
+            logw = orc.stick_expected_log(gp, dp)[0]
+            vg = orc.stick_vlb((g['gate_gammas0'], g['gate_deltas0']), (gp, dp))
+        ell = orc.nw_expected_loglik(x, *post) + logw[:, None]
+        close(ell, g[f'ell_{t}'])
+        resp, lse = orc.responsibilities(ell)
+        close(resp, g[f'resp_{t}'])
+        # VLB through the identity of SURVEY 3.2: data + label terms == sum_n lse_n
+        vlb = vg + np.sum(orc.nw_vlb(prior, post)) + np.sum(lse)
+        close(vlb, g['vlb'][t], 1e-9)
+
+
+def test_dgmm_gibbs_phases():
+    g = load('dgmm_gibbs')
+    x, K = g['obs'], int(g['K'])
+    prior = (g['mus0'], g['kappas0'], g['alphas0'], g['betas0'])
+    labels = g['labels_init']
+    for t in range(int(g['sweeps'])):
+        w = orc.one_hot(labels, K)
+        post = orc.ng_nat_to_std(orc.add_stats(orc.ng_std_to_nat(*prior), orc.gauss_diag_wstats(x, w)))
+        for a, n in zip(post, ('mus', 'kappas', 'alphas', 'betas')):
+            close(a, g[f'post_{n}_{t}'])
+        # the reference trajectory samples with the (bug-compat) prior alphas/betas: SURVEY q1
+        mu_s, l_s = orc.ng_rvs_from_variates(post[0], post[1], g[f'bug_alphas_{t}'], g[f'bug_betas_{t}'],
+                                             g[f'var_gamma_{t}'], g[f'var_z_{t}'])
+        close(mu_s, g[f'lik_mus_{t}'])
+        lp = orc.gauss_diag_loglik(x, g[f'lik_mus_{t}'], g[f'lik_lmbdas_diags_{t}']) + np.log(g[f'probs_{t}'])[:, None]
+        close(lp, g[f'log_prob_{t}'])
+        labels = orc.sample_discrete_from_log(g[f'log_prob_{t}'], g[f'u_{t}'])
+        assert np.array_equal(labels, g[f'labels_{t}'])
+
+
+def test_dgmm_vi_bugcompat():
+    g = load('dgmm_vi_bugcompat')
+    x = g['obs']
+    prior = (g['mus0'], g['kappas0'], g['alphas0'], g['betas0'])
+    resp = g['resp_init']
+    for t in range(int(g['iters'])):
+        post = orc.ng_nat_to_std(orc.add_stats(orc.ng_std_to_nat(*prior), orc.gauss_diag_wstats(x, resp)))
+        close(post[0], g[f'post_mus_{t}'])
+        close(post[1], g[f'post_kappas_{t}'])
+        ga = orc.dirichlet_posterior(g['gate_alphas0'], orc.categorical_wstats(resp))
+        ell = orc.ng_expected_loglik(x, post[0], post[1], prior[2], prior[3]) \
+            + orc.dirichlet_expected_log(ga)[:, None]
+        close(ell, g[f'ell_{t}'])
+        resp, _ = orc.responsibilities(ell)
+        close(resp, g[f'resp_{t}'])
+
+
+@pytest.mark.parametrize('name', ['ilr_tied', 'ilr_stacked', 'ilr_stacked_o2'])
+def test_ilr_phases(name):
+    g = load(name)
+    x, y, K, tied = g['x'], g['y'], int(g['K']), bool(g['tied'])
+    bprior = (g['b_mus0'], g['b_kappas0'], g['b_psis0'], g['b_nus0'])
+    mprior = (g['m_Ms0'], g['m_Ks0'], g['m_psis0'], g['m_nus0'])
+    labels = g['labels_init']
+    for t in range(int(g['sweeps'])):
+        w = orc.one_hot(labels, K)
+        bpost = orc.nw_nat_to_std(orc.add_stats(orc.nw_std_to_nat(*bprior), orc.gauss_full_wstats(x, w)))
+        mpost = orc.mnw_nat_to_std(orc.add_stats(orc.mnw_std_to_nat(*mprior), orc.lingauss_wstats(x, y, w)), tied=tied)
+        for a, n in zip(bpost, ('mus', 'kappas', 'psis', 'nus')):
+            close(a, g[f'b_post_{n}_{t}'])
+        for a, n in zip(mpost, ('Ms', 'Ks', 'psis', 'nus')):
+            close(a, g[f'm_post_{n}_{t}'], 1e-8)
+        for k in range(K):
+            A, lm = orc.mnw_rvs_from_variates(mpost[0][k], mpost[1][k], mpost[2][k], mpost[3][k],
+                                              g[f'm_var_normals_{t}'][k], g[f'm_var_chisq_{t}'][k], g[f'm_var_z_{t}'][k])
+            close(A, g[f'm_lik_As_{t}'][k], 1e-7)
+            close(lm, g[f'm_lik_lmbdas_{t}'][k], 1e-7)
+        lp = orc.gauss_full_loglik(x, g[f'b_lik_mus_{t}'], g[f'b_lik_lmbdas_{t}']) \
+            + orc.lingauss_loglik(x, y, g[f'm_lik_As_{t}'], g[f'm_lik_lmbdas_{t}']) \
+            + np.log(g[f'probs_{t}'])[:, None]
+        close(lp, g[f'log_prob_{t}'])
+        labels = orc.sample_discrete_from_log(g[f'log_prob_{t}'], g[f'u_{t}'])
+        assert np.array_equal(labels, g[f'labels_{t}'])
+    resp = g['vi_resp_init']
+    gprior = (g['gate_gammas0'], g['gate_deltas0'])
+    for t in range(int(g['iters'])):
+        bpost = orc.nw_nat_to_std(orc.add_stats(orc.nw_std_to_nat(*bprior), orc.gauss_full_wstats(x, resp)))
+        mpost = orc.mnw_nat_to_std(orc.add_stats(orc.mnw_std_to_nat(*mprior), orc.lingauss_wstats(x, y, resp)), tied=tied)
+        gp, dp = orc.stick_posterior(*gprior, orc.categorical_wstats(resp))
+        for a, n in zip(mpost, ('Ms', 'Ks', 'psis', 'nus')):
+            close(a, g[f'vi_m_post_{n}_{t}'], 1e-8)
+        ell = orc.nw_expected_loglik(x, *bpost) + orc.mnw_expected_loglik(x, y, *mpost) \
+            + orc.stick_expected_log(gp, dp)[0][:, None]
+        close(ell, g[f'vi_ell_{t}'], 1e-8)
+        resp, lse = orc.responsibilities(ell)
+        close(resp, g[f'vi_resp_{t}'], 1e-8)
+        vlb = orc.stick_vlb(gprior, (gp, dp)) + np.sum(orc.nw_vlb(bprior, bpost)) \
+            + np.sum(orc.mnw_vlb(mprior, mpost)) + np.sum(lse)
+        close(vlb, g['vlb'][t], 1e-8)
+
+
+def test_em_trajectory():
+    g = load('gmm_toy_em')
+    x, K = g['obs'], int(g['K'])
+    resp = g['resp_init']
+    lls = []
+    for _ in range(len(g['ll'])):
+        mus, lmbdas = orc.gauss_full_mstep(orc.gauss_full_wstats(x, resp))
+        probs = orc.categorical_mstep(orc.categorical_wstats(resp))
+        lj = orc.gauss_full_loglik(x, mus, lmbdas) + np.log(probs)[:, None]
+        resp, lse = orc.responsibilities(lj)
+        lls.append(np.sum(lse))
+    close(np.array(lls), g['ll'], 1e-9)
+    close(mus, g['mus'], 1e-8)
+    close(resp, g['resp_final'], 1e-8)
+
+
+@pytest.mark.parametrize('name', ['pointwise_d128', 'pointwise_d16'])
+def test_pointwise(name):
+    g = load(name)
+    x = g['obs']
+    close(orc.gauss_full_loglik(x, g['mus'], g['lmbdas']), g['log_lik'])
+    close(orc.nw_expected_loglik(x, g['mus'], g['kappas'], g['psis'], g['nus']), g['exp_log_lik'])
+    st = orc.gauss_full_wstats(x, g['weights'])
+    close(st[0], g['st_x'])
+    close(st[1], g['st_n'])
+    close(st[2], g['st_xx'])

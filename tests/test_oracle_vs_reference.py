@@ -1,0 +1,291 @@
+"""Pin the oracle against the UNMODIFIED reference, imported from
+/root/reference.  That tree only exists in the build container, so these tests
+skip on the GPU box; the same comparisons travel as fixtures in
+tests/golden/ (see test_oracle_golden.py)."""
+import os
+import sys
+
+import numpy as np
+import numpy.random as npr
+import pytest
+
+REF = '/root/reference'
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'mimo')),
+                                reason='reference tree not present')
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..'))
+from oracle import mimo_oracle as orc  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def ref():
+    sys.path.insert(0, REF)
+    import mimo.distributions as D
+    import mimo.mixtures as M
+    from mimo.utils import stats, data
+    yield type('Ref', (), dict(D=D, M=M, stats=stats, data=data))
+    sys.path.remove(REF)
+
+
+def spd(rng, d, scale=1.0):
+    a = rng.standard_normal((d, d + 2))
+    return scale * (a @ a.T) / d + 0.1 * np.eye(d)
+
+
+def close(a, b, tol=1e-10):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    np.testing.assert_allclose(a, b, rtol=tol, atol=tol * max(1.0, float(np.max(np.abs(b)))))
+
+
+@pytest.mark.parametrize('K,d,N', [(4, 2, 50), (7, 5, 33)])
+def test_gauss_full(ref, K, d, N):
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((N, d)) * 2
+    mus = rng.standard_normal((K, d))
+    lmbdas = np.stack([spd(rng, d) for _ in range(K)])
+    w = rng.random((K, N))
+    lik = ref.D.StackedGaussiansWithPrecision(K, d, mus=mus, lmbdas=lmbdas)
+    close(orc.gauss_full_loglik(x, mus, lmbdas), lik.log_likelihood(x.copy()))
+    for a, b in zip(orc.gauss_full_wstats(x, w), lik.weighted_statistics(x, w)):
+        close(a, b)
+    lik.max_likelihood(x, w)
+    m, l = orc.gauss_full_mstep(orc.gauss_full_wstats(x, w))
+    close(m, lik.mus)
+    close(l, lik.lmbdas, 1e-8)
+
+
+@pytest.mark.parametrize('K,d,N', [(3, 4, 40)])
+def test_gauss_diag(ref, K, d, N):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((N, d)) * 2
+    mus = rng.standard_normal((K, d))
+    ld = rng.random((K, d)) + 0.5
+    w = rng.random((K, N))
+    lik = ref.D.StackedGaussiansWithDiagonalPrecision(K, d, mus=mus, lmbdas_diags=ld)
+    close(orc.gauss_diag_loglik(x, mus, ld), lik.log_likelihood(x.copy()))
+    for a, b in zip(orc.gauss_diag_wstats(x, w), lik.weighted_statistics(x, w)):
+        close(a, b)
+    lik.max_likelihood(x, w)
+    m, l = orc.gauss_diag_mstep(orc.gauss_diag_wstats(x, w))
+    close(m, lik.mus)
+    close(l, lik.lmbdas_diags)
+
+
+@pytest.mark.parametrize('K,din,o,N,affine', [(3, 2, 1, 30, True), (4, 3, 2, 25, True), (2, 3, 2, 25, False)])
+def test_lingauss(ref, K, din, o, N, affine):
+    rng = np.random.default_rng(2)
+    c = din + 1 if affine else din
+    x = rng.standard_normal((N, din))
+    y = rng.standard_normal((N, o))
+    As = rng.standard_normal((K, o, c))
+    lmbdas = np.stack([spd(rng, o) for _ in range(K)])
+    w = rng.random((K, N))
+    lik = ref.D.StackedLinearGaussiansWithPrecision(K, c, o, As=As, lmbdas=lmbdas, affine=affine)
+    close(orc.lingauss_loglik(x, y, As, lmbdas, affine), lik.log_likelihood(x.copy(), y.copy()))
+    for a, b in zip(orc.lingauss_wstats(x, y, w, affine), lik.weighted_statistics(x, y, w)):
+        close(a, b)
+    lik.max_likelihood(x, y, w)
+    A2, l2 = orc.lingauss_mstep(orc.lingauss_wstats(x, y, w, affine))
+    close(A2, lik.As, 1e-8)
+    close(l2, lik.lmbdas, 1e-8)
+
+
+def nw_params(rng, K, d):
+    return (rng.standard_normal((K, d)), rng.random(K) + 0.1,
+            np.stack([spd(rng, d) for _ in range(K)]), d + 1.0 + 3 * rng.random(K))
+
+
+@pytest.mark.parametrize('tied', [False, True])
+def test_normal_wishart(ref, tied):
+    rng = np.random.default_rng(3)
+    K, d, N = 5, 3, 40
+    prior = nw_params(rng, K, d)
+    cls = ref.D.TiedNormalWisharts if tied else ref.D.StackedNormalWisharts
+    rp = cls(K, d, *prior)
+    nat = orc.nw_std_to_nat(*prior)
+    for a, b in zip(nat, rp.nat_param):
+        close(a, b)
+    x = rng.standard_normal((N, d))
+    w = rng.random((K, N))
+    post_nat = orc.add_stats(nat, orc.gauss_full_wstats(x, w))
+    post = orc.nw_nat_to_std(post_nat, tied=tied)
+    rq = cls(K, d, *prior)
+    rq.nat_param = rp.nat_param + ref.D.StackedGaussiansWithPrecision(K, d).weighted_statistics(x, w)
+    for a, b in zip(post, rq.params):
+        close(a, b)
+    for a, b in zip(orc.nw_expected_statistics(*post), rq.expected_statistics()):
+        close(a, b)
+    close(orc.nw_log_partition(*post), rq.log_partition())
+    close(orc.nw_vlb(prior, post), rq.entropy() - rq.cross_entropy(rp), 1e-9)
+    for a, b in zip(orc.nw_mode(*post), rq.mode()):
+        close(a, b)
+    # expected log-likelihood under the posterior
+    wrap = ref.D.StackedGaussiansWithNormalWisharts(K, d, prior=rp)
+    wrap.posterior = rq
+    close(orc.nw_expected_loglik(x, *post), wrap.expected_log_likelihood(x))
+
+
+def test_normal_wishart_rvs(ref):
+    rng = np.random.default_rng(4)
+    K, d = 3, 4
+    post = nw_params(rng, K, d)
+    rq = ref.D.StackedNormalWisharts(K, d, *post)
+    npr.seed(11)
+    mus_ref, lmbdas_ref = rq.rvs()
+    npr.seed(11)
+    n_tril = d * (d - 1) // 2
+    for k in range(K):
+        normals = npr.normal(size=n_tril)
+        chisq = np.array([npr.chisquare(post[3][k] - i, size=1)[0] for i in range(d)])
+        z = npr.normal(size=d)
+        mu, lm = orc.nw_rvs_from_variates(post[0][k], post[1][k], post[2][k], post[3][k], normals, chisq, z)
+        close(mu, mus_ref[k])
+        close(lm, lmbdas_ref[k])
+
+
+def test_normal_gamma(ref):
+    rng = np.random.default_rng(5)
+    K, d, N = 4, 3, 30
+    prior = (rng.standard_normal((K, d)), rng.random((K, d)) + 0.1,
+             rng.random((K, d)) + 1.0, rng.random((K, d)) + 0.5)
+    nat = orc.ng_std_to_nat(*prior)
+    x = rng.standard_normal((N, d))
+    w = rng.random((K, N))
+    post = orc.ng_nat_to_std(orc.add_stats(nat, orc.gauss_diag_wstats(x, w)))
+    lik = ref.D.StackedGaussiansWithDiagonalPrecision(K, d)
+    stats = lik.weighted_statistics(x, w)
+    # per-dist reference (the stacked alphas/betas setters are broken: SURVEY q1)
+    for k in range(K):
+        rp = ref.D.NormalGamma(d, *[p[k] for p in prior])
+        rq = ref.D.NormalGamma(d, *[p[k] for p in prior])
+        rq.nat_param = rp.nat_param + ref.D.composite.Stats([s[k] for s in stats])
+        for a, b in zip([p[k] for p in post], rq.params):
+            close(a, b)
+        for a, b in zip([s[k] for s in orc.ng_expected_statistics(*post)], rq.expected_statistics()):
+            close(a, b)
+        close(orc.ng_vlb(prior, post)[k], rq.entropy() - rq.cross_entropy(rp), 1e-9)
+        for a, b in zip([m[k] for m in orc.ng_mode(*post)], rq.mode()):
+            close(a, b)
+    rs = ref.D.StackedNormalGammas(K, d, *post)
+    wrap = ref.D.StackedGaussiansWithNormalGammas(K, d, prior=rs)
+    close(orc.ng_expected_loglik(x, *post), wrap.expected_log_likelihood(x))
+
+
+@pytest.mark.parametrize('tied', [False, True])
+def test_matrix_normal_wishart(ref, tied):
+    rng = np.random.default_rng(6)
+    K, din, o, N = 4, 3, 2, 35
+    c = din + 1
+    prior = (rng.standard_normal((K, o, c)), np.stack([spd(rng, c) for _ in range(K)]),
+             np.stack([spd(rng, o) for _ in range(K)]), o + 1.0 + 3 * rng.random(K))
+    cls = ref.D.TiedMatrixNormalWisharts if tied else ref.D.StackedMatrixNormalWisharts
+    rp = cls(K, c, o, *prior)
+    nat = orc.mnw_std_to_nat(*prior)
+    for a, b in zip(nat, rp.nat_param):
+        close(a, b)
+    x = rng.standard_normal((N, din))
+    y = rng.standard_normal((N, o))
+    w = rng.random((K, N))
+    post = orc.mnw_nat_to_std(orc.add_stats(nat, orc.lingauss_wstats(x, y, w)), tied=tied)
+    rq = cls(K, c, o, *prior)
+    rq.nat_param = rp.nat_param + ref.D.StackedLinearGaussiansWithPrecision(K, c, o).weighted_statistics(x, y, w)
+    for a, b in zip(post, rq.params):
+        close(a, b, 1e-9)
+    for a, b in zip(orc.mnw_expected_statistics(*post), rq.expected_statistics()):
+        close(a, b, 1e-9)
+    close(orc.mnw_vlb(prior, post), rq.entropy() - rq.cross_entropy(rp), 1e-8)
+    wcls = ref.D.TiedLinearGaussiansWithMatrixNormalWisharts if tied \
+        else ref.D.StackedLinearGaussiansWithMatrixNormalWisharts
+    wrap = wcls(K, c, o, prior=rp)
+    wrap.posterior = rq
+    close(orc.mnw_expected_loglik(x, y, *post), wrap.expected_log_likelihood(x, y), 1e-9)
+
+
+def test_mnw_rvs(ref):
+    rng = np.random.default_rng(7)
+    K, din, o = 3, 2, 2
+    c = din + 1
+    post = (rng.standard_normal((K, o, c)), np.stack([spd(rng, c) for _ in range(K)]),
+            np.stack([spd(rng, o) for _ in range(K)]), o + 1.0 + 3 * rng.random(K))
+    rq = ref.D.StackedMatrixNormalWisharts(K, c, o, *post)
+    npr.seed(5)
+    As_ref, lm_ref = rq.rvs()
+    npr.seed(5)
+    for k in range(K):
+        normals = npr.normal(size=o * (o - 1) // 2)
+        chisq = np.array([npr.chisquare(post[3][k] - i, size=1)[0] for i in range(o)])
+        z = npr.normal(size=o * c)
+        A, lm = orc.mnw_rvs_from_variates(post[0][k], post[1][k], post[2][k], post[3][k], normals, chisq, z)
+        close(A, As_ref[k])
+        close(lm, lm_ref[k])
+
+
+def test_gating(ref):
+    rng = np.random.default_rng(8)
+    K = 6
+    counts = rng.random(K) * 10
+    a0 = np.ones(K) * 2.0
+    g = ref.D.CategoricalWithDirichlet(K, ref.D.Dirichlet(K, a0))
+    g.posterior.nat_param = g.prior.nat_param + counts
+    post = orc.dirichlet_posterior(a0, counts)
+    close(post, g.posterior.alphas)
+    close(orc.dirichlet_expected_log(post), g.expected_log_likelihood())
+    close(orc.dirichlet_vlb(a0, post), g.variational_lowerbound())
+    close(orc.dirichlet_mode(post), g.posterior.mode())
+
+    g0, d0 = np.ones(K), 5.0 * np.ones(K)
+    s = ref.D.CategoricalWithStickBreaking(K, ref.D.TruncatedStickBreaking(K, g0, d0))
+    s.meanfield_update(None, np.tile(counts[:, None] / 4, (1, 4)))
+    gp, dp = orc.stick_posterior(g0, d0, counts)
+    close(gp, s.posterior.gammas)
+    close(dp, s.posterior.deltas)
+    tot, E_stick, E_rest = orc.stick_expected_log(gp, dp)
+    rs, rr = s.expected_log_likelihood()
+    close(E_stick, rs)
+    close(E_rest, rr)
+    close(orc.stick_vlb((g0, d0), (gp, dp)), s.variational_lowerbound())
+    close(orc.stick_mean(gp, dp), s.posterior.mean())
+    npr.seed(3)
+    pr = s.posterior.rvs()
+    npr.seed(3)
+    close(orc.stick_probs_from_betas(npr.beta(gp[:-1], dp[:-1])), pr)
+
+
+def test_label_sampling(ref):
+    rng = np.random.default_rng(9)
+    K, N = 7, 500
+    p_log = rng.standard_normal((K, N)) * 3
+    npr.seed(42)
+    u = npr.random((1, N))
+    npr.seed(42)
+    lab_ref = ref.stats.sample_discrete_from_log(p_log, axis=0)
+    lab = orc.sample_discrete_from_log(p_log, u)
+    assert lab.dtype == np.int32 and np.array_equal(lab, lab_ref)
+    close(orc.one_hot(lab, K), ref.data.one_hot(lab_ref, K))
+
+
+def test_vlb_identity_and_labels_term(ref):
+    """vlb_obs + vlb_labels == sum_n logsumexp_k(E log joint)."""
+    rng = np.random.default_rng(10)
+    K, d, N = 5, 2, 80
+    prior = nw_params(rng, K, d)
+    x = rng.standard_normal((N, d)) * 2
+    comp = ref.D.StackedGaussiansWithNormalWisharts(K, d, prior=ref.D.StackedNormalWisharts(K, d, *prior))
+    for gating in (ref.D.CategoricalWithDirichlet(K, ref.D.Dirichlet(K, np.ones(K))),
+                   ref.D.CategoricalWithStickBreaking(K, ref.D.TruncatedStickBreaking(K, np.ones(K), 3 * np.ones(K)))):
+        model = ref.M.BayesianMixtureOfGaussians(gating=gating, components=comp)
+        npr.seed(1)
+        model.meanfield_coordinate_descent(x, maxiter=3, tol=0., progress_bar=False)
+        resp = model.expected_responsibilities(x)
+        ell = model.expected_log_complete_likelihood(x)
+        r2, lse = orc.responsibilities(ell)
+        close(r2, resp)
+        lhs = model.variational_lowerbound_obs(x, resp) + model.variational_lowerbound_labels(resp)
+        close(lhs, np.sum(lse), 1e-9)
+        if isinstance(gating, ref.D.CategoricalWithDirichlet):
+            close(orc.vlb_labels_dirichlet(resp, gating.expected_log_likelihood()),
+                  model.variational_lowerbound_labels(resp))
+        else:
+            es, er = gating.expected_log_likelihood()
+            close(orc.vlb_labels_stick(resp, es, er), model.variational_lowerbound_labels(resp))
