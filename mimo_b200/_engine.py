@@ -1,0 +1,417 @@
+"""Device plumbing between the NumPy-facing API and the C-ABI kernels.
+
+torch is used for device memory, streams and (in sharded.py) torch.distributed
+only; every numerical operation below is a call into libmimo_b200.so.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F32, F64, WRITE_RESP, WRITE_LSE, DRAW_LABELS, ACC_LSE  # noqa: F401
+
+_DEFAULT_PRECISION = 'fp32'
+
+
+def set_default_precision(precision):
+    """'fp32' (FP32 compute, FP64 accumulation; rel 1e-4 parity) or 'fp64' (1e-9 parity)."""
+    global _DEFAULT_PRECISION
+    assert precision in ('fp32', 'fp64')
+    _DEFAULT_PRECISION = precision
+
+
+def default_precision():
+    return _DEFAULT_PRECISION
+
+
+def tdtype(precision):
+    return torch.float32 if precision == 'fp32' else torch.float64
+
+
+def code(precision):
+    return F32 if precision == 'fp32' else F64
+
+
+def device():
+    _lib.require_device()
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def to_dev(x, dtype=torch.float64):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device(), dtype=dtype).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x))).to(device=device(), dtype=dtype)
+
+
+def to_host(t):
+    return t.detach().cpu().numpy()
+
+
+def zeros(shape, dtype=torch.float64):
+    return torch.zeros(shape, dtype=dtype, device=device())
+
+
+def empty(shape, dtype=torch.float64):
+    return torch.empty(shape, dtype=dtype, device=device())
+
+
+def pad_rows(r):
+    p = 8
+    while p < r:
+        p *= 2
+    if p > 128:
+        raise NotImplementedError('mimo_b200: %d whitening rows per component (> 128) is not supported' % r)
+    return p
+
+
+def pad_cols(dp):
+    return (dp + 3) // 4 * 4
+
+
+# ---- feature tables ---------------------------------------------------------------
+_feat_cache = {}
+
+
+class Features:
+    """Index pairs (fi, fj) into zt = [z ; 1] defining the packed statistics."""
+
+    def __init__(self, fi, fj, D):
+        self.D = D
+        self.F = len(fi)
+        self.fi_host = np.asarray(fi, dtype=np.int32)
+        self.fj_host = np.asarray(fj, dtype=np.int32)
+        self._dev = None
+
+    def dev(self):
+        if self._dev is None:
+            self._dev = (to_dev(self.fi_host, torch.int32), to_dev(self.fj_host, torch.int32))
+        return self._dev
+
+
+def quad_features(D):
+    """all pairs j <= i of zt (length D+1), f = i(i+1)/2 + j."""
+    key = ('quad', D)
+    if key not in _feat_cache:
+        fi, fj = [], []
+        for i in range(D + 1):
+            for j in range(i + 1):
+                fi.append(i)
+                fj.append(j)
+        _feat_cache[key] = Features(fi, fj, D)
+    return _feat_cache[key]
+
+
+def diag_features(D):
+    """[z_j * 1 | z_j * z_j | 1 * 1]."""
+    key = ('diag', D)
+    if key not in _feat_cache:
+        fi = list(range(D)) + list(range(D)) + [D]
+        fj = [D] * D + list(range(D)) + [D]
+        _feat_cache[key] = Features(fi, fj, D)
+    return _feat_cache[key]
+
+
+def tri(a, b):
+    a, b = (a, b) if a >= b else (b, a)
+    return a * (a + 1) // 2 + b
+
+
+# ---- operands -----------------------------------------------------------------------
+class QuadOperands:
+    """W (K, Rp, Dpp), cst (K): a[k][n] = cst[k] - 0.5 || W_k [z_n ; 1] ||^2."""
+    family = 0
+
+    def __init__(self, K, D, rows, precision):
+        self.K, self.D, self.rows = K, D, rows
+        self.Rp, self.Dpp = pad_rows(rows), pad_cols(D + 1)
+        self.precision = precision
+        self.W = zeros((K, self.Rp, self.Dpp), tdtype(precision))
+        self.cst = zeros((K,), tdtype(precision))
+
+    def args(self):
+        return ptr(self.W), None, ptr(self.cst), self.K, self.Rp, self.Dpp
+
+
+class DiagOperands:
+    """S, T (K, D), cst (K): a[k][n] = cst[k] - 0.5 sum_j (S_kj z_nj - T_kj)^2."""
+    family = 1
+
+    def __init__(self, K, D, precision):
+        self.K, self.D = K, D
+        self.Rp, self.Dpp = 8, pad_cols(D + 1)
+        self.precision = precision
+        self.S = zeros((K, D), tdtype(precision))
+        self.T = zeros((K, D), tdtype(precision))
+        self.cst = zeros((K,), tdtype(precision))
+
+    def args(self):
+        return ptr(self.S), ptr(self.T), ptr(self.cst), self.K, self.Rp, self.Dpp
+
+
+class Info:
+    """Device-side status word of the posterior kernels: {code, failing component}."""
+
+    def __init__(self):
+        self.t = zeros((2,), torch.int32)
+
+    def check(self):
+        h = self.t.cpu().numpy()
+        if h[0] != 0:
+            self.t.zero_()
+            if h[0] == _lib.ENOTPD:
+                raise np.linalg.LinAlgError('Matrix is not positive definite (component %d)' % h[1])
+            raise AssertionError('posterior kernel rejected its input (code %d, component %d)' % (h[0], h[1]))
+
+
+def workspace(nbytes):
+    return torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device())
+
+
+# ---- per-point kernels ----------------------------------------------------------------
+def loglik(Z, ops, out=None):
+    """(K, N) log-likelihood block for resident data Z (N, D)."""
+    N, D = Z.shape
+    assert D == ops.D and Z.dtype == tdtype(ops.precision)
+    if out is None:
+        out = empty((ops.K, N), Z.dtype)
+    if ops.family == 0:
+        _lib.call('mimo_loglik_quad', code(ops.precision), ptr(Z), N, D, Z.stride(0), ptr(ops.W), ptr(ops.cst),
+                  ops.K, ops.Rp, ops.Dpp, ptr(out), out.stride(0), stream())
+    else:
+        _lib.call('mimo_loglik_diag', code(ops.precision), ptr(Z), N, D, Z.stride(0), ptr(ops.S), ptr(ops.T),
+                  ptr(ops.cst), ops.K, ptr(out), out.stride(0), stream())
+    return out
+
+
+def softmax(a, precision, resp=False, lse=False, labels=False, lse_sum=False, uniforms=None, seed=0, offset=0):
+    """In-place softmax / label draw over a (K, n) log-joint.  Returns a dict."""
+    K, n = a.shape
+    flags = (WRITE_RESP if resp else 0) | (WRITE_LSE if lse else 0) | (DRAW_LABELS if labels else 0) \
+        | (ACC_LSE if lse_sum else 0)
+    out = {}
+    lse_t = empty((n,), a.dtype) if lse else None
+    lab_t = empty((n,), torch.int32) if labels else None
+    sum_t = zeros((1,), torch.float64) if lse_sum else None
+    uni_t = to_dev(uniforms, torch.float64).reshape(-1) if uniforms is not None else None
+    if uni_t is not None:
+        assert uni_t.numel() == n
+    _lib.call('mimo_softmax', code(precision), ptr(a), K, n, a.stride(0), flags, ptr(lse_t), ptr(uni_t),
+              int(seed), int(offset), ptr(lab_t), ptr(sum_t), stream())
+    out['lse'], out['labels'], out['lse_sum'] = lse_t, lab_t, sum_t
+    return out
+
+
+def stats_soft(Z, resp, feats, precision, stat=None):
+    N, D = Z.shape
+    K = resp.shape[0]
+    fi, fj = feats.dev()
+    if stat is None:
+        stat = zeros((K, feats.F), torch.float64)
+    _lib.call('mimo_stats_soft', code(precision), ptr(Z), N, D, Z.stride(0), ptr(resp), resp.stride(0), K,
+              ptr(fi), ptr(fj), feats.F, ptr(stat), stream())
+    return stat
+
+
+def stats_hard(Z, labels, K, feats, precision, stat=None):
+    N, D = Z.shape
+    fi, fj = feats.dev()
+    if stat is None:
+        stat = zeros((K, feats.F), torch.float64)
+    wsb = _lib.load().mimo_stats_hard_workspace(N, K)
+    ws = workspace(wsb)
+    _lib.call('mimo_stats_hard', code(precision), ptr(Z), N, D, Z.stride(0), ptr(labels), K,
+              ptr(fi), ptr(fj), feats.F, ptr(stat), ptr(ws), wsb, stream())
+    return stat
+
+
+class SweepBuffers:
+    """Reusable device buffers for mimo_sweep on a fixed (N, K, F)."""
+
+    def __init__(self, N, K, F, precision, hard):
+        self.N, self.K, self.F, self.precision, self.hard = N, K, F, precision, hard
+        self.wsb = _lib.load().mimo_sweep_workspace(code(precision), N, K, 1 if hard else 0)
+        self.ws = workspace(self.wsb)
+        self.stat = zeros((K, F), torch.float64)
+        self.lse_sum = zeros((1,), torch.float64)
+        self.labels = empty((N,), torch.int32) if hard else None
+
+
+def sweep(Z, ops, feats, buf, uniforms=None, seed=0, offset=0, ll_out=None, lse_out=None, zero=True):
+    """One E-step + statistics pass over resident Z.  Results land in buf.stat,
+    buf.lse_sum and (hard) buf.labels."""
+    N, D = Z.shape
+    fi, fj = feats.dev()
+    if zero:
+        buf.stat.zero_()
+        buf.lse_sum.zero_()
+    a, b, c, K, Rp, Dpp = ops.args()
+    _lib.call('mimo_sweep', code(ops.precision), ops.family, 1 if buf.hard else 0,
+              ptr(Z), N, D, Z.stride(0), a, b, c, K, Rp, Dpp, ptr(fi), ptr(fj), feats.F,
+              ptr(uniforms), int(seed), int(offset), ptr(buf.stat), ptr(buf.lse_sum), ptr(buf.labels),
+              ptr(lse_out), ptr(ll_out), (ll_out.stride(0) if ll_out is not None else 0),
+              ptr(buf.ws), buf.wsb, stream())
+    return buf
+
+
+# ---- per-component kernels --------------------------------------------------------------
+def _i32(x):
+    return to_dev(np.asarray(x, dtype=np.int32), torch.int32)
+
+
+def identity_map(d, D):
+    """variable j -> column j, constant -> column D (a plain Gaussian over all of z)."""
+    return _i32(list(range(d)) + [D])
+
+
+def nw_posterior(prior, stat, F, stat_idx, Dp, mode=0, tied=False, variates=None, ops=None, row_off=0,
+                 col_map=None, want_lik=False, want_vlb=True, info=None):
+    """prior = (m0 (K,d), kappa0 (K), psi0 (K,d,d), nu0 (K)) device FP64 tensors."""
+    m0, k0, p0, n0 = prior
+    K, d = m0.shape
+    out = dict(m=empty((K, d)), kappa=empty((K,)), psi=empty((K, d, d)), nu=empty((K,)))
+    out['vlb'] = empty((K,)) if want_vlb else None
+    out['lik_mu'] = empty((K, d)) if want_lik else None
+    out['lik_lmbda'] = empty((K, d, d)) if want_lik else None
+    wsb = _lib.load().mimo_nw_workspace(K, d)
+    ws = workspace(wsb)
+    info = info or Info()
+    var_t = to_dev(variates) if variates is not None else None
+    W = ops.W if ops is not None else None
+    _lib.call('mimo_nw_posterior', K, d, int(tied), mode, ptr(m0), ptr(k0), ptr(p0), ptr(n0),
+              ptr(stat), F, ptr(stat_idx), Dp, ptr(var_t),
+              ptr(out['m']), ptr(out['kappa']), ptr(out['psi']), ptr(out['nu']),
+              ptr(out['lik_mu']), ptr(out['lik_lmbda']), ptr(out['vlb']),
+              code(ops.precision) if ops is not None else F64, ptr(W), ptr(ops.cst) if ops is not None else None,
+              ops.Rp if ops is not None else 8, ops.Dpp if ops is not None else pad_cols(Dp), row_off, ptr(col_map),
+              ptr(ws), wsb, ptr(info.t), stream())
+    out['info'] = info
+    return out
+
+
+def ng_posterior(prior, stat, F, mode=0, tied=False, bug_compat=False, variates=None, ops=None,
+                 want_lik=False, want_vlb=True, info=None):
+    m0, k0, a0, b0 = prior
+    K, d = m0.shape
+    out = dict(m=empty((K, d)), kappa=empty((K, d)), alpha=empty((K, d)), beta=empty((K, d)))
+    out['vlb'] = empty((K,)) if want_vlb else None
+    out['lik_mu'] = empty((K, d)) if want_lik else None
+    out['lik_lmbda'] = empty((K, d)) if want_lik else None
+    wsb = _lib.load().mimo_ng_workspace(K, d)
+    ws = workspace(wsb)
+    info = info or Info()
+    var_t = to_dev(variates) if variates is not None else None
+    _lib.call('mimo_ng_posterior', K, d, int(tied), mode, int(bug_compat), ptr(m0), ptr(k0), ptr(a0), ptr(b0),
+              ptr(stat), F, ptr(var_t), ptr(out['m']), ptr(out['kappa']), ptr(out['alpha']), ptr(out['beta']),
+              ptr(out['lik_mu']), ptr(out['lik_lmbda']), ptr(out['vlb']),
+              code(ops.precision) if ops is not None else F64,
+              ptr(ops.S) if ops is not None else None, ptr(ops.T) if ops is not None else None,
+              ptr(ops.cst) if ops is not None else None, ptr(ws), wsb, ptr(info.t), stream())
+    out['info'] = info
+    return out
+
+
+def mnw_posterior(prior, stat, F, stat_idx, Dp, mode=0, tied=False, variates=None, ops=None, row_off=0,
+                  col_map=None, want_lik=False, want_vlb=True, info=None):
+    """prior = (M0 (K,o,c), K0 (K,c,c), psi0 (K,o,o), nu0 (K))."""
+    M0, K0, p0, n0 = prior
+    K, o, c = M0.shape
+    out = dict(M=empty((K, o, c)), K=empty((K, c, c)), psi=empty((K, o, o)), nu=empty((K,)))
+    out['vlb'] = empty((K,)) if want_vlb else None
+    out['lik_A'] = empty((K, o, c)) if want_lik else None
+    out['lik_lmbda'] = empty((K, o, o)) if want_lik else None
+    wsb = _lib.load().mimo_mnw_workspace(K, c, o)
+    ws = workspace(wsb)
+    info = info or Info()
+    var_t = to_dev(variates) if variates is not None else None
+    _lib.call('mimo_mnw_posterior', K, c, o, int(tied), mode, ptr(M0), ptr(K0), ptr(p0), ptr(n0),
+              ptr(stat), F, ptr(stat_idx), Dp, ptr(var_t),
+              ptr(out['M']), ptr(out['K']), ptr(out['psi']), ptr(out['nu']),
+              ptr(out['lik_A']), ptr(out['lik_lmbda']), ptr(out['vlb']),
+              code(ops.precision) if ops is not None else F64, ptr(ops.W) if ops is not None else None,
+              ptr(ops.cst) if ops is not None else None,
+              ops.Rp if ops is not None else 8, ops.Dpp if ops is not None else pad_cols(Dp), row_off, ptr(col_map),
+              ptr(ws), wsb, ptr(info.t), stream())
+    out['info'] = info
+    return out
+
+
+def gating_posterior(kind, prior_a, prior_b, stat, F, count_feature, mode=0, variates=None, ops=None, info=None):
+    """kind 0 Dirichlet / 1 stick-breaking.  Sets ops.cst to the log-weights."""
+    K = prior_a.shape[0]
+    out = dict(a=empty((K,)), b=empty((K,)) if kind == 1 else None, probs=empty((K,)), vlb=empty((1,)))
+    wsb = _lib.load().mimo_gating_workspace(K)
+    ws = workspace(wsb)
+    info = info or Info()
+    var_t = to_dev(variates) if variates is not None else None
+    _lib.call('mimo_gating_posterior', K, kind, mode, ptr(prior_a), ptr(prior_b), ptr(stat), F, count_feature,
+              ptr(var_t), ptr(out['a']), ptr(out['b']), ptr(out['probs']), ptr(out['vlb']),
+              code(ops.precision) if ops is not None else F64, ptr(ops.cst) if ops is not None else None,
+              ptr(ws), wsb, ptr(info.t), stream())
+    out['info'] = info
+    return out
+
+
+def set_log_weights(ops, logw):
+    """cst[k] <- log-weight (explicit gating probabilities; categorical.py:51-59)."""
+    ops.cst.copy_(to_dev(logw, ops.cst.dtype))
+
+
+def operands_gauss(ops, mu, lmbda, row_off=0, col_map=None, info=None):
+    K, d = mu.shape
+    wsb = _lib.load().mimo_operands_workspace(K, d)
+    ws = workspace(wsb)
+    info = info or Info()
+    col_map = col_map if col_map is not None else identity_map(d, ops.D)
+    _lib.call('mimo_operands_gauss', K, d, ptr(mu), ptr(lmbda), code(ops.precision), ptr(ops.W), ptr(ops.cst),
+              ops.Rp, ops.Dpp, row_off, ptr(col_map), ptr(ws), wsb, ptr(info.t), stream())
+    return info
+
+
+def operands_lingauss(ops, A, lmbda, row_off, col_map, info=None):
+    K, o, c = A.shape
+    wsb = _lib.load().mimo_operands_workspace(K, o)
+    ws = workspace(wsb)
+    info = info or Info()
+    _lib.call('mimo_operands_lingauss', K, c, o, ptr(A), ptr(lmbda), code(ops.precision), ptr(ops.W), ptr(ops.cst),
+              ops.Rp, ops.Dpp, row_off, ptr(col_map), ptr(ws), wsb, ptr(info.t), stream())
+    return info
+
+
+def operands_gauss_diag(ops, mu, lam):
+    K, d = mu.shape
+    _lib.call('mimo_operands_gauss_diag', K, d, ptr(mu), ptr(lam), code(ops.precision), ptr(ops.S), ptr(ops.T),
+              ptr(ops.cst), stream())
+
+
+def mstep_gauss(stat, F, stat_idx, Dp, K, d, tied=False, info=None):
+    mu, lmbda = empty((K, d)), empty((K, d, d))
+    wsb = _lib.load().mimo_mstep_workspace(K, d)
+    ws = workspace(wsb)
+    info = info or Info()
+    _lib.call('mimo_mstep_gauss', K, d, int(tied), ptr(stat), F, ptr(stat_idx), Dp, ptr(mu), ptr(lmbda),
+              ptr(ws), wsb, ptr(info.t), stream())
+    return mu, lmbda, info
+
+
+def mstep_gauss_diag(stat, F, K, d, tied=False):
+    mu, lam = empty((K, d)), empty((K, d))
+    ws = workspace(8 * (d + 1))
+    _lib.call('mimo_mstep_gauss_diag', K, d, int(tied), ptr(stat), F, ptr(mu), ptr(lam), ptr(ws), ws.numel(), stream())
+    return mu, lam
+
+
+def mstep_lingauss(stat, F, stat_idx, Dp, K, c, o, tied=False, info=None):
+    A, lmbda = empty((K, o, c)), empty((K, o, o))
+    wsb = _lib.load().mimo_mstep_lingauss_workspace(K, c, o)
+    ws = workspace(wsb)
+    info = info or Info()
+    _lib.call('mimo_mstep_lingauss', K, c, o, int(tied), ptr(stat), F, ptr(stat_idx), Dp, ptr(A), ptr(lmbda),
+              ptr(ws), wsb, ptr(info.t), stream())
+    return A, lmbda, info

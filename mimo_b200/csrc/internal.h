@@ -1,0 +1,81 @@
+// Internal (C++) entry points behind the extern "C" wrappers of abi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace mimo {
+
+int loglik_quad(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const void* W, const void* cst,
+                int K, int Rp, int Dpp, void* out, int64_t ldo, cudaStream_t st);
+int loglik_diag(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const void* S, const void* Tm,
+                const void* cst, int K, void* out, int64_t ldo, cudaStream_t st);
+int softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags, void* lse, const void* uniforms,
+            uint64_t seed, uint64_t point_offset, int32_t* labels, double* lse_sum, cudaStream_t st);
+
+int stats_soft(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K,
+               const int32_t* fi, const int32_t* fj, int F, double* stat, cudaStream_t st);
+size_t stats_hard_workspace(int64_t N, int K);
+int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const int32_t* labels, int K,
+               const int32_t* fi, const int32_t* fj, int F, double* stat,
+               void* workspace, size_t workspace_bytes, bool check, cudaStream_t st);
+
+int64_t sweep_chunk_points(int dtype, int64_t N, int K);
+size_t sweep_workspace(int dtype, int64_t N, int K, int hard);
+int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int64_t ldz,
+          const void* op_a, const void* op_b, const void* cst, int K, int Rp, int Dpp,
+          const int32_t* fi, const int32_t* fj, int F,
+          const void* uniforms, uint64_t seed, uint64_t point_offset,
+          double* stat, double* lse_sum, int32_t* labels_out, void* lse_out, void* ll_out, int64_t ldo,
+          void* workspace, size_t workspace_bytes, cudaStream_t st);
+int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, int D,
+               const void* op_a_host, const void* op_b_host, const void* cst_host, int K, int Rp, int Dpp,
+               const int32_t* fi_host, const int32_t* fj_host, int F,
+               const void* uniforms_host, uint64_t seed,
+               double* stat_host, double* lse_sum_host, int32_t* labels_host);
+
+size_t nw_workspace(int K, int d);
+int nw_posterior(int K, int d, int tied, int mode,
+                 const double* m0, const double* kappa0, const double* psi0, const double* nu0,
+                 const double* stat, int F, const int32_t* stat_idx, int Dp, const double* variates,
+                 double* post_m, double* post_kappa, double* post_psi, double* post_nu,
+                 double* lik_mu, double* lik_lmbda, double* vlb,
+                 int op_dtype, void* W, void* cst, int Rp, int Dpp, int row_off, const int32_t* col_map,
+                 void* workspace, size_t workspace_bytes, int32_t* info, cudaStream_t st);
+size_t ng_workspace(int K, int d);
+int ng_posterior(int K, int d, int tied, int mode, int bug_compat,
+                 const double* m0, const double* kappa0, const double* alpha0, const double* beta0,
+                 const double* stat, int F, const double* variates,
+                 double* post_m, double* post_kappa, double* post_alpha, double* post_beta,
+                 double* lik_mu, double* lik_l, double* vlb,
+                 int op_dtype, void* S, void* T, void* cst, void* workspace, size_t workspace_bytes,
+                 int32_t* info, cudaStream_t st);
+size_t mnw_workspace(int K, int c, int o);
+int mnw_posterior(int K, int c, int o, int tied, int mode,
+                  const double* M0, const double* K0, const double* psi0, const double* nu0,
+                  const double* stat, int F, const int32_t* stat_idx, int Dp, const double* variates,
+                  double* post_M, double* post_K, double* post_psi, double* post_nu,
+                  double* lik_A, double* lik_lmbda, double* vlb,
+                  int op_dtype, void* W, void* cst, int Rp, int Dpp, int row_off, const int32_t* col_map,
+                  void* workspace, size_t workspace_bytes, int32_t* info, cudaStream_t st);
+size_t gating_workspace(int K);
+int gating_posterior(int K, int kind, int mode, const double* prior_a, const double* prior_b,
+                     const double* stat, int F, int count_feature, const double* variates,
+                     double* post_a, double* post_b, double* probs, double* vlb,
+                     int op_dtype, void* cst, void* workspace, size_t workspace_bytes,
+                     int32_t* info, cudaStream_t st);
+int operands_gauss(int K, int d, int c, const double* mu_or_A, const double* lmbda,
+                   int op_dtype, void* W, void* cst, int Rp, int Dpp, int row_off, const int32_t* col_map,
+                   void* workspace, size_t workspace_bytes, int32_t* info, cudaStream_t st);
+int operands_gauss_diag(int K, int d, const double* mu, const double* lam, int op_dtype,
+                        void* S, void* T, void* cst, cudaStream_t st);
+size_t mstep_workspace(int K, int d);
+int mstep_gauss(int K, int d, int tied, const double* stat, int F, const int32_t* stat_idx, int Dp,
+                double* mu, double* lmbda, void* workspace, size_t workspace_bytes, int32_t* info, cudaStream_t st);
+int mstep_gauss_diag(int K, int d, int tied, const double* stat, int F, double* mu, double* lam,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t mstep_lingauss_workspace(int K, int c, int o);
+int mstep_lingauss(int K, int c, int o, int tied, const double* stat, int F, const int32_t* stat_idx, int Dp,
+                   double* A, double* lmbda, void* workspace, size_t workspace_bytes, int32_t* info, cudaStream_t st);
+
+}  // namespace mimo

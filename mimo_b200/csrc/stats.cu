@@ -1,0 +1,283 @@
+// Weighted sufficient statistics, CUDA-core path, sm_100a.
+//
+//   stat[k][f] += sum_n r[k][n] * zt[n][fi[f]] * zt[n][fj[f]]        zt = [z ; 1]
+//
+// soft (mean-field): a register-tiled GEMM  R (K x points) . Phi (points x F)  whose
+//   B operand -- the feature tile Phi -- is generated in shared memory from the point
+//   tile, so neither the one-hot / responsibility-weighted copies of the data nor the
+//   per-point outer products of the reference ever exist.  FP32 partial sums are
+//   folded into FP64 every 1024 points; the CTA's slab total is added to the global
+//   FP64 buffer with one atomic per element.
+// hard (Gibbs): counting sort of the point indices by label, then a segmented dense
+//   reduction per component with FP64 accumulation in registers.
+//
+// Reference call sites replaced: distributions/gaussian.py:491-505, 819-832;
+// lingauss.py:306-325; categorical.py:35-46; utils/data.py:160-169.
+#include "common.cuh"
+
+namespace mimo {
+
+constexpr int SS_THREADS = 256;
+constexpr int SS_BK = 64;     // components per CTA tile   (16 thread rows x 4)
+constexpr int SS_BF = 128;    // features per CTA tile     (16 thread cols x 8)
+constexpr int SS_BP = 32;     // points per inner block
+constexpr int SS_FOLD = 32;   // inner blocks between FP32 -> FP64 folds
+
+template <typename T>
+__global__ void __launch_bounds__(SS_THREADS)
+stats_soft_kernel(const T* __restrict__ Z, int64_t N, int D, int64_t ldz,
+                  const T* __restrict__ resp, int64_t ldr, int K,
+                  const int32_t* __restrict__ fi, const int32_t* __restrict__ fj, int F,
+                  double* __restrict__ stat, int64_t slab) {
+    constexpr int AS = SS_BK + 4, BS = SS_BF + 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ZTS = D + 2;                                   // zt row stride
+    T* Zt = reinterpret_cast<T*>(smem_raw);                  // [BP][ZTS]
+    T* As = Zt + SS_BP * ZTS + ((4 - (SS_BP * ZTS) % 4) % 4);  // [BP][AS]  r, transposed (keep 16B alignment)
+    T* Bs = As + SS_BP * AS;                                 // [BP][BS]  generated features
+    __shared__ int sfi[SS_BF], sfj[SS_BF];
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int f0 = blockIdx.x * SS_BF, k0 = blockIdx.y * SS_BK;
+    const int64_t p_begin = (int64_t)blockIdx.z * slab;
+    const int64_t p_end = min(N, p_begin + slab);
+    if (tid < SS_BF) {
+        bool ok = f0 + tid < F;
+        sfi[tid] = ok ? fi[f0 + tid] : D;
+        sfj[tid] = ok ? fj[f0 + tid] : D;
+    }
+
+    float  accf[4][8];
+    double accd[4][8];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int n = 0; n < 8; ++n) { accf[m][n] = 0.f; accd[m][n] = 0.0; }
+
+    int fold = 0;
+    for (int64_t p0 = p_begin; p0 < p_end; p0 += SS_BP) {
+        __syncthreads();
+        for (int idx = tid; idx < SS_BP * D; idx += SS_THREADS) {
+            int p = idx / D, j = idx - p * D;
+            Zt[p * ZTS + j] = (p0 + p < p_end) ? Z[(p0 + p) * ldz + j] : T(0);
+        }
+        if (tid < SS_BP) Zt[tid * ZTS + D] = T(1);
+        for (int idx = tid; idx < SS_BP * SS_BK; idx += SS_THREADS) {
+            int kk = idx / SS_BP, p = idx - kk * SS_BP;
+            bool ok = (k0 + kk < K) && (p0 + p < p_end);
+            As[p * AS + kk] = ok ? resp[(int64_t)(k0 + kk) * ldr + p0 + p] : T(0);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < SS_BP * SS_BF; idx += SS_THREADS) {
+            int p = idx / SS_BF, f = idx - p * SS_BF;
+            Bs[p * BS + f] = Zt[p * ZTS + sfi[f]] * Zt[p * ZTS + sfj[f]];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int p = 0; p < SS_BP; ++p) {
+            T a[4], b[8];
+            lds_vec<T, 4>(a, As + p * AS + ty * 4);
+            lds_vec<T, 8>(b, Bs + p * BS + tx * 8);
+            if constexpr (sizeof(T) == 4) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) accf[m][n] = fmaf(a[m], b[n], accf[m][n]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) accd[m][n] = fma((double)a[m], (double)b[n], accd[m][n]);
+            }
+        }
+        if constexpr (sizeof(T) == 4) {
+            if (++fold == SS_FOLD) {
+                fold = 0;
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) { accd[m][n] += (double)accf[m][n]; accf[m][n] = 0.f; }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        int k = k0 + ty * 4 + m;
+        if (k >= K) continue;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            int f = f0 + tx * 8 + n;
+            if (f < F) atomicAdd(&stat[(int64_t)k * F + f], accd[m][n] + (double)accf[m][n]);
+        }
+    }
+}
+
+int stats_soft(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K,
+               const int32_t* fi, const int32_t* fj, int F, double* stat, cudaStream_t st) {
+    MIMO_CHECK_ARG(dtype == MIMO_F32 || dtype == MIMO_F64, "dtype");
+    MIMO_CHECK_ARG(Z && resp && fi && fj && stat, "null pointer");
+    MIMO_CHECK_ARG(N >= 0 && D >= 1 && K >= 1 && F >= 1 && ldz >= D && ldr >= N, "shape");
+    if (N == 0) return MIMO_OK;
+    size_t es = dtype == MIMO_F32 ? 4 : 8;
+    size_t smem = ((size_t)SS_BP * (D + 2) + 4 + SS_BP * (SS_BK + 4) + SS_BP * (SS_BF + 4)) * es;
+    if (smem > 200 * 1024) { set_error("soft stats: D=%d too large for shared memory", D); return MIMO_EUNSUPPORTED; }
+    int ft = cdiv(F, SS_BF), kt = cdiv(K, SS_BK);
+    int64_t want = (int64_t)4 * sm_count() / ((int64_t)ft * kt);
+    int64_t slabs = std::max<int64_t>(1, std::min<int64_t>(want, cdiv(N, SS_BP * 8)));
+    slabs = std::min<int64_t>(slabs, 65535);
+    int64_t slab = ((N + slabs - 1) / slabs + SS_BP - 1) / SS_BP * SS_BP;
+    slabs = cdiv(N, slab);
+    dim3 grid(ft, kt, (unsigned)slabs);
+    if (dtype == MIMO_F32) {
+        auto kern = stats_soft_kernel<float>;
+        MIMO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, SS_THREADS, smem, st>>>((const float*)Z, N, D, ldz, (const float*)resp, ldr, K, fi, fj, F, stat, slab);
+    } else {
+        auto kern = stats_soft_kernel<double>;
+        MIMO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, SS_THREADS, smem, st>>>((const double*)Z, N, D, ldz, (const double*)resp, ldr, K, fi, fj, F, stat, slab);
+    }
+    MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
+}
+
+// ---- hard statistics: counting sort + segmented reduction ------------------------
+
+__global__ void label_hist_kernel(const int32_t* __restrict__ labels, int64_t N, int K,
+                                  int32_t* __restrict__ counts, int32_t* __restrict__ bad) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) {
+        int z = labels[i];
+        if (z < 0 || z >= K) atomicExch(bad, 1);
+        else atomicAdd(&counts[z], 1);
+    }
+}
+
+// single block: exclusive scan of counts -> offsets[K+1]; cursor := offsets
+__global__ void label_scan_kernel(const int32_t* __restrict__ counts, int K, int32_t* __restrict__ offsets,
+                                  int32_t* __restrict__ cursor) {
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int k = 0; k < K; ++k) { offsets[k] = run; cursor[k] = run; run += counts[k]; }
+        offsets[K] = run;
+    }
+}
+
+__global__ void label_scatter_kernel(const int32_t* __restrict__ labels, int64_t N, int K,
+                                     int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) {
+        int z = labels[i];
+        if (z >= 0 && z < K) perm[atomicAdd(&cursor[z], 1)] = (int32_t)i;
+    }
+}
+
+constexpr int SH_THREADS = 256;
+constexpr int SH_SEG = 2048;    // points of one component per CTA
+constexpr int SH_PT = 32;       // gathered rows per shared-memory tile
+constexpr int SH_MAXFT = 34;    // features per thread when F > 256  (F <= 8704)
+
+template <typename T>
+__global__ void __launch_bounds__(SH_THREADS)
+stats_hard_kernel(const T* __restrict__ Z, int D, int64_t ldz, const int32_t* __restrict__ perm,
+                  const int32_t* __restrict__ offsets,
+                  const int32_t* __restrict__ fi, const int32_t* __restrict__ fj, int F,
+                  double* __restrict__ stat) {
+    const int k = blockIdx.y;
+    const int beg = offsets[k] + blockIdx.x * SH_SEG;
+    const int end = min(offsets[k + 1], beg + SH_SEG);
+    if (beg >= end) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ZTS = D + 2;
+    T* Zt = reinterpret_cast<T*>(smem_raw);                  // [PT][ZTS]
+    const int tid = threadIdx.x;
+    const int Fc = min(F, SH_THREADS);
+    const int G = (F >= SH_THREADS) ? 1 : SH_THREADS / F;    // point groups working in parallel
+    const int g = tid / Fc, fl = tid - g * Fc;
+    const bool active = g < G;
+    const int nft = (F + SH_THREADS - 1) / SH_THREADS;       // features per thread
+    int myi[SH_MAXFT], myj[SH_MAXFT];
+    double acc[SH_MAXFT];
+#pragma unroll
+    for (int t = 0; t < SH_MAXFT; ++t) {
+        int f = fl + t * SH_THREADS;
+        bool ok = active && t < nft && f < F;
+        myi[t] = ok ? fi[f] : D; myj[t] = ok ? fj[f] : D; acc[t] = 0.0;
+    }
+    for (int p0 = beg; p0 < end; p0 += SH_PT) {
+        int np = min(SH_PT, end - p0);
+        __syncthreads();
+        for (int idx = tid; idx < np * D; idx += SH_THREADS) {
+            int p = idx / D, j = idx - p * D;
+            Zt[p * ZTS + j] = Z[(int64_t)perm[p0 + p] * ldz + j];
+        }
+        if (tid < np) Zt[tid * ZTS + D] = T(1);
+        __syncthreads();
+        if (active) {
+            for (int p = g; p < np; p += G) {
+                const T* row = Zt + p * ZTS;
+                if (nft == 1) {
+                    acc[0] += (double)row[myi[0]] * (double)row[myj[0]];
+                } else {
+#pragma unroll
+                    for (int t = 0; t < SH_MAXFT; ++t)
+                        if (t < nft) acc[t] += (double)row[myi[t]] * (double)row[myj[t]];
+                }
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int t = 0; t < SH_MAXFT; ++t) {
+            int f = fl + t * SH_THREADS;
+            if (t < nft && f < F) atomicAdd(&stat[(int64_t)k * F + f], acc[t]);
+        }
+    }
+}
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+size_t stats_hard_workspace(int64_t N, int K) {
+    return align256((size_t)(K + 1) * 4) * 3 + 256 + align256((size_t)N * 4);
+}
+
+int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const int32_t* labels, int K,
+               const int32_t* fi, const int32_t* fj, int F, double* stat,
+               void* workspace, size_t workspace_bytes, bool check, cudaStream_t st) {
+    MIMO_CHECK_ARG(dtype == MIMO_F32 || dtype == MIMO_F64, "dtype");
+    MIMO_CHECK_ARG(Z && labels && fi && fj && stat && workspace, "null pointer");
+    MIMO_CHECK_ARG(N >= 0 && N < (int64_t)2147483647 && D >= 1 && K >= 1 && F >= 1 && ldz >= D, "shape");
+    MIMO_CHECK_ARG(workspace_bytes >= stats_hard_workspace(N, K), "workspace too small");
+    if (F > SH_MAXFT * SH_THREADS) { set_error("hard stats: F=%d too large", F); return MIMO_EUNSUPPORTED; }
+    if (N == 0) return MIMO_OK;
+    char* ws = (char*)workspace;
+    size_t seg = align256((size_t)(K + 1) * 4);
+    int32_t* counts = (int32_t*)ws;
+    int32_t* offsets = (int32_t*)(ws + seg);
+    int32_t* cursor = (int32_t*)(ws + 2 * seg);
+    int32_t* bad = (int32_t*)(ws + 3 * seg);
+    int32_t* perm = (int32_t*)(ws + 3 * seg + 256);
+    MIMO_CUDA(cudaMemsetAsync(ws, 0, 3 * seg + 256, st));
+    int grid = cdiv(N, 256);
+    label_hist_kernel<<<grid, 256, 0, st>>>(labels, N, K, counts, bad);
+    label_scan_kernel<<<1, 32, 0, st>>>(counts, K, offsets, cursor);
+    label_scatter_kernel<<<grid, 256, 0, st>>>(labels, N, K, cursor, perm);
+    MIMO_LAUNCH_CHECK();
+    if (check) {
+        int32_t hbad = 0;
+        MIMO_CUDA(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, st));
+        MIMO_CUDA(cudaStreamSynchronize(st));
+        if (hbad) { set_error("labels outside [0, K)"); return MIMO_EINVAL; }
+    }
+    size_t es = dtype == MIMO_F32 ? 4 : 8;
+    size_t smem = (size_t)SH_PT * (D + 2) * es;
+    dim3 g2(cdiv(N, SH_SEG), K);
+    if (dtype == MIMO_F32)
+        stats_hard_kernel<float><<<g2, SH_THREADS, smem, st>>>((const float*)Z, D, ldz, perm, offsets, fi, fj, F, stat);
+    else
+        stats_hard_kernel<double><<<g2, SH_THREADS, smem, st>>>((const double*)Z, D, ldz, perm, offsets, fi, fj, F, stat);
+    MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
+}
+
+}  // namespace mimo

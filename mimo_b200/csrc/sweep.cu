@@ -1,0 +1,131 @@
+// One sweep over resident data: E-step -> softmax / label draw -> statistics, walked in
+// point chunks through an L2-sized (K, chunk) scratch so the (K, N) arrays of the
+// reference (mixtures/gmm.py:67-75, utils/data.py:160-169) are never built.
+// CUDA-core path; the tcgen05 path (tc_*.cu) replaces the inner three launches where
+// it supports the shape.
+#include "common.cuh"
+#include "internal.h"
+
+namespace mimo {
+
+static size_t a256(size_t x) { return (x + 255) / 256 * 256; }
+
+// points per chunk: keep the (K, chunk) scratch around 32 MB so every pass over it hits L2
+int64_t sweep_chunk_points(int dtype, int64_t N, int K) {
+    size_t es = dtype == MIMO_F32 ? 4 : 8;
+    int64_t c = (int64_t)((32u << 20) / ((size_t)K * es));
+    c = c / 256 * 256;
+    if (c < 1024) c = 1024;
+    if (c > (1 << 20)) c = 1 << 20;
+    int64_t npad = (N + 255) / 256 * 256;
+    return c < npad ? c : (npad > 0 ? npad : 256);
+}
+
+size_t sweep_workspace(int dtype, int64_t N, int K, int hard) {
+    size_t es = dtype == MIMO_F32 ? 4 : 8;
+    int64_t c = sweep_chunk_points(dtype, N, K);
+    size_t b = a256((size_t)K * c * es) + a256((size_t)c * 4);
+    if (hard) b += a256(stats_hard_workspace(c, K));
+    return b;
+}
+
+int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int64_t ldz,
+          const void* op_a, const void* op_b, const void* cst, int K, int Rp, int Dpp,
+          const int32_t* fi, const int32_t* fj, int F,
+          const void* uniforms, uint64_t seed, uint64_t point_offset,
+          double* stat, double* lse_sum, int32_t* labels_out, void* lse_out, void* ll_out, int64_t ldo,
+          void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    MIMO_CHECK_ARG(dtype == MIMO_F32 || dtype == MIMO_F64, "dtype");
+    MIMO_CHECK_ARG(family == 0 || family == 1, "family");
+    MIMO_CHECK_ARG(Z && op_a && cst && workspace && (family == 0 || op_b), "null pointer");
+    MIMO_CHECK_ARG(!stat || (fi && fj && F >= 1), "feature tables");
+    MIMO_CHECK_ARG(workspace_bytes >= sweep_workspace(dtype, N, K, hard), "workspace too small");
+    MIMO_CHECK_ARG(!ll_out || ldo >= N, "ldo");
+    const size_t es = dtype == MIMO_F32 ? 4 : 8;
+    const int64_t C = sweep_chunk_points(dtype, N, K);
+    char* ws = (char*)workspace;
+    void* scratch = ws; ws += a256((size_t)K * C * es);
+    int32_t* lab_tmp = (int32_t*)ws; ws += a256((size_t)C * 4);
+    void* hard_ws = ws;
+    const size_t hard_ws_bytes = hard ? stats_hard_workspace(C, K) : 0;
+
+    for (int64_t n0 = 0; n0 < N; n0 += C) {
+        const int64_t nc = (N - n0 < C) ? (N - n0) : C;
+        const char* Zc = (const char*)Z + (size_t)n0 * ldz * es;
+        int rc;
+        if (family == 0) rc = loglik_quad(dtype, Zc, nc, D, ldz, op_a, cst, K, Rp, Dpp, scratch, C, st);
+        else             rc = loglik_diag(dtype, Zc, nc, D, ldz, op_a, op_b, cst, K, scratch, C, st);
+        if (rc) return rc;
+        int flags = (lse_sum ? MIMO_ACC_LSE : 0) | (lse_out ? MIMO_WRITE_LSE : 0)
+                  | (hard ? MIMO_DRAW_LABELS : MIMO_WRITE_RESP);
+        int32_t* lab = labels_out ? labels_out + n0 : lab_tmp;
+        const double* uni = uniforms ? (const double*)uniforms + n0 : nullptr;
+        void* lse_c = lse_out ? (char*)lse_out + (size_t)n0 * es : nullptr;
+        rc = softmax(dtype, scratch, K, nc, C, flags, lse_c, uni, seed, point_offset + (uint64_t)n0, lab, lse_sum, st);
+        if (rc) return rc;
+        if (ll_out)
+            MIMO_CUDA(cudaMemcpy2DAsync((char*)ll_out + (size_t)n0 * es, (size_t)ldo * es, scratch, (size_t)C * es,
+                                        (size_t)nc * es, K, cudaMemcpyDeviceToDevice, st));
+        if (stat) {
+            if (hard) rc = stats_hard(dtype, Zc, nc, D, ldz, lab, K, fi, fj, F, stat, hard_ws, hard_ws_bytes, false, st);
+            else      rc = stats_soft(dtype, Zc, nc, D, ldz, scratch, C, K, fi, fj, F, stat, st);
+            if (rc) return rc;
+        }
+    }
+    return MIMO_OK;
+}
+
+// Host-buffer variant: what bench.py's `e2e` leg and a caller without device memory use.
+int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, int D,
+               const void* op_a_host, const void* op_b_host, const void* cst_host, int K, int Rp, int Dpp,
+               const int32_t* fi_host, const int32_t* fj_host, int F,
+               const void* uniforms_host, uint64_t seed,
+               double* stat_host, double* lse_sum_host, int32_t* labels_host) {
+    MIMO_CHECK_ARG(Z_host && op_a_host && cst_host && fi_host && fj_host && stat_host, "null pointer");
+    const size_t es = dtype == MIMO_F32 ? 4 : 8;
+    const size_t zb = (size_t)N * D * es;
+    const size_t ab = (family == 0 ? (size_t)K * Rp * Dpp : (size_t)K * D) * es;
+    const size_t wsb = sweep_workspace(dtype, N, K, hard);
+    char *dZ = nullptr, *dA = nullptr, *dB = nullptr, *dC = nullptr, *dws = nullptr;
+    int32_t *dfi = nullptr, *dfj = nullptr, *dlab = nullptr;
+    double *dstat = nullptr, *dlse = nullptr, *duni = nullptr;
+    cudaStream_t st = 0;
+    int rc = MIMO_OK;
+    auto body = [&]() -> int {
+        MIMO_CUDA(cudaMalloc(&dZ, zb));
+        MIMO_CUDA(cudaMalloc(&dA, ab));
+        MIMO_CUDA(cudaMalloc(&dC, (size_t)K * es));
+        MIMO_CUDA(cudaMalloc(&dfi, (size_t)F * 4));
+        MIMO_CUDA(cudaMalloc(&dfj, (size_t)F * 4));
+        MIMO_CUDA(cudaMalloc(&dstat, (size_t)K * F * 8));
+        MIMO_CUDA(cudaMalloc(&dlse, 8));
+        MIMO_CUDA(cudaMalloc(&dws, wsb));
+        if (family == 1) { MIMO_CUDA(cudaMalloc(&dB, ab)); MIMO_CUDA(cudaMemcpyAsync(dB, op_b_host, ab, cudaMemcpyHostToDevice, st)); }
+        if (hard) MIMO_CUDA(cudaMalloc(&dlab, (size_t)N * 4));
+        if (uniforms_host) {
+            MIMO_CUDA(cudaMalloc(&duni, (size_t)N * 8));
+            MIMO_CUDA(cudaMemcpyAsync(duni, uniforms_host, (size_t)N * 8, cudaMemcpyHostToDevice, st));
+        }
+        MIMO_CUDA(cudaMemcpyAsync(dZ, Z_host, zb, cudaMemcpyHostToDevice, st));
+        MIMO_CUDA(cudaMemcpyAsync(dA, op_a_host, ab, cudaMemcpyHostToDevice, st));
+        MIMO_CUDA(cudaMemcpyAsync(dC, cst_host, (size_t)K * es, cudaMemcpyHostToDevice, st));
+        MIMO_CUDA(cudaMemcpyAsync(dfi, fi_host, (size_t)F * 4, cudaMemcpyHostToDevice, st));
+        MIMO_CUDA(cudaMemcpyAsync(dfj, fj_host, (size_t)F * 4, cudaMemcpyHostToDevice, st));
+        MIMO_CUDA(cudaMemsetAsync(dstat, 0, (size_t)K * F * 8, st));
+        MIMO_CUDA(cudaMemsetAsync(dlse, 0, 8, st));
+        int r = sweep(dtype, family, hard, dZ, N, D, D, dA, dB, dC, K, Rp, Dpp, dfi, dfj, F, duni, seed, 0,
+                      dstat, dlse, dlab, nullptr, nullptr, 0, dws, wsb, st);
+        if (r) return r;
+        MIMO_CUDA(cudaMemcpyAsync(stat_host, dstat, (size_t)K * F * 8, cudaMemcpyDeviceToHost, st));
+        if (lse_sum_host) MIMO_CUDA(cudaMemcpyAsync(lse_sum_host, dlse, 8, cudaMemcpyDeviceToHost, st));
+        if (hard && labels_host) MIMO_CUDA(cudaMemcpyAsync(labels_host, dlab, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+        MIMO_CUDA(cudaStreamSynchronize(st));
+        return MIMO_OK;
+    };
+    rc = body();
+    cudaFree(dZ); cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dws); cudaFree(dfi); cudaFree(dfj);
+    cudaFree(dlab); cudaFree(dstat); cudaFree(dlse); cudaFree(duni);
+    return rc;
+}
+
+}  // namespace mimo
