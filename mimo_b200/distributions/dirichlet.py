@@ -1,0 +1,162 @@
+"""Gating priors: Dirichlet and truncated stick-breaking (mirrors
+mimo/distributions/dirichlet.py).  These are K-vectors of host state; inside a sweep the
+posterior update, expected log-weights and lower-bound term run in the batched gating
+kernel (mimo_gating_posterior) -- the scalar helpers here serve the object API."""
+import warnings
+
+import numpy as np
+import numpy.random as npr
+from scipy.special import digamma, gammaln, betaln
+
+
+class Dirichlet:
+
+    def __init__(self, dim=None, alphas=None):
+        self.dim = dim
+        self.alphas = alphas
+
+    @property
+    def params(self):
+        return self.alphas
+
+    @params.setter
+    def params(self, values):
+        self.alphas = values
+
+    @property
+    def nat_param(self):
+        return self.std_to_nat(self.params)
+
+    @nat_param.setter
+    def nat_param(self, natparam):
+        self.params = self.nat_to_std(natparam)
+
+    @staticmethod
+    def std_to_nat(params):
+        return params - 1.
+
+    @staticmethod
+    def nat_to_std(natparam):
+        return natparam + 1.
+
+    def mean(self):
+        return self.alphas / np.sum(self.alphas)
+
+    def mode(self):
+        assert np.all(self.alphas > 1.), "Make sure alphas > 1."
+        return (self.alphas - 1.) / (np.sum(self.alphas) - self.dim)
+
+    def rvs(self, size=1):
+        return npr.dirichlet(self.alphas)
+
+    @property
+    def base(self):
+        return 1.
+
+    def log_base(self):
+        return 0.
+
+    def log_partition(self):
+        return np.sum(gammaln(self.alphas)) - gammaln(np.sum(self.alphas))
+
+    def log_likelihood(self, x):
+        return np.sum((self.alphas - 1.) * np.log(x)) - self.log_partition()
+
+    def expected_statistics(self):
+        return digamma(self.alphas) - digamma(np.sum(self.alphas))
+
+    def entropy(self):
+        return self.log_partition() - self.nat_param.dot(self.expected_statistics())
+
+    def cross_entropy(self, dist):
+        return dist.log_partition() - dist.nat_param.dot(self.expected_statistics())
+
+
+class TruncatedStickBreaking:
+    """Ishwaran & James (2001) / Blei & Jordan (2006) truncation."""
+
+    def __init__(self, dim=None, gammas=None, deltas=None):
+        self.dim = dim
+        self.gammas = gammas
+        self.deltas = deltas
+
+    @property
+    def params(self):
+        return self.gammas, self.deltas
+
+    @params.setter
+    def params(self, values):
+        self.gammas, self.deltas = values
+
+    @property
+    def nat_param(self):
+        return self.std_to_nat(self.params)
+
+    @nat_param.setter
+    def nat_param(self, natparam):
+        self.params = self.nat_to_std(natparam)
+
+    @staticmethod
+    def std_to_nat(params):
+        return params[0] - 1., params[1] - 1.
+
+    @staticmethod
+    def nat_to_std(natparam):
+        return natparam[0] + 1., natparam[1] + 1.
+
+    @staticmethod
+    def _sticks_to_probs(betas):
+        probs = np.empty(betas.shape)
+        probs[0] = betas[0]
+        probs[1:] = betas[1:] * np.cumprod(1. - betas[:-1])
+        return probs
+
+    def mean(self):
+        betas = np.hstack((self.gammas[:-1] / (self.gammas[:-1] + self.deltas[:-1]), 1.))
+        return self._sticks_to_probs(betas)
+
+    def mode(self):
+        betas = np.ones((self.dim,))
+        for k in range(self.dim - 1):
+            g, d = self.gammas[k], self.deltas[k]
+            if g > 1. and d > 1.:
+                betas[k] = (g - 1.) / (g + d - 2.)
+            elif (g == 1. and d == 1.) or (g < 1. and d < 1.) or (g > 1. and d <= 1.):
+                betas[k] = 1.
+            elif g <= 1. and d > 1.:
+                betas[k] = 0.
+            else:
+                warnings.warn("Mode of Dirichlet process not defined")
+                raise ValueError
+        return self._sticks_to_probs(betas)
+
+    def rvs(self, size=1, truncate=True):
+        betas = np.hstack((npr.beta(self.gammas[:-1], self.deltas[:-1]), 1.))
+        return self._sticks_to_probs(betas)
+
+    @property
+    def base(self):
+        return 1.
+
+    def log_base(self):
+        return 0.
+
+    def log_partition(self):
+        return np.sum(betaln(self.gammas, self.deltas))
+
+    def log_likelihood(self, x):
+        raise NotImplementedError
+
+    def expected_statistics(self):
+        both = digamma(self.gammas + self.deltas)
+        return digamma(self.gammas) - both, digamma(self.deltas) - both
+
+    def _dot(self, nat):
+        e_stick, e_rest = self.expected_statistics()
+        return nat[0].dot(e_stick) + nat[1].dot(e_rest)
+
+    def entropy(self):
+        return self.log_partition() - self._dot(self.nat_param)
+
+    def cross_entropy(self, dist):
+        return dist.log_partition() - self._dot(dist.nat_param)

@@ -1,0 +1,195 @@
+"""Device-resident sweep session shared by the GMM and ILR drivers.
+
+One session = data z = [x | y] uploaded once, one packed operand buffer (W | S,T and cst)
+that every model part writes its block into, one packed FP64 statistics buffer, and the
+fused sweep kernel between them:
+
+    statistics --(batched posterior kernels)--> operands --(mimo_sweep)--> statistics
+
+Mean-field: the data + label terms of the lower bound equal sum_n logsumexp_k (E log joint)
+whenever the responsibilities are the E-step of the current posterior, so the
+sweep returns that scalar and the reference's second E-step per iteration
+(mixtures/gmm.py:338-339) is not needed.
+"""
+import numpy as np
+import numpy.random as npr
+import torch
+
+from .. import _engine as E
+from ..distributions.bayesian import MEANFIELD, GIBBS, MAP
+
+
+class Part:
+    """a conjugate wrapper plus where its variables sit in zt and its rows in W."""
+
+    def __init__(self, wrapper, stat_idx=None, col_map=None):
+        self.w = wrapper
+        self.stat_idx, self.col_map = stat_idx, col_map
+
+    def layout(self, Dp, row_off):
+        return dict(stat_idx=self.stat_idx, col_map=self.col_map, Dp=Dp, row_off=row_off)
+
+
+class Session:
+
+    def __init__(self, z, K, gating, parts, family, precision=None, comm=None):
+        self.precision = precision or E.default_precision()
+        self.K, self.gating, self.parts, self.family = K, gating, parts, family
+        self.Z = z if isinstance(z, torch.Tensor) else E.to_dev(np.ascontiguousarray(z), E.tdtype(self.precision))
+        self.N, self.D = self.Z.shape
+        self.feats = E.quad_features(self.D) if family == 'quad' else E.diag_features(self.D)
+        self.F = self.feats.F
+        self.count_feature = self.F - 1
+        self.comm = comm                     # optional sharded.Communicator: all-reduce of stat / lse
+        self._ops = {}
+        self._bufs = {}
+        self.stat = E.zeros((K, self.F))
+        self.lse_sum = E.zeros((1,))
+        self.gating_prior = gating._prior_dev() if gating is not None else None
+        self.part_priors = [p.w._prior_dev() for p in parts]
+        self.last = None
+
+    # -- buffers ---------------------------------------------------------------------------
+    def ops(self, mode):
+        if mode not in self._ops:
+            if self.family == 'quad':
+                rows = sum(p.w._rows(mode) for p in self.parts)
+                self._ops[mode] = E.QuadOperands(self.K, self.D, rows, self.precision)
+            else:
+                self._ops[mode] = E.DiagOperands(self.K, self.D, self.precision)
+        return self._ops[mode]
+
+    def buf(self, hard):
+        if hard not in self._bufs:
+            self._bufs[hard] = E.SweepBuffers(self.N, self.K, self.F, self.precision, hard)
+        return self._bufs[hard]
+
+    # -- statistics from explicit labels / responsibilities -------------------------------------
+    def stats_from_labels(self, labels):
+        lab = E.to_dev(np.asarray(labels, dtype=np.int32), torch.int32)
+        self.stat = self._reduce(E.stats_hard(self.Z, lab, self.K, self.feats, self.precision))
+        return self.stat
+
+    def stats_from_resp(self, resp):
+        R = resp if isinstance(resp, torch.Tensor) else E.to_dev(resp, E.tdtype(self.precision))
+        self.stat = self._reduce(E.stats_soft(self.Z, R, self.feats, self.precision))
+        return self.stat
+
+    def _reduce(self, stat, lse=None):
+        if self.comm is not None:
+            self.comm.allreduce_stats(stat, lse)
+        return stat
+
+    # -- operands --------------------------------------------------------------------------
+    def update_from_stats(self, mode, variates=None, gating_variates=None, want_lik=False):
+        """gating + every part: posterior update from self.stat, operands into ops(mode)."""
+        ops = self.ops(mode)
+        outs = {}
+        if self.gating is not None:
+            outs['gating'] = self.gating._update(self.stat, self.F, self.count_feature, mode, ops=ops,
+                                                 variates=gating_variates, prior_dev=self.gating_prior)
+        else:
+            ops.cst.zero_()
+        row = 0
+        outs['parts'] = []
+        for i, p in enumerate(self.parts):
+            lay = p.layout(self.D + 1, row)
+            outs['parts'].append(p.w._update(self.stat, self.F, lay, mode, ops=ops,
+                                             variates=None if variates is None else variates[i],
+                                             prior_dev=self.part_priors[i], want_lik=want_lik))
+            row += p.w._rows(mode) if self.family == 'quad' else 0
+        self.last = outs
+        return ops, outs
+
+    def operands_from_posterior(self, gating_mode=MEANFIELD):
+        """operands of the CURRENT posteriors (no new statistics)."""
+        ops = self.ops(MEANFIELD)
+        zero = E.zeros((self.K, self.F))
+        infos = []
+        if self.gating is not None:
+            pa, pb = self.gating._prior_arrays(self.gating.posterior)
+            g = self.gating._update(zero, self.F, self.count_feature, gating_mode, ops=ops,
+                                    prior_dev=(E.to_dev(pa), E.to_dev(pb) if pb is not None else None))
+            infos.append(g['info'])
+        else:
+            ops.cst.zero_()
+        row = 0
+        for p in self.parts:
+            infos.append(p.w._posterior_operands(ops, p.layout(self.D + 1, row)))
+            row += p.w._rows(MEANFIELD) if self.family == 'quad' else 0
+        for i in infos:
+            i.check()
+        return ops
+
+    def operands_from_likelihood(self, log_probs=None):
+        """operands of the explicit likelihood parameters + log gating probabilities."""
+        ops = self.ops(GIBBS)
+        if log_probs is None:
+            ops.cst.zero_()
+        else:
+            E.set_log_weights(ops, log_probs)
+        row = 0
+        for p in self.parts:
+            p.w._likelihood_operands(ops, p.layout(self.D + 1, row)).check()
+            row += p.w._rows(GIBBS) if self.family == 'quad' else 0
+        return ops
+
+    # -- the sweep -------------------------------------------------------------------------
+    def sweep(self, ops, hard, uniforms=None, seed=0, ll_out=None):
+        buf = self.buf(hard)
+        u = None
+        if uniforms is not None:
+            u = uniforms if isinstance(uniforms, torch.Tensor) else E.to_dev(np.asarray(uniforms).reshape(-1))
+        offset = self.comm.point_offset if self.comm is not None else 0
+        E.sweep(self.Z, ops, self.feats, buf, uniforms=u, seed=seed, offset=offset, ll_out=ll_out)
+        self._reduce(buf.stat, buf.lse_sum)
+        self.stat, self.lse_sum = buf.stat, buf.lse_sum
+        return buf
+
+    def loglik(self, ops):
+        return E.loglik(self.Z, ops)
+
+    # -- scalars ---------------------------------------------------------------------------
+    def lower_bound(self, outs):
+        """gating term + component terms (from the posterior kernels that produced the
+        operands) + sum_n lse_n (from the sweep that used them).  One device->host read."""
+        terms = [self.lse_sum.reshape(1)]
+        if 'gating' in outs:
+            terms.append(outs['gating']['vlb'].reshape(1))
+        for o in outs['parts']:
+            terms.append(o['vlb'].sum().reshape(1))
+        return float(torch.cat(terms).sum().item())
+
+    def check(self, outs):
+        if 'gating' in outs:
+            outs['gating']['info'].check()
+        for o in outs['parts']:
+            o['info'].check()
+
+    def store(self, outs, mode, set_probs=True):
+        """download posterior (and sampled / mode likelihood) parameters into the model."""
+        if 'gating' in outs:
+            self.gating._store(outs['gating'], set_probs=set_probs)
+        for p, o in zip(self.parts, outs['parts']):
+            p.w._store(o, mode)
+
+    def counts_host(self):
+        return E.to_host(self.stat[:, self.count_feature])
+
+    def draw_gibbs_variates(self):
+        """host draws from the global numpy.random stream in the reference's order:
+        every part (per component), then the gating."""
+        counts = self.counts_host()
+        stat_host = E.to_host(self.stat) if self.family == 'diag' else None
+        var = []
+        for p in self.parts:
+            var.append(p.w._draw_variates(counts, stat_host) if self.family == 'diag' else p.w._draw_variates(counts))
+        gvar = self.gating._draw_variates(counts) if self.gating is not None else None
+        return var, gvar
+
+
+def random_responsibilities(K, N):
+    """npr.rand(K, N) normalised over components (mixtures/gmm.py:265-267)."""
+    resp = npr.rand(K, N)
+    resp /= np.sum(resp, axis=0)
+    return resp

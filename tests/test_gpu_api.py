@@ -1,0 +1,360 @@
+"""The mimo.mixtures / mimo.distributions API of mimo_b200 against the golden fixtures made
+from the unmodified reference (tests/golden, oracle/make_golden.py) -- whole trajectories:
+constructors, Gibbs chains replayed from the same numpy.random seed, mean-field lower
+bounds, EM log-likelihoods, predictions.  GPU only.
+
+Tolerances: fp64 mode 1e-8 relative on everything (1e-9 on single kernels is checked in
+test_gpu_kernels.py; trajectories accumulate a few ulps per sweep), fp32 mode 1e-4.
+"""
+import os
+
+import numpy as np
+import numpy.random as npr
+import pytest
+
+from oracle import mimo_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+TOL = {'fp32': 2e-4, 'fp64': 1e-8}
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLD, name + '.npz')))
+
+
+def close(a, b, tol, what=''):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(1.0, float(np.max(np.abs(b))))
+    assert np.allclose(a, b, rtol=tol, atol=tol * scale), \
+        '%s: max abs err %.3e (scale %.3e, tol %.1e)' % (what, float(np.max(np.abs(a - b))), scale, tol)
+
+
+@pytest.fixture(params=['fp64', 'fp32'])
+def precision(request):
+    import mimo_b200
+    mimo_b200.set_default_precision(request.param)
+    yield request.param
+    mimo_b200.set_default_precision('fp32')
+
+
+def make_gating(g, K):
+    from mimo_b200.distributions import (Dirichlet, TruncatedStickBreaking, CategoricalWithDirichlet,
+                                         CategoricalWithStickBreaking)
+    if 'gate_alphas0' in g:
+        return CategoricalWithDirichlet(K, Dirichlet(K, g['gate_alphas0']))
+    return CategoricalWithStickBreaking(K, TruncatedStickBreaking(K, g['gate_gammas0'], g['gate_deltas0']))
+
+
+def make_gmm(g):
+    from mimo_b200.distributions import StackedNormalWisharts, StackedGaussiansWithNormalWisharts
+    from mimo_b200.mixtures import BayesianMixtureOfGaussians
+    K, d = int(g['K']), int(g['d'])
+    prior = StackedNormalWisharts(K, d, g['mus0'], g['kappas0'], g['psis0'], g['nus0'])
+    comp = StackedGaussiansWithNormalWisharts(K, d, prior=prior)
+    return BayesianMixtureOfGaussians(gating=make_gating(g, K), components=comp)
+
+
+@pytest.mark.parametrize('name', ['gmm_toy_vi', 'gmm_toy_vi_stick', 'gmm_d16_vi_stick'])
+def test_gmm_meanfield_trajectory(name, precision):
+    g = load(name)
+    model = make_gmm(g)
+    T = int(g['iters'])
+    npr.seed(int(g['seed']))
+    vlb = model.meanfield_coordinate_descent(g['obs'], maxiter=T, tol=0., progress_bar=False)
+    tol = TOL[precision]
+    close(vlb, g['vlb'], tol, 'lower bound')
+    assert np.all(np.diff(vlb) >= -1e-6 * abs(vlb[-1]))       # "vlb monoton?" of the examples
+    for key, ref in zip(model.components.posterior.params, ('mus', 'kappas', 'psis', 'nus')):
+        close(key, g[f'post_{ref}_{T - 1}'], 10 * tol, 'posterior ' + ref)
+    if 'gate_alphas0' in g:
+        close(model.gating.posterior.alphas, g[f'gate_alphas_{T - 1}'], 10 * tol, 'alphas')
+    else:
+        close(model.gating.posterior.gammas, g[f'gate_gammas_{T - 1}'], 10 * tol, 'gammas')
+        close(model.gating.posterior.deltas, g[f'gate_deltas_{T - 1}'], 10 * tol, 'deltas')
+    close(model.expected_log_complete_likelihood(g['obs']), g[f'ell_{T - 1}'], 10 * tol, 'E log joint')
+    resp = model.expected_responsibilities(g['obs'])
+    close(resp, g[f'resp_{T - 1}'], 50 * tol, 'responsibilities')
+    # the public lower bound for explicit responsibilities agrees with the fused one
+    close(model.variational_lowerbound(g['obs'], g[f'resp_{T - 1}']), g['vlb'][-1], 10 * tol, 'public vlb')
+
+
+@pytest.mark.parametrize('name', ['gmm_toy_gibbs', 'gmm_d16_gibbs_stick'])
+def test_gmm_gibbs_chain_replays_reference(name):
+    """Same numpy.random seed => the reference's chain: labels, sampled parameters, posteriors."""
+    import mimo_b200
+    mimo_b200.set_default_precision('fp64')
+    try:
+        g = load(name)
+        model = make_gmm(g)
+        T = int(g['sweeps'])
+        npr.seed(int(g['seed']))
+        model.resample(g['obs'], init_labels='random', maxiter=T, progress_bar=False)
+        assert model.labels_.dtype == np.int32
+        assert np.mean(model.labels_ == g[f'labels_{T - 1}']) == 1.0
+        close(model.components.likelihood.mus, g[f'lik_mus_{T - 1}'], 1e-7, 'sampled mus')
+        close(model.components.likelihood.lmbdas, g[f'lik_lmbdas_{T - 1}'], 1e-7, 'sampled lmbdas')
+        close(model.gating.likelihood.probs, g[f'probs_{T - 1}'], 1e-9, 'sampled probs')
+        for key, ref in zip(model.components.posterior.params, ('mus', 'kappas', 'psis', 'nus')):
+            close(key, g[f'post_{ref}_{T - 1}'], 1e-8, 'posterior ' + ref)
+        # resample_labels: (log_prob, labels) of the current parameters with the next uniforms
+        npr.seed(123)
+        u = npr.random((1, len(g['obs'])))
+        npr.seed(123)
+        log_prob, labels = model.resample_labels(g['obs'])
+        close(log_prob, g[f'log_prob_{T - 1}'], 1e-8, 'log_prob')
+        assert np.array_equal(labels, orc.sample_discrete_from_log(g[f'log_prob_{T - 1}'], u))
+    finally:
+        mimo_b200.set_default_precision('fp32')
+
+
+def test_gmm_gibbs_fp32_stays_on_the_reference_chain():
+    import mimo_b200
+    mimo_b200.set_default_precision('fp32')
+    g = load('gmm_toy_gibbs')
+    model = make_gmm(g)
+    T = int(g['sweeps'])
+    npr.seed(int(g['seed']))
+    model.resample(g['obs'], init_labels='random', maxiter=T, progress_bar=False)
+    assert np.mean(model.labels_ == g[f'labels_{T - 1}']) > 0.99
+    close(model.components.likelihood.mus, g[f'lik_mus_{T - 1}'], 5e-3, 'sampled mus (fp32)')
+
+
+def make_dgmm(g, bug_compat):
+    from mimo_b200.distributions import StackedNormalGammas, StackedGaussiansWithNormalGammas
+    from mimo_b200.mixtures import BayesianMixtureOfGaussians
+    K, d = int(g['K']), int(g['d'])
+    prior = StackedNormalGammas(K, d, g['mus0'], g['kappas0'], g['alphas0'], g['betas0'])
+    comp = StackedGaussiansWithNormalGammas(K, d, prior=prior, bug_compat=bug_compat)
+    return BayesianMixtureOfGaussians(gating=make_gating(g, K), components=comp)
+
+
+def test_dgmm_gibbs_chain_bug_compat():
+    """The reference's diagonal-mixture chain (its stacked alpha/beta setters are broken:
+    SURVEY q1) is reproduced with bug_compat=True; the default gives the textbook posterior."""
+    import mimo_b200
+    mimo_b200.set_default_precision('fp64')
+    try:
+        g = load('dgmm_gibbs')
+        T = int(g['sweeps'])
+        model = make_dgmm(g, bug_compat=True)
+        npr.seed(int(g['seed']))
+        model.resample(g['obs'], init_labels='random', maxiter=T, progress_bar=False)
+        assert np.array_equal(model.labels_, g[f'labels_{T - 1}'])
+        close(model.components.likelihood.mus, g[f'lik_mus_{T - 1}'], 1e-8, 'sampled mus')
+        close(model.components.likelihood.lmbdas_diags, g[f'lik_lmbdas_diags_{T - 1}'], 1e-8, 'sampled lmbdas')
+        close(model.components.posterior.alphas, g[f'bug_alphas_{T - 1}'], 1e-12, 'bug-compat alphas')
+        # textbook update from the same labels
+        model2 = make_dgmm(g, bug_compat=False)
+        labels_prev = g[f'labels_{T - 2}'] if T > 1 else g['labels_init']
+        from mimo_b200.utils.data import one_hot
+        model2.components.meanfield_update(g['obs'], one_hot(labels_prev, int(g['K'])))
+        for key, ref in zip(model2.components.posterior.params, ('mus', 'kappas', 'alphas', 'betas')):
+            close(key, g[f'post_{ref}_{T - 1}'], 1e-9, 'NG posterior ' + ref)
+    finally:
+        mimo_b200.set_default_precision('fp32')
+
+
+def test_dgmm_meanfield_bug_compat(precision):
+    g = load('dgmm_vi_bugcompat')
+    model = make_dgmm(g, bug_compat=True)
+    T = int(g['iters'])
+    npr.seed(int(g['seed']))
+    vlb = model.meanfield_coordinate_descent(g['obs'], maxiter=T, tol=0., progress_bar=False)
+    close(vlb, g['vlb'], TOL[precision], 'diag lower bound')
+    close(model.components.posterior.mus, g[f'post_mus_{T - 1}'], 10 * TOL[precision], 'diag posterior mus')
+    close(model.expected_responsibilities(g['obs']), g[f'resp_{T - 1}'], 50 * TOL[precision], 'diag resp')
+
+
+def make_ilr(g):
+    from mimo_b200.distributions import (StackedNormalWisharts, StackedGaussiansWithNormalWisharts,
+                                         StackedMatrixNormalWisharts, TiedMatrixNormalWisharts,
+                                         StackedLinearGaussiansWithMatrixNormalWisharts,
+                                         TiedLinearGaussiansWithMatrixNormalWisharts)
+    from mimo_b200.mixtures import BayesianMixtureOfLinearGaussians
+    K, din, o, tied = int(g['K']), int(g['din']), int(g['o']), bool(g['tied'])
+    c = din + 1
+    # construction order and RNG consumption as in examples/ilr/evaluate_sine.py:88-123
+    basis = StackedGaussiansWithNormalWisharts(K, din, prior=StackedNormalWisharts(
+        K, din, g['b_mus0'], g['b_kappas0'], g['b_psis0'], g['b_nus0']))
+    pcls = TiedMatrixNormalWisharts if tied else StackedMatrixNormalWisharts
+    mcls = TiedLinearGaussiansWithMatrixNormalWisharts if tied else StackedLinearGaussiansWithMatrixNormalWisharts
+    models = mcls(K, c, o, pcls(K, c, o, g['m_Ms0'], g['m_Ks0'], g['m_psis0'], g['m_nus0']), affine=True)
+    gating = make_gating(g, K)
+    return BayesianMixtureOfLinearGaussians(K, din, o, gating=gating, basis=basis, models=models)
+
+
+@pytest.mark.parametrize('name', ['ilr_tied', 'ilr_stacked', 'ilr_stacked_o2'])
+def test_ilr_gibbs_then_meanfield_replays_reference(name):
+    import mimo_b200
+    mimo_b200.set_default_precision('fp64')
+    try:
+        g = load(name)
+        S, T = int(g['sweeps']), int(g['iters'])
+        npr.seed(int(g['seed']))
+        ilr = make_ilr(g)
+        ilr.resample(g['x'], g['y'], init_labels='random', maxiter=S, progress_bar=False)
+        assert np.array_equal(ilr.labels_, g[f'labels_{S - 1}'])
+        close(ilr.basis.likelihood.mus, g[f'b_lik_mus_{S - 1}'], 1e-7, 'basis mus')
+        close(ilr.models.likelihood.As, g[f'm_lik_As_{S - 1}'], 1e-7, 'expert As')
+        close(ilr.models.likelihood.lmbdas, g[f'm_lik_lmbdas_{S - 1}'], 1e-7, 'expert lmbdas')
+        close(ilr.likelihood.log_complete_likelihood(g['x'], g['y']), g[f'log_prob_{S - 1}'], 1e-7, 'log_prob')
+        vlb = ilr.meanfield_coordinate_descent(g['x'], g['y'], randomize=False, maxiter=T, tol=0., progress_bar=False)
+        close(vlb, g['vlb'], 1e-8, 'ILR lower bound')
+        for key, ref in zip(ilr.models.posterior.params, ('Ms', 'Ks', 'psis', 'nus')):
+            close(key, g[f'vi_m_post_{ref}_{T - 1}'], 1e-7, 'MNW posterior ' + ref)
+        close(ilr.expected_responsibilities(g['x'], g['y']), g[f'vi_resp_{T - 1}'], 1e-7, 'ILR resp')
+        mu, var, std = ilr.meanfield_prediction(g['x'][:32], prediction='average')
+        close(mu, g['pred_mu'], 1e-7, 'prediction mean')
+        close(var, g['pred_var'], 1e-7, 'prediction variance')
+    finally:
+        mimo_b200.set_default_precision('fp32')
+
+
+def test_ilr_meanfield_fp32():
+    import mimo_b200
+    mimo_b200.set_default_precision('fp32')
+    g = load('ilr_tied')
+    S, T = int(g['sweeps']), int(g['iters'])
+    npr.seed(int(g['seed']))
+    ilr = make_ilr(g)
+    # start VI from the reference's Gibbs state so both sides see identical posteriors
+    ilr.basis.posterior.params = tuple(g[f'b_post_{k}_{S - 1}'] for k in ('mus', 'kappas', 'psis', 'nus'))
+    ilr.models.posterior.params = tuple(g[f'm_post_{k}_{S - 1}'] for k in ('Ms', 'Ks', 'psis', 'nus'))
+    ilr.gating.posterior.gammas, ilr.gating.posterior.deltas = g[f'gate_gammas_{S - 1}'], g[f'gate_deltas_{S - 1}']
+    vlb = ilr.meanfield_coordinate_descent(g['x'], g['y'], randomize=False, maxiter=T, tol=0., progress_bar=False)
+    close(vlb, g['vlb'], 2e-4, 'ILR lower bound (fp32)')
+
+
+def test_em_trajectory(precision):
+    from mimo_b200.distributions import Categorical, StackedGaussiansWithPrecision
+    from mimo_b200.mixtures import MixtureOfGaussians
+    g = load('gmm_toy_em')
+    K, d = int(g['K']), int(g['d'])
+    rng = np.random.default_rng(3)
+    comp = StackedGaussiansWithPrecision(K, d, mus=rng.standard_normal((K, d)), lmbdas=np.stack(K * [np.eye(d)]))
+    model = MixtureOfGaussians(gating=Categorical(K), components=comp)
+    npr.seed(3)
+    ll = model.max_likelihood(g['obs'], maxiter=len(g['ll']), progress_bar=False)
+    tol = TOL[precision]
+    close(ll, g['ll'], tol, 'EM log-likelihood')
+    close(comp.mus, g['mus'], 20 * tol, 'EM mus')
+    close(model.gating.probs, g['probs'], 20 * tol, 'EM probs')
+    close(model.responsibilities(g['obs']), g['resp_final'], 100 * tol, 'EM resp')
+    assert np.all(np.diff(ll) >= -1e-6 * abs(ll[-1]))          # "ll monoton?"
+
+
+def test_map_em_matches_oracle():
+    """MAP-EM (gmm.py:176-204) restated with the oracle: statistics -> posterior mode -> E-step."""
+    import mimo_b200
+    mimo_b200.set_default_precision('fp64')
+    try:
+        g = load('gmm_toy_vi')
+        x, K, d = g['obs'], int(g['K']), int(g['d'])
+        g = dict(g)
+        g['gate_alphas0'] = 2.0 * np.ones(K)
+        g['nus0'] = g['nus0'] + 2.0
+        model = make_gmm(g)
+        npr.seed(5)
+        resp = npr.rand(K, len(x))
+        resp /= resp.sum(0)
+        npr.seed(5)
+        lp = model.max_aposteriori(x, maxiter=4, progress_bar=False)
+        prior = (g['mus0'], g['kappas0'], g['psis0'], g['nus0'])
+        ref = []
+        for _ in range(4):
+            post = orc.nw_nat_to_std(orc.add_stats(orc.nw_std_to_nat(*prior), orc.gauss_full_wstats(x, resp)))
+            mus, lmbdas = orc.nw_mode(*post)
+            probs = orc.dirichlet_mode(orc.dirichlet_posterior(g['gate_alphas0'], orc.categorical_wstats(resp)))
+            resp, lse = orc.responsibilities(orc.gauss_full_loglik(x, mus, lmbdas) + np.log(probs)[:, None])
+            ref.append(lse.sum())
+        close(model.components.likelihood.mus, mus, 1e-8, 'MAP mus')
+        close(model.gating.likelihood.probs, probs, 1e-9, 'MAP probs')
+        # log-posterior = log-likelihood + log prior of the point estimate
+        from mimo_b200.distributions import StackedNormalWisharts, Dirichlet
+        lprior = Dirichlet(K, g['gate_alphas0']).log_likelihood(probs) \
+            + StackedNormalWisharts(K, d, *prior).log_likelihood((mus, lmbdas))
+        close(lp[-1], ref[-1] + lprior, 1e-8, 'MAP log-posterior')
+    finally:
+        mimo_b200.set_default_precision('fp32')
+
+
+@pytest.mark.parametrize('name', ['pointwise_d16', 'pointwise_d128'])
+def test_object_api_pointwise(name, precision):
+    from mimo_b200.distributions import (StackedGaussiansWithPrecision, StackedNormalWisharts,
+                                         StackedGaussiansWithNormalWisharts)
+    g = load(name)
+    K, d = g['mus'].shape
+    lik = StackedGaussiansWithPrecision(K, d, mus=g['mus'], lmbdas=g['lmbdas'])
+    tol = TOL[precision]
+    close(lik.log_likelihood(g['obs']), g['log_lik'], tol, 'log_likelihood')
+    st = lik.weighted_statistics(g['obs'], g['weights'])
+    close(st[0], g['st_x'], tol, 'sum r x')
+    close(st[1], g['st_n'], tol, 'sum r')
+    close(st[2], g['st_xx'], tol, 'sum r xx')
+    close(st[3], g['st_n'], tol, 'sum r (4th)')
+    wrap = StackedGaussiansWithNormalWisharts(K, d, prior=StackedNormalWisharts(K, d, g['mus'], g['kappas'], g['psis'], g['nus']),
+                                              likelihood=lik)
+    close(wrap.expected_log_likelihood(g['obs']), g['exp_log_lik'], tol, 'expected_log_likelihood')
+    # list-of-shards semantics (gaussian.py:503-505): statistics add over shards
+    half = len(g['obs']) // 2
+    st2 = lik.weighted_statistics([g['obs'][:half], g['obs'][half:]], [g['weights'][:, :half], g['weights'][:, half:]])
+    close(st2[2], g['st_xx'], tol, 'sharded sum r xx')
+    # NaN rows: zero data term in log_likelihood, dropped from statistics
+    xn = g['obs'].copy()
+    xn[3, 1] = np.nan
+    ll = lik.log_likelihood(xn)
+    assert not np.isnan(xn[3, 0]) and np.isnan(xn[3, 1])            # caller's array is not mutated
+    close(np.delete(ll, 3, axis=1), np.delete(g['log_lik'], 3, axis=1), tol, 'log_likelihood with NaN row')
+    stn = lik.weighted_statistics(xn, g['weights'])
+    ref = orc.gauss_full_wstats(np.delete(g['obs'], 3, axis=0), np.delete(g['weights'], 3, axis=1))
+    close(stn[2], ref[2], tol, 'stats with NaN row')
+
+
+def test_meanfield_update_and_wrappers_api(precision):
+    """single-wrapper public methods: meanfield_update / resample / max_aposteriori."""
+    from mimo_b200.distributions import StackedNormalWisharts, StackedGaussiansWithNormalWisharts
+    from mimo_b200.utils.data import one_hot
+    g = load('gmm_toy_gibbs')
+    K, d, x = int(g['K']), int(g['d']), g['obs']
+    prior = StackedNormalWisharts(K, d, g['mus0'], g['kappas0'], g['psis0'], g['nus0'])
+    comp = StackedGaussiansWithNormalWisharts(K, d, prior=prior)
+    w = one_hot(g['labels_init'], K)
+    comp.meanfield_update(x, w)
+    tol = TOL[precision]
+    for key, ref in zip(comp.posterior.params, ('mus', 'kappas', 'psis', 'nus')):
+        close(key, g[f'post_{ref}_0'], 10 * tol, 'posterior ' + ref)
+    post = comp.posterior.params
+    close(comp.variational_lowerbound(), orc.nw_vlb(prior.params, post), 1e-7, 'vlb term')
+    # resample with replayed variates: the reference drew them right after this update
+    npr.seed(int(g['seed']))
+    npr.choice(K, size=len(x))
+    comp.resample(x, w)
+    close(comp.likelihood.mus, g['lik_mus_0'], 20 * tol, 'resampled mus')
+    close(comp.likelihood.lmbdas, g['lik_lmbdas_0'], 20 * tol, 'resampled lmbdas')
+    comp.max_aposteriori(x, w)
+    m, l = orc.nw_mode(*[g[f'post_{r}_0'] for r in ('mus', 'kappas', 'psis', 'nus')])
+    close(comp.likelihood.lmbdas, l, 20 * tol, 'MAP lmbdas')
+
+
+def test_nonpd_raises_linalgerror():
+    from mimo_b200.distributions import StackedGaussiansWithPrecision
+    lik = StackedGaussiansWithPrecision(2, 2, mus=np.zeros((2, 2)), lmbdas=np.stack([np.eye(2), -np.eye(2)]))
+    with pytest.raises(np.linalg.LinAlgError):
+        lik.log_likelihood(np.zeros((4, 2)))
+
+
+def test_svi_runs_and_improves():
+    import mimo_b200
+    mimo_b200.set_default_precision('fp64')
+    try:
+        g = load('gmm_toy_vi')
+        model = make_gmm(g)
+        npr.seed(1)
+        import random
+        random.seed(1)
+        vlb = model.meanfield_stochastic_descent(g['obs'], maxiter=30, step_size=5e-2, batch_size=64, progress_bar=False)
+        assert len(vlb) == 30 and np.isfinite(vlb).all() and vlb[-1] > vlb[0]
+    finally:
+        mimo_b200.set_default_precision('fp32')

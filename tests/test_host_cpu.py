@@ -1,0 +1,91 @@
+"""Host-side pieces that need no GPU: Statistics algebra, one_hot, batches, feature
+tables, gating / prior closed forms against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import mimo_oracle as orc
+
+
+def test_statistics_algebra():
+    from mimo_b200.utils.abstraction import Statistics
+    a = Statistics([np.ones(3), 2.0, np.eye(2)])
+    b = Statistics([np.arange(3.0), 1.0, 2 * np.eye(2)])
+    c = a + b
+    assert isinstance(c, Statistics) and np.allclose(c[0], [1, 2, 3]) and c[1] == 3.0
+    d = 0.5 * (c - a)
+    assert np.allclose(d[2], np.eye(2)) and np.allclose((d * 2.0)[0], np.arange(3.0))
+    # list-valued entries add element-wise (per-shard statistics)
+    e = Statistics([[np.ones(2), np.ones(2)]]) + Statistics([[np.ones(2), 2 * np.ones(2)]])
+    assert np.allclose(e[0][1], 3.0)
+
+
+def test_one_hot_and_batches():
+    from mimo_b200.utils.data import one_hot, batches
+    z = np.array([0, 2, 1, 2])
+    assert np.array_equal(one_hot(z, 3), orc.one_hot(z, 3))
+    with pytest.raises(AssertionError):
+        one_hot(np.array([0, 3]), 3)
+    out = list(batches(5, 20))
+    assert len(out) == 1 and len(set(out[0])) == 5
+
+
+def test_feature_tables():
+    from mimo_b200 import _engine as E
+    f = E.quad_features(3)
+    assert f.F == 10 and f.fi_host[-1] == 3 and f.fj_host[-1] == 3
+    assert all(E.tri(i, j) == k for k, (i, j) in enumerate(zip(f.fi_host, f.fj_host)))
+    g = E.diag_features(4)
+    assert g.F == 9 and list(g.fj_host[:4]) == [4] * 4 and list(g.fi_host[4:8]) == list(g.fj_host[4:8])
+    assert E.pad_rows(2) == 8 and E.pad_rows(18) == 32 and E.pad_cols(17) == 20
+    with pytest.raises(NotImplementedError):
+        E.pad_rows(200)
+
+
+def test_prior_closed_forms_match_oracle():
+    from mimo_b200.distributions import (StackedNormalWisharts, TiedNormalWisharts, StackedNormalGammas,
+                                         StackedMatrixNormalWisharts, Dirichlet, TruncatedStickBreaking)
+    rng = np.random.default_rng(0)
+
+    def spd(d):
+        a = rng.standard_normal((d, d + 2))
+        return a @ a.T / d + 0.1 * np.eye(d)
+    K, d = 4, 3
+    p = (rng.standard_normal((K, d)), rng.random(K) + 0.2, np.stack([spd(d) for _ in range(K)]), d + 1 + rng.random(K))
+    nw = StackedNormalWisharts(K, d, *p)
+    for a, b in zip(nw.nat_param, orc.nw_std_to_nat(*p)):
+        assert np.allclose(a, b)
+    for a, b in zip(nw.expected_statistics(), orc.nw_expected_statistics(*p)):
+        assert np.allclose(a, b)
+    assert np.allclose(nw.log_partition(), orc.nw_log_partition(*p))
+    q = StackedNormalWisharts(K, d, *p)
+    x, w = rng.standard_normal((50, d)), rng.random((K, 50))
+    q.nat_param = nw.nat_param + orc.gauss_full_wstats(x, w)
+    assert np.allclose(q.entropy() - q.cross_entropy(nw), orc.nw_vlb(p, q.params))
+    t = TiedNormalWisharts(K, d, *p)
+    t.nat_param = nw.nat_param
+    for a, b in zip(t.params, orc.nw_nat_to_std(orc.nw_std_to_nat(*p), tied=True)):
+        assert np.allclose(a, b)
+    g = (rng.standard_normal((K, d)), rng.random((K, d)) + 0.2, rng.random((K, d)) + 1, rng.random((K, d)) + 0.5)
+    ng = StackedNormalGammas(K, d, *g)
+    for a, b in zip(ng.expected_statistics(), orc.ng_expected_statistics(*g)):
+        assert np.allclose(a, b)
+    assert np.allclose(ng.log_partition(), orc.ng_log_partition(*g))
+    o, c = 2, 4
+    m = (rng.standard_normal((K, o, c)), np.stack([spd(c) for _ in range(K)]), np.stack([spd(o) for _ in range(K)]),
+         o + 1 + rng.random(K))
+    mnw = StackedMatrixNormalWisharts(K, c, o, *m)
+    for a, b in zip(mnw.nat_param, orc.mnw_std_to_nat(*m)):
+        assert np.allclose(a, b)
+    for a, b in zip(mnw.expected_statistics(), orc.mnw_expected_statistics(*m)):
+        assert np.allclose(a, b)
+    back = StackedMatrixNormalWisharts(K, c, o, *m)
+    back.nat_param = mnw.nat_param
+    for a, b in zip(back.params, m):
+        assert np.allclose(a, b)
+    al = rng.random(K) + 1.5
+    assert np.allclose(Dirichlet(K, al).expected_statistics(), orc.dirichlet_expected_log(al))
+    assert np.allclose(Dirichlet(K, al).mode(), orc.dirichlet_mode(al))
+    sb = TruncatedStickBreaking(K, al, 2 * al)
+    assert np.allclose(sb.mean(), orc.stick_mean(al, 2 * al))
+    assert np.allclose(sb.entropy() - sb.cross_entropy(TruncatedStickBreaking(K, np.ones(K), np.ones(K))),
+                       orc.stick_vlb((np.ones(K), np.ones(K)), (al, 2 * al)))
