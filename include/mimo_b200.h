@@ -133,6 +133,19 @@ int mimo_sweep(int dtype, int family, int hard,
                void* ll_out, int64_t ldo,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* mimo_sweep with per-phase device timing for benchmarks: CUDA events are recorded on
+ * `stream` around every launch; on return (this variant synchronises) phase_ms_host[0..2]
+ * have been incremented by the milliseconds spent in the E-step, softmax / label and
+ * statistics kernels and phase_ms_host[3] by the number of kernel launches.           */
+int mimo_sweep_timed(int dtype, int family, int hard,
+                     const void* Z, int64_t N, int D, int64_t ldz,
+                     const void* op_a, const void* op_b, const void* cst, int K, int Rp, int Dpp,
+                     const int32_t* fi, const int32_t* fj, int F,
+                     const void* uniforms, uint64_t seed, uint64_t point_offset,
+                     double* stat, double* lse_sum, int32_t* labels_out, void* lse_out,
+                     void* ll_out, int64_t ldo,
+                     void* workspace, size_t workspace_bytes, void* stream, double* phase_ms_host);
+
 /* ---- batched per-component posterior kernels (always FP64 math) -------- */
 
 /* Operand placement: a posterior kernel writes its whitening rows into the

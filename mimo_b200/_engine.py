@@ -238,25 +238,34 @@ class SweepBuffers:
         self.N, self.K, self.F, self.precision, self.hard = N, K, F, precision, hard
         self.wsb = _lib.load().mimo_sweep_workspace(code(precision), N, K, 1 if hard else 0)
         self.ws = workspace(self.wsb)
-        self.stat = zeros((K, F), torch.float64)
-        self.lse_sum = zeros((1,), torch.float64)
+        # statistics and the lower-bound scalar share one buffer: ONE all-reduce message per sweep
+        self.flat = zeros((K * F + 1,), torch.float64)
+        self.stat = self.flat[:K * F].view(K, F)
+        self.lse_sum = self.flat[K * F:]
         self.labels = empty((N,), torch.int32) if hard else None
 
 
-def sweep(Z, ops, feats, buf, uniforms=None, seed=0, offset=0, ll_out=None, lse_out=None, zero=True):
+def sweep(Z, ops, feats, buf, uniforms=None, seed=0, offset=0, ll_out=None, lse_out=None, zero=True,
+          phase_ms=None):
     """One E-step + statistics pass over resident Z.  Results land in buf.stat,
-    buf.lse_sum and (hard) buf.labels."""
+    buf.lse_sum and (hard) buf.labels.  phase_ms: optional float64 numpy array (4,) that
+    accumulates per-phase device milliseconds and the launch count (synchronises)."""
     N, D = Z.shape
     fi, fj = feats.dev()
     if zero:
         buf.stat.zero_()
         buf.lse_sum.zero_()
     a, b, c, K, Rp, Dpp = ops.args()
-    _lib.call('mimo_sweep', code(ops.precision), ops.family, 1 if buf.hard else 0,
-              ptr(Z), N, D, Z.stride(0), a, b, c, K, Rp, Dpp, ptr(fi), ptr(fj), feats.F,
-              ptr(uniforms), int(seed), int(offset), ptr(buf.stat), ptr(buf.lse_sum), ptr(buf.labels),
-              ptr(lse_out), ptr(ll_out), (ll_out.stride(0) if ll_out is not None else 0),
-              ptr(buf.ws), buf.wsb, stream())
+    args = (code(ops.precision), ops.family, 1 if buf.hard else 0,
+            ptr(Z), N, D, Z.stride(0), a, b, c, K, Rp, Dpp, ptr(fi), ptr(fj), feats.F,
+            ptr(uniforms), int(seed), int(offset), ptr(buf.stat), ptr(buf.lse_sum), ptr(buf.labels),
+            ptr(lse_out), ptr(ll_out), (ll_out.stride(0) if ll_out is not None else 0),
+            ptr(buf.ws), buf.wsb, stream())
+    if phase_ms is None:
+        _lib.call('mimo_sweep', *args)
+    else:
+        assert phase_ms.dtype == np.float64 and phase_ms.size >= 4
+        _lib.call('mimo_sweep_timed', *args, phase_ms.ctypes.data)
     return buf
 
 

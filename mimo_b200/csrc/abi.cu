@@ -79,6 +79,16 @@ int mimo_sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D,
     return sweep(dtype, family, hard, Z, N, D, ldz, op_a, op_b, cst, K, Rp, Dpp, fi, fj, F, uniforms, seed,
                  point_offset, stat, lse_sum, labels_out, lse_out, ll_out, ldo, workspace, workspace_bytes, ST(stream));
 }
+int mimo_sweep_timed(int dtype, int family, int hard, const void* Z, int64_t N, int D, int64_t ldz,
+                     const void* op_a, const void* op_b, const void* cst, int K, int Rp, int Dpp,
+                     const int32_t* fi, const int32_t* fj, int F,
+                     const void* uniforms, uint64_t seed, uint64_t point_offset,
+                     double* stat, double* lse_sum, int32_t* labels_out, void* lse_out, void* ll_out, int64_t ldo,
+                     void* workspace, size_t workspace_bytes, void* stream, double* phase_ms_host) {
+    return sweep(dtype, family, hard, Z, N, D, ldz, op_a, op_b, cst, K, Rp, Dpp, fi, fj, F, uniforms, seed,
+                 point_offset, stat, lse_sum, labels_out, lse_out, ll_out, ldo, workspace, workspace_bytes, ST(stream),
+                 phase_ms_host);
+}
 int mimo_sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, int D,
                     const void* op_a_host, const void* op_b_host, const void* cst_host, int K, int Rp, int Dpp,
                     const int32_t* fi_host, const int32_t* fj_host, int F, const void* uniforms_host, uint64_t seed,

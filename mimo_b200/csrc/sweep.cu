@@ -5,6 +5,7 @@
 // it supports the shape.
 #include "common.cuh"
 #include "internal.h"
+#include <vector>
 
 namespace mimo {
 
@@ -34,7 +35,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
           const int32_t* fi, const int32_t* fj, int F,
           const void* uniforms, uint64_t seed, uint64_t point_offset,
           double* stat, double* lse_sum, int32_t* labels_out, void* lse_out, void* ll_out, int64_t ldo,
-          void* workspace, size_t workspace_bytes, cudaStream_t st) {
+          void* workspace, size_t workspace_bytes, cudaStream_t st, double* phase_ms) {
     MIMO_CHECK_ARG(dtype == MIMO_F32 || dtype == MIMO_F64, "dtype");
     MIMO_CHECK_ARG(family == 0 || family == 1, "family");
     MIMO_CHECK_ARG(Z && op_a && cst && workspace && (family == 0 || op_b), "null pointer");
@@ -49,13 +50,18 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     void* hard_ws = ws;
     const size_t hard_ws_bytes = hard ? stats_hard_workspace(C, K) : 0;
 
+    // optional per-phase device timing (bench.py's roofline leg): events on the launching stream
+    std::vector<cudaEvent_t> ev;
+    auto mark = [&]() { if (phase_ms) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); } };
     for (int64_t n0 = 0; n0 < N; n0 += C) {
         const int64_t nc = (N - n0 < C) ? (N - n0) : C;
+        mark();
         const char* Zc = (const char*)Z + (size_t)n0 * ldz * es;
         int rc;
         if (family == 0) rc = loglik_quad(dtype, Zc, nc, D, ldz, op_a, cst, K, Rp, Dpp, scratch, C, st);
         else             rc = loglik_diag(dtype, Zc, nc, D, ldz, op_a, op_b, cst, K, scratch, C, st);
         if (rc) return rc;
+        mark();
         int flags = (lse_sum ? MIMO_ACC_LSE : 0) | (lse_out ? MIMO_WRITE_LSE : 0)
                   | (hard ? MIMO_DRAW_LABELS : MIMO_WRITE_RESP);
         int32_t* lab = labels_out ? labels_out + n0 : lab_tmp;
@@ -63,6 +69,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         void* lse_c = lse_out ? (char*)lse_out + (size_t)n0 * es : nullptr;
         rc = softmax(dtype, scratch, K, nc, C, flags, lse_c, uni, seed, point_offset + (uint64_t)n0, lab, lse_sum, st);
         if (rc) return rc;
+        mark();
         if (ll_out)
             MIMO_CUDA(cudaMemcpy2DAsync((char*)ll_out + (size_t)n0 * es, (size_t)ldo * es, scratch, (size_t)C * es,
                                         (size_t)nc * es, K, cudaMemcpyDeviceToDevice, st));
@@ -71,6 +78,19 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             else      rc = stats_soft(dtype, Zc, nc, D, ldz, scratch, C, K, fi, fj, F, stat, st);
             if (rc) return rc;
         }
+        mark();
+    }
+    if (phase_ms) {
+        MIMO_CUDA(cudaStreamSynchronize(st));
+        for (size_t i = 0; i + 3 < ev.size(); i += 4) {
+            for (int ph = 0; ph < 3; ++ph) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[i + ph], ev[i + ph + 1]);
+                phase_ms[ph] += ms;
+            }
+            phase_ms[3] += hard ? 7.0 : 3.0;     // kernel launches of this chunk
+        }
+        for (auto e : ev) cudaEventDestroy(e);
     }
     return MIMO_OK;
 }
@@ -114,7 +134,7 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
         MIMO_CUDA(cudaMemsetAsync(dstat, 0, (size_t)K * F * 8, st));
         MIMO_CUDA(cudaMemsetAsync(dlse, 0, 8, st));
         int r = sweep(dtype, family, hard, dZ, N, D, D, dA, dB, dC, K, Rp, Dpp, dfi, dfj, F, duni, seed, 0,
-                      dstat, dlse, dlab, nullptr, nullptr, 0, dws, wsb, st);
+                      dstat, dlse, dlab, nullptr, nullptr, 0, dws, wsb, st, nullptr);
         if (r) return r;
         MIMO_CUDA(cudaMemcpyAsync(stat_host, dstat, (size_t)K * F * 8, cudaMemcpyDeviceToHost, st));
         if (lse_sum_host) MIMO_CUDA(cudaMemcpyAsync(lse_sum_host, dlse, 8, cudaMemcpyDeviceToHost, st));

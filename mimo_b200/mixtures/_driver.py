@@ -75,9 +75,9 @@ class Session:
         self.stat = self._reduce(E.stats_soft(self.Z, R, self.feats, self.precision))
         return self.stat
 
-    def _reduce(self, stat, lse=None):
+    def _reduce(self, stat):
         if self.comm is not None:
-            self.comm.allreduce_stats(stat, lse)
+            self.comm.allreduce(stat)
         return stat
 
     # -- operands --------------------------------------------------------------------------
@@ -135,14 +135,16 @@ class Session:
         return ops
 
     # -- the sweep -------------------------------------------------------------------------
-    def sweep(self, ops, hard, uniforms=None, seed=0, ll_out=None):
+    def sweep(self, ops, hard, uniforms=None, seed=0, ll_out=None, phase_ms=None):
         buf = self.buf(hard)
         u = None
         if uniforms is not None:
             u = uniforms if isinstance(uniforms, torch.Tensor) else E.to_dev(np.asarray(uniforms).reshape(-1))
         offset = self.comm.point_offset if self.comm is not None else 0
-        E.sweep(self.Z, ops, self.feats, buf, uniforms=u, seed=seed, offset=offset, ll_out=ll_out)
-        self._reduce(buf.stat, buf.lse_sum)
+        E.sweep(self.Z, ops, self.feats, buf, uniforms=u, seed=seed, offset=offset, ll_out=ll_out,
+                phase_ms=phase_ms)
+        if self.comm is not None:
+            self.comm.allreduce(buf.flat)
         self.stat, self.lse_sum = buf.stat, buf.lse_sum
         return buf
 
