@@ -388,6 +388,16 @@ def main():
         outs = step(False)
     s.check(outs)
     torch.cuda.synchronize()
+    if os.environ.get('MIMO_BENCH_DEBUG') and not hard:
+        for rep in range(2):
+            t = [time.perf_counter()]
+            ops, outs = s.update_from_stats(MEANFIELD); torch.cuda.synchronize(); t.append(time.perf_counter())
+            s.sweep(ops, hard=False); torch.cuda.synchronize(); t.append(time.perf_counter())
+            s.lower_bound(outs); t.append(time.perf_counter())
+            ph = np.zeros(4)
+            s.sweep(ops, hard=False, phase_ms=ph); torch.cuda.synchronize(); t.append(time.perf_counter())
+            sys.stderr.write('DEBUG update %.2f ms | sweep %.2f ms | vlb %.2f ms | timed sweep %.2f ms phases %s\n'
+                             % tuple([1e3 * (t[i + 1] - t[i]) for i in range(4)] + [ph.tolist()]))
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
@@ -414,7 +424,8 @@ def main():
     work = algorithmic_work(w)
     value = w['N'] * K / (ms * 1e-3)
     # roofline of the dominant kernel, from the per-phase CUDA-event times of the timed steps
-    chunks = max(1.0, phase[3] / (7.0 if hard else 3.0))
+    # launches: 3 per chunk (mean-field) or 2 per chunk + 4 for the one counting-sort statistics pass (Gibbs)
+    chunks = max(1.0, (phase[3] - 4.0 * args.steps) / 2.0 if hard else phase[3] / 3.0)
     phase_ms = phase[:3] / args.steps
     dom = int(np.argmax(phase_ms))
     pairs_local = n_local * K
@@ -422,7 +433,7 @@ def main():
     flops = [work['e_flops_pair'] * pairs_local, 0.0, work['s_flops_pair'] * pairs_local]
     t_tensor = sum(flops) / (peaks['tf_sus'] * 1e12)
     bound = 'tensor' if t_tensor >= t_hbm else 'hbm'
-    launches_per_step = chunks / args.steps * (1 if dom != 1 else 1)
+    launches_per_step = 1.0 if (hard and dom == 2) else chunks / args.steps
     if bound == 'tensor':
         ach = flops[dom] / (phase_ms[dom] * 1e-3) / 1e12 if phase_ms[dom] > 0 else 0.0
         roof = dict(bound='tensor', achieved=ach, peak=peaks['tf_sus'], unit='TFLOP/s', frac=ach / peaks['tf_sus'], traffic=None)

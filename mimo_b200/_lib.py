@@ -103,8 +103,16 @@ def call(name, *args):
     check(getattr(load(), name)(*args))
 
 
+_device_checked = False
+
+
 def require_device():
-    """Fail loudly unless the extension is built and an sm_100 GPU is visible."""
+    """Fail loudly unless the extension is built and an sm_100 GPU is visible.  The positive
+    answer is cached: cudaGetDeviceProperties costs milliseconds per call."""
+    global _device_checked
+    if _device_checked:
+        return
     lib = load()
     if not lib.mimo_device_ok():
         raise MimoCudaError('mimo_b200 needs a Blackwell (sm_100) GPU: ' + last_error())
+    _device_checked = True

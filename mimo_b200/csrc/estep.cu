@@ -20,6 +20,9 @@ constexpr int QUAD_BN = 128;   // flat (component,row) columns per chunk: 16 thr
 constexpr int QUAD_PAD = 4;
 
 // grid.x = point tiles of BM = 16*TM points; every CTA walks all K*Rp rows in chunks of 128.
+// Thread (tx, ty) owns rows {4tx..4tx+3} U {64+4tx..64+4tx+3} of the chunk and, for TM = 8,
+// points {4ty..4ty+3} U {64+4ty..64+4ty+3}: consecutive lanes read consecutive 16-byte
+// vectors of shared memory (conflict-free 128-bit loads).
 template <typename T, int TM>
 __global__ void __launch_bounds__(QUAD_THREADS)
 quad_loglik_kernel(const T* __restrict__ Z, int64_t N, int D, int64_t ldz,
@@ -28,6 +31,8 @@ quad_loglik_kernel(const T* __restrict__ Z, int64_t N, int D, int64_t ldz,
     constexpr int BM = 16 * TM;
     constexpr int ZS = BM + QUAD_PAD;        // smem row strides (keep 16-byte alignment)
     constexpr int WS = QUAD_BN + QUAD_PAD;
+    constexpr int VEC = 16 / sizeof(T);      // elements per 128-bit global load
+    using V = typename VecOf<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* Zs = reinterpret_cast<T*>(smem_raw);          // [Dpp][ZS]   transposed point tile, row D == 1
     T* Ws = Zs + (size_t)Dpp * ZS;                   // [Dpp][WS]   transposed operand chunk
@@ -37,9 +42,10 @@ quad_loglik_kernel(const T* __restrict__ Z, int64_t N, int D, int64_t ldz,
     const int64_t n0 = (int64_t)blockIdx.x * BM;
     const int64_t total_rows = (int64_t)K * Rp;
 
-    // ---- stage the point tile, transposed; coalesced along each row of Z ----
+    // ---- stage the point tile, transposed: lanes walk points, so the shared-memory stores are
+    //      conflict-free and each lane streams its own row of Z (sector reuse through L1) ----
     for (int idx = tid; idx < BM * D; idx += QUAD_THREADS) {
-        int p = idx / D, j = idx - p * D;
+        int p = idx % BM, j = idx / BM;
         int64_t n = n0 + p;
         Zs[j * ZS + p] = (n < N) ? Z[n * ldz + j] : T(0);
     }
@@ -48,13 +54,32 @@ quad_loglik_kernel(const T* __restrict__ Z, int64_t N, int D, int64_t ldz,
         Zs[j * ZS + p] = (j == D) ? T(1) : T(0);
     }
 
-    const int G = Rp >> 3;                           // threads sharing one component (power of two <= 16)
+    const int nvec = Dpp / VEC;                      // 128-bit vectors per operand row
     for (int64_t row0 = 0; row0 < total_rows; row0 += QUAD_BN) {
         __syncthreads();                             // Zs ready / previous chunk consumed
-        for (int idx = tid; idx < QUAD_BN * Dpp; idx += QUAD_THREADS) {
-            int r = idx / Dpp, j = idx - r * Dpp;
-            int64_t row = row0 + r;
-            Ws[j * WS + r] = (row < total_rows) ? W[row * Dpp + j] : T(0);
+        // operand chunk: lane -> row (conflict-free transposed stores), 4 independent 128-bit loads in flight
+        for (int v0 = tid; v0 < QUAD_BN * nvec; v0 += 4 * QUAD_THREADS) {
+            V tmp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int v = v0 + u * QUAD_THREADS;
+                int r = v & (QUAD_BN - 1), jv = v >> 7;
+                int64_t row = row0 + r;
+                if (v < QUAD_BN * nvec && row < total_rows)
+                    tmp[u] = __ldg(reinterpret_cast<const V*>(W + row * Dpp) + jv);
+                else
+                    tmp[u] = V{};
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int v = v0 + u * QUAD_THREADS;
+                if (v < QUAD_BN * nvec) {
+                    int r = v & (QUAD_BN - 1), jv = v >> 7;
+                    const T* e = reinterpret_cast<const T*>(&tmp[u]);
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) Ws[(jv * VEC + c) * WS + r] = e[c];
+                }
+            }
         }
         __syncthreads();
 
@@ -64,40 +89,68 @@ quad_loglik_kernel(const T* __restrict__ Z, int64_t N, int D, int64_t ldz,
 #pragma unroll
             for (int n = 0; n < 8; ++n) acc[m][n] = T(0);
 
-        const T* zp = Zs + ty * TM;
-        const T* wp = Ws + tx * 8;
+        const T* zp = Zs + ty * 4;
+        const T* wp = Ws + tx * 4;
 #pragma unroll 4
         for (int j = 0; j < Dpp; ++j) {
             T a[TM], b[8];
-            lds_vec<T, TM>(a, zp + j * ZS);
-            lds_vec<T, 8>(b, wp + j * WS);
+            {
+                T lo[4];
+                lds_vec<T, 4>(lo, zp + j * ZS);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) a[m] = lo[m];
+                if constexpr (TM == 8) {
+                    T hi[4];
+                    lds_vec<T, 4>(hi, zp + j * ZS + 64);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) a[4 + m] = hi[m];
+                }
+                T blo[4], bhi[4];
+                lds_vec<T, 4>(blo, wp + j * WS);
+                lds_vec<T, 4>(bhi, wp + j * WS + 64);
+#pragma unroll
+                for (int n = 0; n < 4; ++n) { b[n] = blo[n]; b[4 + n] = bhi[n]; }
+            }
 #pragma unroll
             for (int m = 0; m < TM; ++m)
 #pragma unroll
                 for (int n = 0; n < 8; ++n) acc[m][n] = fma(a[m], b[n], acc[m][n]);
         }
 
-        // ---- epilogue: sum of squares over the component's rows ----
-        T q[TM];
+        // ---- epilogue: sum of squares over each component's rows ----
+        // half h of the thread's rows = chunk rows 64h + 4tx .. +3, all inside one component
+        T q[2][TM];
 #pragma unroll
-        for (int m = 0; m < TM; ++m) {
-            T s = T(0);
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int n = 0; n < 8; ++n) s = fma(acc[m][n], acc[m][n], s);
-            q[m] = s;
+            for (int m = 0; m < TM; ++m) {
+                T s = T(0);
+#pragma unroll
+                for (int n = 0; n < 4; ++n) s = fma(acc[m][4 * h + n], acc[m][4 * h + n], s);
+                q[h][m] = s;
+            }
+        const int G4 = (Rp >= 64) ? 16 : (Rp >> 2);   // lanes (consecutive tx) sharing a component half
+        for (int o = 1; o < G4; o <<= 1) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int m = 0; m < TM; ++m) q[h][m] += __shfl_xor_sync(0xffffffffu, q[h][m], o);
         }
-        for (int o = 1; o < G; o <<= 1) {
+        if ((tx & (G4 - 1)) == 0) {
 #pragma unroll
-            for (int m = 0; m < TM; ++m) q[m] += __shfl_xor_sync(0xffffffffu, q[m], o);
-        }
-        int64_t row = row0 + tx * 8;
-        if ((tx & (G - 1)) == 0 && row < total_rows) {
-            int k = (int)(row / Rp);
-            T ck = cst[k];
-            T* op = out + (int64_t)k * ldo + n0 + ty * TM;
+            for (int h = 0; h < 2; ++h) {
+                if (Rp == 128 && h == 1) break;       // both halves belong to the same component
+                int64_t row = row0 + 64 * h + 4 * tx;
+                if (row >= total_rows) continue;
+                int k = (int)(row / Rp);
+                T ck = cst[k];
 #pragma unroll
-            for (int m = 0; m < TM; ++m)
-                if (n0 + ty * TM + m < N) op[m] = ck - T(0.5) * q[m];
+                for (int m = 0; m < TM; ++m) {
+                    int p = (m < 4) ? (ty * 4 + m) : (64 + ty * 4 + (m - 4));
+                    T qq = (Rp == 128) ? (q[0][m] + q[1][m]) : q[h][m];
+                    if (n0 + p < N) out[(int64_t)k * ldo + n0 + p] = ck - T(0.5) * qq;
+                }
+            }
         }
     }
 }

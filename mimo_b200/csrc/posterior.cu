@@ -725,87 +725,96 @@ __global__ void gating_kernel(int K, int kind, int mode, const double* prior_a, 
                               const double* stat, int F, int count_feature, const double* variates,
                               double* post_a, double* post_b, double* probs, double* vlb,
                               int op_dtype, void* cst, double* tmp, int32_t* info) {
-    // tmp: (4, K) scratch: a', b', logw, aux
+    // tmp: (8, K) scratch.  The transcendental work (digamma / lgamma per component) is spread over
+    // the threads; thread 0 only does the K-long prefix sums.
+    __shared__ double red[32];
     double* pa = tmp; double* pb = tmp + K; double* lw = tmp + 2 * K; double* aux = tmp + 3 * K;
+    double* e_a = tmp + 4 * K; double* e_b = tmp + 5 * K; double* lz = tmp + 6 * K;
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int k = tid; k < K; k += nt) { pa[k] = prior_a[k] + stat[(size_t)k * F + count_feature]; }
+    for (int k = tid; k < K; k += nt) pa[k] = prior_a[k] + stat[(size_t)k * F + count_feature];
+    if (kind == 1 && tid == 0) {              // tail counts (bayesian.py:143)
+        double run = 0.0;
+        for (int k = K - 1; k >= 0; --k) { pb[k] = prior_b[k] + run; run += stat[(size_t)k * F + count_feature]; }
+    }
     __syncthreads();
-    if (kind == 1) {
-        if (tid == 0) {                       // tail counts (bayesian.py:143)
-            double run = 0.0;
-            for (int k = K - 1; k >= 0; --k) { pb[k] = prior_b[k] + run; run += stat[(size_t)k * F + count_feature]; }
+    double s_part = 0.0, s0_part = 0.0;
+    for (int k = tid; k < K; k += nt) { s_part += pa[k]; s0_part += prior_a[k]; }
+    double sa = block_sum<double>(s_part, red);
+    __shared__ double sh_sa, sh_sa0;
+    if (tid == 0) sh_sa = sa;
+    double sa0 = block_sum<double>(s0_part, red);
+    if (tid == 0) sh_sa0 = sa0;
+    __syncthreads();
+    sa = sh_sa; sa0 = sh_sa0;
+    const bool need_dig = (mode == 0) || (vlb != nullptr);
+    double v_part = 0.0;
+    if (kind == 0) {
+        const double ds = need_dig ? digamma_d(sa) : 0.0;
+        for (int k = tid; k < K; k += nt) {
+            double dg = need_dig ? digamma_d(pa[k]) - ds : 0.0;
+            if (mode == 0) lw[k] = dg;
+            else if (mode == 2) {
+                if (!(pa[k] > 1.0)) { if (atomicCAS(&info[0], 0, MIMO_EINVAL) == 0) info[1] = k; }
+                lw[k] = log((pa[k] - 1.0) / (sa - K));
+            } else if (mode == 4) lw[k] = log(pa[k] / sa);
+            if (vlb) v_part += lgamma(pa[k]) - lgamma(prior_a[k]) - (pa[k] - prior_a[k]) * dg;
+        }
+        if (mode == 1) {
+            double g_part = 0.0;
+            for (int k = tid; k < K; k += nt) g_part += variates[k];
+            double sg = block_sum<double>(g_part, red);
+            __shared__ double sh_sg;
+            if (tid == 0) sh_sg = sg;
+            __syncthreads();
+            for (int k = tid; k < K; k += nt) lw[k] = log(fmax(variates[k] / sh_sg, 2.220446049250313e-16));
+        }
+        if (vlb) {   // bayesian.py:93-96, dirichlet.py:78-97
+            double v = block_sum<double>(v_part, red);
+            if (tid == 0) vlb[0] = v - lgamma(sa) + lgamma(sa0);
+        }
+    } else {
+        for (int k = tid; k < K; k += nt) {
+            if (need_dig) {
+                double dsum = digamma_d(pa[k] + pb[k]);
+                e_a[k] = digamma_d(pa[k]) - dsum;       // E log v_k
+                e_b[k] = digamma_d(pb[k]) - dsum;       // E log (1 - v_k)
+            }
+            if (vlb) {
+                lz[k] = lgamma(pa[k]) + lgamma(pb[k]) - lgamma(pa[k] + pb[k])
+                      - (lgamma(prior_a[k]) + lgamma(prior_b[k]) - lgamma(prior_a[k] + prior_b[k]));
+                v_part += lz[k] - (pa[k] - prior_a[k]) * e_a[k] - (pb[k] - prior_b[k]) * e_b[k];
+            }
+            if (mode != 0) {
+                double b;
+                if (k == K - 1) b = 1.0;
+                else if (mode == 1) b = variates[k];
+                else if (mode == 4) b = pa[k] / (pa[k] + pb[k]);
+                else {                    // mode of a Beta(g, d)   (dirichlet.py:152-170)
+                    double g = pa[k], dd = pb[k];
+                    if (g > 1.0 && dd > 1.0) b = (g - 1.0) / (g + dd - 2.0);
+                    else if (g == 1.0 && dd == 1.0) b = 1.0;
+                    else if (g < 1.0 && dd < 1.0) b = 1.0;
+                    else if (g <= 1.0 && dd > 1.0) b = 0.0;
+                    else if (g > 1.0 && dd <= 1.0) b = 1.0;
+                    else { b = 1.0; if (atomicCAS(&info[0], 0, MIMO_EINVAL) == 0) info[1] = k; }
+                }
+                aux[k] = b;
+            }
+        }
+        if (vlb) {   // bayesian.py:173-176, dirichlet.py:195-214
+            double v = block_sum<double>(v_part, red);
+            if (tid == 0) vlb[0] = v;
         }
         __syncthreads();
-    }
-    if (tid == 0) {
-        double v = 0.0;
-        if (kind == 0) {
-            double sa = 0.0, sa0 = 0.0;
-            for (int k = 0; k < K; ++k) { sa += pa[k]; sa0 += prior_a[k]; }
+        if (tid == 0) {
             if (mode == 0) {
-                double ds = digamma_d(sa);
-                for (int k = 0; k < K; ++k) lw[k] = digamma_d(pa[k]) - ds;
-            } else if (mode == 1) {
-                double sg = 0.0;
-                for (int k = 0; k < K; ++k) sg += variates[k];
-                for (int k = 0; k < K; ++k) lw[k] = log(fmax(variates[k] / sg, 2.220446049250313e-16));
-            } else if (mode == 2) {
-                for (int k = 0; k < K; ++k) {
-                    if (!(pa[k] > 1.0)) { if (atomicCAS(&info[0], 0, MIMO_EINVAL) == 0) info[1] = k; }
-                    lw[k] = log((pa[k] - 1.0) / (sa - K));
-                }
+                double run = 0.0;         // prefix sum of E log(1 - v_j), gmm.py:250-252
+                for (int k = 0; k < K; ++k) { lw[k] = e_a[k] + run; run += e_b[k]; }
             } else {
-                for (int k = 0; k < K; ++k) lw[k] = log(pa[k] / sa);
-            }
-            if (vlb) {   // bayesian.py:93-96, dirichlet.py:78-97
-                double ds = digamma_d(sa), lzq = -lgamma(sa), lzp = -lgamma(sa0), dot = 0.0;
-                for (int k = 0; k < K; ++k) {
-                    lzq += lgamma(pa[k]); lzp += lgamma(prior_a[k]);
-                    dot += (pa[k] - prior_a[k]) * (digamma_d(pa[k]) - ds);
-                }
-                v = lzq - lzp - dot;
-            }
-        } else {
-            if (mode == 0) {
-                double run = 0.0;
-                for (int k = 0; k < K; ++k) {
-                    double dsum = digamma_d(pa[k] + pb[k]);
-                    lw[k] = digamma_d(pa[k]) - dsum + run;
-                    run += digamma_d(pb[k]) - dsum;
-                }
-            } else {
-                double rest = 1.0;            // running prod (1 - v_j)
-                for (int k = 0; k < K; ++k) {
-                    double b;
-                    if (k == K - 1) b = 1.0;
-                    else if (mode == 1) b = variates[k];
-                    else if (mode == 4) b = pa[k] / (pa[k] + pb[k]);
-                    else {                    // mode of a Beta(g, d)   (dirichlet.py:152-170)
-                        double g = pa[k], dd = pb[k];
-                        if (g > 1.0 && dd > 1.0) b = (g - 1.0) / (g + dd - 2.0);
-                        else if (g == 1.0 && dd == 1.0) b = 1.0;
-                        else if (g < 1.0 && dd < 1.0) b = 1.0;
-                        else if (g <= 1.0 && dd > 1.0) b = 0.0;
-                        else if (g > 1.0 && dd <= 1.0) b = 1.0;
-                        else { b = 1.0; if (atomicCAS(&info[0], 0, MIMO_EINVAL) == 0) info[1] = k; }
-                    }
-                    aux[k] = b * rest;
-                    lw[k] = log(aux[k]);
-                    rest *= (1.0 - b);
-                }
-            }
-            if (vlb) {   // bayesian.py:173-176, dirichlet.py:195-214
-                double lzq = 0.0, lzp = 0.0, dot = 0.0;
-                for (int k = 0; k < K; ++k) {
-                    double dsum = digamma_d(pa[k] + pb[k]);
-                    lzq += lgamma(pa[k]) + lgamma(pb[k]) - lgamma(pa[k] + pb[k]);
-                    lzp += lgamma(prior_a[k]) + lgamma(prior_b[k]) - lgamma(prior_a[k] + prior_b[k]);
-                    dot += (pa[k] - prior_a[k]) * (digamma_d(pa[k]) - dsum) + (pb[k] - prior_b[k]) * (digamma_d(pb[k]) - dsum);
-                }
-                v = lzq - lzp - dot;
+                double rest = 1.0;        // running prod (1 - v_j), dirichlet.py:181-184
+                for (int k = 0; k < K; ++k) { double b = aux[k]; lw[k] = log(b * rest); rest *= (1.0 - b); }
             }
         }
-        if (vlb) vlb[0] = v;
     }
     __syncthreads();
     for (int k = tid; k < K; k += nt) {
@@ -816,7 +825,7 @@ __global__ void gating_kernel(int K, int kind, int mode, const double* prior_a, 
     }
 }
 
-size_t gating_workspace(int K) { return a256(8 * (size_t)4 * K); }
+size_t gating_workspace(int K) { return a256(8 * (size_t)8 * K); }
 
 int gating_posterior(int K, int kind, int mode, const double* prior_a, const double* prior_b,
                      const double* stat, int F, int count_feature, const double* variates,

@@ -153,13 +153,19 @@ __global__ void label_hist_kernel(const int32_t* __restrict__ labels, int64_t N,
     }
 }
 
-// single block: exclusive scan of counts -> offsets[K+1]; cursor := offsets
+// single block: exclusive scan of counts -> offsets[K+1]; cursor := offsets;
+// slabs[k] = first work item (SH_SEG-point slab) of component k, slabs[K] = number of items
 __global__ void label_scan_kernel(const int32_t* __restrict__ counts, int K, int32_t* __restrict__ offsets,
-                                  int32_t* __restrict__ cursor) {
+                                  int32_t* __restrict__ cursor, int32_t* __restrict__ slabs, int seg) {
     if (threadIdx.x == 0) {
-        int run = 0;
-        for (int k = 0; k < K; ++k) { offsets[k] = run; cursor[k] = run; run += counts[k]; }
+        int run = 0, items = 0;
+        for (int k = 0; k < K; ++k) {
+            offsets[k] = run; cursor[k] = run; slabs[k] = items;
+            run += counts[k];
+            items += (counts[k] + seg - 1) / seg;
+        }
         offsets[K] = run;
+        slabs[K] = items;
     }
 }
 
@@ -180,11 +186,19 @@ constexpr int SH_MAXFT = 34;    // features per thread when F > 256  (F <= 8704)
 template <typename T>
 __global__ void __launch_bounds__(SH_THREADS)
 stats_hard_kernel(const T* __restrict__ Z, int D, int64_t ldz, const int32_t* __restrict__ perm,
-                  const int32_t* __restrict__ offsets,
+                  const int32_t* __restrict__ offsets, const int32_t* __restrict__ slabs, int K,
                   const int32_t* __restrict__ fi, const int32_t* __restrict__ fj, int F,
                   double* __restrict__ stat) {
-    const int k = blockIdx.y;
-    const int beg = offsets[k] + blockIdx.x * SH_SEG;
+    // work item -> (component, slab): binary search in the per-component slab prefix
+    const int item = blockIdx.x;
+    if (item >= slabs[K]) return;
+    int lo = 0, hi = K;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (slabs[mid] <= item) lo = mid; else hi = mid;
+    }
+    const int k = lo;
+    const int beg = offsets[k] + (item - slabs[k]) * SH_SEG;
     const int end = min(offsets[k + 1], beg + SH_SEG);
     if (beg >= end) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -238,7 +252,7 @@ stats_hard_kernel(const T* __restrict__ Z, int D, int64_t ldz, const int32_t* __
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 size_t stats_hard_workspace(int64_t N, int K) {
-    return align256((size_t)(K + 1) * 4) * 3 + 256 + align256((size_t)N * 4);
+    return align256((size_t)(K + 1) * 4) * 4 + 256 + align256((size_t)N * 4);
 }
 
 int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const int32_t* labels, int K,
@@ -255,12 +269,13 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
     int32_t* counts = (int32_t*)ws;
     int32_t* offsets = (int32_t*)(ws + seg);
     int32_t* cursor = (int32_t*)(ws + 2 * seg);
-    int32_t* bad = (int32_t*)(ws + 3 * seg);
-    int32_t* perm = (int32_t*)(ws + 3 * seg + 256);
-    MIMO_CUDA(cudaMemsetAsync(ws, 0, 3 * seg + 256, st));
+    int32_t* slabs = (int32_t*)(ws + 3 * seg);
+    int32_t* bad = (int32_t*)(ws + 4 * seg);
+    int32_t* perm = (int32_t*)(ws + 4 * seg + 256);
+    MIMO_CUDA(cudaMemsetAsync(ws, 0, 4 * seg + 256, st));
     int grid = cdiv(N, 256);
     label_hist_kernel<<<grid, 256, 0, st>>>(labels, N, K, counts, bad);
-    label_scan_kernel<<<1, 32, 0, st>>>(counts, K, offsets, cursor);
+    label_scan_kernel<<<1, 32, 0, st>>>(counts, K, offsets, cursor, slabs, SH_SEG);
     label_scatter_kernel<<<grid, 256, 0, st>>>(labels, N, K, cursor, perm);
     MIMO_LAUNCH_CHECK();
     if (check) {
@@ -271,11 +286,12 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
     }
     size_t es = dtype == MIMO_F32 ? 4 : 8;
     size_t smem = (size_t)SH_PT * (D + 2) * es;
-    dim3 g2(cdiv(N, SH_SEG), K);
+    // every component contributes at most ceil(count/SEG) <= count/SEG + 1 slabs
+    dim3 g2((unsigned)(cdiv(N, SH_SEG) + K));
     if (dtype == MIMO_F32)
-        stats_hard_kernel<float><<<g2, SH_THREADS, smem, st>>>((const float*)Z, D, ldz, perm, offsets, fi, fj, F, stat);
+        stats_hard_kernel<float><<<g2, SH_THREADS, smem, st>>>((const float*)Z, D, ldz, perm, offsets, slabs, K, fi, fj, F, stat);
     else
-        stats_hard_kernel<double><<<g2, SH_THREADS, smem, st>>>((const double*)Z, D, ldz, perm, offsets, fi, fj, F, stat);
+        stats_hard_kernel<double><<<g2, SH_THREADS, smem, st>>>((const double*)Z, D, ldz, perm, offsets, slabs, K, fi, fj, F, stat);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }

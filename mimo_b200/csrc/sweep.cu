@@ -11,10 +11,11 @@ namespace mimo {
 
 static size_t a256(size_t x) { return (x + 255) / 256 * 256; }
 
-// points per chunk: keep the (K, chunk) scratch around 32 MB so every pass over it hits L2
+// points per chunk: keep the (K, chunk) scratch around 64 MB (half of the 126 MB L2) so the
+// softmax / statistics passes over it are served from L2
 int64_t sweep_chunk_points(int dtype, int64_t N, int K) {
     size_t es = dtype == MIMO_F32 ? 4 : 8;
-    int64_t c = (int64_t)((32u << 20) / ((size_t)K * es));
+    int64_t c = (int64_t)((64u << 20) / ((size_t)K * es));
     c = c / 256 * 256;
     if (c < 1024) c = 1024;
     if (c > (1 << 20)) c = 1 << 20;
@@ -25,8 +26,9 @@ int64_t sweep_chunk_points(int dtype, int64_t N, int K) {
 size_t sweep_workspace(int dtype, int64_t N, int K, int hard) {
     size_t es = dtype == MIMO_F32 ? 4 : 8;
     int64_t c = sweep_chunk_points(dtype, N, K);
-    size_t b = a256((size_t)K * c * es) + a256((size_t)c * 4);
-    if (hard) b += a256(stats_hard_workspace(c, K));
+    size_t b = a256((size_t)K * c * es);
+    // Gibbs: labels of ALL points (when the caller does not keep them) + one counting sort over N
+    if (hard) b += a256((size_t)N * 4) + a256(stats_hard_workspace(N, K));
     return b;
 }
 
@@ -46,9 +48,10 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     const int64_t C = sweep_chunk_points(dtype, N, K);
     char* ws = (char*)workspace;
     void* scratch = ws; ws += a256((size_t)K * C * es);
-    int32_t* lab_tmp = (int32_t*)ws; ws += a256((size_t)C * 4);
+    int32_t* lab_all = labels_out;
+    if (hard && !lab_all) { lab_all = (int32_t*)ws; ws += a256((size_t)N * 4); }
     void* hard_ws = ws;
-    const size_t hard_ws_bytes = hard ? stats_hard_workspace(C, K) : 0;
+    const size_t hard_ws_bytes = hard ? stats_hard_workspace(N, K) : 0;
 
     // optional per-phase device timing (bench.py's roofline leg): events on the launching stream
     std::vector<cudaEvent_t> ev;
@@ -64,7 +67,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         mark();
         int flags = (lse_sum ? MIMO_ACC_LSE : 0) | (lse_out ? MIMO_WRITE_LSE : 0)
                   | (hard ? MIMO_DRAW_LABELS : MIMO_WRITE_RESP);
-        int32_t* lab = labels_out ? labels_out + n0 : lab_tmp;
+        int32_t* lab = hard ? lab_all + n0 : nullptr;
         const double* uni = uniforms ? (const double*)uniforms + n0 : nullptr;
         void* lse_c = lse_out ? (char*)lse_out + (size_t)n0 * es : nullptr;
         rc = softmax(dtype, scratch, K, nc, C, flags, lse_c, uni, seed, point_offset + (uint64_t)n0, lab, lse_sum, st);
@@ -73,12 +76,19 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         if (ll_out)
             MIMO_CUDA(cudaMemcpy2DAsync((char*)ll_out + (size_t)n0 * es, (size_t)ldo * es, scratch, (size_t)C * es,
                                         (size_t)nc * es, K, cudaMemcpyDeviceToDevice, st));
-        if (stat) {
-            if (hard) rc = stats_hard(dtype, Zc, nc, D, ldz, lab, K, fi, fj, F, stat, hard_ws, hard_ws_bytes, false, st);
-            else      rc = stats_soft(dtype, Zc, nc, D, ldz, scratch, C, K, fi, fj, F, stat, st);
+        if (stat && !hard) {
+            rc = stats_soft(dtype, Zc, nc, D, ldz, scratch, C, K, fi, fj, F, stat, st);
             if (rc) return rc;
         }
         mark();
+    }
+    // Gibbs: ONE counting sort + segmented FP64 reduction over all N labels (re-reads Z once)
+    cudaEvent_t h0 = nullptr, h1 = nullptr;
+    if (stat && hard) {
+        if (phase_ms) { cudaEventCreate(&h0); cudaEventCreate(&h1); cudaEventRecord(h0, st); }
+        int rc = stats_hard(dtype, Z, N, D, ldz, lab_all, K, fi, fj, F, stat, hard_ws, hard_ws_bytes, false, st);
+        if (rc) return rc;
+        if (phase_ms) cudaEventRecord(h1, st);
     }
     if (phase_ms) {
         MIMO_CUDA(cudaStreamSynchronize(st));
@@ -88,7 +98,14 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
                 cudaEventElapsedTime(&ms, ev[i + ph], ev[i + ph + 1]);
                 phase_ms[ph] += ms;
             }
-            phase_ms[3] += hard ? 7.0 : 3.0;     // kernel launches of this chunk
+            phase_ms[3] += (hard || !stat) ? 2.0 : 3.0;     // kernel launches of this chunk
+        }
+        if (h0) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h0, h1);
+            phase_ms[2] += ms;
+            phase_ms[3] += 4.0;
+            cudaEventDestroy(h0); cudaEventDestroy(h1);
         }
         for (auto e : ev) cudaEventDestroy(e);
     }
