@@ -92,6 +92,25 @@ int mimo_softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags,
                  void* lse, const void* uniforms, uint64_t seed, uint64_t point_offset,
                  int32_t* labels, double* lse_sum, void* stream);
 
+/* ---- tensor-core (tcgen05 / TMEM) variants: FP32 data, quad family, D <= 128 ----
+ * Operands are split into two FP16 halves after a power-of-two pre-scale and the product is
+ * accumulated in FP32 as Ah*Bh + Ah*Bl + Al*Bh (22 significand bits, FP32-class results; see
+ * DESIGN.md section 5).  mimo_sweep picks these kernels by itself when
+ * mimo_sweep_uses_tensor_cores() says so; the stand-alone entry points exist for parity tests.
+ * Same reference call sites as mimo_loglik_quad / mimo_stats_soft.                          */
+int mimo_set_tensor_cores(int mode);        /* 0: CUDA cores only, 1 (default): automatic; returns the old mode */
+int mimo_sweep_uses_tensor_cores(int dtype, int family, int D, int Rp);
+int mimo_tc_set_flush_tiles(int tiles);     /* 128-point tiles accumulated in TMEM (FP32) between FP64 drains */
+size_t mimo_loglik_quad_tc_workspace(int K, int Rp, int D);
+int mimo_loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz,
+                        const void* W, const void* cst, int K, int Rp, int Dpp,
+                        void* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream);
+/* full-triangle packed statistics only (F = (D+1)(D+2)/2, the order documented above) */
+size_t mimo_stats_soft_tc_workspace(int64_t N, int K);
+int mimo_stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz,
+                       const void* resp, int64_t ldr, int K, int F,
+                       double* stat, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- weighted sufficient statistics ----------------------------------- */
 
 /* replaces: *.weighted_statistics  gaussian.py:491-505, 819-832; lingauss.py:306-325;
@@ -123,7 +142,7 @@ int mimo_stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz,
  *                              (mixtures/gmm.py:220-223 fused)
  * labels_out / lse_out / ll_out may be NULL.  ll_out, if given, is (K, N) and
  * receives the log-joint (hard) or the responsibilities (soft).             */
-size_t mimo_sweep_workspace(int dtype, int64_t N, int K, int hard);
+size_t mimo_sweep_workspace(int dtype, int family, int hard, int64_t N, int D, int K, int Rp);
 int mimo_sweep(int dtype, int family, int hard,
                const void* Z, int64_t N, int D, int64_t ldz,
                const void* op_a, const void* op_b, const void* cst, int K, int Rp, int Dpp,

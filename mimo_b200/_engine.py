@@ -236,13 +236,22 @@ class SweepBuffers:
 
     def __init__(self, N, K, F, precision, hard):
         self.N, self.K, self.F, self.precision, self.hard = N, K, F, precision, hard
-        self.wsb = _lib.load().mimo_sweep_workspace(code(precision), N, K, 1 if hard else 0)
-        self.ws = workspace(self.wsb)
+        self.wsb, self.ws = 0, None
         # statistics and the lower-bound scalar share one buffer: ONE all-reduce message per sweep
         self.flat = zeros((K * F + 1,), torch.float64)
         self.stat = self.flat[:K * F].view(K, F)
         self.lse_sum = self.flat[K * F:]
         self.labels = empty((N,), torch.int32) if hard else None
+
+    def ensure(self, ops, D):
+        """workspace for a sweep with these operands: the operand family / D / Rp decide whether
+        the tensor-core kernels (and their operand image / partial-statistics buffers) are used."""
+        need = _lib.load().mimo_sweep_workspace(code(self.precision), ops.family, 1 if self.hard else 0,
+                                                self.N, D, self.K, ops.Rp)
+        if self.ws is None or need > self.wsb:
+            self.ws = None
+            self.ws = workspace(need)
+            self.wsb = need
 
 
 def sweep(Z, ops, feats, buf, uniforms=None, seed=0, offset=0, ll_out=None, lse_out=None, zero=True,
@@ -252,6 +261,7 @@ def sweep(Z, ops, feats, buf, uniforms=None, seed=0, offset=0, ll_out=None, lse_
     accumulates per-phase device milliseconds and the launch count (synchronises)."""
     N, D = Z.shape
     fi, fj = feats.dev()
+    buf.ensure(ops, D)
     if zero:
         buf.stat.zero_()
         buf.lse_sum.zero_()
@@ -424,3 +434,38 @@ def mstep_lingauss(stat, F, stat_idx, Dp, K, c, o, tied=False, info=None):
     _lib.call('mimo_mstep_lingauss', K, c, o, int(tied), ptr(stat), F, ptr(stat_idx), Dp, ptr(A), ptr(lmbda),
               ptr(ws), wsb, ptr(info.t), stream())
     return A, lmbda, info
+
+
+# ---- tensor-core variants (stand-alone entry points; mimo_sweep dispatches by itself) ---------------
+def set_tensor_cores(mode):
+    """0: CUDA-core kernels only; 1: tcgen05 kernels where supported (default).  Returns the old mode."""
+    return _lib.load().mimo_set_tensor_cores(int(mode))
+
+
+def sweep_uses_tensor_cores(ops, D):
+    return bool(_lib.load().mimo_sweep_uses_tensor_cores(code(ops.precision), ops.family, D, ops.Rp))
+
+
+def loglik_tc(Z, ops, out=None):
+    N, D = Z.shape
+    assert ops.family == 0 and ops.precision == 'fp32' and Z.dtype == torch.float32
+    if out is None:
+        out = empty((ops.K, N), Z.dtype)
+    wsb = _lib.load().mimo_loglik_quad_tc_workspace(ops.K, ops.Rp, D)
+    ws = workspace(wsb)
+    _lib.call('mimo_loglik_quad_tc', ptr(Z), N, D, Z.stride(0), ptr(ops.W), ptr(ops.cst), ops.K, ops.Rp, ops.Dpp,
+              ptr(out), out.stride(0), ptr(ws), wsb, stream())
+    return out
+
+
+def stats_soft_tc(Z, resp, feats, stat=None):
+    N, D = Z.shape
+    K = resp.shape[0]
+    assert Z.dtype == torch.float32 and resp.dtype == torch.float32
+    if stat is None:
+        stat = zeros((K, feats.F), torch.float64)
+    wsb = _lib.load().mimo_stats_soft_tc_workspace(N, K)
+    ws = workspace(wsb)
+    _lib.call('mimo_stats_soft_tc', ptr(Z), N, D, Z.stride(0), ptr(resp), resp.stride(0), K, feats.F,
+              ptr(stat), ptr(ws), wsb, stream())
+    return stat

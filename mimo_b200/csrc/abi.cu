@@ -69,7 +69,22 @@ int mimo_stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, con
                     void* workspace, size_t workspace_bytes, void* stream) {
     return stats_hard(dtype, Z, N, D, ldz, labels, K, fi, fj, F, stat, workspace, workspace_bytes, true, ST(stream));
 }
-size_t mimo_sweep_workspace(int dtype, int64_t N, int K, int hard) { return sweep_workspace(dtype, N, K, hard); }
+size_t mimo_sweep_workspace(int dtype, int family, int hard, int64_t N, int D, int K, int Rp) {
+    return sweep_workspace(dtype, family, hard, N, D, K, Rp);
+}
+int mimo_set_tensor_cores(int mode) { return tc_set_mode(mode); }
+int mimo_sweep_uses_tensor_cores(int dtype, int family, int D, int Rp) { return sweep_uses_tc(dtype, family, D, Rp) ? 1 : 0; }
+int mimo_tc_set_flush_tiles(int tiles) { tc_set_flush_tiles(tiles); return MIMO_OK; }
+size_t mimo_loglik_quad_tc_workspace(int K, int Rp, int D) { return tc_operand_workspace(K, Rp, D); }
+int mimo_loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* W, const void* cst,
+                        int K, int Rp, int Dpp, void* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream) {
+    return loglik_quad_tc(Z, N, D, ldz, W, cst, K, Rp, Dpp, out, ldo, workspace, workspace_bytes, ST(stream));
+}
+size_t mimo_stats_soft_tc_workspace(int64_t N, int K) { return stats_soft_tc_workspace(N, K); }
+int mimo_stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K, int F,
+                       double* stat, void* workspace, size_t workspace_bytes, void* stream) {
+    return stats_soft_tc(Z, N, D, ldz, resp, ldr, K, F, stat, workspace, workspace_bytes, ST(stream));
+}
 int mimo_sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int64_t ldz,
                const void* op_a, const void* op_b, const void* cst, int K, int Rp, int Dpp,
                const int32_t* fi, const int32_t* fj, int F,

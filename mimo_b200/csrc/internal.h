@@ -20,8 +20,32 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
                const int32_t* fi, const int32_t* fj, int F, double* stat,
                void* workspace, size_t workspace_bytes, bool check, cudaStream_t st);
 
-int64_t sweep_chunk_points(int dtype, int64_t N, int K);
-size_t sweep_workspace(int dtype, int64_t N, int K, int hard);
+// tensor-core (tcgen05) path, FP32 quad family, D <= 128  (tc_estep.cu, tc_stats.cu)
+int tc_mode();                       // 0 = CUDA cores only, 1 = tensor cores where supported
+int tc_set_mode(int mode);
+bool tc_estep_supported(int dtype, int D, int Rp);
+size_t tc_operand_workspace(int K, int Rp, int D);
+int tc_data_scale(const float* Z, int64_t N, int D, int64_t ldz, void* ws, cudaStream_t st);
+const unsigned int* tc_maxbits(void* ws);
+int tc_prepare_operands(const float* W, int K, int Rp, int Dpp, int D, void* ws, cudaStream_t st);
+int tc_estep(const float* Z, int64_t N, int D, int64_t ldz, const float* cst, int K, int Rp,
+             float* out, int64_t ldo, void* ws, cudaStream_t st);
+int loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* W, const void* cst,
+                   int K, int Rp, int Dpp, void* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st);
+bool tc_stats_supported(int dtype, int D, int F);
+size_t tc_stats_workspace(int64_t chunk_points, int K);
+int tc_stats_begin(int64_t chunk_points, int K, void* ws, cudaStream_t st);
+int tc_stats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, int K, int F,
+                   const unsigned int* maxbits, double* stat, int64_t plan_points, void* ws, cudaStream_t st);
+int tc_stats_end(int64_t plan_points, int K, int D, int F, const unsigned int* maxbits, double* stat, void* ws, cudaStream_t st);
+void tc_set_flush_tiles(int tiles);
+size_t stats_soft_tc_workspace(int64_t N, int K);
+int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K, int F,
+                  double* stat, void* ws, size_t ws_bytes, cudaStream_t st);
+
+bool sweep_uses_tc(int dtype, int family, int D, int Rp);
+int64_t sweep_chunk_points(int dtype, int family, int64_t N, int D, int K, int Rp);
+size_t sweep_workspace(int dtype, int family, int hard, int64_t N, int D, int K, int Rp);
 int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int64_t ldz,
           const void* op_a, const void* op_b, const void* cst, int K, int Rp, int Dpp,
           const int32_t* fi, const int32_t* fj, int F,

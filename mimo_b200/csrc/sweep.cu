@@ -11,24 +11,50 @@ namespace mimo {
 
 static size_t a256(size_t x) { return (x + 255) / 256 * 256; }
 
-// points per chunk: keep the (K, chunk) scratch around 64 MB (half of the 126 MB L2) so the
-// softmax / statistics passes over it are served from L2
-int64_t sweep_chunk_points(int dtype, int64_t N, int K) {
+static int g_tc_mode = 1;
+int tc_mode() { return g_tc_mode; }
+int tc_set_mode(int mode) { int old = g_tc_mode; g_tc_mode = mode ? 1 : 0; return old; }
+
+// the tensor-core path takes FP32 quad-family sweeps whose contraction is wide enough to pay for
+// the 64-wide K blocks of the operand layout
+bool sweep_uses_tc(int dtype, int family, int D, int Rp) {
+    return g_tc_mode && family == 0 && D >= 24 && tc_estep_supported(dtype, D, Rp);
+}
+
+// points per chunk.
+//  CUDA-core path: keep the (K, chunk) scratch around 64 MB (half of the 126 MB L2) so the softmax /
+//    statistics passes over it are served from L2.
+//  tensor-core path: the kernels are persistent (one CTA per SM walking 256-point pairs / 4-component
+//    units), so a chunk is many waves of 256 x #SM points; the scratch (<= 4 GB) streams through HBM,
+//    which costs ~12 B per pair against ~66 kflop at d = 128.
+int64_t sweep_chunk_points(int dtype, int family, int64_t N, int D, int K, int Rp) {
     size_t es = dtype == MIMO_F32 ? 4 : 8;
+    int64_t npad = (N + 255) / 256 * 256;
+    if (npad <= 0) npad = 256;
+    if (sweep_uses_tc(dtype, family, D, Rp)) {
+        const int64_t wave = (int64_t)256 * sm_count();
+        int64_t c = (int64_t)(((size_t)4 << 30) / ((size_t)K * es));
+        c = c / wave * wave;
+        if (c < wave) c = wave;
+        return c < npad ? c : npad;
+    }
     int64_t c = (int64_t)((64u << 20) / ((size_t)K * es));
     c = c / 256 * 256;
     if (c < 1024) c = 1024;
     if (c > (1 << 20)) c = 1 << 20;
-    int64_t npad = (N + 255) / 256 * 256;
-    return c < npad ? c : (npad > 0 ? npad : 256);
+    return c < npad ? c : npad;
 }
 
-size_t sweep_workspace(int dtype, int64_t N, int K, int hard) {
+size_t sweep_workspace(int dtype, int family, int hard, int64_t N, int D, int K, int Rp) {
     size_t es = dtype == MIMO_F32 ? 4 : 8;
-    int64_t c = sweep_chunk_points(dtype, N, K);
+    int64_t c = sweep_chunk_points(dtype, family, N, D, K, Rp);
     size_t b = a256((size_t)K * c * es);
     // Gibbs: labels of ALL points (when the caller does not keep them) + one counting sort over N
     if (hard) b += a256((size_t)N * 4) + a256(stats_hard_workspace(N, K));
+    if (sweep_uses_tc(dtype, family, D, Rp)) {
+        b += a256(tc_operand_workspace(K, Rp, D));
+        if (!hard) b += a256(tc_stats_workspace(c, K));
+    }
     return b;
 }
 
@@ -42,16 +68,31 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     MIMO_CHECK_ARG(family == 0 || family == 1, "family");
     MIMO_CHECK_ARG(Z && op_a && cst && workspace && (family == 0 || op_b), "null pointer");
     MIMO_CHECK_ARG(!stat || (fi && fj && F >= 1), "feature tables");
-    MIMO_CHECK_ARG(workspace_bytes >= sweep_workspace(dtype, N, K, hard), "workspace too small");
+    MIMO_CHECK_ARG(workspace_bytes >= sweep_workspace(dtype, family, hard, N, D, K, Rp), "workspace too small");
     MIMO_CHECK_ARG(!ll_out || ldo >= N, "ldo");
     const size_t es = dtype == MIMO_F32 ? 4 : 8;
-    const int64_t C = sweep_chunk_points(dtype, N, K);
+    const bool use_tc = sweep_uses_tc(dtype, family, D, Rp);
+    const int64_t C = sweep_chunk_points(dtype, family, N, D, K, Rp);
     char* ws = (char*)workspace;
     void* scratch = ws; ws += a256((size_t)K * C * es);
     int32_t* lab_all = labels_out;
     if (hard && !lab_all) { lab_all = (int32_t*)ws; ws += a256((size_t)N * 4); }
     void* hard_ws = ws;
     const size_t hard_ws_bytes = hard ? stats_hard_workspace(N, K) : 0;
+    if (hard) ws += a256(hard_ws_bytes);
+    void* tc_ops_ws = nullptr;
+    void* tc_stat_ws = nullptr;
+    // the packed full-triangle statistics are what the tensor-core statistics kernel produces
+    const bool tc_stats = use_tc && stat && !hard && tc_stats_supported(dtype, D, F);
+    if (use_tc) {
+        tc_ops_ws = ws; ws += a256(tc_operand_workspace(K, Rp, D));
+        if (!hard) tc_stat_ws = ws;
+        int rc = tc_data_scale((const float*)Z, N, D, ldz, tc_ops_ws, st);
+        if (rc) return rc;
+        rc = tc_prepare_operands((const float*)op_a, K, Rp, Dpp, D, tc_ops_ws, st);
+        if (rc) return rc;
+        if (tc_stats) { rc = tc_stats_begin(C, K, tc_stat_ws, st); if (rc) return rc; }
+    }
 
     // optional per-phase device timing (bench.py's roofline leg): events on the launching stream
     std::vector<cudaEvent_t> ev;
@@ -61,7 +102,8 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         mark();
         const char* Zc = (const char*)Z + (size_t)n0 * ldz * es;
         int rc;
-        if (family == 0) rc = loglik_quad(dtype, Zc, nc, D, ldz, op_a, cst, K, Rp, Dpp, scratch, C, st);
+        if (use_tc)           rc = tc_estep((const float*)Zc, nc, D, ldz, (const float*)cst, K, Rp, (float*)scratch, C, tc_ops_ws, st);
+        else if (family == 0) rc = loglik_quad(dtype, Zc, nc, D, ldz, op_a, cst, K, Rp, Dpp, scratch, C, st);
         else             rc = loglik_diag(dtype, Zc, nc, D, ldz, op_a, op_b, cst, K, scratch, C, st);
         if (rc) return rc;
         mark();
@@ -76,11 +118,18 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         if (ll_out)
             MIMO_CUDA(cudaMemcpy2DAsync((char*)ll_out + (size_t)n0 * es, (size_t)ldo * es, scratch, (size_t)C * es,
                                         (size_t)nc * es, K, cudaMemcpyDeviceToDevice, st));
-        if (stat && !hard) {
+        if (tc_stats) {
+            rc = tc_stats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, F, tc_maxbits(tc_ops_ws), stat, C, tc_stat_ws, st);
+            if (rc) return rc;
+        } else if (stat && !hard) {
             rc = stats_soft(dtype, Zc, nc, D, ldz, scratch, C, K, fi, fj, F, stat, st);
             if (rc) return rc;
         }
         mark();
+    }
+    if (tc_stats) {
+        int rc = tc_stats_end(C, K, D, F, tc_maxbits(tc_ops_ws), stat, tc_stat_ws, st);
+        if (rc) return rc;
     }
     // Gibbs: ONE counting sort + segmented FP64 reduction over all N labels (re-reads Z once)
     cudaEvent_t h0 = nullptr, h1 = nullptr;
@@ -122,7 +171,7 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
     const size_t es = dtype == MIMO_F32 ? 4 : 8;
     const size_t zb = (size_t)N * D * es;
     const size_t ab = (family == 0 ? (size_t)K * Rp * Dpp : (size_t)K * D) * es;
-    const size_t wsb = sweep_workspace(dtype, N, K, hard);
+    const size_t wsb = sweep_workspace(dtype, family, hard, N, D, K, Rp);
     char *dZ = nullptr, *dA = nullptr, *dB = nullptr, *dC = nullptr, *dws = nullptr;
     int32_t *dfi = nullptr, *dfj = nullptr, *dlab = nullptr;
     double *dstat = nullptr, *dlse = nullptr, *duni = nullptr;
@@ -163,6 +212,30 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
     cudaFree(dZ); cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dws); cudaFree(dfi); cudaFree(dfj);
     cudaFree(dlab); cudaFree(dstat); cudaFree(dlse); cudaFree(duni);
     return rc;
+}
+
+}  // namespace mimo
+
+namespace mimo {
+
+// stand-alone tensor-core statistics (mimo_stats_soft_tc): data scale + one chunk + reduce
+size_t stats_soft_tc_workspace(int64_t N, int K) { return 2048 + tc_stats_workspace(N, K); }
+
+int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K, int F,
+                  double* stat, void* ws, size_t ws_bytes, cudaStream_t st) {
+    MIMO_CHECK_ARG(Z && resp && stat && ws, "null pointer");
+    MIMO_CHECK_ARG(N >= 0 && K >= 1 && ldz >= D && ldr >= N, "shape");
+    if (!tc_stats_supported(MIMO_F32, D, F)) { set_error("tensor-core statistics: unsupported shape D=%d F=%d", D, F); return MIMO_EUNSUPPORTED; }
+    MIMO_CHECK_ARG(ws_bytes >= stats_soft_tc_workspace(N, K), "workspace too small");
+    if (N == 0) return MIMO_OK;
+    int rc = tc_data_scale((const float*)Z, N, D, ldz, ws, st);
+    if (rc) return rc;
+    void* pws = (char*)ws + 2048;
+    rc = tc_stats_begin(N, K, pws, st);
+    if (rc) return rc;
+    rc = tc_stats_chunk((const float*)Z, N, D, ldz, (const float*)resp, ldr, K, F, tc_maxbits(ws), stat, N, pws, st);
+    if (rc) return rc;
+    return tc_stats_end(N, K, D, F, tc_maxbits(ws), stat, pws, st);
 }
 
 }  // namespace mimo

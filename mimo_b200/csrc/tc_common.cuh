@@ -1,0 +1,163 @@
+// sm_100a building blocks of the tensor-core kernels: mbarrier, TMEM allocation,
+// tcgen05.mma / tcgen05.ld / tcgen05.commit, 1-D bulk copies (TMA engine) and the
+// shared-memory matrix descriptors of the K-major 128-byte-swizzled operand layout.
+//
+// Numerical scheme shared by tc_estep.cu and tc_stats.cu ("3 x FP16 split"): an FP32
+// operand x (pre-scaled by a power of two so that the largest magnitude sits in
+// [2^13, 2^14)) is written as hi + lo with hi = fp16(x), lo = fp16(x - hi): 22
+// significand bits, the same as 3xTF32 but on the kind::f16 pipe (twice the TF32 rate).
+// A product is accumulated in FP32 in TMEM as  Ah*Bh + Ah*Bl + Al*Bh  (the dropped
+// Al*Bl term is ~2^-22 relative).  Powers of two are undone exactly in the epilogue.
+#pragma once
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace mimo {
+namespace tc {
+
+constexpr long long WATCHDOG_CYCLES = 6000000000ll;   // ~3 s: a stuck pipeline traps instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > WATCHDOG_CYCLES) asm volatile("trap;");
+    }
+}
+
+// ---- proxies / tcgen05 fences ----------------------------------------------------
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM --------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {      // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 32 consecutive FP32 columns of this thread's TMEM lane (lane = 32 * (warp % 4) + laneid)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- UMMA --------------------------------------------------------------------------
+// D[tmem] (+)= A[smem] * B[smem]^T, FP16 operands, FP32 accumulate, one CTA; issued by ONE thread.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on `bar` when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// instruction descriptor: A, B = FP16 (K-major), D = FP32, shape M x N x 16
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 64 FP16 (128 B), 8-row groups 1024 B apart.
+// The tile base must be 1024-byte aligned; a K step of 16 elements advances the start address by 32 B (+2).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;      // leading byte offset (unused for swizzled K-major layouts)
+    d |= (uint64_t)64 << 32;     // stride byte offset: 1024 B between 8-row groups
+    d |= (uint64_t)1 << 46;      // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;      // SWIZZLE_128B
+    return d;
+}
+// byte offset of the 16-byte chunk `chunk` (8 FP16) of row `row` inside a [rows][64] FP16 tile
+__host__ __device__ __forceinline__ uint32_t sw128_chunk_off(int row, int chunk) {
+    return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+}
+
+// ---- bulk copy global -> shared through the TMA engine (no tensor map: the source is already
+//      laid out as the shared-memory image) ------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- 3 x FP16 split ------------------------------------------------------------------------
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+// four values -> 8 bytes of hi and 8 bytes of lo
+__device__ __forceinline__ void split4(const float (&x)[4], uint2& hi, uint2& lo) {
+    __half h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_f16(x[i], h[i], l[i]);
+    __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+    __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+    hi = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+    lo = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+}
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+    float a[4] = {x[0], x[1], x[2], x[3]}, b[4] = {x[4], x[5], x[6], x[7]};
+    uint2 h0, l0, h1, l1;
+    split4(a, h0, l0);
+    split4(b, h1, l1);
+    hi = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
+}
+
+// power-of-two scale that puts `maxabs` into [2^13, 2^14) (1 when maxabs is 0 or not finite)
+__host__ __device__ __forceinline__ float pow2_scale_for(float maxabs) {
+    if (!(maxabs > 0.f) || !(maxabs < 3.0e38f)) return 1.f;
+    int e;
+    frexpf(maxabs, &e);                      // maxabs = m * 2^e, m in [0.5, 1)
+    int s = 14 - e;
+    s = s > 40 ? 40 : (s < -40 ? -40 : s);
+    return ldexpf(1.f, s);
+}
+
+}  // namespace tc
+}  // namespace mimo

@@ -1,0 +1,148 @@
+"""Parity of the tensor-core (tcgen05) kernels with the CPU oracle and with the CUDA-core
+FP32 kernels (GPU only).  Same tolerance as the FP32 mode: rel 1e-4 against the oracle
+(north_star); additionally the 3xFP16-split results must sit within a small multiple of
+the FP32 kernels' own error.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mimo_oracle as orc
+from test_gpu_kernels import close, eng, spd, unpack_quad
+
+pytestmark = pytest.mark.gpu
+
+
+def scaled_err(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return float(np.max(np.abs(np.asarray(a, float) - b)) / max(1.0, float(np.max(np.abs(b)))))
+
+
+@pytest.mark.parametrize('K,d,N,shift', [(5, 128, 300, 0.0), (9, 16, 1000, 1.0), (3, 64, 700, 0.0), (70, 100, 513, 3.0),
+                                         (33, 128, 2100, 5.0), (4, 2, 500, 0.0), (2, 65, 257, 0.0)])
+def test_loglik_tc(K, d, N, shift):
+    E = eng()
+    rng = np.random.default_rng(d + K)
+    x = rng.standard_normal((N, d)) * 2 + rng.standard_normal(d) + shift
+    mus = rng.standard_normal((K, d)) * 2 + shift
+    lmbdas = np.stack([spd(rng, d) for _ in range(K)])
+    logw = np.log(rng.dirichlet(np.ones(K)))
+    ops = E.QuadOperands(K, d, d, 'fp32')
+    E.set_log_weights(ops, logw)
+    E.operands_gauss(ops, E.to_dev(mus), E.to_dev(lmbdas)).check()
+    Z = E.to_dev(x, torch.float32)
+    ll_tc = E.loglik_tc(Z, ops)
+    ll_cc = E.loglik(Z, ops)
+    xr = Z.double().cpu().numpy()
+    ref = orc.gauss_full_loglik(xr, mus, lmbdas) + logw[:, None]
+    close(ll_tc, ref, 1e-4, 'tensor-core log-lik')
+    e_tc, e_cc = scaled_err(ll_tc, ref), scaled_err(ll_cc, ref)
+    print('loglik K=%d d=%d N=%d: scaled err tensor-core %.2e, CUDA-core fp32 %.2e' % (K, d, N, e_tc, e_cc))
+    assert e_tc <= max(4 * e_cc, 2e-6)
+
+
+def test_loglik_tc_strided_rows_and_tiny_scale():
+    """ldz > D, unaligned row stride (scalar load path), data of magnitude 1e-3."""
+    E = eng()
+    rng = np.random.default_rng(0)
+    K, d, N = 6, 37, 1000
+    big = torch.zeros((N, d + 3), dtype=torch.float32, device=E.device())
+    x = rng.standard_normal((N, d)) * 1e-3
+    big[:, :d] = E.to_dev(x, torch.float32)
+    Z = big[:, :d]
+    mus = rng.standard_normal((K, d)) * 1e-3
+    lmbdas = np.stack([spd(rng, d, 1e6) for _ in range(K)])
+    ops = E.QuadOperands(K, d, d, 'fp32')
+    E.operands_gauss(ops, E.to_dev(mus), E.to_dev(lmbdas)).check()
+    ll = E.loglik_tc(Z, ops)
+    ref = orc.gauss_full_loglik(Z.double().cpu().numpy(), mus, lmbdas)
+    close(ll, ref, 1e-4, 'strided tensor-core log-lik')
+
+
+@pytest.mark.parametrize('K,d,N,flush', [(3, 128, 400, 16), (6, 128, 5000, 2), (70, 16, 2100, 16), (5, 40, 1000, 1),
+                                         (9, 128, 20000, 16), (1, 3, 130, 16)])
+def test_stats_tc(K, d, N, flush):
+    E = eng()
+    from mimo_b200 import _lib
+    rng = np.random.default_rng(K + d)
+    x = rng.standard_normal((N, d)) + 2.0
+    w = rng.random((K, N)) ** 4
+    w /= w.sum(0)
+    Z, R = E.to_dev(x, torch.float32), E.to_dev(w, torch.float32)
+    feats = E.quad_features(d)
+    _lib.load().mimo_tc_set_flush_tiles(flush)
+    try:
+        st = E.stats_soft_tc(Z, R, feats).cpu().numpy()
+    finally:
+        _lib.load().mimo_tc_set_flush_tiles(16)
+    cc = E.stats_soft(Z, R, feats, 'fp32').cpu().numpy()
+    ref = orc.gauss_full_wstats(Z.double().cpu().numpy(), R.double().cpu().numpy())
+    S, C = unpack_quad(st, d), unpack_quad(cc, d)
+    close(S[:, :d, :d], ref[2], 1e-4, 'tc sum r xx')
+    close(S[:, d, :d], ref[0], 1e-4, 'tc sum r x')
+    close(S[:, d, d], ref[1], 1e-4, 'tc sum r')
+    e_tc, e_cc = scaled_err(S[:, :d, :d], ref[2]), scaled_err(C[:, :d, :d], ref[2])
+    print('stats K=%d d=%d N=%d flush=%d: scaled err tensor-core %.2e, CUDA-core fp32 %.2e' % (K, d, N, flush, e_tc, e_cc))
+    assert e_tc <= max(8 * e_cc, 4e-6)
+
+
+def test_stats_tc_accumulates_into_stat():
+    """stat is accumulated into (the contract of mimo_stats_soft)."""
+    E = eng()
+    rng = np.random.default_rng(1)
+    K, d, N = 4, 32, 600
+    Z = E.to_dev(rng.standard_normal((N, d)), torch.float32)
+    R = E.to_dev(rng.random((K, N)), torch.float32)
+    feats = E.quad_features(d)
+    one = E.stats_soft_tc(Z, R, feats)
+    two = E.stats_soft_tc(Z, R, feats, stat=one.clone())
+    close(two, 2 * one.cpu().numpy(), 1e-12, 'accumulation')
+
+
+@pytest.mark.parametrize('hard', [False, True])
+@pytest.mark.parametrize('K,d,N', [(12, 32, 70000), (7, 128, 45000)])
+def test_sweep_tc_matches_cuda_cores_and_oracle(hard, K, d, N):
+    """mimo_sweep on the tensor-core path == the CUDA-core FP32 path within FP32 tolerance,
+    and the statistics / lower-bound term match the oracle."""
+    E = eng()
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((N, d)) + rng.integers(0, 3, size=(N, 1))
+    mus = rng.standard_normal((K, d)) + rng.integers(0, 3, size=(K, 1))
+    lmbdas = np.stack([spd(rng, d) for _ in range(K)])
+    logw = np.log(rng.dirichlet(np.ones(K)))
+    ops = E.QuadOperands(K, d, d, 'fp32')
+    E.set_log_weights(ops, logw)
+    E.operands_gauss(ops, E.to_dev(mus), E.to_dev(lmbdas)).check()
+    Z = E.to_dev(x, torch.float32)
+    feats = E.quad_features(d)
+    assert E.sweep_uses_tensor_cores(ops, d)
+    u = E.to_dev(rng.random(N))
+    buf = E.SweepBuffers(N, K, feats.F, 'fp32', hard)
+    E.sweep(Z, ops, feats, buf, uniforms=u if hard else None)
+    old = E.set_tensor_cores(0)
+    try:
+        assert not E.sweep_uses_tensor_cores(ops, d)
+        ref = E.SweepBuffers(N, K, feats.F, 'fp32', hard)
+        E.sweep(Z, ops, feats, ref, uniforms=u if hard else None)
+    finally:
+        E.set_tensor_cores(old)
+    xr = Z.double().cpu().numpy()
+    ll = orc.gauss_full_loglik(xr, mus, lmbdas) + logw[:, None]
+    resp, lse = orc.responsibilities(ll)
+    close(buf.lse_sum, [lse.sum()], 1e-6, 'lse sum vs oracle')
+    close(buf.lse_sum, ref.lse_sum.cpu().numpy(), 1e-6, 'lse sum vs CUDA cores')
+    if hard:
+        lab, lab_cc = buf.labels.cpu().numpy(), ref.labels.cpu().numpy()
+        lab_ref = orc.sample_discrete_from_log(ll, u.cpu().numpy())
+        safe = orc.label_boundary_distance(ll, u.cpu().numpy()) > 1e-3
+        assert np.array_equal(lab[safe], lab_ref[safe])
+        assert (lab == lab_cc).mean() > 0.999
+        st = orc.gauss_full_wstats(xr, orc.one_hot(lab, K))
+    else:
+        st = orc.gauss_full_wstats(xr, resp)
+    S = unpack_quad(buf.stat.cpu().numpy(), d)
+    close(S[:, :d, :d], st[2], 1e-4, 'sweep sum r xx')
+    close(S[:, d, :d], st[0], 1e-4, 'sweep sum r x')
+    close(S[:, d, d], st[1], 1e-4, 'sweep sum r')
+    if not hard:
+        close(buf.stat, ref.stat.cpu().numpy(), 2e-5, 'tensor-core vs CUDA-core statistics')
