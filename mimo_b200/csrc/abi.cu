@@ -74,7 +74,7 @@ size_t mimo_sweep_workspace(int dtype, int family, int hard, int64_t N, int D, i
 }
 int mimo_set_tensor_cores(int mode) { return tc_set_mode(mode); }
 int mimo_sweep_uses_tensor_cores(int dtype, int family, int D, int Rp) { return sweep_uses_tc(dtype, family, D, Rp) ? 1 : 0; }
-int mimo_tc_set_flush_tiles(int tiles) { tc_set_flush_tiles(tiles); return MIMO_OK; }
+int mimo_tc_set_flush_tiles(int tiles) { tc_set_flush_tiles(tiles); tc_fstats_set_flush_tiles(tiles); return MIMO_OK; }
 size_t mimo_loglik_quad_tc_workspace(int K, int Rp, int D) { return tc_operand_workspace(K, Rp, D); }
 int mimo_loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* W, const void* cst,
                         int K, int Rp, int Dpp, void* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream) {

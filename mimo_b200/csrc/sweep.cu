@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "internal.h"
 #include <vector>
+#include <algorithm>
 
 namespace mimo {
 
@@ -53,7 +54,7 @@ size_t sweep_workspace(int dtype, int family, int hard, int64_t N, int D, int K,
     if (hard) b += a256((size_t)N * 4) + a256(stats_hard_workspace(N, K));
     if (sweep_uses_tc(dtype, family, D, Rp)) {
         b += a256(tc_operand_workspace(K, Rp, D));
-        if (!hard) b += a256(tc_stats_workspace(c, K));
+        if (!hard) b += a256(std::max(tc_stats_workspace(c, K), tc_fstats_workspace(K)));
     }
     return b;
 }
@@ -84,6 +85,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     void* tc_stat_ws = nullptr;
     // the packed full-triangle statistics are what the tensor-core statistics kernel produces
     const bool tc_stats = use_tc && stat && !hard && tc_stats_supported(dtype, D, F);
+    const bool tc_fstats = tc_stats && tc_fstats_supported(dtype, D, F);     // feature form (folded triangle) for D > 64
     if (use_tc) {
         tc_ops_ws = ws; ws += a256(tc_operand_workspace(K, Rp, D));
         if (!hard) tc_stat_ws = ws;
@@ -91,7 +93,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         if (rc) return rc;
         rc = tc_prepare_operands((const float*)op_a, K, Rp, Dpp, D, tc_ops_ws, st);
         if (rc) return rc;
-        if (tc_stats) { rc = tc_stats_begin(C, K, tc_stat_ws, st); if (rc) return rc; }
+        if (tc_stats) { rc = tc_fstats ? tc_fstats_begin(K, tc_stat_ws, st) : tc_stats_begin(C, K, tc_stat_ws, st); if (rc) return rc; }
     }
 
     // optional per-phase device timing (bench.py's roofline leg): events on the launching stream
@@ -119,7 +121,8 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             MIMO_CUDA(cudaMemcpy2DAsync((char*)ll_out + (size_t)n0 * es, (size_t)ldo * es, scratch, (size_t)C * es,
                                         (size_t)nc * es, K, cudaMemcpyDeviceToDevice, st));
         if (tc_stats) {
-            rc = tc_stats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, F, tc_maxbits(tc_ops_ws), stat, C, tc_stat_ws, st);
+            rc = tc_fstats ? tc_fstats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, tc_maxbits(tc_ops_ws), tc_stat_ws, st)
+                           : tc_stats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, F, tc_maxbits(tc_ops_ws), stat, C, tc_stat_ws, st);
             if (rc) return rc;
         } else if (stat && !hard) {
             rc = stats_soft(dtype, Zc, nc, D, ldz, scratch, C, K, fi, fj, F, stat, st);
@@ -128,7 +131,8 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         mark();
     }
     if (tc_stats) {
-        int rc = tc_stats_end(C, K, D, F, tc_maxbits(tc_ops_ws), stat, tc_stat_ws, st);
+        int rc = tc_fstats ? tc_fstats_end(K, D, F, tc_maxbits(tc_ops_ws), stat, tc_stat_ws, st)
+                           : tc_stats_end(C, K, D, F, tc_maxbits(tc_ops_ws), stat, tc_stat_ws, st);
         if (rc) return rc;
     }
     // Gibbs: ONE counting sort + segmented FP64 reduction over all N labels (re-reads Z once)
@@ -219,7 +223,7 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
 namespace mimo {
 
 // stand-alone tensor-core statistics (mimo_stats_soft_tc): data scale + one chunk + reduce
-size_t stats_soft_tc_workspace(int64_t N, int K) { return 2048 + tc_stats_workspace(N, K); }
+size_t stats_soft_tc_workspace(int64_t N, int K) { return 2048 + std::max(tc_stats_workspace(N, K), tc_fstats_workspace(K)); }
 
 int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K, int F,
                   double* stat, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -231,6 +235,13 @@ int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp
     int rc = tc_data_scale((const float*)Z, N, D, ldz, ws, st);
     if (rc) return rc;
     void* pws = (char*)ws + 2048;
+    if (tc_fstats_supported(MIMO_F32, D, F)) {
+        rc = tc_fstats_begin(K, pws, st);
+        if (rc) return rc;
+        rc = tc_fstats_chunk((const float*)Z, N, D, ldz, (const float*)resp, ldr, K, tc_maxbits(ws), pws, st);
+        if (rc) return rc;
+        return tc_fstats_end(K, D, F, tc_maxbits(ws), stat, pws, st);
+    }
     rc = tc_stats_begin(N, K, pws, st);
     if (rc) return rc;
     rc = tc_stats_chunk((const float*)Z, N, D, ldz, (const float*)resp, ldr, K, F, tc_maxbits(ws), stat, N, pws, st);

@@ -41,6 +41,30 @@ def test_loglik_tc(K, d, N, shift):
     assert e_tc <= max(4 * e_cc, 2e-6)
 
 
+@pytest.mark.parametrize('K,d,rows', [(5, 128, 128), (7, 70, 70), (6, 40, 64), (9, 33, 17)])
+def test_loglik_tc_dense_operands(K, d, rows):
+    """operand rows that are NOT triangular (what the ILR stack of basis + expert rows looks like):
+    the issuer must fall back to full-width MMAs."""
+    E = eng()
+    rng = np.random.default_rng(5)
+    N = 900
+    ops = E.QuadOperands(K, d, rows, 'fp32')
+    W = np.zeros((K, ops.Rp, ops.Dpp))
+    W[:, :rows, :d + 1] = rng.standard_normal((K, rows, d + 1)) / np.sqrt(d)
+    cst = rng.standard_normal(K)
+    ops.W.copy_(E.to_dev(W, torch.float32))
+    ops.cst.copy_(E.to_dev(cst, torch.float32))
+    x = rng.standard_normal((N, d)) * 1.5 + 0.5
+    Z = E.to_dev(x, torch.float32)
+    ll = E.loglik_tc(Z, ops)
+    Wr = ops.W.double().cpu().numpy()
+    zt = np.concatenate([Z.double().cpu().numpy(), np.ones((N, 1))], axis=1)
+    y = np.einsum('kij,nj->kni', Wr[:, :, :d + 1], zt)
+    ref = ops.cst.double().cpu().numpy()[:, None] - 0.5 * np.sum(y * y, axis=2)
+    close(ll, ref, 1e-4, 'dense-operand tensor-core log-lik')
+    close(ll, E.loglik(Z, ops).cpu().numpy(), 2e-5, 'tensor-core vs CUDA-core log-lik')
+
+
 def test_loglik_tc_strided_rows_and_tiny_scale():
     """ldz > D, unaligned row stride (scalar load path), data of magnitude 1e-3."""
     E = eng()
@@ -60,7 +84,9 @@ def test_loglik_tc_strided_rows_and_tiny_scale():
 
 
 @pytest.mark.parametrize('K,d,N,flush', [(3, 128, 400, 16), (6, 128, 5000, 2), (70, 16, 2100, 16), (5, 40, 1000, 1),
-                                         (9, 128, 20000, 16), (1, 3, 130, 16)])
+                                         (9, 128, 20000, 16), (1, 3, 130, 16),
+                                         # feature-form kernel (64 < d <= 128): ragged K / d / N, several component blocks
+                                         (300, 100, 3000, 16), (130, 65, 1001, 1), (1, 128, 63, 16), (257, 127, 70000, 4)])
 def test_stats_tc(K, d, N, flush):
     E = eng()
     from mimo_b200 import _lib
@@ -83,7 +109,8 @@ def test_stats_tc(K, d, N, flush):
     close(S[:, d, d], ref[1], 1e-4, 'tc sum r')
     e_tc, e_cc = scaled_err(S[:, :d, :d], ref[2]), scaled_err(C[:, :d, :d], ref[2])
     print('stats K=%d d=%d N=%d flush=%d: scaled err tensor-core %.2e, CUDA-core fp32 %.2e' % (K, d, N, flush, e_tc, e_cc))
-    assert e_tc <= max(8 * e_cc, 4e-6)
+    # FP32 accumulation in TMEM over one flush window (16 x 128 points) costs ~1e-5 of the largest entry
+    assert e_tc <= max(8 * e_cc, 3e-5)
 
 
 def test_stats_tc_accumulates_into_stat():
