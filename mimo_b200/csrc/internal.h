@@ -41,11 +41,11 @@ int tc_stats_end(int64_t plan_points, int K, int D, int F, const unsigned int* m
 void tc_set_flush_tiles(int tiles);
 // feature-form statistics (tc_fstats.cu): folded lower triangle, 64 < D <= 128
 bool tc_fstats_supported(int dtype, int D, int F);
-size_t tc_fstats_workspace(int K);
-int tc_fstats_begin(int K, void* ws, cudaStream_t st);
+size_t tc_fstats_workspace(int64_t chunk_points, int K);
+int tc_fstats_begin(int64_t chunk_points, int K, void* ws, cudaStream_t st);
 int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, int K,
-                    const unsigned int* maxbits, void* ws, cudaStream_t st);
-int tc_fstats_end(int K, int D, int F, const unsigned int* maxbits, double* stat, void* ws, cudaStream_t st);
+                    const unsigned int* maxbits, int64_t plan_points, void* ws, cudaStream_t st);
+int tc_fstats_end(int64_t plan_points, int K, int D, int F, const unsigned int* maxbits, double* stat, void* ws, cudaStream_t st);
 void tc_fstats_set_flush_tiles(int tiles);
 size_t stats_soft_tc_workspace(int64_t N, int K);
 int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K, int F,

@@ -54,7 +54,7 @@ size_t sweep_workspace(int dtype, int family, int hard, int64_t N, int D, int K,
     if (hard) b += a256((size_t)N * 4) + a256(stats_hard_workspace(N, K));
     if (sweep_uses_tc(dtype, family, D, Rp)) {
         b += a256(tc_operand_workspace(K, Rp, D));
-        if (!hard) b += a256(std::max(tc_stats_workspace(c, K), tc_fstats_workspace(K)));
+        if (!hard) b += a256(std::max(tc_stats_workspace(c, K), tc_fstats_workspace(c, K)));
     }
     return b;
 }
@@ -93,7 +93,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         if (rc) return rc;
         rc = tc_prepare_operands((const float*)op_a, K, Rp, Dpp, D, tc_ops_ws, st);
         if (rc) return rc;
-        if (tc_stats) { rc = tc_fstats ? tc_fstats_begin(K, tc_stat_ws, st) : tc_stats_begin(C, K, tc_stat_ws, st); if (rc) return rc; }
+        if (tc_stats) { rc = tc_fstats ? tc_fstats_begin(C, K, tc_stat_ws, st) : tc_stats_begin(C, K, tc_stat_ws, st); if (rc) return rc; }
     }
 
     // optional per-phase device timing (bench.py's roofline leg): events on the launching stream
@@ -121,7 +121,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             MIMO_CUDA(cudaMemcpy2DAsync((char*)ll_out + (size_t)n0 * es, (size_t)ldo * es, scratch, (size_t)C * es,
                                         (size_t)nc * es, K, cudaMemcpyDeviceToDevice, st));
         if (tc_stats) {
-            rc = tc_fstats ? tc_fstats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, tc_maxbits(tc_ops_ws), tc_stat_ws, st)
+            rc = tc_fstats ? tc_fstats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, tc_maxbits(tc_ops_ws), C, tc_stat_ws, st)
                            : tc_stats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, F, tc_maxbits(tc_ops_ws), stat, C, tc_stat_ws, st);
             if (rc) return rc;
         } else if (stat && !hard) {
@@ -131,7 +131,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         mark();
     }
     if (tc_stats) {
-        int rc = tc_fstats ? tc_fstats_end(K, D, F, tc_maxbits(tc_ops_ws), stat, tc_stat_ws, st)
+        int rc = tc_fstats ? tc_fstats_end(C, K, D, F, tc_maxbits(tc_ops_ws), stat, tc_stat_ws, st)
                            : tc_stats_end(C, K, D, F, tc_maxbits(tc_ops_ws), stat, tc_stat_ws, st);
         if (rc) return rc;
     }
@@ -223,7 +223,7 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
 namespace mimo {
 
 // stand-alone tensor-core statistics (mimo_stats_soft_tc): data scale + one chunk + reduce
-size_t stats_soft_tc_workspace(int64_t N, int K) { return 2048 + std::max(tc_stats_workspace(N, K), tc_fstats_workspace(K)); }
+size_t stats_soft_tc_workspace(int64_t N, int K) { return 2048 + std::max(tc_stats_workspace(N, K), tc_fstats_workspace(N, K)); }
 
 int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K, int F,
                   double* stat, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -236,11 +236,11 @@ int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp
     if (rc) return rc;
     void* pws = (char*)ws + 2048;
     if (tc_fstats_supported(MIMO_F32, D, F)) {
-        rc = tc_fstats_begin(K, pws, st);
+        rc = tc_fstats_begin(N, K, pws, st);
         if (rc) return rc;
-        rc = tc_fstats_chunk((const float*)Z, N, D, ldz, (const float*)resp, ldr, K, tc_maxbits(ws), pws, st);
+        rc = tc_fstats_chunk((const float*)Z, N, D, ldz, (const float*)resp, ldr, K, tc_maxbits(ws), N, pws, st);
         if (rc) return rc;
-        return tc_fstats_end(K, D, F, tc_maxbits(ws), stat, pws, st);
+        return tc_fstats_end(N, K, D, F, tc_maxbits(ws), stat, pws, st);
     }
     rc = tc_stats_begin(N, K, pws, st);
     if (rc) return rc;

@@ -16,13 +16,10 @@
 // log-joint scratch with coalesced stores.  The offset W[k][i][D] is applied in the epilogue,
 // not in the GEMM, so D = 128 needs no extra K step.
 //
-// Triangular operands.  The whitening rows the posterior kernels emit are Cholesky factors
-// (U_k of gaussian.py:298, C_k^T of composite.py:106-118): row i is zero left of column i.  The
-// operand-image kernel checks that (per 16 x 16 block) and, when it holds for every component
-// with Rp >= 64, the issuer walks the 16-wide K steps from the last to the first with
-// N = 16 (s + 1) instead of N = Rp -- the first MMA still initialises all columns -- which
-// removes 44 % of the tensor-pipe work at d = 128; the all-zero half of the first K block
-// is not copied either.  K steps beyond D are skipped in both modes.
+// K steps (16 columns) beyond D carry no data and are skipped.  (A variant that also skipped the
+// zero lower-triangular blocks of Cholesky-factor operands with narrower MMAs was measured
+// slower on B200: with both operands in shared memory a 128 x N x 16 MMA is bound by the
+// 4 KB A-operand read, not by N.)
 #include "tc_common.cuh"
 #include "internal.h"
 
@@ -61,7 +58,7 @@ __global__ void tc_absmax_kernel(const float* __restrict__ Z, int64_t N, int D, 
 //   invS2  [k]             = 1 / (sw_k * sz)^2
 __global__ void __launch_bounds__(256)
 tc_prep_operands_kernel(const float* __restrict__ W, int K, int Rp, int Dpp, int D, int KB,
-                        unsigned int* __restrict__ maxbits,   // [0] max |z| bits, [1] set when some W is not block upper triangular
+                        const unsigned int* __restrict__ maxbits,
                         __half* __restrict__ Bimg, float* __restrict__ rowoff, float* __restrict__ invS2) {
     __shared__ unsigned int cmax[16];
     __shared__ float csw[16];
@@ -70,18 +67,12 @@ tc_prep_operands_kernel(const float* __restrict__ W, int K, int Rp, int Dpp, int
     const float sz = pow2_scale_for(__uint_as_float(*maxbits));
     if (tid < 16) cmax[tid] = 0u;
     __syncthreads();
-    bool lower = false;
     for (int idx = tid; idx < 128 * D; idx += 256) {
         int r = idx / D, j = idx - r * D;
         int64_t flat = (int64_t)c * 128 + r;
         int k = (int)(flat / Rp);
-        if (k < K) {
-            const float w = W[flat * Dpp + j];
-            atomicMax(&cmax[r / Rp], __float_as_uint(fabsf(w)));
-            if (w != 0.f && (j >> 4) < ((r % Rp) >> 4)) lower = true;      // below the 16 x 16 block diagonal
-        }
+        if (k < K) atomicMax(&cmax[r / Rp], __float_as_uint(fabsf(W[flat * Dpp + j])));
     }
-    if (lower) atomicOr(maxbits + 1, 1u);
     __syncthreads();
     if (tid < cpc) {
         float sw = pow2_scale_for(__uint_as_float(cmax[tid]));
@@ -110,8 +101,7 @@ tc_prep_operands_kernel(const float* __restrict__ W, int K, int Rp, int Dpp, int
         uint4 hi, lo;
         split8(x, hi, lo);
         int kb = ch >> 3, cc = ch & 7;
-        // stages are stored (and streamed) from the LAST K block to the first: see the issuer
-        char* base = img + (size_t)(KB - 1 - kb) * TE_STAGE_BYTES + sw128_chunk_off(r, cc);
+        char* base = img + (size_t)kb * TE_STAGE_BYTES + sw128_chunk_off(r, cc);
         *reinterpret_cast<uint4*>(base) = hi;
         *reinterpret_cast<uint4*>(base + TE_TILE_BYTES) = lo;
     }
@@ -248,10 +238,9 @@ tc_estep_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int 
     } else if (warp == 8) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
+            const uint32_t idesc = make_idesc_f16(128, 128);
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-            const bool tri = (RP >= 64) && (__ldg(maxbits + 1) == 0u);
             const int S = (D + 15) >> 4;                                  // 16-wide K steps that hold data
-            constexpr int CPC = 128 / RP;                                  // components per 128-row chunk
             uint32_t stage = 0, phase = 0, gc = 0, it = 0;
             for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
                 mbar_wait(&bars->a_full, it & 1);
@@ -260,9 +249,7 @@ tc_estep_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int 
                     const uint32_t buf = gc & 1;
                     mbar_wait(&bars->tmem_empty[buf], ((gc >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    bool first = true;
-                    for (int kbi = 0; kbi < KB; ++kbi) {
-                        const int kb = KB - 1 - kbi;                               // last K block first
+                    for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&bars->full[stage], phase);
                         tc_fence_after();
                         const uint64_t bh = make_desc_sw128(b0 + stage * TE_STAGE_BYTES);
@@ -272,32 +259,14 @@ tc_estep_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int 
                             const uint64_t ah = make_desc_sw128(a0 + ((tt * 2 + 0) * KB + kb) * TE_TILE_BYTES);
                             const uint64_t al = make_desc_sw128(a0 + ((tt * 2 + 1) * KB + kb) * TE_TILE_BYTES);
                             const uint32_t d = tmem_base + buf * 256 + tt * 128;
-                            bool f = first;
 #pragma unroll
-                            for (int kk = 3; kk >= 0; --kk) {           // 16-element K steps inside the 64-wide block: +32 B
-                                const int s = kb * 4 + kk;
-                                if (s >= S) continue;
-                                if (!tri) {
-                                    const uint32_t idesc = make_idesc_f16(128, 128);
-                                    umma_f16(d, al + 2 * kk, bh + 2 * kk, idesc, f ? 0u : 1u);
-                                    umma_f16(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
-                                    umma_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
-                                } else {
-                                    // rows below 16 (s + 1) of every component are zero in this K step
-                                    const int n = f ? RP : min(RP, 16 * (s + 1));
-                                    const uint32_t idesc = make_idesc_f16(128, n);
-#pragma unroll
-                                    for (int cc = 0; cc < CPC; ++cc) {
-                                        const uint64_t ro = (uint64_t)((cc * RP * 128) >> 4);     // component's rows in the B tile
-                                        umma_f16(d + cc * RP, al + 2 * kk, bh + ro + 2 * kk, idesc, f ? 0u : 1u);
-                                        umma_f16(d + cc * RP, ah + 2 * kk, bl + ro + 2 * kk, idesc, 1);
-                                        umma_f16(d + cc * RP, ah + 2 * kk, bh + ro + 2 * kk, idesc, 1);
-                                    }
-                                }
-                                f = false;
+                            for (int kk = 0; kk < 4; ++kk) {           // 16-element K steps inside the 64-wide block: +32 B
+                                if (kb * 4 + kk >= S) continue;
+                                umma_f16(d, al + 2 * kk, bh + 2 * kk, idesc, (kb | kk) != 0);
+                                umma_f16(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
+                                umma_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
                             }
                         }
-                        if (kb * 4 < S) first = false;
                         umma_commit(&bars->empty[stage]);                // stage free once these MMAs have read it
                         if (++stage == TE_STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -308,23 +277,13 @@ tc_estep_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int 
     } else {
         // ================= B producer (one thread, TMA engine bulk copies) =================
         if (lane == 0) {
-            // triangular operands with one component per chunk: rows 64..127 of the first K block are zero and never read
-            const bool half0 = (RP == 128) && (KB == 2) && (__ldg(maxbits + 1) == 0u);
             uint32_t stage = 0, phase = 0;
             for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 const unsigned char* src = reinterpret_cast<const unsigned char*>(Bimg);
                 for (int s = 0; s < n_chunks * KB; ++s) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
-                    unsigned char* dst = sB + (size_t)stage * TE_STAGE_BYTES;
-                    const unsigned char* sp = src + (size_t)s * TE_STAGE_BYTES;
-                    if (half0 && (s % KB) == KB - 1) {                   // stage of K block 0 (stored last)
-                        mbar_arrive_expect_tx(&bars->full[stage], TE_TILE_BYTES);
-                        bulk_g2s(dst, sp, TE_TILE_BYTES / 2, &bars->full[stage]);
-                        bulk_g2s(dst + TE_TILE_BYTES, sp + TE_TILE_BYTES, TE_TILE_BYTES / 2, &bars->full[stage]);
-                    } else {
-                        mbar_arrive_expect_tx(&bars->full[stage], TE_STAGE_BYTES);
-                        bulk_g2s(dst, sp, TE_STAGE_BYTES, &bars->full[stage]);
-                    }
+                    mbar_arrive_expect_tx(&bars->full[stage], TE_STAGE_BYTES);
+                    bulk_g2s(sB + (size_t)stage * TE_STAGE_BYTES, src + (size_t)s * TE_STAGE_BYTES, TE_STAGE_BYTES, &bars->full[stage]);
                     if (++stage == TE_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -384,7 +343,7 @@ const unsigned int* tc_maxbits(void* ws) { return (const unsigned int*)align1k(w
 int tc_prepare_operands(const float* W, int K, int Rp, int Dpp, int D, void* ws, cudaStream_t st) {
     TcOperandLayout L = tc_layout(K, Rp, D);
     char* base = align1k(ws);
-    tc_prep_operands_kernel<<<L.n_chunks, 256, 0, st>>>(W, K, Rp, Dpp, D, L.KB, (unsigned int*)(base + L.off_maxbits),
+    tc_prep_operands_kernel<<<L.n_chunks, 256, 0, st>>>(W, K, Rp, Dpp, D, L.KB, (const unsigned int*)(base + L.off_maxbits),
                                                         (__half*)(base + L.off_img), (float*)(base + L.off_rowoff),
                                                         (float*)(base + L.off_invS2));
     MIMO_LAUNCH_CHECK();

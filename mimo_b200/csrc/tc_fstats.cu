@@ -18,14 +18,17 @@
 // 8256 + 128 + 1 features of [z ; 1] (rows 63 and 127 stand alone, row 65 is z_t * 1, and the
 // spare slot of row 64 holds 1 * 1).
 //
-// Work unit = (128-component block, 4 folded rows = 512 TMEM columns, slab of points), handed
-// out by an atomic counter, slab-major so that concurrent CTAs stream the same points through L2.
-// Per 64-point block: 256 producer threads write the A operand (R in the 3xFP16 split,
-// tc_common.cuh) and, per 2 folded rows, one B stage of 256 x 64 products in the same split;
-// one thread issues 4 x 3 tcgen05.mma (M=128, N=256, K=16) per stage.  Accumulators are FP32 in
-// TMEM; every `flush` blocks they are drained with tcgen05.ld and added in FP64 (red.global) to
-// the partial buffer [component block][slot][component lane], which tc_fstats_end folds into
-// the packed (K, F) statistics once per sweep.
+// Work unit = (128-component block, 4 folded rows = 512 TMEM columns[, slab of points]) on a static
+// lock-step schedule.  Two small pre-passes write the operands in their shared-memory image
+// (K-major, 128-byte swizzle, 3xFP16 split of tc_common.cuh): the responsibilities
+// [component block][64-point block][hi|lo][128][64] and the transposed data
+// [64-point block][hi|lo][128 columns][64], so the main kernel receives both with one bulk copy
+// (TMA engine) per block.  Per 64-point block: 512 producer threads form, per folded row, one B
+// stage of 128 slots x 64 points of products directly in split FP16 (Dekker product on the FP16
+// FMA pipe); one thread issues 4 x 3 tcgen05.mma (M=128, N=128, K=16) per stage.  Accumulators
+// are FP32 in TMEM; every `flush` blocks they are drained with tcgen05.ld and added in FP64
+// (red.global) to the partial buffer [component block][slot][component lane], which
+// tc_fstats_end folds into the packed (K, F) statistics once per sweep.
 #include <algorithm>
 #include "tc_common.cuh"
 #include "internal.h"
@@ -34,25 +37,26 @@ namespace mimo {
 
 using namespace tc;
 
-constexpr int TF_THREADS = 384;                  // 2 producer / drain warpgroups + 1 warpgroup holding the MMA warp
+constexpr int TF_PRODUCERS = 512;                // 16 producer / drain warps (4 warpgroups)
+constexpr int TF_THREADS = 640;                  // + 1 warpgroup: MMA warp, bulk-copy warp, 2 idle warps
 constexpr int TF_KB = 64;                        // points per block (one 128-byte operand row)
 constexpr int TF_DC = 128;                       // columns of the folded triangle
 constexpr int TF_H = TF_DC / 2;
 constexpr int TF_ROWS = TF_H + 2;                // folded rows
 constexpr int TF_FBROWS = 4;                     // folded rows per unit (4 x 128 = 512 TMEM columns)
-constexpr uint32_t TF_ATILE = 16384;             // [128 components][64 points] FP16
-constexpr uint32_t TF_BTILE = 32768;             // [256 slots][64 points] FP16
-constexpr uint32_t TF_BSTAGE = 2 * TF_BTILE;     // hi | lo
-constexpr uint32_t TF_ZTILE = 16384;             // [128 columns][64 points] FP16, 16-byte chunks XOR-swizzled by row
+constexpr int TF_BSTAGES = 3;
+constexpr uint32_t TF_TILE = 16384;              // [128 rows][64 points] FP16
+constexpr uint32_t TF_PAIR = 2 * TF_TILE;        // hi | lo
 constexpr float TF_ONE = 128.f;                  // the constant 1 of zt in scaled units
 constexpr float TF_RSCALE = 8192.f;              // responsibilities in [0, 1] -> [0, 2^13]
 
-constexpr uint32_t TF_OFF_A = 2 * TF_BSTAGE;
-constexpr uint32_t TF_OFF_ZS = TF_OFF_A + 4 * TF_ATILE;
-constexpr uint32_t TF_OFF_BARS = TF_OFF_ZS + 2 * TF_ZTILE;
+constexpr uint32_t TF_OFF_A = TF_BSTAGES * TF_PAIR;
+constexpr uint32_t TF_OFF_ZS = TF_OFF_A + 2 * TF_PAIR;
+constexpr uint32_t TF_OFF_BARS = TF_OFF_ZS + 2 * TF_PAIR;
 
 struct TfBars {
-    uint64_t a_full[2], a_empty[2], b_full[2], b_empty[2];
+    uint64_t zs_full[2], zs_empty[2], a_full[2], a_empty[2];
+    uint64_t b_full[TF_BSTAGES], b_empty[TF_BSTAGES];
     uint64_t acc_ready, acc_drained;
     uint32_t tmem_base;
 };
@@ -79,9 +83,6 @@ __device__ __forceinline__ void red_add_f64(double* p, double v) {
 // scale of the data inside this kernel: max |z| * sz in [64, 128)
 __host__ __device__ __forceinline__ float tf_scale(float maxabs) { return pow2_scale_for(maxabs) * (1.f / 128.f); }
 
-// byte offset of the 16-byte chunk `c` (8 points) of column `row` in the swizzled point block
-__device__ __forceinline__ uint32_t tf_z_off(int row, int c) { return (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4); }
-
 // 8 products a*b of split FP16 operands -> split FP16 result (Dekker product on the FP16 FMA pipe):
 //   p = fl(ah*bh);  lo = fl(fl((ah*bh - p) + ah*bl) + al*bh)      (ah*bh - p is exact)
 __device__ __forceinline__ void tf_prod8(const uint4& ah, const uint4& al, const uint4& bh, const uint4& bl, uint4& hi, uint4& lo) {
@@ -102,217 +103,217 @@ __device__ __forceinline__ void tf_prod8(const uint4& ah, const uint4& al, const
     }
 }
 
+// ---- operand images ---------------------------------------------------------------------------
+// data: one CTA per 64-point block; thread = (column t, 32-point half).  zimg block = [hi|lo][128 columns][64 points].
+__global__ void __launch_bounds__(256)
+tc_fstats_zimg_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
+                      const unsigned int* __restrict__ maxbits, unsigned char* __restrict__ zimg) {
+    const float sz = tf_scale(__uint_as_float(__ldg(maxbits)));
+    const int t = threadIdx.x & 127, ph = threadIdx.x >> 7;
+    const int64_t nb = (int64_t)blockIdx.x * TF_KB + ph * 32;
+    float zn[32];
+    if (t < D && nb + 32 <= N) {
+        const float* src = Z + nb * ldz + t;
+#pragma unroll
+        for (int p = 0; p < 32; ++p) zn[p] = __ldg(src + (int64_t)p * ldz);
+    } else {
+#pragma unroll
+        for (int p = 0; p < 32; ++p) zn[p] = (nb + p < N && t < D) ? __ldg(Z + (nb + p) * ldz + t) : 0.f;
+    }
+    unsigned char* blk = zimg + (size_t)blockIdx.x * TF_PAIR;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = zn[8 * q + e] * sz;
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t o = sw128_chunk_off(t, ph * 4 + q);
+        *reinterpret_cast<uint4*>(blk + o) = hi;
+        *reinterpret_cast<uint4*>(blk + TF_TILE + o) = lo;
+    }
+}
+
+// responsibilities: one CTA per (64-point block, component block); thread = (component row, 32-point half).
+// rimg block (cb, kblock) = [hi|lo][128 components][64 points] at ((cb * nkb_cap + kblock) * TF_PAIR).
+__global__ void __launch_bounds__(256)
+tc_fstats_rimg_kernel(const float* __restrict__ R, int64_t N, int64_t ldr, int K, int rvec4, int64_t nkb_cap,
+                      unsigned char* __restrict__ rimg) {
+    const int ca = threadIdx.x >> 1, hh = threadIdx.x & 1;
+    const int cb = blockIdx.y;
+    const int64_t nb = (int64_t)blockIdx.x * TF_KB + hh * 32;
+    const bool kok = cb * 128 + ca < K;
+    const float* src = R + (int64_t)(cb * 128 + ca) * ldr + nb;
+    float rn[32];
+    if (rvec4 && kok && nb + 32 <= N) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+            rn[4 * q] = v.x; rn[4 * q + 1] = v.y; rn[4 * q + 2] = v.z; rn[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 32; ++p) rn[p] = (kok && nb + p < N) ? __ldg(src + p) : 0.f;
+    }
+    unsigned char* blk = rimg + ((size_t)cb * nkb_cap + blockIdx.x) * TF_PAIR;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = rn[8 * q + e] * TF_RSCALE;
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t o = sw128_chunk_off(ca, hh * 4 + q);
+        *reinterpret_cast<uint4*>(blk + o) = hi;
+        *reinterpret_cast<uint4*>(blk + TF_TILE + o) = lo;
+    }
+}
+
+// ---- main kernel ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TF_THREADS, 1)
-tc_fstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
-                 const float* __restrict__ R, int64_t ldr, int K, int rvec4,
-                 const unsigned int* __restrict__ maxbits,
-                 double* __restrict__ partial,
-                 int cbs, int fbs, int slabs, int64_t slab_points, int flush_kb) {
+tc_fstats_kernel(const unsigned char* __restrict__ zimg, const unsigned char* __restrict__ rimg, int64_t nkb_cap,
+                 int64_t N, double* __restrict__ partial, unsigned int* __restrict__ pace,
+                 int cbs, int fbs, int slabs, int64_t slab_points, int flush_kb, int pace_epochs) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
     unsigned char* sA = smem + TF_OFF_A;
-    unsigned char* sZh = smem + TF_OFF_ZS;
-    unsigned char* sZl = sZh + TF_ZTILE;
+    unsigned char* sZ = smem + TF_OFF_ZS;
     TfBars* bars = reinterpret_cast<TfBars*>(smem + TF_OFF_BARS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&bars->a_full[b], 256); mbar_init(&bars->a_empty[b], 1);
-            mbar_init(&bars->b_full[b], 256); mbar_init(&bars->b_empty[b], 1);
+            mbar_init(&bars->zs_full[b], 1); mbar_init(&bars->zs_empty[b], TF_PRODUCERS);
+            mbar_init(&bars->a_full[b], 1);  mbar_init(&bars->a_empty[b], 1);
         }
+        for (int b = 0; b < TF_BSTAGES; ++b) { mbar_init(&bars->b_full[b], TF_PRODUCERS); mbar_init(&bars->b_empty[b], 1); }
         mbar_init(&bars->acc_ready, 1);
-        mbar_init(&bars->acc_drained, 256);
+        mbar_init(&bars->acc_drained, TF_PRODUCERS);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(&bars->tmem_base, 512);
+    if (warp == 16) tmem_alloc(&bars->tmem_base, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     const int n_units = cbs * fbs * slabs;
 
-    // pipeline counters (identical sequences in the producer and MMA roles)
-    uint32_t ac = 0, bc = 0, dc = 0;
-
     // Static schedule: unit u = (slab, feature block, component block) -> CTA u % gridDim.  Every CTA of a slab
-    // streams the same points at the same pace, so the point block and the responsibility rows shared by
-    // the units of a component block are read from HBM once and served from L2 afterwards.
-    // The two roles run their own copy of the unit loop so that each gets its own register budget.
-    if (warp < 8) {
-        // ================= producers / drain: 232 registers (four split 32-point columns live in registers) =================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-        const float sz = tf_scale(__uint_as_float(__ldg(maxbits)));
-        const int t = tid & 127, ph = tid >> 7;          // own column, 32-point half of the block
-        const int ca = tid >> 1, hh = tid & 1;           // A operand: component row, 32-point half
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const int slab = u / (cbs * fbs);
-            const int rem = u - slab * (cbs * fbs);
-            const int fb = rem / cbs, cb = rem - fb * cbs;
-            const int k0 = cb * 128;
-            const int row0 = fb * TF_FBROWS;
-            const int nst = (min(TF_FBROWS, TF_ROWS - row0) + 1) / 2;        // B stages (2 folded rows each) per block
-            const int64_t p0 = (int64_t)slab * slab_points;
-            const int64_t p1 = min(N, p0 + slab_points);
-            const int nkb = (p1 > p0) ? (int)((p1 - p0 + TF_KB - 1) / TF_KB) : 0;
-            if (nkb == 0) continue;
+    // streams the same points at the same pace, so the images shared by the units of a slab are read from
+    // HBM once and served from L2 afterwards.  All roles walk the same unit / block / row sequence.
+#define TF_UNIT_DECODE                                                                   \
+        const int slab = u / (cbs * fbs);                                                \
+        const int rem = u - slab * (cbs * fbs);                                          \
+        const int fb = rem / cbs, cb = rem - fb * cbs;                                   \
+        const int row0 = fb * TF_FBROWS;                                                 \
+        const int nrows = min(TF_FBROWS, TF_ROWS - row0);                                \
+        const int64_t p0 = (int64_t)slab * slab_points;                                  \
+        const int64_t p1 = min(N, p0 + slab_points);                                     \
+        const int nkb = (p1 > p0) ? (int)((p1 - p0 + TF_KB - 1) / TF_KB) : 0;           \
+        const int64_t kblock0 = p0 / TF_KB;                                              \
+        (void)cb; (void)kblock0; (void)row0;
 
-            uint4 zh[4], zl[4], mh[4], ml[4];            // own column t and mirror column 127 - t: 32 points, hi / lo halves
-            float zn[32], rn[32];                        // next block, in flight
-            auto load_z = [&](int kb) {
-                const int64_t nb = p0 + (int64_t)kb * TF_KB + ph * 32;
-                if (t < D && nb + 32 <= p1) {
-                    const float* src = Z + nb * ldz + t;
+    if (warp < 16) {
+        // ================= producers / drain =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const int t = tid & 127, pq = tid >> 7;          // own column, 16-point quarter of the block
+        uint32_t zc = 0, bc = 0, dc = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            TF_UNIT_DECODE
+            for (int kb = 0; kb < nkb; ++kb, ++zc) {
+                // ---- own column t and mirror column 127 - t of the point block (split FP16, 16 points) ----
+                const uint32_t zb = zc & 1;
+                const unsigned char* zh_s = sZ + zb * TF_PAIR;
+                const unsigned char* zl_s = zh_s + TF_TILE;
+                mbar_wait(&bars->zs_full[zb], (zc >> 1) & 1);
+                uint4 zh[2], zl[2], mh[2], ml[2];
 #pragma unroll
-                    for (int p = 0; p < 32; ++p) zn[p] = __ldg(src + (int64_t)p * ldz);
-                } else {
-#pragma unroll
-                    for (int p = 0; p < 32; ++p) zn[p] = (nb + p < p1 && t < D) ? __ldg(Z + (nb + p) * ldz + t) : 0.f;
+                for (int q = 0; q < 2; ++q) {
+                    const uint32_t o = sw128_chunk_off(t, pq * 2 + q), om = sw128_chunk_off(TF_DC - 1 - t, pq * 2 + q);
+                    zh[q] = *reinterpret_cast<const uint4*>(zh_s + o);
+                    zl[q] = *reinterpret_cast<const uint4*>(zl_s + o);
+                    mh[q] = *reinterpret_cast<const uint4*>(zh_s + om);
+                    ml[q] = *reinterpret_cast<const uint4*>(zl_s + om);
                 }
-            };
-            auto load_r = [&](int kb) {
-                const int64_t nb = p0 + (int64_t)kb * TF_KB + hh * 32;
-                const bool kok = k0 + ca < K;
-                const float* src = R + (int64_t)(k0 + ca) * ldr + nb;
-                if (rvec4 && kok && nb + 32 <= p1) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
-                        rn[4 * q] = v.x; rn[4 * q + 1] = v.y; rn[4 * q + 2] = v.z; rn[4 * q + 3] = v.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int p = 0; p < 32; ++p) rn[p] = (kok && nb + p < p1) ? __ldg(src + p) : 0.f;
-                }
-            };
-            load_z(0);
-            load_r(0);
-            for (int kb = 0; kb < nkb; ++kb) {
-                // ---- the point block: own column -> split FP16 in registers + shared copy; mirror column back ----
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float x[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] = zn[8 * q + e] * sz;
-                    split8(x, zh[q], zl[q]);
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");          // broadcast reads of the previous block are done
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t o = tf_z_off(t, ph * 4 + q);
-                    *reinterpret_cast<uint4*>(sZh + o) = zh[q];
-                    *reinterpret_cast<uint4*>(sZl + o) = zl[q];
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t o = tf_z_off(TF_DC - 1 - t, ph * 4 + q);
-                    mh[q] = *reinterpret_cast<const uint4*>(sZh + o);
-                    ml[q] = *reinterpret_cast<const uint4*>(sZl + o);
-                }
-                // ---- A operand: responsibilities of 128 components x 64 points, 3xFP16 split ----
-                {
-                    const uint32_t buf = ac & 1;
-                    mbar_wait(&bars->a_empty[buf], ((ac >> 1) & 1) ^ 1);
-                    unsigned char* ah = sA + (size_t)buf * 2 * TF_ATILE;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float x[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) x[e] = rn[8 * q + e] * TF_RSCALE;
-                        uint4 hi, lo;
-                        split8(x, hi, lo);
-                        const uint32_t o = sw128_chunk_off(ca, hh * 4 + q);
-                        *reinterpret_cast<uint4*>(ah + o) = hi;
-                        *reinterpret_cast<uint4*>(ah + TF_ATILE + o) = lo;
-                    }
-                    fence_proxy_async();
-                    mbar_arrive(&bars->a_full[buf]);
-                    ++ac;
-                }
-                if (kb + 1 < nkb) { load_z(kb + 1); load_r(kb + 1); }   // in flight while this block's products are generated
-                // ---- B stages: 2 folded rows = 256 slots x 64 points of products ----
-                for (int s = 0; s < nst; ++s, ++bc) {
-                    const uint32_t bst = bc & 1;
-                    mbar_wait(&bars->b_empty[bst], ((bc >> 1) & 1) ^ 1);
-                    unsigned char* stage = sB + (size_t)bst * TF_BSTAGE;
+                // ---- B stages: one folded row = 128 slots x 64 points of products ----
 #pragma unroll 1
-                    for (int rr = 0; rr < 2; ++rr) {
-                        const int r = row0 + 2 * s + rr;
-                        const int rowN = rr * 128 + t;
-                        unsigned char* dst = stage + (uint32_t)rowN * 128u;
-                        const int sw = rowN & 7;
-                        // products of the broadcast column `irow` with the thread's own / mirror column
-                        auto emit = [&](const uint4 (&oh)[4], const uint4 (&ol)[4], int irow) {
-                            uint4 ah[4], al[4];
+                for (int rr = 0; rr < nrows; ++rr, ++bc) {
+                    const uint32_t bst = bc % TF_BSTAGES;
+                    mbar_wait(&bars->b_empty[bst], ((bc / TF_BSTAGES) & 1) ^ 1);
+                    const int r = row0 + rr;
+                    unsigned char* dst = sB + (size_t)bst * TF_PAIR + (uint32_t)t * 128u;
+                    const int sw = t & 7;
+                    // products of the broadcast column `irow` with the thread's own / mirror column
+                    auto emit = [&](const uint4 (&oh)[2], const uint4 (&ol)[2], int irow) {
+                        uint4 ah[2], al[2];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint32_t o = tf_z_off(irow, ph * 4 + q);
-                                ah[q] = *reinterpret_cast<const uint4*>(sZh + o);
-                                al[q] = *reinterpret_cast<const uint4*>(sZl + o);
+                        for (int q = 0; q < 2; ++q) {
+                            const uint32_t o = sw128_chunk_off(irow, pq * 2 + q);
+                            ah[q] = *reinterpret_cast<const uint4*>(zh_s + o);
+                            al[q] = *reinterpret_cast<const uint4*>(zl_s + o);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            uint4 hi, lo;
+                            tf_prod8(ah[q], al[q], oh[q], ol[q], hi, lo);
+                            const uint32_t o = (uint32_t)(((pq * 2 + q) ^ sw) << 4);
+                            *reinterpret_cast<uint4*>(dst + o) = hi;
+                            *reinterpret_cast<uint4*>(dst + TF_TILE + o) = lo;
+                        }
+                    };
+                    if (r < TF_H) {
+                        int irow;
+                        bool mirror = false;
+                        if (r < TF_H - 1) {
+                            const int ih = TF_H + r;
+                            if (t <= ih) irow = ih; else { irow = TF_DC - 2 - ih; mirror = true; }
+                        } else irow = TF_DC - 1;
+                        if (mirror) emit(mh, ml, irow); else emit(zh, zl, irow);
+                    } else if (r == TF_H && t < TF_H) {
+                        emit(zh, zl, TF_H - 1);
+                    } else {
+                        // constant row (1 * z_t, exact power-of-two scaling), the 1 * 1 slot, or an unused slot
+                        const __half2 one2 = __float2half2_rn(TF_ONE);
+                        const __half2 cc2 = __float2half2_rn((r == TF_H && t == TF_H) ? TF_ONE * TF_ONE : 0.f);
+                        const bool crow = r > TF_H;
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            uint4 hi, lo;
+                            __half2* h = reinterpret_cast<__half2*>(&hi);
+                            __half2* l = reinterpret_cast<__half2*>(&lo);
+                            const __half2* oh = reinterpret_cast<const __half2*>(&zh[q]);
+                            const __half2* ol = reinterpret_cast<const __half2*>(&zl[q]);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                h[e] = crow ? __hmul2(oh[e], one2) : cc2;
+                                l[e] = crow ? __hmul2(ol[e], one2) : __float2half2_rn(0.f);
                             }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 hi, lo;
-                                tf_prod8(ah[q], al[q], oh[q], ol[q], hi, lo);
-                                const uint32_t o = (uint32_t)(((ph * 4 + q) ^ sw) << 4);
-                                *reinterpret_cast<uint4*>(dst + o) = hi;
-                                *reinterpret_cast<uint4*>(dst + TF_BTILE + o) = lo;
-                            }
-                        };
-                        if (r < TF_H) {
-                            int irow;
-                            bool mirror = false;
-                            if (r < TF_H - 1) {
-                                const int ih = TF_H + r;
-                                if (t <= ih) irow = ih; else { irow = TF_DC - 2 - ih; mirror = true; }
-                            } else irow = TF_DC - 1;
-                            if (mirror) emit(mh, ml, irow); else emit(zh, zl, irow);
-                        } else if (r == TF_H && t < TF_H) {
-                            emit(zh, zl, TF_H - 1);
-                        } else {
-                            // constant row (1 * z_t, exact power-of-two scaling), the 1 * 1 slot, or an unused slot
-                            const __half2 one2 = __float2half2_rn(TF_ONE);
-                            const __half2 cc2 = __float2half2_rn((r == TF_H && t == TF_H) ? TF_ONE * TF_ONE : 0.f);
-                            const bool crow = r > TF_H;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 hi, lo;
-                                __half2* h = reinterpret_cast<__half2*>(&hi);
-                                __half2* l = reinterpret_cast<__half2*>(&lo);
-                                const __half2* oh = reinterpret_cast<const __half2*>(&zh[q]);
-                                const __half2* ol = reinterpret_cast<const __half2*>(&zl[q]);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    h[e] = crow ? __hmul2(oh[e], one2) : cc2;
-                                    l[e] = crow ? __hmul2(ol[e], one2) : __float2half2_rn(0.f);
-                                }
-                                const uint32_t o = (uint32_t)(((ph * 4 + q) ^ sw) << 4);
-                                *reinterpret_cast<uint4*>(dst + o) = hi;
-                                *reinterpret_cast<uint4*>(dst + TF_BTILE + o) = lo;
-                            }
+                            const uint32_t o = (uint32_t)(((pq * 2 + q) ^ sw) << 4);
+                            *reinterpret_cast<uint4*>(dst + o) = hi;
+                            *reinterpret_cast<uint4*>(dst + TF_TILE + o) = lo;
                         }
                     }
                     fence_proxy_async();
                     mbar_arrive(&bars->b_full[bst]);
                 }
+                mbar_arrive(&bars->zs_empty[zb]);                        // done reading this point block
                 // ---- drain the FP32 accumulators into the FP64 partials ----
                 if ((kb + 1) % flush_kb == 0 || kb + 1 == nkb) {
                     mbar_wait(&bars->acc_ready, dc & 1);
                     tc_fence_after();
-                    const int qd = warp & 3, half = warp >> 2;
-                    const int ncol = nst * 128;                          // columns per warp half
-                    double* pk = partial + ((size_t)cb * TF_ROWS * TF_DC + (size_t)row0 * TF_DC + (size_t)half * ncol) * 128
-                               + qd * 32 + lane;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + half * ncol;
+                    const int qd = warp & 3, cg = warp >> 2;             // TMEM lane quarter, 128-column group (= folded row)
+                    if (cg < nrows) {
+                        double* pk = partial + ((size_t)cb * TF_ROWS * TF_DC + (size_t)(row0 + cg) * TF_DC) * 128 + qd * 32 + lane;
+                        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + cg * 128;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < ncol; c0 += 32) {
-                        float v[32];
-                        tmem_ld32(taddr + c0, v);
-                        tmem_ld_wait();
+                        for (int c0 = 0; c0 < 128; c0 += 32) {
+                            float v[32];
+                            tmem_ld32(taddr + c0, v);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (v[j] != 0.f) red_add_f64(pk + (size_t)(c0 + j) * 128, (double)v[j]);
+                            for (int j = 0; j < 32; ++j)
+                                if (v[j] != 0.f) red_add_f64(pk + (size_t)(c0 + j) * 128, (double)v[j]);
+                        }
                     }
                     tc_fence_before();
                     mbar_arrive(&bars->acc_drained);
@@ -321,34 +322,28 @@ tc_fstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
             }
         }
     } else {
-        // ================= MMA warpgroup: one issuing thread, three idle warps =================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp == 8 && lane == 0) {
-            const uint32_t idesc = make_idesc_f16(128, 256);
+        if (warp == 16 && lane == 0) {
+            // ================= MMA issuer (one thread) =================
+            const uint32_t idesc = make_idesc_f16(128, 128);
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            uint32_t ac = 0, bc = 0, dc = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const int slab = u / (cbs * fbs);
-                const int rem = u - slab * (cbs * fbs);
-                const int fb = rem / cbs;
-                const int row0 = fb * TF_FBROWS;
-                const int nst = (min(TF_FBROWS, TF_ROWS - row0) + 1) / 2;
-                const int64_t p0 = (int64_t)slab * slab_points;
-                const int64_t p1 = min(N, p0 + slab_points);
-                const int nkb = (p1 > p0) ? (int)((p1 - p0 + TF_KB - 1) / TF_KB) : 0;
+                TF_UNIT_DECODE
                 bool fresh = true;
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = 0; kb < nkb; ++kb, ++ac) {
                     const uint32_t abuf = ac & 1;
                     mbar_wait(&bars->a_full[abuf], (ac >> 1) & 1);
                     tc_fence_after();
-                    const uint64_t ah = make_desc_sw128(a0 + abuf * 2 * TF_ATILE);
-                    const uint64_t al = make_desc_sw128(a0 + abuf * 2 * TF_ATILE + TF_ATILE);
-                    for (int s = 0; s < nst; ++s, ++bc) {
-                        const uint32_t bst = bc & 1;
-                        mbar_wait(&bars->b_full[bst], (bc >> 1) & 1);
+                    const uint64_t ah = make_desc_sw128(a0 + abuf * TF_PAIR);
+                    const uint64_t al = make_desc_sw128(a0 + abuf * TF_PAIR + TF_TILE);
+                    for (int rr = 0; rr < nrows; ++rr, ++bc) {
+                        const uint32_t bst = bc % TF_BSTAGES;
+                        mbar_wait(&bars->b_full[bst], (bc / TF_BSTAGES) & 1);
                         tc_fence_after();
-                        const uint64_t bh = make_desc_sw128(b0 + bst * TF_BSTAGE);
-                        const uint64_t bl = make_desc_sw128(b0 + bst * TF_BSTAGE + TF_BTILE);
-                        const uint32_t d = tmem_base + s * 256;
+                        const uint64_t bh = make_desc_sw128(b0 + bst * TF_PAIR);
+                        const uint64_t bl = make_desc_sw128(b0 + bst * TF_PAIR + TF_TILE);
+                        const uint32_t d = tmem_base + rr * 128;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
                             umma_f16(d, al + 2 * kk, bh + 2 * kk, idesc, (fresh && kk == 0) ? 0u : 1u);
@@ -358,7 +353,6 @@ tc_fstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
                         umma_commit(&bars->b_empty[bst]);
                     }
                     umma_commit(&bars->a_empty[abuf]);
-                    ++ac;
                     fresh = false;
                     if ((kb + 1) % flush_kb == 0 || kb + 1 == nkb) {
                         umma_commit(&bars->acc_ready);
@@ -369,11 +363,38 @@ tc_fstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
                     }
                 }
             }
+        } else if (warp == 17 && lane == 0) {
+            // ================= operand loader (one thread, TMA engine bulk copies) =================
+            // Pacing: the bulk copies are asynchronous, so nothing couples the speed of a CTA to its L2 hit rate
+            // and CTAs would drift apart until every image tile is fetched from HBM once per CTA.  Every
+            // `flush_kb` blocks (an epoch) the loader announces itself on a global counter and does not start
+            // epoch e before all gridDim CTAs (all co-resident: one per SM) have started epoch e - 1.
+            uint32_t zc = 0, epoch = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                TF_UNIT_DECODE
+                for (int kb = 0; kb < nkb; ++kb, ++zc) {
+                    if (zc % (uint32_t)flush_kb == 0) {
+                        const unsigned int target = epoch * gridDim.x;
+                        while (*reinterpret_cast<volatile unsigned int*>(pace) < target) __nanosleep(100);
+                        atomicAdd(pace, 1u);
+                        ++epoch;
+                    }
+                    const uint32_t b = zc & 1, par = ((zc >> 1) & 1) ^ 1;
+                    mbar_wait(&bars->zs_empty[b], par);
+                    mbar_arrive_expect_tx(&bars->zs_full[b], TF_PAIR);
+                    bulk_g2s(sZ + b * TF_PAIR, zimg + (size_t)(kblock0 + kb) * TF_PAIR, TF_PAIR, &bars->zs_full[b]);
+                    mbar_wait(&bars->a_empty[b], par);
+                    mbar_arrive_expect_tx(&bars->a_full[b], TF_PAIR);
+                    bulk_g2s(sA + b * TF_PAIR, rimg + ((size_t)cb * nkb_cap + kblock0 + kb) * TF_PAIR, TF_PAIR, &bars->a_full[b]);
+                }
+            }
+            if ((int)epoch < pace_epochs) atomicAdd(pace, (unsigned int)pace_epochs - epoch);   // credit the epochs this CTA never starts
         }
     }
+#undef TF_UNIT_DECODE
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 512);
+    if (warp == 16) tmem_dealloc(tmem_base, 512);
 }
 
 // stat[k][tri(i, j)] += scale(i, j) * partial[k / 128][slot][k % 128]
@@ -397,46 +418,76 @@ __global__ void tc_fstats_reduce_kernel(const double* __restrict__ partial, int 
 // ---- host side -------------------------------------------------------------------------------
 
 static char* align1k(void* p) { return (char*)(((uintptr_t)p + 1023) / 1024 * 1024); }
+static size_t up1k(size_t x) { return (x + 1023) / 1024 * 1024; }
 
 bool tc_fstats_supported(int dtype, int D, int F) {
     return dtype == MIMO_F32 && D > TF_H && D <= TF_DC && F == (D + 1) * (D + 2) / 2;
 }
 
-static size_t tf_partial_bytes(int K) { return (size_t)((K + 127) / 128) * TF_ROWS * TF_DC * 128 * sizeof(double); }
+struct TfLayout { int cbs; int64_t nkb_cap; size_t off_partial, off_zimg, off_rimg, bytes; };
+static TfLayout tf_layout(int64_t chunk_points, int K) {
+    TfLayout L;
+    L.cbs = (K + 127) / 128;
+    L.nkb_cap = std::max<int64_t>(1, (chunk_points + TF_KB - 1) / TF_KB);
+    size_t o = 1024;
+    L.off_partial = o; o += up1k((size_t)L.cbs * TF_ROWS * TF_DC * 128 * sizeof(double));
+    L.off_zimg = o;    o += (size_t)L.nkb_cap * TF_PAIR;
+    L.off_rimg = o;    o += (size_t)L.cbs * L.nkb_cap * TF_PAIR;
+    L.bytes = o;
+    return L;
+}
 
-// [reserved (1 KB) | partial]
-size_t tc_fstats_workspace(int K) { return 2048 + tf_partial_bytes(K); }
+// [reserved (1 KB) | FP64 partials | data image of one chunk | responsibility image of one chunk]
+size_t tc_fstats_workspace(int64_t chunk_points, int K) { return 1024 + tf_layout(chunk_points, K).bytes; }
 
-int tc_fstats_begin(int K, void* ws, cudaStream_t st) {
-    MIMO_CUDA(cudaMemsetAsync(align1k(ws), 0, 1024 + tf_partial_bytes(K), st));
+int tc_fstats_begin(int64_t chunk_points, int K, void* ws, cudaStream_t st) {
+    TfLayout L = tf_layout(chunk_points, K);
+    MIMO_CUDA(cudaMemsetAsync(align1k(ws) + L.off_partial, 0, L.off_zimg - L.off_partial, st));
     return MIMO_OK;
 }
 
 static int g_flush_tiles_f = 16;
 void tc_fstats_set_flush_tiles(int t) { g_flush_tiles_f = t < 1 ? 1 : t; }
 
-// one chunk of points: accumulates into the partial buffer
+// one chunk of N <= plan_points points: operand images, then the GEMM; accumulates into the partial buffer
 int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, int K,
-                    const unsigned int* maxbits, void* ws, cudaStream_t st) {
+                    const unsigned int* maxbits, int64_t plan_points, void* ws, cudaStream_t st) {
     if (N == 0) return MIMO_OK;
-    double* partial = (double*)(align1k(ws) + 1024);
-    const int cbs = (K + 127) / 128, fbs = (TF_ROWS + TF_FBROWS - 1) / TF_FBROWS;
-    // point slabs only when one (component block, feature block) grid does not fill the SMs
-    int slabs = std::max(1, sm_count() / (cbs * fbs));
+    TfLayout L = tf_layout(plan_points, K);
+    char* base = align1k(ws);
+    double* partial = (double*)(base + L.off_partial);
+    unsigned char* zimg = (unsigned char*)(base + L.off_zimg);
+    unsigned char* rimg = (unsigned char*)(base + L.off_rimg);
     const int64_t blocks = (N + TF_KB - 1) / TF_KB;
+    MIMO_CHECK_ARG(blocks <= L.nkb_cap, "chunk larger than planned");
+    const int rvec4 = (ldr % 4 == 0) && (((uintptr_t)R & 15) == 0);
+    tc_fstats_zimg_kernel<<<(unsigned)blocks, 256, 0, st>>>(Z, N, D, ldz, maxbits, zimg);
+    MIMO_LAUNCH_CHECK();
+    tc_fstats_rimg_kernel<<<dim3((unsigned)blocks, (unsigned)L.cbs), 256, 0, st>>>(R, N, ldr, K, rvec4, L.nkb_cap, rimg);
+    MIMO_LAUNCH_CHECK();
+    const int fbs = (TF_ROWS + TF_FBROWS - 1) / TF_FBROWS;
+    // point slabs only when one (component block, feature block) grid does not fill the SMs
+    int slabs = std::max(1, sm_count() / (L.cbs * fbs));
     slabs = (int)std::min<int64_t>(slabs, std::max<int64_t>(1, blocks / 8));
     const int64_t slab_points = (blocks + slabs - 1) / slabs * TF_KB;
     MIMO_CUDA(cudaFuncSetAttribute(tc_fstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM));
-    const int grid = std::min(cbs * fbs * slabs, sm_count());
-    const int rvec4 = (ldr % 4 == 0) && (((uintptr_t)R & 15) == 0);
-    tc_fstats_kernel<<<grid, TF_THREADS, TF_SMEM, st>>>(Z, N, D, ldz, R, ldr, K, rvec4, maxbits, partial,
-                                                        cbs, fbs, slabs, slab_points, 2 * g_flush_tiles_f);
+    const int n_units = L.cbs * fbs * slabs;
+    const int grid = std::min(n_units, sm_count());
+    const int flush_kb = 2 * g_flush_tiles_f;
+    // upper bound of the pacing epochs of one CTA: its units hold at most slab_points / 64 blocks each
+    const int64_t units_per_cta = (n_units + grid - 1) / grid;
+    const int pace_epochs = (int)((units_per_cta * (slab_points / TF_KB) + flush_kb - 1) / flush_kb) + 1;
+    unsigned int* pace = (unsigned int*)base;
+    MIMO_CUDA(cudaMemsetAsync(pace, 0, 4, st));
+    tc_fstats_kernel<<<grid, TF_THREADS, TF_SMEM, st>>>(zimg, rimg, L.nkb_cap, N, partial, pace, L.cbs, fbs, slabs, slab_points,
+                                                        flush_kb, pace_epochs);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
 
-int tc_fstats_end(int K, int D, int F, const unsigned int* maxbits, double* stat, void* ws, cudaStream_t st) {
-    tc_fstats_reduce_kernel<<<K, 256, 0, st>>>((const double*)(align1k(ws) + 1024), K, D, F, maxbits, stat);
+int tc_fstats_end(int64_t plan_points, int K, int D, int F, const unsigned int* maxbits, double* stat, void* ws, cudaStream_t st) {
+    TfLayout L = tf_layout(plan_points, K);
+    tc_fstats_reduce_kernel<<<K, 256, 0, st>>>((const double*)(align1k(ws) + L.off_partial), K, D, F, maxbits, stat);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
