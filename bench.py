@@ -370,7 +370,7 @@ def main():
     if comm is not None:
         comm.allreduce(s.stat)
     del true_labels
-    phase = np.zeros(4)
+    phase = np.zeros(5)
     vlbs = []
 
     def step(timed):
@@ -394,7 +394,7 @@ def main():
             ops, outs = s.update_from_stats(MEANFIELD); torch.cuda.synchronize(); t.append(time.perf_counter())
             s.sweep(ops, hard=False); torch.cuda.synchronize(); t.append(time.perf_counter())
             s.lower_bound(outs); t.append(time.perf_counter())
-            ph = np.zeros(4)
+            ph = np.zeros(5)
             s.sweep(ops, hard=False, phase_ms=ph); torch.cuda.synchronize(); t.append(time.perf_counter())
             sys.stderr.write('DEBUG update %.2f ms | sweep %.2f ms | vlb %.2f ms | timed sweep %.2f ms phases %s\n'
                              % tuple([1e3 * (t[i + 1] - t[i]) for i in range(4)] + [ph.tolist()]))
@@ -424,8 +424,7 @@ def main():
     work = algorithmic_work(w)
     value = w['N'] * K / (ms * 1e-3)
     # roofline of the dominant kernel, from the per-phase CUDA-event times of the timed steps
-    # launches: 3 per chunk (mean-field) or 2 per chunk + 4 for the one counting-sort statistics pass (Gibbs)
-    chunks = max(1.0, (phase[3] - 4.0 * args.steps) / 2.0 if hard else phase[3] / 3.0)
+    chunks = max(1.0, phase[4])          # point chunks over the timed steps = launches of each per-chunk kernel
     phase_ms = phase[:3] / args.steps
     dom = int(np.argmax(phase_ms))
     pairs_local = n_local * K

@@ -14,7 +14,7 @@ static size_t a256(size_t x) { return (x + 255) / 256 * 256; }
 
 static int g_tc_mode = 1;
 int tc_mode() { return g_tc_mode; }
-int tc_set_mode(int mode) { int old = g_tc_mode; g_tc_mode = mode ? 1 : 0; return old; }
+int tc_set_mode(int mode) { int old = g_tc_mode; g_tc_mode = (mode < 0 || mode > 2) ? 1 : mode; return old; }
 
 // the tensor-core path takes FP32 quad-family sweeps whose contraction is wide enough to pay for
 // the 64-wide K blocks of the operand layout
@@ -151,7 +151,10 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
                 cudaEventElapsedTime(&ms, ev[i + ph], ev[i + ph + 1]);
                 phase_ms[ph] += ms;
             }
-            phase_ms[3] += (hard || !stat) ? 2.0 : 3.0;     // kernel launches of this chunk
+            // kernel launches of this chunk: E-step (+ offsets blocks for the CTA-pair kernel), softmax,
+            // statistics (feature form: data image + responsibility image + GEMM)
+            phase_ms[3] += 2.0 + ((use_tc && tc_mode() == 1) ? 1.0 : 0.0)
+                         + ((hard || !stat) ? 0.0 : (tc_fstats ? 3.0 : 1.0));
         }
         if (h0) {
             float ms = 0.f;
@@ -160,6 +163,8 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             phase_ms[3] += 4.0;
             cudaEventDestroy(h0); cudaEventDestroy(h1);
         }
+        if (use_tc) phase_ms[3] += 2.0 + (tc_stats ? 1.0 : 0.0);      // data scale, operand image, statistics fold
+        phase_ms[4] += (double)((N + C - 1) / C);                      // point chunks
         for (auto e : ev) cudaEventDestroy(e);
     }
     return MIMO_OK;

@@ -303,17 +303,19 @@ bool tc_estep_supported(int dtype, int D, int Rp) {
 }
 
 struct TcOperandLayout {
-    int KB, n_chunks;
-    size_t off_maxbits, off_invS2, off_rowoff, off_img, bytes;
+    int KB, n_chunks;                  // n_chunks: 128-row chunks, rounded up to an even count (CTA-pair kernel), zero padded
+    size_t off_maxbits, off_invS2, off_rowoff, off_offs2, off_img, bytes;
 };
 static TcOperandLayout tc_layout(int K, int Rp, int D) {
     TcOperandLayout L;
     L.KB = D <= 64 ? 1 : 2;
     L.n_chunks = (int)(((int64_t)K * Rp + 127) / 128);
+    L.n_chunks = (L.n_chunks + 1) / 2 * 2;
     size_t o = 0;
     L.off_maxbits = o; o += 256;
     L.off_invS2 = o;   o += a256((size_t)K * 4);
     L.off_rowoff = o;  o += a256((size_t)L.n_chunks * 128 * 4);
+    L.off_offs2 = o;   o += a256(tc2_offsets_bytes(K, Rp));
     o = (o + 1023) / 1024 * 1024;
     L.off_img = o;     o += (size_t)L.n_chunks * L.KB * TE_STAGE_BYTES;
     L.bytes = o;
@@ -372,6 +374,14 @@ int tc_estep(const float* Z, int64_t N, int D, int64_t ldz, const float* cst, in
     if (N == 0) return MIMO_OK;
     TcOperandLayout L = tc_layout(K, Rp, D);
     char* base = align1k(ws);
+    if (tc_mode() == 1) {
+        // CTA-pair kernel (cta_group::2): needs the per-chunk offsets block, built from the current cst
+        int rc = tc2_prepare_offsets((const float*)(base + L.off_rowoff), (const float*)(base + L.off_invS2), cst, K, Rp,
+                                     (float*)(base + L.off_offs2), st);
+        if (rc) return rc;
+        return tc_estep2(Z, N, D, ldz, K, Rp, L.KB, (const void*)(base + L.off_img), (const float*)(base + L.off_offs2),
+                         (const unsigned int*)(base + L.off_maxbits), out, ldo, st);
+    }
 #define TE_CASE(kb, rp) if (L.KB == kb && Rp == rp) return launch_estep<kb, rp>(Z, N, D, ldz, L, base, cst, K, out, ldo, st);
     TE_CASE(1, 8) TE_CASE(1, 16) TE_CASE(1, 32) TE_CASE(1, 64) TE_CASE(1, 128)
     TE_CASE(2, 8) TE_CASE(2, 16) TE_CASE(2, 32) TE_CASE(2, 64) TE_CASE(2, 128)

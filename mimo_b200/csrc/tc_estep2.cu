@@ -1,0 +1,386 @@
+// Tensor-core E-step on CTA PAIRS (tcgen05 cta_group::2), sm_100a.
+//
+//   a[k][n] = cst[k] - 0.5 * || W_k [z_n ; 1] ||^2        (include/mimo_b200.h, "packed operand form")
+//
+// Same math, operand image and 3xFP16 split as tc_estep.cu (reference call sites
+// distributions/gaussian.py:510-523, lingauss.py:330-347, bayesian.py:287-301, 933-947); what
+// changes is the shape of one MMA.  With both operands in shared memory a 128 x 128 x 16 MMA
+// needs 128 B/clk of shared-memory reads -- the whole bandwidth of an SM -- and tc_estep.cu
+// stalls at ~75 % of the tensor pipe.  Here two CTAs of a cluster (one TPC) issue ONE
+// 256 x 256 x 16 MMA: each CTA supplies its own 128 points (A) and its own 128 operand rows
+// (half of B), so per SM the reads drop to 64 B/clk, every B stage is copied from L2 by one of
+// the two CTAs only, and the issuing thread has half as many instructions per flop.
+//
+// Per cluster pass = 2 x 128 points.  Per CTA: 8 converter / epilogue warps (thread = point,
+// TMEM lane; warps 0-3 own accumulator columns 0..127 = the even 128-row chunk, warps 4-7
+// columns 128..255 = the odd one), warp 8 = MMA issuer (leader CTA) or relay (peer CTA), warp 9
+// = bulk-copy producer of this CTA's half of B and of the per-chunk offsets.  The leader's
+// issuer must see BOTH CTAs' "A written", "B landed" and "accumulator drained" events: the peer's
+// relay thread waits on its local mbarriers and forwards each event with one remote
+// mbarrier.arrive; completions travel the other way with tcgen05.commit ... multicast.
+#include <algorithm>
+#include "tc_common.cuh"
+#include "internal.h"
+
+namespace mimo {
+
+using namespace tc;
+
+constexpr int T2_THREADS = 320;
+constexpr int T2_STAGES = 4;                 // B ring: one stage = this CTA's 128 rows x 64 K, hi + lo = 32 KB
+constexpr uint32_t T2_TILE = 16384;          // 128 rows x 64 FP16
+constexpr uint32_t T2_STAGE = 2 * T2_TILE;
+constexpr int T2_OFFBLK = 320;               // floats per 256-row chunk: 256 row offsets | 32 cst | 32 1/scale^2
+constexpr uint32_t T2_OFFBYTES = T2_OFFBLK * 4;
+
+struct T2Bars {
+    uint64_t full[T2_STAGES], empty[T2_STAGES], peer_full[T2_STAGES];
+    uint64_t tmem_full[2], tmem_empty[2], peer_tmem_empty[2];
+    uint64_t a_full, peer_a_full;
+    uint64_t off_full[2], off_empty[2];
+    uint32_t tmem_base;
+};
+
+// ---- cluster / cta_group::2 primitives ----------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > WATCHDOG_CYCLES) asm volatile("trap;");
+    }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {    // whole warp, both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {       // whole warp, both CTAs
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem, both CTAs] (+)= A * B^T over the CTA pair: M = 256 (128 rows of A per CTA), N columns (N/2 rows of B per CTA)
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+
+// offsets block of every 256-row chunk: [256 row offsets | cst of its components | 1/scale^2 of its components]
+__global__ void tc2_offsets_kernel(const float* __restrict__ rowoff, const float* __restrict__ invS2, const float* __restrict__ cst,
+                                   int K, int Rp, int n_chunks, float* __restrict__ offs2) {
+    const int c2 = blockIdx.x, t = threadIdx.x;                 // 320 threads
+    float v = 0.f;
+    if (t < 256) {
+        const int chunk = 2 * c2 + (t >> 7);
+        v = chunk < n_chunks ? rowoff[(size_t)chunk * 128 + (t & 127)] : 0.f;
+    } else {
+        const int j = (t - 256) & 31;
+        const int k = c2 * (256 / Rp) + j;
+        if (j < 256 / Rp && k < K) v = (t < 288) ? cst[k] : invS2[k];
+    }
+    offs2[(size_t)c2 * T2_OFFBLK + t] = v;
+}
+
+// 32 accumulator columns -> partial squared norms (4 independent chains), component boundaries every RP columns
+template <int RP>
+__device__ __forceinline__ void t2_consume(const float (&v)[32], const float* __restrict__ off_s, int col0, float (&q)[4],
+                                           const float* __restrict__ scal_s, int jbase, int kbase, int K, bool pvalid,
+                                           float* __restrict__ outp, int64_t ldo) {
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 o = *reinterpret_cast<const float4*>(off_s + col0 + j4 * 4);       // broadcast read
+        const float oo[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int col = col0 + j4 * 4 + e;
+            const float t = v[j4 * 4 + e] + oo[e];
+            q[e] = fmaf(t, t, q[e]);
+            if ((col + 1) % RP == 0) {
+                const int j = jbase + col / RP;                    // component inside the 256-row chunk
+                const int k = kbase + j;
+                const float qq = (q[0] + q[1]) + (q[2] + q[3]);
+                if (pvalid && k < K) outp[(int64_t)k * ldo] = scal_s[j] - 0.5f * scal_s[32 + j] * qq;
+                q[0] = q[1] = q[2] = q[3] = 0.f;
+            }
+        }
+    }
+}
+
+template <int KB, int RP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int vec4,
+                 const __half* __restrict__ Bimg, const float* __restrict__ offs2,
+                 const unsigned int* __restrict__ maxbits,
+                 int K, int n_chunks2, float* __restrict__ out, int64_t ldo) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // A: [hi|lo][kb KB] tiles of 16 KB;  B: [stage][hi|lo] tiles of 16 KB;  offsets ring: 2 x T2_OFFBYTES
+    unsigned char* sA = smem_raw;
+    unsigned char* sB = sA + (size_t)2 * KB * T2_TILE;
+    float* sOff = reinterpret_cast<float*>(sB + (size_t)T2_STAGES * T2_STAGE);
+    T2Bars* bars = reinterpret_cast<T2Bars*>(reinterpret_cast<unsigned char*>(sOff) + 2 * T2_OFFBYTES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int64_t n_passes = (N + 255) / 256;
+    const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); mbar_init(&bars->peer_full[s], 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 256); mbar_init(&bars->peer_tmem_empty[b], 1);
+            mbar_init(&bars->off_full[b], 1); mbar_init(&bars->off_empty[b], 256);
+        }
+        mbar_init(&bars->a_full, 256);
+        mbar_init(&bars->peer_a_full, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (warp == 8) tmem_alloc2(&bars->tmem_base, 512);
+    tc_fence_before();
+    cluster_sync_all();                                   // barriers of both CTAs initialised, TMEM allocated
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp < 8) {
+        // ================= converter + epilogue warps =================
+        const float sz = pow2_scale_for(__uint_as_float(__ldg(maxbits)));
+        const int half = warp >> 2, qd = warp & 3;
+        const int prow = qd * 32 + lane;                             // point row inside the tile = TMEM lane
+        uint32_t gc = 0;
+        for (int64_t pass = cluster_id; pass < n_passes; pass += n_clusters) {
+            const int64_t n0 = pass * 256 + rank * 128;
+            // ---- A operand: 128 rows of Z -> 3xFP16 split, K-major swizzled.  Every MMA of the previous pass
+            //      has completed (all threads waited on its last tmem_full), so A may be overwritten. ----
+            const int f = lane * 4;                                  // this lane's 4 features
+            for (int r0 = warp; r0 < 128; r0 += 32) {                // 4 rows in flight per warp
+                float x[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + 8 * u;
+                    const int64_t n = n0 + r;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) x[u][e] = 0.f;
+                    if (n < N && f < D) {
+                        const float* src = Z + n * ldz + f;
+                        if (vec4 && f + 3 < D) {
+                            float4 v = __ldg(reinterpret_cast<const float4*>(src));
+                            x[u][0] = v.x; x[u][1] = v.y; x[u][2] = v.z; x[u][3] = v.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) if (f + e < D) x[u][e] = __ldg(src + e);
+                        }
+                    }
+                }
+                if (f < KB * 64) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int rr = r0 + 8 * u;
+                        float xs[4] = {x[u][0] * sz, x[u][1] * sz, x[u][2] * sz, x[u][3] * sz};
+                        uint2 hi, lo;
+                        split4(xs, hi, lo);
+                        const int kb = f >> 6, ch = (f & 63) >> 3;
+                        unsigned char* base = sA + (size_t)kb * T2_TILE + sw128_chunk_off(rr, ch) + (f & 7) * 2;
+                        *reinterpret_cast<uint2*>(base) = hi;
+                        *reinterpret_cast<uint2*>(base + (size_t)KB * T2_TILE) = lo;
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&bars->a_full);
+
+            // ---- epilogue over the 256-row chunks: this warp group owns columns [128 half, +128) ----
+            const int64_t n = n0 + prow;
+            const bool pvalid = n < N;
+            float* outp = out + n;
+            for (int c = 0; c < n_chunks2; ++c, ++gc) {
+                const uint32_t buf = gc & 1, par = (gc >> 1) & 1;
+                mbar_wait(&bars->off_full[buf], par);
+                mbar_wait(&bars->tmem_full[buf], par);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * 256 + half * 128;
+                const float* blk = sOff + buf * T2_OFFBLK;
+                const float* off_s = blk + half * 128;
+                const float* scal_s = blk + 256;
+                const int kbase = c * (256 / RP), jbase = half * (128 / RP);
+                float va[32], vb[32];
+                float q[4] = {0.f, 0.f, 0.f, 0.f};
+                tmem_ld32(taddr, va);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 32, vb);
+                t2_consume<RP>(va, off_s, 0, q, scal_s, jbase, kbase, K, pvalid, outp, ldo);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 64, va);
+                t2_consume<RP>(vb, off_s, 32, q, scal_s, jbase, kbase, K, pvalid, outp, ldo);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 96, vb);
+                t2_consume<RP>(va, off_s, 64, q, scal_s, jbase, kbase, K, pvalid, outp, ldo);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&bars->tmem_empty[buf]);             // accumulator drained: the pair's MMA may reuse it
+                t2_consume<RP>(vb, off_s, 96, q, scal_s, jbase, kbase, K, pvalid, outp, ldo);
+                mbar_arrive(&bars->off_empty[buf]);
+            }
+        }
+    } else if (warp == 8) {
+        if (lane == 0 && rank == 0) {
+            // ================= MMA issuer (leader CTA, one thread) =================
+            const uint32_t idesc = make_idesc_f16(256, 256);
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            const int S = (D + 15) >> 4;                                  // 16-wide K steps that hold data
+            uint32_t stage = 0, phase = 0, gc = 0, it = 0;
+            for (int64_t pass = cluster_id; pass < n_passes; pass += n_clusters, ++it) {
+                mbar_wait(&bars->a_full, it & 1);
+                mbar_wait_cluster(&bars->peer_a_full, it & 1);
+                tc_fence_after();
+                for (int c = 0; c < n_chunks2; ++c, ++gc) {
+                    const uint32_t buf = gc & 1, par = ((gc >> 1) & 1) ^ 1;
+                    mbar_wait(&bars->tmem_empty[buf], par);
+                    // the peer's drain events are forwarded from the buffer's second use on (the first use is free)
+                    if (gc >= 2) mbar_wait_cluster(&bars->peer_tmem_empty[buf], ((gc >> 1) - 1) & 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + buf * 256;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        mbar_wait(&bars->full[stage], phase);
+                        mbar_wait_cluster(&bars->peer_full[stage], phase);
+                        tc_fence_after();
+                        const uint64_t bh = make_desc_sw128(b0 + stage * T2_STAGE);
+                        const uint64_t bl = make_desc_sw128(b0 + stage * T2_STAGE + T2_TILE);
+                        const uint64_t ah = make_desc_sw128(a0 + kb * T2_TILE);
+                        const uint64_t al = make_desc_sw128(a0 + (KB + kb) * T2_TILE);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {               // 16-element K steps inside the 64-wide block: +32 B
+                            if (kb * 4 + kk >= S) continue;
+                            umma2_f16(d, al + 2 * kk, bh + 2 * kk, idesc, (kb | kk) != 0);
+                            umma2_f16(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
+                            umma2_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
+                        }
+                        umma2_commit(&bars->empty[stage]);               // both CTAs' stage free once these MMAs have read it
+                        if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma2_commit(&bars->tmem_full[buf]);
+                }
+            }
+        } else if (lane == 0) {
+            // ================= relay (peer CTA): forward local events to the leader's issuer =================
+            const uint32_t r_a = map_to_rank(smem_u32(&bars->peer_a_full), 0);
+            uint32_t stage = 0, phase = 0, gc = 0, it = 0;
+            for (int64_t pass = cluster_id; pass < n_passes; pass += n_clusters, ++it) {
+                mbar_wait(&bars->a_full, it & 1);
+                mbar_arrive_remote(r_a);
+                for (int c = 0; c < n_chunks2; ++c, ++gc) {
+                    const uint32_t buf = gc & 1, par = ((gc >> 1) & 1) ^ 1;
+                    if (gc >= 2) {
+                        mbar_wait(&bars->tmem_empty[buf], par);
+                        mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_tmem_empty[buf]), 0));
+                    }
+                    for (int kb = 0; kb < KB; ++kb) {
+                        mbar_wait(&bars->full[stage], phase);
+                        mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_full[stage]), 0));
+                        if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= producer (one thread per CTA): this CTA's half of B + the chunk offsets =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, gc = 0;
+            for (int64_t pass = cluster_id; pass < n_passes; pass += n_clusters) {
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(Bimg);
+                for (int c = 0; c < n_chunks2; ++c, ++gc) {
+                    const uint32_t ob = gc & 1;
+                    mbar_wait(&bars->off_empty[ob], ((gc >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bars->off_full[ob], T2_OFFBYTES);
+                    bulk_g2s(sOff + ob * T2_OFFBLK, offs2 + (size_t)c * T2_OFFBLK, T2_OFFBYTES, &bars->off_full[ob]);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        mbar_wait(&bars->empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&bars->full[stage], T2_STAGE);
+                        bulk_g2s(sB + (size_t)stage * T2_STAGE, src + ((size_t)(2 * c + rank) * KB + kb) * T2_STAGE, T2_STAGE, &bars->full[stage]);
+                        if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                   // no CTA leaves (or frees TMEM) while its partner may still signal it
+    if (warp == 8) tmem_dealloc2(tmem_base, 512);
+}
+
+// ---- host side -------------------------------------------------------------------------------
+
+size_t tc2_offsets_bytes(int K, int Rp) {
+    const int64_t n_chunks = ((int64_t)K * Rp + 127) / 128;
+    return (size_t)((n_chunks + 1) / 2) * T2_OFFBYTES;
+}
+
+int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cst, int K, int Rp, float* offs2, cudaStream_t st) {
+    const int n_chunks = (int)(((int64_t)K * Rp + 127) / 128);
+    tc2_offsets_kernel<<<(n_chunks + 1) / 2, T2_OFFBLK, 0, st>>>(rowoff, invS2, cst, K, Rp, n_chunks, offs2);
+    MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
+}
+
+template <int KB, int RP>
+static int launch_estep2(const float* Z, int64_t N, int D, int64_t ldz, const __half* Bimg, const float* offs2,
+                         const unsigned int* maxbits, int K, int n_chunks2, float* out, int64_t ldo, cudaStream_t st) {
+    const size_t smem = (size_t)2 * KB * T2_TILE + (size_t)T2_STAGES * T2_STAGE + 2 * T2_OFFBYTES + sizeof(T2Bars);
+    auto kern = tc_estep2_kernel<KB, RP>;
+    MIMO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t passes = (N + 255) / 256;
+    const int clusters = (int)std::min<int64_t>(passes, sm_count() / 2);
+    const int vec4 = (ldz % 4 == 0) && (((uintptr_t)Z & 15) == 0);
+    kern<<<2 * clusters, T2_THREADS, smem, st>>>(Z, N, D, ldz, vec4, Bimg, offs2, maxbits, K, n_chunks2, out, ldo);
+    MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
+}
+
+// E-step over N points with a prepared operand image (even number of 128-row chunks, zero padded) and offsets blocks
+int tc_estep2(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, int KB, const void* Bimg_, const float* offs2,
+              const unsigned int* maxbits, float* out, int64_t ldo, cudaStream_t st) {
+    const __half* Bimg = (const __half*)Bimg_;
+    if (N == 0) return MIMO_OK;
+    const int n_chunks = (int)(((int64_t)K * Rp + 127) / 128);
+    const int n_chunks2 = (n_chunks + 1) / 2;
+#define T2_CASE(kb, rp) if (KB == kb && Rp == rp) return launch_estep2<kb, rp>(Z, N, D, ldz, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, st);
+    T2_CASE(1, 8) T2_CASE(1, 16) T2_CASE(1, 32) T2_CASE(1, 64) T2_CASE(1, 128)
+    T2_CASE(2, 8) T2_CASE(2, 16) T2_CASE(2, 32) T2_CASE(2, 64) T2_CASE(2, 128)
+#undef T2_CASE
+    set_error("tensor-core E-step (CTA pairs): unsupported shape D=%d Rp=%d", D, Rp);
+    return MIMO_EUNSUPPORTED;
+}
+
+}  // namespace mimo

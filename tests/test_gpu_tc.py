@@ -31,11 +31,18 @@ def test_loglik_tc(K, d, N, shift):
     E.set_log_weights(ops, logw)
     E.operands_gauss(ops, E.to_dev(mus), E.to_dev(lmbdas)).check()
     Z = E.to_dev(x, torch.float32)
-    ll_tc = E.loglik_tc(Z, ops)
+    ll_tc = E.loglik_tc(Z, ops)                      # default: CTA-pair kernel (cta_group::2)
+    old = E.set_tensor_cores(2)                      # single-CTA kernel
+    try:
+        ll_tc1 = E.loglik_tc(Z, ops)
+    finally:
+        E.set_tensor_cores(old)
     ll_cc = E.loglik(Z, ops)
     xr = Z.double().cpu().numpy()
     ref = orc.gauss_full_loglik(xr, mus, lmbdas) + logw[:, None]
-    close(ll_tc, ref, 1e-4, 'tensor-core log-lik')
+    close(ll_tc, ref, 1e-4, 'tensor-core log-lik (CTA pairs)')
+    close(ll_tc1, ref, 1e-4, 'tensor-core log-lik (single CTA)')
+    close(ll_tc, ll_tc1.cpu().numpy(), 1e-6, 'CTA-pair vs single-CTA kernel')
     e_tc, e_cc = scaled_err(ll_tc, ref), scaled_err(ll_cc, ref)
     print('loglik K=%d d=%d N=%d: scaled err tensor-core %.2e, CUDA-core fp32 %.2e' % (K, d, N, e_tc, e_cc))
     assert e_tc <= max(4 * e_cc, 2e-6)
