@@ -18,14 +18,18 @@
 // 8256 + 128 + 1 features of [z ; 1] (rows 63 and 127 stand alone, row 65 is z_t * 1, and the
 // spare slot of row 64 holds 1 * 1).
 //
-// Work unit = (128-component block, 4 folded rows = 512 TMEM columns[, slab of points]) on a static
+// The GEMM runs on CTA PAIRS (tcgen05 cta_group::2: one 256 x 256 x 16 MMA per pair; see tc_estep2.cu for
+// the pair protocol): a single-CTA 128 x 128 x 16 version was bound by the issue rate of its one MMA thread
+// and by the products its 512 producer threads could form.  In a pair each CTA owns 128 components (its half
+// of M) and forms every second folded row (its half of N), so per MMA flop the producers do half the work.
+// Work unit = (pair of 128-component blocks, 4 folded rows = 512 TMEM columns[, slab of points]) on a static
 // lock-step schedule.  Two small pre-passes write the operands in their shared-memory image
 // (K-major, 128-byte swizzle, 3xFP16 split of tc_common.cuh): the responsibilities
 // [component block][64-point block][hi|lo][128][64] and the transposed data
 // [64-point block][hi|lo][128 columns][64], so the main kernel receives both with one bulk copy
 // (TMA engine) per block.  Per 64-point block: 512 producer threads form, per folded row, one B
 // stage of 128 slots x 64 points of products directly in split FP16 (Dekker product on the FP16
-// FMA pipe); one thread issues 4 x 3 tcgen05.mma (M=128, N=128, K=16) per stage.  Accumulators
+// FMA pipe); the leader's issuing thread runs 4 x 3 tcgen05.mma (M=256, N=256, K=16) per pair of rows.  Accumulators
 // are FP32 in TMEM; every `flush` blocks they are drained with tcgen05.ld and added in FP64
 // (red.global) to the partial buffer [component block][slot][component lane], which
 // tc_fstats_end folds into the packed (K, F) statistics once per sweep.
@@ -58,6 +62,7 @@ struct TfBars {
     uint64_t zs_full[2], zs_empty[2], a_full[2], a_empty[2];
     uint64_t b_full[TF_BSTAGES], b_empty[TF_BSTAGES];
     uint64_t acc_ready, acc_drained;
+    uint64_t peer_a_full[2], peer_b_full[TF_BSTAGES], peer_acc_drained;   // leader CTA only: events forwarded by the peer's relay
     uint32_t tmem_base;
 };
 constexpr uint32_t TF_SMEM = TF_OFF_BARS + sizeof(TfBars);
@@ -170,10 +175,10 @@ tc_fstats_rimg_kernel(const float* __restrict__ R, int64_t N, int64_t ldr, int K
 }
 
 // ---- main kernel ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TF_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1)
 tc_fstats_kernel(const unsigned char* __restrict__ zimg, const unsigned char* __restrict__ rimg, int64_t nkb_cap,
                  int64_t N, double* __restrict__ partial, unsigned int* __restrict__ pace,
-                 int cbs, int fbs, int slabs, int64_t slab_points, int flush_kb, int pace_epochs) {
+                 int cbps, int fbs, int slabs, int64_t slab_points, int flush_kb, int pace_epochs) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
     unsigned char* sA = smem + TF_OFF_A;
@@ -181,32 +186,41 @@ tc_fstats_kernel(const unsigned char* __restrict__ zimg, const unsigned char* __
     TfBars* bars = reinterpret_cast<TfBars*>(smem + TF_OFF_BARS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = (int)cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     if (tid == 0) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->zs_full[b], 1); mbar_init(&bars->zs_empty[b], TF_PRODUCERS);
             mbar_init(&bars->a_full[b], 1);  mbar_init(&bars->a_empty[b], 1);
+            mbar_init(&bars->peer_a_full[b], 1);
         }
-        for (int b = 0; b < TF_BSTAGES; ++b) { mbar_init(&bars->b_full[b], TF_PRODUCERS); mbar_init(&bars->b_empty[b], 1); }
+        for (int b = 0; b < TF_BSTAGES; ++b) {
+            mbar_init(&bars->b_full[b], TF_PRODUCERS); mbar_init(&bars->b_empty[b], 1); mbar_init(&bars->peer_b_full[b], 1);
+        }
         mbar_init(&bars->acc_ready, 1);
         mbar_init(&bars->acc_drained, TF_PRODUCERS);
+        mbar_init(&bars->peer_acc_drained, 1);
         fence_barrier_init();
     }
-    if (warp == 16) tmem_alloc(&bars->tmem_base, 512);
-    tc_fence_before();
     __syncthreads();
+    if (warp == 16) tmem_alloc2(&bars->tmem_base, 512);
+    tc_fence_before();
+    cluster_sync_all();                                   // barriers of both CTAs initialised, TMEM allocated
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    const int n_units = cbs * fbs * slabs;
+    const int n_units = cbps * fbs * slabs;
 
-    // Static schedule: unit u = (slab, feature block, component block) -> CTA u % gridDim.  Every CTA of a slab
-    // streams the same points at the same pace, so the images shared by the units of a slab are read from
-    // HBM once and served from L2 afterwards.  All roles walk the same unit / block / row sequence.
+    // Static schedule: unit u = (slab, feature block, pair of component blocks) -> cluster u % n_clusters.  Every
+    // cluster of a slab streams the same points at the same pace, so the images shared by the units of a slab
+    // are read from HBM once and served from L2 afterwards.  All roles walk the same unit / block / row sequence.
+    // Inside a unit CTA `rank` owns component block 2 cbp + rank (its 128 TMEM lanes) and forms the folded rows
+    // row0 + 2 s + rank (its 128 of the 256 B rows of stage s).
 #define TF_UNIT_DECODE                                                                   \
-        const int slab = u / (cbs * fbs);                                                \
-        const int rem = u - slab * (cbs * fbs);                                          \
-        const int fb = rem / cbs, cb = rem - fb * cbs;                                   \
+        const int slab = u / (cbps * fbs);                                               \
+        const int rem = u - slab * (cbps * fbs);                                         \
+        const int fb = rem / cbps, cb = 2 * (rem - fb * cbps) + rank;                    \
         const int row0 = fb * TF_FBROWS;                                                 \
-        const int nrows = min(TF_FBROWS, TF_ROWS - row0);                                \
+        const int nst = min(TF_FBROWS, TF_ROWS - row0) / 2;                              \
         const int64_t p0 = (int64_t)slab * slab_points;                                  \
         const int64_t p1 = min(N, p0 + slab_points);                                     \
         const int nkb = (p1 > p0) ? (int)((p1 - p0 + TF_KB - 1) / TF_KB) : 0;           \
@@ -218,7 +232,7 @@ tc_fstats_kernel(const unsigned char* __restrict__ zimg, const unsigned char* __
         asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         const int t = tid & 127, pq = tid >> 7;          // own column, 16-point quarter of the block
         uint32_t zc = 0, bc = 0, dc = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        for (int u = cluster_id; u < n_units; u += n_clusters) {
             TF_UNIT_DECODE
             for (int kb = 0; kb < nkb; ++kb, ++zc) {
                 // ---- own column t and mirror column 127 - t of the point block (split FP16, 16 points) ----
@@ -235,12 +249,12 @@ tc_fstats_kernel(const unsigned char* __restrict__ zimg, const unsigned char* __
                     mh[q] = *reinterpret_cast<const uint4*>(zh_s + om);
                     ml[q] = *reinterpret_cast<const uint4*>(zl_s + om);
                 }
-                // ---- B stages: one folded row = 128 slots x 64 points of products ----
+                // ---- B stages: this CTA's folded row of the stage = 128 slots x 64 points of products ----
 #pragma unroll 1
-                for (int rr = 0; rr < nrows; ++rr, ++bc) {
+                for (int st = 0; st < nst; ++st, ++bc) {
                     const uint32_t bst = bc % TF_BSTAGES;
                     mbar_wait(&bars->b_empty[bst], ((bc / TF_BSTAGES) & 1) ^ 1);
-                    const int r = row0 + rr;
+                    const int r = row0 + 2 * st + rank;
                     unsigned char* dst = sB + (size_t)bst * TF_PAIR + (uint32_t)t * 128u;
                     const int sw = t & 7;
                     // products of the broadcast column `irow` with the thread's own / mirror column
@@ -297,12 +311,12 @@ tc_fstats_kernel(const unsigned char* __restrict__ zimg, const unsigned char* __
                     mbar_arrive(&bars->b_full[bst]);
                 }
                 mbar_arrive(&bars->zs_empty[zb]);                        // done reading this point block
-                // ---- drain the FP32 accumulators into the FP64 partials ----
+                // ---- drain the FP32 accumulators (this CTA's 128 components x all columns) into the FP64 partials ----
                 if ((kb + 1) % flush_kb == 0 || kb + 1 == nkb) {
                     mbar_wait(&bars->acc_ready, dc & 1);
                     tc_fence_after();
                     const int qd = warp & 3, cg = warp >> 2;             // TMEM lane quarter, 128-column group (= folded row)
-                    if (cg < nrows) {
+                    if (cg < 2 * nst) {
                         double* pk = partial + ((size_t)cb * TF_ROWS * TF_DC + (size_t)(row0 + cg) * TF_DC) * 128 + qd * 32 + lane;
                         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + cg * 128;
 #pragma unroll 1
@@ -322,59 +336,85 @@ tc_fstats_kernel(const unsigned char* __restrict__ zimg, const unsigned char* __
             }
         }
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp == 16 && lane == 0) {
-            // ================= MMA issuer (one thread) =================
-            const uint32_t idesc = make_idesc_f16(128, 128);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 16 && lane == 0 && rank == 0) {
+            // ================= MMA issuer (leader CTA, one thread) =================
+            const uint32_t idesc = make_idesc_f16(256, 256);
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
             uint32_t ac = 0, bc = 0, dc = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            for (int u = cluster_id; u < n_units; u += n_clusters) {
                 TF_UNIT_DECODE
                 bool fresh = true;
                 for (int kb = 0; kb < nkb; ++kb, ++ac) {
-                    const uint32_t abuf = ac & 1;
-                    mbar_wait(&bars->a_full[abuf], (ac >> 1) & 1);
+                    const uint32_t abuf = ac & 1, apar = (ac >> 1) & 1;
+                    mbar_wait(&bars->a_full[abuf], apar);
+                    mbar_wait_cluster(&bars->peer_a_full[abuf], apar);
                     tc_fence_after();
                     const uint64_t ah = make_desc_sw128(a0 + abuf * TF_PAIR);
                     const uint64_t al = make_desc_sw128(a0 + abuf * TF_PAIR + TF_TILE);
-                    for (int rr = 0; rr < nrows; ++rr, ++bc) {
-                        const uint32_t bst = bc % TF_BSTAGES;
-                        mbar_wait(&bars->b_full[bst], (bc / TF_BSTAGES) & 1);
+                    for (int st = 0; st < nst; ++st, ++bc) {
+                        const uint32_t bst = bc % TF_BSTAGES, bpar = (bc / TF_BSTAGES) & 1;
+                        mbar_wait(&bars->b_full[bst], bpar);
+                        mbar_wait_cluster(&bars->peer_b_full[bst], bpar);
                         tc_fence_after();
                         const uint64_t bh = make_desc_sw128(b0 + bst * TF_PAIR);
                         const uint64_t bl = make_desc_sw128(b0 + bst * TF_PAIR + TF_TILE);
-                        const uint32_t d = tmem_base + rr * 128;
+                        const uint32_t d = tmem_base + st * 256;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            umma_f16(d, al + 2 * kk, bh + 2 * kk, idesc, (fresh && kk == 0) ? 0u : 1u);
-                            umma_f16(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
-                            umma_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
+                            umma2_f16(d, al + 2 * kk, bh + 2 * kk, idesc, (fresh && kk == 0) ? 0u : 1u);
+                            umma2_f16(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
+                            umma2_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
                         }
-                        umma_commit(&bars->b_empty[bst]);
+                        umma2_commit(&bars->b_empty[bst]);
                     }
-                    umma_commit(&bars->a_empty[abuf]);
+                    umma2_commit(&bars->a_empty[abuf]);
                     fresh = false;
                     if ((kb + 1) % flush_kb == 0 || kb + 1 == nkb) {
-                        umma_commit(&bars->acc_ready);
-                        mbar_wait(&bars->acc_drained, dc & 1);     // accumulators read out: may be overwritten
+                        umma2_commit(&bars->acc_ready);
+                        mbar_wait(&bars->acc_drained, dc & 1);     // both CTAs' accumulators read out: may be overwritten
+                        mbar_wait_cluster(&bars->peer_acc_drained, dc & 1);
                         tc_fence_after();
                         ++dc;
                         fresh = true;
                     }
                 }
             }
+        } else if (warp == 16 && lane == 0) {
+            // ================= relay (peer CTA): forward local events to the leader's issuer =================
+            uint32_t ac = 0, bc = 0, dc = 0;
+            const uint32_t r_drained = map_to_rank(smem_u32(&bars->peer_acc_drained), 0);
+            for (int u = cluster_id; u < n_units; u += n_clusters) {
+                TF_UNIT_DECODE
+                for (int kb = 0; kb < nkb; ++kb, ++ac) {
+                    const uint32_t abuf = ac & 1;
+                    mbar_wait(&bars->a_full[abuf], (ac >> 1) & 1);
+                    mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_a_full[abuf]), 0));
+                    for (int st = 0; st < nst; ++st, ++bc) {
+                        const uint32_t bst = bc % TF_BSTAGES;
+                        mbar_wait(&bars->b_full[bst], (bc / TF_BSTAGES) & 1);
+                        mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_b_full[bst]), 0));
+                    }
+                    if ((kb + 1) % flush_kb == 0 || kb + 1 == nkb) {
+                        mbar_wait(&bars->acc_drained, dc & 1);
+                        mbar_arrive_remote(r_drained);
+                        ++dc;
+                    }
+                }
+            }
         } else if (warp == 17 && lane == 0) {
-            // ================= operand loader (one thread, TMA engine bulk copies) =================
-            // Pacing: the bulk copies are asynchronous, so nothing couples the speed of a CTA to its L2 hit rate
-            // and CTAs would drift apart until every image tile is fetched from HBM once per CTA.  Every
-            // `flush_kb` blocks (an epoch) the loader announces itself on a global counter and does not start
-            // epoch e before all gridDim CTAs (all co-resident: one per SM) have started epoch e - 1.
+            // ================= operand loader (one thread per CTA, TMA engine bulk copies) =================
+            // Pacing: the bulk copies are asynchronous, so nothing couples the speed of a cluster to its L2 hit
+            // rate and clusters would drift apart until every image tile is fetched from HBM once per cluster.
+            // Every `flush_kb` blocks (an epoch) the leader's loader announces itself on a global counter and
+            // does not start epoch e before all clusters (all co-resident: one CTA per SM) have started epoch
+            // e - 1; the peer's loader is tied to the leader by the shared a_empty / b_empty completions.
             uint32_t zc = 0, epoch = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            for (int u = cluster_id; u < n_units; u += n_clusters) {
                 TF_UNIT_DECODE
                 for (int kb = 0; kb < nkb; ++kb, ++zc) {
-                    if (zc % (uint32_t)flush_kb == 0) {
-                        const unsigned int target = epoch * gridDim.x;
+                    if (rank == 0 && zc % (uint32_t)flush_kb == 0) {
+                        const unsigned int target = epoch * (unsigned int)n_clusters;
                         while (*reinterpret_cast<volatile unsigned int*>(pace) < target) __nanosleep(100);
                         atomicAdd(pace, 1u);
                         ++epoch;
@@ -388,13 +428,13 @@ tc_fstats_kernel(const unsigned char* __restrict__ zimg, const unsigned char* __
                     bulk_g2s(sA + b * TF_PAIR, rimg + ((size_t)cb * nkb_cap + kblock0 + kb) * TF_PAIR, TF_PAIR, &bars->a_full[b]);
                 }
             }
-            if ((int)epoch < pace_epochs) atomicAdd(pace, (unsigned int)pace_epochs - epoch);   // credit the epochs this CTA never starts
+            if (rank == 0 && (int)epoch < pace_epochs) atomicAdd(pace, (unsigned int)pace_epochs - epoch);   // epochs this cluster never starts
         }
     }
 #undef TF_UNIT_DECODE
     tc_fence_before();
-    __syncthreads();
-    if (warp == 16) tmem_dealloc(tmem_base, 512);
+    cluster_sync_all();                                   // no CTA leaves (or frees TMEM) while its partner may still signal it
+    if (warp == 16) tmem_dealloc2(tmem_base, 512);
 }
 
 // stat[k][tri(i, j)] += scale(i, j) * partial[k / 128][slot][k % 128]
@@ -427,7 +467,7 @@ bool tc_fstats_supported(int dtype, int D, int F) {
 struct TfLayout { int cbs; int64_t nkb_cap; size_t off_partial, off_zimg, off_rimg, bytes; };
 static TfLayout tf_layout(int64_t chunk_points, int K) {
     TfLayout L;
-    L.cbs = (K + 127) / 128;
+    L.cbs = ((K + 127) / 128 + 1) / 2 * 2;            // component blocks, rounded up to whole CTA pairs (zero padded)
     L.nkb_cap = std::max<int64_t>(1, (chunk_points + TF_KB - 1) / TF_KB);
     size_t o = 1024;
     L.off_partial = o; o += up1k((size_t)L.cbs * TF_ROWS * TF_DC * 128 * sizeof(double));
@@ -466,20 +506,22 @@ int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* 
     tc_fstats_rimg_kernel<<<dim3((unsigned)blocks, (unsigned)L.cbs), 256, 0, st>>>(R, N, ldr, K, rvec4, L.nkb_cap, rimg);
     MIMO_LAUNCH_CHECK();
     const int fbs = (TF_ROWS + TF_FBROWS - 1) / TF_FBROWS;
-    // point slabs only when one (component block, feature block) grid does not fill the SMs
-    int slabs = std::max(1, sm_count() / (L.cbs * fbs));
+    const int cbps = L.cbs / 2, max_clusters = sm_count() / 2;
+    // point slabs only when one (component-block pair, feature block) grid does not fill the SMs
+    int slabs = std::max(1, max_clusters / (cbps * fbs));
     slabs = (int)std::min<int64_t>(slabs, std::max<int64_t>(1, blocks / 8));
     const int64_t slab_points = (blocks + slabs - 1) / slabs * TF_KB;
     MIMO_CUDA(cudaFuncSetAttribute(tc_fstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM));
-    const int n_units = L.cbs * fbs * slabs;
-    const int grid = std::min(n_units, sm_count());
+    const int n_units = cbps * fbs * slabs;
+    const int clusters = std::min(n_units, max_clusters);
+    const int grid = 2 * clusters;
     const int flush_kb = 2 * g_flush_tiles_f;
-    // upper bound of the pacing epochs of one CTA: its units hold at most slab_points / 64 blocks each
-    const int64_t units_per_cta = (n_units + grid - 1) / grid;
+    // upper bound of the pacing epochs of one cluster: its units hold at most slab_points / 64 blocks each
+    const int64_t units_per_cta = (n_units + clusters - 1) / clusters;
     const int pace_epochs = (int)((units_per_cta * (slab_points / TF_KB) + flush_kb - 1) / flush_kb) + 1;
     unsigned int* pace = (unsigned int*)base;
     MIMO_CUDA(cudaMemsetAsync(pace, 0, 4, st));
-    tc_fstats_kernel<<<grid, TF_THREADS, TF_SMEM, st>>>(zimg, rimg, L.nkb_cap, N, partial, pace, L.cbs, fbs, slabs, slab_points,
+    tc_fstats_kernel<<<grid, TF_THREADS, TF_SMEM, st>>>(zimg, rimg, L.nkb_cap, N, partial, pace, cbps, fbs, slabs, slab_points,
                                                         flush_kb, pace_epochs);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
