@@ -56,6 +56,16 @@ def read_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src='fallback')
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full` capture of
+    the same kernel on one point chunk of this workload (profiles/r01_ncu_traffic.json); None when not captured."""
+    p = os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
+
+
 def algorithmic_work(w):
     """flops per (point, component) pair and bytes per point of one sweep."""
     d, K = w['d'], w['K']
@@ -439,6 +449,11 @@ def main():
     else:
         ach = n_local * work['bytes_pt'] / (phase_ms[dom] * 1e-3) / 1e9 if phase_ms[dom] > 0 else 0.0
         roof = dict(bound='hbm', achieved=ach, peak=peaks['hbm'], unit='GB/s', frac=ach / peaks['hbm'], traffic=None)
+    if name == 'cfg5' and not args.n_override:
+        tr = ncu_traffic(['tc_estep2_kernel', 'softmax_kernel', 'tc_fstats_kernel'][dom])
+        if tr:
+            roof['traffic'] = tr['bytes']                     # DRAM bytes per launch (one ~1M-point chunk)
+            roof['traffic_source'] = tr['source']
     roof.update(kernel=['E-step (log-likelihood)', 'softmax / label draw', 'sufficient statistics'][dom],
                 launches_per_step=launches_per_step, ms_per_launch=phase_ms[dom] / max(launches_per_step, 1),
                 phase_ms_per_step=dict(estep=phase_ms[0], softmax=phase_ms[1], stats=phase_ms[2]),

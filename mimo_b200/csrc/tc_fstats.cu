@@ -34,6 +34,7 @@
 // (red.global) to the partial buffer [component block][slot][component lane], which
 // tc_fstats_end folds into the packed (K, F) statistics once per sweep.
 #include <algorithm>
+#include <cmath>
 #include "tc_common.cuh"
 #include "internal.h"
 
@@ -507,9 +508,18 @@ int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* 
     MIMO_LAUNCH_CHECK();
     const int fbs = (TF_ROWS + TF_FBROWS - 1) / TF_FBROWS;
     const int cbps = L.cbs / 2, max_clusters = sm_count() / 2;
-    // point slabs only when one (component-block pair, feature block) grid does not fill the SMs
-    int slabs = std::max(1, max_clusters / (cbps * fbs));
-    slabs = (int)std::min<int64_t>(slabs, std::max<int64_t>(1, blocks / 8));
+    // point slabs: the count (<= 16, >= 64 blocks each) that fills the clusters most evenly over whole rounds
+    // of the static schedule, e.g. K = 1024: 68 units x 13 slabs = 884 = 11.95 rounds of 74 clusters
+    int slabs = 1;
+    {
+        double best = 0.0;
+        const int max_slabs = (int)std::min<int64_t>(16, std::max<int64_t>(1, blocks / 64));
+        for (int sl = 1; sl <= max_slabs; ++sl) {
+            const double units = (double)cbps * fbs * sl;
+            const double eff = units / (std::ceil(units / max_clusters) * max_clusters);
+            if (eff > best + 0.01) { best = eff; slabs = sl; }
+        }
+    }
     const int64_t slab_points = (blocks + slabs - 1) / slabs * TF_KB;
     MIMO_CUDA(cudaFuncSetAttribute(tc_fstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM));
     const int n_units = cbps * fbs * slabs;
