@@ -515,4 +515,12 @@ def time_e2e(w, s, E, _lib, hard, steps):
 
 
 if __name__ == '__main__':
-    main()
+    try:
+        main()
+    finally:
+        try:
+            import torch.distributed as _d
+            if _d.is_available() and _d.is_initialized():
+                _d.destroy_process_group()
+        except Exception:
+            pass
