@@ -98,7 +98,13 @@ int mimo_softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags,
  * DESIGN.md section 5).  mimo_sweep picks these kernels by itself when
  * mimo_sweep_uses_tensor_cores() says so; the stand-alone entry points exist for parity tests.
  * Same reference call sites as mimo_loglik_quad / mimo_stats_soft.                          */
-int mimo_set_tensor_cores(int mode);        /* 0: CUDA cores only, 1 (default): automatic; returns the old mode */
+/* mode 0: CUDA cores only; 1 (default): tcgen05 kernels on CTA pairs, E-step screened (one FP16 pass over all
+ * pairs + exact recomputation of the pairs within 40 nats of a point's best component, or -- device-side choice
+ * when more than 4 % of the pairs qualify -- the dense 3-pass kernel); 2: single-CTA dense kernels; 3: CTA pairs,
+ * dense.  Returns the old mode. */
+int mimo_set_tensor_cores(int mode);
+/* {candidate pairs, dense-fallback flag} of the most recent screened point chunk (synchronises; diagnostics) */
+int mimo_tc_screen_last(uint32_t* out_host2);
 int mimo_sweep_uses_tensor_cores(int dtype, int family, int D, int Rp);
 int mimo_tc_set_flush_tiles(int tiles);     /* 128-point tiles accumulated in TMEM (FP32) between FP64 drains */
 size_t mimo_loglik_quad_tc_workspace(int K, int Rp, int D);

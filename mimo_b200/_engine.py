@@ -438,8 +438,16 @@ def mstep_lingauss(stat, F, stat_idx, Dp, K, c, o, tied=False, info=None):
 
 # ---- tensor-core variants (stand-alone entry points; mimo_sweep dispatches by itself) ---------------
 def set_tensor_cores(mode):
-    """0: CUDA-core kernels only; 1: tcgen05 kernels where supported (default).  Returns the old mode."""
+    """0: CUDA-core kernels only; 1 (default): tcgen05 kernels on CTA pairs with the screened E-step;
+    2: single-CTA dense tcgen05 kernels; 3: CTA pairs, dense E-step.  Returns the old mode."""
     return _lib.load().mimo_set_tensor_cores(int(mode))
+
+
+def screen_last():
+    """(candidate pairs, dense-fallback flag) of the most recent screened point chunk."""
+    out = np.zeros(2, dtype=np.uint32)
+    _lib.call('mimo_tc_screen_last', out.ctypes.data)
+    return int(out[0]), int(out[1])
 
 
 def sweep_uses_tensor_cores(ops, D):

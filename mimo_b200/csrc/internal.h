@@ -21,20 +21,35 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
                void* workspace, size_t workspace_bytes, bool check, cudaStream_t st);
 
 // tensor-core (tcgen05) path, FP32 quad family, D <= 128  (tc_estep.cu, tc_stats.cu)
-int tc_mode();                       // 0 = CUDA cores only, 1 = tensor cores (CTA-pair E-step), 2 = tensor cores (single-CTA E-step)
+int tc_mode();                       // 0 CUDA cores only; 1 tensor cores: CTA pairs + screened E-step (default); 2 single-CTA dense; 3 CTA pairs dense
 int tc_set_mode(int mode);
 bool tc_estep_supported(int dtype, int D, int Rp);
 size_t tc_operand_workspace(int K, int Rp, int D);
 int tc_data_scale(const float* Z, int64_t N, int D, int64_t ldz, void* ws, cudaStream_t st);
 const unsigned int* tc_maxbits(void* ws);
-int tc_prepare_operands(const float* W, int K, int Rp, int Dpp, int D, void* ws, cudaStream_t st);
+int tc_prepare_operands(const float* W, const float* cst, int K, int Rp, int Dpp, int D, void* ws, cudaStream_t st);
+unsigned int* tc_flags(void* ws);    // [0] max |z| bits, [2] max_k ||W_k||_F bits, [3] max_n ||z_n||_2 bits
+int tc_estep_pass(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, float* out, int64_t ldo, void* ws,
+                  int passes, const unsigned int* gate, unsigned int gate_value, cudaStream_t st);
+// screened E-step (tc_screen.cu): single-pass screening + exact refinement of the candidates / gated dense pass
+bool tc_screen_supported(int D, int Rp);
+size_t tc_screen_workspace(int64_t chunk_points, int K);
+int tc_screen_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp,
+                      unsigned int* flags, cudaStream_t st);
+const unsigned int* tc_screen_gate(void* ws, int64_t plan_points, int K);
+int tc_screen_last(unsigned int* out_host2);
+int tc_screen_select(const float* a, int K, int64_t n, int64_t ldo, const float* cst, const unsigned int* flags,
+                     int64_t plan_points, void* ws, cudaStream_t st);
+int tc_screen_refine(const float* Z, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp, const float* cst,
+                     float* a, int64_t ldo, int64_t plan_points, void* ws, cudaStream_t st);
 int tc_estep(const float* Z, int64_t N, int D, int64_t ldz, const float* cst, int K, int Rp,
              float* out, int64_t ldo, void* ws, cudaStream_t st);
 // CTA-pair (cta_group::2) E-step, tc_estep2.cu
 size_t tc2_offsets_bytes(int K, int Rp);
 int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cst, int K, int Rp, float* offs2, cudaStream_t st);
 int tc_estep2(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, int KB, const void* Bimg, const float* offs2,
-              const unsigned int* maxbits, float* out, int64_t ldo, cudaStream_t st);
+              const unsigned int* maxbits, float* out, int64_t ldo, int passes, const unsigned int* gate, unsigned int gate_value,
+              cudaStream_t st);
 int loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* W, const void* cst,
                    int K, int Rp, int Dpp, void* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st);
 bool tc_stats_supported(int dtype, int D, int F);

@@ -14,12 +14,16 @@ static size_t a256(size_t x) { return (x + 255) / 256 * 256; }
 
 static int g_tc_mode = 1;
 int tc_mode() { return g_tc_mode; }
-int tc_set_mode(int mode) { int old = g_tc_mode; g_tc_mode = (mode < 0 || mode > 2) ? 1 : mode; return old; }
+int tc_set_mode(int mode) { int old = g_tc_mode; g_tc_mode = (mode < 0 || mode > 3) ? 1 : mode; return old; }
 
 // the tensor-core path takes FP32 quad-family sweeps whose contraction is wide enough to pay for
 // the 64-wide K blocks of the operand layout
 bool sweep_uses_tc(int dtype, int family, int D, int Rp) {
     return g_tc_mode && family == 0 && D >= 24 && tc_estep_supported(dtype, D, Rp);
+}
+// screened E-step: worth it when a point's candidates (>= 1) can stay below 4 % of the K components
+static bool sweep_uses_screen(int dtype, int family, int D, int K, int Rp) {
+    return g_tc_mode == 1 && K >= 32 && sweep_uses_tc(dtype, family, D, Rp) && tc_screen_supported(D, Rp);
 }
 
 // points per chunk.
@@ -54,6 +58,7 @@ size_t sweep_workspace(int dtype, int family, int hard, int64_t N, int D, int K,
     if (hard) b += a256((size_t)N * 4) + a256(stats_hard_workspace(N, K));
     if (sweep_uses_tc(dtype, family, D, Rp)) {
         b += a256(tc_operand_workspace(K, Rp, D));
+        if (sweep_uses_screen(dtype, family, D, K, Rp)) b += a256(tc_screen_workspace(c, K));
         if (!hard) b += a256(std::max(tc_stats_workspace(c, K), tc_fstats_workspace(c, K)));
     }
     return b;
@@ -83,16 +88,24 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     if (hard) ws += a256(hard_ws_bytes);
     void* tc_ops_ws = nullptr;
     void* tc_stat_ws = nullptr;
+    void* screen_ws = nullptr;
+    // the (K, N) log-joint output must hold FP32-class values for every pair: no screening then
+    const bool use_screen = sweep_uses_screen(dtype, family, D, K, Rp) && !ll_out;
     // the packed full-triangle statistics are what the tensor-core statistics kernel produces
     const bool tc_stats = use_tc && stat && !hard && tc_stats_supported(dtype, D, F);
     const bool tc_fstats = tc_stats && tc_fstats_supported(dtype, D, F);     // feature form (folded triangle) for D > 64
     if (use_tc) {
         tc_ops_ws = ws; ws += a256(tc_operand_workspace(K, Rp, D));
+        if (sweep_uses_screen(dtype, family, D, K, Rp)) { screen_ws = ws; ws += a256(tc_screen_workspace(C, K)); }
         if (!hard) tc_stat_ws = ws;
         int rc = tc_data_scale((const float*)Z, N, D, ldz, tc_ops_ws, st);
         if (rc) return rc;
-        rc = tc_prepare_operands((const float*)op_a, K, Rp, Dpp, D, tc_ops_ws, st);
+        rc = tc_prepare_operands((const float*)op_a, (const float*)cst, K, Rp, Dpp, D, tc_ops_ws, st);
         if (rc) return rc;
+        if (use_screen) {
+            rc = tc_screen_prepare((const float*)Z, N, D, ldz, (const float*)op_a, K, Rp, Dpp, tc_flags(tc_ops_ws), st);
+            if (rc) return rc;
+        }
         if (tc_stats) { rc = tc_fstats ? tc_fstats_begin(C, K, tc_stat_ws, st) : tc_stats_begin(C, K, tc_stat_ws, st); if (rc) return rc; }
     }
 
@@ -104,7 +117,18 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         mark();
         const char* Zc = (const char*)Z + (size_t)n0 * ldz * es;
         int rc;
-        if (use_tc)           rc = tc_estep((const float*)Zc, nc, D, ldz, (const float*)cst, K, Rp, (float*)scratch, C, tc_ops_ws, st);
+        if (use_screen) {
+            // single-pass screening over all pairs, then either the exact refinement of the candidates or (device-side
+            // flag, when > 4 % of the pairs are candidates) the dense 3-pass kernel
+            rc = tc_estep_pass((const float*)Zc, nc, D, ldz, K, Rp, (float*)scratch, C, tc_ops_ws, 1, nullptr, 0u, st);
+            if (rc) return rc;
+            rc = tc_screen_select((const float*)scratch, K, nc, C, (const float*)cst, tc_flags(tc_ops_ws), C, screen_ws, st);
+            if (rc) return rc;
+            rc = tc_estep_pass((const float*)Zc, nc, D, ldz, K, Rp, (float*)scratch, C, tc_ops_ws, 3, tc_screen_gate(screen_ws, C, K), 1u, st);
+            if (rc) return rc;
+            rc = tc_screen_refine((const float*)Zc, D, ldz, (const float*)op_a, K, Rp, Dpp, (const float*)cst, (float*)scratch, C, C, screen_ws, st);
+        }
+        else if (use_tc)      rc = tc_estep((const float*)Zc, nc, D, ldz, (const float*)cst, K, Rp, (float*)scratch, C, tc_ops_ws, st);
         else if (family == 0) rc = loglik_quad(dtype, Zc, nc, D, ldz, op_a, cst, K, Rp, Dpp, scratch, C, st);
         else             rc = loglik_diag(dtype, Zc, nc, D, ldz, op_a, op_b, cst, K, scratch, C, st);
         if (rc) return rc;
@@ -153,7 +177,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             }
             // kernel launches of this chunk: E-step (+ offsets blocks for the CTA-pair kernel), softmax,
             // statistics (feature form: data image + responsibility image + GEMM)
-            phase_ms[3] += 2.0 + ((use_tc && tc_mode() == 1) ? 1.0 : 0.0)
+            phase_ms[3] += 2.0 + (use_screen ? 6.0 : 0.0)
                          + ((hard || !stat) ? 0.0 : (tc_fstats ? 3.0 : 1.0));
         }
         if (h0) {
@@ -163,7 +187,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             phase_ms[3] += 4.0;
             cudaEventDestroy(h0); cudaEventDestroy(h1);
         }
-        if (use_tc) phase_ms[3] += 2.0 + (tc_stats ? 1.0 : 0.0);      // data scale, operand image, statistics fold
+        if (use_tc) phase_ms[3] += 3.0 + (tc_stats ? 1.0 : 0.0) + (use_screen ? 2.0 : 0.0);   // data scale, operand image + offsets, norms, statistics fold
         phase_ms[4] += (double)((N + C - 1) / C);                      // point chunks
         for (auto e : ev) cudaEventDestroy(e);
     }

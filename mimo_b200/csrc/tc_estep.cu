@@ -341,15 +341,29 @@ int tc_data_scale(const float* Z, int64_t N, int D, int64_t ldz, void* ws, cudaS
 
 const unsigned int* tc_maxbits(void* ws) { return (const unsigned int*)align1k(ws); }
 
-// operand image for the current W (after tc_data_scale on the same ws)
-int tc_prepare_operands(const float* W, int K, int Rp, int Dpp, int D, void* ws, cudaStream_t st) {
+// operand image for the current W and cst (after tc_data_scale on the same ws)
+int tc_prepare_operands(const float* W, const float* cst, int K, int Rp, int Dpp, int D, void* ws, cudaStream_t st) {
     TcOperandLayout L = tc_layout(K, Rp, D);
     char* base = align1k(ws);
     tc_prep_operands_kernel<<<L.n_chunks, 256, 0, st>>>(W, K, Rp, Dpp, D, L.KB, (const unsigned int*)(base + L.off_maxbits),
                                                         (__half*)(base + L.off_img), (float*)(base + L.off_rowoff),
                                                         (float*)(base + L.off_invS2));
     MIMO_LAUNCH_CHECK();
-    return MIMO_OK;
+    // per-chunk offsets / constants blocks of the CTA-pair kernel
+    return tc2_prepare_offsets((const float*)(base + L.off_rowoff), (const float*)(base + L.off_invS2), cst, K, Rp,
+                               (float*)(base + L.off_offs2), st);
+}
+
+unsigned int* tc_flags(void* ws) { return (unsigned int*)align1k(ws); }
+
+// CTA-pair kernel with an explicit number of passes and an optional device-side gate (tc_screen.cu)
+int tc_estep_pass(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, float* out, int64_t ldo, void* ws,
+                  int passes, const unsigned int* gate, unsigned int gate_value, cudaStream_t st) {
+    if (N == 0) return MIMO_OK;
+    TcOperandLayout L = tc_layout(K, Rp, D);
+    char* base = align1k(ws);
+    return tc_estep2(Z, N, D, ldz, K, Rp, L.KB, (const void*)(base + L.off_img), (const float*)(base + L.off_offs2),
+                     (const unsigned int*)(base + L.off_maxbits), out, ldo, passes, gate, gate_value, st);
 }
 
 template <int KB, int RP>
@@ -374,14 +388,9 @@ int tc_estep(const float* Z, int64_t N, int D, int64_t ldz, const float* cst, in
     if (N == 0) return MIMO_OK;
     TcOperandLayout L = tc_layout(K, Rp, D);
     char* base = align1k(ws);
-    if (tc_mode() == 1) {
-        // CTA-pair kernel (cta_group::2): needs the per-chunk offsets block, built from the current cst
-        int rc = tc2_prepare_offsets((const float*)(base + L.off_rowoff), (const float*)(base + L.off_invS2), cst, K, Rp,
-                                     (float*)(base + L.off_offs2), st);
-        if (rc) return rc;
+    if (tc_mode() != 2)        // CTA-pair kernel (cta_group::2), dense 3-pass
         return tc_estep2(Z, N, D, ldz, K, Rp, L.KB, (const void*)(base + L.off_img), (const float*)(base + L.off_offs2),
-                         (const unsigned int*)(base + L.off_maxbits), out, ldo, st);
-    }
+                         (const unsigned int*)(base + L.off_maxbits), out, ldo, 3, nullptr, 0u, st);
 #define TE_CASE(kb, rp) if (L.KB == kb && Rp == rp) return launch_estep<kb, rp>(Z, N, D, ldz, L, base, cst, K, out, ldo, st);
     TE_CASE(1, 8) TE_CASE(1, 16) TE_CASE(1, 32) TE_CASE(1, 64) TE_CASE(1, 128)
     TE_CASE(2, 8) TE_CASE(2, 16) TE_CASE(2, 32) TE_CASE(2, 64) TE_CASE(2, 128)
@@ -400,7 +409,7 @@ int loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* W, 
     MIMO_CHECK_ARG(ws_bytes >= tc_operand_workspace(K, Rp, D), "workspace too small");
     int rc = tc_data_scale((const float*)Z, N, D, ldz, ws, st);
     if (rc) return rc;
-    rc = tc_prepare_operands((const float*)W, K, Rp, Dpp, D, ws, st);
+    rc = tc_prepare_operands((const float*)W, (const float*)cst, K, Rp, Dpp, D, ws, st);
     if (rc) return rc;
     return tc_estep((const float*)Z, N, D, ldz, (const float*)cst, K, Rp, (float*)out, ldo, ws, st);
 }

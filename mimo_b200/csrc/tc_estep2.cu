@@ -82,12 +82,18 @@ __device__ __forceinline__ void t2_consume(const float (&v)[32], const float* __
     }
 }
 
-template <int KB, int RP>
+// PASSES = 3: Ah*Bh + Ah*Bl + Al*Bh (FP32-class);  PASSES = 1: Ah*Bh only (the screening pass of tc_screen.cu).
+// gate (optional): the whole grid returns at once unless *gate == gate_value (device-side choice between the
+// dense second pass and the per-candidate refinement without a host round trip).
+template <int KB, int RP, int PASSES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int vec4,
                  const __half* __restrict__ Bimg, const float* __restrict__ offs2,
                  const unsigned int* __restrict__ maxbits,
-                 int K, int n_chunks2, float* __restrict__ out, int64_t ldo) {
+                 int K, int n_chunks2, float* __restrict__ out, int64_t ldo,
+                 const unsigned int* __restrict__ gate, unsigned int gate_value) {
+    if (gate != nullptr && __ldg(gate) != gate_value) return;
+    constexpr uint32_t STAGE_TX = PASSES == 3 ? T2_STAGE : T2_TILE;   // bytes copied per stage (hi | lo, or hi only)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // A: [hi|lo][kb KB] tiles of 16 KB;  B: [stage][hi|lo] tiles of 16 KB;  offsets ring: 2 x T2_OFFBYTES
     unsigned char* sA = smem_raw;
@@ -157,7 +163,7 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                         const int kb = f >> 6, ch = (f & 63) >> 3;
                         unsigned char* base = sA + (size_t)kb * T2_TILE + sw128_chunk_off(rr, ch) + (f & 7) * 2;
                         *reinterpret_cast<uint2*>(base) = hi;
-                        *reinterpret_cast<uint2*>(base + (size_t)KB * T2_TILE) = lo;
+                        if (PASSES == 3) *reinterpret_cast<uint2*>(base + (size_t)KB * T2_TILE) = lo;
                     }
                 }
             }
@@ -226,9 +232,13 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {               // 16-element K steps inside the 64-wide block: +32 B
                             if (kb * 4 + kk >= S) continue;
-                            umma2_f16(d, al + 2 * kk, bh + 2 * kk, idesc, (kb | kk) != 0);
-                            umma2_f16(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
-                            umma2_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
+                            if (PASSES == 3) {
+                                umma2_f16(d, al + 2 * kk, bh + 2 * kk, idesc, (kb | kk) != 0);
+                                umma2_f16(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
+                                umma2_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
+                            } else {
+                                umma2_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, (kb | kk) != 0);
+                            }
                         }
                         umma2_commit(&bars->empty[stage]);               // both CTAs' stage free once these MMAs have read it
                         if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
@@ -270,8 +280,8 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                     bulk_g2s(sOff + ob * T2_OFFBLK, offs2 + (size_t)c * T2_OFFBLK, T2_OFFBYTES, &bars->off_full[ob]);
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&bars->empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&bars->full[stage], T2_STAGE);
-                        bulk_g2s(sB + (size_t)stage * T2_STAGE, src + ((size_t)(2 * c + rank) * KB + kb) * T2_STAGE, T2_STAGE, &bars->full[stage]);
+                        mbar_arrive_expect_tx(&bars->full[stage], STAGE_TX);
+                        bulk_g2s(sB + (size_t)stage * T2_STAGE, src + ((size_t)(2 * c + rank) * KB + kb) * T2_STAGE, STAGE_TX, &bars->full[stage]);
                         if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -297,28 +307,33 @@ int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cs
     return MIMO_OK;
 }
 
-template <int KB, int RP>
+template <int KB, int RP, int PASSES>
 static int launch_estep2(const float* Z, int64_t N, int D, int64_t ldz, const __half* Bimg, const float* offs2,
-                         const unsigned int* maxbits, int K, int n_chunks2, float* out, int64_t ldo, cudaStream_t st) {
+                         const unsigned int* maxbits, int K, int n_chunks2, float* out, int64_t ldo,
+                         const unsigned int* gate, unsigned int gate_value, cudaStream_t st) {
     const size_t smem = (size_t)2 * KB * T2_TILE + (size_t)T2_STAGES * T2_STAGE + 2 * T2_OFFBYTES + sizeof(T2Bars);
-    auto kern = tc_estep2_kernel<KB, RP>;
+    auto kern = tc_estep2_kernel<KB, RP, PASSES>;
     MIMO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t passes = (N + 255) / 256;
     const int clusters = (int)std::min<int64_t>(passes, sm_count() / 2);
     const int vec4 = (ldz % 4 == 0) && (((uintptr_t)Z & 15) == 0);
-    kern<<<2 * clusters, T2_THREADS, smem, st>>>(Z, N, D, ldz, vec4, Bimg, offs2, maxbits, K, n_chunks2, out, ldo);
+    kern<<<2 * clusters, T2_THREADS, smem, st>>>(Z, N, D, ldz, vec4, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
 
-// E-step over N points with a prepared operand image (even number of 128-row chunks, zero padded) and offsets blocks
+// E-step over N points with a prepared operand image (even number of 128-row chunks, zero padded) and offsets blocks.
+// passes = 3 (FP32-class) or 1 (screening pass); gate: see the kernel.
 int tc_estep2(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, int KB, const void* Bimg_, const float* offs2,
-              const unsigned int* maxbits, float* out, int64_t ldo, cudaStream_t st) {
+              const unsigned int* maxbits, float* out, int64_t ldo, int passes, const unsigned int* gate, unsigned int gate_value,
+              cudaStream_t st) {
     const __half* Bimg = (const __half*)Bimg_;
     if (N == 0) return MIMO_OK;
     const int n_chunks = (int)(((int64_t)K * Rp + 127) / 128);
     const int n_chunks2 = (n_chunks + 1) / 2;
-#define T2_CASE(kb, rp) if (KB == kb && Rp == rp) return launch_estep2<kb, rp>(Z, N, D, ldz, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, st);
+#define T2_CASE(kb, rp) if (KB == kb && Rp == rp) { \
+        if (passes == 1) return launch_estep2<kb, rp, 1>(Z, N, D, ldz, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, st); \
+        return launch_estep2<kb, rp, 3>(Z, N, D, ldz, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, st); }
     T2_CASE(1, 8) T2_CASE(1, 16) T2_CASE(1, 32) T2_CASE(1, 64) T2_CASE(1, 128)
     T2_CASE(2, 8) T2_CASE(2, 16) T2_CASE(2, 32) T2_CASE(2, 64) T2_CASE(2, 128)
 #undef T2_CASE

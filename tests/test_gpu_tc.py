@@ -180,3 +180,58 @@ def test_sweep_tc_matches_cuda_cores_and_oracle(hard, K, d, N):
     close(S[:, d, d], st[1], 1e-4, 'sweep sum r')
     if not hard:
         close(buf.stat, ref.stat.cpu().numpy(), 2e-5, 'tensor-core vs CUDA-core statistics')
+
+
+@pytest.mark.parametrize('hard', [False, True])
+@pytest.mark.parametrize('K,d,N,sep', [(64, 128, 6000, 6.0), (40, 96, 5000, 6.0), (48, 64, 4000, 0.3), (33, 100, 3000, 1.5)])
+def test_sweep_screened_estep(hard, K, d, N, sep):
+    """default tensor-core mode: single-pass screening + exact refinement of the candidates (separated components)
+    or the device-selected dense second pass (overlapping components).  Either way the sweep must match the dense
+    CTA-pair path and the oracle at the FP32 tolerance."""
+    E = eng()
+    rng = np.random.default_rng(K + d)
+    centres = sep * rng.standard_normal((K, d))
+    z = rng.integers(0, K, size=N)
+    x = centres[z] + rng.standard_normal((N, d))
+    mus = centres + 0.2 * rng.standard_normal((K, d))
+    lmbdas = np.stack([spd(rng, d) for _ in range(K)])
+    logw = np.log(rng.dirichlet(np.ones(K)))
+    ops = E.QuadOperands(K, d, d, 'fp32')
+    E.set_log_weights(ops, logw)
+    E.operands_gauss(ops, E.to_dev(mus), E.to_dev(lmbdas)).check()
+    Z = E.to_dev(x, torch.float32)
+    feats = E.quad_features(d)
+    u = E.to_dev(rng.random(N))
+    buf = E.SweepBuffers(N, K, feats.F, 'fp32', hard)
+    E.sweep(Z, ops, feats, buf, uniforms=u if hard else None)
+    cands, dense = E.screen_last()
+    print('screened sweep K=%d d=%d N=%d sep=%.1f: %d candidates of %d pairs (%.2f%%), dense fallback %d'
+          % (K, d, N, sep, cands, N * K, 100.0 * cands / (N * K), dense))
+    assert cands >= N                                   # every point keeps at least its best component
+    assert dense == (0 if sep >= 1.0 else 1)
+    old = E.set_tensor_cores(3)                         # CTA pairs, dense 3-pass E-step
+    try:
+        ref = E.SweepBuffers(N, K, feats.F, 'fp32', hard)
+        E.sweep(Z, ops, feats, ref, uniforms=u if hard else None)
+    finally:
+        E.set_tensor_cores(old)
+    xr = Z.double().cpu().numpy()
+    ll = orc.gauss_full_loglik(xr, mus, lmbdas) + logw[:, None]
+    resp, lse = orc.responsibilities(ll)
+    close(buf.lse_sum, [lse.sum()], 1e-6, 'lse sum vs oracle')
+    close(buf.lse_sum, ref.lse_sum.cpu().numpy(), 1e-6, 'lse sum vs dense tensor-core path')
+    if hard:
+        lab, lab_d = buf.labels.cpu().numpy(), ref.labels.cpu().numpy()
+        lab_ref = orc.sample_discrete_from_log(ll, u.cpu().numpy())
+        safe = orc.label_boundary_distance(ll, u.cpu().numpy()) > 1e-3
+        assert np.array_equal(lab[safe], lab_ref[safe])
+        assert (lab == lab_d).mean() > 0.999
+        st = orc.gauss_full_wstats(xr, orc.one_hot(lab, K))
+    else:
+        st = orc.gauss_full_wstats(xr, resp)
+    S = unpack_quad(buf.stat.cpu().numpy(), d)
+    close(S[:, :d, :d], st[2], 1e-4, 'screened sweep sum r xx')
+    close(S[:, d, :d], st[0], 1e-4, 'screened sweep sum r x')
+    close(S[:, d, d], st[1], 1e-4, 'screened sweep sum r')
+    if not hard:
+        close(buf.stat, ref.stat.cpu().numpy(), 2e-5, 'screened vs dense statistics')
