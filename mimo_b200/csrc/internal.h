@@ -30,13 +30,14 @@ const unsigned int* tc_maxbits(void* ws);
 int tc_prepare_operands(const float* W, const float* cst, int K, int Rp, int Dpp, int D, void* ws, cudaStream_t st);
 unsigned int* tc_flags(void* ws);    // [0] max |z| bits, [2] max_k ||W_k||_F bits, [3] max_n ||z_n||_2 bits
 int tc_estep_pass(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, float* out, int64_t ldo, void* ws,
-                  int passes, const unsigned int* gate, unsigned int gate_value, cudaStream_t st);
+                  int passes, const unsigned int* gate, unsigned int gate_value, float* lower, int64_t ldl, cudaStream_t st);
 // screened E-step (tc_screen.cu): single-pass screening + exact refinement of the candidates / gated dense pass
 bool tc_screen_supported(int D, int Rp);
 size_t tc_screen_workspace(int64_t chunk_points, int K);
 int tc_screen_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp,
                       unsigned int* flags, cudaStream_t st);
 const unsigned int* tc_screen_gate(void* ws, int64_t plan_points, int K);
+float* tc_screen_lower(void* ws, int64_t plan_points, int K, int64_t* ldl);
 int tc_screen_last(unsigned int* out_host2);
 int tc_screen_select(const float* a, int K, int64_t n, int64_t ldo, const float* cst, const unsigned int* flags,
                      int64_t plan_points, void* ws, cudaStream_t st);
@@ -49,7 +50,7 @@ size_t tc2_offsets_bytes(int K, int Rp);
 int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cst, int K, int Rp, float* offs2, cudaStream_t st);
 int tc_estep2(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, int KB, const void* Bimg, const float* offs2,
               const unsigned int* maxbits, float* out, int64_t ldo, int passes, const unsigned int* gate, unsigned int gate_value,
-              cudaStream_t st);
+              float* lower, int64_t ldl, cudaStream_t st);
 int loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* W, const void* cst,
                    int K, int Rp, int Dpp, void* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st);
 bool tc_stats_supported(int dtype, int D, int F);

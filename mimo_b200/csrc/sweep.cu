@@ -120,11 +120,13 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         if (use_screen) {
             // single-pass screening over all pairs, then either the exact refinement of the candidates or (device-side
             // flag, when > 4 % of the pairs are candidates) the dense 3-pass kernel
-            rc = tc_estep_pass((const float*)Zc, nc, D, ldz, K, Rp, (float*)scratch, C, tc_ops_ws, 1, nullptr, 0u, st);
+            int64_t ldl = 0;
+            float* lower = tc_screen_lower(screen_ws, C, K, &ldl);
+            rc = tc_estep_pass((const float*)Zc, nc, D, ldz, K, Rp, (float*)scratch, C, tc_ops_ws, 1, nullptr, 0u, lower, ldl, st);
             if (rc) return rc;
             rc = tc_screen_select((const float*)scratch, K, nc, C, (const float*)cst, tc_flags(tc_ops_ws), C, screen_ws, st);
             if (rc) return rc;
-            rc = tc_estep_pass((const float*)Zc, nc, D, ldz, K, Rp, (float*)scratch, C, tc_ops_ws, 3, tc_screen_gate(screen_ws, C, K), 1u, st);
+            rc = tc_estep_pass((const float*)Zc, nc, D, ldz, K, Rp, (float*)scratch, C, tc_ops_ws, 3, tc_screen_gate(screen_ws, C, K), 1u, nullptr, 0, st);
             if (rc) return rc;
             rc = tc_screen_refine((const float*)Zc, D, ldz, (const float*)op_a, K, Rp, Dpp, (const float*)cst, (float*)scratch, C, C, screen_ws, st);
         }
@@ -177,7 +179,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             }
             // kernel launches of this chunk: E-step (+ offsets blocks for the CTA-pair kernel), softmax,
             // statistics (feature form: data image + responsibility image + GEMM)
-            phase_ms[3] += 2.0 + (use_screen ? 6.0 : 0.0)
+            phase_ms[3] += 2.0 + (use_screen ? 5.0 : 0.0)
                          + ((hard || !stat) ? 0.0 : (tc_fstats ? 3.0 : 1.0));
         }
         if (h0) {

@@ -174,6 +174,13 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ---- screened E-step (tc_screen.cu): bound B' on || y~ - y ||_2 of the single-pass (FP16-operand) product ----
+// flags (head of the operand workspace): [0] max |z| bits, [2] max_k ||W_k||_F bits, [3] max_n ||z_n||_2 bits
+__device__ __forceinline__ float screen_bound(const unsigned int* __restrict__ flags) {
+    const float wn = __uint_as_float(__ldg(flags + 2)), zn = __uint_as_float(__ldg(flags + 3));
+    return 1.05f * 0.0009765625f * wn * zn + 1e-3f;
+}
+
 // ---- bulk copy global -> shared through the TMA engine (no tensor map: the source is already
 //      laid out as the shared-memory image) ------------------------------------------------
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

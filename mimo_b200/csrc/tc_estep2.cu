@@ -32,12 +32,13 @@ constexpr uint32_t T2_TILE = 16384;          // 128 rows x 64 FP16
 constexpr uint32_t T2_STAGE = 2 * T2_TILE;
 constexpr int T2_OFFBLK = 320;               // floats per 256-row chunk: 256 row offsets | 32 cst | 32 1/scale^2
 constexpr uint32_t T2_OFFBYTES = T2_OFFBLK * 4;
+constexpr int T2_OFFRING = 8;                // offsets blocks in flight: deep enough that the producer never waits for the epilogue
 
 struct T2Bars {
     uint64_t full[T2_STAGES], empty[T2_STAGES], peer_full[T2_STAGES];
     uint64_t tmem_full[2], tmem_empty[2], peer_tmem_empty[2];
     uint64_t a_full, peer_a_full;
-    uint64_t off_full[2], off_empty[2];
+    uint64_t off_full[T2_OFFRING], off_empty[T2_OFFRING];
     uint32_t tmem_base;
 };
 
@@ -58,10 +59,11 @@ __global__ void tc2_offsets_kernel(const float* __restrict__ rowoff, const float
 }
 
 // 32 accumulator columns -> partial squared norms (4 independent chains), component boundaries every RP columns
-template <int RP>
+// SCREEN: also maintain L = max_k [ cst_k - (sqrt(q) + B)^2 / 2 ], the lower bound of the point's best log-joint
+template <int RP, bool SCREEN>
 __device__ __forceinline__ void t2_consume(const float (&v)[32], const float* __restrict__ off_s, int col0, float (&q)[4],
                                            const float* __restrict__ scal_s, int jbase, int kbase, int K, bool pvalid,
-                                           float* __restrict__ outp, int64_t ldo) {
+                                           float* __restrict__ outp, int64_t ldo, float B, float& L) {
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
         const float4 o = *reinterpret_cast<const float4*>(off_s + col0 + j4 * 4);       // broadcast read
@@ -75,7 +77,9 @@ __device__ __forceinline__ void t2_consume(const float (&v)[32], const float* __
                 const int j = jbase + col / RP;                    // component inside the 256-row chunk
                 const int k = kbase + j;
                 const float qq = (q[0] + q[1]) + (q[2] + q[3]);
-                if (pvalid && k < K) outp[(int64_t)k * ldo] = scal_s[j] - 0.5f * scal_s[32 + j] * qq;
+                const float qt = scal_s[32 + j] * qq;              // || W_k [z ; 1] ||^2 in true units
+                if (pvalid && k < K) outp[(int64_t)k * ldo] = scal_s[j] - 0.5f * qt;
+                if (SCREEN && k < K) { const float sq = sqrtf(qt) + B; L = fmaxf(L, scal_s[j] - 0.5f * sq * sq); }
                 q[0] = q[1] = q[2] = q[3] = 0.f;
             }
         }
@@ -91,15 +95,16 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                  const __half* __restrict__ Bimg, const float* __restrict__ offs2,
                  const unsigned int* __restrict__ maxbits,
                  int K, int n_chunks2, float* __restrict__ out, int64_t ldo,
-                 const unsigned int* __restrict__ gate, unsigned int gate_value) {
+                 const unsigned int* __restrict__ gate, unsigned int gate_value,
+                 float* __restrict__ lower, int64_t ldl) {
     if (gate != nullptr && __ldg(gate) != gate_value) return;
     constexpr uint32_t STAGE_TX = PASSES == 3 ? T2_STAGE : T2_TILE;   // bytes copied per stage (hi | lo, or hi only)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // A: [hi|lo][kb KB] tiles of 16 KB;  B: [stage][hi|lo] tiles of 16 KB;  offsets ring: 2 x T2_OFFBYTES
+    // A: [hi|lo][kb KB] tiles of 16 KB;  B: [stage][hi|lo] tiles of 16 KB;  offsets ring: T2_OFFRING x T2_OFFBYTES
     unsigned char* sA = smem_raw;
     unsigned char* sB = sA + (size_t)2 * KB * T2_TILE;
     float* sOff = reinterpret_cast<float*>(sB + (size_t)T2_STAGES * T2_STAGE);
-    T2Bars* bars = reinterpret_cast<T2Bars*>(reinterpret_cast<unsigned char*>(sOff) + 2 * T2_OFFBYTES);
+    T2Bars* bars = reinterpret_cast<T2Bars*>(reinterpret_cast<unsigned char*>(sOff) + T2_OFFRING * T2_OFFBYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
@@ -110,8 +115,8 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
         for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); mbar_init(&bars->peer_full[s], 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 256); mbar_init(&bars->peer_tmem_empty[b], 1);
-            mbar_init(&bars->off_full[b], 1); mbar_init(&bars->off_empty[b], 256);
         }
+        for (int b = 0; b < T2_OFFRING; ++b) { mbar_init(&bars->off_full[b], 1); mbar_init(&bars->off_empty[b], 256); }
         mbar_init(&bars->a_full, 256);
         mbar_init(&bars->peer_a_full, 1);
         fence_barrier_init();
@@ -126,6 +131,8 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
     if (warp < 8) {
         // ================= converter + epilogue warps =================
         const float sz = pow2_scale_for(__uint_as_float(__ldg(maxbits)));
+        constexpr bool SCREEN = PASSES == 1;
+        const float Bnd = SCREEN ? screen_bound(maxbits) : 0.f;
         const int half = warp >> 2, qd = warp & 3;
         const int prow = qd * 32 + lane;                             // point row inside the tile = TMEM lane
         uint32_t gc = 0;
@@ -174,13 +181,15 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
             const int64_t n = n0 + prow;
             const bool pvalid = n < N;
             float* outp = out + n;
+            float Lb = -INFINITY;
             for (int c = 0; c < n_chunks2; ++c, ++gc) {
                 const uint32_t buf = gc & 1, par = (gc >> 1) & 1;
-                mbar_wait(&bars->off_full[buf], par);
+                const uint32_t ob = gc % T2_OFFRING;
+                mbar_wait(&bars->off_full[ob], (gc / T2_OFFRING) & 1);
                 mbar_wait(&bars->tmem_full[buf], par);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * 256 + half * 128;
-                const float* blk = sOff + buf * T2_OFFBLK;
+                const float* blk = sOff + ob * T2_OFFBLK;
                 const float* off_s = blk + half * 128;
                 const float* scal_s = blk + 256;
                 const int kbase = c * (256 / RP), jbase = half * (128 / RP);
@@ -189,19 +198,20 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                 tmem_ld32(taddr, va);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 32, vb);
-                t2_consume<RP>(va, off_s, 0, q, scal_s, jbase, kbase, K, pvalid, outp, ldo);
+                t2_consume<RP, SCREEN>(va, off_s, 0, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Bnd, Lb);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 64, va);
-                t2_consume<RP>(vb, off_s, 32, q, scal_s, jbase, kbase, K, pvalid, outp, ldo);
+                t2_consume<RP, SCREEN>(vb, off_s, 32, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Bnd, Lb);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 96, vb);
-                t2_consume<RP>(va, off_s, 64, q, scal_s, jbase, kbase, K, pvalid, outp, ldo);
+                t2_consume<RP, SCREEN>(va, off_s, 64, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Bnd, Lb);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&bars->tmem_empty[buf]);             // accumulator drained: the pair's MMA may reuse it
-                t2_consume<RP>(vb, off_s, 96, q, scal_s, jbase, kbase, K, pvalid, outp, ldo);
-                mbar_arrive(&bars->off_empty[buf]);
+                t2_consume<RP, SCREEN>(vb, off_s, 96, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Bnd, Lb);
+                mbar_arrive(&bars->off_empty[ob]);
             }
+            if (SCREEN && pvalid) lower[(int64_t)half * ldl + n] = Lb;
         }
     } else if (warp == 8) {
         if (lane == 0 && rank == 0) {
@@ -274,8 +284,8 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
             for (int64_t pass = cluster_id; pass < n_passes; pass += n_clusters) {
                 const unsigned char* src = reinterpret_cast<const unsigned char*>(Bimg);
                 for (int c = 0; c < n_chunks2; ++c, ++gc) {
-                    const uint32_t ob = gc & 1;
-                    mbar_wait(&bars->off_empty[ob], ((gc >> 1) & 1) ^ 1);
+                    const uint32_t ob = gc % T2_OFFRING;
+                    mbar_wait(&bars->off_empty[ob], ((gc / T2_OFFRING) & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars->off_full[ob], T2_OFFBYTES);
                     bulk_g2s(sOff + ob * T2_OFFBLK, offs2 + (size_t)c * T2_OFFBLK, T2_OFFBYTES, &bars->off_full[ob]);
                     for (int kb = 0; kb < KB; ++kb) {
@@ -310,14 +320,14 @@ int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cs
 template <int KB, int RP, int PASSES>
 static int launch_estep2(const float* Z, int64_t N, int D, int64_t ldz, const __half* Bimg, const float* offs2,
                          const unsigned int* maxbits, int K, int n_chunks2, float* out, int64_t ldo,
-                         const unsigned int* gate, unsigned int gate_value, cudaStream_t st) {
-    const size_t smem = (size_t)2 * KB * T2_TILE + (size_t)T2_STAGES * T2_STAGE + 2 * T2_OFFBYTES + sizeof(T2Bars);
+                         const unsigned int* gate, unsigned int gate_value, float* lower, int64_t ldl, cudaStream_t st) {
+    const size_t smem = (size_t)2 * KB * T2_TILE + (size_t)T2_STAGES * T2_STAGE + T2_OFFRING * T2_OFFBYTES + sizeof(T2Bars);
     auto kern = tc_estep2_kernel<KB, RP, PASSES>;
     MIMO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t passes = (N + 255) / 256;
     const int clusters = (int)std::min<int64_t>(passes, sm_count() / 2);
     const int vec4 = (ldz % 4 == 0) && (((uintptr_t)Z & 15) == 0);
-    kern<<<2 * clusters, T2_THREADS, smem, st>>>(Z, N, D, ldz, vec4, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value);
+    kern<<<2 * clusters, T2_THREADS, smem, st>>>(Z, N, D, ldz, vec4, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, lower, ldl);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
@@ -326,14 +336,14 @@ static int launch_estep2(const float* Z, int64_t N, int D, int64_t ldz, const __
 // passes = 3 (FP32-class) or 1 (screening pass); gate: see the kernel.
 int tc_estep2(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, int KB, const void* Bimg_, const float* offs2,
               const unsigned int* maxbits, float* out, int64_t ldo, int passes, const unsigned int* gate, unsigned int gate_value,
-              cudaStream_t st) {
+              float* lower, int64_t ldl, cudaStream_t st) {
     const __half* Bimg = (const __half*)Bimg_;
     if (N == 0) return MIMO_OK;
     const int n_chunks = (int)(((int64_t)K * Rp + 127) / 128);
     const int n_chunks2 = (n_chunks + 1) / 2;
 #define T2_CASE(kb, rp) if (KB == kb && Rp == rp) { \
-        if (passes == 1) return launch_estep2<kb, rp, 1>(Z, N, D, ldz, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, st); \
-        return launch_estep2<kb, rp, 3>(Z, N, D, ldz, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, st); }
+        if (passes == 1) return launch_estep2<kb, rp, 1>(Z, N, D, ldz, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, lower, ldl, st); \
+        return launch_estep2<kb, rp, 3>(Z, N, D, ldz, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, lower, ldl, st); }
     T2_CASE(1, 8) T2_CASE(1, 16) T2_CASE(1, 32) T2_CASE(1, 64) T2_CASE(1, 128)
     T2_CASE(2, 8) T2_CASE(2, 16) T2_CASE(2, 32) T2_CASE(2, 64) T2_CASE(2, 128)
 #undef T2_CASE

@@ -19,20 +19,16 @@
 // more than it saves: a device-side flag then makes the dense 3-pass tensor-core kernel run instead and the
 // refinement kernels return immediately -- no host round trip either way.
 #include <algorithm>
-#include "common.cuh"
+#include "tc_common.cuh"
 #include "internal.h"
 
 namespace mimo {
 
+using tc::screen_bound;
+
 constexpr float SCREEN_T0 = 40.f;
 constexpr int RF_THREADS = 256;
 constexpr int RF_SPLIT = 8;                  // blocks per component
-
-// flags (in the operand workspace): [0] max |z| bits, [2] max_k ||W_k||_F bits, [3] max_n ||z_n||_2 bits
-__device__ __forceinline__ float screen_bound(const unsigned int* __restrict__ flags) {
-    const float wn = __uint_as_float(__ldg(flags + 2)), zn = __uint_as_float(__ldg(flags + 3));
-    return 1.05f * 0.0009765625f * wn * zn + 1e-3f;
-}
 
 // max_n ||z_n||_2: one warp per row (grid-stride)
 __global__ void screen_rownorm_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, unsigned int* __restrict__ flags) {
@@ -62,37 +58,30 @@ __global__ void screen_wnorm_kernel(const float* __restrict__ W, int K, int Rp, 
     if (threadIdx.x == 0) atomicMax(flags + 2, __float_as_uint(sqrtf(s) * 1.0000005f));
 }
 
-// thr[n] = L_n - T0
-__global__ void __launch_bounds__(256)
-screen_thr_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, const float* __restrict__ cst,
-                  const unsigned int* __restrict__ flags, float* __restrict__ thr) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float B = screen_bound(flags);
-    float L = -INFINITY;
-    for (int k = 0; k < K; ++k) {
-        const float c = __ldg(cst + k);
-        const float s = sqrtf(fmaxf(0.f, 2.f * (c - a[(int64_t)k * ldo + i]))) + B;
-        L = fmaxf(L, c - 0.5f * s * s);
-    }
-    thr[i] = L - SCREEN_T0;
-}
-
 // counters: [0] candidates found, [1] dense flag (set by screen_scan_kernel)
 __global__ void __launch_bounds__(256)
 screen_emit_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, const float* __restrict__ cst,
-                   const unsigned int* __restrict__ flags, const float* __restrict__ thr,
+                   const unsigned int* __restrict__ flags, const float* __restrict__ lower, int64_t ldl,
                    int2* __restrict__ list, unsigned int cap, unsigned int* __restrict__ counters, int* __restrict__ hist) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     const float B = screen_bound(flags);
-    const float t = valid ? thr[i] : INFINITY;
+    // L_n (lower bound of the point's best log-joint) was formed by the single-pass E-step epilogue, one value per
+    // half of the accumulator columns
+    const float t = valid ? fmaxf(lower[i], lower[ldl + i]) - SCREEN_T0 : INFINITY;
     const int lane = threadIdx.x & 31;
-    for (int k = 0; k < K; ++k) {
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      float av[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) av[u] = (valid && k0 + u < K) ? a[(int64_t)(k0 + u) * ldo + i] : 0.f;   // 4 loads in flight
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u;
+        if (k >= K) break;
         bool cand = false;
         if (valid) {
             const float c = __ldg(cst + k);
-            const float s = fmaxf(0.f, sqrtf(fmaxf(0.f, 2.f * (c - a[(int64_t)k * ldo + i]))) - B);
+            const float s = fmaxf(0.f, sqrtf(fmaxf(0.f, 2.f * (c - av[u]))) - B);
             cand = (c - 0.5f * s * s) >= t;
         }
         const unsigned int m = __ballot_sync(0xffffffffu, cand);
@@ -106,6 +95,7 @@ screen_emit_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, c
                 if (slot < cap) list[slot] = make_int2(k, (int)i);
             }
         }
+      }
     }
 }
 
@@ -211,15 +201,14 @@ static ScreenLayout screen_layout(int64_t chunk_points, int K) {
     L.off_hist = o;     o += a256((size_t)(K + 1) * 4);
     L.off_offsets = o;  o += a256((size_t)(K + 1) * 4);
     L.off_cursor = o;   o += a256((size_t)(K + 1) * 4);
-    L.off_thr = o;      o += a256((size_t)chunk_points * 4);
+    L.off_thr = o;      o += 2 * a256((size_t)chunk_points * 4);      // lower bounds, one row per accumulator half
     L.off_list = o;     o += a256((size_t)L.cap * 8);
     L.off_perm = o;     o += a256((size_t)L.cap * 4);
     L.bytes = o;
     return L;
 }
-size_t tc_screen_workspace(int64_t chunk_points, int K) { return screen_layout(chunk_points, K).bytes + 256; }
-
 static char* align256(void* p) { return (char*)(((uintptr_t)p + 255) / 256 * 256); }
+size_t tc_screen_workspace(int64_t chunk_points, int K) { return screen_layout(chunk_points, K).bytes + 256; }
 
 // once per sweep, after tc_data_scale (which zeroes the flags): the two norms of the error bound
 int tc_screen_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp,
@@ -235,6 +224,12 @@ int tc_screen_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float
 }
 
 // after the single-pass E-step of a chunk: find the candidates; sets the device flag the dense pass is gated on
+// the two rows (leading dimension *ldl) the single-pass E-step writes its per-point lower bounds into
+float* tc_screen_lower(void* ws, int64_t plan_points, int K, int64_t* ldl) {
+    *ldl = (int64_t)(a256((size_t)plan_points * 4) / 4);
+    return (float*)(align256(ws) + screen_layout(plan_points, K).off_thr);
+}
+
 const unsigned int* tc_screen_gate(void* ws, int64_t plan_points, int K) {
     return (const unsigned int*)(align256(ws) + screen_layout(plan_points, K).off_counters) + 1;
 }
@@ -259,8 +254,8 @@ int tc_screen_select(const float* a, int K, int64_t n, int64_t ldo, const float*
     int* hist = (int*)(base + L.off_hist);
     MIMO_CUDA(cudaMemsetAsync(base, 0, L.off_offsets, st));                 // counters + hist
     const int grid = cdiv(n, 256);
-    screen_thr_kernel<<<grid, 256, 0, st>>>(a, K, n, ldo, cst, flags, (float*)(base + L.off_thr));
     screen_emit_kernel<<<grid, 256, 0, st>>>(a, K, n, ldo, cst, flags, (const float*)(base + L.off_thr),
+                                             (int64_t)(a256((size_t)plan_points * 4) / 4),
                                              (int2*)(base + L.off_list), L.cap, counters, hist);
     const double maxc = std::min<double>((double)L.cap, 0.04 * (double)n * K);
     screen_scan_kernel<<<1, 32, 0, st>>>(hist, K, (int*)(base + L.off_offsets), (int*)(base + L.off_cursor), counters,
