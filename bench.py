@@ -331,6 +331,7 @@ def main():
     ap.add_argument('--n-override', type=int, default=0, help='debug only: smaller N (marks the line invalid)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--tc-mode', type=int, default=-1, help='A/B only: 3 = dense 3-pass E-step (no screening), 0 = CUDA cores')
     args = ap.parse_args()
     name = args.workload
     w = dict(WORKLOADS[name])
@@ -362,6 +363,9 @@ def main():
     from mimo_b200.sharded import Communicator, init_from_env, shard_bounds
     from mimo_b200.distributions.bayesian import MEANFIELD, GIBBS
     init_from_env()
+    if args.tc_mode >= 0:
+        E.set_tensor_cores(args.tc_mode)
+        config['tc_mode'] = args.tc_mode
     if world == 1:
         torch.cuda.set_device(0)
     dev = torch.device('cuda', torch.cuda.current_device())

@@ -21,7 +21,7 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
                void* workspace, size_t workspace_bytes, bool check, cudaStream_t st);
 
 // tensor-core (tcgen05) path, FP32 quad family, D <= 128  (tc_estep.cu, tc_stats.cu)
-int tc_mode();                       // 0 CUDA cores only; 1 tensor cores: CTA pairs + screened E-step (default); 2 single-CTA dense; 3 CTA pairs dense
+int tc_mode();                       // 0 CUDA cores only; 1 tensor cores: CTA pairs + screened E-step + pair-list statistics (default); 2 single-CTA dense; 3 CTA pairs dense; 4 as 1 with dense statistics
 int tc_set_mode(int mode);
 bool tc_estep_supported(int dtype, int D, int Rp);
 size_t tc_operand_workspace(int K, int Rp, int D);
@@ -57,7 +57,8 @@ bool tc_stats_supported(int dtype, int D, int F);
 size_t tc_stats_workspace(int64_t chunk_points, int K);
 int tc_stats_begin(int64_t chunk_points, int K, void* ws, cudaStream_t st);
 int tc_stats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, int K, int F,
-                   const unsigned int* maxbits, double* stat, int64_t plan_points, void* ws, cudaStream_t st);
+                   const unsigned int* maxbits, double* stat, int64_t plan_points, void* ws, cudaStream_t st,
+                   const unsigned int* gate = nullptr, unsigned int gate_value = 0u);
 int tc_stats_end(int64_t plan_points, int K, int D, int F, const unsigned int* maxbits, double* stat, void* ws, cudaStream_t st);
 void tc_set_flush_tiles(int tiles);
 // feature-form statistics (tc_fstats.cu): folded lower triangle, 64 < D <= 128
@@ -65,12 +66,21 @@ bool tc_fstats_supported(int dtype, int D, int F);
 size_t tc_fstats_workspace(int64_t chunk_points, int K);
 int tc_fstats_begin(int64_t chunk_points, int K, void* ws, cudaStream_t st);
 int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, int K,
-                    const unsigned int* maxbits, int64_t plan_points, void* ws, cudaStream_t st);
+                    const unsigned int* maxbits, int64_t plan_points, void* ws, cudaStream_t st,
+                    const unsigned int* gate = nullptr, unsigned int gate_value = 0u);
 int tc_fstats_end(int64_t plan_points, int K, int D, int F, const unsigned int* maxbits, double* stat, void* ws, cudaStream_t st);
 void tc_fstats_set_flush_tiles(int tiles);
 size_t stats_soft_tc_workspace(int64_t N, int K);
 int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K, int F,
                   double* stat, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// statistics over (component, point) lists grouped by component (pair_stats.cu): hard labels / screened candidates
+constexpr int PS_SLAB = 1024;        // listed points of one component per work item
+bool pair_stats_supported(int dtype, int D, int F);
+int pair_stats(const float* Z, int D, int64_t ldz, const int32_t* perm, const int32_t* offsets, const int32_t* slabs, int K,
+               const float* R, int64_t ldr, const unsigned int* gate, unsigned int gate_value,
+               double* stat, int F, cudaStream_t st);
+void tc_screen_lists(void* ws, int64_t plan_points, int K, const int32_t** perm, const int32_t** offsets, const int32_t** slabs);
 
 bool sweep_uses_tc(int dtype, int family, int D, int Rp);
 int64_t sweep_chunk_points(int dtype, int family, int64_t N, int D, int K, int Rp);

@@ -14,6 +14,7 @@
 // Reference call sites replaced: distributions/gaussian.py:491-505, 819-832;
 // lingauss.py:306-325; categorical.py:35-46; utils/data.py:160-169.
 #include "common.cuh"
+#include "internal.h"
 
 namespace mimo {
 
@@ -275,7 +276,9 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
     MIMO_CUDA(cudaMemsetAsync(ws, 0, 4 * seg + 256, st));
     int grid = cdiv(N, 256);
     label_hist_kernel<<<grid, 256, 0, st>>>(labels, N, K, counts, bad);
-    label_scan_kernel<<<1, 32, 0, st>>>(counts, K, offsets, cursor, slabs, SH_SEG);
+    // FP32 data, packed-triangle statistics: the register-tiled pair-list kernel (pair_stats.cu) takes the sorted lists
+    const bool pair = pair_stats_supported(dtype, D, F);
+    label_scan_kernel<<<1, 32, 0, st>>>(counts, K, offsets, cursor, slabs, pair ? PS_SLAB : SH_SEG);
     label_scatter_kernel<<<grid, 256, 0, st>>>(labels, N, K, cursor, perm);
     MIMO_LAUNCH_CHECK();
     if (check) {
@@ -284,6 +287,7 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
         MIMO_CUDA(cudaStreamSynchronize(st));
         if (hbad) { set_error("labels outside [0, K)"); return MIMO_EINVAL; }
     }
+    if (pair) return pair_stats((const float*)Z, D, ldz, perm, offsets, slabs, K, nullptr, 0, nullptr, 0u, stat, F, st);
     size_t es = dtype == MIMO_F32 ? 4 : 8;
     size_t smem = (size_t)SH_PT * (D + 2) * es;
     // every component contributes at most ceil(count/SEG) <= count/SEG + 1 slabs

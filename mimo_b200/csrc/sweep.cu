@@ -14,7 +14,7 @@ static size_t a256(size_t x) { return (x + 255) / 256 * 256; }
 
 static int g_tc_mode = 1;
 int tc_mode() { return g_tc_mode; }
-int tc_set_mode(int mode) { int old = g_tc_mode; g_tc_mode = (mode < 0 || mode > 3) ? 1 : mode; return old; }
+int tc_set_mode(int mode) { int old = g_tc_mode; g_tc_mode = (mode < 0 || mode > 4) ? 1 : mode; return old; }
 
 // the tensor-core path takes FP32 quad-family sweeps whose contraction is wide enough to pay for
 // the 64-wide K blocks of the operand layout
@@ -23,7 +23,7 @@ bool sweep_uses_tc(int dtype, int family, int D, int Rp) {
 }
 // screened E-step: worth it when a point's candidates (>= 1) can stay below 4 % of the K components
 static bool sweep_uses_screen(int dtype, int family, int D, int K, int Rp) {
-    return g_tc_mode == 1 && K >= 32 && sweep_uses_tc(dtype, family, D, Rp) && tc_screen_supported(D, Rp);
+    return (g_tc_mode == 1 || g_tc_mode == 4) && K >= 32 && sweep_uses_tc(dtype, family, D, Rp) && tc_screen_supported(D, Rp);
 }
 
 // points per chunk.
@@ -94,6 +94,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     // the packed full-triangle statistics are what the tensor-core statistics kernel produces
     const bool tc_stats = use_tc && stat && !hard && tc_stats_supported(dtype, D, F);
     const bool tc_fstats = tc_stats && tc_fstats_supported(dtype, D, F);     // feature form (folded triangle) for D > 64
+    const bool pair_stats_list = tc_stats && use_screen && g_tc_mode == 1 && pair_stats_supported(dtype, D, F);
     if (use_tc) {
         tc_ops_ws = ws; ws += a256(tc_operand_workspace(K, Rp, D));
         if (sweep_uses_screen(dtype, family, D, K, Rp)) { screen_ws = ws; ws += a256(tc_screen_workspace(C, K)); }
@@ -147,8 +148,17 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             MIMO_CUDA(cudaMemcpy2DAsync((char*)ll_out + (size_t)n0 * es, (size_t)ldo * es, scratch, (size_t)C * es,
                                         (size_t)nc * es, K, cudaMemcpyDeviceToDevice, st));
         if (tc_stats) {
-            rc = tc_fstats ? tc_fstats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, tc_maxbits(tc_ops_ws), C, tc_stat_ws, st)
-                           : tc_stats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, F, tc_maxbits(tc_ops_ws), stat, C, tc_stat_ws, st);
+            // behind the screened E-step the candidate lists carry the whole statistic (every other pair has r < e^-40):
+            // the pair-list kernel runs when the chunk was refined, the dense tensor-core kernels when it fell back
+            const unsigned int* sgate = pair_stats_list ? tc_screen_gate(screen_ws, C, K) : nullptr;
+            if (sgate) {
+                const int32_t *perm, *offsets, *slabs;
+                tc_screen_lists(screen_ws, C, K, &perm, &offsets, &slabs);
+                rc = pair_stats((const float*)Zc, D, ldz, perm, offsets, slabs, K, (const float*)scratch, C, sgate, 0u, stat, F, st);
+                if (rc) return rc;
+            }
+            rc = tc_fstats ? tc_fstats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, tc_maxbits(tc_ops_ws), C, tc_stat_ws, st, sgate, 1u)
+                           : tc_stats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, F, tc_maxbits(tc_ops_ws), stat, C, tc_stat_ws, st, sgate, 1u);
             if (rc) return rc;
         } else if (stat && !hard) {
             rc = stats_soft(dtype, Zc, nc, D, ldz, scratch, C, K, fi, fj, F, stat, st);
@@ -180,7 +190,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             // kernel launches of this chunk: E-step (+ offsets blocks for the CTA-pair kernel), softmax,
             // statistics (feature form: data image + responsibility image + GEMM)
             phase_ms[3] += 2.0 + (use_screen ? 5.0 : 0.0)
-                         + ((hard || !stat) ? 0.0 : (tc_fstats ? 3.0 : 1.0));
+                         + ((hard || !stat) ? 0.0 : (tc_fstats ? 3.0 : 1.0)) + (pair_stats_list ? 1.0 : 0.0);
         }
         if (h0) {
             float ms = 0.f;

@@ -28,6 +28,7 @@ using namespace tc;
 
 constexpr int T2_THREADS = 320;
 constexpr int T2_STAGES = 4;                 // B ring: one stage = this CTA's 128 rows x 64 K, hi + lo = 32 KB
+constexpr int T2_STAGES1 = 8;                // single-pass kernel: hi tiles only (16 KB), twice as many stages in the same space
 constexpr uint32_t T2_TILE = 16384;          // 128 rows x 64 FP16
 constexpr uint32_t T2_STAGE = 2 * T2_TILE;
 constexpr int T2_OFFBLK = 320;               // floats per 256-row chunk: 256 row offsets | 32 cst | 32 1/scale^2
@@ -35,7 +36,7 @@ constexpr uint32_t T2_OFFBYTES = T2_OFFBLK * 4;
 constexpr int T2_OFFRING = 8;                // offsets blocks in flight: deep enough that the producer never waits for the epilogue
 
 struct T2Bars {
-    uint64_t full[T2_STAGES], empty[T2_STAGES], peer_full[T2_STAGES];
+    uint64_t full[T2_STAGES1], empty[T2_STAGES1], peer_full[T2_STAGES1];
     uint64_t tmem_full[2], tmem_empty[2], peer_tmem_empty[2];
     uint64_t a_full, peer_a_full;
     uint64_t off_full[T2_OFFRING], off_empty[T2_OFFRING];
@@ -99,6 +100,8 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                  float* __restrict__ lower, int64_t ldl) {
     if (gate != nullptr && __ldg(gate) != gate_value) return;
     constexpr uint32_t STAGE_TX = PASSES == 3 ? T2_STAGE : T2_TILE;   // bytes copied per stage (hi | lo, or hi only)
+    constexpr int NST = PASSES == 3 ? T2_STAGES : T2_STAGES1;         // ring depth; a ring slot is STAGE_TX bytes
+    static_assert(NST * STAGE_TX == T2_STAGES * T2_STAGE, "ring size");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // A: [hi|lo][kb KB] tiles of 16 KB;  B: [stage][hi|lo] tiles of 16 KB;  offsets ring: T2_OFFRING x T2_OFFBYTES
     unsigned char* sA = smem_raw;
@@ -112,7 +115,7 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
     const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
     if (tid == 0) {
-        for (int s = 0; s < T2_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); mbar_init(&bars->peer_full[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); mbar_init(&bars->peer_full[s], 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 256); mbar_init(&bars->peer_tmem_empty[b], 1);
         }
@@ -235,8 +238,8 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                         mbar_wait(&bars->full[stage], phase);
                         mbar_wait_cluster(&bars->peer_full[stage], phase);
                         tc_fence_after();
-                        const uint64_t bh = make_desc_sw128(b0 + stage * T2_STAGE);
-                        const uint64_t bl = make_desc_sw128(b0 + stage * T2_STAGE + T2_TILE);
+                        const uint64_t bh = make_desc_sw128(b0 + stage * STAGE_TX);
+                        const uint64_t bl = make_desc_sw128(b0 + stage * STAGE_TX + T2_TILE);
                         const uint64_t ah = make_desc_sw128(a0 + kb * T2_TILE);
                         const uint64_t al = make_desc_sw128(a0 + (KB + kb) * T2_TILE);
 #pragma unroll
@@ -251,7 +254,7 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                             }
                         }
                         umma2_commit(&bars->empty[stage]);               // both CTAs' stage free once these MMAs have read it
-                        if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
                     umma2_commit(&bars->tmem_full[buf]);
                 }
@@ -272,7 +275,7 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&bars->full[stage], phase);
                         mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_full[stage]), 0));
-                        if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -291,8 +294,8 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&bars->empty[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&bars->full[stage], STAGE_TX);
-                        bulk_g2s(sB + (size_t)stage * T2_STAGE, src + ((size_t)(2 * c + rank) * KB + kb) * T2_STAGE, STAGE_TX, &bars->full[stage]);
-                        if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                        bulk_g2s(sB + (size_t)stage * STAGE_TX, src + ((size_t)(2 * c + rank) * KB + kb) * T2_STAGE, STAGE_TX, &bars->full[stage]);
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
                 }
             }

@@ -113,7 +113,9 @@ __device__ __forceinline__ void tf_prod8(const uint4& ah, const uint4& al, const
 // data: one CTA per 64-point block; thread = (column t, 32-point half).  zimg block = [hi|lo][128 columns][64 points].
 __global__ void __launch_bounds__(256)
 tc_fstats_zimg_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
-                      const unsigned int* __restrict__ maxbits, unsigned char* __restrict__ zimg) {
+                      const unsigned int* __restrict__ maxbits, unsigned char* __restrict__ zimg,
+                      const unsigned int* __restrict__ gate, unsigned int gate_value) {
+    if (gate != nullptr && __ldg(gate) != gate_value) return;
     const float sz = tf_scale(__uint_as_float(__ldg(maxbits)));
     const int t = threadIdx.x & 127, ph = threadIdx.x >> 7;
     const int64_t nb = (int64_t)blockIdx.x * TF_KB + ph * 32;
@@ -144,7 +146,8 @@ tc_fstats_zimg_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz
 // rimg block (cb, kblock) = [hi|lo][128 components][64 points] at ((cb * nkb_cap + kblock) * TF_PAIR).
 __global__ void __launch_bounds__(256)
 tc_fstats_rimg_kernel(const float* __restrict__ R, int64_t N, int64_t ldr, int K, int rvec4, int64_t nkb_cap,
-                      unsigned char* __restrict__ rimg) {
+                      unsigned char* __restrict__ rimg, const unsigned int* __restrict__ gate, unsigned int gate_value) {
+    if (gate != nullptr && __ldg(gate) != gate_value) return;
     const int ca = threadIdx.x >> 1, hh = threadIdx.x & 1;
     const int cb = blockIdx.y;
     const int64_t nb = (int64_t)blockIdx.x * TF_KB + hh * 32;
@@ -179,7 +182,9 @@ tc_fstats_rimg_kernel(const float* __restrict__ R, int64_t N, int64_t ldr, int K
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1)
 tc_fstats_kernel(const unsigned char* __restrict__ zimg, const unsigned char* __restrict__ rimg, int64_t nkb_cap,
                  int64_t N, double* __restrict__ partial, unsigned int* __restrict__ pace,
-                 int cbps, int fbs, int slabs, int64_t slab_points, int flush_kb, int pace_epochs) {
+                 int cbps, int fbs, int slabs, int64_t slab_points, int flush_kb, int pace_epochs,
+                 const unsigned int* __restrict__ gate, unsigned int gate_value) {
+    if (gate != nullptr && __ldg(gate) != gate_value) return;     // device-side choice: the pair-list statistics ran instead
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
     unsigned char* sA = smem + TF_OFF_A;
@@ -492,7 +497,8 @@ void tc_fstats_set_flush_tiles(int t) { g_flush_tiles_f = t < 1 ? 1 : t; }
 
 // one chunk of N <= plan_points points: operand images, then the GEMM; accumulates into the partial buffer
 int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, int K,
-                    const unsigned int* maxbits, int64_t plan_points, void* ws, cudaStream_t st) {
+                    const unsigned int* maxbits, int64_t plan_points, void* ws, cudaStream_t st,
+                    const unsigned int* gate, unsigned int gate_value) {
     if (N == 0) return MIMO_OK;
     TfLayout L = tf_layout(plan_points, K);
     char* base = align1k(ws);
@@ -502,9 +508,9 @@ int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* 
     const int64_t blocks = (N + TF_KB - 1) / TF_KB;
     MIMO_CHECK_ARG(blocks <= L.nkb_cap, "chunk larger than planned");
     const int rvec4 = (ldr % 4 == 0) && (((uintptr_t)R & 15) == 0);
-    tc_fstats_zimg_kernel<<<(unsigned)blocks, 256, 0, st>>>(Z, N, D, ldz, maxbits, zimg);
+    tc_fstats_zimg_kernel<<<(unsigned)blocks, 256, 0, st>>>(Z, N, D, ldz, maxbits, zimg, gate, gate_value);
     MIMO_LAUNCH_CHECK();
-    tc_fstats_rimg_kernel<<<dim3((unsigned)blocks, (unsigned)L.cbs), 256, 0, st>>>(R, N, ldr, K, rvec4, L.nkb_cap, rimg);
+    tc_fstats_rimg_kernel<<<dim3((unsigned)blocks, (unsigned)L.cbs), 256, 0, st>>>(R, N, ldr, K, rvec4, L.nkb_cap, rimg, gate, gate_value);
     MIMO_LAUNCH_CHECK();
     const int fbs = (TF_ROWS + TF_FBROWS - 1) / TF_FBROWS;
     const int cbps = L.cbs / 2, max_clusters = sm_count() / 2;
@@ -532,7 +538,7 @@ int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* 
     unsigned int* pace = (unsigned int*)base;
     MIMO_CUDA(cudaMemsetAsync(pace, 0, 4, st));
     tc_fstats_kernel<<<grid, TF_THREADS, TF_SMEM, st>>>(zimg, rimg, L.nkb_cap, N, partial, pace, cbps, fbs, slabs, slab_points,
-                                                        flush_kb, pace_epochs);
+                                                        flush_kb, pace_epochs, gate, gate_value);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }

@@ -101,11 +101,16 @@ screen_emit_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, c
 
 // single block: exclusive scan of hist -> offsets[K+1], cursor := offsets; dense flag when too many candidates
 __global__ void screen_scan_kernel(const int* __restrict__ hist, int K, int* __restrict__ offsets, int* __restrict__ cursor,
-                                   unsigned int* __restrict__ counters, unsigned int max_cands) {
+                                   int* __restrict__ slabs, unsigned int* __restrict__ counters, unsigned int max_cands) {
     if (threadIdx.x == 0) {
-        int run = 0;
-        for (int k = 0; k < K; ++k) { offsets[k] = run; cursor[k] = run; run += hist[k]; }
+        int run = 0, items = 0;                           // slabs: work items (PS_SLAB listed points) of pair_stats.cu
+        for (int k = 0; k < K; ++k) {
+            offsets[k] = run; cursor[k] = run; slabs[k] = items;
+            run += hist[k];
+            items += (hist[k] + PS_SLAB - 1) / PS_SLAB;
+        }
         offsets[K] = run;
+        slabs[K] = items;
         counters[1] = (counters[0] > max_cands) ? 1u : 0u;
     }
 }
@@ -191,7 +196,7 @@ static size_t a256(size_t x) { return (x + 255) / 256 * 256; }
 
 bool tc_screen_supported(int D, int Rp) { return D >= 24 && D <= 128 && (Rp == 32 || Rp == 64 || Rp == 128); }
 
-struct ScreenLayout { unsigned int cap; size_t off_counters, off_hist, off_offsets, off_cursor, off_thr, off_list, off_perm, bytes; };
+struct ScreenLayout { unsigned int cap; size_t off_counters, off_hist, off_offsets, off_cursor, off_slabs, off_thr, off_list, off_perm, bytes; };
 static ScreenLayout screen_layout(int64_t chunk_points, int K) {
     ScreenLayout L;
     const double pairs = (double)chunk_points * K;
@@ -201,6 +206,7 @@ static ScreenLayout screen_layout(int64_t chunk_points, int K) {
     L.off_hist = o;     o += a256((size_t)(K + 1) * 4);
     L.off_offsets = o;  o += a256((size_t)(K + 1) * 4);
     L.off_cursor = o;   o += a256((size_t)(K + 1) * 4);
+    L.off_slabs = o;    o += a256((size_t)(K + 1) * 4);
     L.off_thr = o;      o += 2 * a256((size_t)chunk_points * 4);      // lower bounds, one row per accumulator half
     L.off_list = o;     o += a256((size_t)L.cap * 8);
     L.off_perm = o;     o += a256((size_t)L.cap * 4);
@@ -234,6 +240,15 @@ const unsigned int* tc_screen_gate(void* ws, int64_t plan_points, int K) {
     return (const unsigned int*)(align256(ws) + screen_layout(plan_points, K).off_counters) + 1;
 }
 
+// the candidate lists of the chunk, grouped by component (valid after tc_screen_refine when the dense flag is clear)
+void tc_screen_lists(void* ws, int64_t plan_points, int K, const int32_t** perm, const int32_t** offsets, const int32_t** slabs) {
+    ScreenLayout L = screen_layout(plan_points, K);
+    char* base = align256(ws);
+    *perm = (const int32_t*)(base + L.off_perm);
+    *offsets = (const int32_t*)(base + L.off_offsets);
+    *slabs = (const int32_t*)(base + L.off_slabs);
+}
+
 static const unsigned int* g_last_counters = nullptr;
 
 // {candidates, dense flag} of the most recent screened chunk (synchronises the device; tests / bench reporting)
@@ -258,7 +273,7 @@ int tc_screen_select(const float* a, int K, int64_t n, int64_t ldo, const float*
                                              (int64_t)(a256((size_t)plan_points * 4) / 4),
                                              (int2*)(base + L.off_list), L.cap, counters, hist);
     const double maxc = std::min<double>((double)L.cap, 0.04 * (double)n * K);
-    screen_scan_kernel<<<1, 32, 0, st>>>(hist, K, (int*)(base + L.off_offsets), (int*)(base + L.off_cursor), counters,
+    screen_scan_kernel<<<1, 32, 0, st>>>(hist, K, (int*)(base + L.off_offsets), (int*)(base + L.off_cursor), (int*)(base + L.off_slabs), counters,
                                          (unsigned int)maxc);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;

@@ -42,7 +42,9 @@ tc_stats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
                 const float* __restrict__ R, int64_t ldr, int K,
                 const unsigned int* __restrict__ maxbits,
                 double* __restrict__ partial, double* __restrict__ stat, int F,
-                int groups, int slabs, int64_t slab_points, int flush_tiles) {
+                int groups, int slabs, int64_t slab_points, int flush_tiles,
+                const unsigned int* __restrict__ gate, unsigned int gate_value) {
+    if (gate != nullptr && __ldg(gate) != gate_value) return;     // device-side choice: the pair-list statistics ran instead
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // Bz: [hi|lo][point block 2] ; A: [buf 2][hi|lo][point block 2] ; tiles of 16 KB
     unsigned char* sBz = smem_raw;
@@ -298,14 +300,15 @@ void tc_set_flush_tiles(int t) { g_flush_tiles = t < 1 ? 1 : t; }
 
 // one chunk of points: accumulates into the partial buffer (plan of `plan_points`, the sweep's chunk size)
 int tc_stats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, int K, int F,
-                   const unsigned int* maxbits, double* stat, int64_t plan_points, void* ws, cudaStream_t st) {
+                   const unsigned int* maxbits, double* stat, int64_t plan_points, void* ws, cudaStream_t st,
+                   const unsigned int* gate, unsigned int gate_value) {
     if (N == 0) return MIMO_OK;
     TsPlan P = ts_plan(plan_points, K);
     size_t smem = 12 * (size_t)TS_TILE_BYTES + TS_G * 128 * sizeof(float) + sizeof(TsBarriers) + 1024;
     MIMO_CUDA(cudaFuncSetAttribute(tc_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(P.groups * P.slabs, sm_count());
     tc_stats_kernel<<<grid, TS_THREADS, smem, st>>>(Z, N, D, ldz, R, ldr, K, maxbits, (double*)align1k(ws), stat, F,
-                                                    P.groups, P.slabs, P.slab_points, g_flush_tiles);
+                                                    P.groups, P.slabs, P.slab_points, g_flush_tiles, gate, gate_value);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }

@@ -134,9 +134,33 @@ def test_stats_quad(precision, K, d, N):
     sh = E.stats_hard(Z, E.to_dev(labels, torch.int32), K, feats, precision).cpu().numpy()
     ref = orc.gauss_full_wstats(xr, orc.one_hot(labels, K))
     S = unpack_quad(sh, d)
-    close(S[:, :d, :d], ref[2], 1e-10, 'hard sum xx')
-    close(S[:, d, :d], ref[0], 1e-10, 'hard sum x')
+    # FP32 data with d >= 8 goes through the register-tiled pair-list kernel (FP32 slab sums, FP64 across slabs)
+    htol = 1e-10 if precision == 'fp64' else 1e-5
+    close(S[:, :d, :d], ref[2], htol, 'hard sum xx')
+    close(S[:, d, :d], ref[0], htol, 'hard sum x')
     assert np.array_equal(S[:, d, d], np.bincount(labels, minlength=K))
+
+
+@pytest.mark.parametrize('K,d,N', [(3, 8, 5000), (5, 17, 3000), (40, 24, 9000), (7, 33, 2500), (9, 64, 4000),
+                                   (6, 100, 3000), (4, 128, 6000), (300, 128, 2000)])
+def test_stats_hard_pair_list(K, d, N):
+    """pair-list statistics kernel (pair_stats.cu) behind mimo_stats_hard: uneven and empty components, lists longer
+    than one slab, every column-group count.  Reference: gaussian.py:491-505 on the one-hot matrix of data.py:160-169."""
+    E = eng()
+    rng = np.random.default_rng(K * 1000 + d)
+    x = rng.standard_normal((N, d)) * (1.0 + rng.random(d)) + rng.standard_normal(d)
+    p = rng.dirichlet(0.3 * np.ones(K))
+    p[K // 2] = 0.0                                        # an empty component
+    labels = rng.choice(K, size=N, p=p / p.sum()).astype(np.int32)
+    Z = E.to_dev(x, torch.float32)
+    feats = E.quad_features(d)
+    sh = E.stats_hard(Z, E.to_dev(labels, torch.int32), K, feats, 'fp32').cpu().numpy()
+    ref = orc.gauss_full_wstats(Z.double().cpu().numpy(), orc.one_hot(labels, K))
+    S = unpack_quad(sh, d)
+    close(S[:, :d, :d], ref[2], 1e-5, 'pair-list sum xx')
+    close(S[:, d, :d], ref[0], 1e-5, 'pair-list sum x')
+    assert np.array_equal(S[:, d, d], np.bincount(labels, minlength=K))
+    assert np.all(S[K // 2] == 0.0)
 
 
 def test_stats_hard_rejects_bad_labels():

@@ -235,3 +235,11 @@ def test_sweep_screened_estep(hard, K, d, N, sep):
     close(S[:, d, d], st[1], 1e-4, 'screened sweep sum r')
     if not hard:
         close(buf.stat, ref.stat.cpu().numpy(), 2e-5, 'screened vs dense statistics')
+        # mode 4: screened E-step with the dense tensor-core statistics instead of the pair-list kernel
+        old = E.set_tensor_cores(4)
+        try:
+            mid = E.SweepBuffers(N, K, feats.F, 'fp32', hard)
+            E.sweep(Z, ops, feats, mid)
+        finally:
+            E.set_tensor_cores(old)
+        close(buf.stat, mid.stat.cpu().numpy(), 2e-5, 'pair-list vs dense statistics behind the screened E-step')
