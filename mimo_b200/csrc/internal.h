@@ -28,21 +28,25 @@ size_t tc_operand_workspace(int K, int Rp, int D);
 int tc_data_scale(const float* Z, int64_t N, int D, int64_t ldz, void* ws, cudaStream_t st);
 const unsigned int* tc_maxbits(void* ws);
 int tc_prepare_operands(const float* W, const float* cst, int K, int Rp, int Dpp, int D, void* ws, cudaStream_t st);
-unsigned int* tc_flags(void* ws);    // [0] max |z| bits, [2] max_k ||W_k||_F bits, [3] max_n ||z_n||_2 bits
+unsigned int* tc_flags(void* ws);    // [0] max |z| bits, [2] max_k ||W'_k||_F (screening operands), [3] max_n ||z_n||_2, [4] max_k ||W_k||_F (all columns)
 int tc_estep_pass(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, float* out, int64_t ldo, void* ws,
-                  int passes, const unsigned int* gate, unsigned int gate_value, float* lower, int64_t ldl, cudaStream_t st);
-// screened E-step (tc_screen.cu): single-pass screening + exact refinement of the candidates / gated dense pass
+                  int passes, const unsigned int* gate, unsigned int gate_value, float* lower, int* guess, int64_t ldl, cudaStream_t st);
+// screened E-step (tc_screen.cu): projected single-pass screening + exact refinement of the candidates / gated dense pass
 bool tc_screen_supported(int D, int Rp);
 size_t tc_screen_workspace(int64_t chunk_points, int K);
-int tc_screen_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp,
-                      unsigned int* flags, cudaStream_t st);
+size_t tc_screen_operand_workspace(int K, int Rp, int Dpp, int D);
+int tc_screen_rows(int Rp);
+int tc_screen_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float* W, const float* cst, int K, int Rp, int Dpp,
+                      void* ops_ws, void* sops_ws, cudaStream_t st);
+int tc_screen_pass(const float* Z, int64_t n, int D, int64_t ldz, int K, int Rp, int Dpp, float* out, int64_t ldo,
+                   void* ops_ws, void* sops_ws, int64_t plan_points, void* ws, cudaStream_t st);
 const unsigned int* tc_screen_gate(void* ws, int64_t plan_points, int K);
-float* tc_screen_lower(void* ws, int64_t plan_points, int K, int64_t* ldl);
 int tc_screen_last(unsigned int* out_host2);
-int tc_screen_select(const float* a, int K, int64_t n, int64_t ldo, const float* cst, const unsigned int* flags,
-                     int64_t plan_points, void* ws, cudaStream_t st);
+int tc_screen_select(const float* Z, int D, int64_t ldz, const float* W, const float* cst, int K, int Rp, int Dpp,
+                     float* a, int64_t n, int64_t ldo, void* ops_ws, void* sops_ws, int64_t plan_points, void* ws, cudaStream_t st);
 int tc_screen_refine(const float* Z, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp, const float* cst,
                      float* a, int64_t ldo, int64_t plan_points, void* ws, cudaStream_t st);
+void tc_screen_lists(void* ws, int64_t plan_points, int K, int which, const int32_t** perm, const int32_t** offsets, const int32_t** slabs);
 int tc_estep(const float* Z, int64_t N, int D, int64_t ldz, const float* cst, int K, int Rp,
              float* out, int64_t ldo, void* ws, cudaStream_t st);
 // CTA-pair (cta_group::2) E-step, tc_estep2.cu
@@ -50,7 +54,7 @@ size_t tc2_offsets_bytes(int K, int Rp);
 int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cst, int K, int Rp, float* offs2, cudaStream_t st);
 int tc_estep2(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, int KB, const void* Bimg, const float* offs2,
               const unsigned int* maxbits, float* out, int64_t ldo, int passes, const unsigned int* gate, unsigned int gate_value,
-              float* lower, int64_t ldl, cudaStream_t st);
+              float* lower, int* guess, int64_t ldl, cudaStream_t st);
 int loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* W, const void* cst,
                    int K, int Rp, int Dpp, void* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st);
 bool tc_stats_supported(int dtype, int D, int F);
@@ -80,7 +84,6 @@ bool pair_stats_supported(int dtype, int D, int F);
 int pair_stats(const float* Z, int D, int64_t ldz, const int32_t* perm, const int32_t* offsets, const int32_t* slabs, int K,
                const float* R, int64_t ldr, const unsigned int* gate, unsigned int gate_value,
                double* stat, int F, cudaStream_t st);
-void tc_screen_lists(void* ws, int64_t plan_points, int K, const int32_t** perm, const int32_t** offsets, const int32_t** slabs);
 
 bool sweep_uses_tc(int dtype, int family, int D, int Rp);
 int64_t sweep_chunk_points(int dtype, int family, int64_t N, int D, int K, int Rp);
@@ -91,6 +94,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
           const void* uniforms, uint64_t seed, uint64_t point_offset,
           double* stat, double* lse_sum, int32_t* labels_out, void* lse_out, void* ll_out, int64_t ldo,
           void* workspace, size_t workspace_bytes, cudaStream_t st, double* phase_ms = nullptr);
+int64_t sweep_host_set_segment(int64_t points);
 int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, int D,
                const void* op_a_host, const void* op_b_host, const void* cst_host, int K, int Rp, int Dpp,
                const int32_t* fi_host, const int32_t* fj_host, int F,

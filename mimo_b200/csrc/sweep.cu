@@ -58,7 +58,7 @@ size_t sweep_workspace(int dtype, int family, int hard, int64_t N, int D, int K,
     if (hard) b += a256((size_t)N * 4) + a256(stats_hard_workspace(N, K));
     if (sweep_uses_tc(dtype, family, D, Rp)) {
         b += a256(tc_operand_workspace(K, Rp, D));
-        if (sweep_uses_screen(dtype, family, D, K, Rp)) b += a256(tc_screen_workspace(c, K));
+        if (sweep_uses_screen(dtype, family, D, K, Rp)) b += a256(tc_screen_workspace(c, K)) + a256(tc_screen_operand_workspace(K, Rp, D + 4, D));
         if (!hard) b += a256(std::max(tc_stats_workspace(c, K), tc_fstats_workspace(c, K)));
     }
     return b;
@@ -89,22 +89,26 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     void* tc_ops_ws = nullptr;
     void* tc_stat_ws = nullptr;
     void* screen_ws = nullptr;
+    void* screen_ops_ws = nullptr;
     // the (K, N) log-joint output must hold FP32-class values for every pair: no screening then
-    const bool use_screen = sweep_uses_screen(dtype, family, D, K, Rp) && !ll_out;
+    const bool use_screen = sweep_uses_screen(dtype, family, D, K, Rp) && !ll_out && Dpp <= D + 4;   // (workspace is sized for Dpp <= D + 4)
     // the packed full-triangle statistics are what the tensor-core statistics kernel produces
     const bool tc_stats = use_tc && stat && !hard && tc_stats_supported(dtype, D, F);
     const bool tc_fstats = tc_stats && tc_fstats_supported(dtype, D, F);     // feature form (folded triangle) for D > 64
     const bool pair_stats_list = tc_stats && use_screen && g_tc_mode == 1 && pair_stats_supported(dtype, D, F);
     if (use_tc) {
         tc_ops_ws = ws; ws += a256(tc_operand_workspace(K, Rp, D));
-        if (sweep_uses_screen(dtype, family, D, K, Rp)) { screen_ws = ws; ws += a256(tc_screen_workspace(C, K)); }
+        if (sweep_uses_screen(dtype, family, D, K, Rp)) {
+            screen_ws = ws; ws += a256(tc_screen_workspace(C, K));
+            screen_ops_ws = ws; ws += a256(tc_screen_operand_workspace(K, Rp, D + 4, D));
+        }
         if (!hard) tc_stat_ws = ws;
         int rc = tc_data_scale((const float*)Z, N, D, ldz, tc_ops_ws, st);
         if (rc) return rc;
         rc = tc_prepare_operands((const float*)op_a, (const float*)cst, K, Rp, Dpp, D, tc_ops_ws, st);
         if (rc) return rc;
         if (use_screen) {
-            rc = tc_screen_prepare((const float*)Z, N, D, ldz, (const float*)op_a, K, Rp, Dpp, tc_flags(tc_ops_ws), st);
+            rc = tc_screen_prepare((const float*)Z, N, D, ldz, (const float*)op_a, (const float*)cst, K, Rp, Dpp, tc_ops_ws, screen_ops_ws, st);
             if (rc) return rc;
         }
         if (tc_stats) { rc = tc_fstats ? tc_fstats_begin(C, K, tc_stat_ws, st) : tc_stats_begin(C, K, tc_stat_ws, st); if (rc) return rc; }
@@ -119,15 +123,15 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         const char* Zc = (const char*)Z + (size_t)n0 * ldz * es;
         int rc;
         if (use_screen) {
-            // single-pass screening over all pairs, then either the exact refinement of the candidates or (device-side
-            // flag, when > 4 % of the pairs are candidates) the dense 3-pass kernel
-            int64_t ldl = 0;
-            float* lower = tc_screen_lower(screen_ws, C, K, &ldl);
-            rc = tc_estep_pass((const float*)Zc, nc, D, ldz, K, Rp, (float*)scratch, C, tc_ops_ws, 1, nullptr, 0u, lower, ldl, st);
+            // screening pass over all pairs (projected operands, one FP16 pass), exact guesses, candidate lists; then
+            // either the exact refinement of the candidates or (device-side flag, when > 4 % of the pairs are
+            // candidates) the dense 3-pass kernel
+            rc = tc_screen_pass((const float*)Zc, nc, D, ldz, K, Rp, Dpp, (float*)scratch, C, tc_ops_ws, screen_ops_ws, C, screen_ws, st);
             if (rc) return rc;
-            rc = tc_screen_select((const float*)scratch, K, nc, C, (const float*)cst, tc_flags(tc_ops_ws), C, screen_ws, st);
+            rc = tc_screen_select((const float*)Zc, D, ldz, (const float*)op_a, (const float*)cst, K, Rp, Dpp, (float*)scratch, nc, C,
+                                  tc_ops_ws, screen_ops_ws, C, screen_ws, st);
             if (rc) return rc;
-            rc = tc_estep_pass((const float*)Zc, nc, D, ldz, K, Rp, (float*)scratch, C, tc_ops_ws, 3, tc_screen_gate(screen_ws, C, K), 1u, nullptr, 0, st);
+            rc = tc_estep_pass((const float*)Zc, nc, D, ldz, K, Rp, (float*)scratch, C, tc_ops_ws, 3, tc_screen_gate(screen_ws, C, K), 1u, nullptr, nullptr, 0, st);
             if (rc) return rc;
             rc = tc_screen_refine((const float*)Zc, D, ldz, (const float*)op_a, K, Rp, Dpp, (const float*)cst, (float*)scratch, C, C, screen_ws, st);
         }
@@ -152,10 +156,12 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             // the pair-list kernel runs when the chunk was refined, the dense tensor-core kernels when it fell back
             const unsigned int* sgate = pair_stats_list ? tc_screen_gate(screen_ws, C, K) : nullptr;
             if (sgate) {
-                const int32_t *perm, *offsets, *slabs;
-                tc_screen_lists(screen_ws, C, K, &perm, &offsets, &slabs);
-                rc = pair_stats((const float*)Zc, D, ldz, perm, offsets, slabs, K, (const float*)scratch, C, sgate, 0u, stat, F, st);
-                if (rc) return rc;
+                for (int which = 0; which < 2; ++which) {                  // the guesses, then the other candidates
+                    const int32_t *perm, *offsets, *slabs;
+                    tc_screen_lists(screen_ws, C, K, which, &perm, &offsets, &slabs);
+                    rc = pair_stats((const float*)Zc, D, ldz, perm, offsets, slabs, K, (const float*)scratch, C, sgate, 0u, stat, F, st);
+                    if (rc) return rc;
+                }
             }
             rc = tc_fstats ? tc_fstats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, tc_maxbits(tc_ops_ws), C, tc_stat_ws, st, sgate, 1u)
                            : tc_stats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, F, tc_maxbits(tc_ops_ws), stat, C, tc_stat_ws, st, sgate, 1u);
@@ -189,8 +195,8 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             }
             // kernel launches of this chunk: E-step (+ offsets blocks for the CTA-pair kernel), softmax,
             // statistics (feature form: data image + responsibility image + GEMM)
-            phase_ms[3] += 2.0 + (use_screen ? 5.0 : 0.0)
-                         + ((hard || !stat) ? 0.0 : (tc_fstats ? 3.0 : 1.0)) + (pair_stats_list ? 1.0 : 0.0);
+            phase_ms[3] += 2.0 + (use_screen ? 10.0 : 0.0)
+                         + ((hard || !stat) ? 0.0 : (tc_fstats ? 3.0 : 1.0)) + (pair_stats_list ? 2.0 : 0.0);
         }
         if (h0) {
             float ms = 0.f;
@@ -199,63 +205,93 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             phase_ms[3] += 4.0;
             cudaEventDestroy(h0); cudaEventDestroy(h1);
         }
-        if (use_tc) phase_ms[3] += 3.0 + (tc_stats ? 1.0 : 0.0) + (use_screen ? 2.0 : 0.0);   // data scale, operand image + offsets, norms, statistics fold
+        if (use_tc) phase_ms[3] += 3.0 + (tc_stats ? 1.0 : 0.0) + (use_screen ? 6.0 : 0.0);   // data scale, operand image + offsets, norms, statistics fold
         phase_ms[4] += (double)((N + C - 1) / C);                      // point chunks
         for (auto e : ev) cudaEventDestroy(e);
     }
     return MIMO_OK;
 }
 
+static int64_t g_host_segment = 0;
+int64_t sweep_host_set_segment(int64_t points) { int64_t old = g_host_segment; g_host_segment = points < 0 ? 0 : points; return old; }
+
 // Host-buffer variant: what bench.py's `e2e` leg and a caller without device memory use.
+// The data is uploaded in segments of whole point chunks on a copy stream while the sweep of the previous segment
+// runs on the compute stream (statistics, the lower-bound term and the labels are additive / per point, so a sweep
+// over segments is the same sweep): end to end the call costs max(upload, compute), not their sum.
 int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, int D,
                const void* op_a_host, const void* op_b_host, const void* cst_host, int K, int Rp, int Dpp,
                const int32_t* fi_host, const int32_t* fj_host, int F,
                const void* uniforms_host, uint64_t seed,
                double* stat_host, double* lse_sum_host, int32_t* labels_host) {
     MIMO_CHECK_ARG(Z_host && op_a_host && cst_host && fi_host && fj_host && stat_host, "null pointer");
+    MIMO_CHECK_ARG(N >= 0 && D >= 1 && K >= 1 && F >= 1, "shape");
     const size_t es = dtype == MIMO_F32 ? 4 : 8;
     const size_t zb = (size_t)N * D * es;
     const size_t ab = (family == 0 ? (size_t)K * Rp * Dpp : (size_t)K * D) * es;
-    const size_t wsb = sweep_workspace(dtype, family, hard, N, D, K, Rp);
+    const int64_t C = sweep_chunk_points(dtype, family, N, D, K, Rp);
+    const int64_t want = g_host_segment > 0 ? g_host_segment : (int64_t)(((size_t)1 << 30) / ((size_t)D * es));   // ~1 GB of data
+    const int64_t seg = (want + C - 1) / C * C;                                                               // whole chunks
+    const int n_seg = N > 0 ? (int)((N + seg - 1) / seg) : 0;
+    const size_t wsb = sweep_workspace(dtype, family, hard, std::min<int64_t>(N, seg), D, K, Rp);
     char *dZ = nullptr, *dA = nullptr, *dB = nullptr, *dC = nullptr, *dws = nullptr;
     int32_t *dfi = nullptr, *dfj = nullptr, *dlab = nullptr;
     double *dstat = nullptr, *dlse = nullptr, *duni = nullptr;
-    cudaStream_t st = 0;
+    cudaStream_t st = nullptr, sc = nullptr;
+    std::vector<cudaEvent_t> landed;
     int rc = MIMO_OK;
     auto body = [&]() -> int {
-        MIMO_CUDA(cudaMalloc(&dZ, zb));
+        MIMO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        MIMO_CUDA(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+        MIMO_CUDA(cudaMalloc(&dZ, std::max<size_t>(zb, 16)));
         MIMO_CUDA(cudaMalloc(&dA, ab));
         MIMO_CUDA(cudaMalloc(&dC, (size_t)K * es));
         MIMO_CUDA(cudaMalloc(&dfi, (size_t)F * 4));
         MIMO_CUDA(cudaMalloc(&dfj, (size_t)F * 4));
         MIMO_CUDA(cudaMalloc(&dstat, (size_t)K * F * 8));
         MIMO_CUDA(cudaMalloc(&dlse, 8));
-        MIMO_CUDA(cudaMalloc(&dws, wsb));
+        MIMO_CUDA(cudaMalloc(&dws, std::max<size_t>(wsb, 16)));
         if (family == 1) { MIMO_CUDA(cudaMalloc(&dB, ab)); MIMO_CUDA(cudaMemcpyAsync(dB, op_b_host, ab, cudaMemcpyHostToDevice, st)); }
-        if (hard) MIMO_CUDA(cudaMalloc(&dlab, (size_t)N * 4));
-        if (uniforms_host) {
-            MIMO_CUDA(cudaMalloc(&duni, (size_t)N * 8));
-            MIMO_CUDA(cudaMemcpyAsync(duni, uniforms_host, (size_t)N * 8, cudaMemcpyHostToDevice, st));
-        }
-        MIMO_CUDA(cudaMemcpyAsync(dZ, Z_host, zb, cudaMemcpyHostToDevice, st));
+        if (hard) MIMO_CUDA(cudaMalloc(&dlab, std::max<size_t>((size_t)N * 4, 16)));
+        if (uniforms_host) MIMO_CUDA(cudaMalloc(&duni, std::max<size_t>((size_t)N * 8, 16)));
         MIMO_CUDA(cudaMemcpyAsync(dA, op_a_host, ab, cudaMemcpyHostToDevice, st));
         MIMO_CUDA(cudaMemcpyAsync(dC, cst_host, (size_t)K * es, cudaMemcpyHostToDevice, st));
         MIMO_CUDA(cudaMemcpyAsync(dfi, fi_host, (size_t)F * 4, cudaMemcpyHostToDevice, st));
         MIMO_CUDA(cudaMemcpyAsync(dfj, fj_host, (size_t)F * 4, cudaMemcpyHostToDevice, st));
         MIMO_CUDA(cudaMemsetAsync(dstat, 0, (size_t)K * F * 8, st));
         MIMO_CUDA(cudaMemsetAsync(dlse, 0, 8, st));
-        int r = sweep(dtype, family, hard, dZ, N, D, D, dA, dB, dC, K, Rp, Dpp, dfi, dfj, F, duni, seed, 0,
-                      dstat, dlse, dlab, nullptr, nullptr, 0, dws, wsb, st, nullptr);
-        if (r) return r;
+        // uploads: one segment after the other on the copy stream, an event per segment
+        landed.resize(n_seg);
+        for (int s = 0; s < n_seg; ++s) {
+            const int64_t n0 = (int64_t)s * seg, ns = std::min<int64_t>(seg, N - n0);
+            MIMO_CUDA(cudaMemcpyAsync(dZ + (size_t)n0 * D * es, (const char*)Z_host + (size_t)n0 * D * es, (size_t)ns * D * es,
+                                      cudaMemcpyHostToDevice, sc));
+            if (uniforms_host)
+                MIMO_CUDA(cudaMemcpyAsync(duni + n0, (const double*)uniforms_host + n0, (size_t)ns * 8, cudaMemcpyHostToDevice, sc));
+            MIMO_CUDA(cudaEventCreateWithFlags(&landed[s], cudaEventDisableTiming));
+            MIMO_CUDA(cudaEventRecord(landed[s], sc));
+        }
+        for (int s = 0; s < n_seg; ++s) {
+            const int64_t n0 = (int64_t)s * seg, ns = std::min<int64_t>(seg, N - n0);
+            MIMO_CUDA(cudaStreamWaitEvent(st, landed[s], 0));
+            int r = sweep(dtype, family, hard, dZ + (size_t)n0 * D * es, ns, D, D, dA, dB, dC, K, Rp, Dpp, dfi, dfj, F,
+                          duni ? duni + n0 : nullptr, seed, (uint64_t)n0, dstat, dlse, dlab ? dlab + n0 : nullptr,
+                          nullptr, nullptr, 0, dws, wsb, st, nullptr);
+            if (r) return r;
+        }
         MIMO_CUDA(cudaMemcpyAsync(stat_host, dstat, (size_t)K * F * 8, cudaMemcpyDeviceToHost, st));
         if (lse_sum_host) MIMO_CUDA(cudaMemcpyAsync(lse_sum_host, dlse, 8, cudaMemcpyDeviceToHost, st));
-        if (hard && labels_host) MIMO_CUDA(cudaMemcpyAsync(labels_host, dlab, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+        if (hard && labels_host && N > 0) MIMO_CUDA(cudaMemcpyAsync(labels_host, dlab, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
         MIMO_CUDA(cudaStreamSynchronize(st));
         return MIMO_OK;
     };
     rc = body();
+    if (rc != MIMO_OK) cudaDeviceSynchronize();
+    for (auto e : landed) if (e) cudaEventDestroy(e);
     cudaFree(dZ); cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dws); cudaFree(dfi); cudaFree(dfj);
     cudaFree(dlab); cudaFree(dstat); cudaFree(dlse); cudaFree(duni);
+    if (st) cudaStreamDestroy(st);
+    if (sc) cudaStreamDestroy(sc);
     return rc;
 }
 

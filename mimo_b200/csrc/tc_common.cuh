@@ -178,7 +178,8 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
 // flags (head of the operand workspace): [0] max |z| bits, [2] max_k ||W_k||_F bits, [3] max_n ||z_n||_2 bits
 __device__ __forceinline__ float screen_bound(const unsigned int* __restrict__ flags) {
     const float wn = __uint_as_float(__ldg(flags + 2)), zn = __uint_as_float(__ldg(flags + 3));
-    return 1.05f * 0.0009765625f * wn * zn + 1e-3f;
+    const float wfull = __uint_as_float(__ldg(flags + 4));            // 0 unless the operands were projected (FP32 rounding of Q W)
+    return 1.05f * 0.0009765625f * wn * zn + 4e-6f * wfull * (zn + 1.f) + 1e-3f;
 }
 
 // ---- bulk copy global -> shared through the TMA engine (no tensor map: the source is already

@@ -358,12 +358,12 @@ unsigned int* tc_flags(void* ws) { return (unsigned int*)align1k(ws); }
 
 // CTA-pair kernel with an explicit number of passes and an optional device-side gate (tc_screen.cu)
 int tc_estep_pass(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, float* out, int64_t ldo, void* ws,
-                  int passes, const unsigned int* gate, unsigned int gate_value, float* lower, int64_t ldl, cudaStream_t st) {
+                  int passes, const unsigned int* gate, unsigned int gate_value, float* lower, int* guess, int64_t ldl, cudaStream_t st) {
     if (N == 0) return MIMO_OK;
     TcOperandLayout L = tc_layout(K, Rp, D);
     char* base = align1k(ws);
     return tc_estep2(Z, N, D, ldz, K, Rp, L.KB, (const void*)(base + L.off_img), (const float*)(base + L.off_offs2),
-                     (const unsigned int*)(base + L.off_maxbits), out, ldo, passes, gate, gate_value, lower, ldl, st);
+                     (const unsigned int*)(base + L.off_maxbits), out, ldo, passes, gate, gate_value, lower, guess, ldl, st);
 }
 
 template <int KB, int RP>
@@ -390,7 +390,7 @@ int tc_estep(const float* Z, int64_t N, int D, int64_t ldz, const float* cst, in
     char* base = align1k(ws);
     if (tc_mode() != 2)        // CTA-pair kernel (cta_group::2), dense 3-pass
         return tc_estep2(Z, N, D, ldz, K, Rp, L.KB, (const void*)(base + L.off_img), (const float*)(base + L.off_offs2),
-                         (const unsigned int*)(base + L.off_maxbits), out, ldo, 3, nullptr, 0u, nullptr, 0, st);
+                         (const unsigned int*)(base + L.off_maxbits), out, ldo, 3, nullptr, 0u, nullptr, nullptr, 0, st);
 #define TE_CASE(kb, rp) if (L.KB == kb && Rp == rp) return launch_estep<kb, rp>(Z, N, D, ldz, L, base, cst, K, out, ldo, st);
     TE_CASE(1, 8) TE_CASE(1, 16) TE_CASE(1, 32) TE_CASE(1, 64) TE_CASE(1, 128)
     TE_CASE(2, 8) TE_CASE(2, 16) TE_CASE(2, 32) TE_CASE(2, 64) TE_CASE(2, 128)

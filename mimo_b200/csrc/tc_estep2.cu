@@ -60,11 +60,11 @@ __global__ void tc2_offsets_kernel(const float* __restrict__ rowoff, const float
 }
 
 // 32 accumulator columns -> partial squared norms (4 independent chains), component boundaries every RP columns
-// SCREEN: also maintain L = max_k [ cst_k - (sqrt(q) + B)^2 / 2 ], the lower bound of the point's best log-joint
+// SCREEN: also track the point's best component so far (value, index) -- the guess of tc_screen.cu
 template <int RP, bool SCREEN>
 __device__ __forceinline__ void t2_consume(const float (&v)[32], const float* __restrict__ off_s, int col0, float (&q)[4],
                                            const float* __restrict__ scal_s, int jbase, int kbase, int K, bool pvalid,
-                                           float* __restrict__ outp, int64_t ldo, float B, float& L) {
+                                           float* __restrict__ outp, int64_t ldo, float& best, int& bestk) {
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
         const float4 o = *reinterpret_cast<const float4*>(off_s + col0 + j4 * 4);       // broadcast read
@@ -79,8 +79,9 @@ __device__ __forceinline__ void t2_consume(const float (&v)[32], const float* __
                 const int k = kbase + j;
                 const float qq = (q[0] + q[1]) + (q[2] + q[3]);
                 const float qt = scal_s[32 + j] * qq;              // || W_k [z ; 1] ||^2 in true units
-                if (pvalid && k < K) outp[(int64_t)k * ldo] = scal_s[j] - 0.5f * qt;
-                if (SCREEN && k < K) { const float sq = sqrtf(qt) + B; L = fmaxf(L, scal_s[j] - 0.5f * sq * sq); }
+                const float val = scal_s[j] - 0.5f * qt;
+                if (pvalid && k < K) outp[(int64_t)k * ldo] = val;
+                if (SCREEN && k < K && val > best) { best = val; bestk = k; }
                 q[0] = q[1] = q[2] = q[3] = 0.f;
             }
         }
@@ -97,7 +98,7 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                  const unsigned int* __restrict__ maxbits,
                  int K, int n_chunks2, float* __restrict__ out, int64_t ldo,
                  const unsigned int* __restrict__ gate, unsigned int gate_value,
-                 float* __restrict__ lower, int64_t ldl) {
+                 float* __restrict__ lower, int* __restrict__ guess, int64_t ldl) {
     if (gate != nullptr && __ldg(gate) != gate_value) return;
     constexpr uint32_t STAGE_TX = PASSES == 3 ? T2_STAGE : T2_TILE;   // bytes copied per stage (hi | lo, or hi only)
     constexpr int NST = PASSES == 3 ? T2_STAGES : T2_STAGES1;         // ring depth; a ring slot is STAGE_TX bytes
@@ -135,7 +136,6 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
         // ================= converter + epilogue warps =================
         const float sz = pow2_scale_for(__uint_as_float(__ldg(maxbits)));
         constexpr bool SCREEN = PASSES == 1;
-        const float Bnd = SCREEN ? screen_bound(maxbits) : 0.f;
         const int half = warp >> 2, qd = warp & 3;
         const int prow = qd * 32 + lane;                             // point row inside the tile = TMEM lane
         uint32_t gc = 0;
@@ -185,6 +185,7 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
             const bool pvalid = n < N;
             float* outp = out + n;
             float Lb = -INFINITY;
+            int Lk = 0;
             for (int c = 0; c < n_chunks2; ++c, ++gc) {
                 const uint32_t buf = gc & 1, par = (gc >> 1) & 1;
                 const uint32_t ob = gc % T2_OFFRING;
@@ -201,20 +202,20 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                 tmem_ld32(taddr, va);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 32, vb);
-                t2_consume<RP, SCREEN>(va, off_s, 0, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Bnd, Lb);
+                t2_consume<RP, SCREEN>(va, off_s, 0, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 64, va);
-                t2_consume<RP, SCREEN>(vb, off_s, 32, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Bnd, Lb);
+                t2_consume<RP, SCREEN>(vb, off_s, 32, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
                 tmem_ld_wait();
                 tmem_ld32(taddr + 96, vb);
-                t2_consume<RP, SCREEN>(va, off_s, 64, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Bnd, Lb);
+                t2_consume<RP, SCREEN>(va, off_s, 64, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&bars->tmem_empty[buf]);             // accumulator drained: the pair's MMA may reuse it
-                t2_consume<RP, SCREEN>(vb, off_s, 96, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Bnd, Lb);
+                t2_consume<RP, SCREEN>(vb, off_s, 96, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
                 mbar_arrive(&bars->off_empty[ob]);
             }
-            if (SCREEN && pvalid) lower[(int64_t)half * ldl + n] = Lb;
+            if (SCREEN && pvalid) { lower[(int64_t)half * ldl + n] = Lb; guess[(int64_t)half * ldl + n] = Lk; }
         }
     } else if (warp == 8) {
         if (lane == 0 && rank == 0) {
@@ -323,14 +324,14 @@ int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cs
 template <int KB, int RP, int PASSES>
 static int launch_estep2(const float* Z, int64_t N, int D, int64_t ldz, const __half* Bimg, const float* offs2,
                          const unsigned int* maxbits, int K, int n_chunks2, float* out, int64_t ldo,
-                         const unsigned int* gate, unsigned int gate_value, float* lower, int64_t ldl, cudaStream_t st) {
+                         const unsigned int* gate, unsigned int gate_value, float* lower, int* guess, int64_t ldl, cudaStream_t st) {
     const size_t smem = (size_t)2 * KB * T2_TILE + (size_t)T2_STAGES * T2_STAGE + T2_OFFRING * T2_OFFBYTES + sizeof(T2Bars);
     auto kern = tc_estep2_kernel<KB, RP, PASSES>;
     MIMO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t passes = (N + 255) / 256;
     const int clusters = (int)std::min<int64_t>(passes, sm_count() / 2);
     const int vec4 = (ldz % 4 == 0) && (((uintptr_t)Z & 15) == 0);
-    kern<<<2 * clusters, T2_THREADS, smem, st>>>(Z, N, D, ldz, vec4, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, lower, ldl);
+    kern<<<2 * clusters, T2_THREADS, smem, st>>>(Z, N, D, ldz, vec4, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, lower, guess, ldl);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
@@ -339,14 +340,14 @@ static int launch_estep2(const float* Z, int64_t N, int D, int64_t ldz, const __
 // passes = 3 (FP32-class) or 1 (screening pass); gate: see the kernel.
 int tc_estep2(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, int KB, const void* Bimg_, const float* offs2,
               const unsigned int* maxbits, float* out, int64_t ldo, int passes, const unsigned int* gate, unsigned int gate_value,
-              float* lower, int64_t ldl, cudaStream_t st) {
+              float* lower, int* guess, int64_t ldl, cudaStream_t st) {
     const __half* Bimg = (const __half*)Bimg_;
     if (N == 0) return MIMO_OK;
     const int n_chunks = (int)(((int64_t)K * Rp + 127) / 128);
     const int n_chunks2 = (n_chunks + 1) / 2;
 #define T2_CASE(kb, rp) if (KB == kb && Rp == rp) { \
-        if (passes == 1) return launch_estep2<kb, rp, 1>(Z, N, D, ldz, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, lower, ldl, st); \
-        return launch_estep2<kb, rp, 3>(Z, N, D, ldz, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, lower, ldl, st); }
+        if (passes == 1) return launch_estep2<kb, rp, 1>(Z, N, D, ldz, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, lower, guess, ldl, st); \
+        return launch_estep2<kb, rp, 3>(Z, N, D, ldz, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, lower, guess, ldl, st); }
     T2_CASE(1, 8) T2_CASE(1, 16) T2_CASE(1, 32) T2_CASE(1, 64) T2_CASE(1, 128)
     T2_CASE(2, 8) T2_CASE(2, 16) T2_CASE(2, 32) T2_CASE(2, 64) T2_CASE(2, 128)
 #undef T2_CASE

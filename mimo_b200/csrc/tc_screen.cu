@@ -1,23 +1,29 @@
-// Screened E-step: one FP16 tensor-core pass over ALL (point, component) pairs, an exact pass only over the
-// pairs that can matter.
+// Screened E-step: one cheap FP16 tensor-core pass over ALL (point, component) pairs, an exact pass only over
+// the pairs that can matter.
 //
 //   a[k][n] = cst[k] - 0.5 * q[k][n],   q = || W_k [z_n ; 1] ||^2
 //   (distributions/gaussian.py:510-523, bayesian.py:287-301 followed by the logsumexp of mixtures/gmm.py:72-75, 256-259)
 //
 // The responsibilities and the log-normaliser only depend on the components within a few tens of nats of a
-// point's best component.  The single-pass kernel (tc_estep2.cu, PASSES = 1: operands rounded to FP16, a
-// third of the tensor-pipe work) returns q~ with a RIGOROUS error bound: with y = W z and y~ its FP16-operand
-// value,  || y~ - y ||_2 <= B' = 1.05 * 2^-10 * max_k ||W_k||_F * max_n ||z_n||_2 + 1e-3   (each product carries two
-// roundings of 2^-11; Cauchy-Schwarz over the row, then over the rows), hence | sqrt(q~) - sqrt(q) | <= B'.
-// Per point:   lower bound of the best log-joint   L_n = max_k [ cst_k - (sqrt(q~) + B')^2 / 2 ]
-//              upper bound of component k           U_kn = cst_k - max(0, sqrt(q~) - B')^2 / 2
-// and (n, k) is a CANDIDATE iff U_kn >= L_n - 40.  Every non-candidate has a true log-joint more than 40 nats below
-// the true maximum: all of them together change exp-sums by < K e^-40 relative, far below FP32 resolution, so their
-// single-pass values are kept.  Candidates are grouped by component (counting sort) and recomputed in FP32 on the
-// CUDA cores (one component's operand block in shared memory, 4 x 4 register tiles), overwriting the scratch.
-// When more than 4 % of the pairs are candidates (overlapping components, early sweeps) the refinement would cost
-// more than it saves: a device-side flag then makes the dense 3-pass tensor-core kernel run instead and the
-// refinement kernels return immediately -- no host round trip either way.
+// point's best component.  The screening pass computes a rigorous UPPER bound of every a[k][n] at a fraction of the
+// dense cost:
+//   * rows: with Q (32 x Rp) a matrix with orthonormal rows, || Q y ||^2 <= || y ||^2, so the 32-row operand
+//     W'_k = Q W_k gives q' <= q.  Q is a sub-sampled Hadamard transform with fixed random column signs (a
+//     Johnson-Lindenstrauss projection: E q' = q 32 / Rp whatever the geometry of W_k); a quarter of the MMA work
+//     and of the accumulator traffic at Rp = 128;
+//   * precision: operands rounded to FP16 (tc_estep2.cu, PASSES = 1), a third of the passes.  With y' = W' z and y~ its
+//     FP16-operand value,  || y~ - y' ||_2 <= B = 1.05 * 2^-10 * max_k ||W'_k||_F * max_n ||z_n||_2  + (FP32 rounding
+//     of the projection) + 1e-3   (two roundings of 2^-11 per product; Cauchy-Schwarz over the row, then the rows),
+//     hence  U_kn = cst_k - max(0, sqrt(q~) - B)^2 / 2  >=  a[k][n].
+// The pass also returns each point's best component under the screening values (the guess).  The guesses are
+// recomputed exactly first (list A, one pair per point): L_n = a[guess_n][n] is a lower bound of the point's best
+// log-joint.  Then (n, k) is a CANDIDATE iff U_kn >= L_n - 40 (list B): every other pair lies more than 40 nats below
+// the point's maximum, all of them together change exp-sums by < K e^-40 relative -- far below FP32 resolution --
+// so their screening values (upper bounds, themselves below the cut) are kept.  Both lists are grouped by component
+// (counting sort) and recomputed in FP32 on the CUDA cores, overwriting the scratch; the sufficient statistics are then
+// summed over the two lists only (pair_stats.cu).  When more than 4 % of the pairs are candidates (overlapping
+// components, early sweeps) refinement would cost more than it saves: a device-side flag then makes the dense 3-pass
+// tensor-core kernel and the dense statistics kernels run instead -- no host round trip either way.
 #include <algorithm>
 #include "tc_common.cuh"
 #include "internal.h"
@@ -27,6 +33,7 @@ namespace mimo {
 using tc::screen_bound;
 
 constexpr float SCREEN_T0 = 40.f;
+constexpr int SCREEN_ROWS = 32;              // rows of the screening operands
 constexpr int RF_THREADS = 256;
 constexpr int RF_SPLIT = 8;                  // blocks per component
 
@@ -44,31 +51,79 @@ __global__ void screen_rownorm_kernel(const float* __restrict__ Z, int64_t N, in
     if (lane == 0) atomicMax(flags + 3, __float_as_uint(sqrtf(m) * 1.0000005f));
 }
 
-// max_k ||W_k[:, :D]||_F (the offset column is applied exactly in the epilogue and carries no rounding)
-__global__ void screen_wnorm_kernel(const float* __restrict__ W, int K, int Rp, int Dpp, int D, unsigned int* __restrict__ flags) {
+// max_k ||W_k[:, :cols]||_F -> flags[slot]   (slot 2: screening operands, data columns only -- the offset column is
+// applied in FP32 in the epilogue; slot 4: full operands, all columns -- scale of the projection's FP32 rounding)
+__global__ void screen_wnorm_kernel(const float* __restrict__ W, int K, int Rp, int Dpp, int cols, unsigned int* __restrict__ flags, int slot) {
     __shared__ float red[32];
     const int k = blockIdx.x;
     float s = 0.f;
-    for (int idx = threadIdx.x; idx < Rp * D; idx += blockDim.x) {
-        const int i = idx / D, j = idx - i * D;
+    for (int idx = threadIdx.x; idx < Rp * cols; idx += blockDim.x) {
+        const int i = idx / cols, j = idx - i * cols;
         const float w = W[((size_t)k * Rp + i) * Dpp + j];
         s = fmaf(w, w, s);
     }
     s = block_sum<float>(s, red);
-    if (threadIdx.x == 0) atomicMax(flags + 2, __float_as_uint(sqrtf(s) * 1.0000005f));
+    if (threadIdx.x == 0) atomicMax(flags + slot, __float_as_uint(sqrtf(s) * 1.0000005f));
 }
 
-// counters: [0] candidates found, [1] dense flag (set by screen_scan_kernel)
+// W'_k = Q W_k  (all Dpp columns: data, offset, padding).  Q[s][r] = sign(r) H[sel(s)][r] / sqrt(Rp) with H the
+// Sylvester-Hadamard matrix, H[a][r] = (-1)^popc(a & r): distinct rows of H are orthogonal, so Q has orthonormal rows.
+// grid = K, block = 256, dynamic shared memory = Rp * Dpp floats.
+__global__ void __launch_bounds__(256)
+screen_project_kernel(const float* __restrict__ W, int K, int Rp, int Dpp, float* __restrict__ Wp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* Ws = reinterpret_cast<float*>(smem_raw);
+    const int k = blockIdx.x;
+    for (int idx = threadIdx.x; idx < Rp * Dpp; idx += blockDim.x) {
+        const int r = idx / Dpp;
+        const float sgn = ((((unsigned int)r * 2654435761u) >> 15) & 1u) ? -1.f : 1.f;
+        Ws[idx] = sgn * W[(size_t)k * Rp * Dpp + idx];
+    }
+    __syncthreads();
+    const float inv = rsqrtf((float)Rp);
+    const int step = Rp / SCREEN_ROWS;
+    for (int idx = threadIdx.x; idx < SCREEN_ROWS * Dpp; idx += blockDim.x) {
+        const int s = idx / Dpp, j = idx - s * Dpp;
+        const int a = s * step + step / 2;                       // the selected Hadamard row
+        float acc = 0.f;
+        for (int r = 0; r < Rp; ++r) {
+            const float w = Ws[r * Dpp + j];
+            acc += (__popc(a & r) & 1) ? -w : w;
+        }
+        Wp[((size_t)k * SCREEN_ROWS + s) * Dpp + j] = acc * inv;
+    }
+}
+
+// list A: the better of the two accumulator halves' guesses; histogram over components
+__global__ void __launch_bounds__(256)
+screen_guess_kernel(const float* __restrict__ best_val, const int* __restrict__ best_k, int64_t ldl, int64_t n, int K,
+                    int* __restrict__ guess_k, int* __restrict__ histA) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v0 = best_val[i], v1 = best_val[ldl + i];
+    int k = (v1 > v0) ? best_k[ldl + i] : best_k[i];
+    k = min(max(k, 0), K - 1);
+    guess_k[i] = k;
+    atomicAdd(histA + k, 1);
+}
+
+__global__ void __launch_bounds__(256)
+screen_scatterA_kernel(const int* __restrict__ guess_k, int64_t n, int* __restrict__ cursor, int* __restrict__ perm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[atomicAdd(cursor + guess_k[i], 1)] = (int)i;
+}
+
+// list B: every pair whose upper bound reaches the point's threshold L_n - 40 (its guess excluded: already exact)
+// counters: [0] list B entries found, [1] dense flag (set by screen_scan_kernel), [2] always 0
 __global__ void __launch_bounds__(256)
 screen_emit_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, const float* __restrict__ cst,
-                   const unsigned int* __restrict__ flags, const float* __restrict__ lower, int64_t ldl,
+                   const unsigned int* __restrict__ flags, const float* __restrict__ lower, const int* __restrict__ guess_k,
                    int2* __restrict__ list, unsigned int cap, unsigned int* __restrict__ counters, int* __restrict__ hist) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     const float B = screen_bound(flags);
-    // L_n (lower bound of the point's best log-joint) was formed by the single-pass E-step epilogue, one value per
-    // half of the accumulator columns
-    const float t = valid ? fmaxf(lower[i], lower[ldl + i]) - SCREEN_T0 : INFINITY;
+    const float t = valid ? lower[i] - SCREEN_T0 - 0.01f * (1.f + 1e-4f * fabsf(lower[i])) : INFINITY;   // FP32 slack of the exact value
+    const int gk = valid ? guess_k[i] : -1;
     const int lane = threadIdx.x & 31;
     for (int k0 = 0; k0 < K; k0 += 4) {
       float av[4];
@@ -79,7 +134,7 @@ screen_emit_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, c
         const int k = k0 + u;
         if (k >= K) break;
         bool cand = false;
-        if (valid) {
+        if (valid && k != gk) {
             const float c = __ldg(cst + k);
             const float s = fmaxf(0.f, sqrtf(fmaxf(0.f, 2.f * (c - av[u]))) - B);
             cand = (c - 0.5f * s * s) >= t;
@@ -99,11 +154,12 @@ screen_emit_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, c
     }
 }
 
-// single block: exclusive scan of hist -> offsets[K+1], cursor := offsets; dense flag when too many candidates
+// single block: exclusive scan of hist -> offsets[K+1], cursor := offsets, slabs (work items of pair_stats.cu);
+// flag (optional): dense fallback when the list is too long
 __global__ void screen_scan_kernel(const int* __restrict__ hist, int K, int* __restrict__ offsets, int* __restrict__ cursor,
                                    int* __restrict__ slabs, unsigned int* __restrict__ counters, unsigned int max_cands) {
     if (threadIdx.x == 0) {
-        int run = 0, items = 0;                           // slabs: work items (PS_SLAB listed points) of pair_stats.cu
+        int run = 0, items = 0;
         for (int k = 0; k < K; ++k) {
             offsets[k] = run; cursor[k] = run; slabs[k] = items;
             run += hist[k];
@@ -111,7 +167,7 @@ __global__ void screen_scan_kernel(const int* __restrict__ hist, int K, int* __r
         }
         offsets[K] = run;
         slabs[K] = items;
-        counters[1] = (counters[0] > max_cands) ? 1u : 0u;
+        if (counters) counters[1] = (counters[0] > max_cands) ? 1u : 0u;
     }
 }
 
@@ -131,9 +187,9 @@ template <int RP>
 __global__ void __launch_bounds__(RF_THREADS)
 screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz,
                      const float* __restrict__ W, int Dpp, const float* __restrict__ cst,
-                     const int* __restrict__ perm, const int* __restrict__ offsets, const unsigned int* __restrict__ counters,
-                     float* __restrict__ a, int64_t ldo) {
-    if (counters[1] != 0u) return;
+                     const int* __restrict__ perm, const int* __restrict__ offsets, const unsigned int* __restrict__ gate,
+                     float* __restrict__ a, int64_t ldo, float* __restrict__ exact) {
+    if (gate != nullptr && __ldg(gate) != 0u) return;          // dense second pass instead
     constexpr int RG = RP / 4, CG = RF_THREADS / RG, TILE_C = 4 * CG;
     const int k = blockIdx.x;
     const int beg = offsets[k], cnt = offsets[k + 1] - beg;
@@ -185,7 +241,12 @@ screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz,
 #pragma unroll
             for (int o = RG / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);    // over the RG lanes of this candidate group
             const int ci = 4 * cg + c;
-            if (rg == 0 && ci < nc) a[(int64_t)k * ldo + perm[c0 + ci]] = ck - 0.5f * q;
+            if (rg == 0 && ci < nc) {
+                const int n = perm[c0 + ci];
+                const float val = ck - 0.5f * q;
+                a[(int64_t)k * ldo + n] = val;
+                if (exact) exact[n] = val;                     // list A: the point's guess, exactly (a lower bound of its best log-joint)
+            }
         }
     }
 }
@@ -193,116 +254,178 @@ screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz,
 // ---- host side -------------------------------------------------------------------------------
 
 static size_t a256(size_t x) { return (x + 255) / 256 * 256; }
+static char* align256(void* p) { return (char*)(((uintptr_t)p + 255) / 256 * 256); }
 
 bool tc_screen_supported(int D, int Rp) { return D >= 24 && D <= 128 && (Rp == 32 || Rp == 64 || Rp == 128); }
 
-struct ScreenLayout { unsigned int cap; size_t off_counters, off_hist, off_offsets, off_cursor, off_slabs, off_thr, off_list, off_perm, bytes; };
+struct ScreenLists { size_t hist, offsets, cursor, slabs, perm; };
+struct ScreenLayout {
+    unsigned int cap; int64_t ldl;
+    size_t off_counters; ScreenLists A, B;
+    size_t off_best_val, off_best_k, off_lower, off_guess, off_list, bytes;
+};
 static ScreenLayout screen_layout(int64_t chunk_points, int K) {
     ScreenLayout L;
     const double pairs = (double)chunk_points * K;
     L.cap = (unsigned int)std::min<double>(2.0e9, 0.05 * pairs + 1024.0);
+    L.ldl = (int64_t)(a256((size_t)chunk_points * 4) / 4);
+    const size_t kk = a256((size_t)(K + 1) * 4), pp = (size_t)L.ldl * 4;
     size_t o = 0;
     L.off_counters = o; o += 256;
-    L.off_hist = o;     o += a256((size_t)(K + 1) * 4);
-    L.off_offsets = o;  o += a256((size_t)(K + 1) * 4);
-    L.off_cursor = o;   o += a256((size_t)(K + 1) * 4);
-    L.off_slabs = o;    o += a256((size_t)(K + 1) * 4);
-    L.off_thr = o;      o += 2 * a256((size_t)chunk_points * 4);      // lower bounds, one row per accumulator half
+    L.A.hist = o; o += kk;  L.B.hist = o; o += kk;                 // zeroed together with the counters every chunk
+    L.A.offsets = o; o += kk;  L.A.cursor = o; o += kk;  L.A.slabs = o; o += kk;
+    L.B.offsets = o; o += kk;  L.B.cursor = o; o += kk;  L.B.slabs = o; o += kk;
+    L.off_best_val = o; o += 2 * pp;                               // one row per accumulator half
+    L.off_best_k = o;   o += 2 * pp;
+    L.off_lower = o;    o += pp;
+    L.off_guess = o;    o += pp;
+    L.A.perm = o;       o += pp;
     L.off_list = o;     o += a256((size_t)L.cap * 8);
-    L.off_perm = o;     o += a256((size_t)L.cap * 4);
+    L.B.perm = o;       o += a256((size_t)L.cap * 4);
     L.bytes = o;
     return L;
 }
-static char* align256(void* p) { return (char*)(((uintptr_t)p + 255) / 256 * 256); }
 size_t tc_screen_workspace(int64_t chunk_points, int K) { return screen_layout(chunk_points, K).bytes + 256; }
 
-// once per sweep, after tc_data_scale (which zeroes the flags): the two norms of the error bound
-int tc_screen_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp,
-                      unsigned int* flags, cudaStream_t st) {
+// [projected operands W' (K, 32, Dpp) | their operand image]; nothing when the operands already have <= 32 rows
+size_t tc_screen_operand_workspace(int K, int Rp, int Dpp, int D) {
+    if (Rp <= SCREEN_ROWS) return 0;
+    return 256 + a256((size_t)K * SCREEN_ROWS * Dpp * 4) + tc_operand_workspace(K, SCREEN_ROWS, D);
+}
+static float* screen_wproj(void* sops_ws) { return (float*)align256(sops_ws); }
+static void* screen_ops_ws(void* ops_ws, void* sops_ws, int K, int Rp, int Dpp) {
+    if (Rp <= SCREEN_ROWS) return ops_ws;
+    return align256(sops_ws) + a256((size_t)K * SCREEN_ROWS * Dpp * 4);
+}
+int tc_screen_rows(int Rp) { return Rp <= SCREEN_ROWS ? Rp : SCREEN_ROWS; }
+
+// once per sweep, after tc_data_scale + tc_prepare_operands on ops_ws: the norms of the error bound, the projected
+// operands and their image
+int tc_screen_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float* W, const float* cst, int K, int Rp, int Dpp,
+                      void* ops_ws, void* sops_ws, cudaStream_t st) {
+    unsigned int* flags = tc_flags(ops_ws);
     if (N > 0) {
         const int grid = (int)std::min<int64_t>((N + 7) / 8, (int64_t)sm_count() * 16);
         screen_rownorm_kernel<<<grid, 256, 0, st>>>(Z, N, D, ldz, flags);
         MIMO_LAUNCH_CHECK();
     }
-    screen_wnorm_kernel<<<K, 256, 0, st>>>(W, K, Rp, Dpp, D, flags);
+    if (Rp <= SCREEN_ROWS) {
+        screen_wnorm_kernel<<<K, 256, 0, st>>>(W, K, Rp, Dpp, D, flags, 2);
+        MIMO_LAUNCH_CHECK();
+        return MIMO_OK;
+    }
+    screen_wnorm_kernel<<<K, 256, 0, st>>>(W, K, Rp, Dpp, Dpp, flags, 4);
     MIMO_LAUNCH_CHECK();
-    return MIMO_OK;
+    float* Wp = screen_wproj(sops_ws);
+    const size_t smem = (size_t)Rp * Dpp * sizeof(float);
+    MIMO_CUDA(cudaFuncSetAttribute(screen_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    screen_project_kernel<<<K, 256, smem, st>>>(W, K, Rp, Dpp, Wp);
+    MIMO_LAUNCH_CHECK();
+    void* sws = screen_ops_ws(ops_ws, sops_ws, K, Rp, Dpp);
+    unsigned int* sflags = tc_flags(sws);
+    MIMO_CUDA(cudaMemcpyAsync(sflags, flags, 256, cudaMemcpyDeviceToDevice, st));      // data scale, ||z||, ||W||
+    screen_wnorm_kernel<<<K, 256, 0, st>>>(Wp, K, SCREEN_ROWS, Dpp, D, sflags, 2);
+    MIMO_LAUNCH_CHECK();
+    return tc_prepare_operands(Wp, cst, K, SCREEN_ROWS, Dpp, D, sws, st);
 }
 
-// after the single-pass E-step of a chunk: find the candidates; sets the device flag the dense pass is gated on
-// the two rows (leading dimension *ldl) the single-pass E-step writes its per-point lower bounds into
-float* tc_screen_lower(void* ws, int64_t plan_points, int K, int64_t* ldl) {
-    *ldl = (int64_t)(a256((size_t)plan_points * 4) / 4);
-    return (float*)(align256(ws) + screen_layout(plan_points, K).off_thr);
+// the screening pass over one chunk: upper bounds of every pair into `out`, the per-half guesses into the workspace
+int tc_screen_pass(const float* Z, int64_t n, int D, int64_t ldz, int K, int Rp, int Dpp, float* out, int64_t ldo,
+                   void* ops_ws, void* sops_ws, int64_t plan_points, void* ws, cudaStream_t st) {
+    ScreenLayout L = screen_layout(plan_points, K);
+    char* base = align256(ws);
+    return tc_estep_pass(Z, n, D, ldz, K, tc_screen_rows(Rp), out, ldo, screen_ops_ws(ops_ws, sops_ws, K, Rp, Dpp), 1, nullptr, 0u,
+                         (float*)(base + L.off_best_val), (int*)(base + L.off_best_k), L.ldl, st);
 }
 
 const unsigned int* tc_screen_gate(void* ws, int64_t plan_points, int K) {
     return (const unsigned int*)(align256(ws) + screen_layout(plan_points, K).off_counters) + 1;
 }
 
-// the candidate lists of the chunk, grouped by component (valid after tc_screen_refine when the dense flag is clear)
-void tc_screen_lists(void* ws, int64_t plan_points, int K, const int32_t** perm, const int32_t** offsets, const int32_t** slabs) {
+// the lists of the chunk, grouped by component: which = 0 the guesses (one per point), 1 the other candidates
+// (valid after tc_screen_refine when the dense flag is clear)
+void tc_screen_lists(void* ws, int64_t plan_points, int K, int which, const int32_t** perm, const int32_t** offsets, const int32_t** slabs) {
     ScreenLayout L = screen_layout(plan_points, K);
     char* base = align256(ws);
-    *perm = (const int32_t*)(base + L.off_perm);
-    *offsets = (const int32_t*)(base + L.off_offsets);
-    *slabs = (const int32_t*)(base + L.off_slabs);
+    const ScreenLists& S = which ? L.B : L.A;
+    *perm = (const int32_t*)(base + S.perm);
+    *offsets = (const int32_t*)(base + S.offsets);
+    *slabs = (const int32_t*)(base + S.slabs);
 }
 
 static const unsigned int* g_last_counters = nullptr;
+static int64_t g_last_points = 0;
 
-// {candidates, dense flag} of the most recent screened chunk (synchronises the device; tests / bench reporting)
+// {candidates (guesses + list B), dense flag} of the most recent screened chunk (synchronises the device; tests / bench reporting)
 int tc_screen_last(unsigned int* out_host2) {
     out_host2[0] = out_host2[1] = 0u;
     if (!g_last_counters) return MIMO_OK;
     MIMO_CUDA(cudaDeviceSynchronize());
     MIMO_CUDA(cudaMemcpy(out_host2, g_last_counters, 8, cudaMemcpyDeviceToHost));
+    out_host2[0] += (unsigned int)g_last_points;
     return MIMO_OK;
 }
 
-int tc_screen_select(const float* a, int K, int64_t n, int64_t ldo, const float* cst, const unsigned int* flags,
-                     int64_t plan_points, void* ws, cudaStream_t st) {
+template <int RP>
+static int launch_refine(const float* Z, int D, int64_t ldz, const float* W, int K, int Dpp, const float* cst,
+                         const int* perm, const int* offsets, const unsigned int* gate, float* a, int64_t ldo, float* exact,
+                         cudaStream_t st) {
+    constexpr int TILE_C = 4 * (RF_THREADS / (RP / 4));
+    const size_t smem = (size_t)(RP + TILE_C) * Dpp * sizeof(float);
+    MIMO_CUDA(cudaFuncSetAttribute(screen_refine_kernel<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    screen_refine_kernel<RP><<<dim3(K, RF_SPLIT), RF_THREADS, smem, st>>>(Z, D, ldz, W, Dpp, cst, perm, offsets, gate, a, ldo, exact);
+    MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
+}
+static int refine(const float* Z, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp, const float* cst,
+                  const int* perm, const int* offsets, const unsigned int* gate, float* a, int64_t ldo, float* exact, cudaStream_t st) {
+    if (Rp == 32) return launch_refine<32>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, gate, a, ldo, exact, st);
+    if (Rp == 64) return launch_refine<64>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, gate, a, ldo, exact, st);
+    if (Rp == 128) return launch_refine<128>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, gate, a, ldo, exact, st);
+    set_error("screened E-step: unsupported Rp=%d", Rp);
+    return MIMO_EUNSUPPORTED;
+}
+
+// after the screening pass of a chunk: exact values of the guesses (list A), then the candidates (list B) and the
+// device flag the dense pass is gated on
+int tc_screen_select(const float* Z, int D, int64_t ldz, const float* W, const float* cst, int K, int Rp, int Dpp,
+                     float* a, int64_t n, int64_t ldo, void* ops_ws, void* sops_ws, int64_t plan_points, void* ws, cudaStream_t st) {
     ScreenLayout L = screen_layout(plan_points, K);
     char* base = align256(ws);
     unsigned int* counters = (unsigned int*)(base + L.off_counters);
     g_last_counters = counters;
-    int* hist = (int*)(base + L.off_hist);
-    MIMO_CUDA(cudaMemsetAsync(base, 0, L.off_offsets, st));                 // counters + hist
+    g_last_points = n;
+    MIMO_CUDA(cudaMemsetAsync(base, 0, L.A.offsets, st));                   // counters + both histograms
     const int grid = cdiv(n, 256);
-    screen_emit_kernel<<<grid, 256, 0, st>>>(a, K, n, ldo, cst, flags, (const float*)(base + L.off_thr),
-                                             (int64_t)(a256((size_t)plan_points * 4) / 4),
-                                             (int2*)(base + L.off_list), L.cap, counters, hist);
+    int* guess_k = (int*)(base + L.off_guess);
+    float* lower = (float*)(base + L.off_lower);
+    screen_guess_kernel<<<grid, 256, 0, st>>>((const float*)(base + L.off_best_val), (const int*)(base + L.off_best_k), L.ldl, n, K,
+                                              guess_k, (int*)(base + L.A.hist));
+    screen_scan_kernel<<<1, 32, 0, st>>>((const int*)(base + L.A.hist), K, (int*)(base + L.A.offsets), (int*)(base + L.A.cursor),
+                                         (int*)(base + L.A.slabs), nullptr, 0u);
+    screen_scatterA_kernel<<<grid, 256, 0, st>>>(guess_k, n, (int*)(base + L.A.cursor), (int*)(base + L.A.perm));
+    MIMO_LAUNCH_CHECK();
+    int rc = refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.A.perm), (const int*)(base + L.A.offsets), nullptr, a, ldo, lower, st);
+    if (rc) return rc;
+    const unsigned int* flags = tc_flags(screen_ops_ws(ops_ws, sops_ws, K, Rp, Dpp));
+    screen_emit_kernel<<<grid, 256, 0, st>>>(a, K, n, ldo, cst, flags, lower, guess_k, (int2*)(base + L.off_list), L.cap,
+                                             counters, (int*)(base + L.B.hist));
     const double maxc = std::min<double>((double)L.cap, 0.04 * (double)n * K);
-    screen_scan_kernel<<<1, 32, 0, st>>>(hist, K, (int*)(base + L.off_offsets), (int*)(base + L.off_cursor), (int*)(base + L.off_slabs), counters,
-                                         (unsigned int)maxc);
+    screen_scan_kernel<<<1, 32, 0, st>>>((const int*)(base + L.B.hist), K, (int*)(base + L.B.offsets), (int*)(base + L.B.cursor),
+                                         (int*)(base + L.B.slabs), counters, (unsigned int)maxc);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
 
-// exact values of the candidates (returns immediately on the device when the dense flag is set)
+// exact values of list B (returns immediately on the device when the dense flag is set)
 int tc_screen_refine(const float* Z, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp, const float* cst,
                      float* a, int64_t ldo, int64_t plan_points, void* ws, cudaStream_t st) {
     ScreenLayout L = screen_layout(plan_points, K);
     char* base = align256(ws);
     const unsigned int* counters = (const unsigned int*)(base + L.off_counters);
-    int* perm = (int*)(base + L.off_perm);
-    screen_scatter_kernel<<<sm_count() * 4, 256, 0, st>>>((const int2*)(base + L.off_list), counters, (int*)(base + L.off_cursor), perm);
+    screen_scatter_kernel<<<sm_count() * 4, 256, 0, st>>>((const int2*)(base + L.off_list), counters, (int*)(base + L.B.cursor), (int*)(base + L.B.perm));
     MIMO_LAUNCH_CHECK();
-    const int* offsets = (const int*)(base + L.off_offsets);
-    dim3 grid(K, RF_SPLIT);
-#define RF_CASE(rp)                                                                                                   \
-    if (Rp == rp) {                                                                                                   \
-        constexpr int TILE_C = 4 * (RF_THREADS / (rp / 4));                                                           \
-        const size_t smem = (size_t)(rp + TILE_C) * Dpp * sizeof(float);                                              \
-        MIMO_CUDA(cudaFuncSetAttribute(screen_refine_kernel<rp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        screen_refine_kernel<rp><<<grid, RF_THREADS, smem, st>>>(Z, D, ldz, W, Dpp, cst, perm, offsets, counters, a, ldo); \
-        MIMO_LAUNCH_CHECK();                                                                                          \
-        return MIMO_OK;                                                                                               \
-    }
-    RF_CASE(32) RF_CASE(64) RF_CASE(128)
-#undef RF_CASE
-    set_error("screened E-step: unsupported Rp=%d", Rp);
-    return MIMO_EUNSUPPORTED;
+    return refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.B.perm), (const int*)(base + L.B.offsets), counters + 1, a, ldo, nullptr, st);
 }
 
 }  // namespace mimo
