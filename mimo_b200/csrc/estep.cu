@@ -227,7 +227,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 softmax_kernel(T* __restrict__ a, int K, int64_t n, int64_t ldo, int flags,
                T* __restrict__ lse_out, const double* __restrict__ uniforms, uint64_t seed, uint64_t point_offset,
-               int32_t* __restrict__ labels, double* __restrict__ lse_sum) {
+               int32_t* __restrict__ labels, double* __restrict__ lse_sum,
+               const unsigned int* __restrict__ gate, unsigned int gate_value) {
+    if (gate != nullptr && *gate != gate_value) return;      // the list-based log-normaliser of tc_screen.cu ran instead
     __shared__ double red[32];
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double my_lse = 0.0;
@@ -315,7 +317,8 @@ int loglik_diag(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const v
 }
 
 int softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags, void* lse, const void* uniforms,
-            uint64_t seed, uint64_t point_offset, int32_t* labels, double* lse_sum, cudaStream_t st) {
+            uint64_t seed, uint64_t point_offset, int32_t* labels, double* lse_sum, cudaStream_t st,
+            const unsigned int* gate, unsigned int gate_value) {
     MIMO_CHECK_ARG(dtype == MIMO_F32 || dtype == MIMO_F64, "dtype");
     MIMO_CHECK_ARG(a && K >= 1 && n >= 0 && ldo >= n, "shape");
     MIMO_CHECK_ARG(!(flags & MIMO_WRITE_LSE) || lse, "lse output missing");
@@ -325,10 +328,10 @@ int softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags, void* 
     int grid = cdiv(n, 256);
     if (dtype == MIMO_F32)
         softmax_kernel<float><<<grid, 256, 0, st>>>((float*)a, K, n, ldo, flags, (float*)lse, (const double*)uniforms,
-                                                    seed, point_offset, labels, lse_sum);
+                                                    seed, point_offset, labels, lse_sum, gate, gate_value);
     else
         softmax_kernel<double><<<grid, 256, 0, st>>>((double*)a, K, n, ldo, flags, (double*)lse, (const double*)uniforms,
-                                                     seed, point_offset, labels, lse_sum);
+                                                     seed, point_offset, labels, lse_sum, gate, gate_value);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }

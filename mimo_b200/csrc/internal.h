@@ -11,7 +11,8 @@ int loglik_quad(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const v
 int loglik_diag(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const void* S, const void* Tm,
                 const void* cst, int K, void* out, int64_t ldo, cudaStream_t st);
 int softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags, void* lse, const void* uniforms,
-            uint64_t seed, uint64_t point_offset, int32_t* labels, double* lse_sum, cudaStream_t st);
+            uint64_t seed, uint64_t point_offset, int32_t* labels, double* lse_sum, cudaStream_t st,
+            const unsigned int* gate = nullptr, unsigned int gate_value = 0u);
 
 int stats_soft(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K,
                const int32_t* fi, const int32_t* fj, int F, double* stat, cudaStream_t st);
@@ -46,6 +47,8 @@ int tc_screen_select(const float* Z, int D, int64_t ldz, const float* W, const f
                      float* a, int64_t n, int64_t ldo, void* ops_ws, void* sops_ws, int64_t plan_points, void* ws, cudaStream_t st);
 int tc_screen_refine(const float* Z, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp, const float* cst,
                      float* a, int64_t ldo, int64_t plan_points, void* ws, cudaStream_t st);
+int tc_screen_lse(const float* a, int K, int64_t n, int64_t ldo, double* lse_sum, int64_t plan_points, void* ws, cudaStream_t st);
+const float* tc_screen_lse_values(void* ws, int64_t plan_points, int K);
 void tc_screen_lists(void* ws, int64_t plan_points, int K, int which, const int32_t** perm, const int32_t** offsets, const int32_t** slabs);
 int tc_estep(const float* Z, int64_t N, int D, int64_t ldz, const float* cst, int K, int Rp,
              float* out, int64_t ldo, void* ws, cudaStream_t st);
@@ -82,7 +85,7 @@ int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp
 constexpr int PS_SLAB = 1024;        // listed points of one component per work item
 bool pair_stats_supported(int dtype, int D, int F);
 int pair_stats(const float* Z, int D, int64_t ldz, const int32_t* perm, const int32_t* offsets, const int32_t* slabs, int K,
-               const float* R, int64_t ldr, const unsigned int* gate, unsigned int gate_value,
+               const float* R, int64_t ldr, const float* lse, const unsigned int* gate, unsigned int gate_value,
                double* stat, int F, cudaStream_t st);
 
 bool sweep_uses_tc(int dtype, int family, int D, int Rp);

@@ -31,7 +31,7 @@ __device__ __forceinline__ int ps_off(int c) { return c + ((c >> 5) << 2); }
 __global__ void __launch_bounds__(PS_THREADS, 3)
 pair_stats_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
                   const int32_t* __restrict__ perm, const int32_t* __restrict__ offsets, const int32_t* __restrict__ slabs, int K,
-                  const float* __restrict__ R, int64_t ldr,
+                  const float* __restrict__ R, int64_t ldr, const float* __restrict__ lse,
                   const unsigned int* __restrict__ gate, unsigned int gate_value,
                   double* __restrict__ stat, int F) {
     if (gate != nullptr && __ldg(gate) != gate_value) return;
@@ -77,7 +77,12 @@ pair_stats_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
             if (tid < np) {
                 const int n = perm[p0 + tid];
                 s_idx[tid] = n;
-                s_w[tid] = R ? __ldg(R + (int64_t)k * ldr + n) : 1.f;
+                float w = 1.f;                    // hard labels
+                if (R) {
+                    w = __ldg(R + (int64_t)k * ldr + n);                        // responsibility ...
+                    if (lse) w = __expf(w - __ldg(lse + n));                    // ... or log-joint and the point's log-normaliser
+                }
+                s_w[tid] = w;
             }
             __syncthreads();
             if (vec4) {
@@ -146,7 +151,7 @@ bool pair_stats_supported(int dtype, int D, int F) {
 }
 
 int pair_stats(const float* Z, int D, int64_t ldz, const int32_t* perm, const int32_t* offsets, const int32_t* slabs, int K,
-               const float* R, int64_t ldr, const unsigned int* gate, unsigned int gate_value,
+               const float* R, int64_t ldr, const float* lse, const unsigned int* gate, unsigned int gate_value,
                double* stat, int F, cudaStream_t st) {
     MIMO_CHECK_ARG(Z && perm && offsets && slabs && stat, "null pointer");
     MIMO_CHECK_ARG(pair_stats_supported(MIMO_F32, D, F), "pair statistics: unsupported shape");
@@ -155,7 +160,7 @@ int pair_stats(const float* Z, int D, int64_t ldz, const int32_t* perm, const in
     const size_t smem = (size_t)2 * PS_PT * RS * sizeof(float);
     const int vec4 = (D % 4 == 0) && (ldz % 4 == 0) && (((uintptr_t)Z & 15) == 0);
     MIMO_CUDA(cudaFuncSetAttribute(pair_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pair_stats_kernel<<<sm_count() * 6, PS_THREADS, smem, st>>>(Z, D, ldz, vec4, perm, offsets, slabs, K, R, ldr,
+    pair_stats_kernel<<<sm_count() * 6, PS_THREADS, smem, st>>>(Z, D, ldz, vec4, perm, offsets, slabs, K, R, ldr, lse,
                                                                 gate, gate_value, stat, F);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;

@@ -287,7 +287,7 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
         MIMO_CUDA(cudaStreamSynchronize(st));
         if (hbad) { set_error("labels outside [0, K)"); return MIMO_EINVAL; }
     }
-    if (pair) return pair_stats((const float*)Z, D, ldz, perm, offsets, slabs, K, nullptr, 0, nullptr, 0u, stat, F, st);
+    if (pair) return pair_stats((const float*)Z, D, ldz, perm, offsets, slabs, K, nullptr, 0, nullptr, nullptr, 0u, stat, F, st);
     size_t es = dtype == MIMO_F32 ? 4 : 8;
     size_t smem = (size_t)SH_PT * (D + 2) * es;
     // every component contributes at most ceil(count/SEG) <= count/SEG + 1 slabs

@@ -96,6 +96,8 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     const bool tc_stats = use_tc && stat && !hard && tc_stats_supported(dtype, D, F);
     const bool tc_fstats = tc_stats && tc_fstats_supported(dtype, D, F);     // feature form (folded triangle) for D > 64
     const bool pair_stats_list = tc_stats && use_screen && g_tc_mode == 1 && pair_stats_supported(dtype, D, F);
+    // ... and the log-normalisers too: no pass over the (K, chunk) scratch after the refinement on such chunks
+    const bool list_softmax = pair_stats_list && !lse_out;
     if (use_tc) {
         tc_ops_ws = ws; ws += a256(tc_operand_workspace(K, Rp, D));
         if (sweep_uses_screen(dtype, family, D, K, Rp)) {
@@ -145,7 +147,12 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         int32_t* lab = hard ? lab_all + n0 : nullptr;
         const double* uni = uniforms ? (const double*)uniforms + n0 : nullptr;
         void* lse_c = lse_out ? (char*)lse_out + (size_t)n0 * es : nullptr;
-        rc = softmax(dtype, scratch, K, nc, C, flags, lse_c, uni, seed, point_offset + (uint64_t)n0, lab, lse_sum, st);
+        if (list_softmax) {
+            rc = tc_screen_lse((const float*)scratch, K, nc, C, lse_sum, C, screen_ws, st);
+            if (rc) return rc;
+        }
+        rc = softmax(dtype, scratch, K, nc, C, flags, lse_c, uni, seed, point_offset + (uint64_t)n0, lab, lse_sum, st,
+                     list_softmax ? tc_screen_gate(screen_ws, C, K) : nullptr, 1u);
         if (rc) return rc;
         mark();
         if (ll_out)
@@ -159,7 +166,8 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
                 for (int which = 0; which < 2; ++which) {                  // the guesses, then the other candidates
                     const int32_t *perm, *offsets, *slabs;
                     tc_screen_lists(screen_ws, C, K, which, &perm, &offsets, &slabs);
-                    rc = pair_stats((const float*)Zc, D, ldz, perm, offsets, slabs, K, (const float*)scratch, C, sgate, 0u, stat, F, st);
+                    rc = pair_stats((const float*)Zc, D, ldz, perm, offsets, slabs, K, (const float*)scratch, C,
+                                    list_softmax ? tc_screen_lse_values(screen_ws, C, K) : nullptr, sgate, 0u, stat, F, st);
                     if (rc) return rc;
                 }
             }
@@ -196,7 +204,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             // kernel launches of this chunk: E-step (+ offsets blocks for the CTA-pair kernel), softmax,
             // statistics (feature form: data image + responsibility image + GEMM)
             phase_ms[3] += 2.0 + (use_screen ? 10.0 : 0.0)
-                         + ((hard || !stat) ? 0.0 : (tc_fstats ? 3.0 : 1.0)) + (pair_stats_list ? 2.0 : 0.0);
+                         + ((hard || !stat) ? 0.0 : (tc_fstats ? 3.0 : 1.0)) + (pair_stats_list ? 2.0 : 0.0) + (list_softmax ? 4.0 : 0.0);
         }
         if (h0) {
             float ms = 0.f;

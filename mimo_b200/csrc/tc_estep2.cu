@@ -15,9 +15,14 @@
 // TMEM lane; warps 0-3 own accumulator columns 0..127 = the even 128-row chunk, warps 4-7
 // columns 128..255 = the odd one), warp 8 = MMA issuer (leader CTA) or relay (peer CTA), warp 9
 // = bulk-copy producer of this CTA's half of B and of the per-chunk offsets.  The leader's
-// issuer must see BOTH CTAs' "A written", "B landed" and "accumulator drained" events: the peer's
-// relay thread waits on its local mbarriers and forwards each event with one remote
-// mbarrier.arrive; completions travel the other way with tcgen05.commit ... multicast.
+// issuer must see BOTH CTAs' "A written", "B landed" and "accumulator drained" events: the
+// epilogue warps of both CTAs arrive on the LEADER's accumulator barrier directly (one remote
+// mbarrier.arrive per warp), the peer's relay thread forwards its "A written" / "B landed"
+// events; completions travel the other way with tcgen05.commit ... multicast.
+// The accumulator round trip MMA -> drain -> MMA is what bounds the single-pass (screening)
+// variant -- 8 MMAs per 256 columns instead of 24 -- so an epilogue warp pulls its whole
+// 128-column slice into registers with four tcgen05.ld in flight and releases the accumulator
+// before doing any arithmetic on it.
 #include <algorithm>
 #include "tc_common.cuh"
 #include "internal.h"
@@ -118,7 +123,7 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); mbar_init(&bars->peer_full[s], 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 256); mbar_init(&bars->peer_tmem_empty[b], 1);
+            mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 16); mbar_init(&bars->peer_tmem_empty[b], 1);   // tmem_empty (leader's): one arrival per epilogue warp of BOTH CTAs
         }
         for (int b = 0; b < T2_OFFRING; ++b) { mbar_init(&bars->off_full[b], 1); mbar_init(&bars->off_empty[b], 256); }
         mbar_init(&bars->a_full, 256);
@@ -197,22 +202,25 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                 const float* off_s = blk + half * 128;
                 const float* scal_s = blk + 256;
                 const int kbase = c * (256 / RP), jbase = half * (128 / RP);
-                float va[32], vb[32];
+                // the whole 128-column slice into registers with the four loads in flight, then the accumulator is
+                // free again: the drain costs one TMEM latency on the MMA -> epilogue -> MMA chain, not four plus the math
+                float v0[32], v1[32], v2[32], v3[32];
                 float q[4] = {0.f, 0.f, 0.f, 0.f};
-                tmem_ld32(taddr, va);
-                tmem_ld_wait();
-                tmem_ld32(taddr + 32, vb);
-                t2_consume<RP, SCREEN>(va, off_s, 0, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
-                tmem_ld_wait();
-                tmem_ld32(taddr + 64, va);
-                t2_consume<RP, SCREEN>(vb, off_s, 32, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
-                tmem_ld_wait();
-                tmem_ld32(taddr + 96, vb);
-                t2_consume<RP, SCREEN>(va, off_s, 64, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
+                tmem_ld32(taddr, v0);
+                tmem_ld32(taddr + 32, v1);
+                tmem_ld32(taddr + 64, v2);
+                tmem_ld32(taddr + 96, v3);
                 tmem_ld_wait();
                 tc_fence_before();
-                mbar_arrive(&bars->tmem_empty[buf]);             // accumulator drained: the pair's MMA may reuse it
-                t2_consume<RP, SCREEN>(vb, off_s, 96, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
+                __syncwarp();
+                if (lane == 0) {                                 // straight to the leader's barrier (no relay hop)
+                    if (rank == 0) mbar_arrive(&bars->tmem_empty[buf]);
+                    else mbar_arrive_remote(map_to_rank(smem_u32(&bars->tmem_empty[buf]), 0));
+                }
+                t2_consume<RP, SCREEN>(v0, off_s, 0, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
+                t2_consume<RP, SCREEN>(v1, off_s, 32, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
+                t2_consume<RP, SCREEN>(v2, off_s, 64, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
+                t2_consume<RP, SCREEN>(v3, off_s, 96, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
                 mbar_arrive(&bars->off_empty[ob]);
             }
             if (SCREEN && pvalid) { lower[(int64_t)half * ldl + n] = Lb; guess[(int64_t)half * ldl + n] = Lk; }
@@ -230,9 +238,7 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                 tc_fence_after();
                 for (int c = 0; c < n_chunks2; ++c, ++gc) {
                     const uint32_t buf = gc & 1, par = ((gc >> 1) & 1) ^ 1;
-                    mbar_wait(&bars->tmem_empty[buf], par);
-                    // the peer's drain events are forwarded from the buffer's second use on (the first use is free)
-                    if (gc >= 2) mbar_wait_cluster(&bars->peer_tmem_empty[buf], ((gc >> 1) - 1) & 1);
+                    mbar_wait_cluster(&bars->tmem_empty[buf], par);      // drained by the epilogue warps of both CTAs
                     tc_fence_after();
                     const uint32_t d = tmem_base + buf * 256;
                     for (int kb = 0; kb < KB; ++kb) {
@@ -268,11 +274,6 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                 mbar_wait(&bars->a_full, it & 1);
                 mbar_arrive_remote(r_a);
                 for (int c = 0; c < n_chunks2; ++c, ++gc) {
-                    const uint32_t buf = gc & 1, par = ((gc >> 1) & 1) ^ 1;
-                    if (gc >= 2) {
-                        mbar_wait(&bars->tmem_empty[buf], par);
-                        mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_tmem_empty[buf]), 0));
-                    }
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&bars->full[stage], phase);
                         mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_full[stage]), 0));

@@ -185,7 +185,7 @@ __global__ void screen_scatter_kernel(const int2* __restrict__ list, const unsig
 // Thread (rg, cg): rows rg + RG r (r < 4), candidates 4 cg + c (c < 4) of a tile of TILE_C candidates.
 template <int RP>
 __global__ void __launch_bounds__(RF_THREADS)
-screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz,
+screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
                      const float* __restrict__ W, int Dpp, const float* __restrict__ cst,
                      const int* __restrict__ perm, const int* __restrict__ offsets, const unsigned int* __restrict__ gate,
                      float* __restrict__ a, int64_t ldo, float* __restrict__ exact) {
@@ -205,11 +205,26 @@ screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz,
     for (int t = blockIdx.y; t < tiles; t += gridDim.y) {
         const int c0 = beg + t * TILE_C, nc = min(TILE_C, beg + cnt - c0);
         __syncthreads();                                       // Ws ready / previous tile consumed
-        for (int idx = tid; idx < TILE_C * Dpp; idx += RF_THREADS) {
-            const int c = idx / Dpp, j = idx - c * Dpp;
-            float v = 0.f;
-            if (c < nc) v = (j < D) ? __ldg(Z + (int64_t)perm[c0 + c] * ldz + j) : (j == D ? 1.f : 0.f);
-            Zs[idx] = v;
+        if (vec4) {                                            // rows as float4: several gathers in flight per thread
+            const int q4 = D >> 2, tail = Dpp - D;
+#pragma unroll 4
+            for (int idx = tid; idx < TILE_C * q4; idx += RF_THREADS) {
+                const int c = idx / q4, j = (idx - c * q4) << 2;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < nc) v = __ldg(reinterpret_cast<const float4*>(Z + (int64_t)__ldg(perm + c0 + c) * ldz + j));
+                *reinterpret_cast<float4*>(Zs + (size_t)c * Dpp + j) = v;
+            }
+            for (int idx = tid; idx < TILE_C * tail; idx += RF_THREADS) {
+                const int c = idx / tail, j = D + (idx - c * tail);
+                Zs[(size_t)c * Dpp + j] = (c < nc && j == D) ? 1.f : 0.f;
+            }
+        } else {
+            for (int idx = tid; idx < TILE_C * Dpp; idx += RF_THREADS) {
+                const int c = idx / Dpp, j = idx - c * Dpp;
+                float v = 0.f;
+                if (c < nc) v = (j < D) ? __ldg(Z + (int64_t)perm[c0 + c] * ldz + j) : (j == D ? 1.f : 0.f);
+                Zs[idx] = v;
+            }
         }
         __syncthreads();
         float acc[4][4];
@@ -251,6 +266,56 @@ screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz,
     }
 }
 
+// ---- log-normaliser over the lists only ---------------------------------------------------------
+// lse_n = log sum_k exp(a[k][n]) restricted to the point's guess and its list-B candidates: every other pair lies
+// more than 40 nats below the maximum (mixtures/gmm.py:72-75, 256-259 up to K e^-40 relative).  All kernels return
+// at once when the dense flag is set (the dense softmax kernel runs instead).
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else          atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(256)
+screen_lse_init_kernel(const float* __restrict__ lower, int64_t n, const unsigned int* __restrict__ counters,
+                       float* __restrict__ m, float* __restrict__ s) {
+    if (counters[1] != 0u) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { m[i] = lower[i]; s[i] = 0.f; }
+}
+
+// phase 0: m_n = max(m_n, a) over list B;  phase 1: s_n += exp(a - m_n) over list B
+__global__ void __launch_bounds__(256)
+screen_lse_list_kernel(const int2* __restrict__ list, const unsigned int* __restrict__ counters, const float* __restrict__ a, int64_t ldo,
+                       float* __restrict__ m, float* __restrict__ s, int phase) {
+    if (counters[1] != 0u) return;
+    const unsigned int total = counters[0];
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int2 c = list[e];
+        const float v = a[(int64_t)c.x * ldo + c.y];
+        if (phase == 0) atomic_max_float(m + c.y, v);
+        else            atomicAdd(s + c.y, __expf(v - m[c.y]));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+screen_lse_final_kernel(const float* __restrict__ lower, const float* __restrict__ m, const float* __restrict__ s, int64_t n,
+                        const unsigned int* __restrict__ counters, float* __restrict__ lse, double* __restrict__ lse_sum) {
+    if (counters[1] != 0u) return;
+    __shared__ double red[32];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double mine = 0.0;
+    if (i < n) {
+        const float mm = m[i];
+        const double tot = (double)s[i] + (double)expf(lower[i] - mm);
+        mine = (double)mm + log(tot);
+        lse[i] = (float)mine;
+    }
+    if (lse_sum) {
+        const double tot = block_sum<double>(mine, red);
+        if (threadIdx.x == 0) atomicAdd(lse_sum, tot);
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 
 static size_t a256(size_t x) { return (x + 255) / 256 * 256; }
@@ -262,7 +327,7 @@ struct ScreenLists { size_t hist, offsets, cursor, slabs, perm; };
 struct ScreenLayout {
     unsigned int cap; int64_t ldl;
     size_t off_counters; ScreenLists A, B;
-    size_t off_best_val, off_best_k, off_lower, off_guess, off_list, bytes;
+    size_t off_best_val, off_best_k, off_lower, off_guess, off_m, off_s, off_lse, off_list, bytes;
 };
 static ScreenLayout screen_layout(int64_t chunk_points, int K) {
     ScreenLayout L;
@@ -279,6 +344,9 @@ static ScreenLayout screen_layout(int64_t chunk_points, int K) {
     L.off_best_k = o;   o += 2 * pp;
     L.off_lower = o;    o += pp;
     L.off_guess = o;    o += pp;
+    L.off_m = o;        o += pp;
+    L.off_s = o;        o += pp;
+    L.off_lse = o;      o += pp;
     L.A.perm = o;       o += pp;
     L.off_list = o;     o += a256((size_t)L.cap * 8);
     L.B.perm = o;       o += a256((size_t)L.cap * 4);
@@ -372,8 +440,9 @@ static int launch_refine(const float* Z, int D, int64_t ldz, const float* W, int
                          cudaStream_t st) {
     constexpr int TILE_C = 4 * (RF_THREADS / (RP / 4));
     const size_t smem = (size_t)(RP + TILE_C) * Dpp * sizeof(float);
+    const int vec4 = (D % 4 == 0) && (Dpp % 4 == 0) && (ldz % 4 == 0) && (((uintptr_t)Z & 15) == 0);
     MIMO_CUDA(cudaFuncSetAttribute(screen_refine_kernel<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    screen_refine_kernel<RP><<<dim3(K, RF_SPLIT), RF_THREADS, smem, st>>>(Z, D, ldz, W, Dpp, cst, perm, offsets, gate, a, ldo, exact);
+    screen_refine_kernel<RP><<<dim3(K, RF_SPLIT), RF_THREADS, smem, st>>>(Z, D, ldz, vec4, W, Dpp, cst, perm, offsets, gate, a, ldo, exact);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
@@ -426,6 +495,27 @@ int tc_screen_refine(const float* Z, int D, int64_t ldz, const float* W, int K, 
     screen_scatter_kernel<<<sm_count() * 4, 256, 0, st>>>((const int2*)(base + L.off_list), counters, (int*)(base + L.B.cursor), (int*)(base + L.B.perm));
     MIMO_LAUNCH_CHECK();
     return refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.B.perm), (const int*)(base + L.B.offsets), counters + 1, a, ldo, nullptr, st);
+}
+
+// log-normalisers of the chunk from the lists (after tc_screen_refine): per-point lse into the workspace, their sum
+// added to *lse_sum.  No-op on the device when the chunk fell back to the dense pass.
+int tc_screen_lse(const float* a, int K, int64_t n, int64_t ldo, double* lse_sum, int64_t plan_points, void* ws, cudaStream_t st) {
+    ScreenLayout L = screen_layout(plan_points, K);
+    char* base = align256(ws);
+    const unsigned int* counters = (const unsigned int*)(base + L.off_counters);
+    const float* lower = (const float*)(base + L.off_lower);
+    float* m = (float*)(base + L.off_m);
+    float* s = (float*)(base + L.off_s);
+    const int grid = cdiv(n, 256);
+    screen_lse_init_kernel<<<grid, 256, 0, st>>>(lower, n, counters, m, s);
+    screen_lse_list_kernel<<<sm_count() * 4, 256, 0, st>>>((const int2*)(base + L.off_list), counters, a, ldo, m, s, 0);
+    screen_lse_list_kernel<<<sm_count() * 4, 256, 0, st>>>((const int2*)(base + L.off_list), counters, a, ldo, m, s, 1);
+    screen_lse_final_kernel<<<grid, 256, 0, st>>>(lower, m, s, n, counters, (float*)(base + L.off_lse), lse_sum);
+    MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
+}
+const float* tc_screen_lse_values(void* ws, int64_t plan_points, int K) {
+    return (const float*)(align256(ws) + screen_layout(plan_points, K).off_lse);
 }
 
 }  // namespace mimo
