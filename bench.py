@@ -331,6 +331,7 @@ def main():
     ap.add_argument('--n-override', type=int, default=0, help='debug only: smaller N (marks the line invalid)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-dense', action='store_true', help='skip the dense-path comparison sweep')
     ap.add_argument('--tc-mode', type=int, default=-1, help='A/B only: 3 = dense 3-pass E-step (no screening), 0 = CUDA cores')
     args = ap.parse_args()
     name = args.workload
@@ -453,11 +454,25 @@ def main():
     else:
         ach = n_local * work['bytes_pt'] / (phase_ms[dom] * 1e-3) / 1e9 if phase_ms[dom] > 0 else 0.0
         roof = dict(bound='hbm', achieved=ach, peak=peaks['hbm'], unit='GB/s', frac=ach / peaks['hbm'], traffic=None)
+    screened = (args.tc_mode in (-1, 1, 4)) and w['kind'] == 'gmm' and w['d'] >= 24 and K >= 32 and not hard
     if name == 'cfg5' and not args.n_override:
-        tr = ncu_traffic(['tc_estep2_kernel', 'softmax_kernel', 'tc_fstats_kernel'][dom])
+        tr = ncu_traffic([('tc_estep2_screen_kernel' if screened else 'tc_estep2_kernel'), 'softmax_kernel',
+                          ('pair_stats_kernel' if screened else 'tc_fstats_kernel')][dom])
         if tr:
             roof['traffic'] = tr['bytes']                     # DRAM bytes per launch (one ~1M-point chunk)
             roof['traffic_source'] = tr['source']
+    if bound == 'tensor' and w['kind'] == 'gmm' and w['d'] >= 24:
+        # what the tensor pipe really executes for the E-step: 3 FP16 passes over all Rp operand rows on the dense path;
+        # 1 pass over the 32 projected rows on the screened path (plus FP32 CUDA-core work on the candidate lists)
+        rp = 1 << (max(w['d'], 8) - 1).bit_length()
+        mma_pair = (2.0 * min(rp, 32) * w['d']) if screened else (3 * 2.0 * rp * w['d'])
+        if phase_ms[0] > 0:
+            roof['estep_executed_tflops'] = mma_pair * pairs_local / (phase_ms[0] * 1e-3) / 1e12
+        roof['note'] = ('achieved = ALGORITHMIC flops of the dense formulation (SURVEY 8d) / time; the default path is SCREENED: one '
+                        'FP16 pass over a 32-row orthogonal projection of every operand bounds all N*K log-joints, pairs within 40 '
+                        'nats of a point\'s best component are recomputed in FP32, statistics are summed over those pairs only, so '
+                        'frac can exceed 1; `dense_path` is the same sweep with screening off (3-pass dense tensor-core kernels)'
+                        if screened else 'dense 3-pass tensor-core path')
     roof.update(kernel=['E-step (log-likelihood)', 'softmax / label draw', 'sufficient statistics'][dom],
                 launches_per_step=launches_per_step, ms_per_launch=phase_ms[dom] / max(launches_per_step, 1),
                 phase_ms_per_step=dict(estep=phase_ms[0], softmax=phase_ms[1], stats=phase_ms[2]),
@@ -475,12 +490,36 @@ def main():
     cpu = None
     if not args.no_cpu and world == 1:
         cpu, _ = time_cpu(w, name, 1, 1 if CPU_SAMPLE[name] * K < 5e6 else 0)
+    # the same sweep with the screening off (dense 3-pass E-step + dense tensor-core statistics): what overlapping
+    # components would cost; one warm-up + one timed sweep
+    dense = None
+    screen = None
+    vlb_tail = vlbs[-3:] if vlbs else None
+    if world == 1 and screened and E.sweep_uses_tensor_cores(s.ops(0), w['d']):
+        cands, fell_back = E.screen_last()
+        screen = dict(last_chunk_candidate_pairs=cands, last_chunk_dense_fallback=bool(fell_back))
+        if not args.no_dense:
+            old = E.set_tensor_cores(3)
+            try:
+                step(False)
+                torch.cuda.synchronize()
+                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                d0.record()
+                step(False)
+                d1.record()
+                torch.cuda.synchronize()
+                dms = d0.elapsed_time(d1)
+                dense = dict(value=w['N'] * K / (dms * 1e-3), unit='points*components/s', ms_per_step=dms, steps=1, warmup=1,
+                             tensor_frac=(sum(flops) / (dms * 1e-3) / 1e12) / peaks['tf_sus'],
+                             what='mimo_set_tensor_cores(3): dense 3-pass E-step and dense statistics on every chunk')
+            finally:
+                E.set_tensor_cores(old)
     posterior_launches = {'gmm': 4, 'dgmm': 3, 'ilr': 7}[w['kind']]
     line = dict(metric='points*components/s per full sweep', value=value, unit='points*components/s', n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='strong',
                 vs_baseline=None, dtype='f32', data='synthetic', config=config, roofline=roof, cpu_baseline=cpu, e2e=e2e,
                 gpu_launches=int(phase[3] + posterior_launches * args.steps), clocks=clocks,
-                lower_bound=vlbs[-3:] if vlbs else None,
+                lower_bound=vlb_tail, screen=screen, dense_path=dense,
                 comm=dict(messages=comm.messages, bytes_per_message=comm.bytes // max(comm.messages, 1)) if comm else None)
     print(json.dumps(line))
 

@@ -291,7 +291,7 @@ int mimo_mstep_lingauss(int K, int c, int o, int tied, const double* stat, int F
  * result is the statistics of utils/abstraction.py:12-14 summed over segments
  * (the reference's list-of-arrays semantics, gaussian.py:503-505).
  * mimo_sweep_host_set_segment: points per segment (rounded up to whole chunks;
- * 0 = automatic, about 1 GB of data).                                        */
+ * 0 = automatic, about 0.5 GB of data).                                        */
 int mimo_sweep_host_set_segment(int64_t points);
 int mimo_sweep_host(int dtype, int family, int hard,
                     const void* Z_host, int64_t N, int D,

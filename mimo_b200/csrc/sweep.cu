@@ -238,7 +238,7 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
     const size_t zb = (size_t)N * D * es;
     const size_t ab = (family == 0 ? (size_t)K * Rp * Dpp : (size_t)K * D) * es;
     const int64_t C = sweep_chunk_points(dtype, family, N, D, K, Rp);
-    const int64_t want = g_host_segment > 0 ? g_host_segment : (int64_t)(((size_t)1 << 30) / ((size_t)D * es));   // ~1 GB of data
+    const int64_t want = g_host_segment > 0 ? g_host_segment : (int64_t)(((size_t)1 << 29) / ((size_t)D * es));   // ~0.5 GB of data
     const int64_t seg = (want + C - 1) / C * C;                                                               // whole chunks
     const int n_seg = N > 0 ? (int)((N + seg - 1) / seg) : 0;
     const size_t wsb = sweep_workspace(dtype, family, hard, std::min<int64_t>(N, seg), D, K, Rp);

@@ -215,7 +215,7 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                 __syncwarp();
                 if (lane == 0) {                                 // straight to the leader's barrier (no relay hop)
                     if (rank == 0) mbar_arrive(&bars->tmem_empty[buf]);
-                    else mbar_arrive_remote(map_to_rank(smem_u32(&bars->tmem_empty[buf]), 0));
+                    else mbar_arrive_remote_nofence(map_to_rank(smem_u32(&bars->tmem_empty[buf]), 0));
                 }
                 t2_consume<RP, SCREEN>(v0, off_s, 0, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
                 t2_consume<RP, SCREEN>(v1, off_s, 32, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk);
