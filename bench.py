@@ -480,6 +480,10 @@ def main():
                 whole_sweep_frac=(sum(flops) / (ms * 1e-3) / 1e12) / peaks['tf_sus'] if bound == 'tensor'
                 else (n_local * work['bytes_pt'] / (ms * 1e-3) / 1e9) / peaks['hbm'])
 
+    screen = None
+    if screened and E.sweep_uses_tensor_cores(s.ops(0), w['d']):
+        cands, fell_back = E.screen_last()
+        screen = dict(last_chunk_candidate_pairs=cands, last_chunk_dense_fallback=bool(fell_back))
     # end-to-end through the host-buffer C-ABI call: pinned host data in, statistics out, every step
     e2e = None
     if not args.no_e2e and world == 1:
@@ -493,11 +497,8 @@ def main():
     # the same sweep with the screening off (dense 3-pass E-step + dense tensor-core statistics): what overlapping
     # components would cost; one warm-up + one timed sweep
     dense = None
-    screen = None
     vlb_tail = vlbs[-3:] if vlbs else None
     if world == 1 and screened and E.sweep_uses_tensor_cores(s.ops(0), w['d']):
-        cands, fell_back = E.screen_last()
-        screen = dict(last_chunk_candidate_pairs=cands, last_chunk_dense_fallback=bool(fell_back))
         if not args.no_dense:
             old = E.set_tensor_cores(3)
             try:

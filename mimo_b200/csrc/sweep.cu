@@ -295,6 +295,7 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
     };
     rc = body();
     if (rc != MIMO_OK) cudaDeviceSynchronize();
+    tc_screen_forget();                                   // its counters live in the workspace freed below
     for (auto e : landed) if (e) cudaEventDestroy(e);
     cudaFree(dZ); cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dws); cudaFree(dfi); cudaFree(dfj);
     cudaFree(dlab); cudaFree(dstat); cudaFree(dlse); cudaFree(duni);

@@ -424,6 +424,8 @@ void tc_screen_lists(void* ws, int64_t plan_points, int K, int which, const int3
 static const unsigned int* g_last_counters = nullptr;
 static int64_t g_last_points = 0;
 
+void tc_screen_forget() { g_last_counters = nullptr; g_last_points = 0; }   // the workspace the counters live in is going away
+
 // {candidates (guesses + list B), dense flag} of the most recent screened chunk (synchronises the device; tests / bench reporting)
 int tc_screen_last(unsigned int* out_host2) {
     out_host2[0] = out_host2[1] = 0u;

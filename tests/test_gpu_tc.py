@@ -246,3 +246,59 @@ def test_sweep_screened_estep(hard, K, d, N, sep):
         finally:
             E.set_tensor_cores(old)
         close(buf.stat, mid.stat.cpu().numpy(), 2e-5, 'pair-list vs dense statistics behind the screened E-step')
+
+
+def test_screened_sweep_large_properties():
+    """The sweep at a size the oracle cannot reach (N = 1.5 M, K = 256, d = 128: several point chunks of the tensor-core
+    path), checked through size-independent properties: responsibilities of every point sum to one (soft counts sum
+    to N), the statistics are additive over data shards (the reference's list-of-arrays semantics, gaussian.py:503-505),
+    the screened default path and the dense 3-pass path agree, and a Gibbs sweep's counts equal the label histogram."""
+    E = eng()
+    K, d, N = 256, 128, 1_500_000
+    g = torch.Generator(device='cuda')
+    g.manual_seed(11)
+    centres = 4.0 * torch.randn(K, d, generator=g, device='cuda')
+    z = torch.randint(0, K, (N,), generator=g, device='cuda')
+    Z = (centres[z] + torch.randn(N, d, generator=g, device='cuda')).contiguous()
+    rng = np.random.default_rng(3)
+    mus = centres.double().cpu().numpy() + 0.1 * rng.standard_normal((K, d))
+    lmbdas = np.stack([spd(rng, d) for _ in range(K)])
+    ops = E.QuadOperands(K, d, d, 'fp32')
+    E.set_log_weights(ops, np.log(rng.dirichlet(np.ones(K))))
+    E.operands_gauss(ops, E.to_dev(mus), E.to_dev(lmbdas)).check()
+    feats = E.quad_features(d)
+    buf = E.SweepBuffers(N, K, feats.F, 'fp32', False)
+    E.sweep(Z, ops, feats, buf)
+    cands, dense = E.screen_last()
+    assert dense == 0 and cands < 0.04 * N * K
+    stat = buf.stat.cpu().numpy()
+    counts = stat[:, -1]
+    assert abs(counts.sum() - N) <= 1e-6 * N
+    # additivity over two shards
+    h = N // 2 + 12345
+    tot = np.zeros_like(stat)
+    lse = 0.0
+    for lo, hi in ((0, h), (h, N)):
+        b = E.SweepBuffers(hi - lo, K, feats.F, 'fp32', False)
+        E.sweep(Z[lo:hi], ops, feats, b)
+        tot += b.stat.cpu().numpy()
+        lse += b.lse_sum.item()
+    close(tot, stat, 1e-6, 'statistics additive over shards')
+    assert abs(lse - buf.lse_sum.item()) <= 1e-7 * abs(lse)
+    # dense path
+    old = E.set_tensor_cores(3)
+    try:
+        ref = E.SweepBuffers(N, K, feats.F, 'fp32', False)
+        E.sweep(Z, ops, feats, ref)
+    finally:
+        E.set_tensor_cores(old)
+    close(stat, ref.stat.cpu().numpy(), 2e-5, 'screened vs dense statistics (large)')
+    assert abs(ref.lse_sum.item() - buf.lse_sum.item()) <= 1e-6 * abs(ref.lse_sum.item())
+    # Gibbs: counts == histogram of the drawn labels, labels independent of sharding (Philox keyed by global index)
+    bh = E.SweepBuffers(N, K, feats.F, 'fp32', True)
+    E.sweep(Z, ops, feats, bh, seed=99)
+    lab = bh.labels.cpu().numpy()
+    assert np.array_equal(bh.stat.cpu().numpy()[:, -1], np.bincount(lab, minlength=K))
+    b2 = E.SweepBuffers(N - h, K, feats.F, 'fp32', True)
+    E.sweep(Z[h:], ops, feats, b2, seed=99, offset=h)
+    assert (b2.labels.cpu().numpy() == lab[h:]).mean() > 0.9999
