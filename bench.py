@@ -432,6 +432,21 @@ def main():
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    screened = (args.tc_mode in (-1, 1, 4)) and w['kind'] == 'gmm' and w['d'] >= 24 and K >= 32 and not hard
+    screen = None
+    if rank == 0 and screened and E.sweep_uses_tensor_cores(s.ops(0), w['d']):
+        cands, fell_back = E.screen_last()
+        screen = dict(last_chunk_candidate_pairs=cands, last_chunk_dense_fallback=bool(fell_back))
+    # end-to-end through the host-buffer C-ABI call on every rank: pinned host shard in, statistics out (+ the
+    # all-reduce of the statistics when sharded), every step
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = time_e2e(w, s, E, _lib, hard, min(args.steps, 2), comm)
+        except Exception as ex:   # report, never fake
+            if world > 1:
+                raise
+            e2e = dict(value=None, unit='points*components/s', error=str(ex)[:200])
     if rank != 0:
         return
 
@@ -454,7 +469,6 @@ def main():
     else:
         ach = n_local * work['bytes_pt'] / (phase_ms[dom] * 1e-3) / 1e9 if phase_ms[dom] > 0 else 0.0
         roof = dict(bound='hbm', achieved=ach, peak=peaks['hbm'], unit='GB/s', frac=ach / peaks['hbm'], traffic=None)
-    screened = (args.tc_mode in (-1, 1, 4)) and w['kind'] == 'gmm' and w['d'] >= 24 and K >= 32 and not hard
     if name == 'cfg5' and not args.n_override:
         tr = ncu_traffic([('tc_estep2_screen_kernel' if screened else 'tc_estep2_kernel'), 'softmax_kernel',
                           ('pair_stats_kernel' if screened else 'tc_fstats_kernel')][dom])
@@ -480,17 +494,6 @@ def main():
                 whole_sweep_frac=(sum(flops) / (ms * 1e-3) / 1e12) / peaks['tf_sus'] if bound == 'tensor'
                 else (n_local * work['bytes_pt'] / (ms * 1e-3) / 1e9) / peaks['hbm'])
 
-    screen = None
-    if screened and E.sweep_uses_tensor_cores(s.ops(0), w['d']):
-        cands, fell_back = E.screen_last()
-        screen = dict(last_chunk_candidate_pairs=cands, last_chunk_dense_fallback=bool(fell_back))
-    # end-to-end through the host-buffer C-ABI call: pinned host data in, statistics out, every step
-    e2e = None
-    if not args.no_e2e and world == 1:
-        try:
-            e2e = time_e2e(w, s, E, _lib, hard, min(args.steps, 2))
-        except Exception as ex:   # report, never fake
-            e2e = dict(value=None, unit='points*components/s', error=str(ex)[:200])
     cpu = None
     if not args.no_cpu and world == 1:
         cpu, _ = time_cpu(w, name, 1, 1 if CPU_SAMPLE[name] * K < 5e6 else 0)
@@ -525,11 +528,14 @@ def main():
     print(json.dumps(line))
 
 
-def time_e2e(w, s, E, _lib, hard, steps):
-    """mimo_sweep_host: pinned host Z -> device, one sweep with the current operands, statistics +
-    lower-bound scalar (+ labels) back to the host.  Everything inside the timed region."""
+def time_e2e(w, s, E, _lib, hard, steps, comm=None):
+    """mimo_sweep_host on every rank: pinned host shard of Z -> device, one sweep with the current operands,
+    statistics + lower-bound scalar (+ labels) back to the host; when sharded, the all-reduce of the statistics
+    closes the step.  Everything inside the timed region; the step time is the max over ranks."""
     import torch
+    import torch.distributed as dist
     N, D = s.Z.shape
+    world = comm.world if comm is not None else 1
     ops = s.ops(1 if hard else 0)
     zh = torch.empty((N, D), dtype=torch.float32, pin_memory=True)
     zh.copy_(s.Z)
@@ -537,25 +543,39 @@ def time_e2e(w, s, E, _lib, hard, steps):
     ah = a.cpu().contiguous()
     bh = b.cpu().contiguous() if b is not None else None
     ch = ops.cst.cpu().contiguous()
-    stat_h = torch.zeros((s.K, s.F), dtype=torch.float64, pin_memory=True)
-    lse_h = torch.zeros((1,), dtype=torch.float64, pin_memory=True)
+    flat_h = torch.zeros((s.K * s.F + 1,), dtype=torch.float64, pin_memory=True)      # statistics | sum of lse
+    stat_h, lse_h = flat_h[:s.K * s.F], flat_h[s.K * s.F:]
+    flat_d = torch.empty_like(flat_h, device=s.Z.device) if world > 1 else None
     lab_h = torch.empty((N,), dtype=torch.int32, pin_memory=True) if hard else None
     fi, fj = s.feats.fi_host, s.feats.fj_host
     torch.cuda.synchronize()
-    # free the resident copy so the call's own device buffers fit next to it on big workloads
     times = []
     for it in range(steps + 1):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         _lib.call('mimo_sweep_host', 0, ops.family, 1 if hard else 0, zh.data_ptr(), N, D,
                   ah.data_ptr(), bh.data_ptr() if bh is not None else None, ch.data_ptr(), ops.K, ops.Rp, ops.Dpp,
                   fi.ctypes.data, fj.ctypes.data, s.F, None, 12345 + it,
                   stat_h.data_ptr(), lse_h.data_ptr(), lab_h.data_ptr() if lab_h is not None else None)
+        if world > 1:                                   # close the sweep: sum the shard statistics
+            flat_d.copy_(flat_h, non_blocking=True)
+            comm.allreduce(flat_d)
+            flat_h.copy_(flat_d, non_blocking=True)
+            torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
     dt = float(np.mean(times[1:]))
-    h2d = N * D * 4 + ah.numel() * 4 + (bh.numel() * 4 if bh is not None else 0) + ch.numel() * 4 + 2 * s.F * 4
-    d2h = s.K * s.F * 8 + 8 + (N * 4 if hard else 0)
-    return dict(value=N * s.K / dt, unit='points*components/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                ms_per_step=dt * 1e3, call='mimo_sweep_host (C-ABI, pinned host buffers)')
+    if world > 1:
+        t = torch.tensor([dt], device=s.Z.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    ops_b = ah.numel() * 4 + (bh.numel() * 4 if bh is not None else 0) + ch.numel() * 4 + 2 * s.F * 4
+    h2d = w['N'] * D * 4 + world * ops_b + (world * s.K * s.F * 8 if world > 1 else 0)
+    d2h = world * (s.K * s.F * 8 + 8) * (2 if world > 1 else 1) + (w['N'] * 4 if hard else 0)
+    return dict(value=w['N'] * s.K / dt, unit='points*components/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                ms_per_step=dt * 1e3, call='mimo_sweep_host (C-ABI, pinned host buffers) on every rank'
+                                           + (' + all-reduce of the statistics' if world > 1 else ''))
 
 
 if __name__ == '__main__':

@@ -36,6 +36,7 @@ constexpr float SCREEN_T0 = 40.f;
 constexpr int SCREEN_ROWS = 32;              // rows of the screening operands
 constexpr int RF_THREADS = 256;
 constexpr int RF_SPLIT = 8;                  // blocks per component
+constexpr int RF_CPT = 8;                    // candidates per thread (x 4 rows: 32 accumulators)
 
 // max_n ||z_n||_2: one warp per row (grid-stride)
 __global__ void screen_rownorm_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, unsigned int* __restrict__ flags) {
@@ -182,7 +183,7 @@ __global__ void screen_scatter_kernel(const int2* __restrict__ list, const unsig
 }
 
 // Exact (FP32 FMA) recomputation of the candidates of one component.  grid = (K, RF_SPLIT).
-// Thread (rg, cg): rows rg + RG r (r < 4), candidates 4 cg + c (c < 4) of a tile of TILE_C candidates.
+// Thread (rg, cg): rows rg + RG r (r < 4), candidates RF_CPT cg + c (c < RF_CPT) of a tile of TILE_C candidates.
 template <int RP>
 __global__ void __launch_bounds__(RF_THREADS)
 screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
@@ -190,7 +191,7 @@ screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
                      const int* __restrict__ perm, const int* __restrict__ offsets, const unsigned int* __restrict__ gate,
                      float* __restrict__ a, int64_t ldo, float* __restrict__ exact) {
     if (gate != nullptr && __ldg(gate) != 0u) return;          // dense second pass instead
-    constexpr int RG = RP / 4, CG = RF_THREADS / RG, TILE_C = 4 * CG;
+    constexpr int RG = RP / 4, CG = RF_THREADS / RG, TILE_C = RF_CPT * CG;
     const int k = blockIdx.x;
     const int beg = offsets[k], cnt = offsets[k + 1] - beg;
     const int tiles = (cnt + TILE_C - 1) / TILE_C;
@@ -227,21 +228,22 @@ screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
             }
         }
         __syncthreads();
-        float acc[4][4];
+        float acc[4][RF_CPT];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+            for (int c = 0; c < RF_CPT; ++c) acc[r][c] = 0.f;
+#pragma unroll 2
         for (int j = 0; j < Dpp; j += 4) {
-            float4 w[4], z[4];
+            float4 w[4], z[RF_CPT];
 #pragma unroll
             for (int r = 0; r < 4; ++r) w[r] = *reinterpret_cast<const float4*>(Ws + (size_t)(rg + RG * r) * Dpp + j);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) z[c] = *reinterpret_cast<const float4*>(Zs + (size_t)(4 * cg + c) * Dpp + j);
+            for (int c = 0; c < RF_CPT; ++c) z[c] = *reinterpret_cast<const float4*>(Zs + (size_t)(RF_CPT * cg + c) * Dpp + j);
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < RF_CPT; ++c) {
                     acc[r][c] = fmaf(w[r].x, z[c].x, acc[r][c]);
                     acc[r][c] = fmaf(w[r].y, z[c].y, acc[r][c]);
                     acc[r][c] = fmaf(w[r].z, z[c].z, acc[r][c]);
@@ -249,13 +251,13 @@ screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
                 }
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < RF_CPT; ++c) {
             float q = 0.f;
 #pragma unroll
             for (int r = 0; r < 4; ++r) q = fmaf(acc[r][c], acc[r][c], q);
 #pragma unroll
             for (int o = RG / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);    // over the RG lanes of this candidate group
-            const int ci = 4 * cg + c;
+            const int ci = RF_CPT * cg + c;
             if (rg == 0 && ci < nc) {
                 const int n = perm[c0 + ci];
                 const float val = ck - 0.5f * q;
@@ -440,7 +442,7 @@ template <int RP>
 static int launch_refine(const float* Z, int D, int64_t ldz, const float* W, int K, int Dpp, const float* cst,
                          const int* perm, const int* offsets, const unsigned int* gate, float* a, int64_t ldo, float* exact,
                          cudaStream_t st) {
-    constexpr int TILE_C = 4 * (RF_THREADS / (RP / 4));
+    constexpr int TILE_C = RF_CPT * (RF_THREADS / (RP / 4));
     const size_t smem = (size_t)(RP + TILE_C) * Dpp * sizeof(float);
     const int vec4 = (D % 4 == 0) && (Dpp % 4 == 0) && (ldz % 4 == 0) && (((uintptr_t)Z & 15) == 0);
     MIMO_CUDA(cudaFuncSetAttribute(screen_refine_kernel<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
