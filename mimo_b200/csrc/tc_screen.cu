@@ -126,12 +126,12 @@ screen_emit_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, c
     const float t = valid ? lower[i] - SCREEN_T0 - 0.01f * (1.f + 1e-4f * fabsf(lower[i])) : INFINITY;   // FP32 slack of the exact value
     const int gk = valid ? guess_k[i] : -1;
     const int lane = threadIdx.x & 31;
-    for (int k0 = 0; k0 < K; k0 += 4) {
-      float av[4];
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      float av[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) av[u] = (valid && k0 + u < K) ? a[(int64_t)(k0 + u) * ldo + i] : 0.f;   // 4 loads in flight
+      for (int u = 0; u < 8; ++u) av[u] = (valid && k0 + u < K) ? __ldcs(a + (int64_t)(k0 + u) * ldo + i) : 0.f;   // 8 streaming loads in flight
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int k = k0 + u;
         if (k >= K) break;
         bool cand = false;
