@@ -29,6 +29,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep stdout to the one JSON line (NCCL prints its version banner there)
 
 WORKLOADS = {
     # name: family, N, d (or d_in), o, K, mode
@@ -385,7 +386,7 @@ def main():
     if comm is not None:
         comm.allreduce(s.stat)
     del true_labels
-    phase = np.zeros(5)
+    phase = np.zeros(6)
     vlbs = []
 
     def step(timed):
@@ -409,7 +410,7 @@ def main():
             ops, outs = s.update_from_stats(MEANFIELD); torch.cuda.synchronize(); t.append(time.perf_counter())
             s.sweep(ops, hard=False); torch.cuda.synchronize(); t.append(time.perf_counter())
             s.lower_bound(outs); t.append(time.perf_counter())
-            ph = np.zeros(5)
+            ph = np.zeros(6)
             s.sweep(ops, hard=False, phase_ms=ph); torch.cuda.synchronize(); t.append(time.perf_counter())
             sys.stderr.write('DEBUG update %.2f ms | sweep %.2f ms | vlb %.2f ms | timed sweep %.2f ms phases %s\n'
                              % tuple([1e3 * (t[i + 1] - t[i]) for i in range(4)] + [ph.tolist()]))
@@ -487,8 +488,17 @@ def main():
                         'nats of a point\'s best component are recomputed in FP32, statistics are summed over those pairs only, so '
                         'frac can exceed 1; `dense_path` is the same sweep with screening off (3-pass dense tensor-core kernels)'
                         if screened else 'dense 3-pass tensor-core path')
-    roof.update(kernel=['E-step (log-likelihood)', 'softmax / label draw', 'sufficient statistics'][dom],
-                launches_per_step=launches_per_step, ms_per_launch=phase_ms[dom] / max(launches_per_step, 1),
+    if dom == 0 and bound == 'tensor' and phase[5] > 0:
+        # the dominant KERNEL of the E-step phase (on the screened path: the screening pass; the rest of the phase is list
+        # building and refinement): algorithmic E-step flops / its own launch time
+        kms = phase[5] / args.steps
+        roof['achieved'] = flops[0] / (kms * 1e-3) / 1e12
+        roof['frac'] = roof['achieved'] / peaks['tf_sus']
+        roof['kernel_ms_per_step'] = kms
+    roof.update(kernel=[('E-step: tc_estep2_kernel<.,32,1> screening pass' if screened else 'E-step (log-likelihood)'),
+                        'softmax / label draw', 'sufficient statistics'][dom],
+                launches_per_step=launches_per_step,
+                ms_per_launch=(phase[5] / args.steps if (dom == 0 and phase[5] > 0) else phase_ms[dom]) / max(launches_per_step, 1),
                 phase_ms_per_step=dict(estep=phase_ms[0], softmax=phase_ms[1], stats=phase_ms[2]),
                 peak_source='%s (sustained bf16 / copy bandwidth of MEASURED_PEAKS.json)' % peaks['src'],
                 whole_sweep_frac=(sum(flops) / (ms * 1e-3) / 1e12) / peaks['tf_sus'] if bound == 'tensor'

@@ -163,7 +163,9 @@ int mimo_sweep(int dtype, int family, int hard,
  * `stream` around every launch; on return (this variant synchronises) phase_ms_host[0..2]
  * have been incremented by the milliseconds spent in the E-step, softmax / label and
  * statistics kernels, phase_ms_host[3] by the number of kernel launches and
- * phase_ms_host[4] by the number of point chunks (= launches of each per-chunk kernel).  */
+ * phase_ms_host[4] by the number of point chunks (= launches of each per-chunk kernel) and
+ * phase_ms_host[5] by the device time of the dominant E-step kernel alone (the screening pass on
+ * the screened path; equal to phase 0 otherwise).  phase_ms_host holds 6 doubles.               */
 int mimo_sweep_timed(int dtype, int family, int hard,
                      const void* Z, int64_t N, int D, int64_t ldz,
                      const void* op_a, const void* op_b, const void* cst, int K, int Rp, int Dpp,

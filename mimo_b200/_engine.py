@@ -257,7 +257,7 @@ class SweepBuffers:
 def sweep(Z, ops, feats, buf, uniforms=None, seed=0, offset=0, ll_out=None, lse_out=None, zero=True,
           phase_ms=None):
     """One E-step + statistics pass over resident Z.  Results land in buf.stat,
-    buf.lse_sum and (hard) buf.labels.  phase_ms: optional float64 numpy array (5,) that
+    buf.lse_sum and (hard) buf.labels.  phase_ms: optional float64 numpy array (6,) that
     accumulates per-phase device milliseconds, the launch count and the chunk count (synchronises)."""
     N, D = Z.shape
     fi, fj = feats.dev()
@@ -274,7 +274,7 @@ def sweep(Z, ops, feats, buf, uniforms=None, seed=0, offset=0, ll_out=None, lse_
     if phase_ms is None:
         _lib.call('mimo_sweep', *args)
     else:
-        assert phase_ms.dtype == np.float64 and phase_ms.size >= 5
+        assert phase_ms.dtype == np.float64 and phase_ms.size >= 6
         _lib.call('mimo_sweep_timed', *args, phase_ms.ctypes.data)
     return buf
 

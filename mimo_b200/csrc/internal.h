@@ -15,7 +15,8 @@ int softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags, void* 
             const unsigned int* gate = nullptr, unsigned int gate_value = 0u);
 
 int stats_soft(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K,
-               const int32_t* fi, const int32_t* fj, int F, double* stat, cudaStream_t st);
+               const int32_t* fi, const int32_t* fj, int F, double* stat, cudaStream_t st,
+               const unsigned int* gate = nullptr, unsigned int gate_value = 0u);
 size_t stats_hard_workspace(int64_t N, int K);
 int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const int32_t* labels, int K,
                const int32_t* fi, const int32_t* fj, int F, double* stat,
@@ -88,6 +89,12 @@ bool pair_stats_supported(int dtype, int D, int F);
 int pair_stats(const float* Z, int D, int64_t ldz, const int32_t* perm, const int32_t* offsets, const int32_t* slabs, int K,
                const float* R, int64_t ldr, const float* lse, const unsigned int* gate, unsigned int gate_value,
                double* stat, int F, cudaStream_t st);
+
+// responsibility lists of the CUDA-core path (tc_screen.cu)
+size_t resp_list_workspace(int64_t chunk_points, int K);
+int resp_list_build(const float* R, int K, int64_t n, int64_t ldr, int64_t plan_points, void* ws, cudaStream_t st);
+const unsigned int* resp_list_gate(void* ws, int64_t plan_points, int K);
+void resp_list_get(void* ws, int64_t plan_points, int K, const int32_t** perm, const int32_t** offsets, const int32_t** slabs);
 
 bool sweep_uses_tc(int dtype, int family, int D, int Rp);
 int64_t sweep_chunk_points(int dtype, int family, int64_t N, int D, int K, int Rp);

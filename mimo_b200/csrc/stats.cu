@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(SS_THREADS)
 stats_soft_kernel(const T* __restrict__ Z, int64_t N, int D, int64_t ldz,
                   const T* __restrict__ resp, int64_t ldr, int K,
                   const int32_t* __restrict__ fi, const int32_t* __restrict__ fj, int F,
-                  double* __restrict__ stat, int64_t slab) {
+                  double* __restrict__ stat, int64_t slab, const unsigned int* __restrict__ gate, unsigned int gate_value) {
+    if (gate != nullptr && *gate != gate_value) return;          // the pair-list statistics ran instead
     constexpr int AS = SS_BK + 4, BS = SS_BF + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ZTS = D + 2;                                   // zt row stride
@@ -114,7 +115,8 @@ stats_soft_kernel(const T* __restrict__ Z, int64_t N, int D, int64_t ldz,
 }
 
 int stats_soft(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K,
-               const int32_t* fi, const int32_t* fj, int F, double* stat, cudaStream_t st) {
+               const int32_t* fi, const int32_t* fj, int F, double* stat, cudaStream_t st,
+               const unsigned int* gate, unsigned int gate_value) {
     MIMO_CHECK_ARG(dtype == MIMO_F32 || dtype == MIMO_F64, "dtype");
     MIMO_CHECK_ARG(Z && resp && fi && fj && stat, "null pointer");
     MIMO_CHECK_ARG(N >= 0 && D >= 1 && K >= 1 && F >= 1 && ldz >= D && ldr >= N, "shape");
@@ -132,11 +134,11 @@ int stats_soft(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const vo
     if (dtype == MIMO_F32) {
         auto kern = stats_soft_kernel<float>;
         MIMO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, SS_THREADS, smem, st>>>((const float*)Z, N, D, ldz, (const float*)resp, ldr, K, fi, fj, F, stat, slab);
+        kern<<<grid, SS_THREADS, smem, st>>>((const float*)Z, N, D, ldz, (const float*)resp, ldr, K, fi, fj, F, stat, slab, gate, gate_value);
     } else {
         auto kern = stats_soft_kernel<double>;
         MIMO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, SS_THREADS, smem, st>>>((const double*)Z, N, D, ldz, (const double*)resp, ldr, K, fi, fj, F, stat, slab);
+        kern<<<grid, SS_THREADS, smem, st>>>((const double*)Z, N, D, ldz, (const double*)resp, ldr, K, fi, fj, F, stat, slab, gate, gate_value);
     }
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;

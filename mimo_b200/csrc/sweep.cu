@@ -26,6 +26,11 @@ static bool sweep_uses_screen(int dtype, int family, int D, int K, int Rp) {
     return (g_tc_mode == 1 || g_tc_mode == 4) && K >= 32 && sweep_uses_tc(dtype, family, D, Rp) && tc_screen_supported(D, Rp);
 }
 
+// CUDA-core quad path in FP32: statistics over the list of pairs with a non-negligible responsibility (pair_stats.cu)
+static bool sweep_uses_resp_list(int dtype, int family, int hard, int D, int K, int Rp) {
+    return g_tc_mode == 1 && !hard && family == 0 && dtype == MIMO_F32 && D >= 8 && K >= 8 && !sweep_uses_tc(dtype, family, D, Rp);
+}
+
 // points per chunk.
 //  CUDA-core path: keep the (K, chunk) scratch around 64 MB (half of the 126 MB L2) so the softmax /
 //    statistics passes over it are served from L2.
@@ -56,6 +61,7 @@ size_t sweep_workspace(int dtype, int family, int hard, int64_t N, int D, int K,
     size_t b = a256((size_t)K * c * es);
     // Gibbs: labels of ALL points (when the caller does not keep them) + one counting sort over N
     if (hard) b += a256((size_t)N * 4) + a256(stats_hard_workspace(N, K));
+    if (sweep_uses_resp_list(dtype, family, hard, D, K, Rp)) b += a256(resp_list_workspace(c, K));
     if (sweep_uses_tc(dtype, family, D, Rp)) {
         b += a256(tc_operand_workspace(K, Rp, D));
         if (sweep_uses_screen(dtype, family, D, K, Rp)) b += a256(tc_screen_workspace(c, K)) + a256(tc_screen_operand_workspace(K, Rp, D + 4, D));
@@ -86,6 +92,9 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     void* hard_ws = ws;
     const size_t hard_ws_bytes = hard ? stats_hard_workspace(N, K) : 0;
     if (hard) ws += a256(hard_ws_bytes);
+    void* resp_ws = nullptr;
+    const bool resp_list = stat && sweep_uses_resp_list(dtype, family, hard, D, K, Rp) && pair_stats_supported(dtype, D, F);
+    if (sweep_uses_resp_list(dtype, family, hard, D, K, Rp)) { resp_ws = ws; ws += a256(resp_list_workspace(C, K)); }
     void* tc_ops_ws = nullptr;
     void* tc_stat_ws = nullptr;
     void* screen_ws = nullptr;
@@ -117,7 +126,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     }
 
     // optional per-phase device timing (bench.py's roofline leg): events on the launching stream
-    std::vector<cudaEvent_t> ev;
+    std::vector<cudaEvent_t> ev, evk;
     auto mark = [&]() { if (phase_ms) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); } };
     for (int64_t n0 = 0; n0 < N; n0 += C) {
         const int64_t nc = (N - n0 < C) ? (N - n0) : C;
@@ -130,6 +139,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             // candidates) the dense 3-pass kernel
             rc = tc_screen_pass((const float*)Zc, nc, D, ldz, K, Rp, Dpp, (float*)scratch, C, tc_ops_ws, screen_ops_ws, C, screen_ws, st);
             if (rc) return rc;
+            if (phase_ms) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); evk.push_back(e); }   // end of the screening kernel
             rc = tc_screen_select((const float*)Zc, D, ldz, (const float*)op_a, (const float*)cst, K, Rp, Dpp, (float*)scratch, nc, C,
                                   tc_ops_ws, screen_ops_ws, C, screen_ws, st);
             if (rc) return rc;
@@ -175,7 +185,17 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
                            : tc_stats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, F, tc_maxbits(tc_ops_ws), stat, C, tc_stat_ws, st, sgate, 1u);
             if (rc) return rc;
         } else if (stat && !hard) {
-            rc = stats_soft(dtype, Zc, nc, D, ldz, scratch, C, K, fi, fj, F, stat, st);
+            const unsigned int* rgate = nullptr;
+            if (resp_list) {                                   // pairs with r >= e^-40, grouped by component
+                rc = resp_list_build((const float*)scratch, K, nc, C, C, resp_ws, st);
+                if (rc) return rc;
+                rgate = resp_list_gate(resp_ws, C, K);
+                const int32_t *perm, *offsets, *slabs;
+                resp_list_get(resp_ws, C, K, &perm, &offsets, &slabs);
+                rc = pair_stats((const float*)Zc, D, ldz, perm, offsets, slabs, K, (const float*)scratch, C, nullptr, rgate, 0u, stat, F, st);
+                if (rc) return rc;
+            }
+            rc = stats_soft(dtype, Zc, nc, D, ldz, scratch, C, K, fi, fj, F, stat, st, rgate, 1u);
             if (rc) return rc;
         }
         mark();
@@ -200,11 +220,17 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, ev[i + ph], ev[i + ph + 1]);
                 phase_ms[ph] += ms;
+                if (ph == 0 && evk.empty()) phase_ms[5] += ms;            // the E-step phase is one kernel
+            }
+            if (!evk.empty()) {                                           // the screening kernel alone
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[i], evk[i / 4]);
+                phase_ms[5] += ms;
             }
             // kernel launches of this chunk: E-step (+ offsets blocks for the CTA-pair kernel), softmax,
             // statistics (feature form: data image + responsibility image + GEMM)
             phase_ms[3] += 2.0 + (use_screen ? 10.0 : 0.0)
-                         + ((hard || !stat) ? 0.0 : (tc_fstats ? 3.0 : 1.0)) + (pair_stats_list ? 2.0 : 0.0) + (list_softmax ? 4.0 : 0.0);
+                         + ((hard || !stat) ? 0.0 : (tc_fstats ? 3.0 : 1.0)) + (pair_stats_list ? 2.0 : 0.0) + (list_softmax ? 4.0 : 0.0) + (resp_list ? 4.0 : 0.0);
         }
         if (h0) {
             float ms = 0.f;
@@ -216,6 +242,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         if (use_tc) phase_ms[3] += 3.0 + (tc_stats ? 1.0 : 0.0) + (use_screen ? 6.0 : 0.0);   // data scale, operand image + offsets, norms, statistics fold
         phase_ms[4] += (double)((N + C - 1) / C);                      // point chunks
         for (auto e : ev) cudaEventDestroy(e);
+        for (auto e : evk) cudaEventDestroy(e);
     }
     return MIMO_OK;
 }

@@ -39,13 +39,22 @@ struct TeBarriers {
     uint32_t tmem_base;
 };
 
-__global__ void tc_absmax_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, unsigned int* __restrict__ maxbits) {
+__global__ void tc_absmax_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int flat4, unsigned int* __restrict__ maxbits) {
     float m = 0.f;
     const int64_t total = N * (int64_t)D;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        int64_t n = idx / D;
-        int j = (int)(idx - n * D);
-        m = fmaxf(m, fabsf(Z[n * ldz + j]));
+    if (flat4) {                     // contiguous rows, 16-byte aligned: a flat stream of float4
+        const float4* z4 = reinterpret_cast<const float4*>(Z);
+        const int64_t t4 = total >> 2;
+        for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < t4; idx += (int64_t)gridDim.x * blockDim.x) {
+            const float4 v = __ldg(z4 + idx);
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        }
+    } else {
+        for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+            int64_t n = idx / D;
+            int j = (int)(idx - n * D);
+            m = fmaxf(m, fabsf(Z[n * ldz + j]));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -333,7 +342,8 @@ int tc_data_scale(const float* Z, int64_t N, int D, int64_t ldz, void* ws, cudaS
     if (N > 0) {
         int64_t total = N * (int64_t)D;
         int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
-        tc_absmax_kernel<<<grid, 256, 0, st>>>(Z, N, D, ldz, (unsigned int*)base);
+        const int flat4 = (ldz == D) && (total % 4 == 0) && (((uintptr_t)Z & 15) == 0);
+        tc_absmax_kernel<<<grid, 256, 0, st>>>(Z, N, D, ldz, flat4, (unsigned int*)base);
         MIMO_LAUNCH_CHECK();
     }
     return MIMO_OK;

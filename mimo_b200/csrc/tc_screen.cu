@@ -522,4 +522,84 @@ const float* tc_screen_lse_values(void* ws, int64_t plan_points, int K) {
     return (const float*)(align256(ws) + screen_layout(plan_points, K).off_lse);
 }
 
+
+// ---- responsibility lists for the CUDA-core path (small D) ---------------------------------------------
+// After the dense softmax of a chunk the responsibilities of most pairs are (next to) zero once components are
+// separated.  The pairs with r >= e^-40 are listed, grouped by component, and the statistics summed over the list
+// (pair_stats.cu); the dropped mass is < N e^-40 per component.  Dense CUDA-core statistics (stats.cu) when more
+// than RL_MAX_FRAC of the pairs qualify -- the same device-side flag mechanism as above.
+constexpr float RL_TAU = 4.2e-18f;           // e^-40
+constexpr double RL_MAX_FRAC = 0.15;
+
+__global__ void __launch_bounds__(256)
+resp_emit_kernel(const float* __restrict__ r, int K, int64_t n, int64_t ldr, int2* __restrict__ list, unsigned int cap,
+                 unsigned int* __restrict__ counters, int* __restrict__ hist) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const int lane = threadIdx.x & 31;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        float rv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rv[u] = (valid && k0 + u < K) ? r[(int64_t)(k0 + u) * ldr + i] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u;
+            if (k >= K) break;
+            const bool cand = rv[u] >= RL_TAU;
+            const unsigned int m = __ballot_sync(0xffffffffu, cand);
+            if (m) {
+                unsigned int base = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) { base = atomicAdd(counters, (unsigned int)__popc(m)); atomicAdd(hist + k, __popc(m)); }
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (cand) {
+                    const unsigned int slot = base + __popc(m & ((1u << lane) - 1u));
+                    if (slot < cap) list[slot] = make_int2(k, (int)i);
+                }
+            }
+        }
+    }
+}
+
+struct RespListLayout { unsigned int cap; size_t off_counters, hist, offsets, cursor, slabs, list, perm, bytes; };
+static RespListLayout resp_list_layout(int64_t chunk_points, int K) {
+    RespListLayout L;
+    L.cap = (unsigned int)std::min<double>(2.0e9, (RL_MAX_FRAC + 0.01) * (double)chunk_points * K + 1024.0);
+    const size_t kk = a256((size_t)(K + 1) * 4);
+    size_t o = 0;
+    L.off_counters = o; o += 256;
+    L.hist = o; o += kk;
+    L.offsets = o; o += kk;  L.cursor = o; o += kk;  L.slabs = o; o += kk;
+    L.list = o; o += a256((size_t)L.cap * 8);
+    L.perm = o; o += a256((size_t)L.cap * 4);
+    L.bytes = o;
+    return L;
+}
+size_t resp_list_workspace(int64_t chunk_points, int K) { return resp_list_layout(chunk_points, K).bytes + 256; }
+
+// lists of the chunk's responsibilities R (K, n); sets the dense flag *resp_list_gate() when the list is too long
+int resp_list_build(const float* R, int K, int64_t n, int64_t ldr, int64_t plan_points, void* ws, cudaStream_t st) {
+    RespListLayout L = resp_list_layout(plan_points, K);
+    char* base = align256(ws);
+    unsigned int* counters = (unsigned int*)(base + L.off_counters);
+    MIMO_CUDA(cudaMemsetAsync(base, 0, L.offsets, st));                     // counters + histogram
+    resp_emit_kernel<<<cdiv(n, 256), 256, 0, st>>>(R, K, n, ldr, (int2*)(base + L.list), L.cap, counters, (int*)(base + L.hist));
+    const double maxc = std::min<double>((double)L.cap, RL_MAX_FRAC * (double)n * K);
+    screen_scan_kernel<<<1, 32, 0, st>>>((const int*)(base + L.hist), K, (int*)(base + L.offsets), (int*)(base + L.cursor),
+                                         (int*)(base + L.slabs), counters, (unsigned int)maxc);
+    screen_scatter_kernel<<<sm_count() * 4, 256, 0, st>>>((const int2*)(base + L.list), counters, (int*)(base + L.cursor), (int*)(base + L.perm));
+    MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
+}
+const unsigned int* resp_list_gate(void* ws, int64_t plan_points, int K) {
+    return (const unsigned int*)(align256(ws) + resp_list_layout(plan_points, K).off_counters) + 1;
+}
+void resp_list_get(void* ws, int64_t plan_points, int K, const int32_t** perm, const int32_t** offsets, const int32_t** slabs) {
+    RespListLayout L = resp_list_layout(plan_points, K);
+    char* base = align256(ws);
+    *perm = (const int32_t*)(base + L.perm);
+    *offsets = (const int32_t*)(base + L.offsets);
+    *slabs = (const int32_t*)(base + L.slabs);
+}
+
 }  // namespace mimo

@@ -524,3 +524,40 @@ def test_sweep_host_matches_resident_sweep(hard, K, d, N, segment):
             assert np.array_equal(lab_h, ref)
         else:   # tensor-core path: the FP16-split scale is per segment, draws on a CDF boundary may move
             assert (lab_h == ref).mean() > 0.9995
+
+
+@pytest.mark.parametrize('K,d,N,sep', [(20, 16, 60000, 6.0), (20, 16, 30000, 0.2), (130, 9, 40000, 3.0), (8, 8, 5000, 5.0)])
+def test_sweep_resp_list_statistics(K, d, N, sep):
+    """CUDA-core FP32 sweep, 8 <= d < 24: statistics summed over the pairs with r >= e^-40 (pair-list kernel) when
+    they are few, dense CUDA-core statistics otherwise (device-side choice).  Both must match the plain dense sweep
+    (mimo_set_tensor_cores(0)) and the oracle (gaussian.py:491-505)."""
+    E = eng()
+    rng = np.random.default_rng(K * d)
+    centres = sep * rng.standard_normal((K, d))
+    z = rng.integers(0, K, size=N)
+    x = centres[z] + rng.standard_normal((N, d))
+    mus = centres + 0.1 * rng.standard_normal((K, d))
+    lmbdas = np.stack([spd(rng, d) for _ in range(K)])
+    logw = np.log(rng.dirichlet(np.ones(K)))
+    ops = E.QuadOperands(K, d, d, 'fp32')
+    E.set_log_weights(ops, logw)
+    E.operands_gauss(ops, E.to_dev(mus), E.to_dev(lmbdas)).check()
+    Z = E.to_dev(x, torch.float32)
+    feats = E.quad_features(d)
+    buf = E.SweepBuffers(N, K, feats.F, 'fp32', False)
+    E.sweep(Z, ops, feats, buf)
+    old = E.set_tensor_cores(0)
+    try:
+        ref = E.SweepBuffers(N, K, feats.F, 'fp32', False)
+        E.sweep(Z, ops, feats, ref)
+    finally:
+        E.set_tensor_cores(old)
+    close(buf.stat, ref.stat.cpu().numpy(), 1e-5, 'list vs dense statistics')
+    close(buf.lse_sum, ref.lse_sum.cpu().numpy(), 1e-9, 'lse sum')
+    xr = Z.double().cpu().numpy()
+    resp, lse = orc.responsibilities(orc.gauss_full_loglik(xr, mus, lmbdas) + logw[:, None])
+    st = orc.gauss_full_wstats(xr, resp)
+    S = unpack_quad(buf.stat.cpu().numpy(), d)
+    close(S[:, :d, :d], st[2], 1e-4, 'sum r xx')
+    close(S[:, d, :d], st[0], 1e-4, 'sum r x')
+    close(S[:, d, d], st[1], 1e-4, 'sum r')
