@@ -102,7 +102,9 @@ int mimo_softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags,
  * pairs + exact recomputation of the pairs within 40 nats of a point's best component, or -- device-side choice
  * when more than 4 % of the pairs qualify -- the dense 3-pass kernel) and, for mean-field sweeps, the statistics
  * summed over those candidate pairs only (pair-list kernel; the dense tensor-core statistics on fallback chunks);
- * 2: single-CTA dense kernels; 3: CTA pairs, dense; 4: as 1 with dense statistics.  Returns the old mode. */
+ * 2: single-CTA dense kernels; 3: CTA pairs, dense; 4: as 1 with dense statistics; 5: as 1 with the screening
+ * starting on its second tier (all operand rows in one FP16 pass instead of the 32-row projection -- the tier a sweep
+ * moves to by itself when the projection leaves too many candidates).  Returns the old mode. */
 int mimo_set_tensor_cores(int mode);
 /* {candidate pairs, dense-fallback flag} of the most recent screened point chunk (synchronises; diagnostics) */
 int mimo_tc_screen_last(uint32_t* out_host2);

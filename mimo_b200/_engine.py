@@ -439,7 +439,8 @@ def mstep_lingauss(stat, F, stat_idx, Dp, K, c, o, tied=False, info=None):
 # ---- tensor-core variants (stand-alone entry points; mimo_sweep dispatches by itself) ---------------
 def set_tensor_cores(mode):
     """0: CUDA-core kernels only; 1 (default): tcgen05 kernels on CTA pairs with the screened E-step;
-    2: single-CTA dense tcgen05 kernels; 3: CTA pairs, dense E-step; 4: as 1 with dense statistics.  Returns the old mode."""
+    2: single-CTA dense tcgen05 kernels; 3: CTA pairs, dense E-step; 4: as 1 with dense statistics;
+    5: as 1 with the screening starting on its all-rows tier.  Returns the old mode."""
     return _lib.load().mimo_set_tensor_cores(int(mode))
 
 

@@ -23,7 +23,7 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
                void* workspace, size_t workspace_bytes, bool check, cudaStream_t st);
 
 // tensor-core (tcgen05) path, FP32 quad family, D <= 128  (tc_estep.cu, tc_stats.cu)
-int tc_mode();                       // 0 CUDA cores only; 1 tensor cores: CTA pairs + screened E-step + pair-list statistics (default); 2 single-CTA dense; 3 CTA pairs dense; 4 as 1 with dense statistics
+int tc_mode();                       // 0 CUDA cores only; 1 tensor cores: CTA pairs + screened E-step + pair-list statistics (default); 2 single-CTA dense; 3 CTA pairs dense; 4 as 1 with dense statistics; 5 as 1, screening starts on the all-rows tier
 int tc_set_mode(int mode);
 bool tc_estep_supported(int dtype, int D, int Rp);
 size_t tc_operand_workspace(int K, int Rp, int D);
@@ -42,6 +42,7 @@ int tc_screen_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float
                       void* ops_ws, void* sops_ws, cudaStream_t st);
 int tc_screen_pass(const float* Z, int64_t n, int D, int64_t ldz, int K, int Rp, int Dpp, float* out, int64_t ldo,
                    void* ops_ws, void* sops_ws, int64_t plan_points, void* ws, cudaStream_t st);
+int tc_screen_begin(int64_t plan_points, int K, int Rp, int start_level, void* ws, cudaStream_t st);
 const unsigned int* tc_screen_gate(void* ws, int64_t plan_points, int K);
 int tc_screen_last(unsigned int* out_host2);
 void tc_screen_forget();
@@ -92,7 +93,7 @@ int pair_stats(const float* Z, int D, int64_t ldz, const int32_t* perm, const in
 
 // responsibility lists of the CUDA-core path (tc_screen.cu)
 size_t resp_list_workspace(int64_t chunk_points, int K);
-int resp_list_build(const float* R, int K, int64_t n, int64_t ldr, int64_t plan_points, void* ws, cudaStream_t st);
+int resp_list_build(const float* R, int K, int64_t n, int64_t ldr, int D, int64_t plan_points, void* ws, cudaStream_t st);
 const unsigned int* resp_list_gate(void* ws, int64_t plan_points, int K);
 void resp_list_get(void* ws, int64_t plan_points, int K, const int32_t** perm, const int32_t** offsets, const int32_t** slabs);
 

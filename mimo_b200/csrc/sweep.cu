@@ -6,6 +6,8 @@
 #include "common.cuh"
 #include "internal.h"
 #include <vector>
+#include <chrono>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace mimo {
@@ -14,7 +16,7 @@ static size_t a256(size_t x) { return (x + 255) / 256 * 256; }
 
 static int g_tc_mode = 1;
 int tc_mode() { return g_tc_mode; }
-int tc_set_mode(int mode) { int old = g_tc_mode; g_tc_mode = (mode < 0 || mode > 4) ? 1 : mode; return old; }
+int tc_set_mode(int mode) { int old = g_tc_mode; g_tc_mode = (mode < 0 || mode > 5) ? 1 : mode; return old; }
 
 // the tensor-core path takes FP32 quad-family sweeps whose contraction is wide enough to pay for
 // the 64-wide K blocks of the operand layout
@@ -23,12 +25,12 @@ bool sweep_uses_tc(int dtype, int family, int D, int Rp) {
 }
 // screened E-step: worth it when a point's candidates (>= 1) can stay below 4 % of the K components
 static bool sweep_uses_screen(int dtype, int family, int D, int K, int Rp) {
-    return (g_tc_mode == 1 || g_tc_mode == 4) && K >= 32 && sweep_uses_tc(dtype, family, D, Rp) && tc_screen_supported(D, Rp);
+    return (g_tc_mode == 1 || g_tc_mode == 4 || g_tc_mode == 5) && K >= 32 && sweep_uses_tc(dtype, family, D, Rp) && tc_screen_supported(D, Rp);
 }
 
 // CUDA-core quad path in FP32: statistics over the list of pairs with a non-negligible responsibility (pair_stats.cu)
 static bool sweep_uses_resp_list(int dtype, int family, int hard, int D, int K, int Rp) {
-    return g_tc_mode == 1 && !hard && family == 0 && dtype == MIMO_F32 && D >= 8 && K >= 8 && !sweep_uses_tc(dtype, family, D, Rp);
+    return (g_tc_mode == 1 || g_tc_mode == 5) && !hard && family == 0 && dtype == MIMO_F32 && D >= 8 && K >= 8 && !sweep_uses_tc(dtype, family, D, Rp);
 }
 
 // points per chunk.
@@ -104,7 +106,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     // the packed full-triangle statistics are what the tensor-core statistics kernel produces
     const bool tc_stats = use_tc && stat && !hard && tc_stats_supported(dtype, D, F);
     const bool tc_fstats = tc_stats && tc_fstats_supported(dtype, D, F);     // feature form (folded triangle) for D > 64
-    const bool pair_stats_list = tc_stats && use_screen && g_tc_mode == 1 && pair_stats_supported(dtype, D, F);
+    const bool pair_stats_list = tc_stats && use_screen && g_tc_mode != 4 && pair_stats_supported(dtype, D, F);
     // ... and the log-normalisers too: no pass over the (K, chunk) scratch after the refinement on such chunks
     const bool list_softmax = pair_stats_list && !lse_out;
     if (use_tc) {
@@ -120,6 +122,8 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         if (rc) return rc;
         if (use_screen) {
             rc = tc_screen_prepare((const float*)Z, N, D, ldz, (const float*)op_a, (const float*)cst, K, Rp, Dpp, tc_ops_ws, screen_ops_ws, st);
+            if (rc) return rc;
+            rc = tc_screen_begin(C, K, Rp, g_tc_mode == 5 ? 1 : 0, screen_ws, st);
             if (rc) return rc;
         }
         if (tc_stats) { rc = tc_fstats ? tc_fstats_begin(C, K, tc_stat_ws, st) : tc_stats_begin(C, K, tc_stat_ws, st); if (rc) return rc; }
@@ -187,7 +191,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         } else if (stat && !hard) {
             const unsigned int* rgate = nullptr;
             if (resp_list) {                                   // pairs with r >= e^-40, grouped by component
-                rc = resp_list_build((const float*)scratch, K, nc, C, C, resp_ws, st);
+                rc = resp_list_build((const float*)scratch, K, nc, C, D, C, resp_ws, st);
                 if (rc) return rc;
                 rgate = resp_list_gate(resp_ws, C, K);
                 const int32_t *perm, *offsets, *slabs;
@@ -275,6 +279,9 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
     cudaStream_t st = nullptr, sc = nullptr;
     std::vector<cudaEvent_t> landed;
     int rc = MIMO_OK;
+    const bool dbg = getenv("MIMO_HOST_DEBUG") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
     auto body = [&]() -> int {
         MIMO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         MIMO_CUDA(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
@@ -295,6 +302,7 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
         MIMO_CUDA(cudaMemcpyAsync(dfj, fj_host, (size_t)F * 4, cudaMemcpyHostToDevice, st));
         MIMO_CUDA(cudaMemsetAsync(dstat, 0, (size_t)K * F * 8, st));
         MIMO_CUDA(cudaMemsetAsync(dlse, 0, 8, st));
+        if (dbg) fprintf(stderr, "mimo_sweep_host: %d segment(s) of %lld points, workspace %.2f GB, allocations %.1f ms\n", n_seg, (long long)seg, wsb / 1e9, now() - t_start);
         // uploads: one segment after the other on the copy stream, an event per segment
         landed.resize(n_seg);
         for (int s = 0; s < n_seg; ++s) {
@@ -317,7 +325,9 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
         MIMO_CUDA(cudaMemcpyAsync(stat_host, dstat, (size_t)K * F * 8, cudaMemcpyDeviceToHost, st));
         if (lse_sum_host) MIMO_CUDA(cudaMemcpyAsync(lse_sum_host, dlse, 8, cudaMemcpyDeviceToHost, st));
         if (hard && labels_host && N > 0) MIMO_CUDA(cudaMemcpyAsync(labels_host, dlab, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+        if (dbg) fprintf(stderr, "mimo_sweep_host: everything enqueued at %.1f ms\n", now() - t_start);
         MIMO_CUDA(cudaStreamSynchronize(st));
+        if (dbg) fprintf(stderr, "mimo_sweep_host: device done at %.1f ms\n", now() - t_start);
         return MIMO_OK;
     };
     rc = body();
@@ -328,6 +338,7 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
     cudaFree(dlab); cudaFree(dstat); cudaFree(dlse); cudaFree(duni);
     if (st) cudaStreamDestroy(st);
     if (sc) cudaStreamDestroy(sc);
+    if (dbg) fprintf(stderr, "mimo_sweep_host: buffers freed at %.1f ms\n", now() - t_start);
     return rc;
 }
 

@@ -98,7 +98,8 @@ screen_project_kernel(const float* __restrict__ W, int K, int Rp, int Dpp, float
 // list A: the better of the two accumulator halves' guesses; histogram over components
 __global__ void __launch_bounds__(256)
 screen_guess_kernel(const float* __restrict__ best_val, const int* __restrict__ best_k, int64_t ldl, int64_t n, int K,
-                    int* __restrict__ guess_k, int* __restrict__ histA) {
+                    int* __restrict__ guess_k, int* __restrict__ histA, const unsigned int* __restrict__ level) {
+    if (*level >= 2u) return;                             // earlier chunks of this sweep exhausted the screening tiers: straight to the dense pass
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float v0 = best_val[i], v1 = best_val[ldl + i];
@@ -109,7 +110,9 @@ screen_guess_kernel(const float* __restrict__ best_val, const int* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256)
-screen_scatterA_kernel(const int* __restrict__ guess_k, int64_t n, int* __restrict__ cursor, int* __restrict__ perm) {
+screen_scatterA_kernel(const int* __restrict__ guess_k, int64_t n, int* __restrict__ cursor, int* __restrict__ perm,
+                       const unsigned int* __restrict__ level) {
+    if (*level >= 2u) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) perm[atomicAdd(cursor + guess_k[i], 1)] = (int)i;
 }
@@ -118,11 +121,14 @@ screen_scatterA_kernel(const int* __restrict__ guess_k, int64_t n, int* __restri
 // counters: [0] list B entries found, [1] dense flag (set by screen_scan_kernel), [2] always 0
 __global__ void __launch_bounds__(256)
 screen_emit_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, const float* __restrict__ cst,
-                   const unsigned int* __restrict__ flags, const float* __restrict__ lower, const int* __restrict__ guess_k,
-                   int2* __restrict__ list, unsigned int cap, unsigned int* __restrict__ counters, int* __restrict__ hist) {
+                   const unsigned int* __restrict__ flags_proj, const unsigned int* __restrict__ flags_full,
+                   const float* __restrict__ lower, const int* __restrict__ guess_k,
+                   int2* __restrict__ list, unsigned int cap, unsigned int* __restrict__ counters, int* __restrict__ hist,
+                   const unsigned int* __restrict__ level) {
+    if (*level >= 2u) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
-    const float B = screen_bound(flags);
+    const float B = screen_bound(*level == 0u ? flags_proj : flags_full);      // the bound of the tier that produced the values
     const float t = valid ? lower[i] - SCREEN_T0 - 0.01f * (1.f + 1e-4f * fabsf(lower[i])) : INFINITY;   // FP32 slack of the exact value
     const int gk = valid ? guess_k[i] : -1;
     const int lane = threadIdx.x & 31;
@@ -156,10 +162,15 @@ screen_emit_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, c
 }
 
 // single block: exclusive scan of hist -> offsets[K+1], cursor := offsets, slabs (work items of pair_stats.cu);
-// flag (optional): dense fallback when the list is too long
+// flag (optional): dense fallback when the list is too long; level (optional): the screening tier of the sweep
+// (0 projected rows, 1 all rows in one FP16 pass, 2 none).  A chunk whose tier yields too many candidates takes the
+// dense pass and moves the REST of the sweep one tier up: chunks of one data set look alike, and a dense chunk costs
+// ~10x a projected screening pass, so a failed tier is not worth retrying.
 __global__ void screen_scan_kernel(const int* __restrict__ hist, int K, int* __restrict__ offsets, int* __restrict__ cursor,
-                                   int* __restrict__ slabs, unsigned int* __restrict__ counters, unsigned int max_cands) {
+                                   int* __restrict__ slabs, unsigned int* __restrict__ counters, unsigned int max_cands,
+                                   unsigned int* __restrict__ level) {
     if (threadIdx.x == 0) {
+        if (level && *level >= 2u) { if (counters) counters[1] = 1u; return; }
         int run = 0, items = 0;
         for (int k = 0; k < K; ++k) {
             offsets[k] = run; cursor[k] = run; slabs[k] = items;
@@ -168,7 +179,10 @@ __global__ void screen_scan_kernel(const int* __restrict__ hist, int K, int* __r
         }
         offsets[K] = run;
         slabs[K] = items;
-        if (counters) counters[1] = (counters[0] > max_cands) ? 1u : 0u;
+        if (counters) {
+            counters[1] = (counters[0] > max_cands) ? 1u : 0u;
+            if (level && counters[1]) *level += 1u;
+        }
     }
 }
 
@@ -188,9 +202,9 @@ template <int RP>
 __global__ void __launch_bounds__(RF_THREADS)
 screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
                      const float* __restrict__ W, int Dpp, const float* __restrict__ cst,
-                     const int* __restrict__ perm, const int* __restrict__ offsets, const unsigned int* __restrict__ gate,
+                     const int* __restrict__ perm, const int* __restrict__ offsets, const unsigned int* __restrict__ gate, unsigned int gate_min,
                      float* __restrict__ a, int64_t ldo, float* __restrict__ exact) {
-    if (gate != nullptr && __ldg(gate) != 0u) return;          // dense second pass instead
+    if (gate != nullptr && *gate >= gate_min) return;          // dense pass instead
     constexpr int RG = RP / 4, CG = RF_THREADS / RG, TILE_C = RF_CPT * CG;
     const int k = blockIdx.x;
     const int beg = offsets[k], cnt = offsets[k + 1] - beg;
@@ -329,7 +343,7 @@ struct ScreenLists { size_t hist, offsets, cursor, slabs, perm; };
 struct ScreenLayout {
     unsigned int cap; int64_t ldl;
     size_t off_counters; ScreenLists A, B;
-    size_t off_best_val, off_best_k, off_lower, off_guess, off_m, off_s, off_lse, off_list, bytes;
+    size_t off_best_val, off_best_k, off_lower, off_guess, off_m, off_s, off_lse, off_level, off_list, bytes;
 };
 static ScreenLayout screen_layout(int64_t chunk_points, int K) {
     ScreenLayout L;
@@ -349,6 +363,7 @@ static ScreenLayout screen_layout(int64_t chunk_points, int K) {
     L.off_m = o;        o += pp;
     L.off_s = o;        o += pp;
     L.off_lse = o;      o += pp;
+    L.off_level = o;    o += 256;
     L.A.perm = o;       o += pp;
     L.off_list = o;     o += a256((size_t)L.cap * 8);
     L.B.perm = o;       o += a256((size_t)L.cap * 4);
@@ -384,7 +399,8 @@ int tc_screen_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float
         MIMO_LAUNCH_CHECK();
         return MIMO_OK;
     }
-    screen_wnorm_kernel<<<K, 256, 0, st>>>(W, K, Rp, Dpp, Dpp, flags, 4);
+    screen_wnorm_kernel<<<K, 256, 0, st>>>(W, K, Rp, Dpp, D, flags, 2);        // tier 1 (all rows): data columns
+    screen_wnorm_kernel<<<K, 256, 0, st>>>(W, K, Rp, Dpp, Dpp, flags, 4);      // FP32 rounding of the projection
     MIMO_LAUNCH_CHECK();
     float* Wp = screen_wproj(sops_ws);
     const size_t smem = (size_t)Rp * Dpp * sizeof(float);
@@ -394,6 +410,7 @@ int tc_screen_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float
     void* sws = screen_ops_ws(ops_ws, sops_ws, K, Rp, Dpp);
     unsigned int* sflags = tc_flags(sws);
     MIMO_CUDA(cudaMemcpyAsync(sflags, flags, 256, cudaMemcpyDeviceToDevice, st));      // data scale, ||z||, ||W||
+    MIMO_CUDA(cudaMemsetAsync(sflags + 2, 0, 4, st));
     screen_wnorm_kernel<<<K, 256, 0, st>>>(Wp, K, SCREEN_ROWS, Dpp, D, sflags, 2);
     MIMO_LAUNCH_CHECK();
     return tc_prepare_operands(Wp, cst, K, SCREEN_ROWS, Dpp, D, sws, st);
@@ -404,8 +421,26 @@ int tc_screen_pass(const float* Z, int64_t n, int D, int64_t ldz, int K, int Rp,
                    void* ops_ws, void* sops_ws, int64_t plan_points, void* ws, cudaStream_t st) {
     ScreenLayout L = screen_layout(plan_points, K);
     char* base = align256(ws);
-    return tc_estep_pass(Z, n, D, ldz, K, tc_screen_rows(Rp), out, ldo, screen_ops_ws(ops_ws, sops_ws, K, Rp, Dpp), 1, nullptr, 0u,
+    const unsigned int* level = (const unsigned int*)(base + L.off_level);
+    if (Rp > SCREEN_ROWS) {                              // tier 0: projected rows
+        int rc = tc_estep_pass(Z, n, D, ldz, K, SCREEN_ROWS, out, ldo, screen_ops_ws(ops_ws, sops_ws, K, Rp, Dpp), 1, level, 0u,
+                               (float*)(base + L.off_best_val), (int*)(base + L.off_best_k), L.ldl, st);
+        if (rc) return rc;
+    }
+    // tier 1: all rows, one FP16 pass
+    return tc_estep_pass(Z, n, D, ldz, K, Rp, out, ldo, ops_ws, 1, level, 1u,
                          (float*)(base + L.off_best_val), (int*)(base + L.off_best_k), L.ldl, st);
+}
+
+__global__ void screen_level_kernel(unsigned int* level, unsigned int v) { *level = v; }
+
+// once per sweep: the screening tier the first chunk starts on (0 projected rows -- needs Rp > 32 --, 1 all rows)
+int tc_screen_begin(int64_t plan_points, int K, int Rp, int start_level, void* ws, cudaStream_t st) {
+    unsigned int* level = (unsigned int*)(align256(ws) + screen_layout(plan_points, K).off_level);
+    const unsigned int v = (Rp <= SCREEN_ROWS || start_level >= 1) ? 1u : 0u;
+    screen_level_kernel<<<1, 1, 0, st>>>(level, v);
+    MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
 }
 
 const unsigned int* tc_screen_gate(void* ws, int64_t plan_points, int K) {
@@ -440,21 +475,22 @@ int tc_screen_last(unsigned int* out_host2) {
 
 template <int RP>
 static int launch_refine(const float* Z, int D, int64_t ldz, const float* W, int K, int Dpp, const float* cst,
-                         const int* perm, const int* offsets, const unsigned int* gate, float* a, int64_t ldo, float* exact,
-                         cudaStream_t st) {
+                         const int* perm, const int* offsets, const unsigned int* gate, unsigned int gate_min, float* a, int64_t ldo,
+                         float* exact, cudaStream_t st) {
     constexpr int TILE_C = RF_CPT * (RF_THREADS / (RP / 4));
     const size_t smem = (size_t)(RP + TILE_C) * Dpp * sizeof(float);
     const int vec4 = (D % 4 == 0) && (Dpp % 4 == 0) && (ldz % 4 == 0) && (((uintptr_t)Z & 15) == 0);
     MIMO_CUDA(cudaFuncSetAttribute(screen_refine_kernel<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    screen_refine_kernel<RP><<<dim3(K, RF_SPLIT), RF_THREADS, smem, st>>>(Z, D, ldz, vec4, W, Dpp, cst, perm, offsets, gate, a, ldo, exact);
+    screen_refine_kernel<RP><<<dim3(K, RF_SPLIT), RF_THREADS, smem, st>>>(Z, D, ldz, vec4, W, Dpp, cst, perm, offsets, gate, gate_min, a, ldo, exact);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
 static int refine(const float* Z, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp, const float* cst,
-                  const int* perm, const int* offsets, const unsigned int* gate, float* a, int64_t ldo, float* exact, cudaStream_t st) {
-    if (Rp == 32) return launch_refine<32>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, gate, a, ldo, exact, st);
-    if (Rp == 64) return launch_refine<64>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, gate, a, ldo, exact, st);
-    if (Rp == 128) return launch_refine<128>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, gate, a, ldo, exact, st);
+                  const int* perm, const int* offsets, const unsigned int* gate, unsigned int gate_min, float* a, int64_t ldo,
+                  float* exact, cudaStream_t st) {
+    if (Rp == 32) return launch_refine<32>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, gate, gate_min, a, ldo, exact, st);
+    if (Rp == 64) return launch_refine<64>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, gate, gate_min, a, ldo, exact, st);
+    if (Rp == 128) return launch_refine<128>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, gate, gate_min, a, ldo, exact, st);
     set_error("screened E-step: unsupported Rp=%d", Rp);
     return MIMO_EUNSUPPORTED;
 }
@@ -472,20 +508,20 @@ int tc_screen_select(const float* Z, int D, int64_t ldz, const float* W, const f
     const int grid = cdiv(n, 256);
     int* guess_k = (int*)(base + L.off_guess);
     float* lower = (float*)(base + L.off_lower);
+    unsigned int* level = (unsigned int*)(base + L.off_level);
     screen_guess_kernel<<<grid, 256, 0, st>>>((const float*)(base + L.off_best_val), (const int*)(base + L.off_best_k), L.ldl, n, K,
-                                              guess_k, (int*)(base + L.A.hist));
+                                              guess_k, (int*)(base + L.A.hist), level);
     screen_scan_kernel<<<1, 32, 0, st>>>((const int*)(base + L.A.hist), K, (int*)(base + L.A.offsets), (int*)(base + L.A.cursor),
-                                         (int*)(base + L.A.slabs), nullptr, 0u);
-    screen_scatterA_kernel<<<grid, 256, 0, st>>>(guess_k, n, (int*)(base + L.A.cursor), (int*)(base + L.A.perm));
+                                         (int*)(base + L.A.slabs), nullptr, 0u, nullptr);
+    screen_scatterA_kernel<<<grid, 256, 0, st>>>(guess_k, n, (int*)(base + L.A.cursor), (int*)(base + L.A.perm), level);
     MIMO_LAUNCH_CHECK();
-    int rc = refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.A.perm), (const int*)(base + L.A.offsets), nullptr, a, ldo, lower, st);
+    int rc = refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.A.perm), (const int*)(base + L.A.offsets), level, 2u, a, ldo, lower, st);
     if (rc) return rc;
-    const unsigned int* flags = tc_flags(screen_ops_ws(ops_ws, sops_ws, K, Rp, Dpp));
-    screen_emit_kernel<<<grid, 256, 0, st>>>(a, K, n, ldo, cst, flags, lower, guess_k, (int2*)(base + L.off_list), L.cap,
-                                             counters, (int*)(base + L.B.hist));
+    screen_emit_kernel<<<grid, 256, 0, st>>>(a, K, n, ldo, cst, tc_flags(screen_ops_ws(ops_ws, sops_ws, K, Rp, Dpp)), tc_flags(ops_ws),
+                                             lower, guess_k, (int2*)(base + L.off_list), L.cap, counters, (int*)(base + L.B.hist), level);
     const double maxc = std::min<double>((double)L.cap, 0.04 * (double)n * K);
     screen_scan_kernel<<<1, 32, 0, st>>>((const int*)(base + L.B.hist), K, (int*)(base + L.B.offsets), (int*)(base + L.B.cursor),
-                                         (int*)(base + L.B.slabs), counters, (unsigned int)maxc);
+                                         (int*)(base + L.B.slabs), counters, (unsigned int)maxc, level);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
@@ -498,7 +534,7 @@ int tc_screen_refine(const float* Z, int D, int64_t ldz, const float* W, int K, 
     const unsigned int* counters = (const unsigned int*)(base + L.off_counters);
     screen_scatter_kernel<<<sm_count() * 4, 256, 0, st>>>((const int2*)(base + L.off_list), counters, (int*)(base + L.B.cursor), (int*)(base + L.B.perm));
     MIMO_LAUNCH_CHECK();
-    return refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.B.perm), (const int*)(base + L.B.offsets), counters + 1, a, ldo, nullptr, st);
+    return refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.B.perm), (const int*)(base + L.B.offsets), counters + 1, 1u, a, ldo, nullptr, st);
 }
 
 // log-normalisers of the chunk from the lists (after tc_screen_refine): per-point lse into the workspace, their sum
@@ -527,9 +563,14 @@ const float* tc_screen_lse_values(void* ws, int64_t plan_points, int K) {
 // After the dense softmax of a chunk the responsibilities of most pairs are (next to) zero once components are
 // separated.  The pairs with r >= e^-40 are listed, grouped by component, and the statistics summed over the list
 // (pair_stats.cu); the dropped mass is < N e^-40 per component.  Dense CUDA-core statistics (stats.cu) when more
-// than RL_MAX_FRAC of the pairs qualify -- the same device-side flag mechanism as above.
+// than rl_max_frac(D) of the pairs qualify -- the same device-side flag mechanism as above.
 constexpr float RL_TAU = 4.2e-18f;           // e^-40
-constexpr double RL_MAX_FRAC = 0.15;
+// Break-even: a listed pair costs 64 FMAs per 8 x 8 tile of the triangle (plus a row gather), a dense pair F FMAs; measured
+// on cfg2 (D = 9) and cfg4 (D = 16) the list wins below ~0.1 F / (64 tiles) of the pairs.
+static double rl_max_frac(int D) {
+    const int T = (D + 8) >> 3, ntiles = T * (T + 1) / 2, F = (D + 1) * (D + 2) / 2;
+    return std::min(0.15, 0.1 * (double)F / (64.0 * ntiles));
+}
 
 __global__ void __launch_bounds__(256)
 resp_emit_kernel(const float* __restrict__ r, int K, int64_t n, int64_t ldr, int2* __restrict__ list, unsigned int cap,
@@ -564,7 +605,7 @@ resp_emit_kernel(const float* __restrict__ r, int K, int64_t n, int64_t ldr, int
 struct RespListLayout { unsigned int cap; size_t off_counters, hist, offsets, cursor, slabs, list, perm, bytes; };
 static RespListLayout resp_list_layout(int64_t chunk_points, int K) {
     RespListLayout L;
-    L.cap = (unsigned int)std::min<double>(2.0e9, (RL_MAX_FRAC + 0.01) * (double)chunk_points * K + 1024.0);
+    L.cap = (unsigned int)std::min<double>(2.0e9, 0.16 * (double)chunk_points * K + 1024.0);
     const size_t kk = a256((size_t)(K + 1) * 4);
     size_t o = 0;
     L.off_counters = o; o += 256;
@@ -578,15 +619,15 @@ static RespListLayout resp_list_layout(int64_t chunk_points, int K) {
 size_t resp_list_workspace(int64_t chunk_points, int K) { return resp_list_layout(chunk_points, K).bytes + 256; }
 
 // lists of the chunk's responsibilities R (K, n); sets the dense flag *resp_list_gate() when the list is too long
-int resp_list_build(const float* R, int K, int64_t n, int64_t ldr, int64_t plan_points, void* ws, cudaStream_t st) {
+int resp_list_build(const float* R, int K, int64_t n, int64_t ldr, int D, int64_t plan_points, void* ws, cudaStream_t st) {
     RespListLayout L = resp_list_layout(plan_points, K);
     char* base = align256(ws);
     unsigned int* counters = (unsigned int*)(base + L.off_counters);
     MIMO_CUDA(cudaMemsetAsync(base, 0, L.offsets, st));                     // counters + histogram
     resp_emit_kernel<<<cdiv(n, 256), 256, 0, st>>>(R, K, n, ldr, (int2*)(base + L.list), L.cap, counters, (int*)(base + L.hist));
-    const double maxc = std::min<double>((double)L.cap, RL_MAX_FRAC * (double)n * K);
+    const double maxc = std::min<double>((double)L.cap, rl_max_frac(D) * (double)n * K);
     screen_scan_kernel<<<1, 32, 0, st>>>((const int*)(base + L.hist), K, (int*)(base + L.offsets), (int*)(base + L.cursor),
-                                         (int*)(base + L.slabs), counters, (unsigned int)maxc);
+                                         (int*)(base + L.slabs), counters, (unsigned int)maxc, nullptr);
     screen_scatter_kernel<<<sm_count() * 4, 256, 0, st>>>((const int2*)(base + L.list), counters, (int*)(base + L.cursor), (int*)(base + L.perm));
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;

@@ -246,6 +246,21 @@ def test_sweep_screened_estep(hard, K, d, N, sep):
         finally:
             E.set_tensor_cores(old)
         close(buf.stat, mid.stat.cpu().numpy(), 2e-5, 'pair-list vs dense statistics behind the screened E-step')
+        # mode 5: the second screening tier (all operand rows, one FP16 pass) -- a tighter bound than the projection,
+        # the tier a multi-chunk sweep moves to by itself when the projection leaves too many candidates
+        old = E.set_tensor_cores(5)
+        try:
+            t1 = E.SweepBuffers(N, K, feats.F, 'fp32', hard)
+            E.sweep(Z, ops, feats, t1)
+            c1, d1 = E.screen_last()
+        finally:
+            E.set_tensor_cores(old)
+        print('  all-rows tier: %d candidates (%.2f%%), dense fallback %d' % (c1, 100.0 * c1 / (N * K), d1))
+        assert c1 <= max(cands, N) or dense == 1
+        if sep >= 1.0:
+            assert d1 == 0
+        close(t1.stat, ref.stat.cpu().numpy(), 2e-5, 'all-rows screening tier vs dense statistics')
+        close(t1.lse_sum, ref.lse_sum.cpu().numpy(), 1e-6, 'all-rows screening tier lse sum')
 
 
 def test_screened_sweep_large_properties():
