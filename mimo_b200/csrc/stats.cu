@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(SH_THREADS)
 stats_hard_kernel(const T* __restrict__ Z, int D, int64_t ldz, const int32_t* __restrict__ perm,
                   const int32_t* __restrict__ offsets, const int32_t* __restrict__ slabs, int K,
                   const int32_t* __restrict__ fi, const int32_t* __restrict__ fj, int F,
-                  double* __restrict__ stat) {
+                  double* __restrict__ stat, const int32_t* __restrict__ kind, int fast_kinds) {
+    if (kind != nullptr && ((fast_kinds >> *kind) & 1)) return;      // a fast kernel for this feature layout ran instead
     // work item -> (component, slab): binary search in the per-component slab prefix
     const int item = blockIdx.x;
     if (item >= slabs[K]) return;
@@ -252,10 +253,80 @@ stats_hard_kernel(const T* __restrict__ Z, int D, int64_t ldz, const int32_t* __
     }
 }
 
+// Which canonical layout is the caller's feature table?  1: packed lower triangle of zt zt^T (quad_features), 2: the
+// diagonal family [z_j | z_j^2 | 1], 0: anything else.  The fast kernels below are gated on the answer ON THE DEVICE, so an
+// arbitrary table still gets the generic kernel.
+__global__ void feature_kind_kernel(const int32_t* __restrict__ fi, const int32_t* __restrict__ fj, int F, int D, int32_t* __restrict__ kind) {
+    __shared__ int tri_ok, diag_ok;
+    if (threadIdx.x == 0) { tri_ok = (F == (D + 1) * (D + 2) / 2); diag_ok = (F == 2 * D + 1); }
+    __syncthreads();
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const int i = fi[f], j = fj[f];
+        if (tri_ok) {                                  // f = i (i + 1) / 2 + j, j <= i
+            if (i < 0 || i > D || j < 0 || j > i || i * (i + 1) / 2 + j != f) tri_ok = 0;
+        }
+        if (diag_ok) {
+            const bool ok = (f < D) ? (i == f && j == D) : (f < 2 * D) ? (i == f - D && j == f - D) : (i == D && j == D);
+            if (!ok) diag_ok = 0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *kind = tri_ok ? 1 : (diag_ok ? 2 : 0);
+}
+
+// Hard statistics of the diagonal family: sum x, sum x^2 and the count per component over the label-sorted lists.
+// Work item = (component, slab of <= PS_SLAB points); thread = (row group, column): coalesced row reads, FP32 within the
+// slab, one FP64 atomic per feature and slab.  HBM-bound (one read of Z per sweep).
+constexpr int DH_THREADS = 256;
+__global__ void __launch_bounds__(DH_THREADS)
+diag_hard_stats_kernel(const float* __restrict__ Z, int D, int64_t ldz, const int32_t* __restrict__ perm,
+                       const int32_t* __restrict__ offsets, const int32_t* __restrict__ slabs, int K,
+                       const int32_t* __restrict__ kind, double* __restrict__ stat, int F) {
+    if (*kind != 2) return;
+    __shared__ float s1[DH_THREADS], s2[DH_THREADS];
+    const int tid = threadIdx.x;
+    const int cols = min(D, DH_THREADS);                 // columns handled per pass
+    const int G = DH_THREADS / cols;                     // row groups
+    const int g = tid / cols, c = tid - g * cols;
+    const int n_items = slabs[K];
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int lo = 0, hi = K;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (slabs[mid] <= item) lo = mid; else hi = mid; }
+        const int k = lo;
+        const int beg = offsets[k] + (item - slabs[k]) * PS_SLAB;
+        const int end = min(offsets[k + 1], beg + PS_SLAB);
+        if (beg >= end) continue;
+        for (int c0 = 0; c0 < D; c0 += cols) {
+            const int j = c0 + c;
+            float a1 = 0.f, a2 = 0.f;
+            if (g < G && j < D) {
+                int p = beg + g;
+                for (; p + 3 * G < end; p += 4 * G) {                      // four gathers in flight
+                    const float x0 = __ldg(Z + (int64_t)perm[p] * ldz + j), x1 = __ldg(Z + (int64_t)perm[p + G] * ldz + j);
+                    const float x2 = __ldg(Z + (int64_t)perm[p + 2 * G] * ldz + j), x3 = __ldg(Z + (int64_t)perm[p + 3 * G] * ldz + j);
+                    a1 += (x0 + x1) + (x2 + x3);
+                    a2 = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, a2))));
+                }
+                for (; p < end; p += G) { const float x = __ldg(Z + (int64_t)perm[p] * ldz + j); a1 += x; a2 = fmaf(x, x, a2); }
+            }
+            __syncthreads();
+            s1[tid] = a1; s2[tid] = a2;
+            __syncthreads();
+            if (g == 0 && j < D) {
+                double t1 = 0.0, t2 = 0.0;
+                for (int gg = 0; gg < G; ++gg) { t1 += (double)s1[gg * cols + c]; t2 += (double)s2[gg * cols + c]; }
+                atomicAdd(stat + (int64_t)k * F + j, t1);
+                atomicAdd(stat + (int64_t)k * F + D + j, t2);
+            }
+        }
+        if (tid == 0) atomicAdd(stat + (int64_t)k * F + 2 * D, (double)(end - beg));
+    }
+}
+
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 size_t stats_hard_workspace(int64_t N, int K) {
-    return align256((size_t)(K + 1) * 4) * 4 + 256 + align256((size_t)N * 4);
+    return align256((size_t)(K + 1) * 4) * 5 + 256 + align256((size_t)N * 4);
 }
 
 int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const int32_t* labels, int K,
@@ -273,14 +344,22 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
     int32_t* offsets = (int32_t*)(ws + seg);
     int32_t* cursor = (int32_t*)(ws + 2 * seg);
     int32_t* slabs = (int32_t*)(ws + 3 * seg);
-    int32_t* bad = (int32_t*)(ws + 4 * seg);
-    int32_t* perm = (int32_t*)(ws + 4 * seg + 256);
-    MIMO_CUDA(cudaMemsetAsync(ws, 0, 4 * seg + 256, st));
+    int32_t* slabs_fast = (int32_t*)(ws + 4 * seg);                      // second slab prefix (PS_SLAB points per item)
+    int32_t* bad = (int32_t*)(ws + 5 * seg);                             // [0] bad label seen, [1] feature layout
+    int32_t* perm = (int32_t*)(ws + 5 * seg + 256);
+    MIMO_CUDA(cudaMemsetAsync(ws, 0, 5 * seg + 256, st));
     int grid = cdiv(N, 256);
     label_hist_kernel<<<grid, 256, 0, st>>>(labels, N, K, counts, bad);
-    // FP32 data, packed-triangle statistics: the register-tiled pair-list kernel (pair_stats.cu) takes the sorted lists
+    // FP32 data with a canonical feature table (checked on the device): the register-tiled pair-list kernel
+    // (pair_stats.cu) for the packed triangle, the streaming kernel above for the diagonal family; otherwise -- and in
+    // FP64 -- the generic per-feature kernel.  Slab size of the lists: PS_SLAB for the fast kernels, SH_SEG for the generic.
     const bool pair = pair_stats_supported(dtype, D, F);
-    label_scan_kernel<<<1, 32, 0, st>>>(counts, K, offsets, cursor, slabs, pair ? PS_SLAB : SH_SEG);
+    const bool diag = dtype == MIMO_F32 && D >= 2 && F == 2 * D + 1;
+    int32_t* kind = bad + 1;
+    const int fast_kinds = (pair ? 2 : 0) | (diag ? 4 : 0);                  // bit k: layout k has a fast kernel here
+    if (fast_kinds) feature_kind_kernel<<<1, 256, 0, st>>>(fi, fj, F, D, kind);
+    label_scan_kernel<<<1, 32, 0, st>>>(counts, K, offsets, cursor, slabs, SH_SEG);
+    if (fast_kinds) label_scan_kernel<<<1, 32, 0, st>>>(counts, K, offsets, cursor, slabs_fast, PS_SLAB);
     label_scatter_kernel<<<grid, 256, 0, st>>>(labels, N, K, cursor, perm);
     MIMO_LAUNCH_CHECK();
     if (check) {
@@ -289,15 +368,23 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
         MIMO_CUDA(cudaStreamSynchronize(st));
         if (hbad) { set_error("labels outside [0, K)"); return MIMO_EINVAL; }
     }
-    if (pair) return pair_stats((const float*)Z, D, ldz, perm, offsets, slabs, K, nullptr, 0, nullptr, nullptr, 0u, stat, F, st);
+    if (pair) {
+        int rc = pair_stats((const float*)Z, D, ldz, perm, offsets, slabs_fast, K, nullptr, 0, nullptr, (const unsigned int*)kind, 1u, stat, F, st);
+        if (rc) return rc;
+    }
+    if (diag) {
+        diag_hard_stats_kernel<<<sm_count() * 8, DH_THREADS, 0, st>>>((const float*)Z, D, ldz, perm, offsets, slabs_fast, K, kind, stat, F);
+        MIMO_LAUNCH_CHECK();
+    }
     size_t es = dtype == MIMO_F32 ? 4 : 8;
     size_t smem = (size_t)SH_PT * (D + 2) * es;
     // every component contributes at most ceil(count/SEG) <= count/SEG + 1 slabs
     dim3 g2((unsigned)(cdiv(N, SH_SEG) + K));
+    const int32_t* gk = fast_kinds ? kind : nullptr;
     if (dtype == MIMO_F32)
-        stats_hard_kernel<float><<<g2, SH_THREADS, smem, st>>>((const float*)Z, D, ldz, perm, offsets, slabs, K, fi, fj, F, stat);
+        stats_hard_kernel<float><<<g2, SH_THREADS, smem, st>>>((const float*)Z, D, ldz, perm, offsets, slabs, K, fi, fj, F, stat, gk, fast_kinds);
     else
-        stats_hard_kernel<double><<<g2, SH_THREADS, smem, st>>>((const double*)Z, D, ldz, perm, offsets, slabs, K, fi, fj, F, stat);
+        stats_hard_kernel<double><<<g2, SH_THREADS, smem, st>>>((const double*)Z, D, ldz, perm, offsets, slabs, K, fi, fj, F, stat, gk, fast_kinds);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }

@@ -561,3 +561,52 @@ def test_sweep_resp_list_statistics(K, d, N, sep):
     close(S[:, :d, :d], st[2], 1e-4, 'sum r xx')
     close(S[:, d, :d], st[0], 1e-4, 'sum r x')
     close(S[:, d, d], st[1], 1e-4, 'sum r')
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'fp64'])
+@pytest.mark.parametrize('K,d,N', [(7, 64, 9000), (300, 5, 4000), (3, 300, 2500), (256, 64, 40000)])
+def test_stats_hard_diag(precision, K, d, N):
+    """hard statistics of the diagonal family (gaussian.py:819-832 on the one-hot matrix of data.py:160-169): FP32 goes
+    through the streaming kernel over the label-sorted lists, FP64 through the generic per-feature kernel."""
+    E = eng()
+    rng = np.random.default_rng(K + d)
+    x = rng.standard_normal((N, d)) * (0.5 + rng.random(d)) + rng.standard_normal(d)
+    p = rng.dirichlet(0.3 * np.ones(K))
+    p[K // 2] = 0.0
+    labels = rng.choice(K, size=N, p=p / p.sum()).astype(np.int32)
+    Z = E.to_dev(x, E.tdtype(precision))
+    feats = E.diag_features(d)
+    st = E.stats_hard(Z, E.to_dev(labels, torch.int32), K, feats, precision).cpu().numpy()
+    ref = orc.gauss_diag_wstats(Z.double().cpu().numpy(), orc.one_hot(labels, K))
+    tol = 1e-10 if precision == 'fp64' else 1e-5
+    close(st[:, :d], ref[0], tol, 'hard sum x')
+    close(st[:, d:2 * d], ref[3], tol, 'hard sum x^2')
+    assert np.array_equal(st[:, 2 * d], np.bincount(labels, minlength=K))
+    assert np.all(st[K // 2] == 0.0)
+
+
+@pytest.mark.parametrize('D', [9, 16])
+def test_stats_hard_non_canonical_feature_table(D):
+    """A feature table with the SIZE of a canonical layout but a different order must not take a fast kernel: the layout
+    is verified on the device and the generic per-feature kernel runs."""
+    E = eng()
+    rng = np.random.default_rng(D)
+    N, K = 3000, 4
+    x = rng.standard_normal((N, D)) + 1.0
+    labels = rng.integers(0, K, size=N).astype(np.int32)
+    canon = E.quad_features(D)
+    perm = rng.permutation(canon.F)
+    feats = E.Features(canon.fi_host[perm], canon.fj_host[perm], D)
+    Z = E.to_dev(x, torch.float32)
+    st = E.stats_hard(Z, E.to_dev(labels, torch.int32), K, feats, 'fp32').cpu().numpy()
+    zt = np.concatenate([Z.double().cpu().numpy(), np.ones((N, 1))], axis=1)
+    phi = zt[:, feats.fi_host] * zt[:, feats.fj_host]
+    ref = orc.one_hot(labels, K) @ phi
+    close(st, ref, 1e-10, 'permuted feature table')
+    # diagonal-sized table (F = 2 D + 1) in a different order
+    dcanon = E.diag_features(D)
+    perm = rng.permutation(dcanon.F)
+    feats = E.Features(dcanon.fi_host[perm], dcanon.fj_host[perm], D)
+    st = E.stats_hard(Z, E.to_dev(labels, torch.int32), K, feats, 'fp32').cpu().numpy()
+    phi = zt[:, feats.fi_host] * zt[:, feats.fj_host]
+    close(st, orc.one_hot(labels, K) @ phi, 1e-10, 'permuted diagonal feature table')
