@@ -575,6 +575,7 @@ def time_e2e(w, s, E, _lib, hard, steps, comm=None):
             flat_h.copy_(flat_d, non_blocking=True)
             torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
+    _lib.call('mimo_sweep_host_release')             # give the call's cached device buffers back
     dt = float(np.mean(times[1:]))
     if world > 1:
         t = torch.tensor([dt], device=s.Z.device, dtype=torch.float64)

@@ -288,8 +288,9 @@ int mimo_mstep_lingauss(int K, int c, int o, int tied, const double* stat, int F
 
 /* One mean-field / Gibbs sweep of the quad or diag family with HOST pointers:
  * copies Z (N, D) to the device, runs mimo_sweep, copies stat / lse_sum (and
- * labels if requested) back.  Synchronous.  Allocates and frees its own
- * device buffers (this is the only entry point that does).  Z is uploaded in
+ * labels if requested) back.  Synchronous.  Allocates its own device buffers
+ * (the only entry point that does) and keeps them for the next call;
+ * mimo_sweep_host_release() frees them.  Z is uploaded in
  * segments of whole point chunks on a copy stream while the previous segment
  * is swept, so the call costs max(upload, compute) rather than their sum; the
  * result is the statistics of utils/abstraction.py:12-14 summed over segments
@@ -297,6 +298,7 @@ int mimo_mstep_lingauss(int K, int c, int o, int tied, const double* stat, int F
  * mimo_sweep_host_set_segment: points per segment (rounded up to whole chunks;
  * 0 = automatic, about 0.5 GB of data).                                        */
 int mimo_sweep_host_set_segment(int64_t points);
+int mimo_sweep_host_release(void);
 int mimo_sweep_host(int dtype, int family, int hard,
                     const void* Z_host, int64_t N, int D,
                     const void* op_a_host, const void* op_b_host, const void* cst_host,

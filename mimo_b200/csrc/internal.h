@@ -107,6 +107,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
           double* stat, double* lse_sum, int32_t* labels_out, void* lse_out, void* ll_out, int64_t ldo,
           void* workspace, size_t workspace_bytes, cudaStream_t st, double* phase_ms = nullptr);
 int64_t sweep_host_set_segment(int64_t points);
+void sweep_host_release();
 int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, int D,
                const void* op_a_host, const void* op_b_host, const void* cst_host, int K, int Rp, int Dpp,
                const int32_t* fi_host, const int32_t* fj_host, int F,

@@ -381,6 +381,11 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
     // every component contributes at most ceil(count/SEG) <= count/SEG + 1 slabs
     dim3 g2((unsigned)(cdiv(N, SH_SEG) + K));
     const int32_t* gk = fast_kinds ? kind : nullptr;
+    if (smem > 200 * 1024) { set_error("hard stats: D=%d too large for shared memory", D); return MIMO_EUNSUPPORTED; }
+    if (smem > 48 * 1024) {
+        if (dtype == MIMO_F32) MIMO_CUDA(cudaFuncSetAttribute(stats_hard_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else MIMO_CUDA(cudaFuncSetAttribute(stats_hard_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     if (dtype == MIMO_F32)
         stats_hard_kernel<float><<<g2, SH_THREADS, smem, st>>>((const float*)Z, D, ldz, perm, offsets, slabs, K, fi, fj, F, stat, gk, fast_kinds);
     else

@@ -28,9 +28,11 @@ static bool sweep_uses_screen(int dtype, int family, int D, int K, int Rp) {
     return (g_tc_mode == 1 || g_tc_mode == 4 || g_tc_mode == 5) && K >= 32 && sweep_uses_tc(dtype, family, D, Rp) && tc_screen_supported(D, Rp);
 }
 
-// CUDA-core quad path in FP32: statistics over the list of pairs with a non-negligible responsibility (pair_stats.cu)
+// CUDA-core quad path in FP32, 16 <= D < 24: statistics over the list of pairs with a non-negligible responsibility
+// (pair_stats.cu).  Below D = 16 the triangle has 3 register tiles or fewer and the list kernel loses to the dense one
+// at any list length (measured on cfg2, D = 9).
 static bool sweep_uses_resp_list(int dtype, int family, int hard, int D, int K, int Rp) {
-    return (g_tc_mode == 1 || g_tc_mode == 5) && !hard && family == 0 && dtype == MIMO_F32 && D >= 8 && K >= 8 && !sweep_uses_tc(dtype, family, D, Rp);
+    return (g_tc_mode == 1 || g_tc_mode == 5) && !hard && family == 0 && dtype == MIMO_F32 && D >= 16 && K >= 8 && !sweep_uses_tc(dtype, family, D, Rp);
 }
 
 // points per chunk.
@@ -251,6 +253,35 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     return MIMO_OK;
 }
 
+// Device buffers of mimo_sweep_host, kept between calls (a fresh cudaMalloc / cudaFree of tens of GB per call costs
+// 30 ms at best and hundreds when the driver has to reclaim memory); mimo_sweep_host_release() frees them.
+struct HostSweepCache {
+    static constexpr int SLOTS = 11;
+    void* ptr[SLOTS] = {};
+    size_t bytes[SLOTS] = {};
+    int device = -1;
+    void release() {
+        for (int i = 0; i < SLOTS; ++i) { if (ptr[i]) cudaFree(ptr[i]); ptr[i] = nullptr; bytes[i] = 0; }
+    }
+    cudaError_t get(int slot, size_t need, void** out) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev != device) { release(); device = dev; }
+        need = std::max<size_t>(need, 16);
+        if (bytes[slot] < need) {
+            if (ptr[slot]) cudaFree(ptr[slot]);
+            ptr[slot] = nullptr; bytes[slot] = 0;
+            cudaError_t e = cudaMalloc(&ptr[slot], need);
+            if (e != cudaSuccess) return e;
+            bytes[slot] = need;
+        }
+        *out = ptr[slot];
+        return cudaSuccess;
+    }
+};
+static HostSweepCache g_host_cache;
+void sweep_host_release() { g_host_cache.release(); }
+
 static int64_t g_host_segment = 0;
 int64_t sweep_host_set_segment(int64_t points) { int64_t old = g_host_segment; g_host_segment = points < 0 ? 0 : points; return old; }
 
@@ -285,17 +316,17 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
     auto body = [&]() -> int {
         MIMO_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         MIMO_CUDA(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
-        MIMO_CUDA(cudaMalloc(&dZ, std::max<size_t>(zb, 16)));
-        MIMO_CUDA(cudaMalloc(&dA, ab));
-        MIMO_CUDA(cudaMalloc(&dC, (size_t)K * es));
-        MIMO_CUDA(cudaMalloc(&dfi, (size_t)F * 4));
-        MIMO_CUDA(cudaMalloc(&dfj, (size_t)F * 4));
-        MIMO_CUDA(cudaMalloc(&dstat, (size_t)K * F * 8));
-        MIMO_CUDA(cudaMalloc(&dlse, 8));
-        MIMO_CUDA(cudaMalloc(&dws, std::max<size_t>(wsb, 16)));
-        if (family == 1) { MIMO_CUDA(cudaMalloc(&dB, ab)); MIMO_CUDA(cudaMemcpyAsync(dB, op_b_host, ab, cudaMemcpyHostToDevice, st)); }
-        if (hard) MIMO_CUDA(cudaMalloc(&dlab, std::max<size_t>((size_t)N * 4, 16)));
-        if (uniforms_host) MIMO_CUDA(cudaMalloc(&duni, std::max<size_t>((size_t)N * 8, 16)));
+        MIMO_CUDA(g_host_cache.get(0, zb, (void**)&dZ));
+        MIMO_CUDA(g_host_cache.get(1, ab, (void**)&dA));
+        MIMO_CUDA(g_host_cache.get(2, (size_t)K * es, (void**)&dC));
+        MIMO_CUDA(g_host_cache.get(3, (size_t)F * 4, (void**)&dfi));
+        MIMO_CUDA(g_host_cache.get(4, (size_t)F * 4, (void**)&dfj));
+        MIMO_CUDA(g_host_cache.get(5, (size_t)K * F * 8, (void**)&dstat));
+        MIMO_CUDA(g_host_cache.get(6, 8, (void**)&dlse));
+        MIMO_CUDA(g_host_cache.get(7, wsb, (void**)&dws));
+        if (family == 1) { MIMO_CUDA(g_host_cache.get(8, ab, (void**)&dB)); MIMO_CUDA(cudaMemcpyAsync(dB, op_b_host, ab, cudaMemcpyHostToDevice, st)); }
+        if (hard) MIMO_CUDA(g_host_cache.get(9, (size_t)N * 4, (void**)&dlab));
+        if (uniforms_host) MIMO_CUDA(g_host_cache.get(10, (size_t)N * 8, (void**)&duni));
         MIMO_CUDA(cudaMemcpyAsync(dA, op_a_host, ab, cudaMemcpyHostToDevice, st));
         MIMO_CUDA(cudaMemcpyAsync(dC, cst_host, (size_t)K * es, cudaMemcpyHostToDevice, st));
         MIMO_CUDA(cudaMemcpyAsync(dfi, fi_host, (size_t)F * 4, cudaMemcpyHostToDevice, st));
@@ -332,10 +363,9 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
     };
     rc = body();
     if (rc != MIMO_OK) cudaDeviceSynchronize();
-    tc_screen_forget();                                   // its counters live in the workspace freed below
+    tc_screen_forget();                                   // its counters live in a workspace the next call may replace
     for (auto e : landed) if (e) cudaEventDestroy(e);
-    cudaFree(dZ); cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dws); cudaFree(dfi); cudaFree(dfj);
-    cudaFree(dlab); cudaFree(dstat); cudaFree(dlse); cudaFree(duni);
+    if (rc != MIMO_OK) g_host_cache.release();
     if (st) cudaStreamDestroy(st);
     if (sc) cudaStreamDestroy(sc);
     if (dbg) fprintf(stderr, "mimo_sweep_host: buffers freed at %.1f ms\n", now() - t_start);

@@ -119,45 +119,63 @@ screen_scatterA_kernel(const int* __restrict__ guess_k, int64_t n, int* __restri
 
 // list B: every pair whose upper bound reaches the point's threshold L_n - 40 (its guess excluded: already exact)
 // counters: [0] list B entries found, [1] dense flag (set by screen_scan_kernel), [2] always 0
+// grid = (point tiles of EMIT_PTS, component groups of EMIT_KG): a CTA streams EMIT_KG rows of 4 KB each (the rows of
+// the scratch lie megabytes apart, so a CTA that walked all K rows would touch K pages of the TLB per kilobyte read);
+// thread = 4 consecutive points (one 128-bit streaming load per row).  Candidates are rare: one ballot per row decides
+// whether any lane of the warp has one at all.
+constexpr int EMIT_PTS = 1024;
+constexpr int EMIT_KG = 16;
+
 __global__ void __launch_bounds__(256)
-screen_emit_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, const float* __restrict__ cst,
+screen_emit_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, int vec4, const float* __restrict__ cst,
                    const unsigned int* __restrict__ flags_proj, const unsigned int* __restrict__ flags_full,
                    const float* __restrict__ lower, const int* __restrict__ guess_k,
                    int2* __restrict__ list, unsigned int cap, unsigned int* __restrict__ counters, int* __restrict__ hist,
                    const unsigned int* __restrict__ level) {
     if (*level >= 2u) return;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < n;
     const float B = screen_bound(*level == 0u ? flags_proj : flags_full);      // the bound of the tier that produced the values
-    const float t = valid ? lower[i] - SCREEN_T0 - 0.01f * (1.f + 1e-4f * fabsf(lower[i])) : INFINITY;   // FP32 slack of the exact value
-    const int gk = valid ? guess_k[i] : -1;
+    const int64_t i0 = (int64_t)blockIdx.x * EMIT_PTS + threadIdx.x * 4;
+    const int k_lo = blockIdx.y * EMIT_KG, k_hi = min(K, k_lo + EMIT_KG);
     const int lane = threadIdx.x & 31;
-    for (int k0 = 0; k0 < K; k0 += 8) {
-      float av[8];
+    float t[4];
+    int gk[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) av[u] = (valid && k0 + u < K) ? __ldcs(a + (int64_t)(k0 + u) * ldo + i) : 0.f;   // 8 streaming loads in flight
+    for (int e = 0; e < 4; ++e) {
+        const bool valid = i0 + e < n;
+        const float lw = valid ? lower[i0 + e] : 0.f;
+        t[e] = valid ? lw - SCREEN_T0 - 0.01f * (1.f + 1e-4f * fabsf(lw)) : INFINITY;     // FP32 slack of the exact value
+        gk[e] = valid ? guess_k[i0 + e] : -1;
+    }
+    for (int k = k_lo; k < k_hi; ++k) {
+        float av[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* row = a + (int64_t)k * ldo + i0;
+        if (vec4 && i0 + 3 < n) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(row));
+            av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+        } else {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int k = k0 + u;
-        if (k >= K) break;
-        bool cand = false;
-        if (valid && k != gk) {
-            const float c = __ldg(cst + k);
-            const float s = fmaxf(0.f, sqrtf(fmaxf(0.f, 2.f * (c - av[u]))) - B);
-            cand = (c - 0.5f * s * s) >= t;
+            for (int e = 0; e < 4; ++e) if (i0 + e < n) av[e] = __ldcs(row + e);
         }
-        const unsigned int m = __ballot_sync(0xffffffffu, cand);
-        if (m) {
-            unsigned int base = 0;
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) { base = atomicAdd(counters, (unsigned int)__popc(m)); atomicAdd(hist + k, __popc(m)); }
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (cand) {
-                const unsigned int slot = base + __popc(m & ((1u << lane) - 1u));
-                if (slot < cap) list[slot] = make_int2(k, (int)i);
-            }
+        const float c = __ldg(cst + k);
+        unsigned int mine = 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float s = fmaxf(0.f, sqrtf(fmaxf(0.f, 2.f * (c - av[e]))) - B);
+            if ((c - 0.5f * s * s) >= t[e] && k != gk[e]) mine |= 1u << e;
         }
-      }
+        if (__ballot_sync(0xffffffffu, mine != 0u) == 0u) continue;          // the common case: nothing in this warp
+        // warp-aggregated append: exclusive prefix of the per-lane counts
+        const int cnt = __popc(mine);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned int base = 0;
+        if (lane == 0) { base = atomicAdd(counters, (unsigned int)total); atomicAdd(hist + k, total); }
+        base = __shfl_sync(0xffffffffu, base, 0) + (unsigned int)(incl - cnt);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (mine & (1u << e)) { if (base < cap) list[base] = make_int2(k, (int)(i0 + e)); ++base; }
     }
 }
 
@@ -517,8 +535,10 @@ int tc_screen_select(const float* Z, int D, int64_t ldz, const float* W, const f
     MIMO_LAUNCH_CHECK();
     int rc = refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.A.perm), (const int*)(base + L.A.offsets), level, 2u, a, ldo, lower, st);
     if (rc) return rc;
-    screen_emit_kernel<<<grid, 256, 0, st>>>(a, K, n, ldo, cst, tc_flags(screen_ops_ws(ops_ws, sops_ws, K, Rp, Dpp)), tc_flags(ops_ws),
-                                             lower, guess_k, (int2*)(base + L.off_list), L.cap, counters, (int*)(base + L.B.hist), level);
+    const int evec4 = (ldo % 4 == 0) && (((uintptr_t)a & 15) == 0);
+    screen_emit_kernel<<<dim3(cdiv(n, EMIT_PTS), cdiv(K, EMIT_KG)), 256, 0, st>>>(
+        a, K, n, ldo, evec4, cst, tc_flags(screen_ops_ws(ops_ws, sops_ws, K, Rp, Dpp)), tc_flags(ops_ws),
+        lower, guess_k, (int2*)(base + L.off_list), L.cap, counters, (int*)(base + L.B.hist), level);
     const double maxc = std::min<double>((double)L.cap, 0.04 * (double)n * K);
     screen_scan_kernel<<<1, 32, 0, st>>>((const int*)(base + L.B.hist), K, (int*)(base + L.B.offsets), (int*)(base + L.B.cursor),
                                          (int*)(base + L.B.slabs), counters, (unsigned int)maxc, level);

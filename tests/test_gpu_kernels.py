@@ -516,6 +516,7 @@ def test_sweep_host_matches_resident_sweep(hard, K, d, N, segment):
                   u.ctypes.data if hard else None, 5, stat_h.ctypes.data, lse_h.ctypes.data, lab_h.ctypes.data if hard else None)
     finally:
         _lib.call('mimo_sweep_host_set_segment', 0)
+        _lib.call('mimo_sweep_host_release')
     close(stat_h, buf.stat.cpu().numpy(), 1e-5, 'host-buffer sweep statistics')
     close(lse_h, buf.lse_sum.cpu().numpy().reshape(1), 1e-6, 'host-buffer sweep lse sum')
     if hard:
