@@ -11,10 +11,12 @@
 //     pair outside the list has a responsibility below e^-40, so the list carries the whole statistic to FP32
 //     resolution; when the list would be long (overlapping components) the dense tensor-core kernels run instead.
 //
-// One work item = (component, slab of <= PS_SLAB listed points).  The CTA gathers 32 rows at a time into shared
-// memory (plain and r-scaled copies) and accumulates the lower triangle of the (D+1) x (D+1) outer-product sum in
-// 8 x 8 register tiles, one tile per thread (FP32 FMA pipe; 153 tiles at D = 128); the slab total is added to the
-// FP64 statistics with one atomic per element.  For small D several thread groups split the 32 rows.
+// One work item = (component, slab of <= PS_SLAB listed points).  The CTA gathers 32 rows at a time into a
+// double-buffered shared-memory tile with cp.async (the gather of the next 32 rows runs under the arithmetic of the
+// current ones) and accumulates the lower triangle of the (D+1) x (D+1) outer-product sum in 8 x 8 register tiles,
+// one tile per thread (FP32 FMA pipe; 153 tiles at D = 128; the row weight is applied to the 8 row-side values as
+// they are read); the slab total is added to the FP64 statistics with one atomic per element.  For small D several
+// thread groups split the 32 rows.
 #include <algorithm>
 #include "common.cuh"
 #include "internal.h"
@@ -27,6 +29,13 @@ constexpr int PS_PT = 32;
 // column c of a staged row: 4 floats of padding after every 32 so that the 8-float groups t and t + 4 of one row
 // start in different banks (the 128-bit reads of 8 consecutive threads then never collide)
 __device__ __forceinline__ int ps_off(int c) { return c + ((c >> 5) << 2); }
+
+__device__ __forceinline__ void ps_cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ps_cp_async4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
 
 __global__ void __launch_bounds__(PS_THREADS, 3)
 pair_stats_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
@@ -41,10 +50,8 @@ pair_stats_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
     const int ntiles = T * (T + 1) / 2;
     const int G = max(1, PS_THREADS / ntiles);        // thread groups splitting the rows of a tile
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* As = reinterpret_cast<float*>(smem_raw);   // [PT][RS]  r * zt
-    float* Bs = As + PS_PT * RS;                      // [PT][RS]  zt
-    __shared__ int s_idx[PS_PT];
-    __shared__ float s_w[PS_PT];
+    float* Bs0 = reinterpret_cast<float*>(smem_raw);  // 2 x [PT][RS]  zt, double buffered (rows gathered with cp.async)
+    __shared__ float s_w[2][PS_PT];                   // weight of each staged row
 
     const int tid = threadIdx.x;
     const int g = tid / ntiles, e = tid - g * ntiles;
@@ -54,6 +61,39 @@ pair_stats_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
     const int tj = e - ti * (ti + 1) / 2;
     const int offa = ps_off(ti << 3), offb = ps_off(tj << 3);
     const int n_items = slabs[K];
+
+    // gather of the listed rows [p0, p0 + np) into buffer b: data columns asynchronously, the 1 / padding columns and
+    // the row weights with plain stores
+    auto prefetch = [&](int k, int b, int p0, int np) {
+        float* Bs = Bs0 + (size_t)b * PS_PT * RS;
+        if (tid < np) {
+            float w = 1.f;                            // hard labels
+            if (R) {
+                const int n = __ldg(perm + p0 + tid);
+                w = __ldg(R + (int64_t)k * ldr + n);                            // responsibility ...
+                if (lse) w = __expf(w - __ldg(lse + n));                        // ... or log-joint and the point's log-normaliser
+            }
+            s_w[b][tid] = w;
+        }
+        if (vec4) {
+            const int q = D >> 2;
+            for (int idx = tid; idx < np * q; idx += PS_THREADS) {
+                const int p = idx / q, c = (idx - p * q) << 2;
+                ps_cp_async16(Bs + p * RS + ps_off(c), Z + (int64_t)__ldg(perm + p0 + p) * ldz + c);
+            }
+        } else {
+            for (int idx = tid; idx < np * D; idx += PS_THREADS) {
+                const int p = idx / D, c = idx - p * D;
+                ps_cp_async4(Bs + p * RS + ps_off(c), Z + (int64_t)__ldg(perm + p0 + p) * ldz + c);
+            }
+        }
+        const int tail = W8 - D;                      // the 1 column and the zero padding of the last group
+        for (int idx = tid; idx < np * tail; idx += PS_THREADS) {
+            const int p = idx / tail, c = D + (idx - p * tail);
+            Bs[p * RS + ps_off(c)] = (c == D) ? 1.f : 0.f;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int lo = 0, hi = K;                           // item -> component: last k with slabs[k] <= item
@@ -71,56 +111,28 @@ pair_stats_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
 #pragma unroll
             for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
 
-        for (int p0 = beg; p0 < end; p0 += PS_PT) {
+        __syncthreads();                              // previous item done with both buffers
+        prefetch(k, 0, beg, min(PS_PT, end - beg));
+        int buf = 0;
+        for (int p0 = beg; p0 < end; p0 += PS_PT, buf ^= 1) {
             const int np = min(PS_PT, end - p0);
-            __syncthreads();                          // previous tile consumed
-            if (tid < np) {
-                const int n = perm[p0 + tid];
-                s_idx[tid] = n;
-                float w = 1.f;                    // hard labels
-                if (R) {
-                    w = __ldg(R + (int64_t)k * ldr + n);                        // responsibility ...
-                    if (lse) w = __expf(w - __ldg(lse + n));                    // ... or log-joint and the point's log-normaliser
-                }
-                s_w[tid] = w;
-            }
-            __syncthreads();
-            if (vec4) {
-                const int q = D >> 2;
-                for (int idx = tid; idx < np * q; idx += PS_THREADS) {
-                    const int p = idx / q, c = (idx - p * q) << 2;
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(Z + (int64_t)s_idx[p] * ldz + c));
-                    const float w = s_w[p];
-                    const int o = p * RS + ps_off(c);
-                    *reinterpret_cast<float4*>(Bs + o) = v;
-                    *reinterpret_cast<float4*>(As + o) = make_float4(w * v.x, w * v.y, w * v.z, w * v.w);
-                }
-                const int tail = W8 - D;              // the 1 column and the zero padding of the last group
-                for (int idx = tid; idx < np * tail; idx += PS_THREADS) {
-                    const int p = idx / tail, c = D + (idx - p * tail);
-                    const float v = (c == D) ? 1.f : 0.f;
-                    const int o = p * RS + ps_off(c);
-                    Bs[o] = v;
-                    As[o] = s_w[p] * v;
-                }
+            if (p0 + PS_PT < end) {                   // the other buffer was released by the barrier that ended the previous tile
+                prefetch(k, buf ^ 1, p0 + PS_PT, min(PS_PT, end - p0 - PS_PT));
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
             } else {
-                for (int idx = tid; idx < np * W8; idx += PS_THREADS) {
-                    const int p = idx / W8, c = idx - p * W8;
-                    const float v = (c < D) ? __ldg(Z + (int64_t)s_idx[p] * ldz + c) : (c == D ? 1.f : 0.f);
-                    const int o = p * RS + ps_off(c);
-                    Bs[o] = v;
-                    As[o] = s_w[p] * v;
-                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
-            __syncthreads();
+            __syncthreads();                          // this tile's rows and weights visible to everyone
             if (active) {
+                const float* Bs = Bs0 + (size_t)buf * PS_PT * RS;
 #pragma unroll 2
                 for (int p = g; p < np; p += G) {
-                    const float4 a0 = *reinterpret_cast<const float4*>(As + p * RS + offa);
-                    const float4 a1 = *reinterpret_cast<const float4*>(As + p * RS + offa + 4);
+                    const float w = s_w[buf][p];
+                    const float4 a0 = *reinterpret_cast<const float4*>(Bs + p * RS + offa);
+                    const float4 a1 = *reinterpret_cast<const float4*>(Bs + p * RS + offa + 4);
                     const float4 b0 = *reinterpret_cast<const float4*>(Bs + p * RS + offb);
                     const float4 b1 = *reinterpret_cast<const float4*>(Bs + p * RS + offb + 4);
-                    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const float a[8] = {w * a0.x, w * a0.y, w * a0.z, w * a0.w, w * a1.x, w * a1.y, w * a1.z, w * a1.w};
                     const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                     for (int x = 0; x < 8; ++x)
@@ -128,6 +140,7 @@ pair_stats_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
                         for (int y = 0; y < 8; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
                 }
             }
+            __syncthreads();                          // tile consumed: its buffer may be refilled
         }
         if (active) {
             double* out = stat + (int64_t)k * F;

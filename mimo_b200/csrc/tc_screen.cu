@@ -34,8 +34,7 @@ using tc::screen_bound;
 
 constexpr float SCREEN_T0 = 40.f;
 constexpr int SCREEN_ROWS = 32;              // rows of the screening operands
-constexpr int RF_THREADS = 256;
-constexpr int RF_SPLIT = 8;                  // blocks per component
+constexpr int RF_THREADS = 512;
 constexpr int RF_CPT = 8;                    // candidates per thread (x 4 rows: 32 accumulators)
 
 // max_n ||z_n||_2: one warp per row (grid-stride)
@@ -214,88 +213,129 @@ __global__ void screen_scatter_kernel(const int2* __restrict__ list, const unsig
     }
 }
 
-// Exact (FP32 FMA) recomputation of the candidates of one component.  grid = (K, RF_SPLIT).
-// Thread (rg, cg): rows rg + RG r (r < 4), candidates RF_CPT cg + c (c < RF_CPT) of a tile of TILE_C candidates.
+// Exact (FP32 FMA) recomputation of a list of candidates grouped by component.
+// Work item = (component, slab of <= PS_SLAB listed candidates) on a persistent grid (one CTA per SM): the component's
+// operand block W_k stays in shared memory for the whole slab, candidate rows are gathered TILE_C at a time into a
+// double-buffered tile with cp.async, so the gather of tile i + 1 runs under the arithmetic of tile i.
+// Thread (rg, cg): rows rg + RG r (r < 4), candidates RF_CPT cg + c (c < RF_CPT) of the tile.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int RP>
-__global__ void __launch_bounds__(RF_THREADS)
+__global__ void __launch_bounds__(RF_THREADS, 1)
 screen_refine_kernel(const float* __restrict__ Z, int D, int64_t ldz, int vec4,
-                     const float* __restrict__ W, int Dpp, const float* __restrict__ cst,
-                     const int* __restrict__ perm, const int* __restrict__ offsets, const unsigned int* __restrict__ gate, unsigned int gate_min,
+                     const float* __restrict__ W, int K, int Dpp, const float* __restrict__ cst,
+                     const int* __restrict__ perm, const int* __restrict__ offsets, const int* __restrict__ slabs,
+                     const unsigned int* __restrict__ gate, unsigned int gate_min,
                      float* __restrict__ a, int64_t ldo, float* __restrict__ exact) {
     if (gate != nullptr && *gate >= gate_min) return;          // dense pass instead
     constexpr int RG = RP / 4, CG = RF_THREADS / RG, TILE_C = RF_CPT * CG;
-    const int k = blockIdx.x;
-    const int beg = offsets[k], cnt = offsets[k + 1] - beg;
-    const int tiles = (cnt + TILE_C - 1) / TILE_C;
-    if ((int)blockIdx.y >= tiles) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* Ws = reinterpret_cast<float*>(smem_raw);            // [RP][Dpp]
-    float* Zs = Ws + (size_t)RP * Dpp;                         // [TILE_C][Dpp]   (column D = 1, beyond = 0)
+    float* Zs0 = Ws + (size_t)RP * Dpp;                        // 2 x [TILE_C][Dpp]   (column D = 1, beyond = 0)
     const int tid = threadIdx.x, rg = tid % RG, cg = tid / RG;
-    for (int idx = tid; idx < RP * Dpp / 4; idx += RF_THREADS)
-        reinterpret_cast<float4*>(Ws)[idx] = __ldg(reinterpret_cast<const float4*>(W + (size_t)k * RP * Dpp) + idx);
-    const float ck = __ldg(cst + k);
-    for (int t = blockIdx.y; t < tiles; t += gridDim.y) {
-        const int c0 = beg + t * TILE_C, nc = min(TILE_C, beg + cnt - c0);
-        __syncthreads();                                       // Ws ready / previous tile consumed
-        if (vec4) {                                            // rows as float4: several gathers in flight per thread
-            const int q4 = D >> 2, tail = Dpp - D;
-#pragma unroll 4
+    const int n_items = slabs[K];
+    int k_loaded = -1;
+
+    // gather of one tile (asynchronous for the data columns; rows beyond the tile are zero-filled)
+    auto prefetch = [&](float* Zs, int c0, int nc) {
+        if (vec4) {
+            const int q4 = D >> 2;
             for (int idx = tid; idx < TILE_C * q4; idx += RF_THREADS) {
                 const int c = idx / q4, j = (idx - c * q4) << 2;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < nc) v = __ldg(reinterpret_cast<const float4*>(Z + (int64_t)__ldg(perm + c0 + c) * ldz + j));
-                *reinterpret_cast<float4*>(Zs + (size_t)c * Dpp + j) = v;
-            }
-            for (int idx = tid; idx < TILE_C * tail; idx += RF_THREADS) {
-                const int c = idx / tail, j = D + (idx - c * tail);
-                Zs[(size_t)c * Dpp + j] = (c < nc && j == D) ? 1.f : 0.f;
+                const bool ok = c < nc;
+                const float* src = ok ? Z + (int64_t)__ldg(perm + c0 + c) * ldz + j : Z;
+                cp_async16(Zs + (size_t)c * Dpp + j, src, ok ? 16 : 0);
             }
         } else {
-            for (int idx = tid; idx < TILE_C * Dpp; idx += RF_THREADS) {
-                const int c = idx / Dpp, j = idx - c * Dpp;
-                float v = 0.f;
-                if (c < nc) v = (j < D) ? __ldg(Z + (int64_t)perm[c0 + c] * ldz + j) : (j == D ? 1.f : 0.f);
-                Zs[idx] = v;
+            for (int idx = tid; idx < TILE_C * D; idx += RF_THREADS) {
+                const int c = idx / D, j = idx - c * D;
+                const bool ok = c < nc;
+                const float* src = ok ? Z + (int64_t)__ldg(perm + c0 + c) * ldz + j : Z;
+                cp_async4(Zs + (size_t)c * Dpp + j, src, ok ? 4 : 0);
             }
         }
-        __syncthreads();
-        float acc[4][RF_CPT];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < RF_CPT; ++c) acc[r][c] = 0.f;
-#pragma unroll 2
-        for (int j = 0; j < Dpp; j += 4) {
-            float4 w[4], z[RF_CPT];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) w[r] = *reinterpret_cast<const float4*>(Ws + (size_t)(rg + RG * r) * Dpp + j);
-#pragma unroll
-            for (int c = 0; c < RF_CPT; ++c) z[c] = *reinterpret_cast<const float4*>(Zs + (size_t)(RF_CPT * cg + c) * Dpp + j);
+        const int tail = Dpp - D;
+        for (int idx = tid; idx < TILE_C * tail; idx += RF_THREADS) {
+            const int c = idx / tail, j = D + (idx - c * tail);
+            Zs[(size_t)c * Dpp + j] = (c < nc && j == D) ? 1.f : 0.f;
+        }
+        cp_async_commit();
+    };
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int lo = 0, hi = K;                                    // item -> component: last k with slabs[k] <= item
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (slabs[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int k = lo;
+        const int beg = offsets[k] + (item - slabs[k]) * PS_SLAB;
+        const int end = min(offsets[k + 1], beg + PS_SLAB);
+        if (beg >= end) continue;
+        __syncthreads();                                       // previous item done with Ws and both tiles
+        if (k != k_loaded) {
+            for (int idx = tid; idx < RP * Dpp / 4; idx += RF_THREADS)
+                reinterpret_cast<float4*>(Ws)[idx] = __ldg(reinterpret_cast<const float4*>(W + (size_t)k * RP * Dpp) + idx);
+            k_loaded = k;
+        }
+        const float ck = __ldg(cst + k);
+        const int ntiles = (end - beg + TILE_C - 1) / TILE_C;
+        prefetch(Zs0, beg, min(TILE_C, end - beg));
+        for (int t = 0; t < ntiles; ++t) {
+            float* Zs = Zs0 + (size_t)(t & 1) * TILE_C * Dpp;
+            const int c0 = beg + t * TILE_C, nc = min(TILE_C, end - c0);
+            if (t + 1 < ntiles) {                              // the other buffer was released by the barrier that ended tile t - 1
+                prefetch(Zs0 + (size_t)((t + 1) & 1) * TILE_C * Dpp, c0 + TILE_C, min(TILE_C, end - c0 - TILE_C));
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();                                   // tile t (and Ws) visible to everyone
+            float acc[4][RF_CPT];
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int c = 0; c < RF_CPT; ++c) {
-                    acc[r][c] = fmaf(w[r].x, z[c].x, acc[r][c]);
-                    acc[r][c] = fmaf(w[r].y, z[c].y, acc[r][c]);
-                    acc[r][c] = fmaf(w[r].z, z[c].z, acc[r][c]);
-                    acc[r][c] = fmaf(w[r].w, z[c].w, acc[r][c]);
-                }
-        }
+                for (int c = 0; c < RF_CPT; ++c) acc[r][c] = 0.f;
+#pragma unroll 2
+            for (int j = 0; j < Dpp; j += 4) {
+                float4 w[4], z[RF_CPT];
 #pragma unroll
-        for (int c = 0; c < RF_CPT; ++c) {
-            float q = 0.f;
+                for (int r = 0; r < 4; ++r) w[r] = *reinterpret_cast<const float4*>(Ws + (size_t)(rg + RG * r) * Dpp + j);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) q = fmaf(acc[r][c], acc[r][c], q);
+                for (int c = 0; c < RF_CPT; ++c) z[c] = *reinterpret_cast<const float4*>(Zs + (size_t)(RF_CPT * cg + c) * Dpp + j);
 #pragma unroll
-            for (int o = RG / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);    // over the RG lanes of this candidate group
-            const int ci = RF_CPT * cg + c;
-            if (rg == 0 && ci < nc) {
-                const int n = perm[c0 + ci];
-                const float val = ck - 0.5f * q;
-                a[(int64_t)k * ldo + n] = val;
-                if (exact) exact[n] = val;                     // list A: the point's guess, exactly (a lower bound of its best log-joint)
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < RF_CPT; ++c) {
+                        acc[r][c] = fmaf(w[r].x, z[c].x, acc[r][c]);
+                        acc[r][c] = fmaf(w[r].y, z[c].y, acc[r][c]);
+                        acc[r][c] = fmaf(w[r].z, z[c].z, acc[r][c]);
+                        acc[r][c] = fmaf(w[r].w, z[c].w, acc[r][c]);
+                    }
             }
+#pragma unroll
+            for (int c = 0; c < RF_CPT; ++c) {
+                float q = 0.f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) q = fmaf(acc[r][c], acc[r][c], q);
+#pragma unroll
+                for (int o = RG / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);    // over the RG lanes of this candidate group
+                const int ci = RF_CPT * cg + c;
+                if (rg == 0 && ci < nc) {
+                    const int n = perm[c0 + ci];
+                    const float val = ck - 0.5f * q;
+                    a[(int64_t)k * ldo + n] = val;
+                    if (exact) exact[n] = val;                 // list A: the point's guess, exactly (a lower bound of its best log-joint)
+                }
+            }
+            __syncthreads();                                   // tile t consumed: its buffer may be refilled
         }
     }
 }
@@ -493,22 +533,24 @@ int tc_screen_last(unsigned int* out_host2) {
 
 template <int RP>
 static int launch_refine(const float* Z, int D, int64_t ldz, const float* W, int K, int Dpp, const float* cst,
-                         const int* perm, const int* offsets, const unsigned int* gate, unsigned int gate_min, float* a, int64_t ldo,
-                         float* exact, cudaStream_t st) {
+                         const int* perm, const int* offsets, const int* slabs, const unsigned int* gate, unsigned int gate_min,
+                         float* a, int64_t ldo, float* exact, cudaStream_t st) {
     constexpr int TILE_C = RF_CPT * (RF_THREADS / (RP / 4));
-    const size_t smem = (size_t)(RP + TILE_C) * Dpp * sizeof(float);
+    const size_t smem = (size_t)(RP + 2 * TILE_C) * Dpp * sizeof(float);
+    if (smem > 227 * 1024) { set_error("screened E-step: refinement tile needs %zu B of shared memory", smem); return MIMO_EUNSUPPORTED; }
     const int vec4 = (D % 4 == 0) && (Dpp % 4 == 0) && (ldz % 4 == 0) && (((uintptr_t)Z & 15) == 0);
     MIMO_CUDA(cudaFuncSetAttribute(screen_refine_kernel<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    screen_refine_kernel<RP><<<dim3(K, RF_SPLIT), RF_THREADS, smem, st>>>(Z, D, ldz, vec4, W, Dpp, cst, perm, offsets, gate, gate_min, a, ldo, exact);
+    screen_refine_kernel<RP><<<sm_count(), RF_THREADS, smem, st>>>(Z, D, ldz, vec4, W, K, Dpp, cst, perm, offsets, slabs, gate, gate_min,
+                                                                    a, ldo, exact);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
 static int refine(const float* Z, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp, const float* cst,
-                  const int* perm, const int* offsets, const unsigned int* gate, unsigned int gate_min, float* a, int64_t ldo,
-                  float* exact, cudaStream_t st) {
-    if (Rp == 32) return launch_refine<32>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, gate, gate_min, a, ldo, exact, st);
-    if (Rp == 64) return launch_refine<64>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, gate, gate_min, a, ldo, exact, st);
-    if (Rp == 128) return launch_refine<128>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, gate, gate_min, a, ldo, exact, st);
+                  const int* perm, const int* offsets, const int* slabs, const unsigned int* gate, unsigned int gate_min,
+                  float* a, int64_t ldo, float* exact, cudaStream_t st) {
+    if (Rp == 32) return launch_refine<32>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, slabs, gate, gate_min, a, ldo, exact, st);
+    if (Rp == 64) return launch_refine<64>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, slabs, gate, gate_min, a, ldo, exact, st);
+    if (Rp == 128) return launch_refine<128>(Z, D, ldz, W, K, Dpp, cst, perm, offsets, slabs, gate, gate_min, a, ldo, exact, st);
     set_error("screened E-step: unsupported Rp=%d", Rp);
     return MIMO_EUNSUPPORTED;
 }
@@ -533,7 +575,7 @@ int tc_screen_select(const float* Z, int D, int64_t ldz, const float* W, const f
                                          (int*)(base + L.A.slabs), nullptr, 0u, nullptr);
     screen_scatterA_kernel<<<grid, 256, 0, st>>>(guess_k, n, (int*)(base + L.A.cursor), (int*)(base + L.A.perm), level);
     MIMO_LAUNCH_CHECK();
-    int rc = refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.A.perm), (const int*)(base + L.A.offsets), level, 2u, a, ldo, lower, st);
+    int rc = refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.A.perm), (const int*)(base + L.A.offsets), (const int*)(base + L.A.slabs), level, 2u, a, ldo, lower, st);
     if (rc) return rc;
     const int evec4 = (ldo % 4 == 0) && (((uintptr_t)a & 15) == 0);
     screen_emit_kernel<<<dim3(cdiv(n, EMIT_PTS), cdiv(K, EMIT_KG)), 256, 0, st>>>(
@@ -554,7 +596,7 @@ int tc_screen_refine(const float* Z, int D, int64_t ldz, const float* W, int K, 
     const unsigned int* counters = (const unsigned int*)(base + L.off_counters);
     screen_scatter_kernel<<<sm_count() * 4, 256, 0, st>>>((const int2*)(base + L.off_list), counters, (int*)(base + L.B.cursor), (int*)(base + L.B.perm));
     MIMO_LAUNCH_CHECK();
-    return refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.B.perm), (const int*)(base + L.B.offsets), counters + 1, 1u, a, ldo, nullptr, st);
+    return refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.B.perm), (const int*)(base + L.B.offsets), (const int*)(base + L.B.slabs), counters + 1, 1u, a, ldo, nullptr, st);
 }
 
 // log-normalisers of the chunk from the lists (after tc_screen_refine): per-point lse into the workspace, their sum
