@@ -108,6 +108,8 @@ int mimo_softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags,
 int mimo_set_tensor_cores(int mode);
 /* {candidate pairs, dense-fallback flag} of the most recent screened point chunk (synchronises; diagnostics) */
 int mimo_tc_screen_last(uint32_t* out_host2);
+/* screening tier the most recent screened sweep ended on: 0 projection, 1 all operand rows, 2 none (dense); -1 unknown */
+int mimo_tc_screen_level(void);
 int mimo_sweep_uses_tensor_cores(int dtype, int family, int D, int Rp);
 int mimo_tc_set_flush_tiles(int tiles);     /* 128-point tiles accumulated in TMEM (FP32) between FP64 drains */
 size_t mimo_loglik_quad_tc_workspace(int K, int Rp, int D);

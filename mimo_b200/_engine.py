@@ -451,6 +451,11 @@ def screen_last():
     return int(out[0]), int(out[1])
 
 
+def screen_level():
+    """screening tier the most recent screened sweep ended on (0 projection, 1 all rows, 2 none; -1 unknown)."""
+    return int(_lib.load().mimo_tc_screen_level())
+
+
 def sweep_uses_tensor_cores(ops, D):
     return bool(_lib.load().mimo_sweep_uses_tensor_cores(code(ops.precision), ops.family, D, ops.Rp))
 

@@ -105,6 +105,7 @@ int mimo_sweep_timed(int dtype, int family, int hard, const void* Z, int64_t N, 
                  point_offset, stat, lse_sum, labels_out, lse_out, ll_out, ldo, workspace, workspace_bytes, ST(stream),
                  phase_ms_host);
 }
+int mimo_tc_screen_level(void) { return tc_screen_level(); }
 int mimo_sweep_host_release(void) { sweep_host_release(); return MIMO_OK; }
 int mimo_sweep_host_set_segment(int64_t points) { sweep_host_set_segment(points); return MIMO_OK; }
 int mimo_sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, int D,

@@ -46,6 +46,7 @@ int tc_screen_begin(int64_t plan_points, int K, int Rp, int start_level, void* w
 const unsigned int* tc_screen_gate(void* ws, int64_t plan_points, int K);
 int tc_screen_last(unsigned int* out_host2);
 void tc_screen_forget();
+int tc_screen_level();
 int tc_screen_select(const float* Z, int D, int64_t ldz, const float* W, const float* cst, int K, int Rp, int Dpp,
                      float* a, int64_t n, int64_t ldo, void* ops_ws, void* sops_ws, int64_t plan_points, void* ws, cudaStream_t st);
 int tc_screen_refine(const float* Z, int D, int64_t ldz, const float* W, int K, int Rp, int Dpp, const float* cst,

@@ -517,9 +517,18 @@ void tc_screen_lists(void* ws, int64_t plan_points, int K, int which, const int3
 }
 
 static const unsigned int* g_last_counters = nullptr;
+static const unsigned int* g_last_level = nullptr;
 static int64_t g_last_points = 0;
 
-void tc_screen_forget() { g_last_counters = nullptr; g_last_points = 0; }   // the workspace the counters live in is going away
+void tc_screen_forget() { g_last_counters = nullptr; g_last_level = nullptr; g_last_points = 0; }
+
+// screening tier the most recent sweep ended on (0 projection, 1 all rows, 2 none; -1 unknown); synchronises
+int tc_screen_level() {
+    if (!g_last_level) return -1;
+    unsigned int v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(&v, g_last_level, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int)v;
+}   // the workspace the counters live in is going away
 
 // {candidates (guesses + list B), dense flag} of the most recent screened chunk (synchronises the device; tests / bench reporting)
 int tc_screen_last(unsigned int* out_host2) {
@@ -563,6 +572,7 @@ int tc_screen_select(const float* Z, int D, int64_t ldz, const float* W, const f
     char* base = align256(ws);
     unsigned int* counters = (unsigned int*)(base + L.off_counters);
     g_last_counters = counters;
+    g_last_level = (const unsigned int*)(base + L.off_level);
     g_last_points = n;
     MIMO_CUDA(cudaMemsetAsync(base, 0, L.A.offsets, st));                   // counters + both histograms
     const int grid = cdiv(n, 256);

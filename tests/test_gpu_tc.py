@@ -286,6 +286,7 @@ def test_screened_sweep_large_properties():
     E.sweep(Z, ops, feats, buf)
     cands, dense = E.screen_last()
     assert dense == 0 and cands < 0.04 * N * K
+    assert E.screen_level() == 0                        # separated components: the projection tier all the way
     stat = buf.stat.cpu().numpy()
     counts = stat[:, -1]
     assert abs(counts.sum() - N) <= 1e-6 * N
@@ -317,3 +318,39 @@ def test_screened_sweep_large_properties():
     b2 = E.SweepBuffers(N - h, K, feats.F, 'fp32', True)
     E.sweep(Z[h:], ops, feats, b2, seed=99, offset=h)
     assert (b2.labels.cpu().numpy() == lab[h:]).mean() > 0.9999
+
+
+def test_screen_tiers_across_chunks():
+    """A sweep of several point chunks over moderately separated components (K = 1024, d = 100, centre spread 1.5): the
+    32-row projection leaves too many candidates on the first chunk, which takes the dense pass and moves the sweep to
+    the all-rows screening tier; the remaining chunks are screened there.  The device-side tier state must not change
+    the results: statistics and log-normalisers agree with the dense path."""
+    E = eng()
+    K, d, N = 1024, 100, 2_200_000
+    g = torch.Generator(device='cuda')
+    g.manual_seed(5)
+    centres = 1.5 * torch.randn(K, d, generator=g, device='cuda')
+    z = torch.randint(0, K, (N,), generator=g, device='cuda')
+    Z = (centres[z] + torch.randn(N, d, generator=g, device='cuda')).contiguous()
+    rng = np.random.default_rng(8)
+    mus = centres.double().cpu().numpy() + 0.05 * rng.standard_normal((K, d))
+    lmbdas = np.stack(K * [np.eye(d)]) * (0.8 + 0.4 * rng.random((K, 1, 1)))
+    ops = E.QuadOperands(K, d, d, 'fp32')
+    E.set_log_weights(ops, np.log(rng.dirichlet(5.0 * np.ones(K))))
+    E.operands_gauss(ops, E.to_dev(mus), E.to_dev(lmbdas)).check()
+    feats = E.quad_features(d)
+    buf = E.SweepBuffers(N, K, feats.F, 'fp32', False)
+    E.sweep(Z, ops, feats, buf)
+    cands, dense = E.screen_last()                      # the LAST chunk: screened on the all-rows tier
+    level = E.screen_level()
+    print('tiers across chunks: sweep ended on tier %d; last chunk %d candidates, dense fallback %d' % (level, cands, dense))
+    old = E.set_tensor_cores(3)
+    try:
+        ref = E.SweepBuffers(N, K, feats.F, 'fp32', False)
+        E.sweep(Z, ops, feats, ref)
+    finally:
+        E.set_tensor_cores(old)
+    close(buf.stat, ref.stat.cpu().numpy(), 2e-5, 'tiered vs dense statistics')
+    assert abs(ref.lse_sum.item() - buf.lse_sum.item()) <= 1e-6 * abs(ref.lse_sum.item())
+    assert abs(buf.stat.cpu().numpy()[:, -1].sum() - N) <= 1e-6 * N
+    assert dense == 0 and level == 1, 'the sweep should have moved to the all-rows tier and screened the last chunk there (level %d)' % level
