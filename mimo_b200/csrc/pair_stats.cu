@@ -5,11 +5,14 @@
 // (distributions/gaussian.py:491-505 with the dense one-hot / responsibility matrix of utils/data.py:160-169,
 //  mixtures/gmm.py:236, 289-297; lingauss.py:306-325 on z = [x | y]).
 //
-// Two callers:
+// Three callers:
 //   * Gibbs (hard labels): list(k) = the points labelled k (counting sort of stats.cu), r = 1;
-//   * mean field behind the screened E-step (tc_screen.cu): list(k) = the candidate points of component k.  Every
-//     pair outside the list has a responsibility below e^-40, so the list carries the whole statistic to FP32
-//     resolution; when the list would be long (overlapping components) the dense tensor-core kernels run instead.
+//   * mean field behind the screened E-step (tc_screen.cu): list(k) = the candidate points of component k,
+//     r = exp(a - lse_n) from the refined log-joint.  Every pair outside the list has a responsibility below e^-40,
+//     so the list carries the whole statistic to FP32 resolution; when the list would be long (overlapping
+//     components) the dense tensor-core kernels run instead;
+//   * mean field on the CUDA-core path, 16 <= D < 24: list(k) = the points with r >= e^-40 after the dense softmax
+//     (resp_list_* in tc_screen.cu), dense CUDA-core statistics above a break-even list length.
 //
 // One work item = (component, slab of <= PS_SLAB listed points).  The CTA gathers 32 rows at a time into a
 // double-buffered shared-memory tile with cp.async (the gather of the next 32 rows runs under the arithmetic of the

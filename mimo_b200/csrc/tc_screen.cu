@@ -23,7 +23,10 @@
 // (counting sort) and recomputed in FP32 on the CUDA cores, overwriting the scratch; the sufficient statistics are then
 // summed over the two lists only (pair_stats.cu).  When more than 4 % of the pairs are candidates (overlapping
 // components, early sweeps) refinement would cost more than it saves: a device-side flag then makes the dense 3-pass
-// tensor-core kernel and the dense statistics kernels run instead -- no host round trip either way.
+// tensor-core kernel and the dense statistics kernels run instead -- no host round trip either way -- and the rest of
+// the sweep moves one screening TIER up (device-side state): tier 0 the projection, tier 1 all operand rows in one
+// FP16 pass (q' = q: a tighter bound for moderately separated components at 4x the accumulator traffic), tier 2 no
+// screening.
 #include <algorithm>
 #include "tc_common.cuh"
 #include "internal.h"
