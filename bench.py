@@ -157,7 +157,8 @@ def make_data(w, n_local, lo, seed, dev):
         chol = torch.linalg.cholesky(cov)
         sig = None
     if w.get('stick') or w['kind'] == 'ilr':
-        v = torch.distributions.Beta(torch.tensor(1.0), torch.tensor(5.0 * K / 16)).sample((K,)).to(dev)
+        # seeded on the host: every rank and every run sees the same mixture weights (the global torch RNG is not seeded)
+        v = torch.from_numpy(np.random.default_rng(seed).beta(1.0, 5.0 * K / 16, size=K)).to(device=dev, dtype=torch.float32)
         v[-1] = 1.0
         pi = v * torch.cumprod(torch.cat([torch.ones(1, device=dev), 1 - v[:-1]]), 0)
         pi = (pi + 0.2 / K)

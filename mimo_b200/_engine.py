@@ -290,27 +290,38 @@ def identity_map(d, D):
 
 
 def nw_posterior(prior, stat, F, stat_idx, Dp, mode=0, tied=False, variates=None, ops=None, row_off=0,
-                 col_map=None, want_lik=False, want_vlb=True, info=None):
-    """prior = (m0 (K,d), kappa0 (K), psi0 (K,d,d), nu0 (K)) device FP64 tensors."""
+                 col_map=None, want_lik=False, want_vlb=True, info=None, k_range=None):
+    """prior = (m0 (K,d), kappa0 (K), psi0 (K,d,d), nu0 (K)) device FP64 tensors.
+    k_range = (k0, k1): update only the components [k0, k1) -- the outputs keep their full (K, ...) shapes and only
+    that slice (and that slice of the operand block in `ops`) is written; the sharded driver gathers the slices of
+    all ranks.  The kernels are one CTA per component, so a slice is bit-identical to the same rows of a full call."""
     m0, k0, p0, n0 = prior
     K, d = m0.shape
     out = dict(m=empty((K, d)), kappa=empty((K,)), psi=empty((K, d, d)), nu=empty((K,)))
     out['vlb'] = empty((K,)) if want_vlb else None
     out['lik_mu'] = empty((K, d)) if want_lik else None
     out['lik_lmbda'] = empty((K, d, d)) if want_lik else None
-    wsb = _lib.load().mimo_nw_workspace(K, d)
+    lo, hi = (0, K) if k_range is None else k_range
+    assert 0 <= lo < hi <= K and (k_range is None or not tied), 'a component slice needs untied components'
+    sl = slice(lo, hi)
+    Kl = hi - lo
+
+    def part(t):
+        return None if t is None else t[sl]
+    wsb = _lib.load().mimo_nw_workspace(Kl, d)
     ws = workspace(wsb)
     info = info or Info()
     var_t = to_dev(variates) if variates is not None else None
     W = ops.W if ops is not None else None
-    _lib.call('mimo_nw_posterior', K, d, int(tied), mode, ptr(m0), ptr(k0), ptr(p0), ptr(n0),
-              ptr(stat), F, ptr(stat_idx), Dp, ptr(var_t),
-              ptr(out['m']), ptr(out['kappa']), ptr(out['psi']), ptr(out['nu']),
-              ptr(out['lik_mu']), ptr(out['lik_lmbda']), ptr(out['vlb']),
-              code(ops.precision) if ops is not None else F64, ptr(W), ptr(ops.cst) if ops is not None else None,
+    _lib.call('mimo_nw_posterior', Kl, d, int(tied), mode, ptr(m0[sl]), ptr(k0[sl]), ptr(p0[sl]), ptr(n0[sl]),
+              ptr(stat[sl]), F, ptr(stat_idx), Dp, ptr(part(var_t)),
+              ptr(out['m'][sl]), ptr(out['kappa'][sl]), ptr(out['psi'][sl]), ptr(out['nu'][sl]),
+              ptr(part(out['lik_mu'])), ptr(part(out['lik_lmbda'])), ptr(part(out['vlb'])),
+              code(ops.precision) if ops is not None else F64, ptr(part(W)), ptr(ops.cst[sl]) if ops is not None else None,
               ops.Rp if ops is not None else 8, ops.Dpp if ops is not None else pad_cols(Dp), row_off, ptr(col_map),
               ptr(ws), wsb, ptr(info.t), stream())
     out['info'] = info
+    out['k_range'] = (lo, hi)
     return out
 
 

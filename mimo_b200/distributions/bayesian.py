@@ -205,10 +205,13 @@ class StackedGaussiansWithNormalWisharts(_ComponentsBase):
     def _prior_dev(self, dist=None):
         return [E.to_dev(p) for p in (dist or self.prior).params]
 
-    def _update(self, stat, F, layout, mode, ops=None, variates=None, prior_dev=None, want_lik=False, want_vlb=True):
+    _shardable = True          # one CTA per component, no coupling between components unless tied
+
+    def _update(self, stat, F, layout, mode, ops=None, variates=None, prior_dev=None, want_lik=False, want_vlb=True,
+                k_range=None):
         return E.nw_posterior(prior_dev or self._prior_dev(), stat, F, layout['stat_idx'], layout['Dp'], mode=mode,
                               tied=self._tied, variates=variates, ops=ops, row_off=layout['row_off'],
-                              col_map=layout['col_map'], want_lik=want_lik, want_vlb=want_vlb)
+                              col_map=layout['col_map'], want_lik=want_lik, want_vlb=want_vlb, k_range=k_range)
 
     def _draw_variates(self, counts):
         nus = self.prior.nus + counts

@@ -92,14 +92,57 @@ class Session:
             ops.cst.zero_()
         row = 0
         outs['parts'] = []
+        k_range = self._component_shard()
         for i, p in enumerate(self.parts):
             lay = p.layout(self.D + 1, row)
+            kw = dict(k_range=k_range) if k_range is not None else {}
             outs['parts'].append(p.w._update(self.stat, self.F, lay, mode, ops=ops,
                                              variates=None if variates is None else variates[i],
-                                             prior_dev=self.part_priors[i], want_lik=want_lik))
+                                             prior_dev=self.part_priors[i], want_lik=want_lik, **kw))
             row += p.w._rows(mode) if self.family == 'quad' else 0
+        if k_range is not None:
+            self._gather_components(ops, outs, k_range)
         self.last = outs
         return ops, outs
+
+    # -- posterior update sharded over ranks -------------------------------------------------
+    def _component_shard(self):
+        """[k0, k1) of this rank when the posterior update can be split over ranks: every rank holds the all-reduced
+        statistics, the kernels are one CTA per component, so each rank updates K / world components and the operand
+        blocks (what the next sweep reads) and lower-bound terms are all-gathered -- instead of every rank repeating
+        all K Cholesky factorisations.  Needs untied components (tied ones average over k) and K divisible by world."""
+        import os
+        c = self.comm
+        if c is None or c.world <= 1 or self.K % c.world or self.family != 'quad' or os.environ.get('MIMO_REPLICATED_POSTERIOR'):
+            return None
+        if not all(getattr(p.w, '_shardable', False) and not p.w._tied for p in self.parts):
+            return None
+        n = self.K // c.world
+        return (c.rank * n, (c.rank + 1) * n)
+
+    def _gather(self, t, k_range):
+        """all-gather the component slices of a (K, ...) tensor in place."""
+        import torch.distributed as dist
+        lo, hi = k_range
+        mine = t[lo:hi].clone()
+        dist.all_gather_into_tensor(t.view(-1), mine.view(-1), group=self.comm.group)
+
+    def _gather_components(self, ops, outs, k_range):
+        self._gather(ops.W, k_range)
+        self._gather(ops.cst, k_range)
+        for o in outs['parts']:
+            if o.get('vlb') is not None:
+                self._gather(o['vlb'], k_range)
+            o['gathered'] = False                    # posterior parameters still hold this rank's slice only
+
+    def _gather_parameters(self, outs):
+        """before downloading posterior parameters into the model (store): complete the per-rank slices."""
+        for o in outs['parts']:
+            if o.get('gathered') is False:
+                for key in ('m', 'kappa', 'psi', 'nu', 'lik_mu', 'lik_lmbda'):
+                    if o.get(key) is not None:
+                        self._gather(o[key], o['k_range'])
+                o['gathered'] = True
 
     def operands_from_posterior(self, gating_mode=MEANFIELD):
         """operands of the CURRENT posteriors (no new statistics)."""
@@ -170,6 +213,7 @@ class Session:
 
     def store(self, outs, mode, set_probs=True):
         """download posterior (and sampled / mode likelihood) parameters into the model."""
+        self._gather_parameters(outs)
         if 'gating' in outs:
             self.gating._store(outs['gating'], set_probs=set_probs)
         for p, o in zip(self.parts, outs['parts']):
