@@ -214,6 +214,8 @@ def stats_soft(Z, resp, feats, precision, stat=None):
     fi, fj = feats.dev()
     if stat is None:
         stat = zeros((K, feats.F), torch.float64)
+    if N == 0:
+        return stat
     _lib.call('mimo_stats_soft', code(precision), ptr(Z), N, D, Z.stride(0), ptr(resp), resp.stride(0), K,
               ptr(fi), ptr(fj), feats.F, ptr(stat), stream())
     return stat
@@ -224,6 +226,8 @@ def stats_hard(Z, labels, K, feats, precision, stat=None):
     fi, fj = feats.dev()
     if stat is None:
         stat = zeros((K, feats.F), torch.float64)
+    if N == 0:
+        return stat
     wsb = _lib.load().mimo_stats_hard_workspace(N, K)
     ws = workspace(wsb)
     _lib.call('mimo_stats_hard', code(precision), ptr(Z), N, D, Z.stride(0), ptr(labels), K,
@@ -265,6 +269,8 @@ def sweep(Z, ops, feats, buf, uniforms=None, seed=0, offset=0, ll_out=None, lse_
     if zero:
         buf.stat.zero_()
         buf.lse_sum.zero_()
+    if N == 0:                      # an empty shard: nothing to add (an empty tensor has no device pointer to pass)
+        return buf
     a, b, c, K, Rp, Dpp = ops.args()
     args = (code(ops.precision), ops.family, 1 if buf.hard else 0,
             ptr(Z), N, D, Z.stride(0), a, b, c, K, Rp, Dpp, ptr(fi), ptr(fj), feats.F,

@@ -611,3 +611,41 @@ def test_stats_hard_non_canonical_feature_table(D):
     st = E.stats_hard(Z, E.to_dev(labels, torch.int32), K, feats, 'fp32').cpu().numpy()
     phi = zt[:, feats.fi_host] * zt[:, feats.fj_host]
     close(st, orc.one_hot(labels, K) @ phi, 1e-10, 'permuted diagonal feature table')
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'fp64'])
+def test_sweep_empty_and_single_point(precision):
+    """edge cases of mimo_sweep / mimo_stats_hard: no points (statistics stay zero), one point, one component."""
+    E = eng()
+    rng = np.random.default_rng(1)
+    for K, d in ((3, 2), (1, 5), (40, 96)):
+        mus = rng.standard_normal((K, d))
+        lmbdas = np.stack([spd(rng, d) for _ in range(K)])
+        logw = np.log(rng.dirichlet(np.ones(K))) if K > 1 else np.zeros(1)
+        ops = E.QuadOperands(K, d, d, precision)
+        E.set_log_weights(ops, logw)
+        E.operands_gauss(ops, E.to_dev(mus), E.to_dev(lmbdas)).check()
+        feats = E.quad_features(d)
+        for N in (0, 1, 2):
+            x = rng.standard_normal((N, d)) + mus[0]
+            Z = E.to_dev(x.reshape(N, d), E.tdtype(precision))
+            for hard in (False, True):
+                buf = E.SweepBuffers(max(N, 1), K, feats.F, precision, hard)
+                buf.N = N
+                E.sweep(Z, ops, feats, buf, uniforms=E.to_dev(rng.random(max(N, 1))) if hard else None)
+                st = buf.stat.cpu().numpy()
+                if N == 0:
+                    assert np.all(st == 0.0) and buf.lse_sum.item() == 0.0
+                    continue
+                xr = Z.double().cpu().numpy()
+                ll = orc.gauss_full_loglik(xr, mus, lmbdas) + logw[:, None]
+                resp, lse = orc.responsibilities(ll)
+                assert abs(buf.lse_sum.item() - lse.sum()) <= RTOL[precision] * max(1.0, abs(lse.sum()))
+                S = unpack_quad(st, d)
+                assert abs(S[:, d, d].sum() - N) <= 1e-6 * N          # responsibilities / labels sum to the points
+                if not hard:
+                    close(S[:, d, :d], orc.gauss_full_wstats(xr, resp)[0], RTOL[precision], 'tiny sum r x')
+    # hard statistics of nothing
+    z0 = E.to_dev(np.zeros((0, 3)), E.tdtype(precision))
+    s0 = E.stats_hard(z0, E.to_dev(np.zeros(0, dtype=np.int32), torch.int32), 4, E.quad_features(3), precision)
+    assert np.all(s0.cpu().numpy() == 0.0)
