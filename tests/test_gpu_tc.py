@@ -183,7 +183,8 @@ def test_sweep_tc_matches_cuda_cores_and_oracle(hard, K, d, N):
 
 
 @pytest.mark.parametrize('hard', [False, True])
-@pytest.mark.parametrize('K,d,N,sep', [(64, 128, 6000, 6.0), (40, 96, 5000, 6.0), (48, 64, 4000, 0.3), (33, 100, 3000, 1.5)])
+@pytest.mark.parametrize('K,d,N,sep', [(64, 128, 6000, 6.0), (40, 96, 5000, 6.0), (48, 64, 4000, 0.3), (33, 100, 3000, 1.5),
+                                     (40, 50, 5000, 6.0), (36, 30, 4000, 8.0), (35, 27, 3000, 8.0)])
 def test_sweep_screened_estep(hard, K, d, N, sep):
     """default tensor-core mode: single-pass screening + exact refinement of the candidates (separated components)
     or the device-selected dense second pass (overlapping components).  Either way the sweep must match the dense
