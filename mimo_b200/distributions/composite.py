@@ -208,6 +208,14 @@ class NormalWishart:
         mus, lmbdas = self._stack().rvs()
         return mus[0], lmbdas[0]
 
+    @property
+    def base(self):
+        """(2 pi)^(-d/2): Gaussian base measure times the Wishart's 1 (composite.py:88-93)."""
+        return np.power(2. * np.pi, -0.5 * self.dim)
+
+    def log_base(self):
+        return np.log(self.base)
+
     def log_partition(self):
         return self._stack().log_partition()[0]
 
@@ -342,6 +350,14 @@ class NormalGamma:
         mus, lmbdas = self._stack().rvs()
         return mus[0], lmbdas[0]
 
+    @property
+    def base(self):
+        """(2 pi)^(-d/2): Gaussian base measure times the Gamma's 1 (composite.py:353-358)."""
+        return np.power(2. * np.pi, -0.5 * self.dim)
+
+    def log_base(self):
+        return np.log(self.base)
+
     def log_partition(self):
         return self._stack().log_partition()[0]
 
@@ -446,9 +462,27 @@ class MatrixNormalWishart:
 
     @nat_param.setter
     def nat_param(self, natparam):
-        st = self._stack()
+        self.M, self.K, self.psi, self.nu = self.nat_to_std(natparam)
+
+    def std_to_nat(self, params):
+        """[M K, K, psi^-1 + M K M^T, nu - o - 1 + c]  (composite.py:577-592)."""
+        M, K, psi, nu = params
+        st = StackedMatrixNormalWisharts(1, self.column_dim, self.row_dim)
+        return Stats([s[0] for s in st.std_to_nat((np.asarray(M)[None], np.asarray(K)[None], np.asarray(psi)[None], np.atleast_1d(nu)))])
+
+    def nat_to_std(self, natparam):
+        """inverse of std_to_nat (composite.py:594-599)."""
+        st = StackedMatrixNormalWisharts(1, self.column_dim, self.row_dim)
         out = st.nat_to_std([np.asarray(n)[None] for n in natparam])
-        self.M, self.K, self.psi, self.nu = (o[0] for o in out)
+        return tuple(o[0] for o in out)
+
+    @property
+    def base(self):
+        """(2 pi)^(-o c / 2): matrix-normal base measure times the Wishart's 1 (composite.py:615-620, matrix.py:127-129)."""
+        return np.power(2. * np.pi, -0.5 * self.row_dim * self.column_dim)
+
+    def log_base(self):
+        return np.log(self.base)
 
     def mean(self):
         return self.M, self.nu * self.psi

@@ -49,6 +49,19 @@ class Dirichlet:
     def rvs(self, size=1):
         return npr.dirichlet(self.alphas)
 
+    def statistics(self, data):
+        """log x per point; a list of arrays maps to a list (dirichlet.py:52-58)."""
+        if isinstance(data, np.ndarray):
+            return np.log(data[~np.isnan(data).any(axis=1)])
+        return [self.statistics(d) for d in data]
+
+    def weighted_statistics(self, data, weights):
+        """w_n log x_n per point (dirichlet.py:60-69)."""
+        if isinstance(data, np.ndarray):
+            keep = ~np.isnan(data).any(axis=1)
+            return weights[keep][:, None] * np.log(data[keep])
+        return [self.weighted_statistics(d, w) for d, w in zip(data, weights)]
+
     @property
     def base(self):
         return 1.

@@ -48,6 +48,13 @@ class Gamma:
     def rvs(self, size=1):
         return npr.gamma(self.alphas, 1. / self.betas)
 
+    @property
+    def base(self):
+        return 1.
+
+    def log_base(self):
+        return 0.
+
     def log_partition(self):
         return np.sum(gammaln(self.alphas) - self.alphas * np.log(self.betas))
 

@@ -62,6 +62,13 @@ class Wishart:
         T = self.psi_chol @ A
         return T @ T.T
 
+    @property
+    def base(self):
+        return 1.
+
+    def log_base(self):
+        return 0.
+
     def log_partition(self):
         return 0.5 * self.nu * self.dim * np.log(2) + multigammaln(self.nu / 2., self.dim) \
             + self.nu * np.sum(np.log(np.diag(self.psi_chol)))
