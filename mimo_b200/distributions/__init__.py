@@ -2,6 +2,7 @@ from .dirichlet import Dirichlet, TruncatedStickBreaking  # noqa: F401
 from .wishart import Wishart  # noqa: F401
 from .gamma import Gamma  # noqa: F401
 from .categorical import Categorical  # noqa: F401
+from .matrix import MatrixNormalWithPrecision  # noqa: F401
 from .gaussian import (GaussianWithPrecision, StackedGaussiansWithPrecision, TiedGaussiansWithPrecision,  # noqa: F401
                        GaussianWithDiagonalPrecision, StackedGaussiansWithDiagonalPrecision,
                        TiedGaussiansWithDiagonalPrecision)
