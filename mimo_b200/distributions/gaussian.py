@@ -294,6 +294,16 @@ class GaussianWithPrecision:
     def expected_statistics(self):
         return self.mu, np.outer(self.mu, self.mu) + self.sigma
 
+    def entropy(self):
+        """d/2 (1 + log 2 pi) - 1/2 log det Lambda   (gaussian.py:96-99 in closed form)."""
+        return 0.5 * self.dim * (1. + np.log(2. * np.pi)) - 0.5 * np.linalg.slogdet(self.lmbda)[1]
+
+    def cross_entropy(self, dist):
+        """E_self[-log dist]   (gaussian.py:101-104 in closed form)."""
+        diff = self.mu - dist.mu
+        return 0.5 * self.dim * np.log(2. * np.pi) - 0.5 * np.linalg.slogdet(dist.lmbda)[1] \
+            + 0.5 * np.trace(dist.lmbda @ self.sigma) + 0.5 * diff @ dist.lmbda @ diff
+
     def max_likelihood(self, data, weights=None):
         w = np.ones((len(data),)) if weights is None else np.asarray(weights)
         st = self._stack()

@@ -151,3 +151,16 @@ def test_matrix_normal_with_precision(mods):
     npr.seed(11)
     dm = m.rvs()
     assert np.allclose(dr, dm, rtol=1e-12, atol=1e-12)
+
+
+def test_single_gaussian_entropies(mods):
+    ref_d, _, my_d, _ = mods
+    rng = np.random.default_rng(4)
+    d = 4
+    a, b = rng.standard_normal((d, d + 2)), rng.standard_normal((d, d + 2))
+    l1, l2 = a @ a.T / d + 0.2 * np.eye(d), b @ b.T / d + 0.2 * np.eye(d)
+    m1, m2 = rng.standard_normal(d), rng.standard_normal(d)
+    r1, r2 = ref_d.GaussianWithPrecision(d, m1, l1), ref_d.GaussianWithPrecision(d, m2, l2)
+    g1, g2 = my_d.GaussianWithPrecision(d, m1, l1), my_d.GaussianWithPrecision(d, m2, l2)
+    assert np.isclose(r1.entropy(), g1.entropy(), rtol=1e-12)
+    assert np.isclose(r1.cross_entropy(r2), g1.cross_entropy(g2), rtol=1e-12)
