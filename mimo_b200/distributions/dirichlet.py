@@ -9,35 +9,43 @@ import numpy.random as npr
 from scipy.special import digamma, gammaln, betaln
 
 
-class Dirichlet:
+class _ShiftedByOne:
+    """Both gating priors have natural parameters = standard parameters - 1 (Dirichlet: alpha - 1; stick-breaking:
+    (gamma - 1, delta - 1)) and no base measure; `_fields` names the attributes that make up `params`."""
+    _fields = ()
+    base = 1.
+
+    def log_base(self):
+        return 0.
+
+    def _get_params(self):
+        vals = tuple(getattr(self, f) for f in self._fields)
+        return vals[0] if len(vals) == 1 else vals
+
+    def _set_params(self, values):
+        if len(self._fields) == 1:
+            values = (values,)
+        for f, v in zip(self._fields, values):
+            setattr(self, f, v)
+
+    params = property(_get_params, _set_params)
+    nat_param = property(lambda self: self.std_to_nat(self.params),
+                         lambda self, nat: self._set_params(self.nat_to_std(nat)))
+
+    @classmethod
+    def std_to_nat(cls, params):
+        return params - 1. if len(cls._fields) == 1 else tuple(p - 1. for p in params)
+
+    @classmethod
+    def nat_to_std(cls, natparam):
+        return natparam + 1. if len(cls._fields) == 1 else tuple(n + 1. for n in natparam)
+
+
+class Dirichlet(_ShiftedByOne):
+    _fields = ('alphas',)
 
     def __init__(self, dim=None, alphas=None):
-        self.dim = dim
-        self.alphas = alphas
-
-    @property
-    def params(self):
-        return self.alphas
-
-    @params.setter
-    def params(self, values):
-        self.alphas = values
-
-    @property
-    def nat_param(self):
-        return self.std_to_nat(self.params)
-
-    @nat_param.setter
-    def nat_param(self, natparam):
-        self.params = self.nat_to_std(natparam)
-
-    @staticmethod
-    def std_to_nat(params):
-        return params - 1.
-
-    @staticmethod
-    def nat_to_std(natparam):
-        return natparam + 1.
+        self.dim, self.alphas = dim, alphas
 
     def mean(self):
         return self.alphas / np.sum(self.alphas)
@@ -62,13 +70,6 @@ class Dirichlet:
             return weights[keep][:, None] * np.log(data[keep])
         return [self.weighted_statistics(d, w) for d, w in zip(data, weights)]
 
-    @property
-    def base(self):
-        return 1.
-
-    def log_base(self):
-        return 0.
-
     def log_partition(self):
         return np.sum(gammaln(self.alphas)) - gammaln(np.sum(self.alphas))
 
@@ -85,37 +86,12 @@ class Dirichlet:
         return dist.log_partition() - dist.nat_param.dot(self.expected_statistics())
 
 
-class TruncatedStickBreaking:
+class TruncatedStickBreaking(_ShiftedByOne):
     """Ishwaran & James (2001) / Blei & Jordan (2006) truncation."""
+    _fields = ('gammas', 'deltas')
 
     def __init__(self, dim=None, gammas=None, deltas=None):
-        self.dim = dim
-        self.gammas = gammas
-        self.deltas = deltas
-
-    @property
-    def params(self):
-        return self.gammas, self.deltas
-
-    @params.setter
-    def params(self, values):
-        self.gammas, self.deltas = values
-
-    @property
-    def nat_param(self):
-        return self.std_to_nat(self.params)
-
-    @nat_param.setter
-    def nat_param(self, natparam):
-        self.params = self.nat_to_std(natparam)
-
-    @staticmethod
-    def std_to_nat(params):
-        return params[0] - 1., params[1] - 1.
-
-    @staticmethod
-    def nat_to_std(natparam):
-        return natparam[0] + 1., natparam[1] + 1.
+        self.dim, self.gammas, self.deltas = dim, gammas, deltas
 
     @staticmethod
     def _sticks_to_probs(betas):
@@ -146,13 +122,6 @@ class TruncatedStickBreaking:
     def rvs(self, size=1, truncate=True):
         betas = np.hstack((npr.beta(self.gammas[:-1], self.deltas[:-1]), 1.))
         return self._sticks_to_probs(betas)
-
-    @property
-    def base(self):
-        return 1.
-
-    def log_base(self):
-        return 0.
 
     def log_partition(self):
         return np.sum(betaln(self.gammas, self.deltas))
