@@ -89,3 +89,22 @@ def test_prior_closed_forms_match_oracle():
     assert np.allclose(sb.mean(), orc.stick_mean(al, 2 * al))
     assert np.allclose(sb.entropy() - sb.cross_entropy(TruncatedStickBreaking(K, np.ones(K), np.ones(K))),
                        orc.stick_vlb((np.ones(K), np.ones(K)), (al, 2 * al)))
+
+
+def test_bench_algorithmic_work_matches_survey():
+    """bench.py's flop / byte model is SURVEY.md 8(d): E-step 2d(d+1)+2d, soft statistics 2(d+1)^2 per pair,
+    4*D bytes per point; diagonal 4d+1; linear-Gaussian experts 362 + 362 at d_in = 8, d_out = 1."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location('bench', os.path.join(os.path.dirname(os.path.dirname(__file__)), 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    w5 = bench.algorithmic_work(bench.WORKLOADS['cfg5'])
+    assert w5['e_flops_pair'] == 2 * 128 * 129 + 2 * 128 and w5['s_flops_pair'] == 2 * 129 ** 2 and w5['bytes_pt'] == 512
+    total = (w5['e_flops_pair'] + w5['s_flops_pair']) * 50_000_000 * 1024
+    assert abs(total - 3.4e15) / 3.4e15 < 0.02                      # "flops/sweep 3.4e15" of the SURVEY table
+    w3 = bench.algorithmic_work(bench.WORKLOADS['cfg3'])
+    assert w3['e_flops_pair'] == 4 * 64 + 1 and w3['bytes_pt'] == 4 * 64 + 4
+    w2 = bench.algorithmic_work(bench.WORKLOADS['cfg2'])
+    assert w2['e_flops_pair'] == (2 * 8 * 9 + 2 * 8) + (2 * 1 * 9 + 2 + 2 * 81 + 2 + 18) and w2['s_flops_pair'] == 2 * 81 + 2 * 100
+    assert w2['e_flops_pair'] == 362 and w2['s_flops_pair'] == 362
