@@ -8,9 +8,24 @@ A "step" is one full sweep of the named workload over synthetic data of its shap
                terms) -> fused E-step + statistics sweep -> [all-reduce] -> lower bound read
   Gibbs      : host-drawn parameter variates -> posterior kernels (draw) -> fused E-step +
                label draw + statistics sweep -> [all-reduce]
-`value` = N*K / (device time per step), data resident in HBM (inputs larger than L2).
-`e2e`   = the same metric through the host-buffer C-ABI call (mimo_sweep_host): pinned host
-          data -> device, one sweep, statistics + lower-bound scalar back, every step.
+
+What the one JSON line holds (default workload cfg5: N=50M, d=128, K=1024, mean field):
+  value / roofline : the DENSE regime -- every (point, component) pair goes through the 3-pass
+               tensor-core E-step and the tensor-core statistics GEMM, whatever the data look like.
+               `roofline.frac` = SURVEY 8(d) algorithmic flops of the dominant kernel / its measured
+               device time / the sustained bf16 peak of MEASURED_PEAKS.json.  Timed for --steps.
+  screened_path   : the library's default path on the same data and model (screening pass + exact
+               refinement of the candidate pairs; falls back to the dense kernels per chunk on the
+               device).  Its bound is the TMEM read port, not the algorithmic roofline; candidate
+               fraction and tier are totals over ALL chunks of the last sweep, per rank.
+  overlap_regime  : a second data set whose components overlap (centre spread 1.5 sigma), started
+               from random responsibilities, every sweep timed from the first one.
+  parity_subsample: the CUDA results on a sub-sample of the resident data against oracle/ (log-joint,
+               responsibilities, log-normalisers, statistics, posterior parameters), max scaled errors.
+  e2e             : the full step through host buffers: posterior update from the previous
+               statistics, mimo_sweep_host (pinned host data -> device, sweep, statistics back),
+               lower bound, every step.
+  other_configs   : short legs of cfg1-cfg4 (BASELINE.json's other shapes) with their own roofline.
 `--impl reference` times the CPU port of the reference's algorithm (oracle/) on the box's
 host cores on a bounded sample of the same workload.
 Multi-GPU (torchrun): the N points are split across ranks (strong scaling); one all-reduce
@@ -22,7 +37,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -43,6 +57,8 @@ WORKLOADS = {
     'cfg5': dict(kind='gmm', N=50_000_000, d=128, K=1024, mode='vi', stick=True,
                  desc='DP-GMM full covariance, mean-field, N=50M d=128 K=1024'),
 }
+OVERLAP_N = 8_000_000          # points of the overlapping-components regime (same d, K as the workload)
+OVERLAP_SPREAD = 1.5
 
 
 def read_peaks():
@@ -58,13 +74,16 @@ def read_peaks():
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes (read + write) per launch of the dominant kernel, from the committed `ncu --set full` capture of
-    the same kernel on one point chunk of this workload (profiles/r01_ncu_traffic.json); None when not captured."""
-    p = os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')
-    try:
-        return json.load(open(p)).get(kernel)
-    except Exception:
-        return None
+    """DRAM bytes (read + write) per launch of a kernel, from the committed `ncu --set full` capture of the same
+    kernel on one point chunk of cfg5 (profiles/ncu_traffic.json); None when not captured."""
+    for fn in ('ncu_traffic.json', 'r01_ncu_traffic.json'):
+        try:
+            t = json.load(open(os.path.join(ROOT, 'profiles', fn))).get(kernel)
+            if t:
+                return t
+        except Exception:
+            pass
+    return None
 
 
 def algorithmic_work(w):
@@ -135,7 +154,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 # synthetic data (on the device, never timed)
 # ---------------------------------------------------------------------------------------
-def make_data(w, n_local, lo, seed, dev):
+def make_data(w, n_local, lo, seed, dev, spread=None):
     """points [lo, lo+n_local) of the workload's synthetic data set, as FP32 on `dev`.
     Blobs: centres ~ N(0, spread^2 I); full-covariance blobs have random SPD covariances
     (Wishart(I, d+2)/d), diagonal blobs per-dimension sigmas in [0.5, 1.5]; labels from
@@ -146,7 +165,8 @@ def make_data(w, n_local, lo, seed, dev):
     D = d + w.get('o', 0)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
-    spread = 4.0 if w['kind'] != 'ilr' else 3.0
+    if spread is None:
+        spread = 4.0 if w['kind'] != 'ilr' else 3.0
     centres = spread * torch.randn(K, d, generator=g, device=dev)
     if w['kind'] == 'dgmm':
         chol = None
@@ -257,7 +277,7 @@ def make_session(model, w, Z, comm):
 # CPU arm: the oracle port of the reference's sweep on a bounded sample
 # ---------------------------------------------------------------------------------------
 def cpu_sweep_fn(w, n_sample, seed=0):
-    """returns (step_fn, N_sample, K): one reference-algorithm sweep on n_sample points."""
+    """returns step_fn: one reference-algorithm sweep on n_sample points."""
     from oracle import mimo_oracle as orc
     rng = np.random.default_rng(seed)
     K, d = w['K'], w['d']
@@ -323,18 +343,382 @@ def time_cpu(w, name, steps, warmup):
 
 
 # ---------------------------------------------------------------------------------------
+# one timed leg: W warm-up + K timed full steps of a session
+# ---------------------------------------------------------------------------------------
+class Ctx:
+    """what every leg needs: torch, the engine, rank / world, the communicator."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        from mimo_b200 import _engine as E, _lib
+        self.torch, self.dist, self.E, self._lib = torch, dist, E, _lib
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.dev = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x):
+        if self.world > 1:
+            t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def gather_rows(self, row):
+        """(world, len(row)) float64 array on every rank."""
+        t = self.torch.tensor(row, device=self.dev, dtype=self.torch.float64)
+        if self.world == 1:
+            return t.cpu().numpy()[None]
+        out = self.torch.empty((self.world, t.numel()), device=self.dev, dtype=self.torch.float64)
+        self.dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy()
+
+
+def one_step(s, hard, rng, phase=None, vlbs=None):
+    from mimo_b200.distributions.bayesian import MEANFIELD, GIBBS
+    if hard:
+        var, gvar = s.draw_gibbs_variates()
+        ops, outs = s.update_from_stats(GIBBS, variates=var, gating_variates=gvar)
+        s.sweep(ops, hard=True, seed=int(rng.integers(1 << 30)), phase_ms=phase)
+    else:
+        ops, outs = s.update_from_stats(MEANFIELD)
+        s.sweep(ops, hard=False, phase_ms=phase)
+        v = s.lower_bound(outs)
+        if vlbs is not None:
+            vlbs.append(v)
+    return outs
+
+
+def time_leg(cx, s, hard, steps, warmup, tc_mode=None, sample_clocks=False, per_step=False):
+    """W untimed + K timed full steps; CUDA events on the launching (current) stream, barrier + synchronize on both
+    sides, max over ranks.  Returns ms per step, the per-phase device times of the timed steps and the lower bounds."""
+    torch, E = cx.torch, cx.E
+    old = E.set_tensor_cores(tc_mode) if tc_mode is not None else None
+    rng = np.random.default_rng(7)
+    try:
+        outs = None
+        for _ in range(warmup):
+            outs = one_step(s, hard, rng)
+        if outs is not None:
+            s.check(outs)
+        torch.cuda.synchronize()
+        cx.barrier()
+        sampler = ClockSampler(torch.cuda.current_device()) if (sample_clocks and cx.rank == 0) else None
+        phase = np.zeros(6)
+        vlbs = []
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        torch.cuda.synchronize()
+        evs[0].record()
+        for i in range(steps):
+            outs = one_step(s, hard, rng, phase, vlbs)
+            if per_step:
+                evs[i + 1].record()
+        if not per_step:
+            evs[steps].record()
+        torch.cuda.synchronize()
+        cx.barrier()
+        ms = cx.max_over_ranks(evs[0].elapsed_time(evs[steps]) / steps)
+        clocks = sampler.stop() if sampler else None
+        s.check(outs)
+        out = dict(ms=ms, phase=phase, vlbs=vlbs, clocks=clocks, steps=steps, warmup=warmup)
+        if per_step:
+            out['ms_each'] = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+        return out
+    finally:
+        if old is not None:
+            E.set_tensor_cores(old)
+
+
+def leg_roofline(w, n_local, leg, peaks, kernel_names):
+    """roofline of the dominant phase of a leg from SURVEY 8(d)'s algorithmic work and the per-phase CUDA-event times."""
+    work = algorithmic_work(w)
+    steps = leg['steps']
+    phase = leg['phase']
+    phase_ms = phase[:3] / steps
+    chunks = max(1.0, phase[4])
+    pairs = n_local * w['K']
+    flops = [work['e_flops_pair'] * pairs, 0.0, work['s_flops_pair'] * pairs]
+    t_hbm = n_local * work['bytes_pt'] / (peaks['hbm'] * 1e9)
+    t_tensor = sum(flops) / (peaks['tf_sus'] * 1e12)
+    bound = 'tensor' if t_tensor >= t_hbm else 'hbm'
+    dom = int(np.argmax(phase_ms))
+    hard = w['mode'] == 'gibbs'
+    launches = 1.0 if (hard and dom == 2) else chunks / steps
+    ms = leg['ms']
+    if bound == 'tensor':
+        if flops[dom] <= 0:                       # the softmax phase dominates a tensor-bound config: rate the sweep
+            ach = sum(flops) / (ms * 1e-3) / 1e12
+        else:
+            ach = flops[dom] / (phase_ms[dom] * 1e-3) / 1e12 if phase_ms[dom] > 0 else 0.0
+        roof = dict(bound='tensor', achieved=ach, peak=peaks['tf_sus'], unit='TFLOP/s', frac=ach / peaks['tf_sus'], traffic=None)
+        roof['whole_sweep_frac'] = (sum(flops) / (ms * 1e-3) / 1e12) / peaks['tf_sus']
+        roof['per_kernel_frac'] = {nm: (f / (p * 1e-3) / 1e12) / peaks['tf_sus'] for nm, f, p in
+                                   zip(('estep', 'softmax', 'stats'), flops, phase_ms) if f > 0 and p > 0}
+    else:
+        ach = n_local * work['bytes_pt'] / (phase_ms[dom] * 1e-3) / 1e9 if phase_ms[dom] > 0 else 0.0
+        roof = dict(bound='hbm', achieved=ach, peak=peaks['hbm'], unit='GB/s', frac=ach / peaks['hbm'], traffic=None)
+        roof['whole_sweep_frac'] = (n_local * work['bytes_pt'] / (ms * 1e-3) / 1e9) / peaks['hbm']
+    roof.update(kernel=kernel_names[dom], launches_per_step=launches,
+                ms_per_launch=phase_ms[dom] / max(launches, 1.0),
+                phase_ms_per_step=dict(estep=phase_ms[0], softmax=phase_ms[1], stats=phase_ms[2]),
+                t_tensor_ms=t_tensor * 1e3, t_hbm_ms=t_hbm * 1e3,
+                peak_source='%s (sustained bf16 / copy bandwidth of MEASURED_PEAKS.json)' % peaks['src'],
+                work='SURVEY 8(d): E-step %d flop/pair, statistics %.4g flop/pair, %d B/point'
+                     % (work['e_flops_pair'], work['s_flops_pair'], work['bytes_pt']))
+    return roof
+
+
+def init_from_labels(cx, s, labels, K, comm):
+    s.stat = cx.E.stats_hard(s.Z, labels, K, s.feats, 'fp32')
+    if comm is not None:
+        comm.allreduce(s.stat)
+
+
+def screen_totals(cx, n_local, K):
+    """totals of the last screened sweep over ALL its chunks, one row per rank."""
+    t = cx.E.screen_totals()
+    rows = cx.gather_rows([float(v) for v in t])
+    out = []
+    for r in rows:
+        cand, pts, dense_chunks, chunks, level = r
+        out.append(dict(chunks=int(chunks), dense_chunks=int(dense_chunks), tier_at_end=int(level),
+                        candidate_pairs_per_point=(cand / pts) if pts > 0 else None,
+                        candidate_fraction=(cand / (pts * K)) if pts > 0 else None))
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# parity on a sub-sample of the resident data, against oracle/
+# ---------------------------------------------------------------------------------------
+def parity_subsample(cx, s, w, n_sub):
+    """CUDA results on the first n_sub resident points (dense kernels and the screened default) against the oracle,
+    with the model the benchmark is in (posterior from the session's all-reduced statistics).  max scaled errors:
+    |gpu - ref|_max / max(1, |ref|_max) per quantity."""
+    from oracle import mimo_oracle as orc
+    from mimo_b200.distributions.bayesian import MEANFIELD
+    torch, E = cx.torch, cx.E
+    K, d = w['K'], w['d']
+    n_sub = min(n_sub, s.N)
+    t0 = time.perf_counter()
+    stat_in = s.stat.clone()
+    ops, outs = s.update_from_stats(MEANFIELD)
+    s._gather_parameters(outs)
+    s.check(outs)
+    if cx.rank != 0:                       # the collective part is done; the check itself runs on rank 0's shard
+        s.stat = stat_in
+        return None
+    Zs = s.Z[:n_sub].contiguous()
+    x = Zs.double().cpu().numpy()
+
+    def err(a, b):
+        a = a.detach().double().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, float)
+        return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
+    # ---- oracle: posterior from the statistics, expected log-joint, responsibilities, statistics of the sub-sample
+    S = stat_in.cpu().numpy()
+    il = np.tril_indices(d + 1)
+    M = np.zeros((K, d + 1, d + 1))
+    M[:, il[0], il[1]] = S
+    M[:, il[1], il[0]] = S
+    stats = [M[:, d, :d], M[:, d, d], M[:, :d, :d], M[:, d, d]]
+    prior = (np.zeros((K, d)), 1e-2 * np.ones(K), np.stack(K * [np.eye(d)]), (d + 1.0) * np.ones(K) + 1e-8)
+    post = orc.nw_nat_to_std(orc.add_stats(orc.nw_std_to_nat(*prior), stats))
+    gp, dp = orc.stick_posterior(np.ones(K), 5.0 * np.ones(K), stats[1])
+    ell = orc.nw_expected_loglik(x, *post) + orc.stick_expected_log(gp, dp)[0][:, None]
+    resp, lse = orc.responsibilities(ell)
+    st = orc.gauss_full_wstats(x, resp)
+    ref_stat = np.zeros((K, d + 1, d + 1))
+    ref_stat[:, :d, :d] = st[2]
+    ref_stat[:, d, :d] = st[0]
+    ref_stat[:, d, d] = st[1]
+    ref_packed = ref_stat[:, il[0], il[1]]
+    out = dict(points=n_sub, K=K, d=d, tolerance='rel 1e-4 (FP32 compute, FP64 accumulation); matrices norm-wise')
+    po = outs['parts'][0]
+    out['posterior'] = {k: err(po[k], r) for k, r in zip(('m', 'kappa', 'psi', 'nu'), post)}
+    # ---- dense kernels: log-joint (K, n), log-normalisers, statistics
+    ll = E.empty((K, n_sub), torch.float32)
+    lse_t = E.empty((n_sub,), torch.float32)
+    old = E.set_tensor_cores(3)
+    try:
+        buf = E.SweepBuffers(n_sub, K, s.F, 'fp32', False)
+        E.sweep(Zs, ops, s.feats, buf, ll_out=ll, lse_out=lse_t)
+        g_ll = ll.double().cpu().numpy()
+        g_lse = lse_t.double().cpu().numpy()
+        out['dense'] = dict(log_joint=err(g_ll, ell), lse=err(g_lse, lse), lse_sum_rel=abs(buf.lse_sum.item() - lse.sum()) / abs(lse.sum()),
+                            resp=float(np.max(np.abs(np.exp(g_ll - g_lse[None]) - resp))), stats=err(buf.stat, ref_packed))
+    finally:
+        E.set_tensor_cores(old)
+    # ---- the default (screened) path: statistics and the lower-bound data term (no (K, n) output on this path)
+    buf = E.SweepBuffers(n_sub, K, s.F, 'fp32', False)
+    E.sweep(Zs, ops, s.feats, buf)
+    tot = E.screen_totals()
+    out['screened'] = dict(lse_sum_rel=abs(buf.lse_sum.item() - lse.sum()) / abs(lse.sum()), stats=err(buf.stat, ref_packed),
+                           dense_chunks=int(tot[2]), chunks=int(tot[3]))
+    worst = max([out['dense'][k] for k in ('log_joint', 'lse', 'resp', 'stats')] + [out['screened']['stats']] + list(out['posterior'].values()))
+    out['max_scaled_error'] = worst
+    out['ok'] = bool(worst <= 1e-4)
+    out['seconds'] = time.perf_counter() - t0
+    s.stat = stat_in
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# end to end: the full step through host buffers
+# ---------------------------------------------------------------------------------------
+def time_e2e(cx, w, s, hard, steps, comm, tc_mode=None, cache=None):
+    """Every step: posterior update from the statistics of the previous step (batched posterior kernels on the device),
+    operands device -> host, mimo_sweep_host on every rank (pinned host shard of Z -> device, one sweep, statistics +
+    lower-bound scalar (+ labels) back to pinned host memory), the all-reduce of the statistics when sharded,
+    statistics host -> device for the next update and the lower bound (mean field).  All inside the timed region; the
+    step time is the max over ranks."""
+    from mimo_b200.distributions.bayesian import MEANFIELD, GIBBS
+    torch, E, _lib = cx.torch, cx.E, cx._lib
+    N, D = s.Z.shape
+    world = cx.world
+    old = E.set_tensor_cores(tc_mode) if tc_mode is not None else None
+    cache = cache if cache is not None else {}
+    if 'zh' not in cache:                   # the pinned host copy of this rank's shard (made once, outside the timed region)
+        cache['zh'] = torch.empty((N, D), dtype=torch.float32, pin_memory=True)
+        cache['zh'].copy_(s.Z)
+    zh = cache['zh']
+    ops = s.ops(GIBBS if hard else MEANFIELD)
+    a, b = (ops.W, None) if ops.family == 0 else (ops.S, ops.T)
+    ah = torch.empty(a.shape, dtype=a.dtype, pin_memory=True)
+    bh = torch.empty(b.shape, dtype=b.dtype, pin_memory=True) if b is not None else None
+    ch = torch.empty(ops.cst.shape, dtype=ops.cst.dtype, pin_memory=True)
+    flat_h = torch.zeros((s.K * s.F + 1,), dtype=torch.float64, pin_memory=True)      # statistics | sum of lse
+    stat_h, lse_h = flat_h[:s.K * s.F], flat_h[s.K * s.F:]
+    flat_d = torch.empty_like(flat_h, device=s.Z.device)
+    lab_h = torch.empty((N,), dtype=torch.int32, pin_memory=True) if hard else None
+    fi, fj = s.feats.fi_host, s.feats.fj_host
+    rng = np.random.default_rng(11)
+    stat_keep = s.stat.clone()
+    torch.cuda.synchronize()
+    times, vlbs = [], []
+    try:
+        for it in range(steps + 1):
+            cx.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if hard:
+                var, gvar = s.draw_gibbs_variates()
+                _, outs = s.update_from_stats(GIBBS, variates=var, gating_variates=gvar)
+            else:
+                _, outs = s.update_from_stats(MEANFIELD)
+            ah.copy_(a, non_blocking=True)
+            if bh is not None:
+                bh.copy_(b, non_blocking=True)
+            ch.copy_(ops.cst, non_blocking=True)
+            torch.cuda.synchronize()
+            _lib.call('mimo_sweep_host', 0, ops.family, 1 if hard else 0, zh.data_ptr(), N, D,
+                      ah.data_ptr(), bh.data_ptr() if bh is not None else None, ch.data_ptr(), ops.K, ops.Rp, ops.Dpp,
+                      fi.ctypes.data, fj.ctypes.data, s.F, None, int(rng.integers(1 << 30)),
+                      stat_h.data_ptr(), lse_h.data_ptr(), lab_h.data_ptr() if lab_h is not None else None)
+            flat_d.copy_(flat_h, non_blocking=True)
+            if world > 1:                                   # close the sweep: sum the shard statistics
+                comm.allreduce(flat_d)
+            s.stat.copy_(flat_d[:s.K * s.F].view(s.K, s.F))
+            s.lse_sum = flat_d[s.K * s.F:]
+            if not hard:
+                vlbs.append(s.lower_bound(outs))            # device -> host read of the scalar
+            else:
+                torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        s.check(outs)
+    finally:
+        _lib.call('mimo_sweep_host_release')             # give the call's cached device buffers back
+        if old is not None:
+            E.set_tensor_cores(old)
+        s.stat = stat_keep
+    dt = cx.max_over_ranks(float(np.mean(times[1:])))
+    ops_b = ah.numel() * 4 + (bh.numel() * 4 if bh is not None else 0) + ch.numel() * 4 + 2 * s.F * 4
+    h2d = w['N'] * D * 4 + world * (ops_b + s.K * s.F * 8 + 8)
+    d2h = world * (s.K * s.F * 8 + 8 + ops_b + 8) + (w['N'] * 4 if hard else 0)
+    return dict(value=w['N'] * s.K / dt, unit='points*components/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                ms_per_step=dt * 1e3, steps=steps, warmup=1, lower_bound=vlbs[-2:] if vlbs else None,
+                call='posterior kernels -> operands to host -> mimo_sweep_host (C-ABI, pinned host buffers) on every rank -> '
+                     'statistics back%s -> lower bound' % (' -> all-reduce' if world > 1 else ''))
+
+
+# ---------------------------------------------------------------------------------------
+# overlapping-components regime from a random start
+# ---------------------------------------------------------------------------------------
+def overlap_leg(cx, w, steps, comm_factory, peaks):
+    """Same d, K, priors; OVERLAP_N points whose blob centres are OVERLAP_SPREAD sigma apart, model started from random
+    responsibilities (device-side, mixtures/gmm.py:265-267): every sweep from the first one is timed, on the library's
+    default path (which decides per chunk, on the device, between screening and the dense kernels)."""
+    from mimo_b200.sharded import shard_bounds
+    torch, E = cx.torch, cx.E
+    wo = dict(w)
+    wo['N'] = min(OVERLAP_N, w['N'])
+    lo, hi = shard_bounds(wo['N'], cx.rank, cx.world)
+    Z, _ = make_data(wo, hi - lo, lo, 4242, cx.dev, spread=OVERLAP_SPREAD)
+    comm = comm_factory(wo['N'])
+    model = build_model(wo)
+    s = make_session(model, wo, Z, comm)
+    s.stats_from_random_resp(seed=99)
+    steps = max(2, min(steps, 6))
+    leg = time_leg(cx, s, False, steps, 0, tc_mode=None, per_step=True)
+    tot = screen_totals(cx, hi - lo, wo['K'])
+    work = algorithmic_work(wo)
+    pairs = (hi - lo) * wo['K']
+    fl = (work['e_flops_pair'] + work['s_flops_pair']) * pairs
+    out = dict(N=wo['N'], centre_spread_sigma=OVERLAP_SPREAD, init='random responsibilities (device)', steps=steps, warmup=0,
+               ms_per_step=leg['ms'], ms_each_sweep=leg.get('ms_each'), value=wo['N'] * wo['K'] / (leg['ms'] * 1e-3),
+               unit='points*components/s', tensor_frac=(fl / (leg['ms'] * 1e-3) / 1e12) / peaks['tf_sus'],
+               screen_last_sweep=tot, lower_bound=leg['vlbs'])
+    del s, Z
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+def run_config(cx, name, steps, warmup, comm_factory, peaks, n_override=0):
+    """a short leg of one of the other BASELINE.json shapes on the library's default path."""
+    from mimo_b200.sharded import shard_bounds
+    torch, E = cx.torch, cx.E
+    w = dict(WORKLOADS[name])
+    if n_override:
+        w['N'] = min(w['N'], n_override)
+    lo, hi = shard_bounds(w['N'], cx.rank, cx.world)
+    Z, labels = make_data(w, hi - lo, lo, 1337, cx.dev)
+    comm = comm_factory(w['N'])
+    model = build_model(w)
+    s = make_session(model, w, Z, comm)
+    init_from_labels(cx, s, labels, w['K'], comm)
+    del labels
+    hard = w['mode'] == 'gibbs'
+    leg = time_leg(cx, s, hard, steps, warmup)
+    tcu = E.sweep_uses_tensor_cores(s.ops(1 if hard else 0), Z.shape[1])
+    names = ['E-step (%s)' % ('tcgen05' if tcu else 'CUDA cores'), 'softmax / label draw', 'sufficient statistics']
+    roof = leg_roofline(w, hi - lo, leg, peaks, names)
+    out = dict(workload='%s: %s' % (name, w['desc']), N=w['N'], K=w['K'], d=w['d'], sweep=w['mode'], steps=steps, warmup=warmup,
+               ms_per_step=leg['ms'], value=w['N'] * w['K'] / (leg['ms'] * 1e-3), unit='points*components/s', roofline=roof,
+               lower_bound=leg['vlbs'][-2:] if leg['vlbs'] else None, gpu_launches=int(leg['phase'][3]))
+    del s, Z
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--workload', default=os.environ.get('MIMO_BENCH_WORKLOAD', 'cfg5'))
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--n-override', type=int, default=0, help='debug only: smaller N (marks the line invalid)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--no-dense', action='store_true', help='skip the dense-path comparison sweep')
-    ap.add_argument('--tc-mode', type=int, default=-1, help='A/B only: 3 = dense 3-pass E-step (no screening), 0 = CUDA cores')
+    ap.add_argument('--no-screened', action='store_true', help='skip the screened-path leg')
+    ap.add_argument('--no-overlap', action='store_true', help='skip the overlapping-components regime')
+    ap.add_argument('--no-others', action='store_true', help='skip the short cfg1-cfg4 legs')
+    ap.add_argument('--no-parity', action='store_true', help='skip the oracle check on a sub-sample')
+    ap.add_argument('--parity-points', type=int, default=2048)
+    ap.add_argument('--tc-mode', type=int, default=-1, help='A/B only: force a tensor-core mode for the headline leg')
     args = ap.parse_args()
     name = args.workload
     w = dict(WORKLOADS[name])
@@ -342,6 +726,7 @@ def main():
         w['N'] = args.n_override
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    warmup = max(3, args.warmup)
     config = dict(workload='%s: %s' % (name, w['desc']), N=w['N'], K=w['K'], d=w['d'], sweep=w['mode'],
                   inputs='resident FP32 data %.1f GB per sweep >> 126 MB L2 (no flush needed)' % (w['N'] * (w['d'] + w.get('o', 0)) * 4 / 1e9))
     if args.n_override:
@@ -359,235 +744,142 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
     import __graft_entry__ as ge
     ge.build()
-    from mimo_b200 import _engine as E, _lib
     from mimo_b200.sharded import Communicator, init_from_env, shard_bounds
-    from mimo_b200.distributions.bayesian import MEANFIELD, GIBBS
     init_from_env()
-    if args.tc_mode >= 0:
-        E.set_tensor_cores(args.tc_mode)
-        config['tc_mode'] = args.tc_mode
+    cx = Ctx()
+    E = cx.E
     if world == 1:
         torch.cuda.set_device(0)
-    dev = torch.device('cuda', torch.cuda.current_device())
+    cx.dev = dev = torch.device('cuda', torch.cuda.current_device())
+    peaks = read_peaks()
+    t_start = time.perf_counter()
+
+    def comm_factory(n_global):
+        return Communicator(N_global=n_global) if world > 1 else None
+
     lo, hi = shard_bounds(w['N'], rank, world)
     n_local = hi - lo
     Z, true_labels = make_data(w, n_local, lo, 1337, dev)
-    comm = Communicator(N_global=w['N']) if world > 1 else None
+    comm = comm_factory(w['N'])
     model = build_model(w)
     s = make_session(model, w, Z, comm)
     K = w['K']
     hard = w['mode'] == 'gibbs'
-    rng = np.random.default_rng(7)
-
-    # initial statistics from the generating labels (one-hot), then the sweep loop
-    s.stat = E.stats_hard(s.Z, true_labels, K, s.feats, 'fp32')
-    if comm is not None:
-        comm.allreduce(s.stat)
+    # the model the timed sweeps run in: posterior of the statistics of the generating labels (a converged model)
+    init_from_labels(cx, s, true_labels, K, comm)
     del true_labels
-    phase = np.zeros(6)
-    vlbs = []
+    tcu = E.sweep_uses_tensor_cores(s.ops(1 if hard else 0), Z.shape[1])
+    screenable = tcu and w['kind'] == 'gmm' and w['d'] >= 24 and K >= 32 and not hard
+    head_mode = args.tc_mode if args.tc_mode >= 0 else (3 if screenable else None)
+    if head_mode is not None:
+        config['tc_mode'] = head_mode
+    config['regime'] = ('dense: every pair through the 3-pass tcgen05 E-step and the tcgen05 statistics GEMM (mimo_set_tensor_cores(3))'
+                        if head_mode == 3 else 'library default path')
+    config['model'] = 'posterior of the statistics of the generating labels; blob centres %g sigma apart' % (3.0 if w['kind'] == 'ilr' else 4.0)
 
-    def step(timed):
-        if hard:
-            var, gvar = s.draw_gibbs_variates()
-            ops, outs = s.update_from_stats(GIBBS, variates=var, gating_variates=gvar)
-            s.sweep(ops, hard=True, seed=int(rng.integers(1 << 30)), phase_ms=phase if timed else None)
-        else:
-            ops, outs = s.update_from_stats(MEANFIELD)
-            s.sweep(ops, hard=False, phase_ms=phase if timed else None)
-            vlbs.append(s.lower_bound(outs))
-        return outs
+    # ---- headline leg ------------------------------------------------------------------------------------------
+    stat0 = s.stat.clone()
+    leg = time_leg(cx, s, hard, args.steps, warmup, tc_mode=head_mode, sample_clocks=True)
+    ms = leg['ms']
+    value = w['N'] * K / (ms * 1e-3)
+    knames = [('E-step: tc_estep2_kernel<2,128,3> (3 x FP16 split, CTA pairs)' if (tcu and w['d'] > 64) else
+               'E-step (%s)' % ('tcgen05' if tcu else 'CUDA cores')), 'softmax / label draw',
+              ('statistics: tc_fstats_kernel (feature GEMM over the folded triangle)' if (tcu and w['d'] > 64) else 'sufficient statistics')]
+    roof = leg_roofline(w, n_local, leg, peaks, knames)
+    if name == 'cfg5' and not args.n_override:
+        dom = int(np.argmax(leg['phase'][:3]))
+        tr = ncu_traffic(['tc_estep2_kernel', 'softmax_kernel', 'tc_fstats_kernel'][dom])
+        if tr:
+            roof['traffic'] = tr['bytes']
+            roof['traffic_source'] = tr['source']
+    launches = int(leg['phase'][3] + {'gmm': 4, 'dgmm': 3, 'ilr': 7}[w['kind']] * args.steps)
 
-    for _ in range(args.warmup):
-        outs = step(False)
-    s.check(outs)
-    torch.cuda.synchronize()
-    if os.environ.get('MIMO_BENCH_DEBUG') and not hard:
-        for rep in range(2):
-            t = [time.perf_counter()]
-            ops, outs = s.update_from_stats(MEANFIELD); torch.cuda.synchronize(); t.append(time.perf_counter())
-            s.sweep(ops, hard=False); torch.cuda.synchronize(); t.append(time.perf_counter())
-            s.lower_bound(outs); t.append(time.perf_counter())
-            ph = np.zeros(6)
-            s.sweep(ops, hard=False, phase_ms=ph); torch.cuda.synchronize(); t.append(time.perf_counter())
-            sys.stderr.write('DEBUG update %.2f ms | sweep %.2f ms | vlb %.2f ms | timed sweep %.2f ms phases %s\n'
-                             % tuple([1e3 * (t[i + 1] - t[i]) for i in range(4)] + [ph.tolist()]))
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        outs = step(True)
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    clocks = sampler.stop() if sampler else None
-    s.check(outs)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    screened = (args.tc_mode in (-1, 1, 4)) and w['kind'] == 'gmm' and w['d'] >= 24 and K >= 32 and not hard
-    screen = None
-    if rank == 0 and screened and E.sweep_uses_tensor_cores(s.ops(0), w['d']):
-        cands, fell_back = E.screen_last()
-        screen = dict(last_chunk_candidate_pairs=cands, last_chunk_dense_fallback=bool(fell_back))
-    # end-to-end through the host-buffer C-ABI call on every rank: pinned host shard in, statistics out (+ the
-    # all-reduce of the statistics when sharded), every step
-    e2e = None
-    if not args.no_e2e:
+    # ---- the library's default (screened) path on the same data and model --------------------------------------
+    screened = None
+    if screenable and head_mode == 3 and not args.no_screened:
+        s.stat = stat0.clone()
+        sl = time_leg(cx, s, hard, args.steps, warmup, tc_mode=1)
+        tot = screen_totals(cx, n_local, K)
+        kms = sl['phase'][5] / sl['steps']                         # the screening kernel alone
+        chunks = max(1.0, sl['phase'][4]) / sl['steps']
+        rp = 1 << (max(w['d'], 8) - 1).bit_length()
+        pairs = n_local * K
+        mhz = (leg['clocks'] or {}).get('sm_mhz') or 1900.0
+        floor_ms = pairs * min(rp, 32) * 4 / (64.0 * 148 * mhz * 1e6) * 1e3       # accumulator read-back, 64 B/clk/SM
+        screened = dict(value=w['N'] * K / (sl['ms'] * 1e-3), unit='points*components/s', ms_per_step=sl['ms'], steps=sl['steps'],
+                        warmup=sl['warmup'], per_rank=tot,
+                        dominant_kernel=dict(kernel='tc_estep2_kernel<2,32,1> screening pass', ms_per_step=kms, launches_per_step=chunks,
+                                             bound='TMEM read port (64 B/clk/SM)', floor_ms_per_step=floor_ms,
+                                             frac_of_floor=floor_ms / kms if kms > 0 else None,
+                                             executed_mma_tflops=2.0 * min(rp, 32) * w['d'] * pairs / (kms * 1e-3) / 1e12 if kms > 0 else None),
+                        phase_ms_per_step=dict(estep=sl['phase'][0] / sl['steps'], softmax=sl['phase'][1] / sl['steps'],
+                                               stats=sl['phase'][2] / sl['steps']),
+                        lower_bound=sl['vlbs'][-2:], gpu_launches=int(sl['phase'][3]),
+                        note='does not execute the SURVEY 8(d) flops: one FP16 pass over a 32-row orthogonal projection bounds '
+                             'every log-joint, pairs within 40 nats of a point\'s best component are recomputed in FP32, statistics '
+                             'are summed over those pairs; chunks with > 4 % candidates take the dense kernels (device-side)')
+
+    # ---- parity of what was just timed, on a sub-sample against the oracle -------------------------------------
+    parity = None
+    if name == 'cfg5' and w['kind'] == 'gmm' and not args.no_parity:
+        s.stat = stat0.clone()
         try:
-            e2e = time_e2e(w, s, E, _lib, hard, min(args.steps, 2), comm)
-        except Exception as ex:   # report, never fake
+            parity = parity_subsample(cx, s, w, args.parity_points)
+        except Exception as ex:            # report, never fake
             if world > 1:
                 raise
-            e2e = dict(value=None, unit='points*components/s', error=str(ex)[:200])
+            parity = dict(error=str(ex)[:300])
+
+    # ---- end to end --------------------------------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        s.stat = stat0.clone()
+        try:
+            pinned = {}
+            e2e = time_e2e(cx, w, s, hard, 3 if (ms > 2000) else min(max(args.steps, 3), 5), comm, tc_mode=head_mode, cache=pinned)
+            if screened is not None:
+                s.stat = stat0.clone()
+                screened['e2e'] = time_e2e(cx, w, s, hard, min(max(args.steps, 3), 5), comm, tc_mode=1, cache=pinned)
+            del pinned
+        except Exception as ex:
+            if world > 1:
+                raise
+            e2e = dict(value=None, unit='points*components/s', error=str(ex)[:300])
+    del s, Z, stat0
+    torch.cuda.empty_cache()
+
+    # ---- overlapping components, random start ------------------------------------------------------------------
+    overlap = None
+    if screenable and not args.no_overlap:
+        overlap = overlap_leg(cx, w, args.steps, comm_factory, peaks)
+
+    # ---- the other BASELINE.json shapes, short legs ------------------------------------------------------------
+    others = None
+    if name == 'cfg5' and not args.no_others and not args.n_override:
+        others = {}
+        for nm in ('cfg1', 'cfg2', 'cfg3', 'cfg4'):
+            try:
+                others[nm] = run_config(cx, nm, min(args.steps, 5), 3, comm_factory, peaks)
+            except Exception as ex:
+                if world > 1:
+                    raise
+                others[nm] = dict(error=str(ex)[:300])
     if rank != 0:
         return
-
-    peaks = read_peaks()
-    work = algorithmic_work(w)
-    value = w['N'] * K / (ms * 1e-3)
-    # roofline of the dominant kernel, from the per-phase CUDA-event times of the timed steps
-    chunks = max(1.0, phase[4])          # point chunks over the timed steps = launches of each per-chunk kernel
-    phase_ms = phase[:3] / args.steps
-    dom = int(np.argmax(phase_ms))
-    pairs_local = n_local * K
-    t_hbm = n_local * work['bytes_pt'] / (peaks['hbm'] * 1e9)
-    flops = [work['e_flops_pair'] * pairs_local, 0.0, work['s_flops_pair'] * pairs_local]
-    t_tensor = sum(flops) / (peaks['tf_sus'] * 1e12)
-    bound = 'tensor' if t_tensor >= t_hbm else 'hbm'
-    launches_per_step = 1.0 if (hard and dom == 2) else chunks / args.steps
-    if bound == 'tensor':
-        ach = flops[dom] / (phase_ms[dom] * 1e-3) / 1e12 if phase_ms[dom] > 0 else 0.0
-        roof = dict(bound='tensor', achieved=ach, peak=peaks['tf_sus'], unit='TFLOP/s', frac=ach / peaks['tf_sus'], traffic=None)
-    else:
-        ach = n_local * work['bytes_pt'] / (phase_ms[dom] * 1e-3) / 1e9 if phase_ms[dom] > 0 else 0.0
-        roof = dict(bound='hbm', achieved=ach, peak=peaks['hbm'], unit='GB/s', frac=ach / peaks['hbm'], traffic=None)
-    if name == 'cfg5' and not args.n_override:
-        tr = ncu_traffic([('tc_estep2_screen_kernel' if screened else 'tc_estep2_kernel'), 'softmax_kernel',
-                          ('pair_stats_kernel' if screened else 'tc_fstats_kernel')][dom])
-        if tr:
-            roof['traffic'] = tr['bytes']                     # DRAM bytes per launch (one ~1M-point chunk)
-            roof['traffic_source'] = tr['source']
-    if bound == 'tensor' and w['kind'] == 'gmm' and w['d'] >= 24:
-        # what the tensor pipe really executes for the E-step: 3 FP16 passes over all Rp operand rows on the dense path;
-        # 1 pass over the 32 projected rows on the screened path (plus FP32 CUDA-core work on the candidate lists)
-        rp = 1 << (max(w['d'], 8) - 1).bit_length()
-        mma_pair = (2.0 * min(rp, 32) * w['d']) if screened else (3 * 2.0 * rp * w['d'])
-        if phase_ms[0] > 0:
-            roof['estep_executed_tflops'] = mma_pair * pairs_local / (phase_ms[0] * 1e-3) / 1e12
-        roof['note'] = ('achieved = ALGORITHMIC flops of the dense formulation (SURVEY 8d) / time; the default path is SCREENED: one '
-                        'FP16 pass over a 32-row orthogonal projection of every operand bounds all N*K log-joints, pairs within 40 '
-                        'nats of a point\'s best component are recomputed in FP32, statistics are summed over those pairs only, so '
-                        'frac can exceed 1; `dense_path` is the same sweep with screening off (3-pass dense tensor-core kernels)'
-                        if screened else 'dense 3-pass tensor-core path')
-    if dom == 0 and bound == 'tensor' and phase[5] > 0:
-        # the dominant KERNEL of the E-step phase (on the screened path: the screening pass; the rest of the phase is list
-        # building and refinement): algorithmic E-step flops / its own launch time
-        kms = phase[5] / args.steps
-        roof['achieved'] = flops[0] / (kms * 1e-3) / 1e12
-        roof['frac'] = roof['achieved'] / peaks['tf_sus']
-        roof['kernel_ms_per_step'] = kms
-    roof.update(kernel=[('E-step: tc_estep2_kernel<.,32,1> screening pass' if screened else 'E-step (log-likelihood)'),
-                        'softmax / label draw', 'sufficient statistics'][dom],
-                launches_per_step=launches_per_step,
-                ms_per_launch=(phase[5] / args.steps if (dom == 0 and phase[5] > 0) else phase_ms[dom]) / max(launches_per_step, 1),
-                phase_ms_per_step=dict(estep=phase_ms[0], softmax=phase_ms[1], stats=phase_ms[2]),
-                peak_source='%s (sustained bf16 / copy bandwidth of MEASURED_PEAKS.json)' % peaks['src'],
-                whole_sweep_frac=(sum(flops) / (ms * 1e-3) / 1e12) / peaks['tf_sus'] if bound == 'tensor'
-                else (n_local * work['bytes_pt'] / (ms * 1e-3) / 1e9) / peaks['hbm'])
 
     cpu = None
     if not args.no_cpu and world == 1:
         cpu, _ = time_cpu(w, name, 1, 1 if CPU_SAMPLE[name] * K < 5e6 else 0)
-    # the same sweep with the screening off (dense 3-pass E-step + dense tensor-core statistics): what overlapping
-    # components would cost; one warm-up + one timed sweep
-    dense = None
-    vlb_tail = vlbs[-3:] if vlbs else None
-    if world == 1 and screened and E.sweep_uses_tensor_cores(s.ops(0), w['d']):
-        if not args.no_dense:
-            old = E.set_tensor_cores(3)
-            try:
-                step(False)
-                torch.cuda.synchronize()
-                d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                d0.record()
-                step(False)
-                d1.record()
-                torch.cuda.synchronize()
-                dms = d0.elapsed_time(d1)
-                dense = dict(value=w['N'] * K / (dms * 1e-3), unit='points*components/s', ms_per_step=dms, steps=1, warmup=1,
-                             tensor_frac=(sum(flops) / (dms * 1e-3) / 1e12) / peaks['tf_sus'],
-                             what='mimo_set_tensor_cores(3): dense 3-pass E-step and dense statistics on every chunk')
-            finally:
-                E.set_tensor_cores(old)
-    posterior_launches = {'gmm': 4, 'dgmm': 3, 'ilr': 7}[w['kind']]
     line = dict(metric='points*components/s per full sweep', value=value, unit='points*components/s', n_gpus=world,
-                steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='strong',
+                steps=args.steps, warmup=warmup, ms_per_step=ms, higher_is_better=True, scaling='strong',
                 vs_baseline=None, dtype='f32', data='synthetic', config=config, roofline=roof, cpu_baseline=cpu, e2e=e2e,
-                gpu_launches=int(phase[3] + posterior_launches * args.steps), clocks=clocks,
-                lower_bound=vlb_tail, screen=screen, dense_path=dense,
-                comm=dict(messages=comm.messages, bytes_per_message=comm.bytes // max(comm.messages, 1)) if comm else None)
+                gpu_launches=launches, clocks=leg['clocks'], lower_bound=leg['vlbs'][-3:] if leg['vlbs'] else None,
+                parity_subsample=parity, screened_path=screened, overlap_regime=overlap, other_configs=others,
+                comm=dict(messages=comm.messages, bytes_per_message=comm.bytes // max(comm.messages, 1)) if comm else None,
+                bench_seconds=time.perf_counter() - t_start)
     print(json.dumps(line))
-
-
-def time_e2e(w, s, E, _lib, hard, steps, comm=None):
-    """mimo_sweep_host on every rank: pinned host shard of Z -> device, one sweep with the current operands,
-    statistics + lower-bound scalar (+ labels) back to the host; when sharded, the all-reduce of the statistics
-    closes the step.  Everything inside the timed region; the step time is the max over ranks."""
-    import torch
-    import torch.distributed as dist
-    N, D = s.Z.shape
-    world = comm.world if comm is not None else 1
-    ops = s.ops(1 if hard else 0)
-    zh = torch.empty((N, D), dtype=torch.float32, pin_memory=True)
-    zh.copy_(s.Z)
-    a, b = (ops.W, None) if ops.family == 0 else (ops.S, ops.T)
-    ah = a.cpu().contiguous()
-    bh = b.cpu().contiguous() if b is not None else None
-    ch = ops.cst.cpu().contiguous()
-    flat_h = torch.zeros((s.K * s.F + 1,), dtype=torch.float64, pin_memory=True)      # statistics | sum of lse
-    stat_h, lse_h = flat_h[:s.K * s.F], flat_h[s.K * s.F:]
-    flat_d = torch.empty_like(flat_h, device=s.Z.device) if world > 1 else None
-    lab_h = torch.empty((N,), dtype=torch.int32, pin_memory=True) if hard else None
-    fi, fj = s.feats.fi_host, s.feats.fj_host
-    torch.cuda.synchronize()
-    times = []
-    for it in range(steps + 1):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        _lib.call('mimo_sweep_host', 0, ops.family, 1 if hard else 0, zh.data_ptr(), N, D,
-                  ah.data_ptr(), bh.data_ptr() if bh is not None else None, ch.data_ptr(), ops.K, ops.Rp, ops.Dpp,
-                  fi.ctypes.data, fj.ctypes.data, s.F, None, 12345 + it,
-                  stat_h.data_ptr(), lse_h.data_ptr(), lab_h.data_ptr() if lab_h is not None else None)
-        if world > 1:                                   # close the sweep: sum the shard statistics
-            flat_d.copy_(flat_h, non_blocking=True)
-            comm.allreduce(flat_d)
-            flat_h.copy_(flat_d, non_blocking=True)
-            torch.cuda.synchronize()
-        times.append(time.perf_counter() - t0)
-    _lib.call('mimo_sweep_host_release')             # give the call's cached device buffers back
-    dt = float(np.mean(times[1:]))
-    if world > 1:
-        t = torch.tensor([dt], device=s.Z.device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    ops_b = ah.numel() * 4 + (bh.numel() * 4 if bh is not None else 0) + ch.numel() * 4 + 2 * s.F * 4
-    h2d = w['N'] * D * 4 + world * ops_b + (world * s.K * s.F * 8 if world > 1 else 0)
-    d2h = world * (s.K * s.F * 8 + 8) * (2 if world > 1 else 1) + (w['N'] * 4 if hard else 0)
-    return dict(value=w['N'] * s.K / dt, unit='points*components/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                ms_per_step=dt * 1e3, call='mimo_sweep_host (C-ABI, pinned host buffers) on every rank'
-                                           + (' + all-reduce of the statistics' if world > 1 else ''))
 
 
 if __name__ == '__main__':

@@ -35,6 +35,9 @@
  *   full family : all pairs j <= i, f = i(i+1)/2 + j    (F = Dp(Dp+1)/2)
  *   diag family : (j,D) j<D ; (j,j) j<D ; (D,D)         (F = 2D+1)
  * This K x F buffer is exactly what the data-sharded driver all-reduces.
+ * Any (fi, fj) table is accepted.  The list / tensor-core statistics kernels of mimo_sweep produce the "full family"
+ * order above; the sweep reads the table back once per call (F * 8 bytes) and takes the generic kernel for any other
+ * table, so the result never depends on which kernel ran.
  */
 #ifndef MIMO_B200_H
 #define MIMO_B200_H
@@ -108,6 +111,9 @@ int mimo_softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags,
 int mimo_set_tensor_cores(int mode);
 /* {candidate pairs, dense-fallback flag} of the most recent screened point chunk (synchronises; diagnostics) */
 int mimo_tc_screen_last(uint32_t* out_host2);
+/* totals of the most recent screened sweep over ALL its point chunks: {candidate pairs of the refined chunks,
+ * points of the refined chunks, chunks that took the dense pass, chunks, tier the sweep ended on} (synchronises) */
+int mimo_tc_screen_totals(uint64_t* out_host5);
 /* screening tier the most recent screened sweep ended on: 0 projection, 1 all operand rows, 2 none (dense); -1 unknown */
 int mimo_tc_screen_level(void);
 int mimo_sweep_uses_tensor_cores(int dtype, int family, int D, int Rp);

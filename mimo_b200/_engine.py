@@ -264,6 +264,7 @@ def sweep(Z, ops, feats, buf, uniforms=None, seed=0, offset=0, ll_out=None, lse_
     buf.lse_sum and (hard) buf.labels.  phase_ms: optional float64 numpy array (6,) that
     accumulates per-phase device milliseconds, the launch count and the chunk count (synchronises)."""
     N, D = Z.shape
+    assert Z.is_cuda and Z.dtype == tdtype(ops.precision) and D == ops.D, 'data must be a resident %s tensor of width %d' % (ops.precision, ops.D)
     fi, fj = feats.dev()
     buf.ensure(ops, D)
     if zero:
@@ -466,6 +467,14 @@ def screen_last():
     out = np.zeros(2, dtype=np.uint32)
     _lib.call('mimo_tc_screen_last', out.ctypes.data)
     return int(out[0]), int(out[1])
+
+
+def screen_totals():
+    """totals of the most recent screened sweep over ALL its point chunks: (candidate pairs of the refined chunks,
+    points of the refined chunks, chunks that took the dense pass, chunks, tier the sweep ended on)."""
+    out = np.zeros(5, dtype=np.uint64)
+    _lib.call('mimo_tc_screen_totals', out.ctypes.data)
+    return tuple(int(v) for v in out)
 
 
 def screen_level():

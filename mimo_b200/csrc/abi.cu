@@ -74,6 +74,7 @@ size_t mimo_sweep_workspace(int dtype, int family, int hard, int64_t N, int D, i
 }
 int mimo_set_tensor_cores(int mode) { return tc_set_mode(mode); }
 int mimo_tc_screen_last(uint32_t* out_host2) { return tc_screen_last(out_host2); }
+int mimo_tc_screen_totals(uint64_t* out_host5) { return tc_screen_totals((unsigned long long*)out_host5); }
 int mimo_sweep_uses_tensor_cores(int dtype, int family, int D, int Rp) { return sweep_uses_tc(dtype, family, D, Rp) ? 1 : 0; }
 int mimo_tc_set_flush_tiles(int tiles) { tc_set_flush_tiles(tiles); tc_fstats_set_flush_tiles(tiles); return MIMO_OK; }
 size_t mimo_loglik_quad_tc_workspace(int K, int Rp, int D) { return tc_operand_workspace(K, Rp, D); }

@@ -45,6 +45,7 @@ int tc_screen_pass(const float* Z, int64_t n, int D, int64_t ldz, int K, int Rp,
 int tc_screen_begin(int64_t plan_points, int K, int Rp, int start_level, void* ws, cudaStream_t st);
 const unsigned int* tc_screen_gate(void* ws, int64_t plan_points, int K);
 int tc_screen_last(unsigned int* out_host2);
+int tc_screen_totals(unsigned long long* out_host5);
 void tc_screen_forget();
 int tc_screen_level();
 int tc_screen_select(const float* Z, int D, int64_t ldz, const float* W, const float* cst, int K, int Rp, int Dpp,

@@ -41,6 +41,30 @@ static bool sweep_uses_resp_list(int dtype, int family, int hard, int D, int K, 
 //  tensor-core path: the kernels are persistent (one CTA per SM walking 256-point pairs / 4-component
 //    units), so a chunk is many waves of 256 x #SM points; the scratch (<= 4 GB) streams through HBM,
 //    which costs ~12 B per pair against ~66 kflop at d = 128.
+// The list / tensor-core statistics kernels write the CANONICAL packed triangle (f = i (i + 1) / 2 + j over zt = [z ; 1]);
+// a caller's (fi, fj) table of the same length in another order must take the generic kernel.  The table is read back
+// once per sweep (F * 8 bytes) -- mimo_sweep_host checks its host copy instead and leaves the answer in g_tables_hint.
+static thread_local int g_tables_hint = -1;              // -1 unknown, 0 not canonical, 1 canonical
+static bool canonical_host(const int32_t* fi, const int32_t* fj, int F, int D) {
+    if (F != (D + 1) * (D + 2) / 2) return false;
+    int f = 0;
+    for (int i = 0; i <= D; ++i)
+        for (int j = 0; j <= i; ++j, ++f)
+            if (fi[f] != i || fj[f] != j) return false;
+    return true;
+}
+static int tables_canonical(const int32_t* fi, const int32_t* fj, int F, int D, cudaStream_t st, bool* out) {
+    *out = false;
+    if (F != (D + 1) * (D + 2) / 2) return MIMO_OK;
+    if (g_tables_hint >= 0) { *out = g_tables_hint == 1; return MIMO_OK; }
+    std::vector<int32_t> h((size_t)2 * F);
+    MIMO_CUDA(cudaMemcpyAsync(h.data(), fi, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
+    MIMO_CUDA(cudaMemcpyAsync(h.data() + F, fj, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
+    MIMO_CUDA(cudaStreamSynchronize(st));
+    *out = canonical_host(h.data(), h.data() + F, F, D);
+    return MIMO_OK;
+}
+
 int64_t sweep_chunk_points(int dtype, int family, int64_t N, int D, int K, int Rp) {
     size_t es = dtype == MIMO_F32 ? 4 : 8;
     int64_t npad = (N + 255) / 256 * 256;
@@ -97,7 +121,13 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     const size_t hard_ws_bytes = hard ? stats_hard_workspace(N, K) : 0;
     if (hard) ws += a256(hard_ws_bytes);
     void* resp_ws = nullptr;
-    const bool resp_list = stat && sweep_uses_resp_list(dtype, family, hard, D, K, Rp) && pair_stats_supported(dtype, D, F);
+    // soft statistics through the list / tensor-core kernels need the canonical packed triangle (checked, not assumed)
+    bool canon = false;
+    if (stat && !hard && family == 0 && dtype == MIMO_F32 && (use_tc || sweep_uses_resp_list(dtype, family, hard, D, K, Rp))) {
+        int rc = tables_canonical(fi, fj, F, D, st, &canon);
+        if (rc) return rc;
+    }
+    const bool resp_list = stat && canon && sweep_uses_resp_list(dtype, family, hard, D, K, Rp) && pair_stats_supported(dtype, D, F);
     if (sweep_uses_resp_list(dtype, family, hard, D, K, Rp)) { resp_ws = ws; ws += a256(resp_list_workspace(C, K)); }
     void* tc_ops_ws = nullptr;
     void* tc_stat_ws = nullptr;
@@ -106,7 +136,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     // the (K, N) log-joint output must hold FP32-class values for every pair: no screening then
     const bool use_screen = sweep_uses_screen(dtype, family, D, K, Rp) && !ll_out && Dpp <= D + 4;   // (workspace is sized for Dpp <= D + 4)
     // the packed full-triangle statistics are what the tensor-core statistics kernel produces
-    const bool tc_stats = use_tc && stat && !hard && tc_stats_supported(dtype, D, F);
+    const bool tc_stats = use_tc && stat && !hard && canon && tc_stats_supported(dtype, D, F);
     const bool tc_fstats = tc_stats && tc_fstats_supported(dtype, D, F);     // feature form (folded triangle) for D > 64
     const bool pair_stats_list = tc_stats && use_screen && g_tc_mode != 4 && pair_stats_supported(dtype, D, F);
     // ... and the log-normalisers too: no pass over the (K, chunk) scratch after the refinement on such chunks
@@ -297,6 +327,8 @@ int sweep_host(int dtype, int family, int hard, const void* Z_host, int64_t N, i
     MIMO_CHECK_ARG(Z_host && op_a_host && cst_host && fi_host && fj_host && stat_host, "null pointer");
     MIMO_CHECK_ARG(N >= 0 && D >= 1 && K >= 1 && F >= 1, "shape");
     const size_t es = dtype == MIMO_F32 ? 4 : 8;
+    struct HintGuard { HintGuard(int v) { g_tables_hint = v; } ~HintGuard() { g_tables_hint = -1; } }
+        hint(canonical_host(fi_host, fj_host, F, D) ? 1 : 0);
     const size_t zb = (size_t)N * D * es;
     const size_t ab = (family == 0 ? (size_t)K * Rp * Dpp : (size_t)K * D) * es;
     const int64_t C = sweep_chunk_points(dtype, family, N, D, K, Rp);

@@ -188,9 +188,12 @@ screen_emit_kernel(const float* __restrict__ a, int K, int64_t n, int64_t ldo, i
 // ~10x a projected screening pass, so a failed tier is not worth retrying.
 __global__ void screen_scan_kernel(const int* __restrict__ hist, int K, int* __restrict__ offsets, int* __restrict__ cursor,
                                    int* __restrict__ slabs, unsigned int* __restrict__ counters, unsigned int max_cands,
-                                   unsigned int* __restrict__ level) {
+                                   unsigned int* __restrict__ level, unsigned int n_points) {
     if (threadIdx.x == 0) {
-        if (level && *level >= 2u) { if (counters) counters[1] = 1u; return; }
+        // sweep totals behind the level word (tc_screen_totals): [2,3] candidate pairs of the refined chunks,
+        // [4,5] their points, [6] chunks that took the dense pass, [7] chunks
+        unsigned long long* tot = level ? reinterpret_cast<unsigned long long*>(level + 2) : nullptr;
+        if (level && *level >= 2u) { if (counters) { counters[1] = 1u; level[6] += 1u; level[7] += 1u; } return; }
         int run = 0, items = 0;
         for (int k = 0; k < K; ++k) {
             offsets[k] = run; cursor[k] = run; slabs[k] = items;
@@ -201,7 +204,11 @@ __global__ void screen_scan_kernel(const int* __restrict__ hist, int K, int* __r
         slabs[K] = items;
         if (counters) {
             counters[1] = (counters[0] > max_cands) ? 1u : 0u;
-            if (level && counters[1]) *level += 1u;
+            if (level) {
+                if (counters[1]) { *level += 1u; level[6] += 1u; }
+                else { tot[0] += (unsigned long long)counters[0] + n_points; tot[1] += n_points; }
+                level[7] += 1u;
+            }
         }
     }
 }
@@ -493,7 +500,10 @@ int tc_screen_pass(const float* Z, int64_t n, int D, int64_t ldz, int K, int Rp,
                          (float*)(base + L.off_best_val), (int*)(base + L.off_best_k), L.ldl, st);
 }
 
-__global__ void screen_level_kernel(unsigned int* level, unsigned int v) { *level = v; }
+__global__ void screen_level_kernel(unsigned int* level, unsigned int v) {
+    *level = v;
+    for (int i = 1; i < 8; ++i) level[i] = 0u;           // sweep totals (screen_scan_kernel)
+}
 
 // once per sweep: the screening tier the first chunk starts on (0 projected rows -- needs Rp > 32 --, 1 all rows)
 int tc_screen_begin(int64_t plan_points, int K, int Rp, int start_level, void* ws, cudaStream_t st) {
@@ -532,6 +542,20 @@ int tc_screen_level() {
     if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(&v, g_last_level, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return (int)v;
 }   // the workspace the counters live in is going away
+
+// totals of the most recent screened sweep: {candidate pairs (guesses + list B) of the refined chunks, points of the
+// refined chunks, chunks that took the dense pass, chunks, tier the sweep ended on}; synchronises
+int tc_screen_totals(unsigned long long* out_host5) {
+    for (int i = 0; i < 5; ++i) out_host5[i] = 0ull;
+    if (!g_last_level) return MIMO_OK;
+    unsigned int h[8];
+    MIMO_CUDA(cudaDeviceSynchronize());
+    MIMO_CUDA(cudaMemcpy(h, g_last_level, sizeof(h), cudaMemcpyDeviceToHost));
+    out_host5[0] = ((unsigned long long)h[3] << 32) | h[2];
+    out_host5[1] = ((unsigned long long)h[5] << 32) | h[4];
+    out_host5[2] = h[6]; out_host5[3] = h[7]; out_host5[4] = h[0];
+    return MIMO_OK;
+}
 
 // {candidates (guesses + list B), dense flag} of the most recent screened chunk (synchronises the device; tests / bench reporting)
 int tc_screen_last(unsigned int* out_host2) {
@@ -585,7 +609,7 @@ int tc_screen_select(const float* Z, int D, int64_t ldz, const float* W, const f
     screen_guess_kernel<<<grid, 256, 0, st>>>((const float*)(base + L.off_best_val), (const int*)(base + L.off_best_k), L.ldl, n, K,
                                               guess_k, (int*)(base + L.A.hist), level);
     screen_scan_kernel<<<1, 32, 0, st>>>((const int*)(base + L.A.hist), K, (int*)(base + L.A.offsets), (int*)(base + L.A.cursor),
-                                         (int*)(base + L.A.slabs), nullptr, 0u, nullptr);
+                                         (int*)(base + L.A.slabs), nullptr, 0u, nullptr, 0u);
     screen_scatterA_kernel<<<grid, 256, 0, st>>>(guess_k, n, (int*)(base + L.A.cursor), (int*)(base + L.A.perm), level);
     MIMO_LAUNCH_CHECK();
     int rc = refine(Z, D, ldz, W, K, Rp, Dpp, cst, (const int*)(base + L.A.perm), (const int*)(base + L.A.offsets), (const int*)(base + L.A.slabs), level, 2u, a, ldo, lower, st);
@@ -596,7 +620,7 @@ int tc_screen_select(const float* Z, int D, int64_t ldz, const float* W, const f
         lower, guess_k, (int2*)(base + L.off_list), L.cap, counters, (int*)(base + L.B.hist), level);
     const double maxc = std::min<double>((double)L.cap, 0.04 * (double)n * K);
     screen_scan_kernel<<<1, 32, 0, st>>>((const int*)(base + L.B.hist), K, (int*)(base + L.B.offsets), (int*)(base + L.B.cursor),
-                                         (int*)(base + L.B.slabs), counters, (unsigned int)maxc, level);
+                                         (int*)(base + L.B.slabs), counters, (unsigned int)maxc, level, (unsigned int)n);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
@@ -702,7 +726,7 @@ int resp_list_build(const float* R, int K, int64_t n, int64_t ldr, int D, int64_
     resp_emit_kernel<<<cdiv(n, 256), 256, 0, st>>>(R, K, n, ldr, (int2*)(base + L.list), L.cap, counters, (int*)(base + L.hist));
     const double maxc = std::min<double>((double)L.cap, rl_max_frac(D) * (double)n * K);
     screen_scan_kernel<<<1, 32, 0, st>>>((const int*)(base + L.hist), K, (int*)(base + L.offsets), (int*)(base + L.cursor),
-                                         (int*)(base + L.slabs), counters, (unsigned int)maxc, nullptr);
+                                         (int*)(base + L.slabs), counters, (unsigned int)maxc, nullptr, 0u);
     screen_scatter_kernel<<<sm_count() * 4, 256, 0, st>>>((const int2*)(base + L.list), counters, (int*)(base + L.cursor), (int*)(base + L.perm));
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;

@@ -52,11 +52,11 @@ class _GatingBase:
         pa, pb = prior_dev or self._prior_dev()
         return E.gating_posterior(self._kind, pa, pb, stat, F, count_feature, mode=mode, variates=variates, ops=ops)
 
-    def _apply_counts(self, counts, mode, variates=None):
+    def _apply_counts(self, counts, mode, variates=None, set_probs=True):
         stat = E.to_dev(np.asarray(counts, dtype=np.float64).reshape(-1, 1))
         out = self._update(stat, 1, 0, mode, variates=variates)
         out['info'].check()
-        self._store(out)
+        self._store(out, set_probs=set_probs)
         return out
 
     def _store(self, out, set_probs=True):
@@ -76,12 +76,18 @@ class _GatingBase:
         self._apply_counts(counts, GIBBS, variates=self._draw_variates(counts))
 
     def meanfield_update(self, data, weights=None):
-        out = self._apply_counts(self._counts(data, weights), MEANFIELD)
+        """bayesian.py:77-83 / 151-159: the posterior update, then likelihood.params = posterior.rvs() -- a valid
+        probability vector drawn from the global numpy.random stream like the reference, NOT the
+        unnormalised exp(E log pi) the mean-field kernel works with."""
+        out = self._apply_counts(self._counts(data, weights), MEANFIELD, set_probs=False)
+        self.likelihood.params = self.posterior.rvs()
         return out
 
     def meanfield_sgd(self, data, weights, scale, step_size):
+        """bayesian.py:85-91 / 161-171 (ends with the same posterior.rvs() draw)."""
         counts = self._counts(data, weights)
         self._sgd_blend(counts, scale, step_size)
+        self.likelihood.params = self.posterior.rvs()
 
     def variational_lowerbound(self):
         return self.posterior.entropy() - self.posterior.cross_entropy(self.prior)
@@ -145,6 +151,15 @@ class _ComponentsBase:
 
     def _precision(self):
         return self.likelihood.precision or E.default_precision()
+
+    # the reference ends every mean-field / SGD update with likelihood.params = posterior.rvs()
+    # (bayesian.py:230,238,391,399,844,852): the draw consumes the global numpy.random stream and leaves SAMPLED
+    # likelihood parameters.  Kept here for the stand-alone wrappers; the fused sweep drivers skip it unless asked.
+    sample_likelihood = True
+
+    def _after_meanfield(self):
+        if self.sample_likelihood:
+            self.likelihood.params = self.posterior.rvs()
 
     def variational_lowerbound(self):
         return self.posterior.entropy() - self.posterior.cross_entropy(self.prior)
@@ -249,11 +264,13 @@ class StackedGaussiansWithNormalWisharts(_ComponentsBase):
 
     def meanfield_update(self, data, weights=None):
         self._run(self._stats(data, weights), MEANFIELD)
+        self._after_meanfield()
 
     def meanfield_sgd(self, data, weights, scale, step_size):
         stats = self.likelihood.weighted_statistics(data, self._unit_weights(data) if weights is None else weights)
         self.posterior.nat_param = (1. - step_size) * self.posterior.nat_param \
             + step_size * (self.prior.nat_param + 1. / scale * stats)
+        self._after_meanfield()
 
     def expected_log_likelihood(self, x):
         precision = self._precision()
@@ -321,7 +338,7 @@ class GaussianWithNormalWishart:
     def meanfield_update(self, data, weights=None):
         w = self._stacked()
         w.meanfield_update(data, None if weights is None else np.asarray(weights)[None, :])
-        self._pull(w, lik=False)
+        self._pull(w)                       # likelihood.params = posterior.rvs() (bayesian.py:230)
 
     def variational_lowerbound(self):
         return self.posterior.entropy() - self.posterior.cross_entropy(self.prior)
@@ -421,11 +438,13 @@ class StackedGaussiansWithNormalGammas(_ComponentsBase):
 
     def meanfield_update(self, data, weights=None):
         self._run(self._stats(data, weights), MEANFIELD)
+        self._after_meanfield()
 
     def meanfield_sgd(self, data, weights, scale, step_size):
         stats = self.likelihood.weighted_statistics(data, self._unit_weights(data) if weights is None else weights)
         self.posterior.nat_param = (1. - step_size) * self.posterior.nat_param \
             + step_size * (self.prior.nat_param + 1. / scale * stats)
+        self._after_meanfield()
 
     def expected_log_likelihood(self, x):
         precision = self._precision()
@@ -514,11 +533,13 @@ class StackedLinearGaussiansWithMatrixNormalWisharts(_ComponentsBase):
 
     def meanfield_update(self, x, y, weights=None):
         self._run(self._stats(x, y, weights), MEANFIELD)
+        self._after_meanfield()
 
     def meanfield_sgd(self, x, y, weights, scale, step_size):
         stats = self.likelihood.weighted_statistics(x, y, self._unit_weights(x) if weights is None else weights)
         self.posterior.nat_param = (1. - step_size) * self.posterior.nat_param \
             + step_size * (self.prior.nat_param + 1. / scale * stats)
+        self._after_meanfield()
 
     def expected_log_likelihood(self, x, y):
         precision = self._precision()

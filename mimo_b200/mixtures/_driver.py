@@ -36,6 +36,8 @@ class Session:
         self.precision = precision or E.default_precision()
         self.K, self.gating, self.parts, self.family = K, gating, parts, family
         self.Z = z if isinstance(z, torch.Tensor) else E.to_dev(np.ascontiguousarray(z), E.tdtype(self.precision))
+        assert self.Z.is_cuda and self.Z.dtype == E.tdtype(self.precision), \
+            'a device tensor passed as data must be %s (precision %r)' % (E.tdtype(self.precision), self.precision)
         self.N, self.D = self.Z.shape
         self.feats = E.quad_features(self.D) if family == 'quad' else E.diag_features(self.D)
         self.F = self.feats.F
@@ -73,6 +75,35 @@ class Session:
     def stats_from_resp(self, resp):
         R = resp if isinstance(resp, torch.Tensor) else E.to_dev(resp, E.tdtype(self.precision))
         self.stat = self._reduce(E.stats_soft(self.Z, R, self.feats, self.precision))
+        return self.stat
+
+    def stats_from_random_resp(self, seed=0, chunk=None):
+        """statistics of random responsibilities (mixtures/gmm.py:265-267: uniform variates normalised over the
+        components) drawn ON THE DEVICE in point chunks, so no (K, N) array ever exists on the host -- the start of
+        `meanfield_coordinate_descent(randomize='device')` at sizes where npr.rand(K, N) cannot be built.  The
+        generator is keyed by (seed, global chunk index): the draw does not depend on the shard count."""
+        K, N = self.K, self.N
+        tdt = E.tdtype(self.precision)
+        chunk = chunk or max(256, min(1 << 20, (1 << 28) // max(K, 1)))
+        offset = self.comm.point_offset if self.comm is not None else 0
+        stat = E.zeros((K, self.F))
+        g = torch.Generator(device=self.Z.device)
+        lo = 0
+        while lo < N:
+            # global chunk grid so that shards reproduce the single-process draw
+            gchunk = (offset + lo) // chunk
+            hi = min(N, (gchunk + 1) * chunk - offset)
+            g.manual_seed(int(seed) * 1000003 + gchunk)
+            r = torch.rand((K, chunk), generator=g, device=self.Z.device, dtype=tdt)
+            a0 = offset + lo - gchunk * chunk
+            r = r[:, a0:a0 + (hi - lo)]
+            r = (r / r.sum(0, keepdim=True)).contiguous()
+            if self.precision == 'fp32' and self.family == 'quad' and 24 <= self.D <= 128:
+                E.stats_soft_tc(self.Z[lo:hi], r, self.feats, stat=stat)      # tcgen05 feature GEMM (accumulates)
+            else:
+                E.stats_soft(self.Z[lo:hi], r, self.feats, self.precision, stat=stat)
+            lo = hi
+        self.stat = self._reduce(stat)
         return self.stat
 
     def _reduce(self, stat):
@@ -206,10 +237,17 @@ class Session:
         return float(torch.cat(terms).sum().item())
 
     def check(self, outs):
-        if 'gating' in outs:
-            outs['gating']['info'].check()
-        for o in outs['parts']:
-            o['info'].check()
+        infos = ([outs['gating']['info']] if 'gating' in outs else []) + [o['info'] for o in outs['parts']]
+        if self.comm is not None and self.comm.world > 1:
+            # every rank must raise together (a rank that factorised only its K / world components would otherwise
+            # fail alone and leave the others waiting in the next collective)
+            import torch.distributed as dist
+            word = torch.stack([i.t for i in infos]).view(-1)
+            dist.all_reduce(word, op=dist.ReduceOp.MAX, group=self.comm.group)
+            for n, i in enumerate(infos):
+                i.t.copy_(word.view(-1, 2)[n])
+        for i in infos:
+            i.check()
 
     def store(self, outs, mode, set_probs=True):
         """download posterior (and sampled / mode likelihood) parameters into the model."""
@@ -222,16 +260,47 @@ class Session:
     def counts_host(self):
         return E.to_host(self.stat[:, self.count_feature])
 
+    def host_draw(self, fn):
+        """fn() on rank 0 (its numpy.random stream is THE stream of a sharded chain), the result broadcast to every
+        rank: all ranks then update the same parameters from the same variates.  Without a communicator: fn()."""
+        c = self.comm
+        if c is None or c.world <= 1:
+            return fn()
+        import torch.distributed as dist
+        box = [fn() if c.rank == 0 else None]
+        src = dist.get_global_rank(c.group, 0) if c.group is not None else 0
+        dist.broadcast_object_list(box, src=src, group=c.group)
+        return box[0]
+
     def draw_gibbs_variates(self):
         """host draws from the global numpy.random stream in the reference's order:
-        every part (per component), then the gating."""
+        every part (per component), then the gating.  Sharded: drawn once, on rank 0."""
         counts = self.counts_host()
         stat_host = E.to_host(self.stat) if self.family == 'diag' else None
-        var = []
-        for p in self.parts:
-            var.append(p.w._draw_variates(counts, stat_host) if self.family == 'diag' else p.w._draw_variates(counts))
-        gvar = self.gating._draw_variates(counts) if self.gating is not None else None
-        return var, gvar
+
+        def draw():
+            var = []
+            for p in self.parts:
+                var.append(p.w._draw_variates(counts, stat_host) if self.family == 'diag' else p.w._draw_variates(counts))
+            gvar = self.gating._draw_variates(counts) if self.gating is not None else None
+            return var, gvar
+        return self.host_draw(draw)
+
+    def label_uniforms(self, rng='numpy'):
+        """one uniform per point for the inverse-CDF label draw (utils/stats.py:14).
+        'numpy': npr.random(size=(1, N)) -- the reference's single RNG call; sharded: rank 0 draws all N_global values
+        and every rank keeps its slice, so the chain equals the single-process chain.
+        'philox': no host variates at all -- returns (None, seed): the kernel draws Philox4x32-10 uniforms keyed by
+        (seed, GLOBAL point index), which is what sizes like N = 1e8 need."""
+        if rng == 'philox':
+            return None, int(self.host_draw(lambda: int(npr.randint(1 << 30))))
+        c = self.comm
+        if c is None or c.world <= 1:
+            return npr.random(size=(1, self.N)), 0
+        n_global = c.N_global if c.N_global is not None else None
+        assert n_global is not None, 'a sharded label draw from host uniforms needs Communicator(N_global=...)'
+        u = self.host_draw(lambda: npr.random(size=(1, n_global)))
+        return u[:, c.point_offset:c.point_offset + self.N], 0
 
 
 def random_responsibilities(K, N):

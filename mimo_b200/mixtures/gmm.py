@@ -221,18 +221,26 @@ class BayesianMixtureOfGaussians:
         return log_prob
 
     # -- Gibbs -------------------------------------------------------------------------------
-    def resample(self, obs, init_labels='prior', maxiter=1, progress_bar=True, process_id=0, comm=None):
+    def resample(self, obs, init_labels='prior', maxiter=1, progress_bar=True, process_id=0, comm=None,
+                 label_rng='numpy'):
         """gmm.py:207-225.  Random variates come from the global numpy.random stream in the
         reference's order (components per k, gating, one uniform per point), so a seeded run
-        reproduces the reference's chain; all arithmetic on them is on the device."""
+        reproduces the reference's chain; all arithmetic on them is on the device.
+        Sharded (comm): rank 0's stream is the chain's stream -- parameter variates and label uniforms are drawn
+        there and broadcast, so an identically seeded 1-rank run gives the same chain.
+        label_rng='philox': label uniforms from the kernel's counter-based generator keyed by the global point
+        index (no N host variates per sweep; not the reference's stream)."""
         s = self._session(obs, comm)
+        lo = comm.point_offset if comm is not None else 0
+        n_glob = comm.N_global if (comm is not None and comm.N_global is not None) else s.N
         if init_labels == 'random':
-            labels = npr.choice(self.size, size=(s.N,))
+            labels = s.host_draw(lambda: npr.choice(self.size, size=(n_glob,)))[lo:lo + s.N]
         elif init_labels == 'prior':
-            labels = self.gating.likelihood.rvs(s.N)
+            labels = s.host_draw(lambda: self.gating.likelihood.rvs(n_glob))[lo:lo + s.N]
         elif init_labels == 'posterior':
             ops = s.operands_from_likelihood(self.likelihood._log_probs())
-            labels = s.sweep(ops, hard=True, uniforms=npr.random(size=(1, s.N))).labels
+            u, seed = s.label_uniforms(label_rng)
+            labels = s.sweep(ops, hard=True, uniforms=u, seed=seed).labels
         if init_labels != 'posterior':
             s.stats_from_labels(labels)
         with tqdm(total=maxiter, desc=f'Init #{process_id + 1}', position=process_id, disable=not progress_bar) as pbar:
@@ -240,7 +248,8 @@ class BayesianMixtureOfGaussians:
                 var, gvar = s.draw_gibbs_variates()
                 ops, outs = s.update_from_stats(GIBBS, variates=var, gating_variates=gvar, want_lik=True)
                 s.check(outs)
-                buf = s.sweep(ops, hard=True, uniforms=npr.random(size=(1, s.N)))
+                u, seed = s.label_uniforms(label_rng)
+                buf = s.sweep(ops, hard=True, uniforms=u, seed=seed)
                 pbar.update(1)
         if maxiter > 0:
             s.store(outs, GIBBS)
@@ -284,11 +293,21 @@ class BayesianMixtureOfGaussians:
         return E.to_host(a).astype(np.float64)
 
     def meanfield_coordinate_descent(self, obs, randomize=True, maxiter=250, tol=1e-8,
-                                     progress_bar=True, process_id=0, comm=None):
+                                     progress_bar=True, process_id=0, comm=None, rtol=0., sample_likelihood=False):
         """gmm.py:261-287.  Per iteration: batched posterior kernels (statistics -> posterior,
-        operands, lower-bound terms), then ONE fused E-step + statistics sweep."""
+        operands, lower-bound terms), then ONE fused E-step + statistics sweep.
+        randomize=True draws the reference's npr.rand(K, N) on the host (seeded runs replay the reference);
+        randomize='device' draws the random responsibilities on the device in point chunks, for N where a (K, N)
+        host array cannot exist.  `obs` may be a resident device tensor (N, d) of the model's precision.
+        tol is the reference's ABSOLUTE early-stop threshold; rtol adds a relative one (|delta| < rtol |vlb|): the
+        FP64 statistics are accumulated with atomics in a run-dependent order, so at N ~ 1e7+ the bound jitters by
+        ~1e-9 relative from sweep to sweep and an absolute 1e-8 can never fire.
+        sample_likelihood=True also performs the reference's per-iteration likelihood.params = posterior.rvs()
+        draws (components, then gating) so the numpy.random stream advances as in the reference."""
         s = self._session(obs, comm)
-        if randomize:
+        if randomize == 'device':
+            s.stats_from_random_resp(seed=s.host_draw(lambda: int(npr.randint(1 << 30))))
+        elif randomize:
             s.stats_from_resp(random_responsibilities(self.size, s.N))
         else:
             s.sweep(s.operands_from_posterior(), hard=False)
@@ -300,7 +319,11 @@ class BayesianMixtureOfGaussians:
                 s.sweep(ops, hard=False)
                 s.check(outs)
                 vlb.append(s.lower_bound(outs))
-                if len(vlb) > 1 and abs(vlb[-1] - vlb[-2]) < tol:
+                if sample_likelihood:
+                    s.store(outs, MEANFIELD, set_probs=False)
+                    self.components.likelihood.params = self.components.posterior.rvs()
+                    self.gating.likelihood.params = self.gating.posterior.rvs()
+                if len(vlb) > 1 and (abs(vlb[-1] - vlb[-2]) < tol or abs(vlb[-1] - vlb[-2]) < rtol * abs(vlb[-1])):
                     break
                 pbar.update(1)
         if outs is not None:

@@ -227,11 +227,13 @@ class BayesianMixtureOfLinearGaussians:
         return E.to_host(a).astype(np.float64)
 
     def meanfield_coordinate_descent(self, x, y, randomize=True, maxiter=250, tol=1e-8,
-                                     progress_bar=True, process_id=0, comm=None):
-        """ilr.py:196-228."""
+                                     progress_bar=True, process_id=0, comm=None, rtol=0.):
+        """ilr.py:196-228.  randomize='device' / rtol: see BayesianMixtureOfGaussians.meanfield_coordinate_descent."""
         xx, yy = self._scaled(x, y)
         s = self._session(xx, yy, comm)
-        if randomize:
+        if randomize == 'device':
+            s.stats_from_random_resp(seed=s.host_draw(lambda: int(npr.randint(1 << 30))))
+        elif randomize:
             s.stats_from_resp(random_responsibilities(self.size, s.N))
         else:
             s.sweep(s.operands_from_posterior(), hard=False)
@@ -243,7 +245,7 @@ class BayesianMixtureOfLinearGaussians:
                 s.sweep(ops, hard=False)
                 s.check(outs)
                 vlb.append(s.lower_bound(outs))
-                if len(vlb) > 1 and abs(vlb[-1] - vlb[-2]) < tol:
+                if len(vlb) > 1 and (abs(vlb[-1] - vlb[-2]) < tol or abs(vlb[-1] - vlb[-2]) < rtol * abs(vlb[-1])):
                     break
                 pbar.update(1)
         if outs is not None:

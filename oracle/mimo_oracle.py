@@ -140,6 +140,18 @@ def gauss_full_wstats(x, w):
     return [xk, nk, xxk, nk]
 
 
+def gauss_full_wstats_blas(x, w):
+    """gauss_full_wstats with the K d x d contractions as K GEMMs (x^T diag(w_k) x): the same sums in another order,
+    for the K = 1024, d = 128 parity cases where einsum's generic path takes minutes.  Pinned to gauss_full_wstats
+    in tests/test_oracle_golden.py."""
+    K, d = w.shape[0], x.shape[1]
+    xxk = np.empty((K, d, d))
+    for k in range(K):
+        xxk[k] = (x * w[k][:, None]).T @ x
+    nk = np.sum(w, axis=1)
+    return [w @ x, nk, xxk, nk]
+
+
 def gauss_diag_wstats(x, w):
     """distributions/gaussian.py:819-832 -> [sum r x, n bcast, n bcast,
     sum r x^2], all (K,d)."""
@@ -230,6 +242,19 @@ def nw_expected_loglik(x, mus, kappas, psis, nus):
     out = E_lm @ x.T
     out += E_mlm[:, None]
     out += np.einsum('kdl,nd,nl->kn', E_l, x, x, optimize=True)
+    out += E_logdet[:, None]
+    return out - 0.5 * d * LOG_2PI
+
+
+def nw_expected_loglik_blas(x, mus, kappas, psis, nus):
+    """nw_expected_loglik with the quadratic term x^T E_l[k] x as one GEMM per component (same contraction, BLAS
+    order); pinned to nw_expected_loglik in tests/test_oracle_golden.py."""
+    d = x.shape[1]
+    E_lm, E_mlm, E_l, E_logdet = nw_expected_statistics(mus, kappas, psis, nus)
+    out = E_lm @ x.T
+    out += E_mlm[:, None]
+    for k in range(mus.shape[0]):
+        out[k] += np.einsum('nd,nd->n', x @ E_l[k], x)
     out += E_logdet[:, None]
     return out - 0.5 * d * LOG_2PI
 

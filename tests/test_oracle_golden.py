@@ -189,3 +189,19 @@ def test_pointwise(name):
     close(st[0], g['st_x'])
     close(st[1], g['st_n'])
     close(st[2], g['st_xx'])
+
+
+def test_blas_variants_equal_the_reference_order_contractions():
+    """the GEMM-ordered helpers used by the K = 1024, d = 128 GPU parity cases are the same functions."""
+    rng = np.random.default_rng(0)
+    K, d, N = 7, 12, 300
+    x = rng.standard_normal((N, d)) * 2 + 1
+    w = rng.dirichlet(np.ones(K), size=N).T
+    for a, b in zip(orc.gauss_full_wstats(x, w), orc.gauss_full_wstats_blas(x, w)):
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
+    mus = rng.standard_normal((K, d))
+    kappas, nus = rng.random(K) + 0.5, d + 2 + 5 * rng.random(K)
+    a = rng.standard_normal((K, d, d + 2))
+    psis = a @ a.transpose(0, 2, 1) / d + 0.1 * np.eye(d)
+    np.testing.assert_allclose(orc.nw_expected_loglik(x, mus, kappas, psis, nus),
+                               orc.nw_expected_loglik_blas(x, mus, kappas, psis, nus), rtol=1e-12, atol=1e-10)
