@@ -539,16 +539,16 @@ def parity_subsample(cx, s, w, n_sub):
     po = outs['parts'][0]
     out['posterior'] = {k: err(po[k], r) for k, r in zip(('m', 'kappa', 'psi', 'nu'), post)}
     # ---- dense kernels: log-joint (K, n), log-normalisers, statistics
-    ll = E.empty((K, n_sub), torch.float32)
+    r_t = E.empty((K, n_sub), torch.float32)            # a soft sweep's (K, n) output is the responsibilities
     lse_t = E.empty((n_sub,), torch.float32)
     old = E.set_tensor_cores(3)
     try:
         buf = E.SweepBuffers(n_sub, K, s.F, 'fp32', False)
-        E.sweep(Zs, ops, s.feats, buf, ll_out=ll, lse_out=lse_t)
-        g_ll = ll.double().cpu().numpy()
+        E.sweep(Zs, ops, s.feats, buf, ll_out=r_t, lse_out=lse_t)
+        g_ll = E.loglik_tc(Zs, ops).double().cpu().numpy()          # the same dense 3-pass E-step kernel, stand-alone
         g_lse = lse_t.double().cpu().numpy()
         out['dense'] = dict(log_joint=err(g_ll, ell), lse=err(g_lse, lse), lse_sum_rel=abs(buf.lse_sum.item() - lse.sum()) / abs(lse.sum()),
-                            resp=float(np.max(np.abs(np.exp(g_ll - g_lse[None]) - resp))), stats=err(buf.stat, ref_packed))
+                            resp=float(np.max(np.abs(r_t.double().cpu().numpy() - resp))), stats=err(buf.stat, ref_packed))
     finally:
         E.set_tensor_cores(old)
     # ---- the default (screened) path: statistics and the lower-bound data term (no (K, n) output on this path)
@@ -750,6 +750,12 @@ def main():
     init_from_env()
     cx = Ctx()
     E = cx.E
+    if os.environ.get('MIMO_TC_TRIANGULAR'):                 # A/B only: rows per step of the triangular skip (0 = kernel off)
+        E.set_triangular(int(os.environ['MIMO_TC_TRIANGULAR']))
+        config['tc_triangular'] = int(os.environ['MIMO_TC_TRIANGULAR'])
+    if os.environ.get('MIMO_TC_FLUSH_TILES'):                # A/B only: 128-point tiles between FP64 drains of the statistics
+        E._lib.load().mimo_tc_set_flush_tiles(int(os.environ['MIMO_TC_FLUSH_TILES']))
+        config['tc_flush_tiles'] = int(os.environ['MIMO_TC_FLUSH_TILES'])
     if world == 1:
         torch.cuda.set_device(0)
     cx.dev = dev = torch.device('cuda', torch.cuda.current_device())

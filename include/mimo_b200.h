@@ -117,6 +117,19 @@ int mimo_tc_screen_totals(uint64_t* out_host5);
 /* screening tier the most recent screened sweep ended on: 0 projection, 1 all operand rows, 2 none (dense); -1 unknown */
 int mimo_tc_screen_level(void);
 int mimo_sweep_uses_tensor_cores(int dtype, int family, int D, int Rp);
+/* Diagonal family on the tensor pipe (FP32, D <= 64, K <= 256): the log-density is linear in [z', z'^2] of the centred
+ * point, i.e. one tcgen05 GEMM; labels (inverse CDF of `uniforms`, or Philox(seed, point_offset + n) when NULL) and the
+ * log-normalisers come out of its epilogue.  Replaces distributions/gaussian.py:837-850, bayesian.py:446-460 and
+ * mixtures/gmm.py:72-75 on that shape; mimo_sweep uses it by itself.  out / labels / lse / lse_sum are optional.
+ * *guard_host (optional, synchronises) = 1 when the operands failed the cancellation guard and NOTHING was computed
+ * (mimo_sweep then runs the CUDA-core kernels on the device's own decision). */
+size_t mimo_loglik_diag_tc_workspace(void);
+int mimo_loglik_diag_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* S, const void* T, const void* cst, int K,
+                        void* out, int64_t ldo, int32_t* labels, const void* uniforms, uint64_t seed, uint64_t point_offset,
+                        void* lse, double* lse_sum, uint32_t* guard_host, void* workspace, size_t workspace_bytes, void* stream);
+int mimo_tc_diag_enable(int on);            /* A/B: 0 keeps diagonal sweeps on the CUDA cores; returns the old setting */
+int mimo_tc_set_min_dim(int d);             /* A/B: smallest D a quad-family sweep takes to the tensor pipe (default 8; 24 = round-1 behaviour); returns the old value */
+int mimo_tc_set_triangular(int rows);       /* dense E-step, 64 < D <= 128: rows per step of the triangular skip (16 default, 32; 0 = kernel with both operands in shared memory); returns the old value */
 int mimo_tc_set_flush_tiles(int tiles);     /* 128-point tiles accumulated in TMEM (FP32) between FP64 drains */
 size_t mimo_loglik_quad_tc_workspace(int K, int Rp, int D);
 int mimo_loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz,

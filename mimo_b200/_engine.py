@@ -190,6 +190,26 @@ def loglik(Z, ops, out=None):
     return out
 
 
+def loglik_diag_tc(Z, ops, out=False, labels=False, lse=False, lse_sum=False, uniforms=None, seed=0, offset=0):
+    """Diagonal family on the tensor pipe (FP32, D <= 64, K <= 256): log-joints, labels and log-normalisers of the points
+    of Z in one kernel.  Returns a dict; 'guard' = 1 means the operands failed the cancellation guard and nothing was
+    computed (a sweep then takes the CUDA-core kernels)."""
+    N, D = Z.shape
+    assert ops.family == 1 and D == ops.D and Z.dtype == torch.float32 and ops.precision == 'fp32'
+    out_t = empty((ops.K, N), torch.float32) if out else None
+    lab_t = empty((N,), torch.int32) if labels else None
+    lse_t = empty((N,), torch.float32) if lse else None
+    sum_t = zeros((1,), torch.float64) if lse_sum else None
+    uni_t = to_dev(uniforms, torch.float64).reshape(-1) if uniforms is not None else None
+    wsb = _lib.load().mimo_loglik_diag_tc_workspace()
+    ws = workspace(wsb)
+    guard = np.zeros(1, dtype=np.uint32)
+    _lib.call('mimo_loglik_diag_tc', ptr(Z), N, D, Z.stride(0), ptr(ops.S), ptr(ops.T), ptr(ops.cst), ops.K,
+              ptr(out_t), out_t.stride(0) if out else 0, ptr(lab_t), ptr(uni_t), int(seed), int(offset),
+              ptr(lse_t), ptr(sum_t), guard.ctypes.data, ptr(ws), wsb, stream())
+    return dict(out=out_t, labels=lab_t, lse=lse_t, lse_sum=sum_t, guard=int(guard[0]))
+
+
 def softmax(a, precision, resp=False, lse=False, labels=False, lse_sum=False, uniforms=None, seed=0, offset=0):
     """In-place softmax / label draw over a (K, n) log-joint.  Returns a dict."""
     K, n = a.shape
@@ -460,6 +480,17 @@ def set_tensor_cores(mode):
     2: single-CTA dense tcgen05 kernels; 3: CTA pairs, dense E-step; 4: as 1 with dense statistics;
     5: as 1 with the screening starting on its all-rows tier.  Returns the old mode."""
     return _lib.load().mimo_set_tensor_cores(int(mode))
+
+
+def set_tc_min_dim(d):
+    """Smallest dimension a quad-family sweep takes to the tensor pipe (default 8).  Returns the old value."""
+    return _lib.load().mimo_tc_set_min_dim(int(d))
+
+
+def set_triangular(rows):
+    """Dense E-step for 64 < D <= 128: rows per step of the triangular skip of tc_estep3.cu (16 or 32; 0 = the kernel
+    with both operands in shared memory).  Returns the old value."""
+    return _lib.load().mimo_tc_set_triangular(int(rows))
 
 
 def screen_last():

@@ -55,6 +55,27 @@ int mimo_loglik_diag(int dtype, const void* Z, int64_t N, int D, int64_t ldz, co
                      const void* cst, int K, void* out, int64_t ldo, void* stream) {
     return loglik_diag(dtype, Z, N, D, ldz, S, T, cst, K, out, ldo, ST(stream));
 }
+size_t mimo_loglik_diag_tc_workspace(void) { return tc_diag_workspace(); }
+int mimo_loglik_diag_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* S, const void* T, const void* cst, int K,
+                        void* out, int64_t ldo, int32_t* labels, const void* uniforms, uint64_t seed, uint64_t point_offset,
+                        void* lse, double* lse_sum, uint32_t* guard_host, void* workspace, size_t workspace_bytes, void* stream) {
+    MIMO_CHECK_ARG(Z && S && T && cst && workspace, "null pointer");
+    MIMO_CHECK_ARG(N >= 0 && ldz >= D && (!out || ldo >= N), "shape");
+    if (!tc_diag_supported(MIMO_F32, D, K)) { set_error("tensor-core diagonal E-step: unsupported shape D=%d K=%d", D, K); return MIMO_EUNSUPPORTED; }
+    MIMO_CHECK_ARG(workspace_bytes >= tc_diag_workspace(), "workspace too small");
+    int rc = tc_diag_prepare((const float*)Z, N, D, ldz, (const float*)S, (const float*)T, (const float*)cst, K, workspace, ST(stream));
+    if (rc) return rc;
+    rc = tc_diag_chunk((const float*)Z, N, D, ldz, K, (float*)out, ldo, labels, (const double*)uniforms, seed, point_offset,
+                       (float*)lse, lse_sum, workspace, ST(stream));
+    if (rc) return rc;
+    if (guard_host) {
+        MIMO_CUDA(cudaMemcpyAsync(guard_host, tc_diag_gate(workspace), 4, cudaMemcpyDeviceToHost, ST(stream)));
+        MIMO_CUDA(cudaStreamSynchronize(ST(stream)));
+    }
+    return MIMO_OK;
+}
+int mimo_tc_diag_enable(int on) { return tc_diag_enable(on); }
+int mimo_tc_set_min_dim(int d) { return tc_set_min_dim(d); }
 int mimo_softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags, void* lse, const void* uniforms,
                  uint64_t seed, uint64_t point_offset, int32_t* labels, double* lse_sum, void* stream) {
     return softmax(dtype, a, K, n, ldo, flags, lse, uniforms, seed, point_offset, labels, lse_sum, ST(stream));
@@ -76,6 +97,7 @@ int mimo_set_tensor_cores(int mode) { return tc_set_mode(mode); }
 int mimo_tc_screen_last(uint32_t* out_host2) { return tc_screen_last(out_host2); }
 int mimo_tc_screen_totals(uint64_t* out_host5) { return tc_screen_totals((unsigned long long*)out_host5); }
 int mimo_sweep_uses_tensor_cores(int dtype, int family, int D, int Rp) { return sweep_uses_tc(dtype, family, D, Rp) ? 1 : 0; }
+int mimo_tc_set_triangular(int rows) { return tc3_set_granularity(rows); }
 int mimo_tc_set_flush_tiles(int tiles) { tc_set_flush_tiles(tiles); tc_fstats_set_flush_tiles(tiles); return MIMO_OK; }
 size_t mimo_loglik_quad_tc_workspace(int K, int Rp, int D) { return tc_operand_workspace(K, Rp, D); }
 int mimo_loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* W, const void* cst,

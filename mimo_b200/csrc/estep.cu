@@ -163,7 +163,8 @@ template <typename T>
 __global__ void __launch_bounds__(DIAG_THREADS)
 diag_loglik_kernel(const T* __restrict__ Z, int64_t N, int D, int64_t ldz,
                    const T* __restrict__ S, const T* __restrict__ Tm, const T* __restrict__ cst, int K,
-                   T* __restrict__ out, int64_t ldo) {
+                   T* __restrict__ out, int64_t ldo, const unsigned int* __restrict__ gate, unsigned int gate_value) {
+    if (gate != nullptr && *gate != gate_value) return;      // the tensor-core kernel of tc_diag.cu ran instead
     constexpr int ZS = DIAG_BM + QUAD_PAD;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* Zs = reinterpret_cast<T*>(smem_raw);              // [D][ZS]
@@ -295,25 +296,25 @@ int loglik_quad(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const v
 
 template <typename T>
 static int launch_diag(const void* Z, int64_t N, int D, int64_t ldz, const void* S, const void* Tm, const void* cst,
-                       int K, void* out, int64_t ldo, cudaStream_t st) {
+                       int K, void* out, int64_t ldo, cudaStream_t st, const unsigned int* gate, unsigned int gate_value) {
     size_t smem = ((size_t)D * (DIAG_BM + QUAD_PAD) + (size_t)DIAG_KC * D * 2) * sizeof(T);
     if (smem > 227 * 1024) { set_error("diag E-step: D=%d needs %zu B of shared memory", D, smem); return MIMO_EUNSUPPORTED; }
     auto kern = diag_loglik_kernel<T>;
     MIMO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<cdiv(N, DIAG_BM), DIAG_THREADS, smem, st>>>((const T*)Z, N, D, ldz, (const T*)S, (const T*)Tm,
-                                                        (const T*)cst, K, (T*)out, ldo);
+                                                        (const T*)cst, K, (T*)out, ldo, gate, gate_value);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
 
 int loglik_diag(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const void* S, const void* Tm,
-                const void* cst, int K, void* out, int64_t ldo, cudaStream_t st) {
+                const void* cst, int K, void* out, int64_t ldo, cudaStream_t st, const unsigned int* gate, unsigned int gate_value) {
     MIMO_CHECK_ARG(dtype == MIMO_F32 || dtype == MIMO_F64, "dtype");
     MIMO_CHECK_ARG(Z && S && Tm && cst && out, "null pointer");
     MIMO_CHECK_ARG(N >= 0 && D >= 1 && K >= 1 && ldz >= D && ldo >= N, "shape");
     if (N == 0) return MIMO_OK;
-    if (dtype == MIMO_F32) return launch_diag<float>(Z, N, D, ldz, S, Tm, cst, K, out, ldo, st);
-    return launch_diag<double>(Z, N, D, ldz, S, Tm, cst, K, out, ldo, st);
+    if (dtype == MIMO_F32) return launch_diag<float>(Z, N, D, ldz, S, Tm, cst, K, out, ldo, st, gate, gate_value);
+    return launch_diag<double>(Z, N, D, ldz, S, Tm, cst, K, out, ldo, st, gate, gate_value);
 }
 
 int softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags, void* lse, const void* uniforms,

@@ -9,7 +9,18 @@ namespace mimo {
 int loglik_quad(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const void* W, const void* cst,
                 int K, int Rp, int Dpp, void* out, int64_t ldo, cudaStream_t st);
 int loglik_diag(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const void* S, const void* Tm,
-                const void* cst, int K, void* out, int64_t ldo, cudaStream_t st);
+                const void* cst, int K, void* out, int64_t ldo, cudaStream_t st,
+                const unsigned int* gate = nullptr, unsigned int gate_value = 0u);
+// diagonal family on the tensor pipe (tc_diag.cu): FP32, D <= 64, K <= 256; E-step as one feature GEMM, fused label draw
+bool tc_diag_supported(int dtype, int D, int K);
+int tc_diag_enable(int on);
+size_t tc_diag_workspace();
+const unsigned int* tc_diag_gate(void* ws);      // 1: the operands failed the cancellation guard, the CUDA-core kernels must run
+int tc_diag_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float* S, const float* T, const float* cst, int K,
+                    void* ws, cudaStream_t st);
+int tc_diag_chunk(const float* Z, int64_t N, int D, int64_t ldz, int K, float* out, int64_t ldo,
+                  int32_t* labels, const double* uniforms, uint64_t seed, uint64_t point_offset,
+                  float* lse_out, double* lse_sum, void* ws, cudaStream_t st);
 int softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags, void* lse, const void* uniforms,
             uint64_t seed, uint64_t point_offset, int32_t* labels, double* lse_sum, cudaStream_t st,
             const unsigned int* gate = nullptr, unsigned int gate_value = 0u);
@@ -25,6 +36,7 @@ int stats_hard(int dtype, const void* Z, int64_t N, int D, int64_t ldz, const in
 // tensor-core (tcgen05) path, FP32 quad family, D <= 128  (tc_estep.cu, tc_stats.cu)
 int tc_mode();                       // 0 CUDA cores only; 1 tensor cores: CTA pairs + screened E-step + pair-list statistics (default); 2 single-CTA dense; 3 CTA pairs dense; 4 as 1 with dense statistics; 5 as 1, screening starts on the all-rows tier
 int tc_set_mode(int mode);
+int tc_set_min_dim(int d);
 bool tc_estep_supported(int dtype, int D, int Rp);
 size_t tc_operand_workspace(int K, int Rp, int D);
 int tc_data_scale(const float* Z, int64_t N, int D, int64_t ldz, void* ws, cudaStream_t st);
@@ -32,7 +44,8 @@ const unsigned int* tc_maxbits(void* ws);
 int tc_prepare_operands(const float* W, const float* cst, int K, int Rp, int Dpp, int D, void* ws, cudaStream_t st);
 unsigned int* tc_flags(void* ws);    // [0] max |z| bits, [2] max_k ||W'_k||_F (screening operands), [3] max_n ||z_n||_2, [4] max_k ||W_k||_F (all columns)
 int tc_estep_pass(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, float* out, int64_t ldo, void* ws,
-                  int passes, const unsigned int* gate, unsigned int gate_value, float* lower, int* guess, int64_t ldl, cudaStream_t st);
+                  int passes, const unsigned int* gate, unsigned int gate_value, float* lower, int* guess, int64_t ldl, cudaStream_t st,
+                  float* lse_vals = nullptr, double* lse_sum = nullptr);
 // screened E-step (tc_screen.cu): projected single-pass screening + exact refinement of the candidates / gated dense pass
 bool tc_screen_supported(int D, int Rp);
 size_t tc_screen_workspace(int64_t chunk_points, int K);
@@ -55,14 +68,24 @@ int tc_screen_refine(const float* Z, int D, int64_t ldz, const float* W, int K, 
 int tc_screen_lse(const float* a, int K, int64_t n, int64_t ldo, double* lse_sum, int64_t plan_points, void* ws, cudaStream_t st);
 const float* tc_screen_lse_values(void* ws, int64_t plan_points, int K);
 void tc_screen_lists(void* ws, int64_t plan_points, int K, int which, const int32_t** perm, const int32_t** offsets, const int32_t** slabs);
+// lse_vals / lse_sum (optional, CTA-pair kernel): per-point log-normalisers of the log-joints written to `out`, and their sum
 int tc_estep(const float* Z, int64_t N, int D, int64_t ldz, const float* cst, int K, int Rp,
-             float* out, int64_t ldo, void* ws, cudaStream_t st);
+             float* out, int64_t ldo, void* ws, cudaStream_t st, float* lse_vals = nullptr, double* lse_sum = nullptr);
 // CTA-pair (cta_group::2) E-step, tc_estep2.cu
 size_t tc2_offsets_bytes(int K, int Rp);
-int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cst, int K, int Rp, float* offs2, cudaStream_t st);
+bool tc2_triangular(int KB, int Rp);      // operand image / accumulator columns in the triangular layout of tc_estep2.cu
+int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cst, int K, int Rp, int KB, float* offs2, cudaStream_t st);
 int tc_estep2(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, int KB, const void* Bimg, const float* offs2,
               const unsigned int* maxbits, float* out, int64_t ldo, int passes, const unsigned int* gate, unsigned int gate_value,
-              float* lower, int* guess, int64_t ldl, cudaStream_t st);
+              float* lower, int* guess, int64_t ldl, cudaStream_t st, float* lse_vals = nullptr, double* lse_sum = nullptr);
+// CTA-pair E-step with the points operand in tensor memory + triangular skip (tc_estep3.cu): 64 < D <= 128, Rp = 128
+bool tc3_supported(int D, int Rp);
+int tc3_set_granularity(int g);      // rows per step of the triangular skip: 16 (default) or 32; 0 turns the kernel off
+size_t tc3_workspace(int K);
+int tc3_prepare(const float* W, const float* cst, int K, int Dpp, int D, unsigned int* flags, void* ws3, cudaStream_t st);
+int tc_estep3(const float* Z, int64_t N, int D, int64_t ldz, int K, const void* ws3, const unsigned int* flags,
+              float* out, int64_t ldo, const unsigned int* gate, unsigned int gate_value,
+              float* lse_vals, double* lse_sum, cudaStream_t st);
 int loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* W, const void* cst,
                    int K, int Rp, int Dpp, void* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st);
 bool tc_stats_supported(int dtype, int D, int F);
@@ -70,7 +93,7 @@ size_t tc_stats_workspace(int64_t chunk_points, int K);
 int tc_stats_begin(int64_t chunk_points, int K, void* ws, cudaStream_t st);
 int tc_stats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, int K, int F,
                    const unsigned int* maxbits, double* stat, int64_t plan_points, void* ws, cudaStream_t st,
-                   const unsigned int* gate = nullptr, unsigned int gate_value = 0u);
+                   const unsigned int* gate = nullptr, unsigned int gate_value = 0u, const float* lse = nullptr);
 int tc_stats_end(int64_t plan_points, int K, int D, int F, const unsigned int* maxbits, double* stat, void* ws, cudaStream_t st);
 void tc_set_flush_tiles(int tiles);
 // feature-form statistics (tc_fstats.cu): folded lower triangle, 64 < D <= 128
@@ -79,9 +102,15 @@ size_t tc_fstats_workspace(int64_t chunk_points, int K);
 int tc_fstats_begin(int64_t chunk_points, int K, void* ws, cudaStream_t st);
 int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, int K,
                     const unsigned int* maxbits, int64_t plan_points, void* ws, cudaStream_t st,
-                    const unsigned int* gate = nullptr, unsigned int gate_value = 0u);
+                    const unsigned int* gate = nullptr, unsigned int gate_value = 0u, const float* lse = nullptr);
 int tc_fstats_end(int64_t plan_points, int K, int D, int F, const unsigned int* maxbits, double* stat, void* ws, cudaStream_t st);
 void tc_fstats_set_flush_tiles(int tiles);
+// feature-form statistics for small dimensions (tc_sstats.cu): D <= 21, accumulates straight into stat (K, F)
+bool tc_sstats_supported(int dtype, int D, int F);
+int tc_sstats_enable(int on);
+int tc_sstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, const float* lse, int K, int F,
+                    const unsigned int* maxbits, double* stat, cudaStream_t st,
+                    const unsigned int* gate = nullptr, unsigned int gate_value = 0u);
 size_t stats_soft_tc_workspace(int64_t N, int K);
 int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K, int F,
                   double* stat, void* ws, size_t ws_bytes, cudaStream_t st);

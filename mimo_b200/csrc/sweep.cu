@@ -18,10 +18,13 @@ static int g_tc_mode = 1;
 int tc_mode() { return g_tc_mode; }
 int tc_set_mode(int mode) { int old = g_tc_mode; g_tc_mode = (mode < 0 || mode > 5) ? 1 : mode; return old; }
 
-// the tensor-core path takes FP32 quad-family sweeps whose contraction is wide enough to pay for
-// the 64-wide K blocks of the operand layout
+// the tensor-core path takes FP32 quad-family sweeps from D = 8 up: below D = 24 the E-step is bound by the read-back of
+// its K * Rp accumulator columns per point (one 16-wide K step feeds 256 columns) and the statistics run in feature form
+// (tc_sstats.cu); from D = 24 the contraction is wide enough for the per-component / folded-triangle statistics kernels
+static int g_tc_min_d = 8;
+int tc_set_min_dim(int d) { int old = g_tc_min_d; g_tc_min_d = d < 1 ? 1 : d; return old; }
 bool sweep_uses_tc(int dtype, int family, int D, int Rp) {
-    return g_tc_mode && family == 0 && D >= 24 && tc_estep_supported(dtype, D, Rp);
+    return g_tc_mode && family == 0 && D >= g_tc_min_d && tc_estep_supported(dtype, D, Rp);
 }
 // screened E-step: worth it when a point's candidates (>= 1) can stay below 4 % of the K components
 static bool sweep_uses_screen(int dtype, int family, int D, int K, int Rp) {
@@ -65,11 +68,16 @@ static int tables_canonical(const int32_t* fi, const int32_t* fj, int F, int D, 
     return MIMO_OK;
 }
 
+// diagonal family on the tensor pipe (tc_diag.cu)
+static bool sweep_uses_diag_tc(int dtype, int family, int D, int K) {
+    return g_tc_mode && family == 1 && tc_diag_supported(dtype, D, K);
+}
+
 int64_t sweep_chunk_points(int dtype, int family, int64_t N, int D, int K, int Rp) {
     size_t es = dtype == MIMO_F32 ? 4 : 8;
     int64_t npad = (N + 255) / 256 * 256;
     if (npad <= 0) npad = 256;
-    if (sweep_uses_tc(dtype, family, D, Rp)) {
+    if (sweep_uses_tc(dtype, family, D, Rp) || sweep_uses_diag_tc(dtype, family, D, K)) {
         const int64_t wave = (int64_t)256 * sm_count();
         int64_t c = (int64_t)(((size_t)4 << 30) / ((size_t)K * es));
         c = c / wave * wave;
@@ -90,10 +98,14 @@ size_t sweep_workspace(int dtype, int family, int hard, int64_t N, int D, int K,
     // Gibbs: labels of ALL points (when the caller does not keep them) + one counting sort over N
     if (hard) b += a256((size_t)N * 4) + a256(stats_hard_workspace(N, K));
     if (sweep_uses_resp_list(dtype, family, hard, D, K, Rp)) b += a256(resp_list_workspace(c, K));
+    if (sweep_uses_diag_tc(dtype, family, D, K)) b += a256(tc_diag_workspace());
     if (sweep_uses_tc(dtype, family, D, Rp)) {
         b += a256(tc_operand_workspace(K, Rp, D));
         if (sweep_uses_screen(dtype, family, D, K, Rp)) b += a256(tc_screen_workspace(c, K)) + a256(tc_screen_operand_workspace(K, Rp, D + 4, D));
-        if (!hard) b += a256(std::max(tc_stats_workspace(c, K), tc_fstats_workspace(c, K)));
+        if (!hard) {                                                    // log-normalisers of a chunk + statistics partials
+            b += a256((size_t)c * 4);
+            if (!tc_sstats_supported(dtype, D, (D + 1) * (D + 2) / 2)) b += a256(std::max(tc_stats_workspace(c, K), tc_fstats_workspace(c, K)));
+        }
     }
     return b;
 }
@@ -129,6 +141,16 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     }
     const bool resp_list = stat && canon && sweep_uses_resp_list(dtype, family, hard, D, K, Rp) && pair_stats_supported(dtype, D, F);
     if (sweep_uses_resp_list(dtype, family, hard, D, K, Rp)) { resp_ws = ws; ws += a256(resp_list_workspace(C, K)); }
+    // diagonal family: E-step (+ label draw of a Gibbs sweep) on the tensor pipe; the CUDA-core kernels stay behind a
+    // device-side gate for operands that fail the cancellation guard
+    const bool diag_tc = sweep_uses_diag_tc(dtype, family, D, K);
+    const bool diag_fused = diag_tc && hard && !ll_out;          // labels and log-normalisers out of the kernel's epilogue
+    void* diag_ws = nullptr;
+    if (diag_tc) {
+        diag_ws = ws; ws += a256(tc_diag_workspace());
+        int rc = tc_diag_prepare((const float*)Z, N, D, ldz, (const float*)op_a, (const float*)op_b, (const float*)cst, K, diag_ws, st);
+        if (rc) return rc;
+    }
     void* tc_ops_ws = nullptr;
     void* tc_stat_ws = nullptr;
     void* screen_ws = nullptr;
@@ -138,16 +160,23 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     // the packed full-triangle statistics are what the tensor-core statistics kernel produces
     const bool tc_stats = use_tc && stat && !hard && canon && tc_stats_supported(dtype, D, F);
     const bool tc_fstats = tc_stats && tc_fstats_supported(dtype, D, F);     // feature form (folded triangle) for D > 64
+    const bool tc_sstats = tc_stats && tc_sstats_supported(dtype, D, F);     // feature form, whole triangle in one accumulator, D <= 21
     const bool pair_stats_list = tc_stats && use_screen && g_tc_mode != 4 && pair_stats_supported(dtype, D, F);
     // ... and the log-normalisers too: no pass over the (K, chunk) scratch after the refinement on such chunks
     const bool list_softmax = pair_stats_list && !lse_out;
+    // dense tensor-core chunks: the E-step kernel forms the log-normalisers itself (online log-sum-exp in its epilogue) and
+    // the statistics pre-pass takes r = exp(a - lse_n) from the log-joints -- no softmax pass over the (K, chunk) scratch.
+    // Not when the caller wants the (K, N) responsibilities, labels, or the screened path's refined scratch is normalised
+    // by the softmax kernel.
+    const bool fused_lse = use_tc && !hard && !ll_out && (!stat || tc_stats) && (!use_screen || list_softmax);
+    float* lse_chunk = nullptr;
     if (use_tc) {
         tc_ops_ws = ws; ws += a256(tc_operand_workspace(K, Rp, D));
         if (sweep_uses_screen(dtype, family, D, K, Rp)) {
             screen_ws = ws; ws += a256(tc_screen_workspace(C, K));
             screen_ops_ws = ws; ws += a256(tc_screen_operand_workspace(K, Rp, D + 4, D));
         }
-        if (!hard) tc_stat_ws = ws;
+        if (!hard) { lse_chunk = (float*)ws; ws += a256((size_t)C * 4); tc_stat_ws = ws; }
         int rc = tc_data_scale((const float*)Z, N, D, ldz, tc_ops_ws, st);
         if (rc) return rc;
         rc = tc_prepare_operands((const float*)op_a, (const float*)cst, K, Rp, Dpp, D, tc_ops_ws, st);
@@ -158,7 +187,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             rc = tc_screen_begin(C, K, Rp, g_tc_mode == 5 ? 1 : 0, screen_ws, st);
             if (rc) return rc;
         }
-        if (tc_stats) { rc = tc_fstats ? tc_fstats_begin(C, K, tc_stat_ws, st) : tc_stats_begin(C, K, tc_stat_ws, st); if (rc) return rc; }
+        if (tc_stats && !tc_sstats) { rc = tc_fstats ? tc_fstats_begin(C, K, tc_stat_ws, st) : tc_stats_begin(C, K, tc_stat_ws, st); if (rc) return rc; }
     }
 
     // optional per-phase device timing (bench.py's roofline leg): events on the launching stream
@@ -179,12 +208,22 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             rc = tc_screen_select((const float*)Zc, D, ldz, (const float*)op_a, (const float*)cst, K, Rp, Dpp, (float*)scratch, nc, C,
                                   tc_ops_ws, screen_ops_ws, C, screen_ws, st);
             if (rc) return rc;
-            rc = tc_estep_pass((const float*)Zc, nc, D, ldz, K, Rp, (float*)scratch, C, tc_ops_ws, 3, tc_screen_gate(screen_ws, C, K), 1u, nullptr, nullptr, 0, st);
+            rc = tc_estep_pass((const float*)Zc, nc, D, ldz, K, Rp, (float*)scratch, C, tc_ops_ws, 3, tc_screen_gate(screen_ws, C, K), 1u, nullptr, nullptr, 0, st,
+                               fused_lse ? lse_chunk : nullptr, fused_lse ? lse_sum : nullptr);
             if (rc) return rc;
             rc = tc_screen_refine((const float*)Zc, D, ldz, (const float*)op_a, K, Rp, Dpp, (const float*)cst, (float*)scratch, C, C, screen_ws, st);
         }
-        else if (use_tc)      rc = tc_estep((const float*)Zc, nc, D, ldz, (const float*)cst, K, Rp, (float*)scratch, C, tc_ops_ws, st);
+        else if (use_tc)      rc = tc_estep((const float*)Zc, nc, D, ldz, (const float*)cst, K, Rp, (float*)scratch, C, tc_ops_ws, st,
+                                            fused_lse ? (lse_out ? (float*)lse_out + n0 : lse_chunk) : nullptr, fused_lse ? lse_sum : nullptr);
         else if (family == 0) rc = loglik_quad(dtype, Zc, nc, D, ldz, op_a, cst, K, Rp, Dpp, scratch, C, st);
+        else if (diag_tc) {
+            rc = tc_diag_chunk((const float*)Zc, nc, D, ldz, K, diag_fused ? nullptr : (float*)scratch, C,
+                               diag_fused ? lab_all + n0 : nullptr, uniforms ? (const double*)uniforms + n0 : nullptr, seed,
+                               point_offset + (uint64_t)n0, (diag_fused && lse_out) ? (float*)lse_out + n0 : nullptr,
+                               diag_fused ? lse_sum : nullptr, diag_ws, st);
+            if (rc) return rc;
+            rc = loglik_diag(dtype, Zc, nc, D, ldz, op_a, op_b, cst, K, scratch, C, st, tc_diag_gate(diag_ws), 1u);
+        }
         else             rc = loglik_diag(dtype, Zc, nc, D, ldz, op_a, op_b, cst, K, scratch, C, st);
         if (rc) return rc;
         mark();
@@ -197,9 +236,12 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             rc = tc_screen_lse((const float*)scratch, K, nc, C, lse_sum, C, screen_ws, st);
             if (rc) return rc;
         }
-        rc = softmax(dtype, scratch, K, nc, C, flags, lse_c, uni, seed, point_offset + (uint64_t)n0, lab, lse_sum, st,
-                     list_softmax ? tc_screen_gate(screen_ws, C, K) : nullptr, 1u);
-        if (rc) return rc;
+        if (!fused_lse) {
+            rc = softmax(dtype, scratch, K, nc, C, flags, lse_c, uni, seed, point_offset + (uint64_t)n0, lab, lse_sum, st,
+                         list_softmax ? tc_screen_gate(screen_ws, C, K) : (diag_fused ? tc_diag_gate(diag_ws) : nullptr), 1u);
+            if (rc) return rc;
+        }
+        const float* lse_f = fused_lse ? (lse_out ? (const float*)lse_out + n0 : lse_chunk) : nullptr;   // scratch holds log-joints
         mark();
         if (ll_out)
             MIMO_CUDA(cudaMemcpy2DAsync((char*)ll_out + (size_t)n0 * es, (size_t)ldo * es, scratch, (size_t)C * es,
@@ -217,8 +259,9 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
                     if (rc) return rc;
                 }
             }
-            rc = tc_fstats ? tc_fstats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, tc_maxbits(tc_ops_ws), C, tc_stat_ws, st, sgate, 1u)
-                           : tc_stats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, F, tc_maxbits(tc_ops_ws), stat, C, tc_stat_ws, st, sgate, 1u);
+            rc = tc_sstats ? tc_sstats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, lse_f, K, F, tc_maxbits(tc_ops_ws), stat, st, sgate, 1u)
+               : tc_fstats ? tc_fstats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, tc_maxbits(tc_ops_ws), C, tc_stat_ws, st, sgate, 1u, lse_f)
+                           : tc_stats_chunk((const float*)Zc, nc, D, ldz, (const float*)scratch, C, K, F, tc_maxbits(tc_ops_ws), stat, C, tc_stat_ws, st, sgate, 1u, lse_f);
             if (rc) return rc;
         } else if (stat && !hard) {
             const unsigned int* rgate = nullptr;
@@ -236,7 +279,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
         }
         mark();
     }
-    if (tc_stats) {
+    if (tc_stats && !tc_sstats) {
         int rc = tc_fstats ? tc_fstats_end(C, K, D, F, tc_maxbits(tc_ops_ws), stat, tc_stat_ws, st)
                            : tc_stats_end(C, K, D, F, tc_maxbits(tc_ops_ws), stat, tc_stat_ws, st);
         if (rc) return rc;
@@ -421,6 +464,8 @@ int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp
     int rc = tc_data_scale((const float*)Z, N, D, ldz, ws, st);
     if (rc) return rc;
     void* pws = (char*)ws + 2048;
+    if (tc_sstats_supported(MIMO_F32, D, F))
+        return tc_sstats_chunk((const float*)Z, N, D, ldz, (const float*)resp, ldr, nullptr, K, F, tc_maxbits(ws), stat, st);
     if (tc_fstats_supported(MIMO_F32, D, F)) {
         rc = tc_fstats_begin(N, K, pws, st);
         if (rc) return rc;

@@ -195,6 +195,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// ---- exp on the SFU: one FMUL + one MUFU.EX2 (ftz: results below 2^-126 flush to zero, which is what a softmax wants).
+//      __expf without -ftz=true wraps the same MUFU in a denormal-range fix-up (FSETP + 2 predicated FMUL per call). ----
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_exp(float x) { return ex2_ftz(x * 1.4426950408889634f); }
+
 // ---- 3 x FP16 split ------------------------------------------------------------------------
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);

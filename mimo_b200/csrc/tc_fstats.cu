@@ -145,7 +145,7 @@ tc_fstats_zimg_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz
 // responsibilities: one CTA per (64-point block, component block); thread = (component row, 32-point half).
 // rimg block (cb, kblock) = [hi|lo][128 components][64 points] at ((cb * nkb_cap + kblock) * TF_PAIR).
 __global__ void __launch_bounds__(256)
-tc_fstats_rimg_kernel(const float* __restrict__ R, int64_t N, int64_t ldr, int K, int rvec4, int64_t nkb_cap,
+tc_fstats_rimg_kernel(const float* __restrict__ R, const float* __restrict__ lse, int64_t N, int64_t ldr, int K, int rvec4, int64_t nkb_cap,
                       unsigned char* __restrict__ rimg, const unsigned int* __restrict__ gate, unsigned int gate_value) {
     if (gate != nullptr && __ldg(gate) != gate_value) return;
     const int ca = threadIdx.x >> 1, hh = threadIdx.x & 1;
@@ -163,6 +163,10 @@ tc_fstats_rimg_kernel(const float* __restrict__ R, int64_t N, int64_t ldr, int K
     } else {
 #pragma unroll
         for (int p = 0; p < 32; ++p) rn[p] = (kok && nb + p < N) ? __ldg(src + p) : 0.f;
+    }
+    if (lse != nullptr) {                  // R holds log-joints (fused log-normaliser of tc_estep2.cu): r = exp(a - lse_n)
+#pragma unroll
+        for (int p = 0; p < 32; ++p) rn[p] = (kok && nb + p < N) ? fast_exp(rn[p] - __ldg(lse + nb + p)) : 0.f;
     }
     unsigned char* blk = rimg + ((size_t)cb * nkb_cap + blockIdx.x) * TF_PAIR;
 #pragma unroll
@@ -498,7 +502,7 @@ void tc_fstats_set_flush_tiles(int t) { g_flush_tiles_f = t < 1 ? 1 : t; }
 // one chunk of N <= plan_points points: operand images, then the GEMM; accumulates into the partial buffer
 int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, int K,
                     const unsigned int* maxbits, int64_t plan_points, void* ws, cudaStream_t st,
-                    const unsigned int* gate, unsigned int gate_value) {
+                    const unsigned int* gate, unsigned int gate_value, const float* lse) {
     if (N == 0) return MIMO_OK;
     TfLayout L = tf_layout(plan_points, K);
     char* base = align1k(ws);
@@ -510,7 +514,7 @@ int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* 
     const int rvec4 = (ldr % 4 == 0) && (((uintptr_t)R & 15) == 0);
     tc_fstats_zimg_kernel<<<(unsigned)blocks, 256, 0, st>>>(Z, N, D, ldz, maxbits, zimg, gate, gate_value);
     MIMO_LAUNCH_CHECK();
-    tc_fstats_rimg_kernel<<<dim3((unsigned)blocks, (unsigned)L.cbs), 256, 0, st>>>(R, N, ldr, K, rvec4, L.nkb_cap, rimg, gate, gate_value);
+    tc_fstats_rimg_kernel<<<dim3((unsigned)blocks, (unsigned)L.cbs), 256, 0, st>>>(R, lse, N, ldr, K, rvec4, L.nkb_cap, rimg, gate, gate_value);
     MIMO_LAUNCH_CHECK();
     const int fbs = (TF_ROWS + TF_FBROWS - 1) / TF_FBROWS;
     const int cbps = L.cbs / 2, max_clusters = sm_count() / 2;

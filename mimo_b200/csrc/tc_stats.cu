@@ -39,7 +39,7 @@ struct TsBarriers {
 
 __global__ void __launch_bounds__(TS_THREADS, 1)
 tc_stats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
-                const float* __restrict__ R, int64_t ldr, int K,
+                const float* __restrict__ R, const float* __restrict__ lse, int64_t ldr, int K,
                 const unsigned int* __restrict__ maxbits,
                 double* __restrict__ partial, double* __restrict__ stat, int F,
                 int groups, int slabs, int64_t slab_points, int flush_tiles,
@@ -100,6 +100,7 @@ tc_stats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
                     int idx = tid + e * 256;                 // [g][point]
                     int g = idx >> 7, p = idx & 127;
                     rv[e] = (k0 + g < K && t0 + p < p1) ? __ldg(R + (int64_t)(k0 + g) * ldr + t0 + p) : 0.f;
+                    if (lse != nullptr && k0 + g < K && t0 + p < p1) rv[e] = fast_exp(rv[e] - __ldg(lse + t0 + p));   // R holds log-joints
                 }
                 if (tt + 1 < n_tiles) {                      // prefetch the next tile's column of Z
                     const int64_t nb = t0 + 128 + h * 64;
@@ -301,13 +302,13 @@ void tc_set_flush_tiles(int t) { g_flush_tiles = t < 1 ? 1 : t; }
 // one chunk of points: accumulates into the partial buffer (plan of `plan_points`, the sweep's chunk size)
 int tc_stats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, int K, int F,
                    const unsigned int* maxbits, double* stat, int64_t plan_points, void* ws, cudaStream_t st,
-                   const unsigned int* gate, unsigned int gate_value) {
+                   const unsigned int* gate, unsigned int gate_value, const float* lse) {
     if (N == 0) return MIMO_OK;
     TsPlan P = ts_plan(plan_points, K);
     size_t smem = 12 * (size_t)TS_TILE_BYTES + TS_G * 128 * sizeof(float) + sizeof(TsBarriers) + 1024;
     MIMO_CUDA(cudaFuncSetAttribute(tc_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(P.groups * P.slabs, sm_count());
-    tc_stats_kernel<<<grid, TS_THREADS, smem, st>>>(Z, N, D, ldz, R, ldr, K, maxbits, (double*)align1k(ws), stat, F,
+    tc_stats_kernel<<<grid, TS_THREADS, smem, st>>>(Z, N, D, ldz, R, lse, ldr, K, maxbits, (double*)align1k(ws), stat, F,
                                                     P.groups, P.slabs, P.slab_points, g_flush_tiles, gate, gate_value);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;

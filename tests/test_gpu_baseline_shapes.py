@@ -91,20 +91,25 @@ def test_cfg5_shape_sweep_against_oracle(cfg5_case, mode, what):
     try:
         buf = E.SweepBuffers(N, K, feats.F, 'fp32', False)
         if mode == 3:
-            ll = E.empty((K, N), torch.float32)
+            close(E.loglik_tc(Z, ops), c['ell'], 1e-4, 'expected log-joint (dense 3-pass kernel, K=1024 d=128)')
+            r = E.empty((K, N), torch.float32)          # a soft sweep's (K, N) output is the responsibilities
             lse_t = E.empty((N,), torch.float32)
-            E.sweep(Z, ops, feats, buf, ll_out=ll, lse_out=lse_t)
-            close(ll, c['ell'], 1e-4, 'expected log-joint (dense, K=1024 d=128)')
+            E.sweep(Z, ops, feats, buf, ll_out=r, lse_out=lse_t)
             close(lse_t, c['lse'], 1e-4, 'log-normalisers (dense)')
-            r = np.exp(ll.double().cpu().numpy() - lse_t.double().cpu().numpy()[None])
-            assert np.max(np.abs(r - c['resp'])) <= 1e-4 * 5, 'responsibilities (dense): %.2e' % np.max(np.abs(r - c['resp']))
+            err = float(np.max(np.abs(r.double().cpu().numpy() - c['resp'])))
+            assert err <= 1e-4, 'responsibilities (dense): max abs err %.2e' % err
         else:
             E.sweep(Z, ops, feats, buf)
             cand, pts, dense_chunks, chunks, level = E.screen_totals()
             print('%s: %.2f candidate pairs per point, %d of %d chunks dense, ended on tier %d'
                   % (what, cand / max(pts, 1), dense_chunks, chunks, level))
-            assert chunks >= 1 and dense_chunks == 0, 'the %s screening pass should have handled this chunk' % what
-            assert level == (0 if mode == 1 else 1)
+            assert chunks >= 1
+            if mode == 5:
+                assert dense_chunks == 0 and level == 1, 'the all-rows screening pass should have handled this chunk'
+            else:
+                # the 32-row projection is too loose a bound for components 4 sigma apart in d = 128: the chunk takes the
+                # dense kernels (device-side decision) and the sweep moves one tier up; either way the results must hold
+                assert (dense_chunks == 0 and level == 0) or (dense_chunks == chunks and level == 1)
         close(buf.stat, c['stat'], 1e-4, 'statistics (%s)' % what)
         assert abs(buf.lse_sum.item() - c['lse'].sum()) <= 1e-6 * abs(c['lse'].sum()), 'sum of log-normalisers (%s)' % what
         assert abs(buf.stat.cpu().numpy()[:, -1].sum() - N) <= 1e-6 * N

@@ -97,6 +97,69 @@ def test_loglik_diag_and_softmax_labels(precision):
     close(out['lse_sum'], [lse_ref.sum()], RTOL[precision], 'lse sum')
 
 
+@pytest.mark.parametrize('K,d,N,spread', [(37, 64, 3000, 1.0), (256, 64, 5000, 4.0), (200, 40, 2500, 2.0), (5, 8, 700, 0.5)])
+def test_loglik_diag_tc_labels(K, d, N, spread):
+    """tensor-core diagonal E-step (tc_diag.cu): log-joints, log-normalisers and labels against the oracle
+    (gaussian.py:837-850, gmm.py:72-75, stats.py:8-21); the data sit away from the origin (the kernel centres them)."""
+    E = eng()
+    rng = np.random.default_rng(31)
+    mus = spread * rng.standard_normal((K, d)) + 7.0
+    lam = rng.random((K, d)) * 2 + 0.5
+    lab0 = rng.integers(0, K, N)
+    x = mus[lab0] + rng.standard_normal((N, d)) / np.sqrt(lam[lab0])
+    logw = np.log(rng.dirichlet(np.ones(K)))
+    ops = E.DiagOperands(K, d, 'fp32')
+    E.set_log_weights(ops, logw)
+    E.operands_gauss_diag(ops, E.to_dev(mus), E.to_dev(lam))
+    Z = E.to_dev(x, torch.float32)
+    xr = Z.double().cpu().numpy()
+    ref = orc.gauss_diag_loglik(xr, mus, lam) + logw[:, None]
+    u = np.random.default_rng(5).random(N)
+    got = E.loglik_diag_tc(Z, ops, out=True, labels=True, lse=True, lse_sum=True, uniforms=u)
+    assert got['guard'] == 0
+    close(got['out'], ref, 1e-4, 'diag log-joint (tcgen05 feature GEMM)')
+    resp_ref, lse_ref = orc.responsibilities(ref)
+    close(got['lse'], lse_ref, 1e-4, 'lse')
+    close(got['lse_sum'], [lse_ref.sum()], 1e-4, 'lse sum')
+    # what the labels feel: the error of the log-joints of the components that carry mass, in nats
+    a = got['out'].double().cpu().numpy()
+    heavy = resp_ref > 1e-6
+    assert np.max(np.abs(a - ref)[heavy]) < 2e-3, np.max(np.abs(a - ref)[heavy])
+    lab_ref = orc.sample_discrete_from_log(ref, u)
+    safe = orc.label_boundary_distance(ref, u) > 3e-3
+    lab = got['labels'].cpu().numpy()
+    assert lab.dtype == np.int32 and lab.min() >= 0 and lab.max() < K
+    assert np.array_equal(lab[safe], lab_ref[safe]), int((lab[safe] != lab_ref[safe]).sum())
+    assert safe.mean() > 0.97
+    # labels without the (K, N) output, Philox uniforms keyed by the global index: independent of the chunking
+    l1 = E.loglik_diag_tc(Z, ops, labels=True, seed=99, offset=0)['labels'].cpu().numpy()
+    l2 = E.loglik_diag_tc(Z[500:], ops, labels=True, seed=99, offset=500)['labels'].cpu().numpy()
+    assert np.array_equal(l1[500:], l2)
+
+
+def test_loglik_diag_tc_guard():
+    """components far from the common centre relative to their width: the kernel must decline (device-side guard)"""
+    E = eng()
+    rng = np.random.default_rng(2)
+    K, d, N = 16, 32, 512
+    mus = 100.0 * rng.standard_normal((K, d))
+    lam = np.full((K, d), 4.0)
+    ops = E.DiagOperands(K, d, 'fp32')
+    E.set_log_weights(ops, np.log(np.full(K, 1.0 / K)))
+    E.operands_gauss_diag(ops, E.to_dev(mus), E.to_dev(lam))
+    Z = E.to_dev(mus[rng.integers(0, K, N)] + 0.5 * rng.standard_normal((N, d)), torch.float32)
+    assert E.loglik_diag_tc(Z, ops, labels=True, seed=1)['guard'] == 1
+    # ... and a Gibbs sweep on such operands still matches the oracle (CUDA-core kernels behind the gate)
+    feats = E.diag_features(d)
+    buf = E.SweepBuffers(N, K, feats.F, 'fp32', hard=True)
+    u = rng.random(N)
+    E.sweep(Z, ops, feats, buf, uniforms=E.to_dev(u))
+    xr = Z.double().cpu().numpy()
+    ref = orc.gauss_diag_loglik(xr, mus, lam) + np.log(1.0 / K)
+    safe = orc.label_boundary_distance(ref, u) > 1e-3
+    assert np.array_equal(buf.labels.cpu().numpy()[safe], orc.sample_discrete_from_log(ref, u)[safe])
+
+
 def test_philox_labels_independent_of_chunking():
     E = eng()
     rng = np.random.default_rng(8)
@@ -546,7 +609,11 @@ def test_sweep_resp_list_statistics(K, d, N, sep):
     Z = E.to_dev(x, torch.float32)
     feats = E.quad_features(d)
     buf = E.SweepBuffers(N, K, feats.F, 'fp32', False)
-    E.sweep(Z, ops, feats, buf)
+    old_min = E.set_tc_min_dim(24)                 # keep these dimensions on the CUDA cores (since round 2 the default sends d >= 8 to the tensor pipe)
+    try:
+        E.sweep(Z, ops, feats, buf)
+    finally:
+        E.set_tc_min_dim(old_min)
     old = E.set_tensor_cores(0)
     try:
         ref = E.SweepBuffers(N, K, feats.F, 'fp32', False)

@@ -72,6 +72,36 @@ def test_loglik_tc_dense_operands(K, d, rows):
     close(ll, E.loglik(Z, ops).cpu().numpy(), 2e-5, 'tensor-core vs CUDA-core log-lik')
 
 
+@pytest.mark.parametrize('gran', [16, 32])
+@pytest.mark.parametrize('K,d,tri', [(9, 128, True), (4, 100, True), (5, 128, False), (3, 70, False)])
+def test_loglik_tc_points_in_tensor_memory(gran, K, d, tri):
+    """tc_estep3.cu (points operand in tensor memory, triangular skip; off by default because it measured slower):
+    Cholesky-factor operands take the staircase of narrow MMAs, dense operands the full rows."""
+    E = eng()
+    rng = np.random.default_rng(17)
+    N = 1300
+    ops = E.QuadOperands(K, d, d, 'fp32')
+    W = np.zeros((K, ops.Rp, ops.Dpp))
+    blk = rng.standard_normal((K, d, d)) / np.sqrt(d)
+    W[:, :d, :d] = np.triu(blk) if tri else blk
+    W[:, :d, d] = rng.standard_normal((K, d))
+    cst = rng.standard_normal(K)
+    ops.W.copy_(E.to_dev(W, torch.float32))
+    ops.cst.copy_(E.to_dev(cst, torch.float32))
+    Z = E.to_dev(rng.standard_normal((N, d)) * 1.5 + 0.5, torch.float32)
+    old = E.set_triangular(gran)
+    try:
+        ll = E.loglik_tc(Z, ops)
+    finally:
+        E.set_triangular(old)
+    Wr = ops.W.double().cpu().numpy()
+    zt = np.concatenate([Z.double().cpu().numpy(), np.ones((N, 1))], axis=1)
+    y = np.einsum('kij,nj->kni', Wr[:, :, :d + 1], zt)
+    ref = ops.cst.double().cpu().numpy()[:, None] - 0.5 * np.sum(y * y, axis=2)
+    close(ll, ref, 1e-4, 'log-lik, points operand in tensor memory (G=%d)' % gran)
+    close(ll, E.loglik(Z, ops).cpu().numpy(), 2e-5, 'tensor-core vs CUDA-core log-lik')
+
+
 def test_loglik_tc_strided_rows_and_tiny_scale():
     """ldz > D, unaligned row stride (scalar load path), data of magnitude 1e-3."""
     E = eng()
@@ -92,6 +122,8 @@ def test_loglik_tc_strided_rows_and_tiny_scale():
 
 @pytest.mark.parametrize('K,d,N,flush', [(3, 128, 400, 16), (6, 128, 5000, 2), (70, 16, 2100, 16), (5, 40, 1000, 1),
                                          (9, 128, 20000, 16), (1, 3, 130, 16),
+                                         # small-dimension feature form (tc_sstats.cu, d <= 21): cfg2 / cfg4 shapes, several component tiles
+                                         (128, 9, 5000, 16), (64, 16, 70000, 16), (300, 21, 3000, 16), (2, 1, 64, 16),
                                          # feature-form kernel (64 < d <= 128): ragged K / d / N, several component blocks
                                          (300, 100, 3000, 16), (130, 65, 1001, 1), (1, 128, 63, 16), (257, 127, 9000, 4)])
 def test_stats_tc(K, d, N, flush):
@@ -134,7 +166,7 @@ def test_stats_tc_accumulates_into_stat():
 
 
 @pytest.mark.parametrize('hard', [False, True])
-@pytest.mark.parametrize('K,d,N', [(12, 32, 70000), (7, 128, 45000)])
+@pytest.mark.parametrize('K,d,N', [(12, 32, 70000), (7, 128, 45000), (64, 16, 60000), (128, 9, 40000), (20, 21, 9000)])
 def test_sweep_tc_matches_cuda_cores_and_oracle(hard, K, d, N):
     """mimo_sweep on the tensor-core path == the CUDA-core FP32 path within FP32 tolerance,
     and the statistics / lower-bound term match the oracle."""
