@@ -73,8 +73,7 @@ int tc_estep(const float* Z, int64_t N, int D, int64_t ldz, const float* cst, in
              float* out, int64_t ldo, void* ws, cudaStream_t st, float* lse_vals = nullptr, double* lse_sum = nullptr);
 // CTA-pair (cta_group::2) E-step, tc_estep2.cu
 size_t tc2_offsets_bytes(int K, int Rp);
-bool tc2_triangular(int KB, int Rp);      // operand image / accumulator columns in the triangular layout of tc_estep2.cu
-int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cst, int K, int Rp, int KB, float* offs2, cudaStream_t st);
+int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cst, int K, int Rp, float* offs2, cudaStream_t st);
 int tc_estep2(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, int KB, const void* Bimg, const float* offs2,
               const unsigned int* maxbits, float* out, int64_t ldo, int passes, const unsigned int* gate, unsigned int gate_value,
               float* lower, int* guess, int64_t ldl, cudaStream_t st, float* lse_vals = nullptr, double* lse_sum = nullptr);

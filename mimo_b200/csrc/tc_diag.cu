@@ -33,7 +33,8 @@ namespace mimo {
 using namespace tc;
 
 constexpr int TD_EPI = 512;                   // 16 converter / epilogue warps
-constexpr int TD_THREADS = TD_EPI + 64;       // + MMA (relay) warp + loader warp
+constexpr int TD_THREADS = TD_EPI;             // no extra warps: 16 warps = 4 per scheduler leave 128 registers per thread; thread 0 also loads the
+                                              // weights and issues the MMAs (leader CTA) / relays the peer's barriers
 constexpr uint32_t TD_TILE = 16384;           // 128 rows x 64 FP16
 constexpr uint32_t TD_ABUF = 4 * TD_TILE;     // [hi linear | hi quadratic | lo linear | lo quadratic]
 constexpr uint32_t TD_STAGE = 2 * TD_TILE;    // one K block of this CTA's 128 components: hi | lo
@@ -129,7 +130,8 @@ __global__ void td_gate_kernel(float* __restrict__ prm) {
 // ---- main kernel -------------------------------------------------------------------------------------------------
 // 16 converter / epilogue warps: warp w reads TMEM lanes 32 (w % 4) .. + 31 (its points) and the column quarter w / 4
 // (64 components = two 32-component blocks).  With 8 warps the epilogue ran at 1.2 warp instructions per clock (two
-// warps per scheduler, dependent chains): profiles/r02_tc_diag_kernel.md.
+// warps per scheduler, dependent chains): profiles/r02_tc_diag_kernel.md.  The 24 MMAs of a tile are issued by thread 0
+// right after the tile's features are stored, one iteration before its epilogue.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TD_THREADS, 1)
 tc_diag_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int vec4,
                const unsigned char* __restrict__ img, const float2* __restrict__ consts, const float* __restrict__ prm, int K,
@@ -157,13 +159,13 @@ tc_diag_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int v
         fence_barrier_init();
     }
     __syncthreads();
-    if (warp == TD_EPI / 32) tmem_alloc2(&bars->tmem_base, 512);
+    if (warp == 0) tmem_alloc2(&bars->tmem_base, 512);
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp < TD_EPI / 32) {
+    {
         // ================= converter + epilogue warps =================
         const float s1 = __ldg(prm), s2 = __ldg(prm + 1);
         const int j4 = (lane & 15) * 4, sub = lane >> 4;                 // this lane's 4 dimensions, row parity
@@ -174,16 +176,17 @@ tc_diag_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int v
         const int prow = qd * 32 + lane;                                 // point row inside the tile = TMEM lane
         const uint32_t lane_base = tmem_base + ((uint32_t)(qd * 32) << 16);
 
-        auto convert = [&](int64_t tile, uint32_t buf) {
-            unsigned char* sA = smem + (buf ? TD_OFF_A1 : 0u);
+        // a tile's rows reach the A operand in two steps, a whole tile apart: the global loads are issued one iteration
+        // ahead (their latency hides behind that iteration's epilogue), the feature tiles are written the iteration after
+        float4 z[4];
+        auto load_rows = [&](int64_t tile) {
             const int64_t n0 = tile * 256 + rank * 128;
-            float4 z[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = warp * 8 + 2 * i + sub;
                 const int64_t n = n0 + r;
                 z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n < N && j4 < D) {
+                if (tile < n_tiles && n < N && j4 < D) {
                     const float* src = Z + n * ldz + j4;
                     if (vec4 && j4 + 3 < D) z[i] = __ldg(reinterpret_cast<const float4*>(src));
                     else {
@@ -192,16 +195,18 @@ tc_diag_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int v
                         if (j4 + 2 < D) z[i].z = __ldg(src + 2);
                         if (j4 + 3 < D) z[i].w = __ldg(src + 3);
                     }
-                    z[i].x -= mu[0]; z[i].y -= mu[1]; z[i].z -= mu[2]; z[i].w -= mu[3];
-                    if (j4 + 1 >= D) z[i].y = 0.f;
-                    if (j4 + 2 >= D) z[i].z = 0.f;
-                    if (j4 + 3 >= D) z[i].w = 0.f;
                 }
             }
+        };
+        auto store_features = [&](uint32_t buf) {
+            unsigned char* sA = smem + (buf ? TD_OFF_A1 : 0u);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = warp * 8 + 2 * i + sub;
-                const float zz[4] = {z[i].x, z[i].y, z[i].z, z[i].w};
+                // (rows beyond N carry -mu: their results are never stored)
+                const bool on = j4 < D;
+                const float zz[4] = {on ? z[i].x - mu[0] : 0.f, (on && j4 + 1 < D) ? z[i].y - mu[1] : 0.f,
+                                     (on && j4 + 2 < D) ? z[i].z - mu[2] : 0.f, (on && j4 + 3 < D) ? z[i].w - mu[3] : 0.f};
                 float f1[4], f2[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { f1[e] = zz[e] * s1; const float t = zz[e] * s2; f2[e] = t * t; }
@@ -218,13 +223,64 @@ tc_diag_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int v
             mbar_arrive(&bars->a_full[buf]);
         };
 
+        // thread 0: the MMAs of local tile i (leader CTA), or the peer's "features stored" event forwarded to the leader
+        auto issue = [&](uint32_t i) {
+            const uint32_t buf = i & 1, par = (i >> 1) & 1;
+            mbar_wait(&bars->a_full[buf], par);
+            if (rank != 0) { mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_a_full[buf]), 0)); return; }
+            mbar_wait_cluster(&bars->peer_a_full[buf], par);
+            mbar_wait_cluster(&bars->tmem_empty[buf], par ^ 1);
+            tc_fence_after();
+            const uint32_t idesc = make_idesc_f16(256, 256);
+            const int S = (D + 15) >> 4;                                  // 16-wide K steps that hold data, per feature block
+            const uint32_t a0 = smem_u32(smem + (buf ? TD_OFF_A1 : 0u)), b0 = smem_u32(sB);
+            const uint32_t d = tmem_base + buf * 256;
+            bool first = true;
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+                const uint64_t ah = make_desc_sw128(a0 + kb * TD_TILE), al = make_desc_sw128(a0 + (2 + kb) * TD_TILE);
+                const uint64_t bh = make_desc_sw128(b0 + kb * TD_STAGE), bl = make_desc_sw128(b0 + kb * TD_STAGE + TD_TILE);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    if (kk >= S) continue;
+                    umma2_f16(d, al + 2 * kk, bh + 2 * kk, idesc, first ? 0u : 1u);
+                    umma2_f16(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
+                    umma2_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
+                    first = false;
+                }
+            }
+            umma2_commit(&bars->tmem_full[buf]);
+        };
+
         uint32_t it = 0;
-        if (cluster_id < n_tiles) convert(cluster_id, 0);
+        if (tid == 0) {
+            // this CTA's 128 weight rows + the constants, once
+            for (int kb = 0; kb < 2; ++kb) {
+                mbar_arrive_expect_tx(&bars->b_full[kb], TD_STAGE);
+                bulk_g2s(sB + (size_t)kb * TD_STAGE, img + (size_t)(kb * 2 + rank) * TD_STAGE, TD_STAGE, &bars->b_full[kb]);
+            }
+            mbar_arrive_expect_tx(&bars->c_full, TD_KMAX * 8);
+            bulk_g2s(smem + TD_OFF_C, consts, TD_KMAX * 8, &bars->c_full);
+        }
+        if (cluster_id < n_tiles) { load_rows(cluster_id); store_features(0); }
+        load_rows(cluster_id + n_clusters);
+        if (tid == 0) {
+            mbar_wait(&bars->b_full[0], 0); mbar_wait(&bars->b_full[1], 0);
+            if (rank == 0) { mbar_wait_cluster(&bars->peer_b_full[0], 0); mbar_wait_cluster(&bars->peer_b_full[1], 0); }
+            else { mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_b_full[0]), 0)); mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_b_full[1]), 0)); }
+            if (cluster_id < n_tiles) issue(0);
+        }
+        __syncwarp();
         mbar_wait(&bars->c_full, 0);
         for (int64_t tile = cluster_id; tile < n_tiles; tile += n_clusters, ++it) {
             const uint32_t buf = it & 1;
             // the MMAs that read A[buf ^ 1] (tile it - 1) have completed: this thread waited for their accumulator
-            if (tile + n_clusters < n_tiles) convert(tile + n_clusters, buf ^ 1);
+            if (tile + n_clusters < n_tiles) {
+                store_features(buf ^ 1);
+                if (tid == 0) issue(it + 1);
+                __syncwarp();
+            }
+            load_rows(tile + 2 * n_clusters);
 
             const int64_t n = tile * 256 + rank * 128 + prow;
             const bool pvalid = n < N;
@@ -321,63 +377,10 @@ tc_diag_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int v
                 }
             }
         }
-    } else if (warp == TD_EPI / 32) {
-        if (lane == 0 && rank == 0) {
-            // ================= MMA issuer (leader CTA, one thread) =================
-            const uint32_t idesc = make_idesc_f16(256, 256);
-            const int S = (D + 15) >> 4;                                  // 16-wide K steps that hold data, per feature block
-            mbar_wait(&bars->b_full[0], 0); mbar_wait(&bars->b_full[1], 0);
-            mbar_wait_cluster(&bars->peer_b_full[0], 0); mbar_wait_cluster(&bars->peer_b_full[1], 0);
-            uint32_t it = 0;
-            for (int64_t tile = cluster_id; tile < n_tiles; tile += n_clusters, ++it) {
-                const uint32_t buf = it & 1, par = (it >> 1) & 1;
-                mbar_wait(&bars->a_full[buf], par);
-                mbar_wait_cluster(&bars->peer_a_full[buf], par);
-                mbar_wait_cluster(&bars->tmem_empty[buf], par ^ 1);
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(smem + (buf ? TD_OFF_A1 : 0u)), b0 = smem_u32(sB);
-                const uint32_t d = tmem_base + buf * 256;
-                bool first = true;
-#pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
-                    const uint64_t ah = make_desc_sw128(a0 + kb * TD_TILE), al = make_desc_sw128(a0 + (2 + kb) * TD_TILE);
-                    const uint64_t bh = make_desc_sw128(b0 + kb * TD_STAGE), bl = make_desc_sw128(b0 + kb * TD_STAGE + TD_TILE);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        if (kk >= S) continue;
-                        umma2_f16(d, al + 2 * kk, bh + 2 * kk, idesc, first ? 0u : 1u);
-                        umma2_f16(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
-                        umma2_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
-                        first = false;
-                    }
-                }
-                umma2_commit(&bars->tmem_full[buf]);
-            }
-        } else if (lane == 0) {
-            // ================= relay (peer CTA): forward local events to the leader's issuer =================
-            mbar_wait(&bars->b_full[0], 0);
-            mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_b_full[0]), 0));
-            mbar_wait(&bars->b_full[1], 0);
-            mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_b_full[1]), 0));
-            uint32_t it = 0;
-            for (int64_t tile = cluster_id; tile < n_tiles; tile += n_clusters, ++it) {
-                const uint32_t buf = it & 1;
-                mbar_wait(&bars->a_full[buf], (it >> 1) & 1);
-                mbar_arrive_remote(map_to_rank(smem_u32(&bars->peer_a_full[buf]), 0));
-            }
-        }
-    } else if (lane == 0) {
-        // ================= loader (one thread per CTA): this CTA's 128 weight rows + the constants, once =================
-        for (int kb = 0; kb < 2; ++kb) {
-            mbar_arrive_expect_tx(&bars->b_full[kb], TD_STAGE);
-            bulk_g2s(sB + (size_t)kb * TD_STAGE, img + (size_t)(kb * 2 + rank) * TD_STAGE, TD_STAGE, &bars->b_full[kb]);
-        }
-        mbar_arrive_expect_tx(&bars->c_full, TD_KMAX * 8);
-        bulk_g2s(smem + TD_OFF_C, consts, TD_KMAX * 8, &bars->c_full);
     }
     tc_fence_before();
     cluster_sync_all();                                   // no CTA leaves (or frees TMEM) while its partner may still signal it
-    if (warp == TD_EPI / 32) tmem_dealloc2(tmem_base, 512);
+    if (warp == 0) tmem_dealloc2(tmem_base, 512);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------

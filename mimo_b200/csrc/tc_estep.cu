@@ -65,13 +65,9 @@ __global__ void tc_absmax_kernel(const float* __restrict__ Z, int64_t N, int D, 
 //   Bimg   [chunk][kb][hi|lo][128 rows][64] FP16, swizzled exactly as the kernel's shared-memory stage
 //   rowoff [chunk*128 + r] = W[k][i][D] * sw_k * sz        (offset column in accumulator units)
 //   invS2  [k]             = 1 / (sw_k * sz)^2
-// tri (Rp = 128, KB = 2; a chunk is one component): the triangular layout of tc_estep2.cu.  The K block 0 tile of a
-// chunk keeps the component's rows in order (the kernel copies rows 0..63 only); the K block 1 tiles of a chunk PAIR
-// hold [rows 0..63 of both components] and [rows 64..127 of both].  flags[8] is raised when some row 64..127 has data
-// in columns 0..63 (operands that are not Cholesky factors): the kernel then runs the full-width K block 0 as well.
 __global__ void __launch_bounds__(256)
-tc_prep_operands_kernel(const float* __restrict__ W, int K, int Rp, int Dpp, int D, int KB, int tri,
-                        unsigned int* __restrict__ maxbits,
+tc_prep_operands_kernel(const float* __restrict__ W, int K, int Rp, int Dpp, int D, int KB,
+                        const unsigned int* __restrict__ maxbits,
                         __half* __restrict__ Bimg, float* __restrict__ rowoff, float* __restrict__ invS2) {
     __shared__ unsigned int cmax[16];
     __shared__ float csw[16];
@@ -100,7 +96,6 @@ tc_prep_operands_kernel(const float* __restrict__ W, int K, int Rp, int Dpp, int
         rowoff[flat] = (k < K) ? W[flat * Dpp + D] * csw[tid / Rp] * sz : 0.f;
     }
     char* img = reinterpret_cast<char*>(Bimg) + (size_t)c * KB * TE_STAGE_BYTES;
-    bool below = false;                            // data left of the diagonal 64 x 64 block (tri)
     for (int idx = tid; idx < 128 * KB * 8; idx += 256) {
         int r = idx / (KB * 8), ch = idx - r * (KB * 8);      // ch = 16-byte chunk along K (8 elements)
         int64_t flat = (int64_t)c * 128 + r;
@@ -116,17 +111,9 @@ tc_prep_operands_kernel(const float* __restrict__ W, int K, int Rp, int Dpp, int
         split8(x, hi, lo);
         int kb = ch >> 3, cc = ch & 7;
         char* base = img + (size_t)kb * TE_STAGE_BYTES + sw128_chunk_off(r, cc);
-        if (tri && kb == 1)
-            base = reinterpret_cast<char*>(Bimg) + ((size_t)((c & ~1) + (r >> 6)) * KB + 1) * TE_STAGE_BYTES
-                 + sw128_chunk_off((c & 1) * 64 + (r & 63), cc);
-        if (tri && kb == 0 && r >= 64) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) below |= (x[e] != 0.f);
-        }
         *reinterpret_cast<uint4*>(base) = hi;
         *reinterpret_cast<uint4*>(base + TE_TILE_BYTES) = lo;
     }
-    if (below) maxbits[8] = 1u;
 }
 
 template <int RP>
@@ -369,8 +356,7 @@ const unsigned int* tc_maxbits(void* ws) { return (const unsigned int*)align1k(w
 int tc_prepare_operands(const float* W, const float* cst, int K, int Rp, int Dpp, int D, void* ws, cudaStream_t st) {
     TcOperandLayout L = tc_layout(K, Rp, D);
     char* base = align1k(ws);
-    MIMO_CUDA(cudaMemsetAsync(base + L.off_maxbits + 32, 0, 4, st));          // flags[8]: operands with data below the diagonal block
-    tc_prep_operands_kernel<<<L.n_chunks, 256, 0, st>>>(W, K, Rp, Dpp, D, L.KB, tc2_triangular(L.KB, Rp) ? 1 : 0, (unsigned int*)(base + L.off_maxbits),
+    tc_prep_operands_kernel<<<L.n_chunks, 256, 0, st>>>(W, K, Rp, Dpp, D, L.KB, (const unsigned int*)(base + L.off_maxbits),
                                                         (__half*)(base + L.off_img), (float*)(base + L.off_rowoff),
                                                         (float*)(base + L.off_invS2));
     MIMO_LAUNCH_CHECK();
@@ -379,7 +365,7 @@ int tc_prepare_operands(const float* W, const float* cst, int K, int Rp, int Dpp
         if (rc) return rc;
     }
     // per-chunk offsets / constants blocks of the CTA-pair kernel
-    return tc2_prepare_offsets((const float*)(base + L.off_rowoff), (const float*)(base + L.off_invS2), cst, K, Rp, L.KB,
+    return tc2_prepare_offsets((const float*)(base + L.off_rowoff), (const float*)(base + L.off_invS2), cst, K, Rp,
                                (float*)(base + L.off_offs2), st);
 }
 
@@ -423,7 +409,7 @@ int tc_estep(const float* Z, int64_t N, int D, int64_t ldz, const float* cst, in
     if (tc_mode() != 2 && tc3_supported(D, Rp))     // points operand in tensor memory, triangular skip
         return tc_estep3(Z, N, D, ldz, K, base + L.off_t3, (const unsigned int*)(base + L.off_maxbits), out, ldo, nullptr, 0u, lse_vals, lse_sum, st);
     // CTA-pair kernel (cta_group::2), dense 3-pass; the single-CTA kernel (mode 2) reads the plain image only
-    if (tc_mode() != 2 || tc2_triangular(L.KB, Rp) || lse_vals)
+    if (tc_mode() != 2 || lse_vals)
         return tc_estep2(Z, N, D, ldz, K, Rp, L.KB, (const void*)(base + L.off_img), (const float*)(base + L.off_offs2),
                          (const unsigned int*)(base + L.off_maxbits), out, ldo, 3, nullptr, 0u, nullptr, nullptr, 0, st, lse_vals, lse_sum);
 #define TE_CASE(kb, rp) if (L.KB == kb && Rp == rp) return launch_estep<kb, rp>(Z, N, D, ldz, L, base, cst, K, out, ldo, st);

@@ -24,14 +24,13 @@
 // 128-column slice into registers with four tcgen05.ld in flight and releases the accumulator
 // before doing any arithmetic on it.
 //
-// Triangular operands (KB = 2, Rp = 128: one component per CTA per chunk, d > 64).  The rows of W_k are Cholesky
-// factors (U_k, sqrt(nu_k) C_k^T): row r is zero left of column r, so rows 64..127 contribute nothing in the first
-// 64-wide K block.  The accumulator columns of a chunk are ordered [A rows 0..63 | B rows 0..63 | A rows 64..127 |
-// B rows 64..127] (A, B = the two components of the chunk): the second K block runs first as one 256-column MMA per
-// K step (it initialises every column), the first K block then only needs the first 128 columns -- a quarter of the
-// MMA work and of the operand copies gone.  tc_prep_operands_tri_kernel (tc_estep.cu) lays the image out for this and
-// raises a device flag when some operand is NOT triangular (stacked ILR blocks): the issuer then adds the missing
-// 128-column MMAs, the producer copies whole tiles.
+// Narrow components (Rp <= 64, dense passes): 16 converter / epilogue warps instead of 8, each thread takes 64 of the
+// chunk's 256 columns.  On the small-dimension shapes (cfg2 / cfg4 of BASELINE.json: one 16-wide K step feeds 256
+// columns) the kernel is bound by the accumulator read-back and the per-column arithmetic behind it, and with two warps
+// per scheduler that arithmetic ran at 1.7 warp instructions per clock (profiles/r02_small_d_kernels.md).  The rows of
+// the NEXT pass are prefetched into L2 while this pass's chunks are drained.
+// (A block-triangular variant for Cholesky-factor operands -- narrower MMAs for the K block where the lower row half is
+// zero -- was measured slower twice, with the points operand in shared memory and in tensor memory: tc_estep3.cu.)
 //
 // Fused log-normaliser (PASSES = 3, lse_vals != nullptr): thread = point, so the running (max, sum) of the point's
 // log-joints over all components is thread-local; the two column halves of a point meet once per pass through
@@ -45,10 +44,8 @@ namespace mimo {
 
 using namespace tc;
 
-// the block-triangular variant with both operands in shared memory (header comment) is compiled out: measured slower
-// than the plain kernel (profiles/r02_tri_ss_mode.md); tc_estep3.cu is the triangular kernel (points operand in TMEM)
-constexpr bool T2_TRI_SS = false;
-constexpr int T2_THREADS = 320;
+// converter / epilogue warps of an instantiation (then one MMA / relay warp and one producer warp)
+__host__ __device__ constexpr int t2_warps(int RP, int PASSES) { return (PASSES == 3 && RP <= 64) ? 16 : 8; }
 constexpr int T2_STAGES = 4;                 // B ring: one stage = this CTA's 128 rows x 64 K, hi + lo = 32 KB
 constexpr int T2_STAGES1 = 8;                // single-pass kernel: hi tiles only (16 KB), twice as many stages in the same space
 constexpr uint32_t T2_TILE = 16384;          // 128 rows x 64 FP16
@@ -63,19 +60,17 @@ struct T2Bars {
     uint64_t a_full, peer_a_full;
     uint64_t off_full[T2_OFFRING], off_empty[T2_OFFRING];
     uint32_t tmem_base;
-    float2 comb[128];                        // fused log-normaliser: (max, sum) of the odd column half, per point
+    float2 comb[3][128];                     // fused log-normaliser: (max, sum) of the other column groups, per point
 };
 
 // offsets block of every 256-row chunk: [256 row offsets | cst of its components | 1/scale^2 of its components]
-// tri: accumulator column t of the triangular layout (header comment) = component (t / 64) % 2, row 64 (t / 128) + t % 64
 __global__ void tc2_offsets_kernel(const float* __restrict__ rowoff, const float* __restrict__ invS2, const float* __restrict__ cst,
-                                   int K, int Rp, int n_chunks, int tri, float* __restrict__ offs2) {
+                                   int K, int Rp, int n_chunks, float* __restrict__ offs2) {
     const int c2 = blockIdx.x, t = threadIdx.x;                 // 320 threads
     float v = 0.f;
     if (t < 256) {
-        const int chunk = 2 * c2 + (tri ? ((t >> 6) & 1) : (t >> 7));
-        const int row = tri ? (((t >> 7) << 6) | (t & 63)) : (t & 127);
-        v = chunk < n_chunks ? rowoff[(size_t)chunk * 128 + row] : 0.f;
+        const int chunk = 2 * c2 + (t >> 7);
+        v = chunk < n_chunks ? rowoff[(size_t)chunk * 128 + (t & 127)] : 0.f;
     } else {
         const int j = (t - 256) & 31;
         const int k = c2 * (256 / Rp) + j;
@@ -119,21 +114,11 @@ __device__ __forceinline__ void t2_consume(const float (&v)[32], const float* __
     }
 }
 
-// 32 accumulator columns of ONE component -> partial squared norms (4 independent chains)
-__device__ __forceinline__ void t2_sum32(const float (&v)[32], const float* __restrict__ off_s, float (&q)[4]) {
-#pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 o = *reinterpret_cast<const float4*>(off_s + j4 * 4);             // broadcast read
-        const float t0 = v[j4 * 4] + o.x, t1 = v[j4 * 4 + 1] + o.y, t2 = v[j4 * 4 + 2] + o.z, t3 = v[j4 * 4 + 3] + o.w;
-        q[0] = fmaf(t0, t0, q[0]); q[1] = fmaf(t1, t1, q[1]); q[2] = fmaf(t2, t2, q[2]); q[3] = fmaf(t3, t3, q[3]);
-    }
-}
-
 // PASSES = 3: Ah*Bh + Ah*Bl + Al*Bh (FP32-class);  PASSES = 1: Ah*Bh only (the screening pass of tc_screen.cu).
 // gate (optional): the whole grid returns at once unless *gate == gate_value (device-side choice between the
 // dense second pass and the per-candidate refinement without a host round trip).
 template <int KB, int RP, int PASSES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (t2_warps(RP, PASSES) + 2), 1)
 tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int vec4,
                  const __half* __restrict__ Bimg, const float* __restrict__ offs2,
                  const unsigned int* __restrict__ maxbits,
@@ -142,7 +127,8 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                  float* __restrict__ lower, int* __restrict__ guess, int64_t ldl,
                  float* __restrict__ lse_vals, double* __restrict__ lse_sum) {
     if (gate != nullptr && __ldg(gate) != gate_value) return;
-    constexpr bool TRI = T2_TRI_SS && KB == 2 && RP == 128;             // column layout / K-block order of the header comment
+    constexpr int NW = t2_warps(RP, PASSES);                            // converter / epilogue warps
+    constexpr int NG = NW / 4, CW = 256 / NG;                           // column groups of a chunk, columns per group
     constexpr uint32_t STAGE_TX = PASSES == 3 ? T2_STAGE : T2_TILE;   // bytes copied per stage (hi | lo, or hi only)
     constexpr int NST = PASSES == 3 ? T2_STAGES : T2_STAGES1;         // ring depth; a ring slot is STAGE_TX bytes
     static_assert(NST * STAGE_TX == T2_STAGES * T2_STAGE, "ring size");
@@ -161,25 +147,25 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); mbar_init(&bars->peer_full[s], 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 16); mbar_init(&bars->peer_tmem_empty[b], 1);   // tmem_empty (leader's): one arrival per epilogue warp of BOTH CTAs
+            mbar_init(&bars->tmem_full[b], 1); mbar_init(&bars->tmem_empty[b], 2 * NW); mbar_init(&bars->peer_tmem_empty[b], 1);   // tmem_empty (leader's): one arrival per epilogue warp of BOTH CTAs
         }
-        for (int b = 0; b < T2_OFFRING; ++b) { mbar_init(&bars->off_full[b], 1); mbar_init(&bars->off_empty[b], 256); }
-        mbar_init(&bars->a_full, 256);
+        for (int b = 0; b < T2_OFFRING; ++b) { mbar_init(&bars->off_full[b], 1); mbar_init(&bars->off_empty[b], 32 * NW); }
+        mbar_init(&bars->a_full, 32 * NW);
         mbar_init(&bars->peer_a_full, 1);
         fence_barrier_init();
     }
     __syncthreads();
-    if (warp == 8) tmem_alloc2(&bars->tmem_base, 512);
+    if (warp == NW) tmem_alloc2(&bars->tmem_base, 512);
     tc_fence_before();
     cluster_sync_all();                                   // barriers of both CTAs initialised, TMEM allocated
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp < 8) {
+    if (warp < NW) {
         // ================= converter + epilogue warps =================
         const float sz = pow2_scale_for(__uint_as_float(__ldg(maxbits)));
         constexpr bool SCREEN = PASSES == 1;
-        const int half = warp >> 2, qd = warp & 3;
+        const int half = warp >> 2, qd = warp & 3;                   // half: column group of this warp (0 .. NG-1)
         const int prow = qd * 32 + lane;                             // point row inside the tile = TMEM lane
         uint32_t gc = 0;
         for (int64_t pass = cluster_id; pass < n_passes; pass += n_clusters) {
@@ -187,11 +173,11 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
             // ---- A operand: 128 rows of Z -> 3xFP16 split, K-major swizzled.  Every MMA of the previous pass
             //      has completed (all threads waited on its last tmem_full), so A may be overwritten. ----
             const int f = lane * 4;                                  // this lane's 4 features
-            for (int r0 = warp; r0 < 128; r0 += 32) {                // 4 rows in flight per warp
+            for (int r0 = warp; r0 < 128; r0 += 4 * NW) {            // 4 rows in flight per warp
                 float x[4][4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int r = r0 + 8 * u;
+                    const int r = r0 + NW * u;
                     const int64_t n = n0 + r;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) x[u][e] = 0.f;
@@ -209,7 +195,7 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                 if (f < KB * 64) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int rr = r0 + 8 * u;
+                        const int rr = r0 + NW * u;
                         float xs[4] = {x[u][0] * sz, x[u][1] * sz, x[u][2] * sz, x[u][3] * sz};
                         uint2 hi, lo;
                         split4(xs, hi, lo);
@@ -222,8 +208,17 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
             }
             fence_proxy_async();
             mbar_arrive(&bars->a_full);
+            // the rows of this cluster's next pass -> L2 (one 128-byte line per lane; the conversion above then hits L2)
+            if (pass + n_clusters < n_passes) {
+                const int64_t nn0 = (pass + n_clusters) * 256 + rank * 128;
+                const int64_t lines = ((int64_t)128 * ldz * 4 + 127) / 128;
+                for (int64_t l = tid; l < lines; l += 32 * NW) {
+                    const char* pf = reinterpret_cast<const char*>(Z + nn0 * ldz) + l * 128;
+                    if (pf < reinterpret_cast<const char*>(Z + N * ldz)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                }
+            }
 
-            // ---- epilogue over the 256-row chunks: this warp group owns columns [128 half, +128) ----
+            // ---- epilogue over the 256-row chunks: this warp group owns columns [CW half, +CW) ----
             const int64_t n = n0 + prow;
             const bool pvalid = n < N;
             float* outp = out + n;
@@ -238,24 +233,13 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                 tc_fence_after();
                 const float* blk = sOff + ob * T2_OFFBLK;
                 const float* scal_s = blk + 256;
-                // the whole 128-column slice into registers with the four loads in flight, then the accumulator is
-                // free again: the drain costs one TMEM latency on the MMA -> epilogue -> MMA chain, not four plus the math
-                float v0[32], v1[32], v2[32], v3[32];
+                // the whole column slice into registers with its loads in flight, then the accumulator is free again: the
+                // drain costs one TMEM latency on the MMA -> epilogue -> MMA chain, not one per load plus the math
+                float v[CW / 32][32];
                 float q[4] = {0.f, 0.f, 0.f, 0.f};
-                if constexpr (TRI) {
-                    // this half's component: columns [64 half, +64) (rows 0..63) and [128 + 64 half, +64) (rows 64..127)
-                    const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * 256 + half * 64;
-                    tmem_ld32(taddr, v0);
-                    tmem_ld32(taddr + 32, v1);
-                    tmem_ld32(taddr + 128, v2);
-                    tmem_ld32(taddr + 160, v3);
-                } else {
-                    const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * 256 + half * 128;
-                    tmem_ld32(taddr, v0);
-                    tmem_ld32(taddr + 32, v1);
-                    tmem_ld32(taddr + 64, v2);
-                    tmem_ld32(taddr + 96, v3);
-                }
+                const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * 256 + half * CW;
+#pragma unroll
+                for (int g = 0; g < CW / 32; ++g) tmem_ld32(taddr + 32 * g, v[g]);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -263,44 +247,26 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                     if (rank == 0) mbar_arrive(&bars->tmem_empty[buf]);
                     else mbar_arrive_remote_nofence(map_to_rank(smem_u32(&bars->tmem_empty[buf]), 0));
                 }
-                if constexpr (TRI) {
-                    const float* o = blk + half * 64;
-                    t2_sum32(v0, o, q);
-                    t2_sum32(v1, o + 32, q);
-                    t2_sum32(v2, o + 128, q);
-                    t2_sum32(v3, o + 160, q);
-                    const int k = c * 2 + half;
-                    if (k < K) {
-                        const float qq = (q[0] + q[1]) + (q[2] + q[3]);
-                        const float val = scal_s[half] - 0.5f * (scal_s[32 + half] * qq);
-                        if (pvalid) outp[(int64_t)k * ldo] = val;
-                        if (SCREEN && val > Lb) { Lb = val; Lk = k; }
-                        if (!SCREEN) {                           // online log-sum-exp of this point's column half
-                            const float mn = fmaxf(lm, val);
-                            ls = fmaf(ls, fast_exp(lm - mn), fast_exp(val - mn));
-                            lm = mn;
-                        }
-                    }
-                } else {
-                    const float* off_s = blk + half * 128;
-                    const int kbase = c * (256 / RP), jbase = half * (128 / RP);
-                    t2_consume<RP, SCREEN>(v0, off_s, 0, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk, lm, ls);
-                    t2_consume<RP, SCREEN>(v1, off_s, 32, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk, lm, ls);
-                    t2_consume<RP, SCREEN>(v2, off_s, 64, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk, lm, ls);
-                    t2_consume<RP, SCREEN>(v3, off_s, 96, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk, lm, ls);
-                }
+                const float* off_s = blk + half * CW;
+                const int kbase = c * (256 / RP), jbase = half * (CW / RP);
+#pragma unroll
+                for (int g = 0; g < CW / 32; ++g)
+                    t2_consume<RP, SCREEN>(v[g], off_s, 32 * g, q, scal_s, jbase, kbase, K, pvalid, outp, ldo, Lb, Lk, lm, ls);
                 mbar_arrive(&bars->off_empty[ob]);
             }
             if (SCREEN && pvalid) { lower[(int64_t)half * ldl + n] = Lb; guess[(int64_t)half * ldl + n] = Lk; }
             if (!SCREEN && lse_vals != nullptr) {
-                // the two column halves of a point meet: the next write of comb is a whole pass away (behind the
-                // a_full arrival of every epilogue thread), so one barrier is enough
-                if (half == 1) bars->comb[prow] = make_float2(lm, ls);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                // the column groups of a point meet: the next write of comb is a whole pass away (behind the a_full
+                // arrival of every epilogue thread), so one barrier is enough
+                if (half > 0) bars->comb[half - 1][prow] = make_float2(lm, ls);
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * NW) : "memory");
                 if (half == 0) {
-                    const float2 o = bars->comb[prow];
-                    const float M = fmaxf(lm, o.x);
-                    const float S = ls * fast_exp(lm - M) + o.y * fast_exp(o.x - M);
+                    float M = lm;
+#pragma unroll
+                    for (int g = 0; g < NG - 1; ++g) M = fmaxf(M, bars->comb[g][prow].x);
+                    float S = ls * fast_exp(lm - M);
+#pragma unroll
+                    for (int g = 0; g < NG - 1; ++g) { const float2 o = bars->comb[g][prow]; S = fmaf(o.y, fast_exp(o.x - M), S); }
                     const float lse = M + __logf(S);
                     double part = 0.0;
                     if (pvalid) { lse_vals[n] = lse; part = (double)lse; }
@@ -312,12 +278,10 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == NW) {
         if (lane == 0 && rank == 0) {
             // ================= MMA issuer (leader CTA, one thread) =================
             const uint32_t idesc = make_idesc_f16(256, 256);
-            const uint32_t idesc_half = make_idesc_f16(256, 128);
-            const bool dense0 = TRI && __ldg(maxbits + 8) != 0u;          // some operand has data left of its diagonal block
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
             const int S = (D + 15) >> 4;                                  // 16-wide K steps that hold data
             uint32_t stage = 0, phase = 0, gc = 0, it = 0;
@@ -330,8 +294,7 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                     mbar_wait_cluster(&bars->tmem_empty[buf], par);      // drained by the epilogue warps of both CTAs
                     tc_fence_after();
                     const uint32_t d = tmem_base + buf * 256;
-                    for (int it_kb = 0; it_kb < KB; ++it_kb) {
-                        const int kb = TRI ? (KB - 1 - it_kb) : it_kb;  // TRI: the full-width K block first (it initialises all columns)
+                    for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&bars->full[stage], phase);
                         mbar_wait_cluster(&bars->peer_full[stage], phase);
                         tc_fence_after();
@@ -340,36 +303,16 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                         const uint64_t bl = make_desc_sw128(bs + T2_TILE);
                         const uint64_t ah = make_desc_sw128(a0 + kb * T2_TILE);
                         const uint64_t al = make_desc_sw128(a0 + (KB + kb) * T2_TILE);
-                        if (TRI && kb == 0) {
-                            // rows 0..63 of both components (columns 0..127); rows 64..127 only when some operand is dense
-                            const uint64_t bh2 = make_desc_sw128(bs + 8192), bl2 = make_desc_sw128(bs + T2_TILE + 8192);
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                if (PASSES == 3) {
-                                    umma2_f16(d, al + 2 * kk, bh + 2 * kk, idesc_half, 1);
-                                    umma2_f16(d, ah + 2 * kk, bl + 2 * kk, idesc_half, 1);
-                                }
-                                umma2_f16(d, ah + 2 * kk, bh + 2 * kk, idesc_half, 1);
-                                if (dense0) {
-                                    if (PASSES == 3) {
-                                        umma2_f16(d + 128, al + 2 * kk, bh2 + 2 * kk, idesc_half, 1);
-                                        umma2_f16(d + 128, ah + 2 * kk, bl2 + 2 * kk, idesc_half, 1);
-                                    }
-                                    umma2_f16(d + 128, ah + 2 * kk, bh2 + 2 * kk, idesc_half, 1);
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {               // 16-element K steps inside the 64-wide block: +32 B
-                                if (kb * 4 + kk >= S) continue;
-                                const uint32_t acc = TRI ? (uint32_t)(kk != 0) : (uint32_t)((kb | kk) != 0);
-                                if (PASSES == 3) {
-                                    umma2_f16(d, al + 2 * kk, bh + 2 * kk, idesc, acc);
-                                    umma2_f16(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
-                                    umma2_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
-                                } else {
-                                    umma2_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, acc);
-                                }
+                        for (int kk = 0; kk < 4; ++kk) {               // 16-element K steps inside the 64-wide block: +32 B
+                            if (kb * 4 + kk >= S) continue;
+                            const uint32_t acc = (uint32_t)((kb | kk) != 0);
+                            if (PASSES == 3) {
+                                umma2_f16(d, al + 2 * kk, bh + 2 * kk, idesc, acc);
+                                umma2_f16(d, ah + 2 * kk, bl + 2 * kk, idesc, 1);
+                                umma2_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, 1);
+                            } else {
+                                umma2_f16(d, ah + 2 * kk, bh + 2 * kk, idesc, acc);
                             }
                         }
                         umma2_commit(&bars->empty[stage]);               // both CTAs' stage free once these MMAs have read it
@@ -397,7 +340,6 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
     } else {
         // ================= producer (one thread per CTA): this CTA's half of B + the chunk offsets =================
         if (lane == 0) {
-            const bool dense0 = TRI && __ldg(maxbits + 8) != 0u;
             uint32_t stage = 0, phase = 0, gc = 0;
             for (int64_t pass = cluster_id; pass < n_passes; pass += n_clusters) {
                 const unsigned char* src = reinterpret_cast<const unsigned char*>(Bimg);
@@ -406,19 +348,10 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
                     mbar_wait(&bars->off_empty[ob], ((gc / T2_OFFRING) & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars->off_full[ob], T2_OFFBYTES);
                     bulk_g2s(sOff + ob * T2_OFFBLK, offs2 + (size_t)c * T2_OFFBLK, T2_OFFBYTES, &bars->off_full[ob]);
-                    for (int it_kb = 0; it_kb < KB; ++it_kb) {
-                        const int kb = TRI ? (KB - 1 - it_kb) : it_kb;
+                    for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&bars->empty[stage], phase ^ 1);
-                        const unsigned char* tile = src + ((size_t)(2 * c + rank) * KB + kb) * T2_STAGE;
-                        unsigned char* dst = sB + (size_t)stage * STAGE_TX;
-                        if (TRI && kb == 0 && !dense0) {                 // rows 0..63 only: 8 KB of hi (and of lo)
-                            mbar_arrive_expect_tx(&bars->full[stage], PASSES == 3 ? 16384u : 8192u);
-                            bulk_g2s(dst, tile, 8192u, &bars->full[stage]);
-                            if (PASSES == 3) bulk_g2s(dst + T2_TILE, tile + T2_TILE, 8192u, &bars->full[stage]);
-                        } else {
-                            mbar_arrive_expect_tx(&bars->full[stage], STAGE_TX);
-                            bulk_g2s(dst, tile, STAGE_TX, &bars->full[stage]);
-                        }
+                        mbar_arrive_expect_tx(&bars->full[stage], STAGE_TX);
+                        bulk_g2s(sB + (size_t)stage * STAGE_TX, src + ((size_t)(2 * c + rank) * KB + kb) * T2_STAGE, STAGE_TX, &bars->full[stage]);
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -427,7 +360,7 @@ tc_estep2_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int
     }
     tc_fence_before();
     cluster_sync_all();                                   // no CTA leaves (or frees TMEM) while its partner may still signal it
-    if (warp == 8) tmem_dealloc2(tmem_base, 512);
+    if (warp == NW) tmem_dealloc2(tmem_base, 512);
 }
 
 // ---- host side -------------------------------------------------------------------------------
@@ -437,11 +370,9 @@ size_t tc2_offsets_bytes(int K, int Rp) {
     return (size_t)((n_chunks + 1) / 2) * T2_OFFBYTES;
 }
 
-bool tc2_triangular(int KB, int Rp) { return T2_TRI_SS && KB == 2 && Rp == 128; }
-
-int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cst, int K, int Rp, int KB, float* offs2, cudaStream_t st) {
+int tc2_prepare_offsets(const float* rowoff, const float* invS2, const float* cst, int K, int Rp, float* offs2, cudaStream_t st) {
     const int n_chunks = (int)(((int64_t)K * Rp + 127) / 128);
-    tc2_offsets_kernel<<<(n_chunks + 1) / 2, T2_OFFBLK, 0, st>>>(rowoff, invS2, cst, K, Rp, n_chunks, tc2_triangular(KB, Rp) ? 1 : 0, offs2);
+    tc2_offsets_kernel<<<(n_chunks + 1) / 2, T2_OFFBLK, 0, st>>>(rowoff, invS2, cst, K, Rp, n_chunks, offs2);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }
@@ -457,7 +388,7 @@ static int launch_estep2(const float* Z, int64_t N, int D, int64_t ldz, const __
     const int64_t passes = (N + 255) / 256;
     const int clusters = (int)std::min<int64_t>(passes, sm_count() / 2);
     const int vec4 = (ldz % 4 == 0) && (((uintptr_t)Z & 15) == 0);
-    kern<<<2 * clusters, T2_THREADS, smem, st>>>(Z, N, D, ldz, vec4, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, lower, guess, ldl, lse_vals, lse_sum);
+    kern<<<2 * clusters, 32 * (t2_warps(RP, PASSES) + 2), smem, st>>>(Z, N, D, ldz, vec4, Bimg, offs2, maxbits, K, n_chunks2, out, ldo, gate, gate_value, lower, guess, ldl, lse_vals, lse_sum);
     MIMO_LAUNCH_CHECK();
     return MIMO_OK;
 }

@@ -115,20 +115,55 @@ tc_sstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
                 const int ch = idx & 7, r = kt + ((idx >> 3) % (128 - kt)), hl = ((idx >> 3) / (128 - kt)) & 1, stz = ((idx >> 3) / (128 - kt)) >> 1;
                 *reinterpret_cast<uint4*>(smem + stz * stage_bytes + hl * SS_ATILE + sw128_chunk_off(r, ch)) = make_uint4(0, 0, 0, 0);
             }
+            // the global loads of a block are issued one block ahead (into registers) so that their latency hides behind the
+            // feature products of the block before
+            float zr[6], lr = 0.f;                                        // ceil(64 * 21 / 256) data values per thread, one log-normaliser
+            float4 rx[4][2];                                              // <= 4 responsibility items of 8 points
+            auto fetch = [&](int64_t blk) {
+                const int64_t n0 = blk * SS_KB;
+                const bool live = blk < b1;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const int idx = tid + 256 * q;
+                    const int p = idx / D, i = idx - p * D;
+                    zr[q] = (live && idx < SS_KB * D && n0 + p < N) ? __ldg(Z + (n0 + p) * ldz + i) : 0.f;
+                }
+                lr = (live && lse != nullptr && tid < SS_KB && n0 + tid < N) ? __ldg(lse + n0 + tid) : 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int item = tid + 256 * q;
+                    const int ca = item >> 3, c = item & 7;
+                    rx[q][0] = rx[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live && item < kt * 8) {
+                        const float* src = R + (int64_t)(k0 + ca) * ldr + n0;
+                        if (n0 + SS_KB <= N && rvec4) {
+                            rx[q][0] = __ldg(reinterpret_cast<const float4*>(src) + c);
+                            rx[q][1] = __ldg(reinterpret_cast<const float4*>(src) + 8 + c);
+                        } else {
+                            float t[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { const int p = (e < 4 ? 4 * c + e : 28 + 4 * c + e); t[e] = (n0 + p < N) ? __ldg(src + p) : 0.f; }
+                            rx[q][0] = make_float4(t[0], t[1], t[2], t[3]);
+                            rx[q][1] = make_float4(t[4], t[5], t[6], t[7]);
+                        }
+                    }
+                }
+            };
+            fetch(b0);
             for (int64_t blk = b0; blk < b1; ++blk, ++bc) {
                 const uint32_t st = bc & 1;
                 const int64_t n0 = blk * SS_KB;
                 mbar_wait(&bars->empty[st], ((bc >> 1) & 1) ^ 1);         // the MMAs that read this stage (and zsT two blocks ago) are done
                 asm volatile("bar.sync 1, 256;" ::: "memory");            // everyone finished reading zsT / lse_s of the previous block
                 // (a) the block's data, transposed and scaled; the constant row
-                for (int idx = tid; idx < SS_KB * D; idx += 256) {
-                    const int p = idx / D, i = idx - p * D;
-                    const int64_t n = n0 + p;
-                    zsT[i * SS_ZLD + p] = n < N ? __ldg(Z + n * ldz + i) * sz : 0.f;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const int idx = tid + 256 * q;
+                    if (idx < SS_KB * D) { const int p = idx / D, i = idx - p * D; zsT[i * SS_ZLD + p] = zr[q] * sz; }
                 }
                 if (tid < SS_KB) {
                     zsT[D * SS_ZLD + tid] = (n0 + tid < N) ? SS_ONE : 0.f;
-                    lse_s[tid] = (lse != nullptr && n0 + tid < N) ? __ldg(lse + n0 + tid) : 0.f;
+                    lse_s[tid] = lr;
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 unsigned char* sA = smem + st * stage_bytes;
@@ -136,17 +171,12 @@ tc_sstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
                 // Operand slot s = 8 c + e of the block holds point 4 c + e (e < 4) or 32 + 4 c + e - 4: both tiles use the same
                 // order (the contraction does not care), and the eight lanes of a row then read 128 contiguous bytes.
                 // (b) responsibilities: item = (component row, 8-slot chunk), spread over all threads whatever K is
-                for (int item = tid; item < kt * 8; item += 256) {
-                    const int ca = item >> 3, c = item & 7;
-                    const float* src = R + (int64_t)(k0 + ca) * ldr + n0;
-                    float x[8];
-                    if (n0 + SS_KB <= N && rvec4) {
-                        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src) + c), v1 = __ldg(reinterpret_cast<const float4*>(src) + 8 + c);
-                        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-                    } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) { const int p = (e < 4 ? 4 * c + e : 28 + 4 * c + e); x[e] = (n0 + p < N) ? __ldg(src + p) : 0.f; }
-                    }
+                for (int q = 0; q < 4; ++q) {
+                    const int item = tid + 256 * q;
+                    if (item >= kt * 8) break;
+                    const int ca = item >> 3, c = item & 7;
+                    float x[8] = {rx[q][0].x, rx[q][0].y, rx[q][0].z, rx[q][0].w, rx[q][1].x, rx[q][1].y, rx[q][1].z, rx[q][1].w};
                     if (lse != nullptr) {
                         const float4 l0 = *reinterpret_cast<const float4*>(lse_s + 4 * c), l1 = *reinterpret_cast<const float4*>(lse_s + 32 + 4 * c);
                         const float ll[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
@@ -161,6 +191,7 @@ tc_sstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
                     *reinterpret_cast<uint4*>(sA + o) = hi;
                     *reinterpret_cast<uint4*>(sA + SS_ATILE + o) = lo;
                 }
+                fetch(blk + 1);                                           // in flight while the features are formed
                 // (c) features: item = (feature f, 8-slot chunk c)
                 for (int item = tid; item < F * 8; item += 256) {
                     const int f = item >> 3, c = item & 7;
