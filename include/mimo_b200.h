@@ -117,6 +117,23 @@ int mimo_tc_screen_totals(uint64_t* out_host5);
 /* screening tier the most recent screened sweep ended on: 0 projection, 1 all operand rows, 2 none (dense); -1 unknown */
 int mimo_tc_screen_level(void);
 int mimo_sweep_uses_tensor_cores(int dtype, int family, int D, int Rp);
+/* ---- prediction path (mixtures/ilr.py:325-430) ----------------------------------------------------------------
+ * mimo_studentt_from_quad: a[k][n] <- add[k] + log1p(2 (c0[k] - a[k][n]) / df[k]), the reference's Student-t form
+ * (utils/stats.py:53-79) of a Gaussian-form log-joint a = c0 - delta/2 produced by mimo_loglik_quad.
+ * mimo_predict_lingauss: per point the posterior-predictive moments of the K linear-Gaussian experts
+ * (distributions/bayesian.py:876-912, 949-985: mu = M x~, c = 1 + x~^T K^-1 x~, Lambda = Psi df / c), combined with the
+ * predictive weights W (K, ldw) into the mixture mean / covariance (mode 0, ilr.py:375-383) or taken from the expert
+ * with the largest weight (mode 1); studentt scales the covariances by df / (df - 2); with Y the negative log
+ * predictive density (ilr.py:407-411) is written to nlpd_out.  M (K, o, c), Kinv (K, c, c), Sigma = Psi^-1 and Psi
+ * (K, o, o), logdet_psi and df (K) are FP64 device arrays (one entry instead of K when tied); c = din + affine;
+ * o <= 4.  Outputs mu (N, o), cov (N, o, o), nlpd (N) in dtype. */
+int mimo_studentt_from_quad(int dtype, void* a, int K, int64_t N, int64_t lda, const double* c0, const double* add, const double* df,
+                            void* stream);
+int mimo_predict_lingauss(int dtype, const void* X, int64_t N, int64_t ldx, int din, int affine, const void* W, int64_t ldw, int K,
+                          const double* M, const double* Kinv, const double* Sigma, const double* Psi, const double* logdet_psi,
+                          const double* df, int o, int tied, int mode, int studentt, const void* Y, int64_t ldy, double eps,
+                          void* mu_out, void* cov_out, void* nlpd_out, void* stream);
+
 /* Diagonal family on the tensor pipe (FP32, D <= 64, K <= 256): the log-density is linear in [z', z'^2] of the centred
  * point, i.e. one tcgen05 GEMM; labels (inverse CDF of `uniforms`, or Philox(seed, point_offset + n) when NULL) and the
  * log-normalisers come out of its epilogue.  Replaces distributions/gaussian.py:837-850, bayesian.py:446-460 and

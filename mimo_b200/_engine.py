@@ -210,6 +210,31 @@ def loglik_diag_tc(Z, ops, out=False, labels=False, lse=False, lse_sum=False, un
     return dict(out=out_t, labels=lab_t, lse=lse_t, lse_sum=sum_t, guard=int(guard[0]))
 
 
+def studentt_from_quad(a, precision, c0, add, df):
+    """In place: a[k][n] <- add[k] + log1p(2 (c0[k] - a[k][n]) / df[k])   (utils/stats.py:53-79 from a Gaussian-form log-joint)."""
+    K, n = a.shape
+    dev = [to_dev(np.ascontiguousarray(np.broadcast_to(t, (K,)), dtype=np.float64)) for t in (c0, add, df)]   # kept alive over the call
+    _lib.call('mimo_studentt_from_quad', code(precision), ptr(a), K, n, a.stride(0), ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), stream())
+    return a
+
+
+def predict_lingauss(X, W, M, Kinv, Sigma, Psi, logdet_psi, df, affine, mode, studentt, precision, Y=None, eps=0.0):
+    """Posterior-predictive moments of K linear-Gaussian experts combined with the weights W (K, N): (mu (N, o),
+    cov (N, o, o), nlpd (N) or None), all on the device (mixtures/ilr.py:352-411)."""
+    N, din = X.shape
+    K, o, c = M.shape
+    dt = tdtype(precision)
+    assert X.dtype == dt and W.dtype == dt and W.shape == (K, N) and c == din + (1 if affine else 0)
+    tied = 0                                   # the mirror classes hand over stacked (K, ...) parameters also for tied experts
+    dev = [to_dev(np.ascontiguousarray(t, dtype=np.float64)) for t in (M, Kinv, Sigma, Psi, np.atleast_1d(logdet_psi), np.atleast_1d(df))]
+    mu, cov = empty((N, o), dt), empty((N, o, o), dt)
+    nlpd = empty((N,), dt) if Y is not None else None
+    _lib.call('mimo_predict_lingauss', code(precision), ptr(X), N, X.stride(0), din, int(bool(affine)), ptr(W), W.stride(0), K,
+              ptr(dev[0]), ptr(dev[1]), ptr(dev[2]), ptr(dev[3]), ptr(dev[4]), ptr(dev[5]), o, tied, int(mode), int(bool(studentt)),
+              ptr(Y), Y.stride(0) if Y is not None else 0, float(eps), ptr(mu), ptr(cov), ptr(nlpd), stream())
+    return mu, cov, nlpd
+
+
 def softmax(a, precision, resp=False, lse=False, labels=False, lse_sum=False, uniforms=None, seed=0, offset=0):
     """In-place softmax / label draw over a (K, n) log-joint.  Returns a dict."""
     K, n = a.shape

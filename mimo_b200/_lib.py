@@ -20,7 +20,8 @@ OK, EINVAL, ECUDA, ENOTPD, EUNSUPPORTED = 0, 1, 2, 3, 4
 F32, F64 = 0, 1
 WRITE_RESP, WRITE_LSE, DRAW_LABELS, ACC_LSE = 1, 2, 4, 8
 
-_T = {'i': ctypes.c_int, 'l': ctypes.c_int64, 'p': ctypes.c_void_p, 'z': ctypes.c_size_t, 'u': ctypes.c_uint64}
+_T = {'i': ctypes.c_int, 'l': ctypes.c_int64, 'p': ctypes.c_void_p, 'z': ctypes.c_size_t, 'u': ctypes.c_uint64,
+      'd': ctypes.c_double}
 
 def _parse_header():
     """Read the prototypes from include/mimo_b200.h so the binding cannot drift from it:
@@ -46,6 +47,8 @@ def _parse_header():
                     codes += 'z'
                 elif prm.startswith('int'):
                     codes += 'i'
+                elif prm.startswith('double'):
+                    codes += 'd'
                 else:
                     raise ValueError('unhandled parameter %r in %s' % (prm, name))
         sigs[name] = ('s' if '*' in res else ('z' if res == 'size_t' else 'i'), codes)

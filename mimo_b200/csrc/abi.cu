@@ -74,6 +74,17 @@ int mimo_loglik_diag_tc(const void* Z, int64_t N, int D, int64_t ldz, const void
     }
     return MIMO_OK;
 }
+int mimo_studentt_from_quad(int dtype, void* a, int K, int64_t N, int64_t lda, const double* c0, const double* add, const double* df,
+                            void* stream) {
+    return studentt_from_quad(dtype, a, K, N, lda, c0, add, df, ST(stream));
+}
+int mimo_predict_lingauss(int dtype, const void* X, int64_t N, int64_t ldx, int din, int affine, const void* W, int64_t ldw, int K,
+                          const double* M, const double* Kinv, const double* Sigma, const double* Psi, const double* logdet_psi,
+                          const double* df, int o, int tied, int mode, int studentt, const void* Y, int64_t ldy, double eps,
+                          void* mu_out, void* cov_out, void* nlpd_out, void* stream) {
+    return predict_lingauss(dtype, X, N, ldx, din, affine, W, ldw, K, M, Kinv, Sigma, Psi, logdet_psi, df, o, tied, mode, studentt,
+                            Y, ldy, eps, mu_out, cov_out, nlpd_out, ST(stream));
+}
 int mimo_tc_diag_enable(int on) { return tc_diag_enable(on); }
 int mimo_tc_set_min_dim(int d) { return tc_set_min_dim(d); }
 int mimo_softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags, void* lse, const void* uniforms,

@@ -114,6 +114,14 @@ size_t stats_soft_tc_workspace(int64_t N, int K);
 int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K, int F,
                   double* stat, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// prediction path of the linear-Gaussian mixtures (predict.cu)
+int studentt_from_quad(int dtype, void* a, int K, int64_t N, int64_t lda, const double* c0, const double* add, const double* df,
+                       cudaStream_t st);
+int predict_lingauss(int dtype, const void* X, int64_t N, int64_t ldx, int din, int affine, const void* W, int64_t ldw, int K,
+                     const double* M, const double* Kinv, const double* Sig, const double* Psi, const double* logdet, const double* df,
+                     int o, int tied, int mode, int studentt, const void* Y, int64_t ldy, double eps,
+                     void* mu_out, void* cov_out, void* nlpd_out, cudaStream_t st);
+
 // statistics over (component, point) lists grouped by component (pair_stats.cu): hard labels / screened candidates
 constexpr int PS_SLAB = 1024;        // listed points of one component per work item
 bool pair_stats_supported(int dtype, int D, int F);

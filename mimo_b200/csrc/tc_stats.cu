@@ -297,7 +297,7 @@ int tc_stats_begin(int64_t chunk_points, int K, void* ws, cudaStream_t st) {
 }
 
 static int g_flush_tiles = 16;
-void tc_set_flush_tiles(int t) { g_flush_tiles = t < 1 ? 1 : t; }
+void tc_set_flush_tiles(int t) { g_flush_tiles = t < 1 ? 16 : t; }
 
 // one chunk of points: accumulates into the partial buffer (plan of `plan_points`, the sweep's chunk size)
 int tc_stats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* R, int64_t ldr, int K, int F,

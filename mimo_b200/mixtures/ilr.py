@@ -8,7 +8,7 @@ single pass of the same fused sweep the GMM uses, and their sufficient statistic
 sub-blocks of one packed second-moment matrix of [x | y | 1]."""
 import numpy as np
 import numpy.random as npr
-from scipy.special import logsumexp
+from scipy.special import logsumexp, gammaln
 from tqdm import tqdm
 
 from .. import _engine as E
@@ -328,27 +328,57 @@ class BayesianMixtureOfLinearGaussians:
             + self.variational_lowerbound_labels(resp)
 
     # -- prediction (ilr.py:325-430) -----------------------------------------------------------
-    def meanfield_predictive_weights(self, x, dist='gaussian'):
-        """softmax_k( log E[pi_k] + log N(x; posterior-predictive basis_k) ) on the GPU."""
-        if dist != 'gaussian':
-            raise NotImplementedError("only dist='gaussian' is implemented")
+    def _predictive_weights_dev(self, x, dist):
+        """softmax_k( log E[pi_k] + log p(x; posterior-predictive basis_k) ) as a (K, N) device tensor: the Gaussian form
+        through the E-step kernel, the Student-t form (utils/stats.py:53-79) by a device transform of its output."""
+        if dist not in ('gaussian', 'studentt'):
+            raise NotImplementedError(dist)
         mus, lmbdas = self.basis.posterior_predictive_gaussian()
         precision = self.precision or E.default_precision()
-        ops = E.QuadOperands(self.size, self.input_dim, self.input_dim, precision)
-        E.set_log_weights(ops, np.log(self.gating.posterior.mean()))
+        d = self.input_dim
+        ops = E.QuadOperands(self.size, d, d, precision)
+        log_gating = np.log(self.gating.posterior.mean())
+        E.set_log_weights(ops, log_gating if dist == 'gaussian' else np.zeros(self.size))
         E.operands_gauss(ops, E.to_dev(mus), E.to_dev(lmbdas)).check()
-        a = E.loglik(E.to_dev(np.reshape(x, (-1, self.input_dim)), E.tdtype(precision)), ops)
+        a = E.loglik(E.to_dev(np.reshape(x, (-1, d)), E.tdtype(precision)), ops)
+        if dist == 'studentt':
+            dfs = self.basis.posterior_predictive_studentt()[2]
+            half_logdet = 0.5 * np.linalg.slogdet(lmbdas)[1]
+            c0 = half_logdet - 0.5 * d * np.log(2. * np.pi)                 # constant of the Gaussian form the kernel produced
+            aux = gammaln((dfs + d) / 2.) - gammaln(dfs / 2.) + half_logdet - (d / 2.) * np.log(dfs * np.pi) - 0.5 * (dfs + d)
+            E.studentt_from_quad(a, precision, c0, log_gating + aux, dfs)
         E.softmax(a, precision, resp=True)
-        return E.to_host(a).astype(np.float64)
+        return a
+
+    def meanfield_predictive_weights(self, x, dist='gaussian'):
+        return E.to_host(self._predictive_weights_dev(x, dist)).astype(np.float64)
 
     def meanfield_predictive_activation(self, x, dist='gaussian'):
         return self.meanfield_predictive_weights(self._scaled(x), dist)
 
     def meanfield_predictive_moments(self, x, dist='gaussian'):
-        if dist != 'gaussian':
-            raise NotImplementedError("only dist='gaussian' is implemented")
-        mus, lmbdas = self.models.posterior_predictive_gaussian(x)
-        return mus, np.linalg.inv(lmbdas)
+        """Per-expert moments (K, N, o), (K, N, o, o) as the reference returns them (API use at plotting sizes; the
+        prediction itself combines them on the device without building these arrays)."""
+        if dist == 'gaussian':
+            mus, lmbdas = self.models.posterior_predictive_gaussian(x)
+            return mus, np.linalg.inv(lmbdas)
+        if dist != 'studentt':
+            raise NotImplementedError(dist)
+        mus, lmbdas, dfs = self.models.posterior_predictive_studentt(x)
+        dfs = np.broadcast_to(dfs, (self.size,))
+        return mus, np.einsum('kndl,k->kndl', np.linalg.inv(lmbdas), dfs / (dfs - 2))
+
+    def meanfiled_log_predictive_likelihood(self, x, y, dist='gaussian'):
+        mus, lmbdas = self.models.posterior_predictive_gaussian(x)[:2]
+        diff = np.reshape(y, (-1, self.output_dim))[None, :, :] - mus
+        delta = np.einsum('knd,kndl,knl->kn', diff, lmbdas, diff)
+        if dist == 'gaussian':
+            return -0.5 * delta + 0.5 * np.linalg.slogdet(lmbdas)[1] - 0.5 * self.output_dim * np.log(2. * np.pi)
+        dfs = np.broadcast_to(self.models.posterior_predictive_studentt(x)[2], (self.size,))[:, None]
+        o = self.output_dim
+        aux = gammaln((dfs + o) / 2.) - gammaln(dfs / 2.) + 0.5 * np.linalg.slogdet(lmbdas)[1] \
+            - (o / 2.) * np.log(dfs * np.pi) - 0.5 * (dfs + o)
+        return aux + np.log1p(delta / dfs)
 
     @staticmethod
     def mixture_moments(mus, covars, weights):
@@ -359,27 +389,29 @@ class BayesianMixtureOfLinearGaussians:
 
     def meanfield_prediction(self, x, y=None, prediction='average', dist='gaussian',
                              incremental=False, variance='diagonal'):
+        """ilr.py:384-430.  Weights (E-step kernel + softmax), expert moments, their mixture / mode and the negative log
+        predictive density all stay on the device (mimo_predict_lingauss); only (N, o)-sized results come back."""
+        if prediction not in ('mode', 'average'):
+            raise NotImplementedError
         x = np.reshape(x, (-1, self.input_dim))
         xx = self._scaled(x)
-        weights = self.meanfield_predictive_weights(xx, dist)
-        mus, covars = self.meanfield_predictive_moments(xx, dist)
-        if prediction == 'mode':
-            k = np.argmax(weights, axis=0)
-            idx = (k, range(len(k)), ...)
-            mu, covar = mus[idx], covars[idx]
-        elif prediction == 'average':
-            mu, covar = self.mixture_moments(mus, covars, weights)
-        else:
-            raise NotImplementedError
-        nlpd = None
+        precision = self.precision or E.default_precision()
+        W = self._predictive_weights_dev(xx, dist)
+        Ms, Ks, psis, nus = self.models.posterior.params
+        o = self.output_dim
+        K = self.size
+        psis = np.ascontiguousarray(np.broadcast_to(psis, (K, o, o)))
+        dfs = np.broadcast_to(np.asarray(nus, dtype=np.float64) - self.models.likelihood.row_dim + 1, (K,))
+        yy = None
         if y is not None:
             yy = np.reshape(y, (-1, self.output_dim))
             yy = self.output_transform.transform(yy) if self.scale else yy
-            m, l = self.models.posterior_predictive_gaussian(xx)
-            diff = yy[None, :, :] - m
-            log_pl = -0.5 * np.einsum('knd,kndl,knl->kn', diff, l, diff) \
-                + 0.5 * np.linalg.slogdet(l)[1] - 0.5 * self.output_dim * np.log(2. * np.pi)
-            nlpd = -1.0 * logsumexp(log_pl + np.log(weights + eps), axis=0)
+        mu, covar, nlpd = E.predict_lingauss(
+            E.to_dev(xx, E.tdtype(precision)), W, Ms, np.linalg.inv(Ks), np.linalg.inv(psis), psis, np.linalg.slogdet(psis)[1],
+            dfs, self.models.likelihood.affine, 0 if prediction == 'average' else 1, dist == 'studentt', precision,
+            Y=None if yy is None else E.to_dev(yy, E.tdtype(precision)), eps=eps)
+        mu, covar = E.to_host(mu).astype(np.float64), E.to_host(covar).astype(np.float64)
+        nlpd = None if nlpd is None else E.to_host(nlpd).astype(np.float64)
         if self.scale:
             mu = self.output_transform.inverse_transform(mu)
             mat = np.diag(np.sqrt(self.output_transform.var_))

@@ -312,6 +312,15 @@ def ilr_case(name, x, y, K, tied, seed, sweeps=2, iters=3):
     rec['vlb'] = np.array(vlbs)
     mu, var, std = ilr.meanfield_prediction(x[:32], prediction='average')
     rec['pred_mu'], rec['pred_var'] = mu, var
+    # the branches of the prediction path (ilr.py:325-430) the reference can run: Gaussian weights and moments, mixture /
+    # mode.  Its Student-t branches (stats.py:79 divides (K, N) by (K,); ilr.py:358 contracts a 4-D array as 'ndl') and its
+    # NLPD branch (bayesian.py:964-966 feeds per-point precisions to stacked_mvn_logpdf) raise broadcasting errors for
+    # every K != N, so no fixture can exist for them: tests check those against oracle/mimo_oracle.py's restatement with
+    # the evident broadcasting.
+    rec['pred_weights_gaussian'] = ilr.meanfield_predictive_weights(x[:48], 'gaussian')
+    for pred in ('average', 'mode'):
+        mu, cov, std = ilr.meanfield_prediction(x[:48].copy(), prediction=pred, dist='gaussian', variance='full')
+        rec[f'pred_gaussian_{pred}_mu'], rec[f'pred_gaussian_{pred}_cov'] = mu, cov
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
     print(name, 'ok', 'vlb monotone:', bool(np.all(np.diff(vlbs) >= -1e-8)))
 

@@ -610,6 +610,64 @@ def vlb_labels_stick(resp, E_stick, E_rest):
         return np.sum(resp * E_stick[:, None] + acc * E_rest[:, None]) - np.nansum(resp * np.log(resp))
 
 
+# ---- prediction path (mixtures/ilr.py:325-430) ------------------------------------------------------------------
+def nw_predictive(mus, kappas, psis, nus):
+    """distributions/bayesian.py:303-308, 314-320: (mus, lmbdas, dfs) of the Normal-Wishart posterior predictive."""
+    d = mus.shape[-1]
+    dfs = nus - d + 1
+    return mus, (dfs / (1. + 1. / kappas))[:, None, None] * psis, dfs
+
+
+def studentt_loglik_reference_form(x, mus, lmbdas, dfs):
+    """utils/stats.py:67-79 with the broadcasting the shapes call for (the reference divides a (K, N) array by a (K,)
+    vector and raises for K != N).  The form is the reference's own: the -(df + d)/2 factor sits in the constant."""
+    d = mus.shape[-1]
+    xc = x[:, None, :] - mus[None, :, :]
+    deltas = np.einsum('nkd,kdl,nkl->kn', xc, lmbdas, xc)
+    aux = gammaln((dfs + d) / 2.) - gammaln(dfs / 2.) + 0.5 * np.linalg.slogdet(lmbdas)[1] \
+        - (d / 2.) * np.log(dfs * np.pi) - 0.5 * (dfs + d)
+    return aux[:, None] + np.log1p(deltas / dfs[:, None])
+
+
+def ilr_predictive_weights(x, gating_mean, basis_post, dist='gaussian'):
+    """ilr.py:337-346."""
+    mus, lmbdas, dfs = nw_predictive(*basis_post)
+    lp = gauss_full_loglik(x, mus, lmbdas) if dist == 'gaussian' else studentt_loglik_reference_form(x, mus, lmbdas, dfs)
+    return responsibilities(np.log(gating_mean)[:, None] + lp)[0]
+
+
+def mnw_predictive(x, Ms, Ks, psis, nus, affine=True):
+    """bayesian.py:949-985: mus (K, N, o), lmbdas (K, N, o, o), dfs (K,)."""
+    xt = _augment(x, affine)
+    o = Ms.shape[1]
+    dfs = nus - o + 1
+    mus = np.einsum('kdl,nl->knd', Ms, xt)
+    cs = 1. + np.einsum('nd,kdl,nl->kn', xt, np.linalg.inv(Ks), xt)
+    return mus, np.einsum('kdl,k,kn->kndl', psis, dfs, 1. / cs), dfs
+
+
+def ilr_prediction(x, weights, models_post, prediction='average', dist='gaussian', y=None, eps=np.finfo(np.float64).tiny):
+    """ilr.py:348-411 with the evident shapes: (mu (N, o), covar (N, o, o), nlpd (N) or None)."""
+    mus, lmbdas, dfs = mnw_predictive(x, *models_post)
+    covars = np.linalg.inv(lmbdas)
+    if dist == 'studentt':
+        covars = covars * (dfs / (dfs - 2))[:, None, None, None]
+    if prediction == 'mode':
+        k = np.argmax(weights, axis=0)
+        n = np.arange(len(k))
+        mu, covar = mus[k, n], covars[k, n]
+    else:
+        mu = np.einsum('knd,kn->nd', mus, weights)
+        covar = np.einsum('kndl,kn->ndl', covars + np.einsum('knd,knl->kndl', mus, mus), weights) - np.einsum('nd,nl->ndl', mu, mu)
+    nlpd = None
+    if y is not None:
+        diff = y[None, :, :] - mus
+        o = mus.shape[-1]
+        log_pl = -0.5 * np.einsum('knd,kndl,knl->kn', diff, lmbdas, diff) + 0.5 * np.linalg.slogdet(lmbdas)[1] - 0.5 * o * np.log(2. * np.pi)
+        nlpd = -logsumexp(log_pl + np.log(weights + eps), axis=0)
+    return mu, covar, nlpd
+
+
 def chunked(fn, n, chunk):
     """Apply fn(slice) over point chunks and concatenate along the point axis
     (axis 1 for (K,N) outputs).  Exact: every per-point quantity is

@@ -1,0 +1,75 @@
+"""Worker of tests/test_gpu_multirank.py (launched under torch.distributed.run, one rank per GPU): the data-sharded
+Session -- all-reduce of the packed statistics, posterior update split over the ranks (Session._component_shard), operand
+all-gather -- must reproduce the single-process run of the same model on the whole data set.  Rank 0 writes the verdict."""
+import json
+import os
+import sys
+
+import numpy as np
+import numpy.random as npr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def build_model(K, d, precision):
+    from mimo_b200.distributions import (StackedNormalWisharts, StackedGaussiansWithNormalWisharts, TruncatedStickBreaking,
+                                         CategoricalWithStickBreaking)
+    from mimo_b200.mixtures import BayesianMixtureOfGaussians
+    prior = StackedNormalWisharts(K, d, mus=np.zeros((K, d)), kappas=1e-2 * np.ones(K), psis=np.stack(K * [np.eye(d)]),
+                                  nus=(d + 1) * np.ones(K) + 1e-8)
+    comps = StackedGaussiansWithNormalWisharts(K, d, prior=prior)
+    gating = CategoricalWithStickBreaking(K, TruncatedStickBreaking(K, np.ones(K), 2.0 * np.ones(K)))
+    return BayesianMixtureOfGaussians(gating=gating, components=comps, precision=precision)
+
+
+def main():
+    out_path = sys.argv[1]
+    import torch
+    from mimo_b200.sharded import Communicator, init_from_env, shard_bounds
+    rank, world = init_from_env()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    results = {}
+    for precision, K, d, N in (('fp64', 8, 6, 40000), ('fp32', 64, 32, 60000)):
+        rng = np.random.default_rng(11)
+        centres = 3.0 * rng.standard_normal((K, d))
+        x = centres[rng.integers(0, K, N)] + rng.standard_normal((N, d))
+        lo, hi = shard_bounds(N, rank, world)
+        # sharded run: every rank its shard
+        npr.seed(3)
+        m_sh = build_model(K, d, precision)
+        comm = Communicator(N_global=N)
+        vlb_sh = m_sh.meanfield_coordinate_descent(x[lo:hi], randomize='device', maxiter=4, tol=0., progress_bar=False, comm=comm)
+        # single-process run of the whole data set on this rank's GPU (no communicator)
+        npr.seed(3)
+        m_1 = build_model(K, d, precision)
+        vlb_1 = m_1.meanfield_coordinate_descent(x, randomize='device', maxiter=4, tol=0., progress_bar=False)
+        tol = 1e-9 if precision == 'fp64' else 1e-5          # lower bound; parameters: 10x (FP32: the north-star 1e-4)
+        err = {}
+        err['vlb'] = float(np.max(np.abs(np.array(vlb_sh) - np.array(vlb_1)) / np.abs(np.array(vlb_1))))
+        for name, a, b in zip(('mus', 'kappas', 'psis', 'nus'), m_sh.components.posterior.params, m_1.components.posterior.params):
+            err[name] = float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+        err['gammas'] = float(np.max(np.abs(m_sh.gating.posterior.gammas - m_1.gating.posterior.gammas)) / np.max(np.abs(m_1.gating.posterior.gammas)))
+        results[precision] = dict(err=err, tol=tol, ok=bool(all(v <= tol * (10 if k != 'vlb' else 1) for k, v in err.items())),
+                                  messages=comm.messages)
+        # Gibbs: labels must not depend on the shard count (uniforms drawn from rank 0's stream, Philox by global index)
+        npr.seed(5)
+        g_sh = build_model(K, d, precision)
+        g_sh.resample(x[lo:hi], init_labels='random', maxiter=2, progress_bar=False, comm=Communicator(N_global=N))
+        npr.seed(5)
+        g_1 = build_model(K, d, precision)
+        g_1.resample(x, init_labels='random', maxiter=2, progress_bar=False)
+        same = float(np.mean(np.asarray(g_sh.labels_) == np.asarray(g_1.labels_)[lo:hi]))
+        results[precision]['gibbs_label_agreement'] = same
+        results[precision]['ok'] = results[precision]['ok'] and same >= (1.0 if precision == 'fp64' else 0.995)
+    gathered = [None] * world
+    torch.distributed.all_gather_object(gathered, results)
+    if rank == 0:
+        with open(out_path, 'w') as f:
+            json.dump(gathered, f)
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

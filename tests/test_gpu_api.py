@@ -208,6 +208,32 @@ def test_ilr_gibbs_then_meanfield_replays_reference(name):
         mu, var, std = ilr.meanfield_prediction(g['x'][:32], prediction='average')
         close(mu, g['pred_mu'], 1e-7, 'prediction mean')
         close(var, g['pred_var'], 1e-7, 'prediction variance')
+        # every branch of the prediction path (ilr.py:325-430), moments combined on the device
+        x48, y48 = g['x'][:48], g['y'][:48]
+        close(ilr.meanfield_predictive_weights(x48, 'gaussian'), g['pred_weights_gaussian'], 1e-7, 'predictive weights')
+        for pred in ('average', 'mode'):
+            mu, cov, std = ilr.meanfield_prediction(x48, prediction=pred, dist='gaussian', variance='full')
+            close(mu, g[f'pred_gaussian_{pred}_mu'], 1e-7, 'prediction mean (%s)' % pred)
+            close(cov, g[f'pred_gaussian_{pred}_cov'], 1e-7, 'prediction covariance (%s)' % pred)
+        # Student-t weights / moments and the NLPD: the reference raises broadcasting errors on these branches (see
+        # oracle/make_golden.py), so the check is against the oracle's restatement with the evident shapes
+        K = int(g['K'])
+        bpost = ilr.basis.posterior.params
+        mp = ilr.models.posterior.params
+        mpost = (mp[0], mp[1], np.broadcast_to(mp[2], (K,) + np.shape(mp[2])[-2:]), np.broadcast_to(mp[3], (K,)))
+        gmean = ilr.gating.posterior.mean()
+        for dist in ('gaussian', 'studentt'):
+            w_ref = orc.ilr_predictive_weights(x48, gmean, bpost, dist)
+            close(ilr.meanfield_predictive_weights(x48, dist), w_ref, 1e-7, 'predictive weights (%s)' % dist)
+            mus_k, covs_k = ilr.meanfield_predictive_moments(x48, dist)
+            for pred in ('average', 'mode'):
+                mu_r, cov_r, nlpd_r = orc.ilr_prediction(x48, w_ref, mpost, pred, dist, y=y48)
+                mu, cov, std, nlpd = ilr.meanfield_prediction(x48, y48, prediction=pred, dist=dist, variance='full')
+                close(mu, mu_r, 1e-7, 'prediction mean (%s, %s)' % (dist, pred))
+                close(cov, cov_r, 1e-7, 'prediction covariance (%s, %s)' % (dist, pred))
+                close(nlpd, nlpd_r, 1e-7, 'NLPD (%s, %s)' % (dist, pred))
+            mu_m, cov_m = ilr.mixture_moments(mus_k, covs_k, w_ref)
+            close(mu_m, orc.ilr_prediction(x48, w_ref, mpost, 'average', dist)[0], 1e-9, 'per-expert moments (%s)' % dist)
     finally:
         mimo_b200.set_default_precision('fp32')
 

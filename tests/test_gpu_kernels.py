@@ -160,6 +160,48 @@ def test_loglik_diag_tc_guard():
     assert np.array_equal(buf.labels.cpu().numpy()[safe], orc.sample_discrete_from_log(ref, u)[safe])
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'fp64'])
+@pytest.mark.parametrize('K,din,o', [(6, 1, 1), (17, 8, 1), (5, 3, 2)])
+def test_predict_lingauss_kernel(precision, K, din, o):
+    """mimo_predict_lingauss / mimo_studentt_from_quad against the oracle's restatement of ilr.py:325-430."""
+    E = eng()
+    rng = np.random.default_rng(K + din)
+    N, c = 300, din + 1
+    x = rng.standard_normal((N, din)) * 2
+    y = rng.standard_normal((N, o))
+    Ms = rng.standard_normal((K, o, c))
+    Ks = np.stack([spd(rng, c) for _ in range(K)])
+    psis = np.stack([spd(rng, o) for _ in range(K)])
+    nus = o + 2.5 + 3 * rng.random(K)
+    w = rng.dirichlet(np.ones(K), size=N).T
+    tol = 1e-9 if precision == 'fp64' else 1e-4
+    dt = E.tdtype(precision)
+    X, W, Y = E.to_dev(x, dt), E.to_dev(w, dt), E.to_dev(y, dt)
+    xr, wr, yr = X.double().cpu().numpy(), W.double().cpu().numpy(), Y.double().cpu().numpy()
+    for dist in ('gaussian', 'studentt'):
+        for mode, pred in ((0, 'average'), (1, 'mode')):
+            mu, cov, nlpd = E.predict_lingauss(X, W, Ms, np.linalg.inv(Ks), np.linalg.inv(psis), psis, np.linalg.slogdet(psis)[1],
+                                               nus - o + 1, True, mode, dist == 'studentt', precision, Y=Y, eps=1e-300)
+            mu_r, cov_r, nlpd_r = orc.ilr_prediction(xr, wr, (Ms, Ks, psis, nus), pred, dist, y=yr, eps=1e-300)
+            close(mu, mu_r, tol, 'mean %s %s' % (dist, pred))
+            close(cov, cov_r, tol, 'covariance %s %s' % (dist, pred))
+            close(nlpd, nlpd_r, tol, 'nlpd %s %s' % (dist, pred))
+    # Student-t form of a Gaussian-form log-joint
+    d = din
+    mus = rng.standard_normal((K, d))
+    lmbdas = np.stack([spd(rng, d) for _ in range(K)])
+    dfs = 3.0 + rng.random(K)
+    ops = E.QuadOperands(K, d, d, precision)
+    E.set_log_weights(ops, np.zeros(K))
+    E.operands_gauss(ops, E.to_dev(mus), E.to_dev(lmbdas)).check()
+    a = E.loglik(X, ops)
+    half_logdet = 0.5 * np.linalg.slogdet(lmbdas)[1]
+    from scipy.special import gammaln
+    aux = gammaln((dfs + d) / 2.) - gammaln(dfs / 2.) + half_logdet - (d / 2.) * np.log(dfs * np.pi) - 0.5 * (dfs + d)
+    E.studentt_from_quad(a, precision, half_logdet - 0.5 * d * np.log(2 * np.pi), aux, dfs)
+    close(a, orc.studentt_loglik_reference_form(xr, mus, lmbdas, dfs), tol * 10, 'Student-t form')
+
+
 def test_philox_labels_independent_of_chunking():
     E = eng()
     rng = np.random.default_rng(8)

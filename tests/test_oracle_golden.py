@@ -163,6 +163,25 @@ def test_ilr_phases(name):
         close(vlb, g['vlb'][t], 1e-8)
 
 
+@pytest.mark.parametrize('name', ['ilr_tied', 'ilr_stacked', 'ilr_stacked_o2'])
+def test_ilr_prediction(name):
+    """ilr.py:325-430 on the posteriors of the last mean-field iteration: predictive weights, mixture / mode moments."""
+    g = load(name)
+    T = int(g['iters']) - 1
+    x = g['x'][:48]
+    bpost = tuple(g[f'vi_b_post_{n}_{T}'] for n in ('mus', 'kappas', 'psis', 'nus'))
+    mpost = tuple(g[f'vi_m_post_{n}_{T}'] for n in ('Ms', 'Ks', 'psis', 'nus'))
+    K = int(g['K'])
+    mpost = mpost[:2] + (np.broadcast_to(mpost[2], (K,) + mpost[2].shape[-2:]), np.broadcast_to(mpost[3], (K,)))
+    gmean = orc.stick_mean(g[f'vi_gate_gammas_{T}'], g[f'vi_gate_deltas_{T}'])
+    w = orc.ilr_predictive_weights(x, gmean, bpost, 'gaussian')
+    close(w, g['pred_weights_gaussian'], 1e-9)
+    for pred in ('average', 'mode'):
+        mu, cov, _ = orc.ilr_prediction(x, w, mpost, pred, 'gaussian')
+        close(mu, g[f'pred_gaussian_{pred}_mu'], 1e-9)
+        close(cov, g[f'pred_gaussian_{pred}_cov'], 1e-9)
+
+
 def test_em_trajectory():
     g = load('gmm_toy_em')
     x, K = g['obs'], int(g['K'])

@@ -4,6 +4,7 @@
   python tools/ncu_summary.py launches <launches.csv> <out.md>     # per-kernel totals / shares from a
                                                                     # gpu__time_duration.sum launch list
   python tools/ncu_summary.py full <report.ncu-rep> <out.md>       # key counters of a --set full capture
+  python tools/ncu_summary.py mix <report.ncu-rep> <out.md>        # APPEND instruction mix + top stall sites (source page)
 """
 import csv
 import io
@@ -63,5 +64,39 @@ def full(path, out):
                     f.write('| %s | %s | %s |\n' % (k, r[hdr.index(k)], units[hdr.index(k)]))
 
 
+def mix(path, out):
+    """append the warp-instruction mix and the top stall sites of each kernel (ncu --page source) to `out`"""
+    import collections
+    txt = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    blocks, cur = [], None
+    for r in rows:
+        if r and r[0] == 'Kernel Name':
+            cur = dict(name=short(r[1]), rows=[])
+            blocks.append(cur)
+        elif cur is not None:
+            cur['rows'].append(r)
+    with open(out, 'a') as f:
+        for b in blocks:
+            h = b['rows'][0]
+            ia, isamp, iex = h.index('Source'), h.index('# Samples'), h.index('Instructions Executed')
+            op, ops, data = collections.Counter(), collections.Counter(), []
+            for r in b['rows'][1:]:
+                if len(r) <= isamp:
+                    continue
+                toks = r[ia].split()
+                o = (toks[1] if toks and toks[0].startswith('@') else (toks[0] if toks else '')).split('.')[0]
+                op[o] += int(r[iex] or 0)
+                ops[o] += int(r[isamp] or 0)
+                data.append((int(r[isamp] or 0), int(r[iex] or 0), r[ia].strip()[:90]))
+            tot, ts = sum(op.values()), max(1, sum(ops.values()))
+            f.write('\n## %s: warp instructions by opcode (%.3g executed)\n\n| opcode | %% of instructions | %% of stall samples |\n|---|---|---|\n' % (b['name'], tot))
+            for o, c in op.most_common(14):
+                f.write('| %s | %.1f | %.1f |\n' % (o, 100.0 * c / tot, 100.0 * ops[o] / ts))
+            f.write('\ntop stall sites (samples, executions, SASS):\n\n')
+            for d in sorted(data, reverse=True)[:10]:
+                f.write('    %d  %d  %s\n' % d)
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {'launches': launches, 'full': full, 'mix': mix}[sys.argv[1]](sys.argv[2], sys.argv[3])
