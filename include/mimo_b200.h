@@ -117,6 +117,18 @@ int mimo_tc_screen_totals(uint64_t* out_host5);
 /* screening tier the most recent screened sweep ended on: 0 projection, 1 all operand rows, 2 none (dense); -1 unknown */
 int mimo_tc_screen_level(void);
 int mimo_sweep_uses_tensor_cores(int dtype, int family, int D, int Rp);
+/* ---- data-sharded sweeps: the one exchange step -------------------------------------------------------
+ * Sum over shards of the packed FP64 statistics (and the lower-bound scalar packed behind them): the reference's
+ * list-of-arrays semantics, distributions/gaussian.py:503-505, utils/abstraction.py:12-14.  NCCL is loaded at run time
+ * (dlopen "libnccl.so.2"); MIMO_EUNSUPPORTED when it is not installed.  Rank 0 calls mimo_comm_unique_id and hands the
+ * mimo_comm_unique_id_bytes() = 128 bytes to every rank out of band; every rank (one process per GPU, its device
+ * current) then calls mimo_comm_init; mimo_comm_allreduce_stats sums `count` doubles in place on `stream`. */
+size_t mimo_comm_unique_id_bytes(void);
+int mimo_comm_unique_id(void* out);
+int mimo_comm_init(int world, int rank, const void* unique_id, void** comm_out);
+int mimo_comm_allreduce_stats(void* comm, double* stat, int64_t count, void* stream);
+int mimo_comm_destroy(void* comm);
+
 /* ---- prediction path (mixtures/ilr.py:325-430) ----------------------------------------------------------------
  * mimo_studentt_from_quad: a[k][n] <- add[k] + log1p(2 (c0[k] - a[k][n]) / df[k]), the reference's Student-t form
  * (utils/stats.py:53-79) of a Gaussian-form log-joint a = c0 - delta/2 produced by mimo_loglik_quad.
@@ -145,6 +157,10 @@ int mimo_loglik_diag_tc(const void* Z, int64_t N, int D, int64_t ldz, const void
                         void* out, int64_t ldo, int32_t* labels, const void* uniforms, uint64_t seed, uint64_t point_offset,
                         void* lse, double* lse_sum, uint32_t* guard_host, void* workspace, size_t workspace_bytes, void* stream);
 int mimo_tc_diag_enable(int on);            /* A/B: 0 keeps diagonal sweeps on the CUDA cores; returns the old setting */
+/* One-shot hint for the NEXT mimo_sweep / mimo_sweep_timed of the calling thread: max |Z| over the data it will be given
+ * (>= the true maximum).  The tensor-core paths then skip their own pass over Z for the common power-of-two data scale
+ * -- for callers that keep the data resident and unchanged across sweeps (the Python Session does). */
+int mimo_sweep_absmax_hint(double absmax);
 int mimo_tc_set_min_dim(int d);             /* A/B: smallest D a quad-family sweep takes to the tensor pipe (default 8; 24 = round-1 behaviour); returns the old value */
 int mimo_tc_set_triangular(int rows);       /* dense E-step, 64 < D <= 128: rows per step of the triangular skip (16 default, 32; 0 = kernel with both operands in shared memory); returns the old value */
 int mimo_tc_set_flush_tiles(int tiles);     /* 128-point tiles accumulated in TMEM (FP32) between FP64 drains */

@@ -304,7 +304,7 @@ class SweepBuffers:
 
 
 def sweep(Z, ops, feats, buf, uniforms=None, seed=0, offset=0, ll_out=None, lse_out=None, zero=True,
-          phase_ms=None):
+          phase_ms=None, absmax=None):
     """One E-step + statistics pass over resident Z.  Results land in buf.stat,
     buf.lse_sum and (hard) buf.labels.  phase_ms: optional float64 numpy array (6,) that
     accumulates per-phase device milliseconds, the launch count and the chunk count (synchronises)."""
@@ -318,6 +318,8 @@ def sweep(Z, ops, feats, buf, uniforms=None, seed=0, offset=0, ll_out=None, lse_
     if N == 0:                      # an empty shard: nothing to add (an empty tensor has no device pointer to pass)
         return buf
     a, b, c, K, Rp, Dpp = ops.args()
+    if absmax is not None and absmax > 0:      # max |Z| of resident, unchanged data: the sweep skips its own pass over Z for it
+        _lib.call('mimo_sweep_absmax_hint', float(absmax))
     args = (code(ops.precision), ops.family, 1 if buf.hard else 0,
             ptr(Z), N, D, Z.stride(0), a, b, c, K, Rp, Dpp, ptr(fi), ptr(fj), feats.F,
             ptr(uniforms), int(seed), int(offset), ptr(buf.stat), ptr(buf.lse_sum), ptr(buf.labels),

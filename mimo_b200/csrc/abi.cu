@@ -85,6 +85,12 @@ int mimo_predict_lingauss(int dtype, const void* X, int64_t N, int64_t ldx, int 
     return predict_lingauss(dtype, X, N, ldx, din, affine, W, ldw, K, M, Kinv, Sigma, Psi, logdet_psi, df, o, tied, mode, studentt,
                             Y, ldy, eps, mu_out, cov_out, nlpd_out, ST(stream));
 }
+size_t mimo_comm_unique_id_bytes(void) { return comm_unique_id_bytes(); }
+int mimo_comm_unique_id(void* out) { return comm_unique_id(out); }
+int mimo_comm_init(int world, int rank, const void* unique_id, void** comm_out) { return comm_init(world, rank, unique_id, comm_out); }
+int mimo_comm_allreduce_stats(void* comm, double* stat, int64_t count, void* stream) { return comm_allreduce_stats(comm, stat, count, ST(stream)); }
+int mimo_comm_destroy(void* comm) { return comm_destroy(comm); }
+int mimo_sweep_absmax_hint(double absmax) { tc_set_absmax_hint((float)absmax); return MIMO_OK; }
 int mimo_tc_diag_enable(int on) { return tc_diag_enable(on); }
 int mimo_tc_set_min_dim(int d) { return tc_set_min_dim(d); }
 int mimo_softmax(int dtype, void* a, int K, int64_t n, int64_t ldo, int flags, void* lse, const void* uniforms,

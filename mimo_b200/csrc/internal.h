@@ -41,6 +41,7 @@ bool tc_estep_supported(int dtype, int D, int Rp);
 size_t tc_operand_workspace(int K, int Rp, int D);
 int tc_data_scale(const float* Z, int64_t N, int D, int64_t ldz, void* ws, cudaStream_t st);
 const unsigned int* tc_maxbits(void* ws);
+void tc_set_absmax_hint(float v);     // one-shot: the next tc_data_scale of this thread takes v instead of scanning Z
 int tc_prepare_operands(const float* W, const float* cst, int K, int Rp, int Dpp, int D, void* ws, cudaStream_t st);
 unsigned int* tc_flags(void* ws);    // [0] max |z| bits, [2] max_k ||W'_k||_F (screening operands), [3] max_n ||z_n||_2, [4] max_k ||W_k||_F (all columns)
 int tc_estep_pass(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, float* out, int64_t ldo, void* ws,
@@ -113,6 +114,13 @@ int tc_sstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* 
 size_t stats_soft_tc_workspace(int64_t N, int K);
 int stats_soft_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* resp, int64_t ldr, int K, int F,
                   double* stat, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// statistics all-reduce over NCCL, loaded at run time (comm.cu)
+size_t comm_unique_id_bytes();
+int comm_unique_id(void* out);
+int comm_init(int world, int rank, const void* unique_id, void** comm_out);
+int comm_allreduce_stats(void* comm, double* stat, int64_t count, cudaStream_t st);
+int comm_destroy(void* comm);
 
 // prediction path of the linear-Gaussian mixtures (predict.cu)
 int studentt_from_quad(int dtype, void* a, int K, int64_t N, int64_t lda, const double* c0, const double* add, const double* df,

@@ -20,6 +20,7 @@
 // zero lower-triangular blocks of Cholesky-factor operands with narrower MMAs was measured
 // slower on B200: with both operands in shared memory a 128 x N x 16 MMA is bound by the
 // 4 KB A-operand read, not by N.)
+#include <string.h>
 #include "tc_common.cuh"
 #include "internal.h"
 
@@ -336,10 +337,24 @@ size_t tc_operand_workspace(int K, int Rp, int D) { return tc_layout(K, Rp, D).b
 
 static char* align1k(void* p) { return (char*)(((uintptr_t)p + 1023) / 1024 * 1024); }
 
+// A caller that keeps the data resident across sweeps may pass max |Z| of that data (mimo_sweep_absmax_hint): the next
+// sweep of this thread then skips the pass over Z below (25.6 GB = 4.5 ms per sweep at N = 100M, d = 64).  One-shot.
+static thread_local float g_absmax_hint = 0.f;
+void tc_set_absmax_hint(float v) { g_absmax_hint = (v > 0.f && v < 3.0e38f) ? v : 0.f; }
+__global__ void tc_store_bits_kernel(unsigned int* dst, unsigned int bits) { *dst = bits; }
+
 // max |Z| over the resident data -> ws (the common power-of-two data scale of a sweep)
 int tc_data_scale(const float* Z, int64_t N, int D, int64_t ldz, void* ws, cudaStream_t st) {
     char* base = align1k(ws);
     MIMO_CUDA(cudaMemsetAsync(base, 0, 256, st));
+    if (g_absmax_hint > 0.f) {
+        unsigned int bits;
+        memcpy(&bits, &g_absmax_hint, 4);
+        g_absmax_hint = 0.f;
+        tc_store_bits_kernel<<<1, 1, 0, st>>>((unsigned int*)base, bits);
+        MIMO_LAUNCH_CHECK();
+        return MIMO_OK;
+    }
     if (N > 0) {
         int64_t total = N * (int64_t)D;
         int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);

@@ -50,6 +50,7 @@ class Session:
         self.gating_prior = gating._prior_dev() if gating is not None else None
         self.part_priors = [p.w._prior_dev() for p in parts]
         self.last = None
+        self._absmax = None
 
     # -- buffers ---------------------------------------------------------------------------
     def ops(self, mode):
@@ -215,8 +216,10 @@ class Session:
         if uniforms is not None:
             u = uniforms if isinstance(uniforms, torch.Tensor) else E.to_dev(np.asarray(uniforms).reshape(-1))
         offset = self.comm.point_offset if self.comm is not None else 0
+        if self._absmax is None:                 # the data are resident and never change: their scale is taken once
+            self._absmax = float(self.Z.abs().max().item()) if (self.N > 0 and self.precision == 'fp32') else 0.0
         E.sweep(self.Z, ops, self.feats, buf, uniforms=u, seed=seed, offset=offset, ll_out=ll_out,
-                phase_ms=phase_ms)
+                phase_ms=phase_ms, absmax=self._absmax)
         if self.comm is not None:
             self.comm.allreduce(buf.flat)
         self.stat, self.lse_sum = buf.stat, buf.lse_sum

@@ -40,6 +40,43 @@ class Communicator:
         return t
 
 
+class AbiCommunicator(Communicator):
+    """Same interface, the all-reduce through the library's own C-ABI (mimo_comm_*: NCCL loaded by the library at run
+    time) instead of torch.distributed -- what a caller that binds libmimo_b200.so without torch uses.  Here the 128-byte
+    unique id of rank 0 is handed out over the already initialised torch.distributed group."""
+
+    def __init__(self, N_global=None, group=None):
+        super().__init__(N_global, group)
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        nbytes = lib.mimo_comm_unique_id_bytes()
+        buf = (ctypes.c_char * nbytes)()
+        if self.rank == 0:
+            _lib.call('mimo_comm_unique_id', ctypes.addressof(buf))
+        box = [bytes(buf)]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self._id = ctypes.create_string_buffer(box[0], nbytes)
+        handle = ctypes.c_void_p()
+        _lib.call('mimo_comm_init', self.world, self.rank, ctypes.addressof(self._id), ctypes.addressof(handle))
+        self._handle = handle
+
+    def allreduce(self, t):
+        from . import _lib
+        assert t.dtype == torch.float64 and t.is_cuda and t.is_contiguous()
+        _lib.call('mimo_comm_allreduce_stats', self._handle, t.data_ptr(), t.numel(), torch.cuda.current_stream().cuda_stream)
+        self.messages += 1
+        self.bytes += t.numel() * t.element_size()
+        return t
+
+    def close(self):
+        from . import _lib
+        if self._handle:
+            _lib.call('mimo_comm_destroy', self._handle)
+            self._handle = None
+
+
 def init_from_env(backend=None):
     """torchrun-style initialisation (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*)."""
     world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -215,6 +215,41 @@ def gmm_vi_case(name, x, components, gating, iters, seed, diag=False):
     print(name, 'ok', 'vlb monotone:', bool(np.all(np.diff(vlbs) >= -1e-8)))
 
 
+def gmm_svi_case(name, x, components, gating, iters, batch_size, step_size, seed):
+    """mixtures/gmm.py:300-336 (stochastic variational inference): one minibatch per iteration drawn with Python's
+    `random.sample` (utils/data.py:9-12), natural-parameter blending in distributions/bayesian.py:85-91, 232-238, and the
+    full-data lower bound after every iteration.  Seeds: random.seed (minibatches), numpy.random.seed (the randomised
+    first responsibilities and the reference's trailing posterior.rvs() draws)."""
+    import random
+    model = M.BayesianMixtureOfGaussians(gating=gating, components=components)
+    K, d = model.size, model.dim
+    rec = dict(obs=x, K=K, d=d, seed=seed, iters=iters, batch_size=batch_size, step_size=step_size)
+    rec.update(gating_prior_arrays(gating))
+    for n, p in zip(('mus0', 'kappas0', 'psis0', 'nus0'), components.prior.params):
+        rec[n] = p
+    for n, p in zip(('pmus0', 'pkappas0', 'ppsis0', 'pnus0'), components.posterior.params):
+        rec[n] = p
+    # replay of the draws the run below makes, for the oracle test: batch indices and the first responsibilities
+    random.seed(seed)
+    npr.seed(seed)
+    rec['batches'] = np.array([random.sample(range(len(x)), batch_size) for _ in range(iters)])
+    r0 = npr.rand(K, batch_size)
+    rec['resp0'] = r0 / np.sum(r0, axis=0)
+    random.seed(seed)
+    npr.seed(seed)
+    vlb = model.meanfield_stochastic_descent(x, randomize=True, maxiter=iters, step_size=step_size, batch_size=batch_size,
+                                             progress_bar=False)
+    rec['vlb'] = np.array(vlb)
+    for n, p in zip(('mus', 'kappas', 'psis', 'nus'), components.posterior.params):
+        rec[f'post_{n}'] = p
+    if gating_kind(gating) == 'dirichlet':
+        rec['gate_alphas'] = gating.posterior.alphas
+    else:
+        rec['gate_gammas'], rec['gate_deltas'] = gating.posterior.gammas, gating.posterior.deltas
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'ok', 'vlb', vlb[0], '->', vlb[-1])
+
+
 def gmm_em_case(name, x, K, seed):
     """mixtures/gmm.py:77-103 (EM) on full-covariance components."""
     d = x.shape[1]
@@ -370,6 +405,8 @@ def main():
     gmm_gibbs_case('gmm_toy_gibbs', toy, *toy_model(), sweeps=3, seed=1337)
     gmm_vi_case('gmm_toy_vi', toy, *toy_model(), iters=6, seed=1337)
     gmm_vi_case('gmm_toy_vi_stick', toy, *toy_model('stick'), iters=4, seed=7)
+    gmm_svi_case('gmm_toy_svi', toy, *toy_model(), iters=8, batch_size=96, step_size=0.2, seed=5)
+    gmm_svi_case('gmm_toy_svi_stick', toy, *toy_model('stick'), iters=6, batch_size=64, step_size=0.1, seed=9)
     gmm_em_case('gmm_toy_em', toy, K, seed=3)
 
     # cfg4-shaped: full covariance d=16, stick-breaking DP-GMM

@@ -62,6 +62,19 @@ def main():
         same = float(np.mean(np.asarray(g_sh.labels_) == np.asarray(g_1.labels_)[lo:hi]))
         results[precision]['gibbs_label_agreement'] = same
         results[precision]['ok'] = results[precision]['ok'] and same >= (1.0 if precision == 'fp64' else 0.995)
+    # the same exchange through the library's own C-ABI (mimo_comm_*: NCCL loaded by the library, no torch in the call)
+    from mimo_b200.sharded import AbiCommunicator
+    abi = AbiCommunicator(N_global=1000)
+    g = torch.Generator(device=dev)
+    g.manual_seed(100 + rank)
+    t = torch.rand((64 * 561 + 1,), generator=g, device=dev, dtype=torch.float64)
+    ref = t.clone()
+    torch.distributed.all_reduce(ref)
+    abi.allreduce(t)
+    torch.cuda.synchronize()
+    results['abi_allreduce'] = dict(ok=bool(torch.equal(t, ref) or float((t - ref).abs().max()) <= 1e-12 * float(ref.abs().max())),
+                                    messages=abi.messages, err={})
+    abi.close()
     gathered = [None] * world
     torch.distributed.all_gather_object(gathered, results)
     if rank == 0:

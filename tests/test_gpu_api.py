@@ -371,6 +371,28 @@ def test_nonpd_raises_linalgerror():
         lik.log_likelihood(np.zeros((4, 2)))
 
 
+@pytest.mark.parametrize('name', ['gmm_toy_svi', 'gmm_toy_svi_stick'])
+def test_gmm_svi_trajectory_replays_reference(name, precision):
+    """mixtures/gmm.py:300-336 with the reference's seeds (random.seed: minibatches of utils/data.py:9-12; numpy.random.seed:
+    first responsibilities + trailing posterior.rvs() draws): lower-bound trajectory and final posteriors."""
+    import random
+    g = load(name)
+    model = make_gmm(g)
+    random.seed(int(g['seed']))
+    npr.seed(int(g['seed']))
+    vlb = model.meanfield_stochastic_descent(g['obs'], randomize=True, maxiter=int(g['iters']), step_size=float(g['step_size']),
+                                             batch_size=int(g['batch_size']), progress_bar=False)
+    tol = 1e-8 if precision == 'fp64' else 2e-4
+    close(vlb, g['vlb'], tol, 'SVI lower bound')
+    for key, ref in zip(model.components.posterior.params, ('mus', 'kappas', 'psis', 'nus')):
+        close(key, g[f'post_{ref}'], 10 * tol, 'SVI posterior ' + ref)
+    if 'gate_alphas' in g:
+        close(model.gating.posterior.alphas, g['gate_alphas'], 10 * tol, 'SVI alphas')
+    else:
+        close(model.gating.posterior.gammas, g['gate_gammas'], 10 * tol, 'SVI gammas')
+        close(model.gating.posterior.deltas, g['gate_deltas'], 10 * tol, 'SVI deltas')
+
+
 def test_svi_runs_and_improves():
     import mimo_b200
     mimo_b200.set_default_precision('fp64')

@@ -36,4 +36,4 @@ def test_two_rank_nccl_session_matches_single_process(tmp_path):
     for rank_result in verdict:
         for precision, res in rank_result.items():
             assert res['ok'], (precision, res)
-            assert res['messages'] >= 4
+            assert res['messages'] >= (1 if precision == 'abi_allreduce' else 4)

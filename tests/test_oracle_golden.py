@@ -163,6 +163,40 @@ def test_ilr_phases(name):
         close(vlb, g['vlb'][t], 1e-8)
 
 
+@pytest.mark.parametrize('name', ['gmm_toy_svi', 'gmm_toy_svi_stick'])
+def test_gmm_svi_trajectory(name):
+    """mixtures/gmm.py:300-336 + distributions/bayesian.py:85-91, 232-238: natural-parameter blending on one minibatch per
+    iteration, full-data lower bound after each."""
+    g = load(name)
+    x, K = g['obs'], int(g['K'])
+    step, scale = float(g['step_size']), int(g['batch_size']) / float(len(x))
+    prior = (g['mus0'], g['kappas0'], g['psis0'], g['nus0'])
+    post = (g['pmus0'], g['pkappas0'], g['ppsis0'], g['pnus0'])
+    stick = 'gate_gammas0' in g
+    gprior = (g['gate_gammas0'], g['gate_deltas0']) if stick else (g['gate_alphas0'],)
+    gpost = gprior
+
+    def log_weights(gp):
+        return orc.stick_expected_log(*gp)[0] if stick else orc.dirichlet_expected_log(gp[0])
+
+    vlbs = []
+    for i in range(int(g['iters'])):
+        xb = x[g['batches'][i]]
+        resp = g['resp0'] if i == 0 else orc.responsibilities(orc.nw_expected_loglik(xb, *post) + log_weights(gpost)[:, None])[0]
+        st = orc.gauss_full_wstats(xb, resp)
+        nat = [(1. - step) * a + step * (b + c / scale) for a, b, c in zip(orc.nw_std_to_nat(*post), orc.nw_std_to_nat(*prior), st)]
+        post = orc.nw_nat_to_std(nat)
+        counts = orc.categorical_wstats(resp) / scale
+        target = orc.stick_posterior(*gprior, counts) if stick else (orc.dirichlet_posterior(gprior[0], counts),)
+        gpost = tuple((1. - step) * a + step * b for a, b in zip(gpost, target))
+        _, lse = orc.responsibilities(orc.nw_expected_loglik(x, *post) + log_weights(gpost)[:, None])
+        vg = orc.stick_vlb(gprior, gpost) if stick else orc.dirichlet_vlb(gprior[0], gpost[0])
+        vlbs.append(vg + np.sum(orc.nw_vlb(prior, post)) + np.sum(lse))
+    close(np.array(vlbs), g['vlb'], 1e-9)
+    for a, n in zip(post, ('mus', 'kappas', 'psis', 'nus')):
+        close(a, g[f'post_{n}'], 1e-9)
+
+
 @pytest.mark.parametrize('name', ['ilr_tied', 'ilr_stacked', 'ilr_stacked_o2'])
 def test_ilr_prediction(name):
     """ilr.py:325-430 on the posteriors of the last mean-field iteration: predictive weights, mixture / mode moments."""
