@@ -753,6 +753,9 @@ def main():
     if os.environ.get('MIMO_TC_TRIANGULAR'):                 # A/B only: rows per step of the triangular skip (0 = kernel off)
         E.set_triangular(int(os.environ['MIMO_TC_TRIANGULAR']))
         config['tc_triangular'] = int(os.environ['MIMO_TC_TRIANGULAR'])
+    if os.environ.get('MIMO_TC_QUAD_GEN'):                   # A/B only: 0 = the plain CTA-pair dense E-step
+        E.set_quad_generations(int(os.environ['MIMO_TC_QUAD_GEN']))
+        config['tc_quad_generations'] = int(os.environ['MIMO_TC_QUAD_GEN'])
     if os.environ.get('MIMO_TC_FLUSH_TILES'):                # A/B only: 128-point tiles between FP64 drains of the statistics
         E._lib.load().mimo_tc_set_flush_tiles(int(os.environ['MIMO_TC_FLUSH_TILES']))
         config['tc_flush_tiles'] = int(os.environ['MIMO_TC_FLUSH_TILES'])

@@ -162,6 +162,7 @@ int mimo_tc_diag_enable(int on);            /* A/B: 0 keeps diagonal sweeps on t
  * -- for callers that keep the data resident and unchanged across sweeps (the Python Session does). */
 int mimo_sweep_absmax_hint(double absmax);
 int mimo_tc_set_min_dim(int d);             /* A/B: smallest D a quad-family sweep takes to the tensor pipe (default 8; 24 = round-1 behaviour); returns the old value */
+int mimo_tc_set_quad_generations(int on);   /* A/B: dense E-step, 64 < D <= 128: 1 = four components per accumulator generation with the zero block of the Cholesky factors skipped (tc_estep4.cu; measured slower), 0 (default) = the plain CTA-pair kernel (tc_estep2.cu); returns the old setting */
 int mimo_tc_set_triangular(int rows);       /* dense E-step, 64 < D <= 128: rows per step of the triangular skip (16 default, 32; 0 = kernel with both operands in shared memory); returns the old value */
 int mimo_tc_set_flush_tiles(int tiles);     /* 128-point tiles accumulated in TMEM (FP32) between FP64 drains */
 size_t mimo_loglik_quad_tc_workspace(int K, int Rp, int D);

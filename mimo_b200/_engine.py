@@ -514,6 +514,12 @@ def set_tc_min_dim(d):
     return _lib.load().mimo_tc_set_min_dim(int(d))
 
 
+def set_quad_generations(on):
+    """Dense E-step for 64 < D <= 128: True = tc_estep4.cu (four components per accumulator generation, zero block of the
+    Cholesky factors skipped; measured slower), False (default) = tc_estep2.cu.  Returns the old setting."""
+    return _lib.load().mimo_tc_set_quad_generations(int(bool(on)))
+
+
 def set_triangular(rows):
     """Dense E-step for 64 < D <= 128: rows per step of the triangular skip of tc_estep3.cu (16 or 32; 0 = the kernel
     with both operands in shared memory).  Returns the old value."""

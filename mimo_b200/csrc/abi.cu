@@ -115,6 +115,7 @@ int mimo_tc_screen_last(uint32_t* out_host2) { return tc_screen_last(out_host2);
 int mimo_tc_screen_totals(uint64_t* out_host5) { return tc_screen_totals((unsigned long long*)out_host5); }
 int mimo_sweep_uses_tensor_cores(int dtype, int family, int D, int Rp) { return sweep_uses_tc(dtype, family, D, Rp) ? 1 : 0; }
 int mimo_tc_set_triangular(int rows) { return tc3_set_granularity(rows); }
+int mimo_tc_set_quad_generations(int on) { return tc4_enable(on); }
 int mimo_tc_set_flush_tiles(int tiles) { tc_set_flush_tiles(tiles); tc_fstats_set_flush_tiles(tiles); return MIMO_OK; }
 size_t mimo_loglik_quad_tc_workspace(int K, int Rp, int D) { return tc_operand_workspace(K, Rp, D); }
 int mimo_loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* W, const void* cst,

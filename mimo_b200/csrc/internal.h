@@ -86,6 +86,14 @@ int tc3_prepare(const float* W, const float* cst, int K, int Dpp, int D, unsigne
 int tc_estep3(const float* Z, int64_t N, int D, int64_t ldz, int K, const void* ws3, const unsigned int* flags,
               float* out, int64_t ldo, const unsigned int* gate, unsigned int gate_value,
               float* lse_vals, double* lse_sum, cudaStream_t st);
+// CTA-pair E-step, four components per accumulator generation, zero block skipped at full MMA width (tc_estep4.cu)
+bool tc4_supported(int D, int Rp);
+int tc4_enable(int on);
+size_t tc4_workspace(int K);
+int tc4_prepare(const float* W, const float* cst, int K, int Dpp, int D, unsigned int* flags, void* ws4, cudaStream_t st);
+int tc_estep4(const float* Z, int64_t N, int D, int64_t ldz, int K, const void* ws4, const unsigned int* flags,
+              float* out, int64_t ldo, const unsigned int* gate, unsigned int gate_value,
+              float* lse_vals, double* lse_sum, cudaStream_t st);
 int loglik_quad_tc(const void* Z, int64_t N, int D, int64_t ldz, const void* W, const void* cst,
                    int K, int Rp, int Dpp, void* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st);
 bool tc_stats_supported(int dtype, int D, int F);

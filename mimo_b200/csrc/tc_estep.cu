@@ -314,7 +314,7 @@ bool tc_estep_supported(int dtype, int D, int Rp) {
 
 struct TcOperandLayout {
     int KB, n_chunks;                  // n_chunks: 128-row chunks, rounded up to an even count (CTA-pair kernel), zero padded
-    size_t off_maxbits, off_invS2, off_rowoff, off_offs2, off_img, off_t3, bytes;   // off_t3: image + offsets of tc_estep3.cu (always reserved for its shapes)
+    size_t off_maxbits, off_invS2, off_rowoff, off_offs2, off_img, off_t3, off_t4, bytes;   // off_t3 / off_t4: image + offsets of tc_estep3.cu / tc_estep4.cu (always reserved for their shapes)
 };
 static TcOperandLayout tc_layout(int K, int Rp, int D) {
     TcOperandLayout L;
@@ -329,6 +329,8 @@ static TcOperandLayout tc_layout(int K, int Rp, int D) {
     o = (o + 1023) / 1024 * 1024;
     L.off_img = o;     o += (size_t)L.n_chunks * L.KB * TE_STAGE_BYTES;
     L.off_t3 = o;      if (D > 64 && Rp == 128) o += tc3_workspace(K);
+    o = (o + 1023) / 1024 * 1024;
+    L.off_t4 = o;      if (D > 64 && Rp == 128) o += tc4_workspace(K);
     L.bytes = o;
     return L;
 }
@@ -379,6 +381,10 @@ int tc_prepare_operands(const float* W, const float* cst, int K, int Rp, int Dpp
         int rc = tc3_prepare(W, cst, K, Dpp, D, (unsigned int*)(base + L.off_maxbits), base + L.off_t3, st);
         if (rc) return rc;
     }
+    if (tc4_supported(D, Rp)) {
+        int rc = tc4_prepare(W, cst, K, Dpp, D, (unsigned int*)(base + L.off_maxbits), base + L.off_t4, st);
+        if (rc) return rc;
+    }
     // per-chunk offsets / constants blocks of the CTA-pair kernel
     return tc2_prepare_offsets((const float*)(base + L.off_rowoff), (const float*)(base + L.off_invS2), cst, K, Rp,
                                (float*)(base + L.off_offs2), st);
@@ -395,6 +401,8 @@ int tc_estep_pass(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, 
     char* base = align1k(ws);
     if (passes == 3 && tc3_supported(D, Rp))
         return tc_estep3(Z, N, D, ldz, K, base + L.off_t3, (const unsigned int*)(base + L.off_maxbits), out, ldo, gate, gate_value, lse_vals, lse_sum, st);
+    if (passes == 3 && tc4_supported(D, Rp))
+        return tc_estep4(Z, N, D, ldz, K, base + L.off_t4, (const unsigned int*)(base + L.off_maxbits), out, ldo, gate, gate_value, lse_vals, lse_sum, st);
     return tc_estep2(Z, N, D, ldz, K, Rp, L.KB, (const void*)(base + L.off_img), (const float*)(base + L.off_offs2),
                      (const unsigned int*)(base + L.off_maxbits), out, ldo, passes, gate, gate_value, lower, guess, ldl, st, lse_vals, lse_sum);
 }
@@ -423,6 +431,8 @@ int tc_estep(const float* Z, int64_t N, int D, int64_t ldz, const float* cst, in
     char* base = align1k(ws);
     if (tc_mode() != 2 && tc3_supported(D, Rp))     // points operand in tensor memory, triangular skip
         return tc_estep3(Z, N, D, ldz, K, base + L.off_t3, (const unsigned int*)(base + L.off_maxbits), out, ldo, nullptr, 0u, lse_vals, lse_sum, st);
+    if (tc_mode() != 2 && tc4_supported(D, Rp))     // four components per generation, zero block skipped at full MMA width
+        return tc_estep4(Z, N, D, ldz, K, base + L.off_t4, (const unsigned int*)(base + L.off_maxbits), out, ldo, nullptr, 0u, lse_vals, lse_sum, st);
     // CTA-pair kernel (cta_group::2), dense 3-pass; the single-CTA kernel (mode 2) reads the plain image only
     if (tc_mode() != 2 || lse_vals)
         return tc_estep2(Z, N, D, ldz, K, Rp, L.KB, (const void*)(base + L.off_img), (const float*)(base + L.off_offs2),

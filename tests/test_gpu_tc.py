@@ -72,6 +72,35 @@ def test_loglik_tc_dense_operands(K, d, rows):
     close(ll, E.loglik(Z, ops).cpu().numpy(), 2e-5, 'tensor-core vs CUDA-core log-lik')
 
 
+@pytest.mark.parametrize('quad', [True, False])
+@pytest.mark.parametrize('K,d,tri', [(9, 128, True), (4, 100, True), (5, 128, False), (3, 70, False), (1, 65, True), (1030, 128, True)])
+def test_loglik_tc_dense_kernels_d_above_64(quad, K, d, tri):
+    """the two dense E-step kernels for 64 < d <= 128: tc_estep2.cu (default) and tc_estep4.cu (four components per
+    accumulator generation, the zero block of Cholesky-factor operands skipped; dense operands take the fourth step)."""
+    E = eng()
+    rng = np.random.default_rng(23)
+    N = 1300 if K < 100 else 700
+    ops = E.QuadOperands(K, d, d, 'fp32')
+    W = np.zeros((K, ops.Rp, ops.Dpp))
+    blk = rng.standard_normal((K, d, d)) / np.sqrt(d)
+    W[:, :d, :d] = np.triu(blk) if tri else blk
+    W[:, :d, d] = rng.standard_normal((K, d))
+    cst = rng.standard_normal(K)
+    ops.W.copy_(E.to_dev(W, torch.float32))
+    ops.cst.copy_(E.to_dev(cst, torch.float32))
+    Z = E.to_dev(rng.standard_normal((N, d)) * 1.5 + 0.5, torch.float32)
+    old = E.set_quad_generations(quad)
+    try:
+        ll = E.loglik_tc(Z, ops)
+    finally:
+        E.set_quad_generations(old)
+    Wr = ops.W.double().cpu().numpy()
+    zt = np.concatenate([Z.double().cpu().numpy(), np.ones((N, 1))], axis=1)
+    y = np.einsum('kij,nj->kni', Wr[:, :, :d + 1], zt)
+    ref = ops.cst.double().cpu().numpy()[:, None] - 0.5 * np.sum(y * y, axis=2)
+    close(ll, ref, 1e-4, 'dense log-lik (%s)' % ('tc_estep4' if quad else 'tc_estep2'))
+
+
 @pytest.mark.parametrize('gran', [16, 32])
 @pytest.mark.parametrize('K,d,tri', [(9, 128, True), (4, 100, True), (5, 128, False), (3, 70, False)])
 def test_loglik_tc_points_in_tensor_memory(gran, K, d, tri):
