@@ -676,6 +676,25 @@ def overlap_leg(cx, w, steps, comm_factory, peaks):
 
 
 # ---------------------------------------------------------------------------------------
+def kernel_names(w, tcu, D):
+    """names of the kernels behind the three phases of a leg (what the library dispatches to for this shape) and the bound
+    that holds for the E-step kernel where it is not the algorithmic roofline."""
+    d, K = w['d'], w['K']
+    if w['kind'] == 'dgmm' and d <= 64 and K <= 256:
+        return (['E-step + label draw: tc_diag_kernel (tcgen05 feature GEMM on [z, z^2], CTA pairs, labels in the epilogue)',
+                 'softmax / label draw (fused into the E-step kernel)', 'hard statistics: block-local counting sort + diag_hard_stats_kernel'],
+                'epilogue instruction issue (max / exp / cumulative sum per pair: 22 warp instructions per column at 2.1 per clock); '
+                'the MMAs alone need 3072 clk per 256-point tile')
+    if tcu and d > 64:
+        return (['E-step: tc_estep2_kernel<2,128,3> (3 x FP16 split, CTA pairs, fused log-normaliser)', 'softmax / label draw',
+                 'statistics: tc_fstats_kernel (feature GEMM over the folded triangle)'], None)
+    if tcu and D < 24:
+        return (['E-step: tc_estep2_kernel<1,Rp,3> (tcgen05, one 16-wide K step per 256 columns, 16 epilogue warps, fused log-normaliser)',
+                 'softmax / label draw', 'statistics: tc_sstats_kernel (tcgen05 feature GEMM, whole packed triangle in one accumulator)'],
+                'tensor-memory read port: K x Rp accumulator columns x 4 B per point at 64 B/clk/SM')
+    return (['E-step (%s)' % ('tcgen05' if tcu else 'CUDA cores'), 'softmax / label draw', 'sufficient statistics'], None)
+
+
 def run_config(cx, name, steps, warmup, comm_factory, peaks, n_override=0):
     """a short leg of one of the other BASELINE.json shapes on the library's default path."""
     from mimo_b200.sharded import shard_bounds
@@ -693,8 +712,10 @@ def run_config(cx, name, steps, warmup, comm_factory, peaks, n_override=0):
     hard = w['mode'] == 'gibbs'
     leg = time_leg(cx, s, hard, steps, warmup)
     tcu = E.sweep_uses_tensor_cores(s.ops(1 if hard else 0), Z.shape[1])
-    names = ['E-step (%s)' % ('tcgen05' if tcu else 'CUDA cores'), 'softmax / label draw', 'sufficient statistics']
+    names, true_bound = kernel_names(w, tcu, Z.shape[1])
     roof = leg_roofline(w, hi - lo, leg, peaks, names)
+    if true_bound:
+        roof['estep_bound'] = true_bound
     out = dict(workload='%s: %s' % (name, w['desc']), N=w['N'], K=w['K'], d=w['d'], sweep=w['mode'], steps=steps, warmup=warmup,
                ms_per_step=leg['ms'], value=w['N'] * w['K'] / (leg['ms'] * 1e-3), unit='points*components/s', roofline=roof,
                lower_bound=leg['vlbs'][-2:] if leg['vlbs'] else None, gpu_launches=int(leg['phase'][3]))
@@ -793,10 +814,10 @@ def main():
     leg = time_leg(cx, s, hard, args.steps, warmup, tc_mode=head_mode, sample_clocks=True)
     ms = leg['ms']
     value = w['N'] * K / (ms * 1e-3)
-    knames = [('E-step: tc_estep2_kernel<2,128,3> (3 x FP16 split, CTA pairs)' if (tcu and w['d'] > 64) else
-               'E-step (%s)' % ('tcgen05' if tcu else 'CUDA cores')), 'softmax / label draw',
-              ('statistics: tc_fstats_kernel (feature GEMM over the folded triangle)' if (tcu and w['d'] > 64) else 'sufficient statistics')]
+    knames, true_bound = kernel_names(w, tcu, Z.shape[1])
     roof = leg_roofline(w, n_local, leg, peaks, knames)
+    if true_bound:
+        roof['estep_bound'] = true_bound
     if name == 'cfg5' and not args.n_override:
         dom = int(np.argmax(leg['phase'][:3]))
         tr = ncu_traffic(['tc_estep2_kernel', 'softmax_kernel', 'tc_fstats_kernel'][dom])
