@@ -5,6 +5,7 @@
 // it supports the shape.
 #include "common.cuh"
 #include "internal.h"
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges cost nothing unless a profiler is attached (tracing)
 #include <vector>
 #include <chrono>
 #include <stdlib.h>
@@ -193,11 +194,14 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     // optional per-phase device timing (bench.py's roofline leg): events on the launching stream
     std::vector<cudaEvent_t> ev, evk;
     auto mark = [&]() { if (phase_ms) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); } };
+    struct Range { explicit Range(const char* n) { nvtxRangePushA(n); } ~Range() { nvtxRangePop(); } };
+    Range sweep_range(hard ? "mimo_sweep (Gibbs)" : "mimo_sweep (mean field)");
     for (int64_t n0 = 0; n0 < N; n0 += C) {
         const int64_t nc = (N - n0 < C) ? (N - n0) : C;
         mark();
         const char* Zc = (const char*)Z + (size_t)n0 * ldz * es;
         int rc;
+        nvtxRangePushA("E-step");
         if (use_screen) {
             // screening pass over all pairs (projected operands, one FP16 pass), exact guesses, candidate lists; then
             // either the exact refinement of the candidates or (device-side flag, when > 4 % of the pairs are
@@ -225,6 +229,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             rc = loglik_diag(dtype, Zc, nc, D, ldz, op_a, op_b, cst, K, scratch, C, st, tc_diag_gate(diag_ws), 1u);
         }
         else             rc = loglik_diag(dtype, Zc, nc, D, ldz, op_a, op_b, cst, K, scratch, C, st);
+        nvtxRangePop();
         if (rc) return rc;
         mark();
         int flags = (lse_sum ? MIMO_ACC_LSE : 0) | (lse_out ? MIMO_WRITE_LSE : 0)

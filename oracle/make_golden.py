@@ -409,6 +409,22 @@ def main():
     gmm_svi_case('gmm_toy_svi_stick', toy, *toy_model('stick'), iters=6, batch_size=64, step_size=0.1, seed=9)
     gmm_em_case('gmm_toy_em', toy, K, seed=3)
 
+    # cfg1 at its shipped size: examples/gmm/sine/{vi,gibbs}_gmm.py (N = 2500 points on a noisy sine, K = 25, alpha = 2)
+    rs = np.random.default_rng(4242)
+    xs = np.arange(2500) * (14. * np.pi / 2500) - 6.
+    sine = np.stack([xs + rs.normal(0, 0.1, 2500), 3. * (np.sin(xs) + rs.normal(0, .1, 2500))], axis=1)
+
+    def sine_model():
+        Ks = 25
+        prior = D.StackedNormalWisharts(Ks, 2, mus=np.zeros((Ks, 2)), kappas=0.01 * np.ones(Ks),
+                                        psis=np.stack(Ks * [np.eye(2)]), nus=3. * np.ones(Ks) + 1e-8)
+        npr.seed(1)
+        return (D.StackedGaussiansWithNormalWisharts(Ks, 2, prior=prior),
+                D.CategoricalWithDirichlet(Ks, D.Dirichlet(Ks, 2. * np.ones(Ks))))
+
+    gmm_vi_case('gmm_sine_vi', sine, *sine_model(), iters=2, seed=2500)
+    gmm_gibbs_case('gmm_sine_gibbs', sine, *sine_model(), sweeps=3, seed=2500)
+
     # cfg4-shaped: full covariance d=16, stick-breaking DP-GMM
     K4, d4 = 8, 16
     x4 = blobs(rng, 600, d4, K4, spread=3.0)

@@ -56,7 +56,7 @@ def make_gmm(g):
     return BayesianMixtureOfGaussians(gating=make_gating(g, K), components=comp)
 
 
-@pytest.mark.parametrize('name', ['gmm_toy_vi', 'gmm_toy_vi_stick', 'gmm_d16_vi_stick'])
+@pytest.mark.parametrize('name', ['gmm_toy_vi', 'gmm_toy_vi_stick', 'gmm_d16_vi_stick', 'gmm_sine_vi'])
 def test_gmm_meanfield_trajectory(name, precision):
     g = load(name)
     model = make_gmm(g)
@@ -80,7 +80,7 @@ def test_gmm_meanfield_trajectory(name, precision):
     close(model.variational_lowerbound(g['obs'], g[f'resp_{T - 1}']), g['vlb'][-1], 10 * tol, 'public vlb')
 
 
-@pytest.mark.parametrize('name', ['gmm_toy_gibbs', 'gmm_d16_gibbs_stick'])
+@pytest.mark.parametrize('name', ['gmm_toy_gibbs', 'gmm_d16_gibbs_stick', 'gmm_sine_gibbs'])
 def test_gmm_gibbs_chain_replays_reference(name):
     """Same numpy.random seed => the reference's chain: labels, sampled parameters, posteriors."""
     import mimo_b200

@@ -26,7 +26,7 @@ def gate_logw_vi(g, t, prefix=''):
     return orc.stick_expected_log(g[f'{prefix}gate_gammas_{t}'], g[f'{prefix}gate_deltas_{t}'])[0]
 
 
-@pytest.mark.parametrize('name', ['gmm_toy_gibbs', 'gmm_d16_gibbs_stick'])
+@pytest.mark.parametrize('name', ['gmm_toy_gibbs', 'gmm_d16_gibbs_stick', 'gmm_sine_gibbs'])
 def test_gmm_gibbs_phases(name):
     g = load(name)
     x, K = g['obs'], int(g['K'])
@@ -52,7 +52,7 @@ def test_gmm_gibbs_phases(name):
         assert np.array_equal(labels, g[f'labels_{t}'])
 
 
-@pytest.mark.parametrize('name', ['gmm_toy_vi', 'gmm_toy_vi_stick', 'gmm_d16_vi_stick'])
+@pytest.mark.parametrize('name', ['gmm_toy_vi', 'gmm_toy_vi_stick', 'gmm_d16_vi_stick', 'gmm_sine_vi'])
 def test_gmm_vi_trajectory(name):
     g = load(name)
     x, K = g['obs'], int(g['K'])
