@@ -161,6 +161,9 @@ int mimo_tc_diag_enable(int on);            /* A/B: 0 keeps diagonal sweeps on t
  * (>= the true maximum).  The tensor-core paths then skip their own pass over Z for the common power-of-two data scale
  * -- for callers that keep the data resident and unchanged across sweeps (the Python Session does). */
 int mimo_sweep_absmax_hint(double absmax);
+/* diagnostics: clocks the MMA issuers of tc_fstats_kernel waited, summed over clusters since the last call: {A tile, peer's A
+ * tile, B stage, peer's B stage, accumulator drain, total issuer clocks, stages issued, 0} (synchronises, resets) */
+int mimo_tc_fstats_stall_clocks(uint64_t* out_host8);
 int mimo_tc_set_min_dim(int d);             /* A/B: smallest D a quad-family sweep takes to the tensor pipe (default 8; 24 = round-1 behaviour); returns the old value */
 int mimo_tc_set_quad_generations(int on);   /* A/B: dense E-step, 64 < D <= 128: 1 = four components per accumulator generation with the zero block of the Cholesky factors skipped (tc_estep4.cu; measured slower), 0 (default) = the plain CTA-pair kernel (tc_estep2.cu); returns the old setting */
 int mimo_tc_set_triangular(int rows);       /* dense E-step, 64 < D <= 128: rows per step of the triangular skip (16 default, 32; 0 = kernel with both operands in shared memory); returns the old value */

@@ -113,6 +113,7 @@ int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* 
                     const unsigned int* gate = nullptr, unsigned int gate_value = 0u, const float* lse = nullptr);
 int tc_fstats_end(int64_t plan_points, int K, int D, int F, const unsigned int* maxbits, double* stat, void* ws, cudaStream_t st);
 void tc_fstats_set_flush_tiles(int tiles);
+int tc_fstats_stall_clocks(unsigned long long* out_host8);
 // feature-form statistics for small dimensions (tc_sstats.cu): D <= 21, accumulates straight into stat (K, F)
 bool tc_sstats_supported(int dtype, int D, int F);
 int tc_sstats_enable(int on);

@@ -182,6 +182,11 @@ tc_fstats_rimg_kernel(const float* __restrict__ R, const float* __restrict__ lse
     }
 }
 
+// Diagnostics: clocks the MMA issuers spent waiting, by cause, summed over clusters (mimo_tc_fstats_stall_clocks):
+// [0] A (responsibility) tile landed, [1] peer's A tile, [2] B stage formed, [3] peer's B stage, [4] accumulator drained,
+// [5] total clocks of the issuer loops, [6] stages issued
+__device__ unsigned long long g_tf_stall[8];
+
 // ---- main kernel ------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TF_THREADS, 1)
 tc_fstats_kernel(const unsigned char* __restrict__ zimg, const unsigned char* __restrict__ rimg, int64_t nkb_cap,
@@ -352,20 +357,28 @@ tc_fstats_kernel(const unsigned char* __restrict__ zimg, const unsigned char* __
             const uint32_t idesc = make_idesc_f16(256, 256);
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
             uint32_t ac = 0, bc = 0, dc = 0;
+            long long w_a = 0, w_pa = 0, w_b = 0, w_pb = 0, w_d = 0, n_st = 0;
+            const long long t_begin = clock64();
             for (int u = cluster_id; u < n_units; u += n_clusters) {
                 TF_UNIT_DECODE
                 bool fresh = true;
                 for (int kb = 0; kb < nkb; ++kb, ++ac) {
                     const uint32_t abuf = ac & 1, apar = (ac >> 1) & 1;
+                    long long t0 = clock64();
                     mbar_wait(&bars->a_full[abuf], apar);
+                    long long t1 = clock64();
                     mbar_wait_cluster(&bars->peer_a_full[abuf], apar);
+                    w_a += t1 - t0; w_pa += clock64() - t1;
                     tc_fence_after();
                     const uint64_t ah = make_desc_sw128(a0 + abuf * TF_PAIR);
                     const uint64_t al = make_desc_sw128(a0 + abuf * TF_PAIR + TF_TILE);
                     for (int st = 0; st < nst; ++st, ++bc) {
                         const uint32_t bst = bc % TF_BSTAGES, bpar = (bc / TF_BSTAGES) & 1;
+                        t0 = clock64();
                         mbar_wait(&bars->b_full[bst], bpar);
+                        t1 = clock64();
                         mbar_wait_cluster(&bars->peer_b_full[bst], bpar);
+                        w_b += t1 - t0; w_pb += clock64() - t1; ++n_st;
                         tc_fence_after();
                         const uint64_t bh = make_desc_sw128(b0 + bst * TF_PAIR);
                         const uint64_t bl = make_desc_sw128(b0 + bst * TF_PAIR + TF_TILE);
@@ -382,14 +395,20 @@ tc_fstats_kernel(const unsigned char* __restrict__ zimg, const unsigned char* __
                     fresh = false;
                     if ((kb + 1) % flush_kb == 0 || kb + 1 == nkb) {
                         umma2_commit(&bars->acc_ready);
+                        t0 = clock64();
                         mbar_wait(&bars->acc_drained, dc & 1);     // both CTAs' accumulators read out: may be overwritten
                         mbar_wait_cluster(&bars->peer_acc_drained, dc & 1);
+                        w_d += clock64() - t0;
                         tc_fence_after();
                         ++dc;
                         fresh = true;
                     }
                 }
             }
+            atomicAdd(&g_tf_stall[0], (unsigned long long)w_a); atomicAdd(&g_tf_stall[1], (unsigned long long)w_pa);
+            atomicAdd(&g_tf_stall[2], (unsigned long long)w_b); atomicAdd(&g_tf_stall[3], (unsigned long long)w_pb);
+            atomicAdd(&g_tf_stall[4], (unsigned long long)w_d); atomicAdd(&g_tf_stall[5], (unsigned long long)(clock64() - t_begin));
+            atomicAdd(&g_tf_stall[6], (unsigned long long)n_st);
         } else if (warp == 16 && lane == 0) {
             // ================= relay (peer CTA): forward local events to the leader's issuer =================
             uint32_t ac = 0, bc = 0, dc = 0;
@@ -545,6 +564,15 @@ int tc_fstats_chunk(const float* Z, int64_t N, int D, int64_t ldz, const float* 
     tc_fstats_kernel<<<grid, TF_THREADS, TF_SMEM, st>>>(zimg, rimg, L.nkb_cap, N, partial, pace, cbps, fbs, slabs, slab_points,
                                                         flush_kb, pace_epochs, gate, gate_value);
     MIMO_LAUNCH_CHECK();
+    return MIMO_OK;
+}
+
+// read and reset the issuer stall counters (synchronises)
+int tc_fstats_stall_clocks(unsigned long long* out_host8) {
+    MIMO_CUDA(cudaDeviceSynchronize());
+    MIMO_CUDA(cudaMemcpyFromSymbol(out_host8, g_tf_stall, 8 * sizeof(unsigned long long)));
+    unsigned long long zero[8] = {};
+    MIMO_CUDA(cudaMemcpyToSymbol(g_tf_stall, zero, sizeof(zero)));
     return MIMO_OK;
 }
 
