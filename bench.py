@@ -719,6 +719,23 @@ def run_config(cx, name, steps, warmup, comm_factory, peaks, n_override=0):
     out = dict(workload='%s: %s' % (name, w['desc']), N=w['N'], K=w['K'], d=w['d'], sweep=w['mode'], steps=steps, warmup=warmup,
                ms_per_step=leg['ms'], value=w['N'] * w['K'] / (leg['ms'] * 1e-3), unit='points*components/s', roofline=roof,
                lower_bound=leg['vlbs'][-2:] if leg['vlbs'] else None, gpu_launches=int(leg['phase'][3]))
+    if name == 'cfg1' and not hard and cx.world == 1:
+        # at this size an iteration is ~30 launches of microseconds each: the same iteration replayed from a CUDA graph
+        # (Session.capture_meanfield_step, what meanfield_coordinate_descent(graph=True) uses), lower bound read every step
+        graph, outs = s.capture_meanfield_step()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(steps, 20)
+        e0.record()
+        for _ in range(reps):
+            graph.replay()
+            v = s.lower_bound(outs)
+        e1.record()
+        torch.cuda.synchronize()
+        gms = e0.elapsed_time(e1) / reps
+        out['cuda_graph'] = dict(ms_per_step=gms, value=w['N'] * w['K'] / (gms * 1e-3), steps=reps, lower_bound=v)
     del s, Z
     torch.cuda.empty_cache()
     return out

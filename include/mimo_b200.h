@@ -161,6 +161,10 @@ int mimo_tc_diag_enable(int on);            /* A/B: 0 keeps diagonal sweeps on t
  * (>= the true maximum).  The tensor-core paths then skip their own pass over Z for the common power-of-two data scale
  * -- for callers that keep the data resident and unchanged across sweeps (the Python Session does). */
 int mimo_sweep_absmax_hint(double absmax);
+/* One-shot promise for the NEXT mimo_sweep of the calling thread: the (fi, fj) tables are (1) / are not (0) the canonical
+ * packed triangle f = i (i + 1) / 2 + j.  Without it a soft quad-family sweep reads the tables back once to decide whether
+ * its list / tensor-core statistics kernels apply (a stream synchronisation, which a CUDA-graph capture cannot contain). */
+int mimo_sweep_tables_hint(int canonical);
 /* diagnostics: clocks the MMA issuers of tc_fstats_kernel waited, summed over clusters since the last call: {A tile, peer's A
  * tile, B stage, peer's B stage, accumulator drain, total issuer clocks, stages issued, 0} (synchronises, resets) */
 int mimo_tc_fstats_stall_clocks(uint64_t* out_host8);

@@ -88,6 +88,11 @@ class Features:
         self.fi_host = np.asarray(fi, dtype=np.int32)
         self.fj_host = np.asarray(fj, dtype=np.int32)
         self._dev = None
+        # canonical packed triangle f = i (i + 1) / 2 + j?  (the device copy is made from these host arrays, so the sweep can
+        # be told instead of reading the tables back)
+        il = np.tril_indices(D + 1)
+        self.canonical = bool(self.F == (D + 1) * (D + 2) // 2 and np.array_equal(self.fi_host, il[0])
+                              and np.array_equal(self.fj_host, il[1]))
 
     def dev(self):
         if self._dev is None:
@@ -320,6 +325,8 @@ def sweep(Z, ops, feats, buf, uniforms=None, seed=0, offset=0, ll_out=None, lse_
     a, b, c, K, Rp, Dpp = ops.args()
     if absmax is not None and absmax > 0:      # max |Z| of resident, unchanged data: the sweep skips its own pass over Z for it
         _lib.call('mimo_sweep_absmax_hint', float(absmax))
+    if getattr(feats, 'canonical', None) is not None:      # tables this module built itself: no read-back inside the sweep
+        _lib.call('mimo_sweep_tables_hint', 1 if feats.canonical else 0)
     args = (code(ops.precision), ops.family, 1 if buf.hard else 0,
             ptr(Z), N, D, Z.stride(0), a, b, c, K, Rp, Dpp, ptr(fi), ptr(fj), feats.F,
             ptr(uniforms), int(seed), int(offset), ptr(buf.stat), ptr(buf.lse_sum), ptr(buf.labels),

@@ -90,6 +90,7 @@ int mimo_comm_unique_id(void* out) { return comm_unique_id(out); }
 int mimo_comm_init(int world, int rank, const void* unique_id, void** comm_out) { return comm_init(world, rank, unique_id, comm_out); }
 int mimo_comm_allreduce_stats(void* comm, double* stat, int64_t count, void* stream) { return comm_allreduce_stats(comm, stat, count, ST(stream)); }
 int mimo_comm_destroy(void* comm) { return comm_destroy(comm); }
+int mimo_sweep_tables_hint(int canonical) { sweep_set_tables_hint(canonical); return MIMO_OK; }
 int mimo_sweep_absmax_hint(double absmax) { tc_set_absmax_hint((float)absmax); return MIMO_OK; }
 int mimo_tc_fstats_stall_clocks(uint64_t* out_host8) { return tc_fstats_stall_clocks((unsigned long long*)out_host8); }
 int mimo_tc_diag_enable(int on) { return tc_diag_enable(on); }

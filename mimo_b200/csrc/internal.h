@@ -152,6 +152,7 @@ int resp_list_build(const float* R, int K, int64_t n, int64_t ldr, int D, int64_
 const unsigned int* resp_list_gate(void* ws, int64_t plan_points, int K);
 void resp_list_get(void* ws, int64_t plan_points, int K, const int32_t** perm, const int32_t** offsets, const int32_t** slabs);
 
+void sweep_set_tables_hint(int canonical);
 bool sweep_uses_tc(int dtype, int family, int D, int Rp);
 int64_t sweep_chunk_points(int dtype, int family, int64_t N, int D, int K, int Rp);
 size_t sweep_workspace(int dtype, int family, int hard, int64_t N, int D, int K, int Rp);

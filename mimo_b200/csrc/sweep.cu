@@ -57,10 +57,16 @@ static bool canonical_host(const int32_t* fi, const int32_t* fj, int F, int D) {
             if (fi[f] != i || fj[f] != j) return false;
     return true;
 }
-static int tables_canonical(const int32_t* fi, const int32_t* fj, int F, int D, cudaStream_t st, bool* out) {
+// A caller that built the tables itself may say so for its NEXT sweep (mimo_sweep_tables_hint): the sweep then does not
+// synchronise to read them back -- which is also what lets a whole iteration be captured in a CUDA graph.  One-shot.
+static thread_local int g_tables_promise = -1;
+void sweep_set_tables_hint(int canonical) { g_tables_promise = canonical < 0 ? -1 : (canonical ? 1 : 0); }
+
+static int tables_canonical(const int32_t* fi, const int32_t* fj, int F, int D, cudaStream_t st, int promise, bool* out) {
     *out = false;
     if (F != (D + 1) * (D + 2) / 2) return MIMO_OK;
     if (g_tables_hint >= 0) { *out = g_tables_hint == 1; return MIMO_OK; }
+    if (promise >= 0) { *out = promise == 1; return MIMO_OK; }
     std::vector<int32_t> h((size_t)2 * F);
     MIMO_CUDA(cudaMemcpyAsync(h.data(), fi, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
     MIMO_CUDA(cudaMemcpyAsync(h.data() + F, fj, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
@@ -117,6 +123,8 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
           const void* uniforms, uint64_t seed, uint64_t point_offset,
           double* stat, double* lse_sum, int32_t* labels_out, void* lse_out, void* ll_out, int64_t ldo,
           void* workspace, size_t workspace_bytes, cudaStream_t st, double* phase_ms) {
+    const int promise = g_tables_promise;              // one-shot: whatever this sweep does with it, the next one starts clean
+    g_tables_promise = -1;
     MIMO_CHECK_ARG(dtype == MIMO_F32 || dtype == MIMO_F64, "dtype");
     MIMO_CHECK_ARG(family == 0 || family == 1, "family");
     MIMO_CHECK_ARG(Z && op_a && cst && workspace && (family == 0 || op_b), "null pointer");
@@ -137,7 +145,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     // soft statistics through the list / tensor-core kernels need the canonical packed triangle (checked, not assumed)
     bool canon = false;
     if (stat && !hard && family == 0 && dtype == MIMO_F32 && (use_tc || sweep_uses_resp_list(dtype, family, hard, D, K, Rp))) {
-        int rc = tables_canonical(fi, fj, F, D, st, &canon);
+        int rc = tables_canonical(fi, fj, F, D, st, promise, &canon);
         if (rc) return rc;
     }
     const bool resp_list = stat && canon && sweep_uses_resp_list(dtype, family, hard, D, K, Rp) && pair_stats_supported(dtype, D, F);

@@ -52,7 +52,8 @@ constexpr uint32_t TD_OFF_B = TD_ABUF;                         // A0 | B (kb0, k
 constexpr uint32_t TD_OFF_A1 = TD_ABUF + 2 * TD_STAGE;
 constexpr uint32_t TD_OFF_C = TD_OFF_A1 + TD_ABUF;             // constants: 256 x (c_k, 1 / g_k)
 constexpr uint32_t TD_OFF_X = TD_OFF_C + TD_KMAX * 8;          // block statistics: [tile parity][half][block 4][point 128] (max, sum)
-constexpr uint32_t TD_OFF_BARS = TD_OFF_X + 2 * 2 * 4 * 128 * 8;
+constexpr uint32_t TD_OFF_U = TD_OFF_X + 2 * 2 * 4 * 128 * 8;   // the points' uniforms: [tile parity][point 128] floats
+constexpr uint32_t TD_OFF_BARS = TD_OFF_U + 2 * 128 * 4;
 constexpr uint32_t TD_SMEM = TD_OFF_BARS + sizeof(TdBars);
 
 // ---- prepare: centre, scales, weight image, constants -----------------------------------------------------------
@@ -142,6 +143,7 @@ tc_diag_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int v
     unsigned char* sB = smem + TD_OFF_B;
     const float2* sC = reinterpret_cast<const float2*>(smem + TD_OFF_C);
     float2* sX = reinterpret_cast<float2*>(smem + TD_OFF_X);
+    float* sU = reinterpret_cast<float*>(smem + TD_OFF_U);
     TdBars* bars = reinterpret_cast<TdBars*>(smem + TD_OFF_BARS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -331,7 +333,11 @@ tc_diag_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int v
                 }
                 xw[b * 128] = make_float2(mb, (s0 + s1_) + (s2_ + s3_));
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(TD_EPI) : "memory");
+            // the point's uniform: drawn once, by the first quarter, and handed over with the block statistics
+            if (qtr == 0 && labels != nullptr)
+                sU[buf * 128 + prow] = pvalid ? (float)(uniforms ? uniforms[n] : philox_uniform(seed, point_offset + (uint64_t)n)) : 0.f;
+            // only the four warps that share this TMEM lane quarter exchange anything: one named barrier per quarter
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");
             // ---- the four quarters of a point meet: log-normaliser, position of the uniform in the cumulative sum ----
             const float2* xr = sX + ((size_t)buf * 8) * 128 + prow;
             float sbs[8];
@@ -342,8 +348,7 @@ tc_diag_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz, int v
 #pragma unroll
             for (int b = 0; b < 8; ++b) { const float2 t = xr[b * 128]; sbs[b] = t.y * ex2_ftz(t.x - m); Ssum += sbs[b]; }   // 2^-inf = 0: empty blocks
             if (labels != nullptr) {
-                const double u = pvalid ? (uniforms ? uniforms[n] : philox_uniform(seed, point_offset + (uint64_t)n)) : 0.0;
-                const float thr = (float)u * Ssum;
+                const float thr = sU[buf * 128 + prow] * Ssum;
                 float before = 0.f;                                        // cumulative sum in front of this quarter
 #pragma unroll
                 for (int b = 0; b < 6; ++b) if (b < 2 * qtr) before += sbs[b];

@@ -228,6 +228,21 @@ class Session:
     def loglik(self, ops):
         return E.loglik(self.Z, ops)
 
+    def capture_meanfield_step(self):
+        """One mean-field iteration (batched posterior kernels -> operands -> fused sweep) captured in a CUDA graph: at the
+        sizes the reference ships (N ~ 1e3, K ~ 25) an iteration is ~30 kernel launches of microseconds each and the launch
+        latency is the whole cost.  Call after at least one eager iteration (buffers allocated, self.stat aliasing the sweep
+        buffer).  Returns (graph, outs): graph.replay() performs the iteration, `outs` are the tensors it refreshes."""
+        assert self.comm is None or self.comm.world == 1, 'graph capture of a sharded iteration is not supported'
+        buf = self.buf(False)
+        assert self.stat is buf.stat, 'run one eager iteration first'
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ops, outs = self.update_from_stats(MEANFIELD)
+            self.sweep(ops, hard=False)
+        return graph, outs
+
     # -- scalars ---------------------------------------------------------------------------
     def lower_bound(self, outs):
         """gating term + component terms (from the posterior kernels that produced the

@@ -293,7 +293,8 @@ class BayesianMixtureOfGaussians:
         return E.to_host(a).astype(np.float64)
 
     def meanfield_coordinate_descent(self, obs, randomize=True, maxiter=250, tol=1e-8,
-                                     progress_bar=True, process_id=0, comm=None, rtol=0., sample_likelihood=False):
+                                     progress_bar=True, process_id=0, comm=None, rtol=0., sample_likelihood=False,
+                                     graph=False):
         """gmm.py:261-287.  Per iteration: batched posterior kernels (statistics -> posterior,
         operands, lower-bound terms), then ONE fused E-step + statistics sweep.
         randomize=True draws the reference's npr.rand(K, N) on the host (seeded runs replay the reference);
@@ -303,7 +304,9 @@ class BayesianMixtureOfGaussians:
         FP64 statistics are accumulated with atomics in a run-dependent order, so at N ~ 1e7+ the bound jitters by
         ~1e-9 relative from sweep to sweep and an absolute 1e-8 can never fire.
         sample_likelihood=True also performs the reference's per-iteration likelihood.params = posterior.rvs()
-        draws (components, then gating) so the numpy.random stream advances as in the reference."""
+        draws (components, then gating) so the numpy.random stream advances as in the reference.
+        graph=True replays iterations 2.. from a CUDA graph of the first one (single process only): the same kernels on
+        the same buffers, without their launch latencies -- what bounds an iteration at the reference's own example sizes."""
         s = self._session(obs, comm)
         if randomize == 'device':
             s.stats_from_random_resp(seed=s.host_draw(lambda: int(npr.randint(1 << 30))))
@@ -314,9 +317,15 @@ class BayesianMixtureOfGaussians:
         vlb = []
         outs = None
         with tqdm(total=maxiter, desc=f'VI #{process_id + 1}', position=process_id, disable=not progress_bar) as pbar:
-            for _ in range(maxiter):
-                ops, outs = s.update_from_stats(MEANFIELD)
-                s.sweep(ops, hard=False)
+            cuda_graph = None
+            for it in range(maxiter):
+                if graph and comm is None and it == 1:
+                    cuda_graph, outs = s.capture_meanfield_step()
+                if cuda_graph is not None:
+                    cuda_graph.replay()
+                else:
+                    ops, outs = s.update_from_stats(MEANFIELD)
+                    s.sweep(ops, hard=False)
                 s.check(outs)
                 vlb.append(s.lower_bound(outs))
                 if sample_likelihood:

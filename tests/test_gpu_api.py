@@ -371,6 +371,21 @@ def test_nonpd_raises_linalgerror():
         lik.log_likelihood(np.zeros((4, 2)))
 
 
+@pytest.mark.parametrize('name', ['gmm_toy_vi_stick', 'gmm_sine_vi'])
+def test_gmm_meanfield_trajectory_from_cuda_graph(name, precision):
+    """meanfield_coordinate_descent(graph=True): iterations 2.. replayed from a CUDA graph of the first one give the
+    reference's lower-bound trajectory (gmm.py:261-287) like the eager path."""
+    g = load(name)
+    model = make_gmm(g)
+    T = int(g['iters'])
+    npr.seed(int(g['seed']))
+    vlb = model.meanfield_coordinate_descent(g['obs'], maxiter=T, tol=0., progress_bar=False, graph=True)
+    tol = TOL[precision]
+    close(vlb, g['vlb'], tol, 'lower bound (CUDA graph)')
+    for key, ref in zip(model.components.posterior.params, ('mus', 'kappas', 'psis', 'nus')):
+        close(key, g[f'post_{ref}_{T - 1}'], 10 * tol, 'posterior ' + ref)
+
+
 @pytest.mark.parametrize('name', ['gmm_toy_svi', 'gmm_toy_svi_stick'])
 def test_gmm_svi_trajectory_replays_reference(name, precision):
     """mixtures/gmm.py:300-336 with the reference's seeds (random.seed: minibatches of utils/data.py:9-12; numpy.random.seed:

@@ -20,5 +20,7 @@ for path in sys.argv[1:]:
         if d.get(k):
             print(' ' + k, json.dumps(d[k])[:600])
     if d.get('other_configs'):
-        for o in d['other_configs']:
-            print(' other', json.dumps(o)[:500])
+        for k, o in d['other_configs'].items():
+            r2 = (o.get('roofline') or {})
+            print(' other', k, json.dumps({kk: o.get(kk) for kk in ('ms_per_step', 'value', 'cuda_graph', 'error')}),
+                  {kk: r2.get(kk) for kk in ('frac', 'whole_sweep_frac', 'phase_ms_per_step')})
