@@ -195,7 +195,8 @@ def test_stats_tc_accumulates_into_stat():
 
 
 @pytest.mark.parametrize('hard', [False, True])
-@pytest.mark.parametrize('K,d,N', [(12, 32, 70000), (7, 128, 45000), (64, 16, 60000), (128, 9, 40000), (20, 21, 9000)])
+@pytest.mark.parametrize('K,d,N', [(12, 32, 70000), (7, 128, 45000), (64, 16, 60000), (128, 9, 40000), (20, 21, 9000), (40, 8, 5000),
+                                   (9, 50, 20000), (3, 23, 3000)])
 def test_sweep_tc_matches_cuda_cores_and_oracle(hard, K, d, N):
     """mimo_sweep on the tensor-core path == the CUDA-core FP32 path within FP32 tolerance,
     and the statistics / lower-bound term match the oracle."""
