@@ -381,7 +381,7 @@ class Ctx:
 def one_step(s, hard, rng, phase=None, vlbs=None):
     from mimo_b200.distributions.bayesian import MEANFIELD, GIBBS
     if hard:
-        var, gvar = s.draw_gibbs_variates()
+        var, gvar = s.draw_gibbs_variates('device')      # parameter variates from the device generator: no host read per sweep
         ops, outs = s.update_from_stats(GIBBS, variates=var, gating_variates=gvar)
         s.sweep(ops, hard=True, seed=int(rng.integers(1 << 30)), phase_ms=phase)
     else:
@@ -604,7 +604,7 @@ def time_e2e(cx, w, s, hard, steps, comm, tc_mode=None, cache=None):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             if hard:
-                var, gvar = s.draw_gibbs_variates()
+                var, gvar = s.draw_gibbs_variates('device')
                 _, outs = s.update_from_stats(GIBBS, variates=var, gating_variates=gvar)
             else:
                 _, outs = s.update_from_stats(MEANFIELD)
@@ -767,6 +767,8 @@ def main():
     warmup = max(3, args.warmup)
     config = dict(workload='%s: %s' % (name, w['desc']), N=w['N'], K=w['K'], d=w['d'], sweep=w['mode'],
                   inputs='resident FP32 data %.1f GB per sweep >> 126 MB L2 (no flush needed)' % (w['N'] * (w['d'] + w.get('o', 0)) * 4 / 1e9))
+    if w['mode'] == 'gibbs':
+        config['rng'] = 'labels: Philox4x32-10 keyed by the global point index; parameter variates: device generator (draw_gibbs_variates(\'device\'))'
     if args.n_override:
         config['INVALID'] = 'N overridden for debugging'
 

@@ -24,6 +24,11 @@ from .lingauss import (StackedLinearGaussiansWithPrecision, TiedLinearGaussiansW
 MEANFIELD, GIBBS, MAP, NONE = 0, 1, 2, 3
 
 
+def torch_full_mean(t):
+    """np.full_like(t, np.mean(t)) for a device tensor (tied degrees of freedom)."""
+    return t.mean().expand_as(t).contiguous()
+
+
 # ---------------------------------------------------------------------------------------
 # gating
 # ---------------------------------------------------------------------------------------
@@ -111,6 +116,11 @@ class CategoricalWithDirichlet(_GatingBase):
         # npr.dirichlet(alphas) == normalised standard_gamma(alphas) on the same stream
         return npr.standard_gamma(self.prior.alphas + counts)
 
+    def _draw_variates_device(self, counts, gen, prior_dev):
+        """the same gamma draws from the DEVICE generator (no host read of the counts): counts (K,) device FP64."""
+        import torch
+        return torch._standard_gamma(prior_dev[0] + counts, generator=gen)
+
     def _sgd_blend(self, counts, scale, step_size):
         self.posterior.nat_param = (1. - step_size) * self.posterior.nat_param \
             + step_size * (self.prior.nat_param + 1. / scale * counts)
@@ -131,6 +141,15 @@ class CategoricalWithStickBreaking(_GatingBase):
     def _draw_variates(self, counts):
         acc = np.hstack((np.cumsum(counts[::-1])[-2::-1], 0))
         return npr.beta((self.prior.gammas + counts)[:-1], (self.prior.deltas + acc)[:-1])
+
+    def _draw_variates_device(self, counts, gen, prior_dev):
+        """K - 1 Beta(gamma_k, delta_k) draws as g1 / (g1 + g2) of two device gamma draws."""
+        import torch
+        tail = torch.flip(torch.cumsum(torch.flip(counts, [0]), 0), [0])       # sum_{j >= k} counts
+        acc = torch.cat((tail[1:], tail.new_zeros(1)))
+        g1 = torch._standard_gamma((prior_dev[0] + counts)[:-1], generator=gen)
+        g2 = torch._standard_gamma((prior_dev[1] + acc)[:-1], generator=gen)
+        return g1 / (g1 + g2)
 
     def _sgd_blend(self, counts, scale, step_size):
         acc = np.hstack((np.cumsum(counts[::-1])[-2::-1], 0))
@@ -188,6 +207,19 @@ class _ComponentsBase:
     def _unit_weights(self, *data):
         return np.ones((self.size, len(data[0])))
 
+    def _wishart_variates_device(self, nus, d, extra, gen):
+        """draw_wishart_variates on the device: [normal(d(d-1)/2) | chisquare(nu - i), i < d | normal(extra)] per
+        component, chi-square(df) = 2 Gamma(df / 2); nus (K,) device FP64.  Not the reference's stream."""
+        import torch
+        K = nus.shape[0]
+        nt = d * (d - 1) // 2
+        var = torch.empty((K, nt + d + extra), dtype=torch.float64, device=nus.device)
+        var[:, :nt].normal_(generator=gen)
+        df = nus[:, None] - torch.arange(d, dtype=torch.float64, device=nus.device)[None, :]
+        var[:, nt:nt + d] = 2. * torch._standard_gamma(0.5 * df, generator=gen)
+        var[:, nt + d:].normal_(generator=gen)
+        return var
+
     def _counts_of(self, stat):
         return E.to_host(stat[:, self._feats().F - 1])
 
@@ -233,6 +265,12 @@ class StackedGaussiansWithNormalWisharts(_ComponentsBase):
         if self._tied:
             nus = np.full_like(nus, np.mean(nus))
         return draw_wishart_variates(nus, self.dim, self.dim)
+
+    def _draw_variates_device(self, counts, stat, gen, prior_dev):
+        nus = prior_dev[3] + counts
+        if self._tied:
+            nus = torch_full_mean(nus)
+        return self._wishart_variates_device(nus, self.dim, self.dim, gen)
 
     def _store(self, out, mode):
         self.posterior.params = tuple(E.to_host(out[k]) for k in ('m', 'kappa', 'psi', 'nu'))
@@ -405,6 +443,28 @@ class StackedGaussiansWithNormalGammas(_ComponentsBase):
             var[k, d:] = npr.normal(size=d)
         return var
 
+    def _draw_variates_device(self, counts, stat, gen, prior_dev):
+        """_draw_variates with the posterior shape / rate formed on the device from the packed statistics
+        [sum r z | sum r z^2 | sum r] and the draws from the device generator: no host read per sweep."""
+        import torch
+        d = self.dim
+        m0, k0, a0, b0 = prior_dev
+        if self.bug_compat:
+            al, be = a0, b0
+        else:
+            n = stat[:, 2 * d][:, None]
+            kap = k0 + n
+            m = (k0 * m0 + stat[:, :d]) / kap
+            al = a0 + 0.5 * n
+            be = b0 + 0.5 * (stat[:, d:2 * d] + k0 * m0 ** 2 - kap * m ** 2)
+            if self._tied:
+                al = al.mean(0, keepdim=True).expand_as(al)
+                be = be.mean(0, keepdim=True).expand_as(be)
+        var = torch.empty((self.size, 2 * d), dtype=torch.float64, device=stat.device)
+        var[:, :d] = torch._standard_gamma(al.contiguous(), generator=gen) / be
+        var[:, d:].normal_(generator=gen)
+        return var
+
     def _store(self, out, mode):
         self.posterior.params = tuple(E.to_host(out[k]) for k in ('m', 'kappa', 'alpha', 'beta'))
         if out.get('lik_mu') is not None:
@@ -504,6 +564,12 @@ class StackedLinearGaussiansWithMatrixNormalWisharts(_ComponentsBase):
         if self._tied:
             nus = np.full_like(nus, np.mean(nus))
         return draw_wishart_variates(nus, self.row_dim, self.row_dim * self.column_dim)
+
+    def _draw_variates_device(self, counts, stat, gen, prior_dev):
+        nus = prior_dev[3] + counts
+        if self._tied:
+            nus = torch_full_mean(nus)
+        return self._wishart_variates_device(nus, self.row_dim, self.row_dim * self.column_dim, gen)
 
     def _store(self, out, mode):
         self.posterior.params = tuple(E.to_host(out[k]) for k in ('M', 'K', 'psi', 'nu'))

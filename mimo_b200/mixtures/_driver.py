@@ -290,9 +290,27 @@ class Session:
         dist.broadcast_object_list(box, src=src, group=c.group)
         return box[0]
 
-    def draw_gibbs_variates(self):
+    def seed_parameters(self, seed):
+        """(re)seed the device generator of draw_gibbs_variates('device'); every rank of a sharded run must pass the
+        same seed (they then draw the same variates from the same all-reduced statistics: no broadcast)."""
+        self._param_gen = torch.Generator(device=self.Z.device)
+        self._param_gen.manual_seed(int(seed))
+
+    def draw_gibbs_variates(self, rng='numpy'):
         """host draws from the global numpy.random stream in the reference's order:
-        every part (per component), then the gating.  Sharded: drawn once, on rank 0."""
+        every part (per component), then the gating.  Sharded: drawn once, on rank 0.
+        rng='device': the same variates (gamma / chi-square / normal, shaped by the current statistics) from a device
+        generator, with no host read of the statistics and no broadcast -- what a sweep of a few milliseconds needs
+        (cfg3: the host draw + broadcast cost as much as the sweep at 8 GPUs).  Not the reference's stream."""
+        if rng == 'device':
+            if getattr(self, '_param_gen', None) is None:
+                self.seed_parameters(0)
+            counts = self.stat[:, self.count_feature]
+            var = [p.w._draw_variates_device(counts, self.stat, self._param_gen, self.part_priors[i])
+                   for i, p in enumerate(self.parts)]
+            gvar = self.gating._draw_variates_device(counts, self._param_gen, self.gating_prior) \
+                if self.gating is not None else None
+            return var, gvar
         counts = self.counts_host()
         stat_host = E.to_host(self.stat) if self.family == 'diag' else None
 

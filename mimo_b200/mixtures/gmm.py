@@ -222,15 +222,19 @@ class BayesianMixtureOfGaussians:
 
     # -- Gibbs -------------------------------------------------------------------------------
     def resample(self, obs, init_labels='prior', maxiter=1, progress_bar=True, process_id=0, comm=None,
-                 label_rng='numpy'):
+                 label_rng='numpy', param_rng='numpy'):
         """gmm.py:207-225.  Random variates come from the global numpy.random stream in the
         reference's order (components per k, gating, one uniform per point), so a seeded run
         reproduces the reference's chain; all arithmetic on them is on the device.
         Sharded (comm): rank 0's stream is the chain's stream -- parameter variates and label uniforms are drawn
         there and broadcast, so an identically seeded 1-rank run gives the same chain.
         label_rng='philox': label uniforms from the kernel's counter-based generator keyed by the global point
-        index (no N host variates per sweep; not the reference's stream)."""
+        index (no N host variates per sweep; not the reference's stream).
+        param_rng='device': the parameter variates from a device generator seeded once from numpy.random (no host
+        read of the statistics and no broadcast per sweep; not the reference's stream)."""
         s = self._session(obs, comm)
+        if param_rng == 'device':
+            s.seed_parameters(s.host_draw(lambda: int(npr.randint(1 << 30))))
         lo = comm.point_offset if comm is not None else 0
         n_glob = comm.N_global if (comm is not None and comm.N_global is not None) else s.N
         if init_labels == 'random':
@@ -245,7 +249,7 @@ class BayesianMixtureOfGaussians:
             s.stats_from_labels(labels)
         with tqdm(total=maxiter, desc=f'Init #{process_id + 1}', position=process_id, disable=not progress_bar) as pbar:
             for _ in range(maxiter):
-                var, gvar = s.draw_gibbs_variates()
+                var, gvar = s.draw_gibbs_variates(param_rng)
                 ops, outs = s.update_from_stats(GIBBS, variates=var, gating_variates=gvar, want_lik=True)
                 s.check(outs)
                 u, seed = s.label_uniforms(label_rng)

@@ -668,6 +668,146 @@ def ilr_prediction(x, weights, models_post, prediction='average', dist='gaussian
     return mu, covar, nlpd
 
 
+# ---------------------------------------------------------------------------
+# hierarchical Normal-Wishart: K tied Gaussians whose means have scaled-precision priors N(tau, (kappa_k Lambda)^-1)
+# and whose shared (tau, Lambda) has a Normal-Wishart hyper-prior -- SURVEY 8 f4 (mixtures/hgmm.py:118-295)
+# ---------------------------------------------------------------------------
+
+def hnw_hyper_update(hyper_prior, kappas0, mus, xk, nk, xxk):
+    """distributions/bayesian.py:671-684 (the same block at :643-656 and :709-722): hyper-posterior (rho, kappa, psi, nu)
+    of the shared (tau, Lambda) given the component means `mus` and the weighted statistics.  hyper_prior = (mu0, kappa0,
+    psi0, nu0) of one Normal-Wishart; kappas0 (K,) are the scaled-precision prior's kappas."""
+    mu0, k0, psi0, nu0 = hyper_prior
+    K = mus.shape[0]
+    rho = np.sum(kappas0[:, None] * mus + k0 * mu0, axis=0) / np.sum(kappas0 + k0)
+    kappa = np.sum(kappas0 + k0) / K
+    dm = mu0[None, :] - mus
+    spread = np.sum((k0 * kappas0 / (k0 + kappas0))[:, None, None] * np.einsum('kd,kl->kdl', dm, dm), axis=0) / K
+    inner = np.linalg.inv(psi0) + spread + np.sum(xxk, axis=0) / K - np.einsum('kd,kl->dl', mus, xk) / K \
+        - np.einsum('kd,kl->dl', xk, mus) / K + np.einsum('k,kd,kl->dl', nk, mus, mus) / K
+    return rho, kappa, np.linalg.inv(inner), np.sum(nu0 + nk + 1) / K
+
+
+def hnw_meanfield_update(hyper_prior, hyper_post, kappas0, xk, nk, xxk, nb_iter):
+    """bayesian.py:662-684: nb_iter alternations of the variational E-step on the component means (their posterior
+    precision scale kappa_k + n_k, mean pulled towards the hyper-posterior's location) and the hyper-posterior update.
+    Returns (posterior mus, posterior kappas, hyper-posterior params)."""
+    post_k = kappas0 + nk
+    mus = None
+    for _ in range(nb_iter):
+        mus = (kappas0[:, None] * hyper_post[0][None, :] + xk) / post_k[:, None]
+        hyper_post = hnw_hyper_update(hyper_prior, kappas0, mus, xk, nk, xxk)
+    return mus, post_k, hyper_post
+
+
+def hnw_expected_loglik(x, hyper_post, post_mus, post_omegas):
+    """bayesian.py:731-749: E_q log N(x | mu_k, Lambda) with Lambda ~ W(psi, nu) of the hyper-posterior and
+    mu_k ~ N(post_mus[k], post_omegas[k]^-1).  post_omegas = posterior.kappas * posterior.lmbdas (gaussian.py:954-955)."""
+    _, _, psi, nu = hyper_post
+    d = x.shape[1]
+    EL = nu * psi
+    E_logdet = 0.5 * wishart_expected_logdet(psi[None], np.array([nu]))[0]
+    dx = x[None, :, :] - post_mus[:, None, :]
+    quad = np.einsum('knd,dl,knl->kn', dx, EL, dx, optimize=True)
+    tr = np.einsum('dl,kld->k', EL, np.linalg.inv(post_omegas))
+    return -0.5 * d * LOG_2PI + E_logdet - 0.5 * quad - 0.5 * tr[:, None]
+
+
+def scaled_gaussian_entropy(omega):
+    """distributions/gaussian.py:1029-1031."""
+    d = omega.shape[0]
+    return 0.5 * d * np.log(2.0 * np.pi * np.e) - np.sum(np.log(np.diag(sp_cholesky(omega, lower=False))))
+
+
+def hnw_vlb(hyper_prior, hyper_post, kappas0, post_mus, post_omegas, entropy_omegas=None):
+    """bayesian.py:751-781: the component-parameter terms of the lower bound; the hyper-posterior's entropy and
+    cross-entropy are counted once per component, as the reference's loop does.  entropy_omegas: the precisions the
+    entropy term sees -- the reference caches the Cholesky factor of kappa * lmbda (gaussian.py:957-961) and only a
+    new lmbda resets the cache (:947-951), so within a mean-field run the entropy keeps the factor of the FIRST
+    evaluation while kappa moves on (quirk q11); None = the current precisions."""
+    K, d = post_mus.shape
+    stack = lambda p: (np.asarray(p[0])[None], np.atleast_1d(p[1]), np.asarray(p[2])[None], np.atleast_1d(p[3]))  # noqa: E731
+    hyper = nw_vlb(stack(hyper_prior), stack(hyper_post))[0]
+    rho, kap, psi, nu = hyper_post
+    E_logdet = wishart_expected_logdet(psi[None], np.array([nu]))[0]
+    vlb = 0.0
+    for k in range(K):
+        vlb += hyper + scaled_gaussian_entropy((post_omegas if entropy_omegas is None else entropy_omegas)[k]) - 0.5 * d * LOG_2PI
+        vlb += 0.5 * d * np.log(kappas0[k]) + 0.5 * E_logdet - 0.5 * kappas0[k] * d / kap
+        dm = post_mus[k] - rho
+        EL = kappas0[k] * nu * psi
+        vlb += -0.5 * dm @ EL @ dm - 0.5 * np.trace(EL @ np.linalg.inv(post_omegas[k]))
+    return vlb
+
+
+def hnw_resample(hyper_prior, hyper_post, kappas0, xk, nk, xxk, nb_iter, normal, chisquare):
+    """bayesian.py:623-659 with the random draws made explicit: normal(size) / chisquare(df) are called in the
+    reference's order -- per sub-iteration K hyper-posterior draws (Wishart: normal(d(d-1)/2), d chisquare; then
+    normal(d) for tau: composite.py:82-86), then K draws normal(d) of the component means (gaussian.py:973-975).
+    Returns (mus, lmbdas, posterior (mus, kappas), hyper-posterior params)."""
+    K, d = xk.shape
+    nt = d * (d - 1) // 2
+    mus = lmbdas = post_mus = None
+    post_k = kappas0 + nk
+    for _ in range(nb_iter):
+        rho, kap, psi, nu = hyper_post
+        taus, lmbdas = np.zeros((K, d)), np.zeros((K, d, d))
+        for k in range(K):
+            nrm = normal(nt)
+            chi = np.array([chisquare(nu - i) for i in range(d)])
+            taus[k], lmbdas[k] = nw_rvs_from_variates(rho, kap, psi, nu, nrm, chi, normal(d))
+        post_mus = (kappas0[:, None] * taus + xk) / post_k[:, None]
+        mus = np.zeros((K, d))
+        for k in range(K):
+            U = sp_cholesky(post_k[k] * lmbdas[k], lower=False)
+            mus[k] = post_mus[k] + normal(d) @ np.linalg.inv(U).T
+        hyper_post = hnw_hyper_update(hyper_prior, kappas0, mus, xk, nk, xxk)
+    return mus, lmbdas, (post_mus, post_k), hyper_post
+
+
+def hgmm_log_weights(gating):
+    """mixtures/hgmm.py:171-176: expected log gating weights; gating = ('dirichlet', alphas) | ('stick', gammas, deltas)."""
+    if gating[0] == 'dirichlet':
+        return dirichlet_expected_log(gating[1])
+    return stick_expected_log(gating[1], gating[2])[0]
+
+
+def hgmm_meanfield(obs, resp, gating_prior, hyper_prior, kappas0, post_lmbdas, iters, subiters, hyper_post=None,
+                   stale_entropy=True):
+    """mixtures/hgmm.py:186-225, 264-289: mean-field coordinate descent of the mixture with a hierarchical prior.
+    gating_prior = ('dirichlet', alphas0) | ('stick', gammas0, deltas0); post_lmbdas (K, d, d) are the precisions the
+    posterior object of the component means carries (the constructor's draw: the mean-field update never refreshes
+    them, bayesian.py:662-689).  stale_entropy: quirk q11 of hnw_vlb, as the reference behaves.
+    Returns dict(vlb, mus, kappas, hyper, gating, resp, ell)."""
+    hyper_post = hyper_prior if hyper_post is None else hyper_post
+    vlb, out, ent_omegas = [], {}, None
+    for _ in range(iters):
+        xk, nk, xxk, _ = gauss_full_wstats(obs, resp)
+        mus, post_k, hyper_post = hnw_meanfield_update(hyper_prior, hyper_post, kappas0, xk, nk, xxk, subiters)
+        omegas = post_k[:, None, None] * post_lmbdas
+        counts = np.sum(resp, axis=1)
+        if gating_prior[0] == 'dirichlet':
+            gpost = ('dirichlet', dirichlet_posterior(gating_prior[1], counts))
+            gv = dirichlet_vlb(gating_prior[1], gpost[1])
+        else:
+            gpost = ('stick',) + tuple(stick_posterior(gating_prior[1], gating_prior[2], counts))
+            gv = stick_vlb(gating_prior[1:], gpost[1:])
+        ell = hnw_expected_loglik(obs, hyper_post, mus, omegas)
+        joint = ell + hgmm_log_weights(gpost)[:, None]
+        resp = responsibilities(joint)[0]
+        if gpost[0] == 'dirichlet':
+            lab = vlb_labels_dirichlet(resp, dirichlet_expected_log(gpost[1]))
+        else:
+            _, Es, Er = stick_expected_log(gpost[1], gpost[2])
+            lab = vlb_labels_stick(resp, Es, Er)
+        if ent_omegas is None or not stale_entropy:
+            ent_omegas = omegas
+        vlb.append(gv + hnw_vlb(hyper_prior, hyper_post, kappas0, mus, omegas, ent_omegas) + lab + np.sum(resp * ell))
+        out = dict(mus=mus, kappas=post_k, hyper=hyper_post, gating=gpost, resp=resp, ell=joint)
+    out['vlb'] = np.array(vlb)
+    return out
+
+
 def chunked(fn, n, chunk):
     """Apply fn(slice) over point chunks and concatenate along the point axis
     (axis 1 for (K,N) outputs).  Exact: every per-point quantity is

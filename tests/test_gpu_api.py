@@ -421,3 +421,68 @@ def test_svi_runs_and_improves():
         assert len(vlb) == 30 and np.isfinite(vlb).all() and vlb[-1] > vlb[0]
     finally:
         mimo_b200.set_default_precision('fp32')
+
+
+@pytest.mark.parametrize('family', ['diag', 'full', 'full_stick'])
+def test_gibbs_device_parameter_rng(family):
+    """resample(param_rng='device', label_rng='philox'): no host variates per sweep.  The device variates are the same
+    distributions in the same layout as the host draws: (i) the sampled parameters equal the oracle's sampling
+    restatement applied to the downloaded device variates, (ii) the same seed gives the same chain, (iii) the chain
+    finds the blobs."""
+    import torch
+    import mimo_b200
+    from mimo_b200.distributions.bayesian import GIBBS
+    mimo_b200.set_default_precision('fp64')
+    try:
+        g = load('dgmm_gibbs' if family == 'diag' else ('gmm_d16_gibbs_stick' if family == 'full_stick' else 'gmm_toy_gibbs'))
+        K, d = int(g['K']), int(g['d'])
+        make = (lambda: make_dgmm(g, False)) if family == 'diag' else (lambda: make_gmm(g))
+        chains = []
+        for rep in range(2):
+            model = make()
+            npr.seed(5)
+            model.resample(g['obs'], init_labels='random', maxiter=6, progress_bar=False, label_rng='philox', param_rng='device')
+            chains.append((model.labels_.copy(), np.array(model.components.likelihood.mus)))
+        assert np.array_equal(chains[0][0], chains[1][0])
+        close(chains[0][1], chains[1][1], 1e-9, 'same seed, same chain (statistics are summed with FP64 atomics: last-bit order effects)')
+        # one update from explicit statistics: the kernel's draw == the oracle's restatement on the same variates
+        model = make()
+        s = model._session(g['obs'])
+        s.stats_from_labels(g['labels_init'])
+        s.seed_parameters(3)
+        var, gvar = s.draw_gibbs_variates('device')
+        assert isinstance(var[0], torch.Tensor) and var[0].is_cuda and var[0].dtype == torch.float64
+        ops, outs = s.update_from_stats(GIBBS, variates=var, gating_variates=gvar, want_lik=True)
+        s.check(outs)
+        s.store(outs, GIBBS)
+        v = var[0].cpu().numpy()
+        w = orc.one_hot(g['labels_init'], K)
+        if family == 'diag':
+            nat = orc.add_stats(orc.ng_std_to_nat(*model.components.prior.params), orc.gauss_diag_wstats(g['obs'], w))
+            post = orc.ng_nat_to_std(nat)
+            lam = v[:, :d]
+            mu = post[0] + v[:, d:] / np.sqrt(post[1] * lam)
+            close(model.components.likelihood.lmbdas_diags, lam, 1e-12, 'device gamma draws = sampled precisions')
+            close(model.components.likelihood.mus, mu, 1e-9, 'sampled means')
+            assert abs(np.mean(lam * post[3] / post[2]) - 1.0) < 0.2       # E[gamma(a, 1/b)] = a / b
+        else:
+            nat = orc.add_stats(orc.nw_std_to_nat(*model.components.prior.params), orc.gauss_full_wstats(g['obs'], w))
+            post = orc.nw_nat_to_std(nat)
+            nt = d * (d - 1) // 2
+            for k in range(K):
+                mu_k, lm_k = orc.nw_rvs_from_variates(post[0][k], post[1][k], post[2][k], post[3][k],
+                                                      v[k, :nt], v[k, nt:nt + d], v[k, nt + d:])
+                close(model.components.likelihood.lmbdas[k], lm_k, 1e-8, 'sampled precision')
+                close(model.components.likelihood.mus[k], mu_k, 1e-8, 'sampled mean')
+            df = post[3][:, None] - np.arange(d)[None, :]
+            assert np.all(v[:, nt:nt + d] > 0) and abs(np.mean(v[:, nt:nt + d] / df) - 1.0) < 0.5   # E[chi2(df)] = df
+        gv = gvar.cpu().numpy()
+        counts = w.sum(1)
+        if family == 'full_stick':
+            close(model.gating.likelihood.probs, orc.stick_probs_from_betas(gv), 1e-12, 'stick probabilities')
+            assert gv.shape == (K - 1,) and np.all((gv > 0) & (gv < 1))
+        else:
+            close(model.gating.likelihood.probs, orc.dirichlet_probs_from_gammas(gv), 1e-12, 'dirichlet probabilities')
+            assert gv.shape == (K,) and np.all(gv > 0) and counts.sum() == len(g['obs'])
+    finally:
+        mimo_b200.set_default_precision('fp32')

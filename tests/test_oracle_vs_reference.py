@@ -289,3 +289,77 @@ def test_vlb_identity_and_labels_term(ref):
         else:
             es, er = gating.expected_log_likelihood()
             close(orc.vlb_labels_stick(resp, es, er), model.variational_lowerbound_labels(resp))
+
+
+# ---- hierarchical Normal-Wishart mixtures (mixtures/hgmm.py, bayesian.py:595-793) ----------------------
+def _ref_hgmm(ref, K, d, stick, kappa_prior=1e-2):
+    D, M = ref.D, ref.M
+    if stick:
+        gating = D.CategoricalWithStickBreaking(dim=K, prior=D.TruncatedStickBreaking(dim=K, gammas=np.ones(K), deltas=2. * np.ones(K)))
+    else:
+        gating = D.CategoricalWithDirichlet(dim=K, prior=D.Dirichlet(dim=K, alphas=np.ones(K)))
+    hp = D.NormalWishart(dim=d, mu=np.zeros(d), kappa=1e-2, psi=np.eye(d), nu=d + 1 + 1e-8)
+    pr = D.TiedGaussiansWithScaledPrecision(size=K, dim=d, kappas=kappa_prior * (1. + np.arange(K)))
+    comp = D.TiedGaussiansWithHierarchicalNormalWisharts(size=K, dim=d, hyper_prior=hp, prior=pr)
+    return M.BayesianMixtureOfGaussiansWithHierarchicalPrior(size=K, dim=d, gating=gating, components=comp)
+
+
+def _gating_prior(model):
+    p = model.gating.prior
+    return ('stick', p.gammas, p.deltas) if hasattr(p, 'gammas') else ('dirichlet', p.alphas)
+
+
+@pytest.mark.parametrize('K,d,N,stick', [(4, 2, 300, False), (5, 3, 200, True)])
+def test_hgmm_meanfield(ref, K, d, N, stick):
+    rng = np.random.default_rng(3)
+    centres = 4. * rng.standard_normal((K, d))
+    obs = centres[rng.integers(0, K, N)] + rng.standard_normal((N, d))
+    npr.seed(7)
+    model = _ref_hgmm(ref, K, d, stick)
+    comp = model.components
+    lm0 = comp.posterior.lmbdas.copy()
+    resp0 = npr.rand(K, N)
+    resp0 /= resp0.sum(0)
+    npr.seed(11)
+    state = npr.get_state()
+    npr.rand(K, N)                                   # consumed by the reference's randomize=True
+    npr.set_state(state)
+    vlb = model.meanfield_coordinate_descent(obs, randomize=True, maxiter=6, maxsubiter=4, tol=0., progress_bar=False)
+    npr.seed(11)
+    r0 = npr.rand(K, N)
+    r0 /= r0.sum(0)
+    out = orc.hgmm_meanfield(obs, r0, _gating_prior(model), tuple(comp.hyper_prior.params), comp.prior.kappas, lm0, 6, 4)
+    close(out['vlb'], vlb, 1e-9)
+    close(out['mus'], comp.posterior.mus)
+    close(out['kappas'], comp.posterior.kappas)
+    for a, b in zip(out['hyper'], comp.hyper_posterior.params):
+        close(a, b, 1e-9)
+    close(out['ell'], model.expected_log_complete_likelihood(obs), 1e-9)
+    # single pieces
+    close(orc.hnw_expected_loglik(obs, out['hyper'], out['mus'], out['kappas'][:, None, None] * lm0), comp.expected_log_likelihood(obs), 1e-9)
+    ent = np.stack([dd.omega_chol.T @ dd.omega_chol for dd in comp.posterior.dists])        # the cached factors (q11)
+    close(orc.hnw_vlb(tuple(comp.hyper_prior.params), out['hyper'], comp.prior.kappas, out['mus'], comp.posterior.omegas, ent),
+          comp.variational_lowerbound(), 1e-9)
+
+
+@pytest.mark.parametrize('K,d,N', [(4, 2, 200), (3, 3, 120)])
+def test_hnw_resample(ref, K, d, N):
+    rng = np.random.default_rng(4)
+    obs = 3. * rng.standard_normal((K, d))[rng.integers(0, K, N)] + rng.standard_normal((N, d))
+    labels = rng.integers(0, K, N)
+    npr.seed(5)
+    comp = _ref_hgmm(ref, K, d, False).components
+    w = orc.one_hot(labels, K)
+    hp0, hq0 = tuple(comp.hyper_prior.params), tuple(comp.hyper_posterior.params)
+    npr.seed(21)
+    comp.resample(obs, w, nb_iter=3)
+    npr.seed(21)
+    xk, nk, xxk, _ = orc.gauss_full_wstats(obs, w)
+    mus, lmbdas, (pm, pk), hq = orc.hnw_resample(hp0, hq0, comp.prior.kappas, xk, nk, xxk, 3,
+                                                 lambda n: npr.normal(size=n), lambda df: npr.chisquare(df, size=1)[0])
+    close(mus, comp.likelihood.mus, 1e-9)
+    close(lmbdas, comp.likelihood.lmbdas, 1e-9)
+    close(pm, comp.posterior.mus, 1e-9)
+    close(pk, comp.posterior.kappas)
+    for a, b in zip(hq, comp.hyper_posterior.params):
+        close(a, b, 1e-9)
