@@ -5,13 +5,15 @@ from .categorical import Categorical  # noqa: F401
 from .matrix import MatrixNormalWithPrecision  # noqa: F401
 from .gaussian import (GaussianWithPrecision, StackedGaussiansWithPrecision, TiedGaussiansWithPrecision,  # noqa: F401
                        GaussianWithDiagonalPrecision, StackedGaussiansWithDiagonalPrecision,
-                       TiedGaussiansWithDiagonalPrecision)
+                       TiedGaussiansWithDiagonalPrecision, GaussianWithScaledPrecision, TiedGaussiansWithScaledPrecision)
 from .lingauss import (LinearGaussianWithPrecision, StackedLinearGaussiansWithPrecision,  # noqa: F401
-                       TiedLinearGaussiansWithPrecision)
+                       TiedLinearGaussiansWithPrecision, StackedAffineLinearGaussiansWithPrecision)
 from .composite import (NormalWishart, StackedNormalWisharts, TiedNormalWisharts,  # noqa: F401
                         NormalGamma, StackedNormalGammas, TiedNormalGammas,
                         MatrixNormalWishart, StackedMatrixNormalWisharts, TiedMatrixNormalWisharts)
 from .bayesian import (CategoricalWithDirichlet, CategoricalWithStickBreaking,  # noqa: F401
                        GaussianWithNormalWishart, StackedGaussiansWithNormalWisharts, TiedGaussiansWithNormalWisharts,
                        StackedGaussiansWithNormalGammas, TiedGaussiansWithNormalGammas,
-                       StackedLinearGaussiansWithMatrixNormalWisharts, TiedLinearGaussiansWithMatrixNormalWisharts)
+                       StackedLinearGaussiansWithMatrixNormalWisharts, TiedLinearGaussiansWithMatrixNormalWisharts,
+                       GaussianWithHierarchicalNormalWishart, TiedGaussiansWithHierarchicalNormalWisharts,
+                       TiedAffineLinearGaussiansWithMatrixNormalWisharts)

@@ -15,6 +15,7 @@ import numpy as np
 import numpy.random as npr
 
 from .. import _engine as E
+from ..utils.abstraction import Statistics as E_stats
 from .categorical import Categorical
 from .composite import draw_wishart_variates
 from .gaussian import (StackedGaussiansWithPrecision, TiedGaussiansWithPrecision,
@@ -22,6 +23,11 @@ from .gaussian import (StackedGaussiansWithPrecision, TiedGaussiansWithPrecision
 from .lingauss import (StackedLinearGaussiansWithPrecision, TiedLinearGaussiansWithPrecision, ExpertLayout)
 
 MEANFIELD, GIBBS, MAP, NONE = 0, 1, 2, 3
+
+
+def torch_long():
+    import torch
+    return torch.int64
 
 
 def torch_full_mean(t):
@@ -635,3 +641,459 @@ class StackedLinearGaussiansWithMatrixNormalWisharts(_ComponentsBase):
 class TiedLinearGaussiansWithMatrixNormalWisharts(StackedLinearGaussiansWithMatrixNormalWisharts):
     _tied = True
     _likelihood_cls = TiedLinearGaussiansWithPrecision
+
+
+# ---------------------------------------------------------------------------------------
+# hierarchical Normal-Wishart
+# ---------------------------------------------------------------------------------------
+def _hyper_nw_update(hyper_prior, kappas0, mus, xk, nk, sxx):
+    """(rho, kappa, psi, nu) of the shared (tau, Lambda) given component means `mus` (K, d) and the statistics
+    xk = sum r x (K, d), nk = sum r (K,), sxx = sum_k sum r x x^T (d, d): the closed form of bayesian.py:671-684
+    (= :643-656, :709-722) with the sums over k taken once."""
+    mu0, k0, psi0, nu0 = hyper_prior
+    K = mus.shape[0]
+    tot = np.sum(kappas0 + k0)
+    rho = (kappas0 @ mus + K * k0 * mu0) / tot
+    dm = mu0[None, :] - mus
+    c = k0 * kappas0 / (k0 + kappas0)
+    cross = mus.T @ xk
+    inner = np.linalg.inv(psi0) + ((dm * c[:, None]).T @ dm + sxx - cross - cross.T + (mus * nk[:, None]).T @ mus) / K
+    return rho, tot / K, np.linalg.inv(inner), np.sum(nu0 + nk + 1) / K
+
+
+class TiedGaussiansWithHierarchicalNormalWisharts(_ComponentsBase):
+    """K Gaussians with one shared precision Lambda: means mu_k ~ N(tau, (kappa_k Lambda)^-1) (`prior`, a
+    TiedGaussiansWithScaledPrecision) and (tau, Lambda) ~ Normal-Wishart (`hyper_prior`)   (bayesian.py:595-793).
+
+    What is per point runs on the GPU: the weighted statistics (mimo_stats_soft, or the fused sweep of the mixture
+    drivers) and the expected log-likelihood (the whitened quad-form kernels with rows chol(nu psi) shared by all
+    components, offsets -U m_k and the trace / log-det constants folded into cst).  The nested sub-iterations between
+    the component means and the hyper-posterior only touch sum r x (K, d), sum r (K) and sum_k sum r x x^T (d, d): the
+    (K, F) statistics are reduced over k on the device and these K (d + 1) + F numbers cross to the host, where the
+    sub-iterations run in FP64 (O(nb_iter (K d^2 + d^3)), independent of N)."""
+    _tied = True
+    _shardable = False
+    nb_iter = 5                     # sub-iterations of a sweep driven by mixtures/hgmm.py (its maxsubiter)
+    track_bound = True              # evaluate the lower-bound term in every sweep update (hgmm.py:207 does; hilr.py:194 does
+                                    # not -- and the FIRST evaluation fixes the cached factors of quirk q11)
+
+    def __init__(self, size, dim, hyper_prior, prior, precision=None):
+        self.size, self.dim = size, dim
+        draws = [hyper_prior.rvs() for _ in range(size)]                     # the reference's stream order (:602-605)
+        prior.mus = np.stack([t for t, _ in draws])
+        prior.lmbdas = np.stack([l for _, l in draws])
+        self.hyper_prior = hyper_prior
+        self.hyper_posterior = copy.deepcopy(hyper_prior)
+        self.prior = prior
+        self.posterior = copy.deepcopy(prior)
+        self.likelihood = TiedGaussiansWithPrecision(size=size, dim=dim, mus=self.prior.rvs(sizes=size * [1]),
+                                                     lmbdas=prior.lmbdas, precision=precision)
+
+    # -- statistics ------------------------------------------------------------------------
+    def _feats(self):
+        return E.quad_features(self.dim)
+
+    def _own_layout(self):
+        idx = E.identity_map(self.dim, self.dim)
+        return dict(stat_idx=idx, col_map=idx, Dp=self.dim + 1, row_off=0)
+
+    def _rows(self, mode):
+        return self.dim
+
+    def _prior_dev(self, dist=None):
+        return None
+
+    def _reduced(self, stat, layout=None):
+        """device (K, F) packed statistics -> host (xk, nk, sum_k xxT_k): K (d + 1) + d (d + 1) / 2 numbers cross the
+        boundary.  layout['stat_idx']: columns of zt holding this part's variables and the constant (a mixture of linear
+        experts keeps the input density's variables inside [x | y | 1]); default: the part's own [z | 1]."""
+        d = self.dim
+        cols = list(range(d)) + [d] if layout is None else [int(c) for c in E.to_host(layout['stat_idx'])]
+        key = tuple(cols)
+        if getattr(self, '_red_key', None) != key:
+            v, c = cols[:d], cols[d]
+            il = np.tril_indices(d)
+            self._red_key = key
+            self._red_lin = E.to_dev(np.array([E.tri(a, c) for a in v] + [E.tri(c, c)], dtype=np.int64), torch_long())
+            self._red_quad = E.to_dev(np.array([E.tri(v[i], v[j]) for i, j in zip(*il)], dtype=np.int64), torch_long())
+        lin = E.to_host(stat[:, self._red_lin])
+        tri = E.to_host(stat[:, self._red_quad].sum(0))
+        sxx = np.zeros((d, d))
+        il = np.tril_indices(d)
+        sxx[il] = tri
+        sxx[(il[1], il[0])] = tri
+        return lin[:, :d], lin[:, d], sxx
+
+    def _suff(self, data, weights):
+        return self._reduced(self._stats_from(weights, data))
+
+    # -- the three coordinate updates on reduced statistics ----------------------------------------
+    def _meanfield(self, xk, nk, sxx, nb_iter):
+        """bayesian.py:662-684."""
+        hp, k0 = tuple(self.hyper_prior.params), self.prior.kappas
+        self.posterior.kappas = k0 + nk
+        for _ in range(nb_iter):
+            self.posterior.mus = (k0[:, None] * self.hyper_posterior.mu[None, :] + xk) / (k0 + nk)[:, None]
+            self.hyper_posterior.params = _hyper_nw_update(hp, k0, self.posterior.mus, xk, nk, sxx)
+
+    def _gibbs(self, xk, nk, sxx, nb_iter):
+        """bayesian.py:623-659; the draws come from the global numpy.random stream in the reference's order."""
+        hp, k0 = tuple(self.hyper_prior.params), self.prior.kappas
+        mus = lmbdas = None
+        for _ in range(nb_iter):
+            draws = [self.hyper_posterior.rvs() for _ in range(self.size)]
+            self.prior.mus = np.stack([t for t, _ in draws])
+            lmbdas = np.stack([l for _, l in draws])
+            self.prior.lmbdas = lmbdas
+            self.posterior.nat_param = self.prior.nat_param + E_stats([xk, nk])
+            self.posterior.lmbdas = lmbdas
+            mus = self.posterior.rvs(sizes=self.size * [1])
+            self.hyper_posterior.params = _hyper_nw_update(hp, k0, mus, xk, nk, sxx)
+        self.likelihood.mus, self.likelihood.lmbdas = mus, lmbdas
+
+    def _sgd(self, xk, nk, sxx, nb_iter, scale, step_size):
+        """bayesian.py:691-729."""
+        hp, k0 = tuple(self.hyper_prior.params), self.prior.kappas
+        xk, nk, sxx = xk / scale, nk / scale, sxx / scale
+        for _ in range(nb_iter):
+            tau, lmbda = self.hyper_posterior.mean()
+            self.prior.mus = np.stack(self.size * [tau])
+            self.prior.lmbdas = np.stack(self.size * [lmbda])
+            self.posterior.nat_param = (1. - step_size) * self.posterior.nat_param \
+                + step_size * (self.prior.nat_param + E_stats([xk, nk]))
+            self.posterior.lmbdas = np.stack(self.size * [lmbda])
+            params = _hyper_nw_update(hp, k0, self.posterior.mean(), xk, nk, sxx)
+            self.hyper_posterior.nat_param = (1. - step_size) * self.hyper_posterior.nat_param \
+                + step_size * self.hyper_posterior.std_to_nat(params)
+
+    def _set_mode(self):
+        _, lmbda = self.hyper_posterior.mode()
+        self.likelihood.mus = self.posterior.mode()
+        self.likelihood.lmbdas = np.stack(self.size * [lmbda])
+
+    # -- reference API -------------------------------------------------------------------
+    def resample(self, data, labels, nb_iter=5):
+        self._gibbs(*self._suff(data, labels), nb_iter)
+
+    def meanfield_update(self, data, weights, nb_iter=25):
+        self._meanfield(*self._suff(data, weights), nb_iter)
+        self._set_mode()
+
+    def meanfield_sgd(self, data, weights, nb_iter, scale, step_size):
+        self._sgd(*self._suff(data, weights), nb_iter, scale, step_size)
+        self._set_mode()
+
+    # -- operands of E_q log N(x | mu_k, Lambda) -------------------------------------------------
+    def _expected_constants(self):
+        """per component: 1/2 (E log det Lambda - log det E Lambda) - 1/2 tr(E Lambda omega_k^-1), what
+        bayesian.py:731-749 adds to the Gaussian log-density of precision E Lambda = nu psi at the posterior means."""
+        from scipy.special import digamma
+        _, _, psi, nu = self.hyper_posterior.params
+        d = self.dim
+        logdet_psi = np.linalg.slogdet(psi)[1]
+        e_logdet = np.sum(digamma((nu - np.arange(d)) / 2.)) + d * np.log(2.) + logdet_psi
+        tr = np.einsum('dl,kld->k', nu * psi, np.linalg.inv(self.posterior.omegas))
+        return 0.5 * (e_logdet - (d * np.log(nu) + logdet_psi)) - 0.5 * tr
+
+    def _posterior_operands(self, ops, layout, dist=None):
+        _, _, psi, nu = self.hyper_posterior.params
+        info = E.operands_gauss(ops, E.to_dev(self.posterior.mus), E.to_dev(np.stack(self.size * [nu * psi])),
+                                row_off=layout['row_off'], col_map=layout['col_map'])
+        ops.cst += E.to_dev(self._expected_constants(), ops.cst.dtype)
+        return info
+
+    def _likelihood_operands(self, ops, layout):
+        return E.operands_gauss(ops, E.to_dev(self.likelihood.mus), E.to_dev(self.likelihood.lmbdas),
+                                row_off=layout['row_off'], col_map=layout['col_map'])
+
+    def expected_log_likelihood(self, x):
+        precision = self._precision()
+        ops = E.QuadOperands(self.size, self.dim, self.dim, precision)
+        self._posterior_operands(ops, self._own_layout()).check()
+        return E.to_host(E.loglik(E.to_dev(np.nan_to_num(x), E.tdtype(precision)), ops)).astype(np.float64)
+
+    # -- hooks of the sweep session (mixtures/_driver.py) ------------------------------------------
+    def _update(self, stat, F, layout, mode, ops=None, variates=None, prior_dev=None, want_lik=False, want_vlb=True):
+        red = self._reduced(stat, layout)
+        if mode == GIBBS:
+            self._gibbs(*red, self.nb_iter)
+            info = self._likelihood_operands(ops, layout) if ops is not None else E.Info()
+            return dict(info=info, vlb=None)
+        assert mode == MEANFIELD, 'hierarchical components support Gibbs and mean-field sweeps'
+        self._meanfield(*red, self.nb_iter)
+        info = self._posterior_operands(ops, layout) if ops is not None else E.Info()
+        vlb = E.zeros((self.size,))
+        if want_vlb and self.track_bound:
+            vlb[0] = float(self.variational_lowerbound())
+        return dict(info=info, vlb=vlb)
+
+    def _store(self, out, mode):
+        if mode == MEANFIELD:
+            self._set_mode()
+
+    # -- lower bound, predictive -------------------------------------------------------------
+    def variational_lowerbound(self):
+        """bayesian.py:751-781 in closed form; the entropy of the means' posteriors uses the cached Cholesky factors of
+        the reference (quirk q11, gaussian.py GaussianWithScaledPrecision.omega_chol)."""
+        from scipy.special import digamma
+        d, K = self.dim, self.size
+        rho, kap, psi, nu = self.hyper_posterior.params
+        k0 = self.prior.kappas
+        hyper = self.hyper_posterior.entropy() - self.hyper_posterior.cross_entropy(self.hyper_prior)
+        e_logdet = np.sum(digamma((nu - np.arange(d)) / 2.)) + d * np.log(2.) + np.linalg.slogdet(psi)[1]
+        ent = sum(dist.entropy() for dist in self.posterior.dists)
+        dm = self.posterior.mus - rho[None, :]
+        el = nu * psi
+        quad = np.einsum('kd,dl,kl->k', dm, el, dm)
+        tr = np.einsum('dl,kld->k', el, np.linalg.inv(self.posterior.omegas))
+        return K * hyper + ent - 0.5 * K * d * np.log(2. * np.pi) + np.sum(0.5 * d * np.log(k0) + 0.5 * e_logdet
+                                                                        - 0.5 * k0 * d / kap - 0.5 * k0 * (quad + tr))
+
+    def posterior_predictive_gaussian(self):
+        _, _, psi, nu = self.hyper_posterior.params
+        return self.posterior.mus, np.stack(self.size * [(nu - self.dim + 1) * psi])
+
+    def log_posterior_predictive_gaussian(self, x):
+        mus, lmbdas = self.posterior_predictive_gaussian()
+        return StackedGaussiansWithPrecision(self.size, self.dim, mus, lmbdas,
+                                             precision=self.likelihood.precision).log_likelihood(np.array(x))
+
+
+class GaussianWithHierarchicalNormalWishart:
+    """one Gaussian whose mean has a scaled-precision prior under a Normal-Wishart hyper-prior (bayesian.py:503-592):
+    the K = 1 case of the updates above with the reference's slightly different bookkeeping (the mean's posterior
+    carries the current precision draw / expectation)."""
+
+    def __init__(self, dim, hyper_prior, prior, precision=None):
+        from .gaussian import GaussianWithPrecision
+        self.dim = dim
+        tau, lmbda = hyper_prior.rvs()
+        prior.mu, prior.lmbda = tau, lmbda
+        self.hyper_prior = hyper_prior
+        self.hyper_posterior = copy.deepcopy(hyper_prior)
+        self.prior = prior
+        self.posterior = copy.deepcopy(prior)
+        self.likelihood = GaussianWithPrecision(dim=dim, mu=self.prior.rvs(), lmbda=lmbda, precision=precision)
+
+    def empirical_bayes(self, data):
+        raise NotImplementedError
+
+    def _suff(self, data):
+        """sum x, n, sum x x^T of the rows without NaN, computed on the GPU."""
+        x, n, xx, _ = self.likelihood.statistics(data)
+        return np.asarray(x)[None, :], np.atleast_1d(float(n)), np.asarray(xx)
+
+    def _hyper(self, mu, xk, nk, sxx):
+        return _hyper_nw_update(tuple(self.hyper_prior.params), np.atleast_1d(self.prior.kappa), mu[None, :], xk, nk, sxx)
+
+    def resample(self, data, nb_iter=1):
+        xk, nk, sxx = self._suff(data)
+        mu = lmbda = None
+        for _ in range(nb_iter):
+            _, lmbda = self.hyper_posterior.rvs()
+            self.posterior.kappa = self.prior.kappa + nk[0]
+            self.posterior.mu = (self.prior.kappa * self.hyper_prior.mu + xk[0]) / (self.prior.kappa + nk[0])
+            self.posterior.lmbda = lmbda
+            mu = self.posterior.rvs()
+            self.hyper_posterior.params = self._hyper(mu, xk, nk, sxx)
+        self.likelihood.params = mu, lmbda
+
+    def meanfield_update(self, data, nb_iter=25):
+        xk, nk, sxx = self._suff(data)
+        for _ in range(nb_iter):
+            self.posterior.kappa = self.prior.kappa + nk[0]
+            self.posterior.mu = (self.prior.kappa * self.hyper_posterior.mu + xk[0]) / (self.prior.kappa + nk[0])
+            self.posterior.lmbda = self.hyper_posterior.wishart.mean()
+            self.hyper_posterior.params = self._hyper(self.posterior.mu, xk, nk, sxx)
+        _, lmbda = self.hyper_posterior.mean()
+        self.likelihood.params = self.posterior.rvs(), lmbda
+        return []
+
+    def expected_log_likelihood(self, x):
+        raise NotImplementedError
+
+    def variational_lowerbound(self, x):
+        raise NotImplementedError
+
+
+class TiedAffineLinearGaussiansWithMatrixNormalWisharts(_ComponentsBase):
+    """K linear-Gaussian experts y = A x + c_k + eps that share the slope A and the precision Lambda and keep their own
+    offsets c_k   (bayesian.py:1222-1522): slope_prior Matrix-Normal on A, offset_prior scaled-precision Gaussians on
+    c_k, precision_prior Wishart on Lambda.
+
+    Per point: the weighted second moments of [x | y | 1] (mimo_stats_soft or the fused sweep) and the expected
+    log-likelihood, which is the Matrix-Normal-Wishart expectation of the affine expert [A | c_k] with the block-
+    diagonal column precision diag(K, kappa_k) -- the same mimo_mnw_posterior operands as the plain experts.  The
+    nested sub-iterations between slope / precision and the offsets run on the (K, F) statistics in FP64 on the host
+    (O(nb_iter K c^3), independent of N)."""
+    _tied = True
+    _shardable = False
+    nb_iter = 25
+
+    def __init__(self, size, column_dim, row_dim, slope_prior, offset_prior, precision_prior, likelihood=None, precision=None):
+        from .lingauss import StackedAffineLinearGaussiansWithPrecision
+        from .composite import StackedMatrixNormalWisharts
+        self.size, self.column_dim, self.row_dim = size, column_dim, row_dim
+        As = np.zeros((size, row_dim, column_dim))
+        lmbdas = np.zeros((size, row_dim, row_dim))
+        for k in range(size):                                   # the reference's stream order (:1233-1241)
+            lmbdas[k] = precision_prior.rvs()
+            slope_prior.V = lmbdas[k]
+            As[k] = slope_prior.rvs()
+        offset_prior.lmbdas = lmbdas
+        cs = offset_prior.rvs(sizes=size * [1])
+        self.slope_prior, self.offset_prior, self.precision_prior = slope_prior, offset_prior, precision_prior
+        self.likelihood = StackedAffineLinearGaussiansWithPrecision(size, column_dim, row_dim, As, cs, lmbdas, precision=precision)
+        self.slope_posterior = copy.deepcopy(slope_prior)
+        self.offset_posterior = copy.deepcopy(offset_prior)
+        self.precision_posterior = copy.deepcopy(precision_prior)
+        self.layout = ExpertLayout(column_dim + 1, row_dim, affine=True)
+        self._S = StackedMatrixNormalWisharts
+
+    # -- the expert [A | c_k] as a stacked Matrix-Normal-Wishart (what :1391-1417 builds) -------------------------
+    def _joint(self, slope, offset, precision):
+        from scipy.linalg import block_diag
+        K = self.size
+        Ms = np.stack([np.hstack((slope.M, offset.mus[k][:, None])) for k in range(K)])
+        Ks = np.stack([block_diag(slope.K, np.array([[offset.kappas[k]]])) for k in range(K)])
+        return self._S(K, self.column_dim + 1, self.row_dim, Ms=Ms, Ks=Ks, psis=np.stack(K * [precision.psi]),
+                       nus=np.array(K * [precision.nu], dtype=np.float64))
+
+    def _mnw(self):
+        prior = self._joint(self.slope_prior, self.offset_prior, self.precision_prior)
+        w = StackedLinearGaussiansWithMatrixNormalWisharts(self.size, self.column_dim + 1, self.row_dim, prior=prior,
+                                                           likelihood=self.likelihood._combined(), affine=True)
+        w.posterior = self._joint(self.slope_posterior, self.offset_posterior, self.precision_posterior)
+        return w
+
+    # -- statistics ------------------------------------------------------------------------
+    def _feats(self):
+        return E.quad_features(self.layout.D)
+
+    def _own_layout(self):
+        dev = self.layout.dev()
+        return dict(stat_idx=dev['stat_idx'], col_map=dev['col_map'], Dp=self.layout.D + 1, row_off=0)
+
+    def _rows(self, mode):
+        return self.row_dim + self.column_dim + 1 if mode == MEANFIELD else self.row_dim
+
+    def _prior_dev(self, dist=None):
+        return None
+
+    def _moments(self, stat):
+        """device (K, F) packed statistics of [x | y | 1] -> dict of the host arrays the updates are written in."""
+        from .gaussian import unpack_quad
+        c = self.column_dim
+        yxt, xxt, yy, n = self.layout.split(unpack_quad(E.to_host(stat), self.layout.D + 1))     # xt = [x ; 1]
+        return dict(xm=xxt[:, :c, c], ym=yxt[:, :, c], n=n, yx=yxt[:, :, :c], xx=xxt[:, :c, :c], yy=yy)
+
+    def _suff(self, x, y, weights):
+        return self._moments(self._stats_from(weights, x, y))
+
+    # -- coordinate updates (bayesian.py:1260-1383) ---------------------------------------------
+    def _slope_precision(self, m, cs):
+        """slope posterior (M, K) and precision posterior (psi, nu) given the offsets cs (K, o)."""
+        K = self.size
+        M0, K0 = self.slope_prior.M, self.slope_prior.K
+        psi0, nu0 = self.precision_prior.psi, self.precision_prior.nu
+        G = (M0 @ K0)[None] + m['yx'] - cs[:, :, None] * m['xm'][:, None, :]
+        Kk = K0[None] + m['xx']
+        GKi = G @ np.linalg.inv(Kk)
+        self.slope_posterior.M = GKi.sum(0) / K
+        self.slope_posterior.K = Kk.sum(0) / K
+        yc = np.einsum('kd,kl->kdl', m['ym'], cs)
+        resid = m['yy'] - yc - yc.transpose(0, 2, 1) + m['n'][:, None, None] * np.einsum('kd,kl->kdl', cs, cs)
+        dc = cs - self.offset_prior.mus
+        pull = self.offset_prior.kappas[:, None, None] * np.einsum('kd,kl->kdl', dc, dc)
+        inner = np.linalg.inv(psi0) + M0 @ self.slope_posterior.K @ M0.T \
+            + (resid + pull - GKi @ G.transpose(0, 2, 1)).sum(0) / K
+        self.precision_posterior.psi = np.linalg.inv(inner)
+        self.precision_posterior.nu = np.sum(nu0 + m['n'] + 1) / K
+
+    def _offsets(self, m, As, lmbdas):
+        k0, mu0 = self.offset_prior.kappas, self.offset_prior.mus
+        self.offset_posterior.mus = (k0[:, None] * mu0 + m['ym'] - np.einsum('kdl,kl->kd', As, m['xm'])) / (k0 + m['n'])[:, None]
+        self.offset_posterior.kappas = k0 + m['n']
+        self.offset_posterior.lmbdas = lmbdas
+
+    def _gibbs(self, m, nb_iter):
+        K = self.size
+        As = lmbdas = cs = None
+        for _ in range(nb_iter):
+            cs = self.offset_posterior.rvs(sizes=K * [1])
+            self._slope_precision(m, cs)
+            As = np.zeros((K, self.row_dim, self.column_dim))
+            lmbdas = np.zeros((K, self.row_dim, self.row_dim))
+            for k in range(K):
+                lmbdas[k] = self.precision_posterior.rvs()
+                self.slope_posterior.V = lmbdas[k]
+                As[k] = self.slope_posterior.rvs()
+            self._offsets(m, As, lmbdas)
+        self.likelihood.As, self.likelihood.cs, self.likelihood.lmbdas = As, cs, lmbdas
+
+    def _meanfield(self, m, nb_iter):
+        K = self.size
+        for _ in range(nb_iter):
+            self._slope_precision(m, self.offset_posterior.mean())
+            lmbda = self.precision_posterior.mean()
+            self.slope_posterior.V = lmbda
+            self._offsets(m, np.stack(K * [self.slope_posterior.mean()]), np.stack(K * [lmbda]))
+
+    def _set_mode(self):
+        K = self.size
+        self.likelihood.As = np.stack(K * [self.slope_posterior.mode()])
+        self.likelihood.lmbdas = np.stack(K * [self.precision_posterior.mode()])
+        self.likelihood.cs = self.offset_posterior.mode()
+
+    # -- reference API -------------------------------------------------------------------
+    def resample(self, x, y, z, nb_iter=25):
+        self._gibbs(self._suff(x, y, z), nb_iter)
+
+    def meanfield_update(self, x, y, weights, nb_iter=25):
+        self._meanfield(self._suff(x, y, weights), nb_iter)
+        self._set_mode()
+
+    def meanfield_sgd(self, x, y, weights, nb_iter, scale, step_size):
+        raise NotImplementedError
+
+    def expected_log_likelihood(self, x, y):
+        return self._mnw().expected_log_likelihood(x, y)
+
+    def variational_lowerbound(self):
+        w = self._mnw()
+        return w.posterior.entropy() - w.posterior.cross_entropy(w.prior)
+
+    def posterior_predictive_gaussian(self, x):
+        return self._mnw().posterior_predictive_gaussian(x)
+
+    def log_posterior_predictive_gaussian(self, x, y):
+        from .gaussian import LOG_2PI
+        mus, lmbdas = self.posterior_predictive_gaussian(x)
+        dy = np.asarray(y)[None] - mus
+        return -0.5 * self.row_dim * LOG_2PI + 0.5 * np.linalg.slogdet(lmbdas)[1] - 0.5 * np.einsum('knd,kndl,knl->kn', dy, lmbdas, dy)
+
+    # -- hooks of the sweep session ------------------------------------------------------------
+    def _posterior_operands(self, ops, layout, dist=None):
+        return self._mnw()._posterior_operands(ops, layout)
+
+    def _likelihood_operands(self, ops, layout):
+        return E.operands_lingauss(ops, E.to_dev(self.likelihood._affine_As()), E.to_dev(self.likelihood.lmbdas),
+                                   layout['row_off'], layout['col_map'])
+
+    def _update(self, stat, F, layout, mode, ops=None, variates=None, prior_dev=None, want_lik=False, want_vlb=True):
+        m = self._moments(stat)
+        if mode == GIBBS:
+            self._gibbs(m, self.nb_iter)
+            info = self._likelihood_operands(ops, layout) if ops is not None else E.Info()
+            return dict(info=info, vlb=None)
+        assert mode == MEANFIELD, 'tied affine experts support Gibbs and mean-field sweeps'
+        self._meanfield(m, self.nb_iter)
+        info = self._posterior_operands(ops, layout) if ops is not None else E.Info()
+        vlb = E.zeros((self.size,))
+        if want_vlb:
+            vlb.copy_(E.to_dev(np.asarray(self.variational_lowerbound(), dtype=np.float64)))
+        return dict(info=info, vlb=vlb)
+
+    def _store(self, out, mode):
+        if mode == MEANFIELD:
+            self._set_mode()

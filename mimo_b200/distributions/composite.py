@@ -175,6 +175,18 @@ class NormalWishart:
                                      np.asarray(self.psi)[None], np.atleast_1d(self.nu))
 
     @property
+    def gaussian(self):
+        """the location factor (composite.py:26); a view: assign through `params`, not through the view."""
+        from .gaussian import GaussianWithPrecision
+        return GaussianWithPrecision(self.dim, mu=self.mu)
+
+    @property
+    def wishart(self):
+        """the precision factor (composite.py:27); a view."""
+        from .wishart import Wishart
+        return Wishart(self.dim, psi=self.psi, nu=self.nu)
+
+    @property
     def params(self):
         return self.mu, self.kappa, self.psi, self.nu
 

@@ -513,3 +513,216 @@ class GaussianWithDiagonalPrecision:
         st = self._stack()
         st.max_likelihood(data, w[None, :])
         self.mu, self.lmbda_diag = st.mus[0], st.lmbdas_diags[0]
+
+
+# ---------------------------------------------------------------------------------------
+# scaled precision: the prior over a Gaussian mean that shares the likelihood's precision up to a factor kappa
+# (hierarchical mixtures).  Host-side parameter objects of a few K d^2 numbers: the per-point work of the
+# models that use them runs in the sweep kernels (distributions/bayesian.py: TiedGaussiansWithHierarchicalNormalWisharts).
+# ---------------------------------------------------------------------------------------
+class GaussianWithScaledPrecision:
+    """N(mu, (kappa lmbda)^-1)   (gaussian.py:890-1035).  The reference caches the Cholesky factor of kappa * lmbda
+    and resets the cache only when lmbda is assigned, not kappa (:947-961): `omega_chol` keeps that behaviour
+    (quirk q11) because the lower bound of the hierarchical mixture depends on it; `omega` is always current."""
+
+    def __init__(self, dim, kappa, mu=None, lmbda=None):
+        self.dim, self.mu, self.kappa = dim, mu, kappa
+        self._lmbda = lmbda
+        self._omega_chol = None
+
+    @property
+    def params(self):
+        return self.mu, self.kappa
+
+    @params.setter
+    def params(self, values):
+        self.mu, self.kappa = values
+
+    @property
+    def nb_params(self):
+        raise NotImplementedError
+
+    @staticmethod
+    def std_to_nat(params):
+        return Stats([params[1] * params[0], params[1]])
+
+    @staticmethod
+    def nat_to_std(natparam):
+        return natparam[0] / natparam[1], natparam[1]
+
+    @property
+    def nat_param(self):
+        return self.std_to_nat(self.params)
+
+    @nat_param.setter
+    def nat_param(self, natparam):
+        self.params = self.nat_to_std(natparam)
+
+    @property
+    def lmbda(self):
+        return self._lmbda
+
+    @lmbda.setter
+    def lmbda(self, value):
+        self._lmbda = value
+        self._omega_chol = None
+
+    @property
+    def omega(self):
+        return self.kappa * self.lmbda
+
+    @property
+    def omega_chol(self):
+        if self._omega_chol is None:
+            self._omega_chol = np.linalg.cholesky(self.omega).T
+        return self._omega_chol
+
+    @property
+    def omega_chol_inv(self):
+        return np.linalg.inv(self.omega_chol)
+
+    @property
+    def sigma(self):
+        ci = self.omega_chol_inv
+        return ci @ ci.T
+
+    def mean(self):
+        return self.mu
+
+    def mode(self):
+        return self.mu
+
+    @property
+    def base(self):
+        return np.power(2. * np.pi, -self.dim / 2.)
+
+    def log_base(self):
+        return np.log(self.base)
+
+    def rvs(self, size=1):
+        size = self.dim if size == 1 else (size, self.dim)
+        return self.mu + npr.normal(size=size).dot(self.omega_chol_inv.T)
+
+    def statistics(self, data, fold=True):
+        if not isinstance(data, np.ndarray):
+            stats = [self.statistics(d, fold=fold) for d in data]
+            return sum(stats[1:], stats[0]) if fold else stats
+        data = data[_clean_rows(data)]
+        return Stats([data.sum(0), data.shape[0]]) if fold else Stats([data, np.ones((data.shape[0],))])
+
+    def weighted_statistics(self, data, weights):
+        if not isinstance(data, np.ndarray):
+            stats = [self.weighted_statistics(d, w) for d, w in zip(data, weights)]
+            return sum(stats[1:], stats[0])
+        good = _clean_rows(data)
+        w = np.asarray(weights)[good]
+        return Stats([w @ data[good], np.sum(w)])
+
+    def log_partition(self):
+        return 0.5 * self.mu @ self.lmbda @ self.mu - np.sum(np.log(np.diag(self.omega_chol)))
+
+    def log_likelihood(self, x):
+        if not isinstance(x, np.ndarray):
+            return [self.log_likelihood(xi) for xi in x]
+        bads = np.isnan(np.atleast_2d(x)).any(axis=1)
+        x = np.nan_to_num(x).reshape((-1, self.dim))
+        om = self.omega
+        out = x @ (om @ self.mu) - 0.5 * np.einsum('nd,nd->n', x @ om, x)
+        out[bads] = 0.
+        return out - self.log_partition() + self.log_base()
+
+    def entropy(self):
+        return 0.5 * self.dim * np.log(2. * np.pi * np.e) - np.sum(np.log(np.diag(self.omega_chol)))
+
+    def max_likelihood(self, data, weights=None):
+        raise NotImplementedError
+
+
+class TiedGaussiansWithScaledPrecision:
+    """K of the above (gaussian.py:1038-1202); `dists` are live per-component objects, as in the reference."""
+
+    def __init__(self, size, dim, kappas, mus=None, lmbdas=None):
+        self.size, self.dim = size, dim
+        pick = lambda v, k: None if v is None else v[k]                      # noqa: E731
+        self.dists = [GaussianWithScaledPrecision(dim, pick(kappas, k), pick(mus, k), pick(lmbdas, k)) for k in range(size)]
+
+    def _get(self, name):
+        return np.array([getattr(dist, name) for dist in self.dists])
+
+    def _set(self, name, value):
+        for k, dist in enumerate(self.dists):
+            setattr(dist, name, value[k, ...])
+
+    mus = property(lambda self: self._get('mu'), lambda self, v: self._set('mu', v))
+    kappas = property(lambda self: self._get('kappa'), lambda self, v: self._set('kappa', v))
+    lmbdas = property(lambda self: self._get('lmbda'), lambda self, v: self._set('lmbda', v))
+    omegas = property(lambda self: self._get('omega'))
+    omegas_chol = property(lambda self: self._get('omega_chol'))
+    omegas_chol_ins = property(lambda self: self._get('omega_chol_inv'))
+    sigmas = property(lambda self: self._get('sigma'))
+    base = property(lambda self: self._get('base'))
+
+    @property
+    def params(self):
+        return self.mus, self.kappas
+
+    @params.setter
+    def params(self, values):
+        self.mus, self.kappas = values
+
+    @property
+    def nb_params(self):
+        raise NotImplementedError
+
+    def std_to_nat(self, params):
+        mus, kappas = params
+        return Stats([np.asarray(kappas)[:, None] * np.asarray(mus), np.asarray(kappas)])
+
+    def nat_to_std(self, natparam):
+        return natparam[0] / natparam[1][:, None], natparam[1]
+
+    @property
+    def nat_param(self):
+        return self.std_to_nat(self.params)
+
+    @nat_param.setter
+    def nat_param(self, natparam):
+        self.params = self.nat_to_std(natparam)
+
+    def rvs(self, sizes):
+        return np.vstack([dist.rvs(size) for dist, size in zip(self.dists, sizes)])
+
+    def mean(self):
+        return self.mus
+
+    def mode(self):
+        return self.mus
+
+    def log_base(self):
+        return np.log(self.base)
+
+    def statistics(self, data, fold=True):
+        if not isinstance(data, np.ndarray):
+            stats = [self.statistics(d, fold=fold) for d in data]
+            return sum(stats[1:], stats[0]) if fold else stats
+        x, n = self.dists[0].statistics(data, fold=fold)
+        return Stats([np.array(self.size * [x]), np.array(self.size * [n])])
+
+    def weighted_statistics(self, data, weights):
+        if not isinstance(data, np.ndarray):
+            stats = [self.weighted_statistics(d, w) for d, w in zip(data, weights)]
+            return sum(stats[1:], stats[0])
+        good = _clean_rows(data)
+        w = np.asarray(weights)[:, good]
+        return Stats([w @ data[good], np.sum(w, axis=1)])
+
+    def log_partition(self):
+        return np.array([dist.log_partition() for dist in self.dists])
+
+    def log_likelihood(self, x):
+        if not isinstance(x, np.ndarray):
+            return [self.log_likelihood(xi) for xi in x]
+        return np.stack([dist.log_likelihood(x) for dist in self.dists])
+
+    def max_likelihood(self, data, weights):
+        raise NotImplementedError

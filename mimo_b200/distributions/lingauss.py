@@ -257,3 +257,57 @@ class LinearGaussianWithPrecision:
         st = self._stack()
         st.max_likelihood(x, y, w[None, :])
         self.A, self.lmbda = st.As[0], st.lmbdas[0]
+
+
+class StackedAffineLinearGaussiansWithPrecision:
+    """y = A_k x + c_k + eps with slope and offset kept apart (lingauss.py:576-745): the likelihood object of the
+    tied-slope experts of the hierarchical mixtures.  On the device it is the affine expert
+    [A_k | c_k] of StackedLinearGaussiansWithPrecision: same operands, same kernels."""
+
+    def __init__(self, size, column_dim, row_dim, As=None, cs=None, lmbdas=None, precision=None):
+        self.size, self.column_dim, self.row_dim, self.precision = size, column_dim, row_dim, precision
+        self.As, self.cs, self.lmbdas = As, cs, lmbdas
+        self.layout = ExpertLayout(column_dim + 1, row_dim, affine=True)
+        self.affine = True
+
+    @property
+    def params(self):
+        return self.As, self.cs, self.lmbdas
+
+    @params.setter
+    def params(self, values):
+        self.As, self.cs, self.lmbdas = values
+
+    @property
+    def input_dim(self):
+        return self.column_dim
+
+    @property
+    def output_dim(self):
+        return self.row_dim
+
+    def _affine_As(self):
+        """(K, o, c + 1): [A_k | c_k], what the operand kernels take."""
+        return np.concatenate((np.asarray(self.As, dtype=np.float64), np.asarray(self.cs, dtype=np.float64)[:, :, None]), axis=2)
+
+    def _combined(self):
+        return StackedLinearGaussiansWithPrecision(self.size, self.column_dim + 1, self.row_dim, As=self._affine_As(),
+                                                   lmbdas=self.lmbdas, affine=True, precision=self.precision)
+
+    def predict(self, x):
+        return self._combined().predict(x)
+
+    def mean(self, x):
+        return self.predict(x)
+
+    def mode(self, x):
+        return self.predict(x)
+
+    def rvs(self, x):
+        return self._combined().rvs(x)
+
+    def log_likelihood(self, x, y):
+        return self._combined().log_likelihood(x, y)
+
+    def weighted_statistics(self, x, y, weights):
+        return self._combined().weighted_statistics(x, y, weights)

@@ -56,7 +56,8 @@ class _LikPart:
         if self.kind == 'basis':
             return E.operands_gauss(ops, E.to_dev(self.lik.mus), E.to_dev(self.lik.lmbdas),
                                     row_off=layout['row_off'], col_map=layout['col_map'])
-        return E.operands_lingauss(ops, E.to_dev(self.lik.As), E.to_dev(self.lik.lmbdas),
+        As = self.lik._affine_As() if hasattr(self.lik, '_affine_As') else self.lik.As      # slope and offset kept apart (hilr)
+        return E.operands_lingauss(ops, E.to_dev(As), E.to_dev(self.lik.lmbdas),
                                    layout['row_off'], layout['col_map'])
 
 

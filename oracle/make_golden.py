@@ -469,5 +469,215 @@ def main():
     pointwise_case('pointwise_d16', K=9, d=16, N=200, seed=42)
 
 
+# ---- hierarchical mixtures (mixtures/hgmm.py, distributions/bayesian.py:595-793) -------------------------
+def hgmm_model(K, d, stick, ctor_seed):
+    """examples/hgmm/vi_component.py:42-60 with a parameterised size; returns the model and what its constructor drew."""
+    npr.seed(ctor_seed)
+    if stick:
+        gating = D.CategoricalWithStickBreaking(dim=K, prior=D.TruncatedStickBreaking(dim=K, gammas=np.ones(K), deltas=2. * np.ones(K)))
+    else:
+        gating = D.CategoricalWithDirichlet(dim=K, prior=D.Dirichlet(dim=K, alphas=np.ones(K)))
+    hp = D.NormalWishart(dim=d, mu=np.zeros(d), kappa=1e-2, psi=np.eye(d), nu=d + 1 + 1e-8)
+    pr = D.TiedGaussiansWithScaledPrecision(size=K, dim=d, kappas=1e-2 * (1. + np.arange(K)))
+    comp = D.TiedGaussiansWithHierarchicalNormalWisharts(size=K, dim=d, hyper_prior=hp, prior=pr)
+    model = M.BayesianMixtureOfGaussiansWithHierarchicalPrior(size=K, dim=d, gating=gating, components=comp)
+    rec = dict(K=K, d=d, stick=int(stick), ctor_seed=ctor_seed, kappas0=pr.kappas.copy(),
+               hyper_mu0=hp.gaussian.mu, hyper_kappa0=hp.kappa, hyper_psi0=hp.wishart.psi, hyper_nu0=hp.wishart.nu,
+               init_prior_mus=comp.prior.mus.copy(), init_prior_lmbdas=comp.prior.lmbdas.copy(),
+               init_lik_mus=comp.likelihood.mus.copy(), init_probs=gating.likelihood.probs.copy())
+    rec.update(gating_prior_arrays(gating))
+    return model, rec
+
+
+def hier_state(model, rec, tag):
+    comp = model.components
+    rec[f'post_mus_{tag}'], rec[f'post_kappas_{tag}'] = comp.posterior.mus.copy(), comp.posterior.kappas.copy()
+    for n, p in zip(('rho', 'kappa', 'psi', 'nu'), comp.hyper_posterior.params):
+        rec[f'hyper_{n}_{tag}'] = np.array(p)
+    rec[f'lik_mus_{tag}'], rec[f'lik_lmbdas_{tag}'] = comp.likelihood.mus.copy(), comp.likelihood.lmbdas.copy()
+    g = model.gating
+    if gating_kind(g) == 'dirichlet':
+        rec[f'gate_alphas_{tag}'] = g.posterior.alphas.copy()
+    else:
+        rec[f'gate_gammas_{tag}'], rec[f'gate_deltas_{tag}'] = g.posterior.gammas.copy(), g.posterior.deltas.copy()
+
+
+def hgmm_vi_case(name, x, K, stick, iters, subiters, ctor_seed, seed):
+    """mixtures/hgmm.py:186-215; the oracle's restatement is asserted against the run while recording."""
+    model, rec = hgmm_model(K, x.shape[1], stick, ctor_seed)
+    comp = model.components
+    lm0 = comp.posterior.lmbdas.copy()
+    rec.update(obs=x, iters=iters, subiters=subiters, seed=seed)
+    npr.seed(seed)
+    vlb = model.meanfield_coordinate_descent(x, randomize=True, maxiter=iters, maxsubiter=subiters, tol=0., progress_bar=False)
+    rec['vlb'] = np.array(vlb)
+    hier_state(model, rec, 'end')
+    rec['ell_end'] = model.expected_log_complete_likelihood(x)
+    rec['resp_end'] = model.expected_responsibilities(x)
+    rec['comp_vlb_end'] = comp.variational_lowerbound()
+    npr.seed(seed)
+    r0 = npr.rand(K, len(x))
+    r0 /= r0.sum(0)
+    gp = ('stick', model.gating.prior.gammas, model.gating.prior.deltas) if stick else ('dirichlet', model.gating.prior.alphas)
+    out = orc.hgmm_meanfield(x, r0, gp, tuple(comp.hyper_prior.params), comp.prior.kappas, lm0, iters, subiters)
+    close(out['vlb'], vlb)
+    close(out['mus'], comp.posterior.mus)
+    close(out['ell'], rec['ell_end'])
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'vlb', vlb[0], '->', vlb[-1])
+
+
+def hgmm_gibbs_case(name, x, K, stick, sweeps, subiters, ctor_seed, seed):
+    """mixtures/hgmm.py:137-161."""
+    model, rec = hgmm_model(K, x.shape[1], stick, ctor_seed)
+    rec.update(obs=x, sweeps=sweeps, subiters=subiters, seed=seed)
+    npr.seed(seed)
+    model.resample(x, maxiter=sweeps, maxsubiter=subiters, progress_bar=False)
+    hier_state(model, rec, 'end')
+    rec['probs_end'] = model.gating.likelihood.probs.copy()
+    npr.seed(seed + 1)
+    lp, lab = model.resample_labels(x)
+    rec['log_prob_end'], rec['labels_next'] = lp, lab.astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'label counts', np.bincount(lab, minlength=K))
+
+
+def hgmm_svi_case(name, x, K, stick, iters, subiters, step_size, ctor_seed, seed):
+    """mixtures/hgmm.py:228-262 (full-batch natural-gradient steps)."""
+    model, rec = hgmm_model(K, x.shape[1], stick, ctor_seed)
+    rec.update(obs=x, iters=iters, subiters=subiters, seed=seed, step_size=step_size)
+    npr.seed(seed)
+    model.meanfield_stochastic_descent(x, randomize=True, maxiter=iters, maxsubiter=subiters, step_size=step_size, progress_bar=False)
+    hier_state(model, rec, 'end')
+    rec['resp_end'] = model.expected_responsibilities(x)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'posterior kappas', model.components.posterior.kappas)
+
+
+def hmom_case(name, x, M_, K, iters, subiters, subsubiters, ctor_seed, seed):
+    """mixtures/hgmm.py:298-431: a mixture of M_ hierarchical mixtures of K Gaussians, mean field."""
+    d = x.shape[1]
+    npr.seed(ctor_seed)
+    gating = D.CategoricalWithDirichlet(dim=M_, prior=D.Dirichlet(dim=M_, alphas=np.ones(M_)))
+    subs = []
+    for m in range(M_):
+        sub, _ = hgmm_model(K, d, False, ctor_seed + 1 + m)
+        subs.append(sub)
+    model = M.BayesianMixtureOfMixtureOfGaussians(M_, K, d, gating=gating, components=subs)
+    rec = dict(obs=x, M=M_, K=K, d=d, iters=iters, subiters=subiters, subsubiters=subsubiters, ctor_seed=ctor_seed, seed=seed)
+    npr.seed(seed)
+    model.meanfield_coordinate_descent(x, randomize=True, maxiter=iters, maxsubiter=subiters, maxsubsubiter=subsubiters, progress_bar=False)
+    rec['resp_end'] = model.expected_responsibilities(x)
+    rec['gate_alphas_end'] = gating.posterior.alphas.copy()
+    for m, sub in enumerate(subs):
+        rec[f'sub{m}_post_mus'] = sub.components.posterior.mus.copy()
+        rec[f'sub{m}_hyper_psi'] = np.array(sub.components.hyper_posterior.params[2])
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'cluster masses', rec['resp_end'].sum(1))
+
+
+def hilr_model(K, din, o, stick, ctor_seed):
+    """examples/hilr/vi_component.py:45-79 with parameterised sizes; returns the model and what its constructor drew."""
+    npr.seed(ctor_seed)
+    if stick:
+        gating = D.CategoricalWithStickBreaking(dim=K, prior=D.TruncatedStickBreaking(dim=K, gammas=np.ones(K), deltas=2. * np.ones(K)))
+    else:
+        gating = D.CategoricalWithDirichlet(dim=K, prior=D.Dirichlet(dim=K, alphas=np.ones(K)))
+    bh = D.NormalWishart(dim=din, mu=np.zeros(din), kappa=1e-2, psi=np.eye(din), nu=din + 1 + 1e-8)
+    bp = D.TiedGaussiansWithScaledPrecision(size=K, dim=din, kappas=1e-2 * np.ones(K))
+    basis = D.TiedGaussiansWithHierarchicalNormalWisharts(size=K, dim=din, hyper_prior=bh, prior=bp)
+    sp = D.MatrixNormalWithPrecision(column_dim=din, row_dim=o, M=np.zeros((o, din)), K=1e-2 * np.eye(din))
+    op = D.TiedGaussiansWithScaledPrecision(size=K, dim=o, mus=np.zeros((K, o)), kappas=1e-2 * (1. + np.arange(K)))
+    pp = D.Wishart(dim=o, psi=np.eye(o), nu=o + 1 + 1e-8)
+    models = D.TiedAffineLinearGaussiansWithMatrixNormalWisharts(size=K, column_dim=din, row_dim=o, slope_prior=sp,
+                                                                 offset_prior=op, precision_prior=pp)
+    model = M.BayesianMixtureOfLinearGaussiansWithTiedActivation(size=K, input_dim=din, output_dim=o, gating=gating,
+                                                                 basis=basis, models=models)
+    rec = dict(K=K, din=din, o=o, stick=int(stick), ctor_seed=ctor_seed,
+               init_basis_lmbdas=basis.prior.lmbdas.copy(), init_basis_lik_mus=basis.likelihood.mus.copy(),
+               init_As=models.likelihood.As.copy(), init_cs=models.likelihood.cs.copy(), init_lmbdas=models.likelihood.lmbdas.copy(),
+               init_probs=gating.likelihood.probs.copy(), off_kappas0=op.kappas.copy())
+    rec.update(gating_prior_arrays(gating))
+    return model, rec
+
+
+def hilr_state(model, rec):
+    b, m = model.basis, model.models
+    rec['basis_post_mus'], rec['basis_post_kappas'] = b.posterior.mus.copy(), b.posterior.kappas.copy()
+    for n, p in zip(('rho', 'kappa', 'psi', 'nu'), b.hyper_posterior.params):
+        rec[f'basis_hyper_{n}'] = np.array(p)
+    rec['slope_M'], rec['slope_K'] = m.slope_posterior.M.copy(), m.slope_posterior.K.copy()
+    rec['prec_psi'], rec['prec_nu'] = m.precision_posterior.psi.copy(), m.precision_posterior.nu
+    rec['off_mus'], rec['off_kappas'] = m.offset_posterior.mus.copy(), m.offset_posterior.kappas.copy()
+    rec['lik_As'], rec['lik_cs'], rec['lik_lmbdas'] = m.likelihood.As.copy(), m.likelihood.cs.copy(), m.likelihood.lmbdas.copy()
+    rec['basis_lik_mus'], rec['basis_lik_lmbdas'] = b.likelihood.mus.copy(), b.likelihood.lmbdas.copy()
+    rec['probs'] = model.gating.likelihood.probs.copy()
+
+
+def hilr_vi_case(name, x, y, K, stick, iters, subiters, ctor_seed, seed):
+    model, rec = hilr_model(K, x.shape[1], y.shape[1], stick, ctor_seed)
+    rec.update(x=x, y=y, iters=iters, subiters=subiters, seed=seed)
+    npr.seed(seed)
+    model.meanfield_coordinate_descent(x, y, randomize=True, maxiter=iters, maxsubiter=subiters, progress_bar=False)
+    hilr_state(model, rec)
+    rec['ell_end'] = model.expected_log_complete_likelihood(x, y)
+    rec['resp_end'] = model.expected_responsibilities(x, y)
+    rec['models_vlb'] = model.models.variational_lowerbound()
+    rec['vlb_end'] = model.variational_lowerbound(x, y, rec['resp_end'])
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'slope', model.models.slope_posterior.M.ravel(), 'vlb', rec['vlb_end'])
+
+
+def hilr_gibbs_case(name, x, y, K, stick, sweeps, subiters, ctor_seed, seed):
+    model, rec = hilr_model(K, x.shape[1], y.shape[1], stick, ctor_seed)
+    rec.update(x=x, y=y, sweeps=sweeps, subiters=subiters, seed=seed)
+    npr.seed(seed)
+    model.resample(x, y, maxiter=sweeps, maxsubiter=subiters, progress_bar=False)
+    hilr_state(model, rec)
+    npr.seed(seed + 1)
+    lp, lab = model.resample_labels(x, y)
+    rec['log_prob_end'], rec['labels_next'] = lp, lab.astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'label counts', np.bincount(lab, minlength=K))
+
+
+def hierarchical_ilr():
+    rng = np.random.default_rng(78)
+    n = 300
+    x1 = np.linspace(-1.5, 1.5, n)[:, None]
+    y1 = np.vstack([np.linspace(-.5, .5, n // 3)[:, None] for _ in range(3)]) + 0.05 * rng.standard_normal((n, 1))
+    y1[:n // 3] += .5
+    y1[-n // 3:] -= .5
+    hilr_vi_case('hilr_vi', x1, y1, 3, False, iters=5, subiters=4, ctor_seed=1337, seed=3)
+    hilr_gibbs_case('hilr_gibbs', x1, y1, 3, False, sweeps=3, subiters=3, ctor_seed=1337, seed=4)
+    x2 = rng.uniform(-1.5, 1.5, (240, 2))
+    y2 = x2 @ rng.standard_normal((2, 2)) + 0.5 * rng.integers(-1, 2, (240, 1)) + 0.05 * rng.standard_normal((240, 2))
+    hilr_vi_case('hilr_d2_vi_stick', x2, y2, 4, True, iters=4, subiters=3, ctor_seed=9, seed=10)
+
+
+def hierarchical():
+    rng = np.random.default_rng(77)
+    K, d = 4, 2
+    centres = np.array([[3., -3.], [-3., 3.], [-5., -5.], [5., 5.]])
+    x = centres[rng.integers(0, K, 500)] + rng.standard_normal((500, d))
+    hgmm_vi_case('hgmm_vi', x, K, False, iters=8, subiters=5, ctor_seed=1337, seed=3)
+    hgmm_gibbs_case('hgmm_gibbs', x, K, False, sweeps=4, subiters=3, ctor_seed=1337, seed=4)
+    hgmm_svi_case('hgmm_svi', x, K, False, iters=6, subiters=3, step_size=0.2, ctor_seed=1337, seed=5)
+    x8 = blobs(rng, 400, 8, 5, spread=3.0)
+    x8 = x8 @ np.linalg.inv(np.linalg.cholesky(np.cov(x8.T))).T          # one shared covariance scale: the model ties Lambda
+    hgmm_vi_case('hgmm_d8_vi_stick', x8, 5, True, iters=5, subiters=4, ctor_seed=8, seed=9)
+    xm = np.vstack([centres[:2][rng.integers(0, 2, 150)] + rng.standard_normal((150, d)),
+                    (centres[2:][rng.integers(0, 2, 150)] + rng.standard_normal((150, d))) * np.array([1., 0.4])])
+    hmom_case('hmom_vi', xm, 2, 2, iters=3, subiters=3, subsubiters=3, ctor_seed=50, seed=6)
+
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'hier':       # only the hierarchical fixtures (the others stay untouched)
+        hierarchical()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'hilr':
+        hierarchical_ilr()
+    else:
+        main()
+        hierarchical()
+        hierarchical_ilr()

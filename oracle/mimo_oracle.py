@@ -808,6 +808,109 @@ def hgmm_meanfield(obs, resp, gating_prior, hyper_prior, kappas0, post_lmbdas, i
     return out
 
 
+# ---------------------------------------------------------------------------
+# tied-slope affine experts y = A x + c_k + eps (shared A and Lambda, own offsets) -- SURVEY 8 f4 (mixtures/hilr.py:79-291)
+# ---------------------------------------------------------------------------
+
+def tam_slope_precision(slope_prior, prec_prior, off_prior, cs, x, y, w):
+    """distributions/bayesian.py:1301-1335 (mean field; the Gibbs block :1262-1296 is the same arithmetic): slope
+    posterior (M, K) and precision posterior (psi, nu) given the offsets cs (K, o) and weights w (K, N), contracted over
+    the points like the reference.  slope_prior = (M0, K0), prec_prior = (psi0, nu0), off_prior = (mus0, kappas0)."""
+    M0, K0 = slope_prior
+    psi0, nu0 = prec_prior
+    mus0, kap0 = off_prior
+    Kn = w.shape[0]
+    nk = np.sum(w, axis=1)
+    yx = np.einsum('nd,kn,nl->kdl', y, w, x, optimize=True)
+    xx = np.einsum('nd,kn,nl->kdl', x, w, x, optimize=True)
+    cx = np.einsum('kd,kn,nl->kdl', cs, w, x, optimize=True)
+    G = (M0 @ K0)[None] + yx - cx
+    Kinv = np.linalg.inv(K0[None] + xx)
+    M = np.sum(np.einsum('kdl,klh->kdh', G, Kinv), axis=0) / Kn
+    K = np.sum(K0[None] + xx, axis=0) / Kn
+    dy = y[None, :, :] - cs[:, None, :]
+    psi = np.linalg.inv(np.linalg.inv(psi0) + M0 @ K @ M0.T
+                        + np.sum(np.einsum('kn,knd,knl->kdl', w, dy, dy), axis=0) / Kn
+                        + np.sum(np.einsum('k,kd,kl->kdl', kap0, cs - mus0, cs - mus0), axis=0) / Kn
+                        - np.sum(np.einsum('kdl,klm,khm->kdh', G, Kinv, G), axis=0) / Kn)
+    return M, K, psi, np.sum(nu0 + nk + 1) / Kn
+
+
+def tam_meanfield_update(slope_prior, prec_prior, off_prior, off_post_mus, x, y, w, nb_iter):
+    """bayesian.py:1298-1383: nb_iter alternations; returns (slope (M, K), precision (psi, nu), offsets (mus, kappas))."""
+    mus0, kap0 = off_prior
+    xm, ym, nk = w @ x, w @ y, np.sum(w, axis=1)
+    M = K = psi = nu = None
+    mus = off_post_mus
+    for _ in range(nb_iter):
+        M, K, psi, nu = tam_slope_precision(slope_prior, prec_prior, off_prior, mus, x, y, w)
+        mus = (kap0[:, None] * mus0 + ym - xm @ M.T) / (kap0 + nk)[:, None]
+    return (M, K), (psi, nu), (mus, kap0 + nk)
+
+
+def tam_joint(slope, offsets, precision):
+    """bayesian.py:1395-1417: the experts [A | c_k] as stacked Matrix-Normal-Wisharts (Ms, Ks, psis, nus) with the
+    block-diagonal column precision diag(K, kappa_k)."""
+    M, K = slope
+    mus, kappas = offsets
+    psi, nu = precision
+    Kn, c = mus.shape[0], K.shape[0]
+    Ms = np.stack([np.hstack((M, mus[k][:, None])) for k in range(Kn)])
+    Ks = np.zeros((Kn, c + 1, c + 1))
+    Ks[:, :c, :c] = K
+    Ks[:, c, c] = kappas
+    return Ms, Ks, np.stack(Kn * [psi]), np.array(Kn * [nu], dtype=float)
+
+
+def tam_expected_loglik(x, y, slope, offsets, precision):
+    """bayesian.py:1388-1417."""
+    return mnw_expected_loglik(x, y, *tam_joint(slope, offsets, precision), affine=True)
+
+
+def tam_vlb(slope_prior, off_prior, prec_prior, slope, offsets, precision):
+    """bayesian.py:1448-1479, per component."""
+    return mnw_vlb(tam_joint(slope_prior, off_prior, prec_prior), tam_joint(slope, offsets, precision))
+
+
+def hilr_meanfield(x, y, resp, gating_prior, basis, models, iters, subiters):
+    """mixtures/hilr.py:175-218: basis = dict(hyper_prior, kappas0, post_lmbdas) of the input densities (hnw_*),
+    models = dict(slope_prior, prec_prior, off_prior, off_post_mus) of the experts.  Returns the end state and the
+    public lower bound (hilr.py:283-290) evaluated once, after the last iteration (the loop itself never evaluates it,
+    hilr.py:194, so quirk q11 of hnw_vlb does not arise: the entropy sees the current precisions)."""
+    hq = basis['hyper_prior']
+    off_mus = models['off_post_mus']
+    out = {}
+    for _ in range(iters):
+        xk, nk, xxk, _ = gauss_full_wstats(x, resp)
+        bm, bk, hq = hnw_meanfield_update(basis['hyper_prior'], hq, basis['kappas0'], xk, nk, xxk, subiters)
+        slope, prec, offs = tam_meanfield_update(models['slope_prior'], models['prec_prior'], models['off_prior'], off_mus,
+                                                 x, y, resp, subiters)
+        off_mus = offs[0]
+        counts = np.sum(resp, axis=1)
+        if gating_prior[0] == 'dirichlet':
+            gpost = ('dirichlet', dirichlet_posterior(gating_prior[1], counts))
+            gv = dirichlet_vlb(gating_prior[1], gpost[1])
+        else:
+            gpost = ('stick',) + tuple(stick_posterior(gating_prior[1], gating_prior[2], counts))
+            gv = stick_vlb(gating_prior[1:], gpost[1:])
+        omegas = bk[:, None, None] * basis['post_lmbdas']
+        ell_b = hnw_expected_loglik(x, hq, bm, omegas)
+        ell_m = tam_expected_loglik(x, y, slope, offs, prec)
+        joint = ell_b + ell_m + hgmm_log_weights(gpost)[:, None]
+        resp = responsibilities(joint)[0]
+        out = dict(basis_mus=bm, basis_kappas=bk, hyper=hq, slope=slope, precision=prec, offsets=offs, gating=gpost,
+                   resp=resp, ell=joint)
+        if gpost[0] == 'dirichlet':
+            lab = vlb_labels_dirichlet(resp, dirichlet_expected_log(gpost[1]))
+        else:
+            _, Es, Er = stick_expected_log(gpost[1], gpost[2])
+            lab = vlb_labels_stick(resp, Es, Er)
+        out['vlb'] = gv + hnw_vlb(basis['hyper_prior'], hq, basis['kappas0'], bm, omegas) \
+            + np.sum(tam_vlb(models['slope_prior'], models['off_prior'], models['prec_prior'], slope, offs, prec)) \
+            + lab + np.sum(resp * (ell_b + ell_m))
+    return out
+
+
 def chunked(fn, n, chunk):
     """Apply fn(slice) over point chunks and concatenate along the point axis
     (axis 1 for (K,N) outputs).  Exact: every per-point quantity is

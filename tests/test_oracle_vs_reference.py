@@ -363,3 +363,55 @@ def test_hnw_resample(ref, K, d, N):
     close(pk, comp.posterior.kappas)
     for a, b in zip(hq, comp.hyper_posterior.params):
         close(a, b, 1e-9)
+
+
+# ---- tied-slope affine experts + tied activation (mixtures/hilr.py:79-291, bayesian.py:1222-1522) ---------------------
+def _ref_hilr(ref, K, din, o, stick=False):
+    D, M = ref.D, ref.M
+    if stick:
+        gating = D.CategoricalWithStickBreaking(dim=K, prior=D.TruncatedStickBreaking(dim=K, gammas=np.ones(K), deltas=2. * np.ones(K)))
+    else:
+        gating = D.CategoricalWithDirichlet(dim=K, prior=D.Dirichlet(dim=K, alphas=np.ones(K)))
+    bh = D.NormalWishart(dim=din, mu=np.zeros(din), kappa=1e-2, psi=np.eye(din), nu=din + 1 + 1e-8)
+    bp = D.TiedGaussiansWithScaledPrecision(size=K, dim=din, kappas=1e-2 * np.ones(K))
+    basis = D.TiedGaussiansWithHierarchicalNormalWisharts(size=K, dim=din, hyper_prior=bh, prior=bp)
+    sp = D.MatrixNormalWithPrecision(column_dim=din, row_dim=o, M=np.zeros((o, din)), K=1e-2 * np.eye(din))
+    op = D.TiedGaussiansWithScaledPrecision(size=K, dim=o, mus=np.zeros((K, o)), kappas=1e-2 * (1. + np.arange(K)))
+    pp = D.Wishart(dim=o, psi=np.eye(o), nu=o + 1 + 1e-8)
+    models = D.TiedAffineLinearGaussiansWithMatrixNormalWisharts(size=K, column_dim=din, row_dim=o, slope_prior=sp,
+                                                                 offset_prior=op, precision_prior=pp)
+    return M.BayesianMixtureOfLinearGaussiansWithTiedActivation(size=K, input_dim=din, output_dim=o, gating=gating,
+                                                                basis=basis, models=models)
+
+
+@pytest.mark.parametrize('K,din,o,N,stick', [(3, 1, 1, 240, False), (4, 2, 2, 200, True)])
+def test_hilr_meanfield(ref, K, din, o, N, stick):
+    rng = np.random.default_rng(8)
+    x = rng.uniform(-1.5, 1.5, (N, din))
+    y = x @ rng.standard_normal((din, o)) + 0.5 * rng.integers(-1, 2, (N, 1)) + 0.05 * rng.standard_normal((N, o))
+    npr.seed(2)
+    model = _ref_hilr(ref, K, din, o, stick)
+    b, m = model.basis, model.models
+    basis = dict(hyper_prior=tuple(b.hyper_prior.params), kappas0=b.prior.kappas.copy(), post_lmbdas=b.posterior.lmbdas.copy())
+    models = dict(slope_prior=(m.slope_prior.M.copy(), m.slope_prior.K.copy()), prec_prior=(m.precision_prior.psi.copy(), m.precision_prior.nu),
+                  off_prior=(m.offset_prior.mus.copy(), m.offset_prior.kappas.copy()), off_post_mus=m.offset_posterior.mus.copy())
+    npr.seed(13)
+    model.meanfield_coordinate_descent(x, y, randomize=True, maxiter=4, maxsubiter=3, progress_bar=False)
+    npr.seed(13)
+    r0 = npr.rand(K, N)
+    r0 /= r0.sum(0)
+    out = orc.hilr_meanfield(x, y, r0, _gating_prior(model), basis, models, 4, 3)
+    close(out['slope'][0], m.slope_posterior.M, 1e-9)
+    close(out['slope'][1], m.slope_posterior.K, 1e-9)
+    close(out['precision'][0], m.precision_posterior.psi, 1e-9)
+    close(out['precision'][1], m.precision_posterior.nu, 1e-9)
+    close(out['offsets'][0], m.offset_posterior.mus, 1e-9)
+    close(out['offsets'][1], m.offset_posterior.kappas, 1e-9)
+    close(out['basis_mus'], b.posterior.mus, 1e-9)
+    close(out['ell'], model.expected_log_complete_likelihood(x, y), 1e-9)
+    resp = model.expected_responsibilities(x, y)
+    close(out['resp'], resp, 1e-8)
+    close(orc.tam_expected_loglik(x, y, out['slope'], out['offsets'], out['precision']), m.expected_log_likelihood(x, y), 1e-9)
+    close(orc.tam_vlb(models['slope_prior'], models['off_prior'], models['prec_prior'], out['slope'], out['offsets'], out['precision']),
+          m.variational_lowerbound(), 1e-9)
+    close(out['vlb'], model.variational_lowerbound(x, y, resp), 1e-9)
