@@ -2,4 +2,5 @@ from .gmm import MixtureOfGaussians, BayesianMixtureOfGaussians  # noqa: F401
 from .ilr import MixtureOfLinearGaussians, BayesianMixtureOfLinearGaussians  # noqa: F401
 from .hgmm import (BayesianMixtureOfGaussiansWithHierarchicalPrior, MixtureOfMixtureOfGaussians,  # noqa: F401
                    BayesianMixtureOfMixtureOfGaussians)
-from .hilr import BayesianMixtureOfLinearGaussiansWithTiedActivation  # noqa: F401
+from .hilr import (BayesianMixtureOfLinearGaussiansWithTiedActivation, MixtureOfMixtureOfLinearGaussians,  # noqa: F401
+                   BayesianMixtureOfMixtureOfLinearGaussians)

@@ -641,6 +641,31 @@ def hilr_gibbs_case(name, x, y, K, stick, sweeps, subiters, ctor_seed, seed):
     print(name, 'label counts', np.bincount(lab, minlength=K))
 
 
+def hmoilr_case(name, x, y, M_, K, iters, subiters, subsubiters, ctor_seed, seed):
+    """mixtures/hilr.py:293-609: a mixture of M_ tied-activation mixtures of K experts: mean field, then the predictive path."""
+    din, o = x.shape[1], y.shape[1]
+    npr.seed(ctor_seed)
+    gating = D.CategoricalWithDirichlet(dim=M_, prior=D.Dirichlet(dim=M_, alphas=np.ones(M_)))
+    subs = [hilr_model(K, din, o, False, ctor_seed + 1 + m)[0] for m in range(M_)]
+    model = M.BayesianMixtureOfMixtureOfLinearGaussians(M_, K, din, o, gating=gating, components=subs)
+    rec = dict(x=x, y=y, M=M_, K=K, din=din, o=o, iters=iters, subiters=subiters, subsubiters=subsubiters, ctor_seed=ctor_seed, seed=seed,
+               off_kappas0=1e-2 * (1. + np.arange(K)), gate_alphas0=np.ones(K), stick=0)
+    npr.seed(seed)
+    model.meanfield_coordinate_descent(x, y, randomize=True, maxiter=iters, maxsubiter=subiters, maxsubsubiter=subsubiters, progress_bar=False)
+    rec['resp_end'] = model.expected_responsibilities(x, y)
+    rec['gate_alphas_end'] = gating.posterior.alphas.copy()
+    for m, sub in enumerate(subs):
+        rec[f'sub{m}_slope_M'] = sub.models.slope_posterior.M.copy()
+        rec[f'sub{m}_off_mus'] = sub.models.offset_posterior.mus.copy()
+        rec[f'sub{m}_basis_mus'] = sub.basis.posterior.mus.copy()
+    rec['weights'] = model.meanfield_predictive_weights(x)
+    for pred in ('average', 'mode'):
+        mean, var, std = model.meanfield_prediction(x, prediction=pred)
+        rec[f'pred_{pred}_mean'], rec[f'pred_{pred}_var'] = mean, var
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'cluster masses', rec['resp_end'].sum(1), 'rmse', np.sqrt(np.mean((rec['pred_average_mean'] - y) ** 2)))
+
+
 def hierarchical_ilr():
     rng = np.random.default_rng(78)
     n = 300
@@ -653,6 +678,7 @@ def hierarchical_ilr():
     x2 = rng.uniform(-1.5, 1.5, (240, 2))
     y2 = x2 @ rng.standard_normal((2, 2)) + 0.5 * rng.integers(-1, 2, (240, 1)) + 0.05 * rng.standard_normal((240, 2))
     hilr_vi_case('hilr_d2_vi_stick', x2, y2, 4, True, iters=4, subiters=3, ctor_seed=9, seed=10)
+    hmoilr_case('hmoilr_vi', x1[::2], y1[::2], 2, 2, iters=2, subiters=2, subsubiters=2, ctor_seed=60, seed=7)
 
 
 def hierarchical():

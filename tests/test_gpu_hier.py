@@ -290,3 +290,37 @@ def test_hilr_gibbs_chain_replays_reference(fp64):
     assert np.array_equal(labels, g['labels_next'])
     with pytest.raises(NotImplementedError):
         model.meanfield_stochastic_descent(g['x'], g['y'], maxiter=1, maxsubiter=1, progress_bar=False)
+
+
+def test_mixture_of_mixtures_of_linear_experts(fp64):
+    """hilr.py:293-609: nested mean field of tied-activation mixtures trained with per-point weights, then the predictive
+    path (weights over clusters x experts, posterior-predictive moments, mixture / mode)."""
+    from mimo_b200.distributions import Dirichlet, CategoricalWithDirichlet
+    from mimo_b200.mixtures import BayesianMixtureOfMixtureOfLinearGaussians
+    g = load('hmoilr_vi')
+    M_, K = int(g['M']), int(g['K'])
+    npr.seed(int(g['ctor_seed']))
+    gating = CategoricalWithDirichlet(M_, Dirichlet(M_, np.ones(M_)))
+    subs = []
+    for m in range(M_):
+        sg = dict(g)
+        sg['ctor_seed'] = int(g['ctor_seed']) + 1 + m
+        subs.append(make_hilr(sg))
+    model = BayesianMixtureOfMixtureOfLinearGaussians(M_, K, int(g['din']), int(g['o']), gating=gating, components=subs)
+    npr.seed(int(g['seed']))
+    out = model.meanfield_coordinate_descent(g['x'], g['y'], randomize=True, maxiter=int(g['iters']), maxsubiter=int(g['subiters']),
+                                             maxsubsubiter=int(g['subsubiters']), progress_bar=False)
+    assert out == []
+    close(gating.posterior.alphas, g['gate_alphas_end'], 1e-7, 'cluster alphas')
+    for m, sub in enumerate(subs):
+        close(sub.models.slope_posterior.M, g[f'sub{m}_slope_M'], 1e-7, 'slopes')
+        close(sub.models.offset_posterior.mus, g[f'sub{m}_off_mus'], 1e-7, 'offsets')
+        close(sub.basis.posterior.mus, g[f'sub{m}_basis_mus'], 1e-7, 'input-density means')
+    close(model.expected_responsibilities(g['x'], g['y']), g['resp_end'], 1e-6, 'cluster responsibilities')
+    close(model.meanfield_predictive_weights(g['x']), g['weights'], 1e-6, 'predictive weights')
+    for pred in ('average', 'mode'):
+        mean, var, std = model.meanfield_prediction(g['x'], prediction=pred)
+        close(mean, g[f'pred_{pred}_mean'], 1e-6, pred + ' prediction')
+        close(var, g[f'pred_{pred}_var'], 1e-6, pred + ' predictive variance')
+    lp = model.likelihood.log_complete_likelihood(g['x'], g['y'])
+    assert lp.shape == (M_, len(g['x'])) and np.all(np.isfinite(lp))

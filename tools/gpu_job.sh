@@ -5,7 +5,7 @@ TAG=$1; shift
 TESTS=$1; shift
 mkdir -p gpurun_out
 if [ -n "$TESTS" ]; then
-  timeout 900 python -m pytest $TESTS -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1
+  timeout 900 python -m pytest $TESTS -m gpu -q > gpurun_out/${TAG}_tests.log 2>&1
   tail -8 gpurun_out/${TAG}_tests.log
 fi
 i=0
