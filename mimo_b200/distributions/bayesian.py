@@ -1056,7 +1056,16 @@ class TiedAffineLinearGaussiansWithMatrixNormalWisharts(_ComponentsBase):
     def meanfield_sgd(self, x, y, weights, nb_iter, scale, step_size):
         raise NotImplementedError
 
+    def _consume_reference_draws(self):
+        """The reference builds a fresh StackedLinearGaussiansWithMatrixNormalWisharts inside expected_log_likelihood and
+        posterior_predictive_gaussian (bayesian.py:1411-1414, 1503-1506) whose constructor samples a likelihood from the
+        prior (:805-809): K Wishart + matrix-normal draws that nothing reads.  The same variates are taken from
+        numpy.random here so that a seeded script stays on the reference's stream (quirk q12)."""
+        draw_wishart_variates(np.array(self.size * [self.precision_prior.nu], dtype=np.float64), self.row_dim,
+                              self.row_dim * (self.column_dim + 1))
+
     def expected_log_likelihood(self, x, y):
+        self._consume_reference_draws()
         return self._mnw().expected_log_likelihood(x, y)
 
     def variational_lowerbound(self):
@@ -1064,6 +1073,7 @@ class TiedAffineLinearGaussiansWithMatrixNormalWisharts(_ComponentsBase):
         return w.posterior.entropy() - w.posterior.cross_entropy(w.prior)
 
     def posterior_predictive_gaussian(self, x):
+        self._consume_reference_draws()
         return self._mnw().posterior_predictive_gaussian(x)
 
     def log_posterior_predictive_gaussian(self, x, y):

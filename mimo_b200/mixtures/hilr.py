@@ -71,8 +71,9 @@ class BayesianMixtureOfLinearGaussiansWithTiedActivation(BayesianMixtureOfLinear
                                      progress_bar=True, process_id=0, lower_bound=False, sample_likelihood=False):
         """The reference returns an empty list (its lower-bound line is commented out, hilr.py:194); lower_bound=True
         returns the bound of every iteration instead (parameter terms + sum_n logsumexp from the fused sweep) and
-        stops on tol like the other drivers.  sample_likelihood: see
-        BayesianMixtureOfGaussiansWithHierarchicalPrior.meanfield_coordinate_descent."""
+        stops on tol like the other drivers.  sample_likelihood=True replays the draws the reference's loop makes and
+        never reads (the gating's posterior.rvs(), SURVEY q3, and the experts its E-step samples, quirk q12): a mixture of
+        mixtures takes its next cluster's random start from the same stream."""
         xx, yy = self._scaled(x, y)
         s = self._session(xx, yy)
         self._sub_iterations(maxsubiter)
@@ -85,11 +86,14 @@ class BayesianMixtureOfLinearGaussiansWithTiedActivation(BayesianMixtureOfLinear
                 s.stats_from_resp(r0)
             else:
                 resp = E.to_dev(r0, E.tdtype(s.precision))
-        elif w is None:
-            s.sweep(s.operands_from_posterior(), hard=False)
         else:
-            resp = s.loglik(s.operands_from_posterior())
-            E.softmax(resp, s.precision, resp=True)
+            if sample_likelihood:
+                self.models._consume_reference_draws()
+            if w is None:
+                s.sweep(s.operands_from_posterior(), hard=False)
+            else:
+                resp = s.loglik(s.operands_from_posterior())
+                E.softmax(resp, s.precision, resp=True)
         vlb, outs = [], None
         with tqdm(total=maxiter, desc=f'VI #{process_id + 1}', position=process_id, disable=not progress_bar) as pbar:
             for _ in range(maxiter):
@@ -106,6 +110,7 @@ class BayesianMixtureOfLinearGaussiansWithTiedActivation(BayesianMixtureOfLinear
                 if sample_likelihood:
                     self.gating._store(outs['gating'], set_probs=False)
                     self.gating.likelihood.params = self.gating.posterior.rvs()
+                    self.models._consume_reference_draws()
                 if lower_bound:
                     vlb.append(float(lse.item()) + float(outs['gating']['vlb'].item())
                                + sum(float(o['vlb'].sum().item()) for o in outs['parts']))
@@ -116,8 +121,17 @@ class BayesianMixtureOfLinearGaussiansWithTiedActivation(BayesianMixtureOfLinear
             s.store(outs, MEANFIELD, set_probs=False)
         return vlb
 
+    def expected_log_complete_likelihood(self, x, y):
+        self.models._consume_reference_draws()          # quirk q12: the reference's E-step samples and discards K experts
+        return super().expected_log_complete_likelihood(x, y)
+
+    def expected_responsibilities(self, x, y):
+        self.models._consume_reference_draws()
+        return super().expected_responsibilities(x, y)
+
     def expected_log_likelihood(self, x, y):
         """(N,): log sum_k exp(E log joint)   (hilr.py:151-153)."""
+        self.models._consume_reference_draws()
         s = self._session(x, y)
         a = s.loglik(s.operands_from_posterior())
         return E.to_host(E.softmax(a, s.precision, lse=True)['lse']).astype(np.float64)

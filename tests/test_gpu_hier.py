@@ -324,3 +324,39 @@ def test_mixture_of_mixtures_of_linear_experts(fp64):
         close(var, g[f'pred_{pred}_var'], 1e-6, pred + ' predictive variance')
     lp = model.likelihood.log_complete_likelihood(g['x'], g['y'])
     assert lp.shape == (M_, len(g['x'])) and np.all(np.isfinite(lp))
+
+
+def test_hilr_weighted_meanfield_matches_oracle(fp64):
+    """weights (N,) multiply the responsibilities in every parameter update (hilr.py:191): the non-fused path a mixture of
+    mixtures drives, against the oracle's loop from raw data."""
+    g = load('hilr_vi')
+    model = make_hilr(g)
+    b, m = model.basis, model.models
+    x, y, K = g['x'], g['y'], int(g['K'])
+    lm0 = b.posterior.lmbdas.copy()
+    hyper = tuple(b.hyper_prior.params)
+    sp, pp, op = (m.slope_prior.M, m.slope_prior.K), (m.precision_prior.psi, m.precision_prior.nu), (m.offset_prior.mus, m.offset_prior.kappas)
+    off = m.offset_posterior.mus.copy()
+    wts = np.random.default_rng(6).random(len(x))
+    npr.seed(12)
+    model.meanfield_coordinate_descent(x, y, randomize=True, weights=wts, maxiter=3, maxsubiter=2, progress_bar=False)
+    npr.seed(12)
+    resp = npr.rand(K, len(x))
+    resp /= resp.sum(0)
+    hq = hyper
+    for _ in range(3):
+        rw = resp * wts[None, :]
+        xk, nk, xxk, _ = orc.gauss_full_wstats(x, rw)
+        bm, bk, hq = orc.hnw_meanfield_update(hyper, hq, b.prior.kappas, xk, nk, xxk, 2)
+        slope, prec, offs = orc.tam_meanfield_update(sp, pp, op, off, x, y, rw, 2)
+        off = offs[0]
+        alphas = orc.dirichlet_posterior(g['gate_alphas0'], rw.sum(1))
+        joint = orc.hnw_expected_loglik(x, hq, bm, bk[:, None, None] * lm0) + orc.tam_expected_loglik(x, y, slope, offs, prec) \
+            + orc.dirichlet_expected_log(alphas)[:, None]
+        resp = orc.responsibilities(joint)[0]
+    close(b.posterior.mus, bm, 1e-8, 'basis means')
+    close(m.slope_posterior.M, slope[0], 1e-8, 'slope')
+    close(m.offset_posterior.mus, offs[0], 1e-8, 'offsets')
+    close(model.gating.posterior.alphas, alphas, 1e-8, 'alphas')
+    close(model.expected_responsibilities(x, y), resp, 1e-7, 'responsibilities')
+    close(model.expected_log_likelihood(x, y), orc.responsibilities(joint)[1], 1e-8, 'expected log-likelihood')
