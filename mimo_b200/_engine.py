@@ -44,6 +44,12 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def ld(t):
+    """leading dimension of a (K, N) tensor for the C-ABI; a single row may carry any stride (torch normalises the
+    strides of size-1 dimensions when it copies), the kernels want ld >= N."""
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
 def to_dev(x, dtype=torch.float64):
     if isinstance(x, torch.Tensor):
         return x.to(device=device(), dtype=dtype).contiguous()
@@ -266,7 +272,7 @@ def stats_soft(Z, resp, feats, precision, stat=None):
         stat = zeros((K, feats.F), torch.float64)
     if N == 0:
         return stat
-    _lib.call('mimo_stats_soft', code(precision), ptr(Z), N, D, Z.stride(0), ptr(resp), resp.stride(0), K,
+    _lib.call('mimo_stats_soft', code(precision), ptr(Z), N, D, Z.stride(0), ptr(resp), ld(resp), K,
               ptr(fi), ptr(fj), feats.F, ptr(stat), stream())
     return stat
 
@@ -577,6 +583,6 @@ def stats_soft_tc(Z, resp, feats, stat=None):
         stat = zeros((K, feats.F), torch.float64)
     wsb = _lib.load().mimo_stats_soft_tc_workspace(N, K)
     ws = workspace(wsb)
-    _lib.call('mimo_stats_soft_tc', ptr(Z), N, D, Z.stride(0), ptr(resp), resp.stride(0), K, feats.F,
+    _lib.call('mimo_stats_soft_tc', ptr(Z), N, D, Z.stride(0), ptr(resp), ld(resp), K, feats.F,
               ptr(stat), ptr(ws), wsb, stream())
     return stat

@@ -7,7 +7,8 @@ from .gaussian import (GaussianWithPrecision, StackedGaussiansWithPrecision, Tie
                        GaussianWithDiagonalPrecision, StackedGaussiansWithDiagonalPrecision,
                        TiedGaussiansWithDiagonalPrecision, GaussianWithScaledPrecision, TiedGaussiansWithScaledPrecision)
 from .lingauss import (LinearGaussianWithPrecision, StackedLinearGaussiansWithPrecision,  # noqa: F401
-                       TiedLinearGaussiansWithPrecision, StackedAffineLinearGaussiansWithPrecision)
+                       TiedLinearGaussiansWithPrecision, StackedAffineLinearGaussiansWithPrecision,
+                       AffineLinearGaussianWithPrecision)
 from .composite import (NormalWishart, StackedNormalWisharts, TiedNormalWisharts,  # noqa: F401
                         NormalGamma, StackedNormalGammas, TiedNormalGammas,
                         MatrixNormalWishart, StackedMatrixNormalWisharts, TiedMatrixNormalWisharts)
@@ -16,4 +17,4 @@ from .bayesian import (CategoricalWithDirichlet, CategoricalWithStickBreaking,  
                        StackedGaussiansWithNormalGammas, TiedGaussiansWithNormalGammas,
                        StackedLinearGaussiansWithMatrixNormalWisharts, TiedLinearGaussiansWithMatrixNormalWisharts,
                        GaussianWithHierarchicalNormalWishart, TiedGaussiansWithHierarchicalNormalWisharts,
-                       TiedAffineLinearGaussiansWithMatrixNormalWisharts)
+                       TiedAffineLinearGaussiansWithMatrixNormalWisharts, AffineLinearGaussianWithMatrixNormalWishart)

@@ -1107,3 +1107,56 @@ class TiedAffineLinearGaussiansWithMatrixNormalWisharts(_ComponentsBase):
     def _store(self, out, mode):
         if mode == MEANFIELD:
             self._set_mode()
+
+
+class AffineLinearGaussianWithMatrixNormalWishart(_ComponentsBase):
+    """one expert y = A x + c + eps with a Matrix-Normal prior on the slope, a scaled-precision Gaussian prior on the
+    offset and a Wishart prior on the precision: the Gibbs sampler of bayesian.py:1137-1219 (examples/lingauss).  The
+    second moments of [x | y | 1] come from the statistics kernel; the alternation between (slope, precision) and the
+    offset runs on them on the host."""
+
+    def __init__(self, column_dim, row_dim, slope_prior, offset_prior, precision_prior, likelihood=None, precision=None):
+        from .lingauss import AffineLinearGaussianWithPrecision
+        self.column_dim, self.row_dim = column_dim, row_dim
+        self.size = 1
+        lmbda = precision_prior.rvs()
+        slope_prior.V = lmbda
+        A = slope_prior.rvs()
+        offset_prior.lmbda = lmbda
+        c = offset_prior.rvs()
+        self.slope_prior, self.offset_prior, self.precision_prior = slope_prior, offset_prior, precision_prior
+        self.likelihood = AffineLinearGaussianWithPrecision(column_dim, row_dim, A, c, lmbda, precision=precision)
+        self.slope_posterior = copy.deepcopy(slope_prior)
+        self.offset_posterior = copy.deepcopy(offset_prior)
+        self.precision_posterior = copy.deepcopy(precision_prior)
+        self.layout = ExpertLayout(column_dim + 1, row_dim, affine=True)
+
+    def _feats(self):
+        return E.quad_features(self.layout.D)
+
+    def resample(self, x, y, nb_iter=25):
+        from .gaussian import unpack_quad
+        cdim = self.column_dim
+        stat = self._stats_from(np.ones((1, len(x))), x, y)
+        yxt, xxt, yy, n = (a[0] for a in self.layout.split(unpack_quad(E.to_host(stat), self.layout.D + 1)))
+        xm, ym, yx, xx = xxt[:cdim, cdim], yxt[:, cdim], yxt[:, :cdim], xxt[:cdim, :cdim]
+        M0, K0 = self.slope_prior.M, self.slope_prior.K
+        psi0, nu0 = self.precision_prior.psi, self.precision_prior.nu
+        k0, mu0 = self.offset_prior.kappa, self.offset_prior.mu
+        A = c = lmbda = None
+        for _ in range(nb_iter):
+            c = self.offset_posterior.rvs()
+            K = K0 + xx
+            M = (M0 @ K0 + yx - np.outer(c, xm)) @ np.linalg.inv(K)
+            self.slope_posterior.M, self.slope_posterior.K = M, K
+            resid = yy - np.outer(ym, c) - np.outer(c, ym) + n * np.outer(c, c)
+            self.precision_posterior.psi = np.linalg.inv(np.linalg.inv(psi0) + M0 @ K0 @ M0.T + resid
+                                                         + k0 * np.outer(c - mu0, c - mu0) - M @ K @ M.T)
+            self.precision_posterior.nu = nu0 + n + 1
+            lmbda = self.precision_posterior.rvs()
+            self.slope_posterior.V = lmbda
+            A = self.slope_posterior.rvs()
+            self.offset_posterior.mu = (k0 * mu0 + ym - A @ xm) / (k0 + n)
+            self.offset_posterior.kappa = k0 + n
+            self.offset_posterior.lmbda = lmbda
+        self.likelihood.params = A, c, lmbda

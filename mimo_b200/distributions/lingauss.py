@@ -311,3 +311,35 @@ class StackedAffineLinearGaussiansWithPrecision:
 
     def weighted_statistics(self, x, y, weights):
         return self._combined().weighted_statistics(x, y, weights)
+
+
+class AffineLinearGaussianWithPrecision:
+    """one expert y = A x + c + eps with slope and offset kept apart (lingauss.py:401-573) = a stack of one."""
+
+    def __init__(self, column_dim, row_dim, A=None, c=None, lmbda=None, precision=None):
+        self.column_dim, self.row_dim, self.precision = column_dim, row_dim, precision
+        self.A, self.c, self.lmbda = A, c, lmbda
+
+    @property
+    def params(self):
+        return self.A, self.c, self.lmbda
+
+    @params.setter
+    def params(self, values):
+        self.A, self.c, self.lmbda = values
+
+    def _stack(self):
+        return StackedAffineLinearGaussiansWithPrecision(1, self.column_dim, self.row_dim, np.asarray(self.A)[None],
+                                                         np.asarray(self.c)[None], np.asarray(self.lmbda)[None], precision=self.precision)
+
+    def predict(self, x):
+        return self._stack().predict(x)[0]
+
+    def mean(self, x):
+        return self.predict(x)
+
+    def rvs(self, x):
+        return self._stack().rvs(x)[0]
+
+    def log_likelihood(self, x, y):
+        return self._stack().log_likelihood(x, y)[0]

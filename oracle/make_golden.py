@@ -666,6 +666,23 @@ def hmoilr_case(name, x, y, M_, K, iters, subiters, subsubiters, ctor_seed, seed
     print(name, 'cluster masses', rec['resp_end'].sum(1), 'rmse', np.sqrt(np.mean((rec['pred_average_mean'] - y) ** 2)))
 
 
+def affine_expert_gibbs_case(name, x, y, iters, ctor_seed, seed):
+    """distributions/bayesian.py:1137-1219 (examples/lingauss/gibbs_affine.py): one affine expert, seeded Gibbs."""
+    din, o = x.shape[1], y.shape[1]
+    npr.seed(ctor_seed)
+    sp = D.MatrixNormalWithPrecision(column_dim=din, row_dim=o, M=np.zeros((o, din)), K=1e-2 * np.eye(din))
+    op = D.GaussianWithScaledPrecision(dim=o, kappa=1e-2, mu=np.zeros(o))
+    pp = D.Wishart(dim=o, psi=np.eye(o), nu=o + 1 + 1e-8)
+    w = D.AffineLinearGaussianWithMatrixNormalWishart(din, o, slope_prior=sp, offset_prior=op, precision_prior=pp)
+    rec = dict(x=x, y=y, iters=iters, ctor_seed=ctor_seed, seed=seed, init_A=w.likelihood.A.copy(), init_c=w.likelihood.c.copy())
+    npr.seed(seed)
+    w.resample(x, y, nb_iter=iters)
+    rec.update(A=w.likelihood.A, c=w.likelihood.c, lmbda=w.likelihood.lmbda, slope_M=w.slope_posterior.M, slope_K=w.slope_posterior.K,
+               psi=w.precision_posterior.psi, nu=w.precision_posterior.nu, off_mu=w.offset_posterior.mu, off_kappa=w.offset_posterior.kappa)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'A', w.likelihood.A.ravel(), 'c', w.likelihood.c)
+
+
 def hierarchical_ilr():
     rng = np.random.default_rng(78)
     n = 300
@@ -678,6 +695,7 @@ def hierarchical_ilr():
     x2 = rng.uniform(-1.5, 1.5, (240, 2))
     y2 = x2 @ rng.standard_normal((2, 2)) + 0.5 * rng.integers(-1, 2, (240, 1)) + 0.05 * rng.standard_normal((240, 2))
     hilr_vi_case('hilr_d2_vi_stick', x2, y2, 4, True, iters=4, subiters=3, ctor_seed=9, seed=10)
+    affine_expert_gibbs_case('affine_expert_gibbs', x2, y2 + np.array([1., -2.]), iters=5, ctor_seed=70, seed=8)
     hmoilr_case('hmoilr_vi', x1[::2], y1[::2], 2, 2, iters=2, subiters=2, subsubiters=2, ctor_seed=60, seed=7)
 
 

@@ -360,3 +360,26 @@ def test_hilr_weighted_meanfield_matches_oracle(fp64):
     close(model.gating.posterior.alphas, alphas, 1e-8, 'alphas')
     close(model.expected_responsibilities(x, y), resp, 1e-7, 'responsibilities')
     close(model.expected_log_likelihood(x, y), orc.responsibilities(joint)[1], 1e-8, 'expected log-likelihood')
+
+
+def test_single_affine_expert_gibbs_replays_reference(fp64):
+    """bayesian.py:1137-1219 (examples/lingauss): slope, offset and precision of one expert, seeded chain."""
+    from mimo_b200.distributions import (MatrixNormalWithPrecision, GaussianWithScaledPrecision, Wishart,
+                                         AffineLinearGaussianWithMatrixNormalWishart)
+    g = load('affine_expert_gibbs')
+    din, o = g['x'].shape[1], g['y'].shape[1]
+    npr.seed(int(g['ctor_seed']))
+    w = AffineLinearGaussianWithMatrixNormalWishart(din, o, slope_prior=MatrixNormalWithPrecision(column_dim=din, row_dim=o, M=np.zeros((o, din)), K=1e-2 * np.eye(din)),
+                                                    offset_prior=GaussianWithScaledPrecision(dim=o, kappa=1e-2, mu=np.zeros(o)),
+                                                    precision_prior=Wishart(dim=o, psi=np.eye(o), nu=o + 1 + 1e-8))
+    close(w.likelihood.A, g['init_A'], 1e-10, 'constructor: slope')
+    close(w.likelihood.c, g['init_c'], 1e-10, 'constructor: offset')
+    npr.seed(int(g['seed']))
+    w.resample(g['x'], g['y'], nb_iter=int(g['iters']))
+    for key, val in (('A', w.likelihood.A), ('c', w.likelihood.c), ('lmbda', w.likelihood.lmbda), ('slope_M', w.slope_posterior.M),
+                     ('slope_K', w.slope_posterior.K), ('psi', w.precision_posterior.psi), ('nu', w.precision_posterior.nu),
+                     ('off_mu', w.offset_posterior.mu), ('off_kappa', w.offset_posterior.kappa)):
+        close(val, g[key], 1e-8, key)
+    ll = w.likelihood.log_likelihood(g['x'], g['y'])
+    ref = orc.lingauss_loglik(g['x'], g['y'], np.hstack((g['A'], g['c'][:, None]))[None], g['lmbda'][None], affine=True)[0]
+    close(ll, ref, 1e-9, 'log-likelihood of the sampled expert')
