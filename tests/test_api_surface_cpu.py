@@ -31,9 +31,19 @@ PATH_CLASSES = ['Dirichlet', 'TruncatedStickBreaking', 'Categorical', 'Categoric
                 'LinearGaussianWithPrecision', 'StackedLinearGaussiansWithPrecision', 'TiedLinearGaussiansWithPrecision',
                 'GaussianWithNormalWishart', 'StackedGaussiansWithNormalWisharts', 'TiedGaussiansWithNormalWisharts',
                 'StackedGaussiansWithNormalGammas', 'TiedGaussiansWithNormalGammas',
-                'StackedLinearGaussiansWithMatrixNormalWisharts', 'TiedLinearGaussiansWithMatrixNormalWisharts']
-MIXTURES = ['MixtureOfGaussians', 'BayesianMixtureOfGaussians', 'MixtureOfLinearGaussians', 'BayesianMixtureOfLinearGaussians']
-DRIVER_METHODS = ['resample', 'resample_labels', 'meanfield_coordinate_descent', 'meanfield_update_parameters',
+                'StackedLinearGaussiansWithMatrixNormalWisharts', 'TiedLinearGaussiansWithMatrixNormalWisharts',
+                # hierarchical mixtures
+                'GaussianWithScaledPrecision', 'TiedGaussiansWithScaledPrecision', 'GaussianWithHierarchicalNormalWishart',
+                'TiedGaussiansWithHierarchicalNormalWisharts', 'AffineLinearGaussianWithPrecision',
+                'StackedAffineLinearGaussiansWithPrecision', 'AffineLinearGaussianWithMatrixNormalWishart',
+                'TiedAffineLinearGaussiansWithMatrixNormalWisharts', 'MatrixNormalWithPrecision']
+MIXTURES = ['MixtureOfGaussians', 'BayesianMixtureOfGaussians', 'MixtureOfLinearGaussians', 'BayesianMixtureOfLinearGaussians',
+            'MixtureOfMixtureOfGaussians', 'BayesianMixtureOfGaussiansWithHierarchicalPrior', 'BayesianMixtureOfMixtureOfGaussians',
+            'MixtureOfMixtureOfLinearGaussians', 'BayesianMixtureOfLinearGaussiansWithTiedActivation',
+            'BayesianMixtureOfMixtureOfLinearGaussians']
+DRIVER_METHODS = ['resample', 'resample_labels', 'resample_components', 'resample_basis', 'resample_models',
+                  'meanfield_update_components', 'meanfield_update_basis', 'meanfield_update_models', 'meanfield_sgd_parameters',
+                  'meanfield_coordinate_descent', 'meanfield_update_parameters',
                   'expected_responsibilities', 'expected_log_complete_likelihood', 'max_aposteriori', 'max_likelihood',
                   'meanfield_stochastic_descent', 'variational_lowerbound', 'log_likelihood', 'responsibilities',
                   'meanfield_prediction']
