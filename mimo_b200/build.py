@@ -24,19 +24,29 @@ def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
 
 
-def _newest_dep():
-    t = 0.0
+STAMP = LIB + '.stamp'
+
+
+def _fingerprint():
+    """sha256 over the flags and the CONTENT of every source / header the library is built from: the library is reused
+    only when it was built from exactly this tree (file times mean nothing after a checkout or a snapshot copy)."""
+    import hashlib
+    h = hashlib.sha256(' '.join(FLAGS).encode())
     for d in (CSRC, os.path.join(ROOT, 'include')):
-        for f in os.listdir(d):
-            t = max(t, os.path.getmtime(os.path.join(d, f)))
-    return t
+        for f in sorted(os.listdir(d)):
+            h.update(f.encode())
+            with open(os.path.join(d, f), 'rb') as fh:
+                h.update(fh.read())
+    return h.hexdigest()
 
 
 def build(force=False, verbose=False):
     os.makedirs(BUILD, exist_ok=True)
-    dep = _newest_dep()
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= dep:
-        return LIB
+    fp = _fingerprint()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+        with open(STAMP) as fh:
+            if fh.read().split()[:1] == [fp]:
+                return LIB
     objs = []
 
     def compile_one(src):
@@ -55,6 +65,9 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stderr)
+    ver = subprocess.run([NVCC, '--version'], capture_output=True, text=True).stdout.strip().splitlines()[-1:]
+    with open(STAMP, 'w') as fh:
+        fh.write('%s\nsources: %s\nflags: %s\nnvcc: %s\n' % (fp, ' '.join(sources()), ' '.join(FLAGS), ' '.join(ver)))
     return LIB
 
 
