@@ -28,7 +28,11 @@ def _parse_header():
     name -> (restype code, argument codes)."""
     import re
     path = os.path.join(os.path.dirname(HERE), 'include', 'mimo_b200.h')
-    text = open(path).read()
+    if not os.path.exists(path):
+        raise ImportError('mimo_b200: the C-ABI header %s is missing -- the ctypes signatures are read from it; keep '
+                          'include/ next to the package (in-tree layout) or copy mimo_b200.h there' % path)
+    with open(path) as fh:
+        text = fh.read()
     text = re.sub(r'/\*.*?\*/', ' ', text, flags=re.S)
     sigs = {}
     for m in re.finditer(r'(const\s+char\s*\*|int|size_t)\s+(mimo_\w+)\s*\(([^)]*)\)\s*;', text):
