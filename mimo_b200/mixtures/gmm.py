@@ -355,8 +355,22 @@ class BayesianMixtureOfGaussians:
 
     # -- SVI ---------------------------------------------------------------------------------
     def meanfield_stochastic_descent(self, obs, randomize=True, maxiter=500, step_size=1e-2,
-                                     batch_size=128, progress_bar=True, procces_id=0):
-        """gmm.py:300-326."""
+                                     batch_size=128, progress_bar=True, procces_id=0, device=False, graph=False,
+                                     lower_bound_every=1):
+        """gmm.py:300-326.  device=True keeps the whole loop on the device (mixtures/_svi.py: resident data, minibatch
+        gather, natural-parameter blend folded into the conjugate-update kernel, lower bounds read once at the end;
+        Normal-Wishart components); graph=True also replays the iterations from a CUDA graph; lower_bound_every=k
+        evaluates the full-data bound (the reference does it after EVERY minibatch, which costs a full sweep) only
+        every k-th iteration.  The device path does not perform the reference's trailing likelihood.params =
+        posterior.rvs() draws: they never feed back into the iterations."""
+        if device:
+            from . import _svi
+            from ..distributions.bayesian import StackedGaussiansWithNormalWisharts
+            assert isinstance(self.components, StackedGaussiansWithNormalWisharts), \
+                'device-resident SVI is implemented for Normal-Wishart components'
+            with tqdm(total=maxiter, desc=f'SVI #{procces_id + 1}', position=procces_id, disable=not progress_bar) as pbar:
+                return _svi.run(self, obs if not isinstance(obs, (np.ndarray, list)) else _as_obs(obs), randomize, maxiter, step_size,
+                                batch_size, graph, lower_bound_every, batches, random_responsibilities, pbar)
         obs = _as_obs(obs)
         vlb = []
         with tqdm(total=maxiter, desc=f'SVI #{procces_id + 1}', position=procces_id, disable=not progress_bar) as pbar:

@@ -486,3 +486,53 @@ def test_gibbs_device_parameter_rng(family):
             assert gv.shape == (K,) and np.all(gv > 0) and counts.sum() == len(g['obs'])
     finally:
         mimo_b200.set_default_precision('fp32')
+
+
+@pytest.mark.parametrize('name', ['gmm_toy_svi', 'gmm_toy_svi_stick'])
+@pytest.mark.parametrize('graph', [False, True])
+def test_gmm_svi_on_the_device_replays_reference(name, graph, precision):
+    """meanfield_stochastic_descent(device=True): resident data, the natural-parameter blend folded into the conjugate-update
+    kernel, bounds from device closed forms -- the reference's trajectory again, also when the iterations
+    are replayed from a CUDA graph."""
+    import random
+    g = load(name)
+    model = make_gmm(g)
+    random.seed(int(g['seed']))
+    npr.seed(int(g['seed']))
+    vlb = model.meanfield_stochastic_descent(g['obs'], randomize=True, maxiter=int(g['iters']), step_size=float(g['step_size']),
+                                             batch_size=int(g['batch_size']), progress_bar=False, device=True, graph=graph)
+    tol = 1e-8 if precision == 'fp64' else 2e-4
+    close(vlb, g['vlb'], tol, 'SVI lower bound (device)')
+    for key, ref in zip(model.components.posterior.params, ('mus', 'kappas', 'psis', 'nus')):
+        close(key, g[f'post_{ref}'], 10 * tol, 'SVI posterior ' + ref)
+    if 'gate_alphas' in g:
+        close(model.gating.posterior.alphas, g['gate_alphas'], 10 * tol, 'SVI alphas')
+    else:
+        close(model.gating.posterior.gammas, g['gate_gammas'], 10 * tol, 'SVI gammas')
+        close(model.gating.posterior.deltas, g['gate_deltas'], 10 * tol, 'SVI deltas')
+
+
+def test_svi_device_bound_every_k_and_speed():
+    """lower_bound_every: the skipped bounds do not change the iterates; the graph replay is not slower than the eager loop."""
+    import random
+    import time
+    import torch
+    import mimo_b200
+    mimo_b200.set_default_precision('fp32')
+    g = load('gmm_toy_vi')
+    out = {}
+    for key, kw in (('every', dict(lower_bound_every=1)), ('sparse', dict(lower_bound_every=10)), ('graph', dict(lower_bound_every=1, graph=True))):
+        model = make_gmm(g)
+        random.seed(2)
+        npr.seed(2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        v = model.meanfield_stochastic_descent(g['obs'], maxiter=40, step_size=5e-2, batch_size=64, progress_bar=False, device=True, **kw)
+        torch.cuda.synchronize()
+        out[key] = (v, time.perf_counter() - t0, np.array(model.components.posterior.mus))
+    assert len(out['every'][0]) == 40 and len(out['sparse'][0]) == 4
+    close(out['sparse'][0], out['every'][0][9::10], 1e-5, 'same iterates with fewer bound evaluations')
+    close(out['graph'][0], out['every'][0], 1e-5, 'graph replay = eager')
+    close(out['sparse'][2], out['every'][2], 1e-5, 'posterior means')
+    assert out['every'][0][-1] > out['every'][0][0]
+    print('SVI 40 iterations: eager %.1f ms, bound every 10th %.1f ms, graph %.1f ms' % tuple(1e3 * out[k][1] for k in ('every', 'sparse', 'graph')))
