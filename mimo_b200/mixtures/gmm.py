@@ -365,12 +365,9 @@ class BayesianMixtureOfGaussians:
         posterior.rvs() draws: they never feed back into the iterations."""
         if device:
             from . import _svi
-            from ..distributions.bayesian import StackedGaussiansWithNormalWisharts
-            assert isinstance(self.components, StackedGaussiansWithNormalWisharts), \
-                'device-resident SVI is implemented for Normal-Wishart components'
             with tqdm(total=maxiter, desc=f'SVI #{procces_id + 1}', position=procces_id, disable=not progress_bar) as pbar:
-                return _svi.run(self, obs if not isinstance(obs, (np.ndarray, list)) else _as_obs(obs), randomize, maxiter, step_size,
-                                batch_size, graph, lower_bound_every, batches, random_responsibilities, pbar)
+                return _svi.run(self, self._session(obs), randomize, maxiter, step_size, batch_size, graph, lower_bound_every,
+                                batches, random_responsibilities, pbar)
         obs = _as_obs(obs)
         vlb = []
         with tqdm(total=maxiter, desc=f'SVI #{procces_id + 1}', position=procces_id, disable=not progress_bar) as pbar:

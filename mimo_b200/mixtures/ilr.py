@@ -269,9 +269,16 @@ class BayesianMixtureOfLinearGaussians:
 
     # -- SVI ---------------------------------------------------------------------------------
     def meanfield_stochastic_descent(self, x, y, randomize=True, maxiter=500, step_size=1e-3,
-                                     batch_size=128, progress_bar=True, procces_id=0):
-        """ilr.py:245-278."""
+                                     batch_size=128, progress_bar=True, procces_id=0, device=False, graph=False,
+                                     lower_bound_every=1):
+        """ilr.py:245-278.  device / graph / lower_bound_every: the device-resident route of mixtures/_svi.py, see
+        BayesianMixtureOfGaussians.meanfield_stochastic_descent."""
         xx, yy = self._scaled(x, y)
+        if device:
+            from . import _svi
+            with tqdm(total=maxiter, desc=f'SVI #{procces_id + 1}', position=procces_id, disable=not progress_bar) as pbar:
+                return _svi.run(self, self._session(xx, yy), randomize, maxiter, step_size, batch_size, graph, lower_bound_every,
+                                batches, random_responsibilities, pbar)
         vlb = []
         with tqdm(total=maxiter, desc=f'SVI #{procces_id + 1}', position=procces_id, disable=not progress_bar) as pbar:
             scale = batch_size / float(len(xx))

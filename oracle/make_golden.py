@@ -699,6 +699,44 @@ def hierarchical_ilr():
     hmoilr_case('hmoilr_vi', x1[::2], y1[::2], 2, 2, iters=2, subiters=2, subsubiters=2, ctor_seed=60, seed=7)
 
 
+def ilr_svi_case(name, x, y, K, tied, iters, batch_size, step_size, seed):
+    """mixtures/ilr.py:245-291 (stochastic variational inference of the linear-expert mixture): seeds as in gmm_svi_case."""
+    import random
+    din, o = x.shape[1], y.shape[1]
+    rng = np.random.default_rng(seed)
+    npr.seed(seed)
+    basis, models, gating = ilr_models(K, din, o, tied, rng)
+    ilr = M.BayesianMixtureOfLinearGaussians(K, din, o, gating=gating, basis=basis, models=models)
+    rec = dict(x=x, y=y, K=K, din=din, o=o, tied=int(tied), seed=seed, iters=iters, batch_size=batch_size, step_size=step_size)
+    for n, p in zip(('b_mus0', 'b_kappas0', 'b_psis0', 'b_nus0'), basis.prior.params):
+        rec[n] = p
+    for n, p in zip(('m_Ms0', 'm_Ks0', 'm_psis0', 'm_nus0'), models.prior.params):
+        rec[n] = p
+    rec.update(gating_prior_arrays(gating))
+    random.seed(seed)
+    npr.seed(seed)
+    vlb = ilr.meanfield_stochastic_descent(x, y, randomize=True, maxiter=iters, step_size=step_size, batch_size=batch_size, progress_bar=False)
+    rec['vlb'] = np.array(vlb)
+    for n, p in zip(('mus', 'kappas', 'psis', 'nus'), basis.posterior.params):
+        rec[f'b_post_{n}'] = p
+    for n, p in zip(('Ms', 'Ks', 'psis', 'nus'), models.posterior.params):
+        rec[f'm_post_{n}'] = p
+    rec['gate_gammas'], rec['gate_deltas'] = gating.posterior.gammas, gating.posterior.deltas
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'vlb', vlb[0], '->', vlb[-1])
+
+
+def ilr_svi():
+    rng = np.random.default_rng(20170)
+    N2, din, o = 400, 2, 1
+    xi = rng.standard_normal((N2, din)) * 2.0
+    yi = np.sin(xi @ np.array([[1.0], [0.5]])) + 0.3 * rng.standard_normal((N2, o))
+    xi = (xi - xi.mean(0)) / xi.std(0)
+    yi = (yi - yi.mean(0)) / yi.std(0)
+    ilr_svi_case('ilr_svi_stacked', xi, yi, K=5, tied=False, iters=8, batch_size=96, step_size=0.1, seed=51)
+    ilr_svi_case('ilr_svi_tied', xi, yi, K=4, tied=True, iters=6, batch_size=64, step_size=0.2, seed=52)
+
+
 def hierarchical():
     rng = np.random.default_rng(77)
     K, d = 4, 2
@@ -721,7 +759,10 @@ if __name__ == '__main__':
         hierarchical()
     elif len(sys.argv) > 1 and sys.argv[1] == 'hilr':
         hierarchical_ilr()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'ilr_svi':
+        ilr_svi()
     else:
         main()
         hierarchical()
         hierarchical_ilr()
+        ilr_svi()

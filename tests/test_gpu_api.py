@@ -536,3 +536,29 @@ def test_svi_device_bound_every_k_and_speed():
     close(out['sparse'][2], out['every'][2], 1e-5, 'posterior means')
     assert out['every'][0][-1] > out['every'][0][0]
     print('SVI 40 iterations: eager %.1f ms, bound every 10th %.1f ms, graph %.1f ms' % tuple(1e3 * out[k][1] for k in ('every', 'sparse', 'graph')))
+
+
+@pytest.mark.parametrize('name', ['ilr_svi_stacked', 'ilr_svi_tied'])
+@pytest.mark.parametrize('route', ['api', 'device', 'graph'])
+def test_ilr_svi_trajectory_replays_reference(name, route, precision):
+    """mixtures/ilr.py:245-291 with the reference's seeds, on the API route (host blend) and on the device-resident route
+    (Normal-Wishart input densities + Matrix-Normal-Wishart experts blended through pseudo-priors, stick-breaking gating)."""
+    import random
+    g = load(name)
+    random.seed(int(g['seed']))
+    npr.seed(int(g['seed']))
+    np.random.default_rng(int(g['seed']))
+    ilr = make_ilr(g)
+    random.seed(int(g['seed']))
+    npr.seed(int(g['seed']))
+    kw = dict(device=True, graph=(route == 'graph')) if route != 'api' else {}
+    vlb = ilr.meanfield_stochastic_descent(g['x'], g['y'], randomize=True, maxiter=int(g['iters']), step_size=float(g['step_size']),
+                                           batch_size=int(g['batch_size']), progress_bar=False, **kw)
+    tol = 1e-8 if precision == 'fp64' else 2e-4
+    close(vlb, g['vlb'], tol, 'ILR SVI lower bound (%s)' % route)
+    for key, ref in zip(ilr.basis.posterior.params, ('mus', 'kappas', 'psis', 'nus')):
+        close(key, g[f'b_post_{ref}'], 10 * tol, 'input-density posterior ' + ref)
+    for key, ref in zip(ilr.models.posterior.params, ('Ms', 'Ks', 'psis', 'nus')):
+        close(key, g[f'm_post_{ref}'], 10 * tol, 'expert posterior ' + ref)
+    close(ilr.gating.posterior.gammas, g['gate_gammas'], 10 * tol, 'gammas')
+    close(ilr.gating.posterior.deltas, g['gate_deltas'], 10 * tol, 'deltas')
