@@ -112,13 +112,14 @@ class _NWPart:
         self.w, self.lay = wrapper, layout
         self.prior = [t.clone() for t in prior_dev]
         self.post = [E.to_dev(np.asarray(p, dtype=np.float64)) for p in wrapper.posterior.params]
+        self.prior_psi_inv = _inv(self.prior[2])            # constant: taken once
 
     def pseudo_prior(self, rho):
         m, k, psi, nu = self.post
         m0, k0, psi0, nu0 = self.prior
         kq = (1. - rho) * k + rho * k0
         mq = ((1. - rho) * k[:, None] * m + rho * k0[:, None] * m0) / kq[:, None]
-        cq = (1. - rho) * (_inv(psi) + k[:, None, None] * _outer(m)) + rho * (_inv(psi0) + k0[:, None, None] * _outer(m0))
+        cq = (1. - rho) * (_inv(psi) + k[:, None, None] * _outer(m)) + rho * (self.prior_psi_inv + k0[:, None, None] * _outer(m0))
         return [mq.contiguous(), kq.contiguous(), _inv(cq - kq[:, None, None] * _outer(mq)).contiguous(),
                 ((1. - rho) * nu + rho * nu0).contiguous()]
 
@@ -137,7 +138,7 @@ class _MNWPart(_NWPart):
         Kq = (1. - rho) * Kc + rho * K0
         mk, mk0 = torch.einsum('kdl,klm->kdm', M, Kc), torch.einsum('kdl,klm->kdm', M0, K0)
         Mq = torch.einsum('kdl,klm->kdm', (1. - rho) * mk + rho * mk0, _inv(Kq))
-        cq = (1. - rho) * (_inv(psi) + torch.einsum('kdm,khm->kdh', mk, M)) + rho * (_inv(psi0) + torch.einsum('kdm,khm->kdh', mk0, M0))
+        cq = (1. - rho) * (_inv(psi) + torch.einsum('kdm,khm->kdh', mk, M)) + rho * (self.prior_psi_inv + torch.einsum('kdm,khm->kdh', mk0, M0))
         inner = cq - torch.einsum('kdl,klm,khm->kdh', Mq, Kq, Mq)
         return [Mq.contiguous(), Kq.contiguous(), _inv(inner).contiguous(), ((1. - rho) * nu + rho * nu0).contiguous()]
 
@@ -271,7 +272,7 @@ def run(model, session, randomize, maxiter, step_size, batch_size, graph, lower_
     every = max(1, int(lower_bound_every))
     bounds = E.zeros((maxiter,))
     asked = []
-    g = None
+    graphs = {}                                         # one capture per kind of iteration: with / without the full-data bound
     for i in range(maxiter):
         for batch in batches(batch_size, s.N):
             st.set_batch(batch)
@@ -281,16 +282,16 @@ def run(model, session, randomize, maxiter, step_size, batch_size, graph, lower_
                 st.blend()
                 if want:
                     st.lower_bound()
-            elif graph and want and g is None and i >= 1:
-                st.iteration(True)                      # one eager iteration allocates every buffer ...
+            elif graph and want in graphs:
+                graphs[want].replay()
+            elif graph and i >= 1 and st.ops_current:
+                st.iteration(want)                      # one eager iteration allocates every buffer ...
                 st.check()
                 torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()              # ... the next ones replay this capture (capturing does not execute)
-                with torch.cuda.graph(g):
-                    st.iteration(True)
+                graphs[want] = torch.cuda.CUDAGraph()   # ... the next ones replay this capture (capturing does not execute)
+                with torch.cuda.graph(graphs[want]):
+                    st.iteration(want)
                 st.infos = []
-            elif g is not None and want:
-                g.replay()
             else:
                 st.iteration(want)
             if want:
