@@ -708,7 +708,11 @@ class TiedGaussiansWithHierarchicalNormalWisharts(_ComponentsBase):
         boundary.  layout['stat_idx']: columns of zt holding this part's variables and the constant (a mixture of linear
         experts keeps the input density's variables inside [x | y | 1]); default: the part's own [z | 1]."""
         d = self.dim
-        cols = list(range(d)) + [d] if layout is None else [int(c) for c in E.to_host(layout['stat_idx'])]
+        lid = None if layout is None else id(layout['stat_idx'])
+        if getattr(self, '_red_layout', -1) != lid:                  # the index tensors of a layout are read back once
+            self._red_layout = lid
+            self._red_cols = list(range(d)) + [d] if layout is None else [int(c) for c in E.to_host(layout['stat_idx'])]
+        cols = self._red_cols
         key = tuple(cols)
         if getattr(self, '_red_key', None) != key:
             v, c = cols[:d], cols[d]
@@ -732,9 +736,13 @@ class TiedGaussiansWithHierarchicalNormalWisharts(_ComponentsBase):
         """bayesian.py:662-684."""
         hp, k0 = tuple(self.hyper_prior.params), self.prior.kappas
         self.posterior.kappas = k0 + nk
-        for _ in range(nb_iter):
-            self.posterior.mus = (k0[:, None] * self.hyper_posterior.mu[None, :] + xk) / (k0 + nk)[:, None]
-            self.hyper_posterior.params = _hyper_nw_update(hp, k0, self.posterior.mus, xk, nk, sxx)
+        mus, hq = None, tuple(self.hyper_posterior.params)
+        for _ in range(nb_iter):                         # (local arrays: the K per-component objects are written once)
+            mus = (k0[:, None] * hq[0][None, :] + xk) / (k0 + nk)[:, None]
+            hq = _hyper_nw_update(hp, k0, mus, xk, nk, sxx)
+        if mus is not None:
+            self.posterior.mus = mus
+            self.hyper_posterior.params = hq
 
     def _gibbs(self, xk, nk, sxx, nb_iter):
         """bayesian.py:623-659; the draws come from the global numpy.random stream in the reference's order."""

@@ -95,7 +95,7 @@ class BayesianMixtureOfGaussiansWithHierarchicalPrior(BayesianMixtureOfGaussians
                 else:
                     resp = s.loglik(ops)
                     lse = E.softmax(resp, s.precision, resp=True, lse_sum=True)['lse_sum']
-                vlb.append(float(lse.item()) + float(outs['gating']['vlb'].item()) + float(outs['parts'][0]['vlb'].sum().item()))
+                vlb.append(float((lse.reshape(()) + outs['gating']['vlb'].reshape(()) + outs['parts'][0]['vlb'].sum()).item()))   # one read
                 if sample_likelihood:
                     self.gating._store(outs['gating'], set_probs=False)
                     self.gating.likelihood.params = self.gating.posterior.rvs()
