@@ -8,7 +8,7 @@
 // One GEMM over the points, S (components x features) = R (components x points) . Phi (points x features), with all
 // F = (D + 1)(D + 2) / 2 <= 253 features of the packed triangle in ONE accumulator (128 component lanes x round16(F)
 // columns of tensor memory) that stays resident while the CTA's slab of points streams through.  Per 64-point block
-// the 256 producer threads (a) stage the block's data transposed in shared memory, (b) write the responsibility tile
+// the 512 producer threads (a) stage the block's data transposed in shared memory, (b) write the responsibility tile
 // [128 components][64 points] -- taken as given, or formed as exp(a - lse_n) from the log-joints when the E-step kernel
 // supplied the log-normalisers (tc_estep2.cu, fused softmax) -- and (c) form the feature tile [F][64 points] as FP32
 // products split into FP16 hi + lo (tc_common.cuh); one thread issues 4 K steps x 3 passes of tcgen05.mma (M = 128,
@@ -22,7 +22,12 @@ namespace mimo {
 
 using namespace tc;
 
-constexpr int SS_THREADS = 288;                 // 8 producer / drain warps + MMA warp
+constexpr int SS_NP = 512;                      // producer / drain threads: 16 warps (8 ran the block loop at 0.9 warp instructions per clock:
+                                                // latency-bound with two warps per scheduler)
+constexpr int SS_NPW = SS_NP / 32;
+constexpr int SS_THREADS = SS_NP + 32;          // + MMA warp
+constexpr int SS_ZQ = (64 * 21 + SS_NP - 1) / SS_NP;   // data values a thread stages per block
+constexpr int SS_RQ = 128 * 8 / SS_NP;          // responsibility items (component row, 8-point chunk) per thread
 constexpr int SS_KB = 64;                       // points per block (one 128-byte operand row)
 constexpr int SS_DMAX = 21;                     // (D + 1)(D + 2) / 2 <= 253 features
 constexpr int SS_FMAX = 256;
@@ -76,9 +81,9 @@ tc_sstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float sz = ss_scale(__uint_as_float(__ldg(maxbits)));
     if (tid == 0) {
-        for (int b = 0; b < 2; ++b) { mbar_init(&bars->full[b], 256); mbar_init(&bars->empty[b], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->full[b], SS_NP); mbar_init(&bars->empty[b], 1); }
         mbar_init(&bars->acc_ready, 1);
-        mbar_init(&bars->acc_drained, 256);
+        mbar_init(&bars->acc_drained, SS_NP);
         fence_barrier_init();
     }
     // feature tables + zero rows F .. Fpad-1 of both stages' B tiles (never written again)
@@ -94,7 +99,7 @@ tc_sstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
         const int ch = idx & 7, r = F + ((idx >> 3) % (Fpad - F)), hl = (idx >> 3) / (Fpad - F) & 1, st = (idx >> 3) / (Fpad - F) >> 1;
         *reinterpret_cast<uint4*>(smem + st * stage_bytes + 2 * SS_ATILE + hl * btile + sw128_chunk_off(r, ch)) = make_uint4(0, 0, 0, 0);
     }
-    if (warp == 8) tmem_alloc(&bars->tmem_base, 256);
+    if (warp == SS_NPW) tmem_alloc(&bars->tmem_base, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -102,7 +107,7 @@ tc_sstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
     const int n_units = mtiles * slabs;
     const int64_t n_blocks = (N + SS_KB - 1) / SS_KB;
 
-    if (warp < 8) {
+    if (warp < SS_NPW) {
         // ================= producers / drain =================
         uint32_t bc = 0, dc = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -111,27 +116,27 @@ tc_sstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
             const int k0 = mt * 128;
             const int kt = min(128, K - k0);                              // component rows of this tile; the rest stay zero
             const int rvec4 = ((ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0);
-            for (int idx = tid; idx < 2 * 2 * (128 - kt) * 8; idx += 256) {
+            for (int idx = tid; idx < 2 * 2 * (128 - kt) * 8; idx += SS_NP) {
                 const int ch = idx & 7, r = kt + ((idx >> 3) % (128 - kt)), hl = ((idx >> 3) / (128 - kt)) & 1, stz = ((idx >> 3) / (128 - kt)) >> 1;
                 *reinterpret_cast<uint4*>(smem + stz * stage_bytes + hl * SS_ATILE + sw128_chunk_off(r, ch)) = make_uint4(0, 0, 0, 0);
             }
             // the global loads of a block are issued one block ahead (into registers) so that their latency hides behind the
             // feature products of the block before
-            float zr[6], lr = 0.f;                                        // ceil(64 * 21 / 256) data values per thread, one log-normaliser
-            float4 rx[4][2];                                              // <= 4 responsibility items of 8 points
+            float zr[SS_ZQ], lr = 0.f;                                    // data values per thread, one log-normaliser
+            float4 rx[SS_RQ][2];                                          // responsibility items of 8 points
             auto fetch = [&](int64_t blk) {
                 const int64_t n0 = blk * SS_KB;
                 const bool live = blk < b1;
 #pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const int idx = tid + 256 * q;
+                for (int q = 0; q < SS_ZQ; ++q) {
+                    const int idx = tid + SS_NP * q;
                     const int p = idx / D, i = idx - p * D;
                     zr[q] = (live && idx < SS_KB * D && n0 + p < N) ? __ldg(Z + (n0 + p) * ldz + i) : 0.f;
                 }
                 lr = (live && lse != nullptr && tid < SS_KB && n0 + tid < N) ? __ldg(lse + n0 + tid) : 0.f;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int item = tid + 256 * q;
+                for (int q = 0; q < SS_RQ; ++q) {
+                    const int item = tid + SS_NP * q;
                     const int ca = item >> 3, c = item & 7;
                     rx[q][0] = rx[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (live && item < kt * 8) {
@@ -154,26 +159,26 @@ tc_sstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
                 const uint32_t st = bc & 1;
                 const int64_t n0 = blk * SS_KB;
                 mbar_wait(&bars->empty[st], ((bc >> 1) & 1) ^ 1);         // the MMAs that read this stage (and zsT two blocks ago) are done
-                asm volatile("bar.sync 1, 256;" ::: "memory");            // everyone finished reading zsT / lse_s of the previous block
+                asm volatile("bar.sync 1, %0;" ::"n"(SS_NP) : "memory");   // everyone finished reading zsT / lse_s of the previous block
                 // (a) the block's data, transposed and scaled; the constant row
 #pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const int idx = tid + 256 * q;
+                for (int q = 0; q < SS_ZQ; ++q) {
+                    const int idx = tid + SS_NP * q;
                     if (idx < SS_KB * D) { const int p = idx / D, i = idx - p * D; zsT[i * SS_ZLD + p] = zr[q] * sz; }
                 }
                 if (tid < SS_KB) {
                     zsT[D * SS_ZLD + tid] = (n0 + tid < N) ? SS_ONE : 0.f;
                     lse_s[tid] = lr;
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(SS_NP) : "memory");
                 unsigned char* sA = smem + st * stage_bytes;
                 unsigned char* sBt = sA + 2 * SS_ATILE;
                 // Operand slot s = 8 c + e of the block holds point 4 c + e (e < 4) or 32 + 4 c + e - 4: both tiles use the same
                 // order (the contraction does not care), and the eight lanes of a row then read 128 contiguous bytes.
                 // (b) responsibilities: item = (component row, 8-slot chunk), spread over all threads whatever K is
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int item = tid + 256 * q;
+                for (int q = 0; q < SS_RQ; ++q) {
+                    const int item = tid + SS_NP * q;
                     if (item >= kt * 8) break;
                     const int ca = item >> 3, c = item & 7;
                     float x[8] = {rx[q][0].x, rx[q][0].y, rx[q][0].z, rx[q][0].w, rx[q][1].x, rx[q][1].y, rx[q][1].z, rx[q][1].w};
@@ -192,8 +197,9 @@ tc_sstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
                     *reinterpret_cast<uint4*>(sA + SS_ATILE + o) = lo;
                 }
                 fetch(blk + 1);                                           // in flight while the features are formed
-                // (c) features: item = (feature f, 8-slot chunk c)
-                for (int item = tid; item < F * 8; item += 256) {
+                // (c) features: item = (feature f, 8-slot chunk c)   (loading a thread's items together before multiplying
+                // them was measured slower: 2.8 vs 2.0 ms at cfg4)
+                for (int item = tid; item < F * 8; item += SS_NP) {
                     const int f = item >> 3, c = item & 7;
                     const int i = fij[2 * f], j = fij[2 * f + 1];
                     const float4 a0 = *reinterpret_cast<const float4*>(zsT + i * SS_ZLD + 4 * c), a1 = *reinterpret_cast<const float4*>(zsT + i * SS_ZLD + 32 + 4 * c);
@@ -215,7 +221,7 @@ tc_sstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
                     const int qd = warp & 3, cg = warp >> 2;
                     const int k = k0 + qd * 32 + lane;
                     const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
-                    for (int c16 = cg; c16 < Fpad / 16; c16 += 2) {
+                    for (int c16 = cg; c16 < Fpad / 16; c16 += SS_NPW / 4) {
                         float v[16];
                         tmem_ld16(taddr + 16 * c16, v);
                         tmem_ld_wait();
@@ -270,7 +276,7 @@ tc_sstats_kernel(const float* __restrict__ Z, int64_t N, int D, int64_t ldz,
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 256);
+    if (warp == SS_NPW) tmem_dealloc(tmem_base, 256);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
