@@ -93,7 +93,7 @@ class Features:
         self.F = len(fi)
         self.fi_host = np.asarray(fi, dtype=np.int32)
         self.fj_host = np.asarray(fj, dtype=np.int32)
-        self._dev = None
+        self._dev = {}                                   # device index -> (fi, fj) tensors
         # canonical packed triangle f = i (i + 1) / 2 + j?  (the device copy is made from these host arrays, so the sweep can
         # be told instead of reading the tables back)
         il = np.tril_indices(D + 1)
@@ -101,9 +101,10 @@ class Features:
                               and np.array_equal(self.fj_host, il[1]))
 
     def dev(self):
-        if self._dev is None:
-            self._dev = (to_dev(self.fi_host, torch.int32), to_dev(self.fj_host, torch.int32))
-        return self._dev
+        idx = device().index
+        if idx not in self._dev:
+            self._dev[idx] = (to_dev(self.fi_host, torch.int32), to_dev(self.fj_host, torch.int32))
+        return self._dev[idx]
 
 
 def quad_features(D):
