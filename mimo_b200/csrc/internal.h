@@ -17,7 +17,7 @@ int tc_diag_enable(int on);
 size_t tc_diag_workspace();
 const unsigned int* tc_diag_gate(void* ws);      // 1: the operands failed the cancellation guard, the CUDA-core kernels must run
 int tc_diag_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float* S, const float* T, const float* cst, int K,
-                    void* ws, cudaStream_t st);
+                    void* ws, cudaStream_t st, float absmax_hint = 0.f);
 int tc_diag_chunk(const float* Z, int64_t N, int D, int64_t ldz, int K, float* out, int64_t ldo,
                   int32_t* labels, const double* uniforms, uint64_t seed, uint64_t point_offset,
                   float* lse_out, double* lse_sum, void* ws, cudaStream_t st);
@@ -39,9 +39,10 @@ int tc_set_mode(int mode);
 int tc_set_min_dim(int d);
 bool tc_estep_supported(int dtype, int D, int Rp);
 size_t tc_operand_workspace(int K, int Rp, int D);
-int tc_data_scale(const float* Z, int64_t N, int D, int64_t ldz, void* ws, cudaStream_t st);
+int tc_data_scale(const float* Z, int64_t N, int D, int64_t ldz, void* ws, cudaStream_t st, float absmax_hint = 0.f);   // hint > 0: max |Z| is known, no pass over Z
 const unsigned int* tc_maxbits(void* ws);
-void tc_set_absmax_hint(float v);     // one-shot: the next tc_data_scale of this thread takes v instead of scanning Z
+void tc_set_absmax_hint(float v);     // one-shot: the next sweep() of this thread takes v instead of scanning Z
+float tc_take_absmax_hint();          // read and clear
 int tc_prepare_operands(const float* W, const float* cst, int K, int Rp, int Dpp, int D, void* ws, cudaStream_t st);
 unsigned int* tc_flags(void* ws);    // [0] max |z| bits, [2] max_k ||W'_k||_F (screening operands), [3] max_n ||z_n||_2, [4] max_k ||W_k||_F (all columns)
 int tc_estep_pass(const float* Z, int64_t N, int D, int64_t ldz, int K, int Rp, float* out, int64_t ldo, void* ws,

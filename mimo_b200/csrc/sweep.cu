@@ -125,6 +125,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
           void* workspace, size_t workspace_bytes, cudaStream_t st, double* phase_ms) {
     const int promise = g_tables_promise;              // one-shot: whatever this sweep does with it, the next one starts clean
     g_tables_promise = -1;
+    const float absmax_hint = tc_take_absmax_hint();   // likewise: taken here, whichever kernels the sweep ends up running
     MIMO_CHECK_ARG(dtype == MIMO_F32 || dtype == MIMO_F64, "dtype");
     MIMO_CHECK_ARG(family == 0 || family == 1, "family");
     MIMO_CHECK_ARG(Z && op_a && cst && workspace && (family == 0 || op_b), "null pointer");
@@ -157,7 +158,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
     void* diag_ws = nullptr;
     if (diag_tc) {
         diag_ws = ws; ws += a256(tc_diag_workspace());
-        int rc = tc_diag_prepare((const float*)Z, N, D, ldz, (const float*)op_a, (const float*)op_b, (const float*)cst, K, diag_ws, st);
+        int rc = tc_diag_prepare((const float*)Z, N, D, ldz, (const float*)op_a, (const float*)op_b, (const float*)cst, K, diag_ws, st, absmax_hint);
         if (rc) return rc;
     }
     void* tc_ops_ws = nullptr;
@@ -186,7 +187,7 @@ int sweep(int dtype, int family, int hard, const void* Z, int64_t N, int D, int6
             screen_ops_ws = ws; ws += a256(tc_screen_operand_workspace(K, Rp, D + 4, D));
         }
         if (!hard) { lse_chunk = (float*)ws; ws += a256((size_t)C * 4); tc_stat_ws = ws; }
-        int rc = tc_data_scale((const float*)Z, N, D, ldz, tc_ops_ws, st);
+        int rc = tc_data_scale((const float*)Z, N, D, ldz, tc_ops_ws, st, absmax_hint);
         if (rc) return rc;
         rc = tc_prepare_operands((const float*)op_a, (const float*)cst, K, Rp, Dpp, D, tc_ops_ws, st);
         if (rc) return rc;

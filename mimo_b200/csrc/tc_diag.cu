@@ -439,9 +439,9 @@ const unsigned int* tc_diag_gate(void* ws) { return reinterpret_cast<const unsig
 
 // once per sweep: data scale, centre, weight image
 int tc_diag_prepare(const float* Z, int64_t N, int D, int64_t ldz, const float* S, const float* T, const float* cst, int K,
-                    void* ws, cudaStream_t st) {
+                    void* ws, cudaStream_t st, float absmax_hint) {
     TdLayout L = td_layout(ws);
-    int rc = tc_data_scale(Z, N, D, ldz, ws, st);                 // max |z| -> L.zmax[0]
+    int rc = tc_data_scale(Z, N, D, ldz, ws, st, absmax_hint);    // max |z| -> L.zmax[0]
     if (rc) return rc;
     td_center_kernel<<<1, 64, 0, st>>>(S, T, K, D, L.zmax, L.prm);
     MIMO_LAUNCH_CHECK();

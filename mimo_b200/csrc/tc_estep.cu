@@ -340,19 +340,22 @@ size_t tc_operand_workspace(int K, int Rp, int D) { return tc_layout(K, Rp, D).b
 static char* align1k(void* p) { return (char*)(((uintptr_t)p + 1023) / 1024 * 1024); }
 
 // A caller that keeps the data resident across sweeps may pass max |Z| of that data (mimo_sweep_absmax_hint): the next
-// sweep of this thread then skips the pass over Z below (25.6 GB = 4.5 ms per sweep at N = 100M, d = 64).  One-shot.
+// SWEEP of this thread then skips the pass over Z below (25.6 GB = 4.5 ms per sweep at N = 100M, d = 64).  One-shot, and
+// scoped to that sweep: sweep() takes the value on entry whatever kernels it ends up running (a sweep that stays on the
+// CUDA cores used to leave it behind, and the next tensor-core call -- on other data -- scaled its operands with it) and
+// hands it to tc_data_scale explicitly; the stand-alone entry points never see it.
 static thread_local float g_absmax_hint = 0.f;
 void tc_set_absmax_hint(float v) { g_absmax_hint = (v > 0.f && v < 3.0e38f) ? v : 0.f; }
+float tc_take_absmax_hint() { const float v = g_absmax_hint; g_absmax_hint = 0.f; return v; }
 __global__ void tc_store_bits_kernel(unsigned int* dst, unsigned int bits) { *dst = bits; }
 
 // max |Z| over the resident data -> ws (the common power-of-two data scale of a sweep)
-int tc_data_scale(const float* Z, int64_t N, int D, int64_t ldz, void* ws, cudaStream_t st) {
+int tc_data_scale(const float* Z, int64_t N, int D, int64_t ldz, void* ws, cudaStream_t st, float absmax_hint) {
     char* base = align1k(ws);
     MIMO_CUDA(cudaMemsetAsync(base, 0, 256, st));
-    if (g_absmax_hint > 0.f) {
+    if (absmax_hint > 0.f) {
         unsigned int bits;
-        memcpy(&bits, &g_absmax_hint, 4);
-        g_absmax_hint = 0.f;
+        memcpy(&bits, &absmax_hint, 4);
         tc_store_bits_kernel<<<1, 1, 0, st>>>((unsigned int*)base, bits);
         MIMO_LAUNCH_CHECK();
         return MIMO_OK;

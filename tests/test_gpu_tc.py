@@ -417,3 +417,39 @@ def test_screen_tiers_across_chunks():
     assert abs(ref.lse_sum.item() - buf.lse_sum.item()) <= 1e-6 * abs(ref.lse_sum.item())
     assert abs(buf.stat.cpu().numpy()[:, -1].sum() - N) <= 1e-6 * N
     assert dense == 0 and level == 1, 'the sweep should have moved to the all-rows tier and screened the last chunk there (level %d)' % level
+
+
+def test_absmax_hint_is_scoped_to_its_sweep():
+    """mimo_sweep_absmax_hint belongs to the NEXT SWEEP, whatever kernels that sweep runs: a small-dimension sweep stays on
+    the CUDA cores and used to leave its max |Z| behind, and the next tensor-core call -- on other data -- scaled its FP16
+    operands with it (overflow -> NaN when the new data are larger).  Found by test order in round 2."""
+    E = eng()
+    rng = np.random.default_rng(3)
+    # 1. a d = 2 sweep (no tensor cores) on tiny-valued data, with the hint the Python Session gives
+    K0, d0, N0 = 3, 2, 400
+    x0 = 1e-3 * rng.standard_normal((N0, d0))
+    ops0 = E.QuadOperands(K0, d0, d0, 'fp32')
+    E.set_log_weights(ops0, np.log(np.ones(K0) / K0))
+    E.operands_gauss(ops0, E.to_dev(1e-3 * rng.standard_normal((K0, d0))), E.to_dev(np.stack(K0 * [1e6 * np.eye(d0)]))).check()
+    Z0 = E.to_dev(x0, torch.float32)
+    feats0 = E.quad_features(d0)
+    assert not E.sweep_uses_tensor_cores(ops0, d0)
+    E.sweep(Z0, ops0, feats0, E.SweepBuffers(N0, K0, feats0.F, 'fp32', False), absmax=float(np.abs(x0).max()))
+    # 2. the tensor-core log-likelihood on data five orders of magnitude larger
+    K, d, N = 6, 64, 500
+    x = 40. * rng.standard_normal((N, d))
+    mus = 40. * rng.standard_normal((K, d))
+    lmbdas = np.stack([spd(rng, d) / 1600. for _ in range(K)])
+    ops = E.QuadOperands(K, d, d, 'fp32')
+    E.set_log_weights(ops, np.zeros(K))
+    E.operands_gauss(ops, E.to_dev(mus), E.to_dev(lmbdas)).check()
+    Z = E.to_dev(x, torch.float32)
+    ll = E.loglik_tc(Z, ops)
+    assert torch.isfinite(ll).all()
+    close(ll, orc.gauss_full_loglik(Z.double().cpu().numpy(), mus, lmbdas), 1e-4, 'tensor-core log-lik after a hinted CUDA-core sweep')
+    # ... and a tensor-core sweep takes its own hint
+    feats = E.quad_features(d)
+    buf = E.SweepBuffers(N, K, feats.F, 'fp32', False)
+    E.sweep(Z, ops, feats, buf, absmax=float(np.abs(x).max()))
+    resp, lse = orc.responsibilities(orc.gauss_full_loglik(Z.double().cpu().numpy(), mus, lmbdas))
+    assert abs(buf.lse_sum.item() - lse.sum()) <= 1e-5 * abs(lse.sum())
