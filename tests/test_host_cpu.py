@@ -108,3 +108,56 @@ def test_bench_algorithmic_work_matches_survey():
     w2 = bench.algorithmic_work(bench.WORKLOADS['cfg2'])
     assert w2['e_flops_pair'] == (2 * 8 * 9 + 2 * 8) + (2 * 1 * 9 + 2 + 2 * 81 + 2 + 18) and w2['s_flops_pair'] == 2 * 81 + 2 * 100
     assert w2['e_flops_pair'] == 362 and w2['s_flops_pair'] == 362
+
+
+# ---- device-resident SVI (mixtures/_svi.py): its closed forms and pseudo-priors are plain torch, checked here on CPU tensors
+def _spd(rng, d):
+    a = rng.standard_normal((d, d + 2))
+    return a @ a.T / d + 0.2 * np.eye(d)
+
+
+def test_svi_lower_bound_closed_forms_match_oracle():
+    import torch
+    from oracle import mimo_oracle as orc
+    from mimo_b200.mixtures import _svi
+    rng = np.random.default_rng(0)
+    K, d, o, c = 4, 3, 2, 4
+    T = lambda *a: [torch.from_numpy(np.ascontiguousarray(np.asarray(v, dtype=np.float64))) for v in a]      # noqa: E731
+    nw_p = (rng.standard_normal((K, d)), rng.random(K) + .1, np.stack([_spd(rng, d) for _ in range(K)]), d + 1. + rng.random(K))
+    nw_q = (rng.standard_normal((K, d)), rng.random(K) + 5., np.stack([_spd(rng, d) / 30. for _ in range(K)]), d + 30. + rng.random(K))
+    np.testing.assert_allclose(_svi.nw_lower_bound(T(*nw_p), T(*nw_q)).numpy(), orc.nw_vlb(nw_p, nw_q), rtol=1e-10)
+    mnw_p = (rng.standard_normal((K, o, c)), np.stack([_spd(rng, c) for _ in range(K)]), np.stack([_spd(rng, o) for _ in range(K)]), o + 1. + rng.random(K))
+    mnw_q = (rng.standard_normal((K, o, c)), np.stack([_spd(rng, c) * 20. for _ in range(K)]), np.stack([_spd(rng, o) / 25. for _ in range(K)]),
+             o + 25. + rng.random(K))
+    np.testing.assert_allclose(_svi.mnw_lower_bound(T(*mnw_p), T(*mnw_q)).numpy(), orc.mnw_vlb(mnw_p, mnw_q), rtol=1e-10)
+    a0, a = np.ones(K), 1. + 10. * rng.random(K)
+    np.testing.assert_allclose(float(_svi.dirichlet_lower_bound(*T(a0, a))), orc.dirichlet_vlb(a0, a), rtol=1e-10)
+    g0, d0, g, dl = np.ones(K), 5. * np.ones(K), 1. + 9. * rng.random(K), 5. + 9. * rng.random(K)
+    np.testing.assert_allclose(float(_svi.stick_lower_bound(T(g0, d0), T(g, dl))), orc.stick_vlb((g0, d0), (g, dl)), rtol=1e-10)
+
+
+def test_svi_pseudo_prior_is_the_natural_parameter_blend():
+    """nat_to_std((1 - rho) nat(q) + rho nat(p)): what folds the SVI blend into the conjugate-update kernels."""
+    import torch
+    from oracle import mimo_oracle as orc
+    from mimo_b200.mixtures import _svi
+    rng = np.random.default_rng(1)
+    K, d, o, c, rho = 3, 4, 2, 3, 0.3
+    T = lambda *a: [torch.from_numpy(np.ascontiguousarray(np.asarray(v, dtype=np.float64))) for v in a]      # noqa: E731
+
+    def part(cls, prior, post):
+        p = object.__new__(cls)
+        p.prior, p.post = T(*prior), T(*post)
+        p.prior_psi_inv = torch.linalg.inv(p.prior[2])
+        return p
+    nw_p = (rng.standard_normal((K, d)), rng.random(K) + .1, np.stack([_spd(rng, d) for _ in range(K)]), d + 1. + rng.random(K))
+    nw_q = (rng.standard_normal((K, d)), rng.random(K) + 5., np.stack([_spd(rng, d) / 30. for _ in range(K)]), d + 30. + rng.random(K))
+    blend = [(1. - rho) * a + rho * b for a, b in zip(orc.nw_std_to_nat(*nw_q), orc.nw_std_to_nat(*nw_p))]
+    for got, ref in zip(part(_svi._NWPart, nw_p, nw_q).pseudo_prior(rho), orc.nw_nat_to_std(blend)):
+        np.testing.assert_allclose(got.numpy(), ref, rtol=1e-9, atol=1e-12)
+    mnw_p = (rng.standard_normal((K, o, c)), np.stack([_spd(rng, c) for _ in range(K)]), np.stack([_spd(rng, o) for _ in range(K)]), o + 1. + rng.random(K))
+    mnw_q = (rng.standard_normal((K, o, c)), np.stack([_spd(rng, c) * 20. for _ in range(K)]), np.stack([_spd(rng, o) / 25. for _ in range(K)]),
+             o + 25. + rng.random(K))
+    blend = [(1. - rho) * a + rho * b for a, b in zip(orc.mnw_std_to_nat(*mnw_q), orc.mnw_std_to_nat(*mnw_p))]
+    for got, ref in zip(part(_svi._MNWPart, mnw_p, mnw_q).pseudo_prior(rho), orc.mnw_nat_to_std(blend)):
+        np.testing.assert_allclose(got.numpy(), ref, rtol=1e-9, atol=1e-12)
