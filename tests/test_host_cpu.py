@@ -161,3 +161,43 @@ def test_svi_pseudo_prior_is_the_natural_parameter_blend():
     blend = [(1. - rho) * a + rho * b for a, b in zip(orc.mnw_std_to_nat(*mnw_q), orc.mnw_std_to_nat(*mnw_p))]
     for got, ref in zip(part(_svi._MNWPart, mnw_p, mnw_q).pseudo_prior(rho), orc.mnw_nat_to_std(blend)):
         np.testing.assert_allclose(got.numpy(), ref, rtol=1e-9, atol=1e-12)
+
+
+def test_device_parameter_variates_layout_on_cpu_tensors():
+    """draw_gibbs_variates('device') helpers are plain torch: the layout of draw_wishart_variates ([normal(d(d-1)/2) |
+    chisquare(nu - i) | normal(extra)]), the Normal-Gamma layout ([gamma(alpha, 1/beta) | normal]) and the gating draws."""
+    import torch
+    from mimo_b200.distributions.bayesian import (_ComponentsBase, StackedGaussiansWithNormalGammas, CategoricalWithDirichlet,
+                                                  CategoricalWithStickBreaking)
+    g = torch.Generator().manual_seed(5)
+    K, d = 2000, 3
+    nus = torch.full((K,), 7.5, dtype=torch.float64)
+    v = _ComponentsBase()._wishart_variates_device(nus, d, d, g)
+    nt = d * (d - 1) // 2
+    assert v.shape == (K, nt + d + d)
+    chi = v[:, nt:nt + d].numpy()
+    np.testing.assert_allclose(chi.mean(0), 7.5 - np.arange(d), rtol=0.05)          # E chi2(df) = df
+    np.testing.assert_allclose(chi.var(0), 2. * (7.5 - np.arange(d)), rtol=0.15)
+    assert abs(v[:, :nt].mean()) < 0.05 and abs(v[:, :nt].var() - 1.) < 0.1
+    ng = object.__new__(StackedGaussiansWithNormalGammas)
+    ng.size, ng.dim, ng.bug_compat, ng._tied = K, d, False, False
+    stat = torch.zeros((K, 2 * d + 1), dtype=torch.float64)
+    stat[:, 2 * d] = 10.
+    stat[:, :d] = 20.
+    stat[:, d:2 * d] = 50.
+    prior = [torch.zeros((K, d), dtype=torch.float64), torch.full((K, d), 0.1, dtype=torch.float64),
+             torch.full((K, d), 2., dtype=torch.float64), torch.full((K, d), 1., dtype=torch.float64)]
+    w = ng._draw_variates_device(None, stat, g, prior)
+    kap = 0.1 + 10.
+    al, be = 2. + 5., 1. + 0.5 * (50. - kap * (20. / kap) ** 2)
+    np.testing.assert_allclose(w[:, :d].mean().item(), al / be, rtol=0.05)           # E gamma(alpha, 1 / beta)
+    assert abs(w[:, d:].mean().item()) < 0.05
+    gate = object.__new__(CategoricalWithDirichlet)
+    counts = torch.tensor([3., 0., 5.], dtype=torch.float64)
+    gv = gate._draw_variates_device(counts, g, (torch.ones(3, dtype=torch.float64), None))
+    assert gv.shape == (3,) and bool((gv > 0).all())
+    stick = object.__new__(CategoricalWithStickBreaking)
+    sv = stick._draw_variates_device(counts, g, (torch.ones(3, dtype=torch.float64), 2. * torch.ones(3, dtype=torch.float64)))
+    assert sv.shape == (2,) and bool(((sv > 0) & (sv < 1)).all())
+    g2 = torch.Generator().manual_seed(5)
+    assert torch.equal(_ComponentsBase()._wishart_variates_device(nus, d, d, g2), v)   # same seed, same draws: ranks agree without a broadcast
