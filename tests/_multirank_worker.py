@@ -61,7 +61,23 @@ def main():
         g_1.resample(x, init_labels='random', maxiter=2, progress_bar=False)
         same = float(np.mean(np.asarray(g_sh.labels_) == np.asarray(g_1.labels_)[lo:hi]))
         results[precision]['gibbs_label_agreement'] = same
-        results[precision]['ok'] = results[precision]['ok'] and same >= (1.0 if precision == 'fp64' else 0.995)
+        # (FP32: sharded and single-process statistics differ in the last bits, a point within ~1e-7 of a CDF boundary may
+        #  flip, and the two chains then drift apart slowly: 0.9987 and 1.0 were observed after 2 sweeps, the bar is 0.97)
+        results[precision]['ok'] = results[precision]['ok'] and same >= (1.0 if precision == 'fp64' else 0.97)
+        # ... nor when nothing is drawn on the host: Philox labels + parameter variates from the device generator every rank
+        # seeds identically (no host read of the statistics, no broadcast per sweep)
+        npr.seed(6)
+        d_sh = build_model(K, d, precision)
+        d_sh.resample(x[lo:hi], init_labels='random', maxiter=3, progress_bar=False, comm=Communicator(N_global=N),
+                      label_rng='philox', param_rng='device')
+        npr.seed(6)
+        d_1 = build_model(K, d, precision)
+        d_1.resample(x, init_labels='random', maxiter=3, progress_bar=False, label_rng='philox', param_rng='device')
+        same_d = float(np.mean(np.asarray(d_sh.labels_) == np.asarray(d_1.labels_)[lo:hi]))
+        mu_err = float(np.max(np.abs(d_sh.components.likelihood.mus - d_1.components.likelihood.mus)))
+        results[precision]['gibbs_device_rng'] = dict(label_agreement=same_d, sampled_means_err=mu_err)
+        results[precision]['ok'] = results[precision]['ok'] and same_d >= (1.0 if precision == 'fp64' else 0.97) \
+            and mu_err <= (1e-8 if precision == 'fp64' else 0.5)
     # the same exchange through the library's own C-ABI (mimo_comm_*: NCCL loaded by the library, no torch in the call)
     from mimo_b200.sharded import AbiCommunicator
     abi = AbiCommunicator(N_global=1000)

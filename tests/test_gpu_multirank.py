@@ -32,6 +32,7 @@ def test_two_rank_nccl_session_matches_single_process(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=570)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     verdict = json.load(open(out))
+    print(json.dumps(verdict[0]))            # (shown with pytest -s / on failure)
     assert len(verdict) == 2
     for rank_result in verdict:
         for precision, res in rank_result.items():
