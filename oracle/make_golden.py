@@ -737,6 +737,31 @@ def ilr_svi():
     ilr_svi_case('ilr_svi_tied', xi, yi, K=4, tied=True, iters=6, batch_size=64, step_size=0.2, seed=52)
 
 
+def hmom_em_case(name, x, M_, K, iters, subiters, seed):
+    """mixtures/hgmm.py:16-89 (examples/hgmm/em_hgmm.py:66-93): EM of a mixture of mixtures of tied Gaussians."""
+    d = x.shape[1]
+    rng = np.random.default_rng(seed)
+    rec = dict(obs=x, M=M_, K=K, d=d, iters=iters, subiters=subiters, seed=seed)
+    comps = []
+    for m in range(M_):
+        prob = rng.random(K)
+        prob /= prob.sum()
+        mus = 3. * rng.standard_normal((K, d))
+        rec[f'probs{m}'], rec[f'mus{m}'] = prob, mus
+        comps.append(M.MixtureOfGaussians(gating=D.Categorical(dim=K, probs=prob),
+                                          components=D.TiedGaussiansWithPrecision(size=K, dim=d, mus=mus, lmbdas=np.stack(K * [0.5 * np.eye(d)]))))
+    model = M.MixtureOfMixtureOfGaussians(cluster_size=M_, mixture_size=K, dim=d, gating=D.Categorical(dim=M_), components=comps)
+    npr.seed(seed)
+    ll = model.max_likelihood(x, maxiter=iters, maxsubiter=subiters, progress_bar=False)
+    rec['ll'] = np.array(ll)
+    rec['gate_probs'] = model.gating.probs.copy()
+    for m, c in enumerate(comps):
+        rec[f'end_mus{m}'], rec[f'end_lmbdas{m}'], rec[f'end_probs{m}'] = c.components.mus.copy(), c.components.lmbdas.copy(), c.gating.probs.copy()
+    rec['resp_end'] = model.responsibilities(x)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, 'll', ll[0], '->', ll[-1], 'monotone', bool(np.all(np.diff(ll) >= -1e-8)))
+
+
 def hierarchical():
     rng = np.random.default_rng(77)
     K, d = 4, 2
@@ -751,6 +776,7 @@ def hierarchical():
     xm = np.vstack([centres[:2][rng.integers(0, 2, 150)] + rng.standard_normal((150, d)),
                     (centres[2:][rng.integers(0, 2, 150)] + rng.standard_normal((150, d))) * np.array([1., 0.4])])
     hmom_case('hmom_vi', xm, 2, 2, iters=3, subiters=3, subsubiters=3, ctor_seed=50, seed=6)
+    hmom_em_case('hmom_em', xm, 2, 2, iters=4, subiters=3, seed=12)
 
 
 

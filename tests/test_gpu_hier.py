@@ -383,3 +383,26 @@ def test_single_affine_expert_gibbs_replays_reference(fp64):
     ll = w.likelihood.log_likelihood(g['x'], g['y'])
     ref = orc.lingauss_loglik(g['x'], g['y'], np.hstack((g['A'], g['c'][:, None]))[None], g['lmbda'][None], affine=True)[0]
     close(ll, ref, 1e-9, 'log-likelihood of the sampled expert')
+
+
+def test_mixture_of_mixtures_em(fp64):
+    """hgmm.py:59-89 (examples/hgmm/em_hgmm.py): EM of a mixture of mixtures of tied Gaussians; the clusters are trained
+    by weighted EM (gmm.py:77-103 with weights)."""
+    from mimo_b200.distributions import Categorical, TiedGaussiansWithPrecision
+    from mimo_b200.mixtures import MixtureOfGaussians, MixtureOfMixtureOfGaussians
+    g = load('hmom_em')
+    M_, K, d = int(g['M']), int(g['K']), int(g['d'])
+    comps = [MixtureOfGaussians(gating=Categorical(dim=K, probs=g[f'probs{m}']),
+                                components=TiedGaussiansWithPrecision(size=K, dim=d, mus=g[f'mus{m}'], lmbdas=np.stack(K * [0.5 * np.eye(d)])))
+             for m in range(M_)]
+    model = MixtureOfMixtureOfGaussians(cluster_size=M_, mixture_size=K, dim=d, gating=Categorical(dim=M_), components=comps)
+    npr.seed(int(g['seed']))
+    ll = model.max_likelihood(g['obs'], maxiter=int(g['iters']), maxsubiter=int(g['subiters']), progress_bar=False)
+    close(ll, g['ll'], 1e-8, 'log-likelihood trajectory')
+    assert np.all(np.diff(ll) >= -1e-8)                        # "ll monoton?" of the example
+    close(model.gating.probs, g['gate_probs'], 1e-8, 'cluster probabilities')
+    for m, c in enumerate(comps):
+        close(c.components.mus, g[f'end_mus{m}'], 1e-7, 'means')
+        close(c.components.lmbdas, g[f'end_lmbdas{m}'], 1e-7, 'tied precisions')
+        close(c.gating.probs, g[f'end_probs{m}'], 1e-8, 'local probabilities')
+    close(model.responsibilities(g['obs']), g['resp_end'], 1e-7, 'cluster responsibilities')
