@@ -762,6 +762,58 @@ def hmom_em_case(name, x, M_, K, iters, subiters, seed):
     print(name, 'll', ll[0], '->', ll[-1], 'monotone', bool(np.all(np.diff(ll) >= -1e-8)))
 
 
+def api_misc():
+    """small public methods of the drivers that the trajectory fixtures do not reach: used_labels, log_marginal_likelihood,
+    posterior_predictive_studentt, meanfield_update_{gating,components}, ILR resample_{basis,models},
+    meanfield_predictive_activation -- on the models of gmm_toy_vi / ilr_stacked after a short seeded mean-field run."""
+    g = dict(np.load(os.path.join(OUT, 'gmm_toy_vi.npz')))
+    K, d = int(g['K']), int(g['d'])
+    prior = D.StackedNormalWisharts(K, d, g['mus0'], g['kappas0'], g['psis0'], g['nus0'])
+    npr.seed(1)
+    comp = D.StackedGaussiansWithNormalWisharts(K, d, prior=prior)
+    gating = D.CategoricalWithDirichlet(K, D.Dirichlet(K, g['gate_alphas0']))
+    model = M.BayesianMixtureOfGaussians(gating=gating, components=comp)
+    x = g['obs']
+    npr.seed(17)
+    model.meanfield_coordinate_descent(x, maxiter=3, tol=0., progress_bar=False)
+    rec = dict(used_labels=model.used_labels(x), lml=comp.log_marginal_likelihood())
+    for n, p in zip(('mus', 'lmbdas', 'dfs'), comp.posterior_predictive_studentt()):
+        rec['pst_' + n] = p
+    resp = model.expected_responsibilities(x)
+    rec['resp'] = resp
+    npr.seed(18)
+    model.meanfield_update_gating(resp)
+    rec['gate_alphas'] = gating.posterior.alphas.copy()
+    npr.seed(19)
+    model.meanfield_update_components(x, resp)
+    for n, p in zip(('mus', 'kappas', 'psis', 'nus'), comp.posterior.params):
+        rec['post_' + n] = p
+    np.savez_compressed(os.path.join(OUT, 'api_misc_gmm.npz'), **rec)
+    # ILR
+    g = dict(np.load(os.path.join(OUT, 'ilr_stacked.npz')))
+    K, din, o = int(g['K']), int(g['din']), int(g['o'])
+    c = din + 1
+    npr.seed(2)
+    basis = D.StackedGaussiansWithNormalWisharts(K, din, prior=D.StackedNormalWisharts(K, din, g['b_mus0'], g['b_kappas0'], g['b_psis0'], g['b_nus0']))
+    models = D.StackedLinearGaussiansWithMatrixNormalWisharts(K, c, o, D.StackedMatrixNormalWisharts(K, c, o, g['m_Ms0'], g['m_Ks0'], g['m_psis0'], g['m_nus0']), affine=True)
+    gating = D.CategoricalWithStickBreaking(K, D.TruncatedStickBreaking(K, g['gate_gammas0'], g['gate_deltas0']))
+    ilr = M.BayesianMixtureOfLinearGaussians(K, din, o, gating=gating, basis=basis, models=models)
+    x, y = g['x'], g['y']
+    npr.seed(27)
+    ilr.meanfield_coordinate_descent(x, y, maxiter=3, tol=0., progress_bar=False)
+    rec = dict(used_labels=ilr.used_labels(x, y), activation=ilr.meanfield_predictive_activation(x[:40]))
+    z = np.argmax(ilr.expected_responsibilities(x, y), axis=0)
+    rec['z'] = z.astype(np.int32)
+    npr.seed(28)
+    ilr.resample_basis(x, z)
+    rec['b_lik_mus'], rec['b_lik_lmbdas'] = basis.likelihood.mus.copy(), basis.likelihood.lmbdas.copy()
+    npr.seed(29)
+    ilr.resample_models(x, y, z)
+    rec['m_lik_As'], rec['m_lik_lmbdas'] = models.likelihood.As.copy(), models.likelihood.lmbdas.copy()
+    np.savez_compressed(os.path.join(OUT, 'api_misc_ilr.npz'), **rec)
+    print('api_misc ok: used labels', rec['used_labels'])
+
+
 def hierarchical():
     rng = np.random.default_rng(77)
     K, d = 4, 2
@@ -787,8 +839,11 @@ if __name__ == '__main__':
         hierarchical_ilr()
     elif len(sys.argv) > 1 and sys.argv[1] == 'ilr_svi':
         ilr_svi()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'api_misc':
+        api_misc()
     else:
         main()
         hierarchical()
         hierarchical_ilr()
         ilr_svi()
+        api_misc()

@@ -562,3 +562,45 @@ def test_ilr_svi_trajectory_replays_reference(name, route, precision):
         close(key, g[f'm_post_{ref}'], 10 * tol, 'expert posterior ' + ref)
     close(ilr.gating.posterior.gammas, g['gate_gammas'], 10 * tol, 'gammas')
     close(ilr.gating.posterior.deltas, g['gate_deltas'], 10 * tol, 'deltas')
+
+
+def test_small_public_methods_against_reference(precision):
+    """used_labels, log_marginal_likelihood, posterior_predictive_studentt, meanfield_update_{gating,components} (GMM) and
+    used_labels, meanfield_predictive_activation, resample_{basis,models} (ILR): fixtures api_misc_*.npz made from the
+    reference on the models of gmm_toy_vi / ilr_stacked after a short seeded mean-field run."""
+    tol = TOL[precision]
+    g, r = load('gmm_toy_vi'), load('api_misc_gmm')
+    npr.seed(1)
+    model = make_gmm(g)
+    npr.seed(17)
+    model.meanfield_coordinate_descent(g['obs'], maxiter=3, tol=0., progress_bar=False)
+    assert np.array_equal(model.used_labels(g['obs']), r['used_labels'])
+    close(model.components.log_marginal_likelihood(), r['lml'], 10 * tol, 'log marginal likelihood')
+    for got, n in zip(model.components.posterior_predictive_studentt(), ('mus', 'lmbdas', 'dfs')):
+        close(got, r['pst_' + n], 10 * tol, 'Student-t predictive ' + n)
+    close(model.expected_responsibilities(g['obs']), r['resp'], 50 * tol, 'responsibilities')
+    npr.seed(18)
+    model.meanfield_update_gating(r['resp'])
+    close(model.gating.posterior.alphas, r['gate_alphas'], 10 * tol, 'meanfield_update_gating')
+    assert abs(model.gating.likelihood.probs.sum() - 1.) < 1e-12            # a drawn probability vector (bayesian.py:83)
+    npr.seed(19)
+    model.meanfield_update_components(g['obs'], r['resp'])
+    for got, n in zip(model.components.posterior.params, ('mus', 'kappas', 'psis', 'nus')):
+        close(got, r['post_' + n], 10 * tol, 'meanfield_update_components ' + n)
+    # ILR
+    g, r = load('ilr_stacked'), load('api_misc_ilr')
+    npr.seed(2)
+    ilr = make_ilr(g)
+    npr.seed(27)
+    ilr.meanfield_coordinate_descent(g['x'], g['y'], maxiter=3, tol=0., progress_bar=False)
+    assert np.array_equal(ilr.used_labels(g['x'], g['y']), r['used_labels'])
+    close(ilr.meanfield_predictive_activation(g['x'][:40]), r['activation'], 50 * tol, 'predictive activation')
+    if precision == 'fp64':                     # seeded draws: the posteriors must match to the last digits for the chain to
+        npr.seed(28)
+        ilr.resample_basis(g['x'], r['z'])
+        close(ilr.basis.likelihood.mus, r['b_lik_mus'], 1e-7, 'resample_basis: means')
+        close(ilr.basis.likelihood.lmbdas, r['b_lik_lmbdas'], 1e-7, 'resample_basis: precisions')
+        npr.seed(29)
+        ilr.resample_models(g['x'], g['y'], r['z'])
+        close(ilr.models.likelihood.As, r['m_lik_As'], 1e-7, 'resample_models: regression matrices')
+        close(ilr.models.likelihood.lmbdas, r['m_lik_lmbdas'], 1e-7, 'resample_models: precisions')
