@@ -8,7 +8,7 @@ import numpy.random as npr
 
 from .. import _engine as E
 from ..utils.abstraction import Statistics as Stats
-from .gaussian import _clean_rows, soft_stats_quad, LOG_2PI
+from .gaussian import _clean_rows, soft_stats_quad
 
 
 class ExpertLayout:

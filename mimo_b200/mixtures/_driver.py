@@ -16,7 +16,7 @@ import numpy.random as npr
 import torch
 
 from .. import _engine as E
-from ..distributions.bayesian import MEANFIELD, GIBBS, MAP
+from ..distributions.bayesian import MEANFIELD, GIBBS
 
 
 class Part:

@@ -1,7 +1,6 @@
 """Hierarchical mixtures of Gaussians (mimo/mixtures/hgmm.py, distributions/bayesian.py:595-793) on the
 GPU against fixtures made from the unmodified reference (oracle/make_golden.py hier): seeded constructors, mean-field
 trajectories, a Gibbs chain, natural-gradient steps, a mixture of mixtures.  Tolerances: 1e-8 in FP64 mode, 2e-4 FP32."""
-import os
 
 import numpy as np
 import numpy.random as npr

@@ -4,7 +4,6 @@ import os
 
 import numpy as np
 import numpy.random as npr
-import pytest
 
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 
