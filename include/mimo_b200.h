@@ -159,7 +159,9 @@ int mimo_loglik_diag_tc(const void* Z, int64_t N, int D, int64_t ldz, const void
 int mimo_tc_diag_enable(int on);            /* A/B: 0 keeps diagonal sweeps on the CUDA cores; returns the old setting */
 /* One-shot hint for the NEXT mimo_sweep / mimo_sweep_timed of the calling thread: max |Z| over the data it will be given
  * (>= the true maximum).  The tensor-core paths then skip their own pass over Z for the common power-of-two data scale
- * -- for callers that keep the data resident and unchanged across sweeps (the Python Session does). */
+ * -- for callers that keep the data resident and unchanged across sweeps (the Python Session does).  The hint is consumed
+ * by that sweep whichever kernels it runs (a sweep that stays on the CUDA cores discards it) and is never seen by the
+ * stand-alone entry points. */
 int mimo_sweep_absmax_hint(double absmax);
 /* One-shot promise for the NEXT mimo_sweep of the calling thread: the (fi, fj) tables are (1) / are not (0) the canonical
  * packed triangle f = i (i + 1) / 2 + j.  Without it a soft quad-family sweep reads the tables back once to decide whether
