@@ -935,7 +935,7 @@ def main():
 
     cpu = None
     if not args.no_cpu and world == 1:
-        cpu, _ = time_cpu(w, name, 1, 1 if CPU_SAMPLE[name] * K < 5e6 else 0)
+        cpu, _ = time_cpu(w, name, 3, 1 if CPU_SAMPLE[name] * K < 5e6 else 0)      # ~10-20 s of host work on the bounded sample
     line = dict(metric='points*components/s per full sweep', value=value, unit='points*components/s', n_gpus=world,
                 steps=args.steps, warmup=warmup, ms_per_step=ms, higher_is_better=True, scaling='strong',
                 vs_baseline=None, dtype='f32', data='synthetic', config=config, roofline=roof, cpu_baseline=cpu, e2e=e2e,
